@@ -1,0 +1,256 @@
+"""ctypes binding of oracle/flashe_oracle.c — TEST INFRASTRUCTURE, NOT PRODUCT.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  See the header of flashe_oracle.c for the parity status ("pinned by FIPS-197 C.3 and
+by tests/golden/flashe_golden.npz, which holds outputs of the reference's own Python code").
+
+Word layout (same as the device library): int_bits <= 32 -> uint32, <= 64 -> uint64,
+<= 128 -> uint64 pairs (lo, hi), shape [L, 2].
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libflashe_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    """Compile the C restatement with gcc (no GPU, no reference needed)."""
+    src = os.path.join(_HERE, "flashe_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        u8p, i32p, vp, u64, u32, i32 = (C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.c_void_p,
+                                        C.c_uint64, C.c_uint32, C.c_int)
+        L.fo_aes256_expand.argtypes = [u8p, u8p]
+        L.fo_aes256_encrypt_block.argtypes = [u8p, u8p, u8p]
+        L.fo_reduce_key.argtypes = [u8p, C.c_size_t, u8p]
+        L.fo_chunk_bounds.argtypes = [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]
+        L.fo_masks.argtypes = [u8p, i32, u32, u32, i32p, i32p, i32, u64, u64, u64, vp]
+        L.fo_apply_masks.argtypes = [u8p, i32, u32, u32, i32p, i32p, i32, u64, u64, u64, vp, vp]
+        L.fo_collapse_runs.argtypes = [i32p, i32, i32p, i32p]
+        L.fo_aggregate_elementwise.argtypes = [i32, i32, u64, u64, vp, vp]
+        L.fo_aggregate_packed.argtypes = [i32, i32, u64, u64, vp, vp, u32, C.POINTER(u32)]
+        L.fo_quantize.argtypes = [vp, vp, u64, C.c_double, i32, vp]
+        L.fo_unquantize.argtypes = [vp, u64, i32, C.c_double, i32, i32, vp]
+        L.fo_batch.argtypes = [vp, u64, i32, i32, i32, vp]
+        L.fo_unbatch.argtypes = [vp, u64, i32, i32, i32, vp]
+        L.fo_expand_to_dense.argtypes = [i32, vp, vp, u64, u64, vp, vp]
+        L.fo_sparse_stream_accumulate.argtypes = [u8p, i32, u32, u32, C.c_int32, C.c_int32, vp, u64, u64, vp]
+        L.fo_dynamic_masking.argtypes = [C.POINTER(vp), C.POINTER(u64), i32, C.POINTER(u64), C.POINTER(u64)]
+        L.fo_set_threads.argtypes = [i32]
+        for f in ("fo_masks", "fo_apply_masks", "fo_collapse_runs", "fo_aggregate_elementwise",
+                  "fo_aggregate_packed", "fo_quantize", "fo_unquantize", "fo_batch", "fo_unbatch",
+                  "fo_expand_to_dense", "fo_sparse_stream_accumulate", "fo_dynamic_masking",
+                  "fo_num_threads", "fo_word_bytes"):
+            getattr(L, f).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def set_threads(n):
+    lib().fo_set_threads(int(n))
+
+
+# ----------------------------------------------------------------------------- word helpers
+def word_bytes(int_bits):
+    return 4 if int_bits <= 32 else (8 if int_bits <= 64 else 16)
+
+
+def empty_words(n, int_bits):
+    wb = word_bytes(int_bits)
+    if wb == 4:
+        return np.empty(n, dtype=np.uint32)
+    if wb == 8:
+        return np.empty(n, dtype=np.uint64)
+    return np.empty((n, 2), dtype=np.uint64)
+
+
+def to_words(values, int_bits):
+    """Sequence of Python ints (< 2^int_bits) -> word array."""
+    wb = word_bytes(int_bits)
+    if wb == 4:
+        return np.array([int(v) for v in values], dtype=np.uint32)
+    if wb == 8:
+        return np.array([int(v) for v in values], dtype=np.uint64)
+    m = (1 << 64) - 1
+    out = np.empty((len(values), 2), dtype=np.uint64)
+    out[:, 0] = [int(v) & m for v in values]
+    out[:, 1] = [int(v) >> 64 for v in values]
+    return out
+
+
+def from_words(arr, int_bits):
+    """Word array -> list of Python ints."""
+    if word_bytes(int_bits) == 16:
+        return [int(lo) | (int(hi) << 64) for lo, hi in arr]
+    return [int(v) for v in arr]
+
+
+def _key(key):
+    key = bytes(key)
+    out = (C.c_uint8 * 32)()
+    lib().fo_reduce_key((C.c_uint8 * len(key)).from_buffer_copy(key), len(key), out)
+    return out
+
+
+def _i32(xs):
+    return (C.c_int32 * max(1, len(xs)))(*[int(x) for x in xs])
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise ValueError("oracle %s failed (rc=%d)" % (what, rc))
+
+
+# ----------------------------------------------------------------------------- primitives
+def aes256_encrypt_block(key, block):
+    rk = (C.c_uint8 * 240)()
+    out = (C.c_uint8 * 16)()
+    lib().fo_aes256_expand(_key(key), rk)
+    lib().fo_aes256_encrypt_block(rk, (C.c_uint8 * 16).from_buffer_copy(bytes(block)), out)
+    return bytes(out)
+
+
+def chunk_bounds(L, n_jobs, i):
+    b, e = C.c_uint64(), C.c_uint64()
+    lib().fo_chunk_bounds(L, n_jobs, i, C.byref(b), C.byref(e))
+    return b.value, e.value
+
+
+def masks(key, int_bits, n_jobs, it, prf_idx, sign, L, j0=0, cnt=None):
+    """sum_k sign[k]*F(it, prf_idx[k])[j] mod 2^b for j in [j0, j0+cnt)."""
+    cnt = L - j0 if cnt is None else cnt
+    out = empty_words(cnt, int_bits)
+    _check(lib().fo_masks(_key(key), int_bits, n_jobs, it & 0xFFFFFFFF, _i32(prf_idx), _i32(sign),
+                          len(prf_idx), L, j0, cnt, _ptr(out)), "masks")
+    return out
+
+
+def apply_masks(key, int_bits, n_jobs, it, prf_idx, sign, words, L=None, j0=0):
+    words = np.ascontiguousarray(words)
+    cnt = words.shape[0]
+    L = cnt if L is None else L
+    out = np.empty_like(words)
+    _check(lib().fo_apply_masks(_key(key), int_bits, n_jobs, it & 0xFFFFFFFF, _i32(prf_idx),
+                                _i32(sign), len(prf_idx), L, j0, cnt, _ptr(words), _ptr(out)), "apply")
+    return out
+
+
+def encrypt(key, int_bits, n_jobs, it, idx, scheme, q_words, L=None, j0=0):
+    """FlasheCipher.encrypt (jzf_flashe.py:490-504)."""
+    if scheme == "double":
+        return apply_masks(key, int_bits, n_jobs, it, [idx, idx + 1], [1, -1], q_words, L, j0)
+    return apply_masks(key, int_bits, n_jobs, it, [idx], [1], q_words, L, j0)
+
+
+def collapse_runs(survivors):
+    n = len(survivors)
+    add, minus = (C.c_int32 * max(1, n))(), (C.c_int32 * max(1, n))()
+    r = lib().fo_collapse_runs(_i32(survivors), n, add, minus)
+    return list(add[:r]), list(minus[:r])
+
+
+def decrypt(key, int_bits, n_jobs, it, survivors, scheme, agg_words, L=None, j0=0):
+    """set_idx_list(mode='decrypt') + FlasheCipher.decrypt (jzf_flashe.py:306-314, 354-386, 506-594)."""
+    if scheme == "double":
+        add, minus = collapse_runs(survivors)
+        idx = add + minus
+        sign = [1] * len(add) + [-1] * len(minus)
+    else:
+        idx = list(survivors)
+        sign = [-1] * len(idx)
+    return apply_masks(key, int_bits, n_jobs, it, idx, sign, agg_words, L, j0)
+
+
+def aggregate(int_bits, cts, mode="elementwise", carry_in=0, return_carry=False):
+    """cts: array [n, L] (+[,2] for wide words).  mode 'elementwise' (B) or 'packed' (A)."""
+    cts = np.ascontiguousarray(cts)
+    n, L = cts.shape[0], cts.shape[1]
+    out = np.empty_like(cts[0])
+    if mode == "elementwise":
+        _check(lib().fo_aggregate_elementwise(int_bits, n, L, L, _ptr(cts), _ptr(out)), "aggregate")
+        return out
+    co = C.c_uint32()
+    _check(lib().fo_aggregate_packed(int_bits, n, L, L, _ptr(cts), _ptr(out), carry_in, C.byref(co)),
+           "aggregate_packed")
+    return (out, co.value) if return_carry else out
+
+
+def quantize(x, u, alpha, element_bits=16):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    q = np.empty(x.shape[0], dtype=np.uint32)
+    _check(lib().fo_quantize(_ptr(x), _ptr(u), x.shape[0], float(alpha), element_bits, _ptr(q)), "quantize")
+    return q
+
+
+def unquantize(v, alpha, element_bits, n_clients):
+    v = np.ascontiguousarray(v)
+    assert v.dtype in (np.uint32, np.uint64)
+    out = np.empty(v.shape[0], dtype=np.float64)
+    _check(lib().fo_unquantize(_ptr(v), v.shape[0], v.dtype.itemsize, float(alpha), element_bits,
+                               n_clients, _ptr(out)), "unquantize")
+    return out
+
+
+def batch(q, int_bits, element_bits, factor):
+    q = np.ascontiguousarray(q, dtype=np.uint32)
+    bs = int_bits // (element_bits + factor)
+    nw = (q.shape[0] + bs - 1) // bs
+    out = empty_words(nw, int_bits)
+    _check(lib().fo_batch(_ptr(q), q.shape[0], int_bits, element_bits, factor, _ptr(out)), "batch")
+    return out
+
+
+def unbatch(words, int_bits, element_bits, factor):
+    words = np.ascontiguousarray(words)
+    bs = int_bits // (element_bits + factor)
+    out = np.empty(words.shape[0] * bs, dtype=np.uint32)
+    _check(lib().fo_unbatch(_ptr(words), words.shape[0], int_bits, element_bits, factor, _ptr(out)), "unbatch")
+    return out
+
+
+def expand_to_dense(int_bits, compact, index, total, zero):
+    compact = np.ascontiguousarray(compact)
+    index = np.ascontiguousarray(index, dtype=np.int64)
+    dense = empty_words(total, int_bits)
+    z = to_words([zero], int_bits)
+    _check(lib().fo_expand_to_dense(int_bits, _ptr(compact), _ptr(index), index.shape[0], total,
+                                    _ptr(z), _ptr(dense)), "expand")
+    return dense
+
+
+def sparse_single_decrypt(key, int_bits, n_jobs, it, index_lists, total, agg_words):
+    """jzf_flashe.py:315-343 + 528-535: subtract every client's scattered compact stream."""
+    acc = np.ascontiguousarray(agg_words).copy()
+    for c, index in enumerate(index_lists):
+        index = np.ascontiguousarray(index, dtype=np.int64)
+        _check(lib().fo_sparse_stream_accumulate(_key(key), int_bits, n_jobs, it & 0xFFFFFFFF, c, -1,
+                                                 _ptr(index), index.shape[0], total, _ptr(acc)), "sparse")
+    return acc
+
+
+def dynamic_masking(index_lists):
+    n = len(index_lists)
+    arrs = [np.ascontiguousarray(ix, dtype=np.int64) for ix in index_lists]
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    ks = (C.c_uint64 * n)(*[a.shape[0] for a in arrs])
+    sc, dc = C.c_uint64(), C.c_uint64()
+    r = lib().fo_dynamic_masking(ptrs, ks, n, C.byref(sc), C.byref(dc))
+    return ("single" if r == 0 else "double"), sc.value, dc.value

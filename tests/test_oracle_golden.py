@@ -1,0 +1,185 @@
+"""The CPU oracle against the committed outputs of the reference's own Python code
+(tests/golden/flashe_golden.npz, made by tests/golden/make_golden.py) and FIPS-197 C.3."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def test_aes256_fips197_c3():
+    key = bytes(range(32))
+    pt = bytes.fromhex("00112233445566778899aabbccddeeff")
+    assert O.aes256_encrypt_block(key, pt).hex() == "8ea2b7ca516745bfeafc49904b496089"
+
+
+def test_key_reduction_matches_reference_rule():
+    # jzf_flashe.py:285-292 left-pads the seed to 256 BYTES; jzf_aes.py:21-28 keeps the low 32.
+    key = bytes(range(32))
+    pt = bytes(16)
+    assert O.aes256_encrypt_block(bytes(224) + key, pt) == O.aes256_encrypt_block(key, pt)
+    assert O.aes256_encrypt_block(b"\x01", pt) == O.aes256_encrypt_block(bytes(31) + b"\x01", pt)
+
+
+def test_chunk_bounds_cover():
+    for L in (0, 1, 3, 8, 1000, 1003):
+        for n in (1, 3, 8, 16):
+            prev = 0
+            for i in range(n):
+                b, e = O.chunk_bounds(L, n, i)
+                assert b == prev and e >= b
+                prev = e
+            assert prev == L
+
+
+def test_masks(golden):
+    for c in golden.cases("masks"):
+        b = c["int_bits"]
+        got = O.masks(golden.key, b, c["n_jobs"], c["iter"], [c["prf_idx"]], [1], c["L"])
+        assert np.array_equal(got, golden.words(c["name"], b)), c
+        # a sub-range must agree with the full vector (shards)
+        if c["L"] > 10:
+            j0, cnt = c["L"] // 3, c["L"] // 2
+            sub = O.masks(golden.key, b, c["n_jobs"], c["iter"], [c["prf_idx"]], [1], c["L"], j0, cnt)
+            assert np.array_equal(sub, got[j0:j0 + cnt])
+
+
+def test_threads_do_not_change_results(golden):
+    c = golden.cases("masks")[6]
+    O.set_threads(5)
+    try:
+        got = O.masks(golden.key, c["int_bits"], c["n_jobs"], c["iter"], [c["prf_idx"]], [1], c["L"])
+    finally:
+        O.set_threads(1)
+    assert np.array_equal(got, golden.words(c["name"], c["int_bits"]))
+
+
+def test_roundtrip(golden):
+    for c in golden.cases("roundtrip"):
+        name, b, nj, L, n, it, scheme = (c[k] for k in ("name", "int_bits", "n_jobs", "L", "n_clients", "iter", "scheme"))
+        xs, us = golden[name + "_x"], golden[name + "_u"]
+        q_ref = golden.words(name + "_q", 32).reshape(n, L)
+        ct_ref = golden.words(name + "_ct", b).reshape(n, L)
+        cts = []
+        for k in range(n):
+            q = O.quantize(xs[k], us[k], c["alpha"], c["element_bits"])
+            assert np.array_equal(q, q_ref[k]), (name, k)
+            ct = O.encrypt(golden.key, b, nj, it, k, scheme, q.astype(ct_ref.dtype))
+            assert np.array_equal(ct, ct_ref[k]), (name, k)
+            cts.append(ct)
+        cts = np.stack(cts)
+        agg_b = O.aggregate(b, cts, "elementwise")
+        agg_a = O.aggregate(b, cts, "packed")
+        assert np.array_equal(agg_b, golden.words(name + "_aggB", b))
+        assert np.array_equal(agg_a, golden.words(name + "_aggA", b))
+        dec_b = O.decrypt(golden.key, b, nj, it, list(range(n)), scheme, agg_b)
+        dec_a = O.decrypt(golden.key, b, nj, it, list(range(n)), scheme, agg_a)
+        assert np.array_equal(dec_b, golden.words(name + "_decB", b))
+        assert np.array_equal(dec_a, golden.words(name + "_decA", b))
+        out = O.unquantize(dec_b, c["alpha"], c["element_bits"], n)
+        assert np.array_equal(out.view(np.uint64), golden[name + "_decoded"].view(np.uint64))
+
+
+def test_packed_aggregate_differs_from_elementwise(golden):
+    c = golden.cases("roundtrip")[0]
+    a = golden.words(c["name"] + "_aggA", c["int_bits"])
+    b = golden.words(c["name"] + "_aggB", c["int_bits"])
+    assert (a != b).sum() > len(a) // 2     # the carry leak of SURVEY §0.4 is real and reproduced
+
+
+def test_dropout(golden):
+    cases = golden.cases("dropout")
+    c0 = cases[0]
+    b, nj, L, n, it = (c0[k] for k in ("int_bits", "n_jobs", "L", "n_clients", "iter"))
+    ct = golden.words("drop_ct", b).reshape(n, L)
+    q = golden.words("drop_q", 32).reshape(n, L)
+    for c in cases:
+        add, minus = O.collapse_runs(c["survivors"])
+        assert add == c["add"] and minus == c["minus"], c
+        agg = O.aggregate(b, ct[sorted(c["survivors"])], "elementwise")
+        assert np.array_equal(agg, golden.words(c["name"] + "_agg", b))
+        dec = O.decrypt(golden.key, b, nj, it, c["survivors"], "double", agg)
+        assert np.array_equal(dec, golden.words(c["name"] + "_dec", b))
+        assert np.array_equal(dec, q[sorted(c["survivors"])].sum(axis=0).astype(np.uint32))
+
+
+def test_runs(golden):
+    for row in golden.cases("runs")[0]["rows"]:
+        add, minus = O.collapse_runs(row["survivors"])
+        assert add == row["add"] and minus == row["minus"], row
+
+
+def test_precompute_buffers(golden):
+    c = golden.cases("precompute")[0]
+    b, nj, L, n, it, idx = (c[k] for k in ("int_bits", "n_jobs", "L", "n_clients", "iter", "idx"))
+    add = O.masks(golden.key, b, nj, it, [idx], [1], L)
+    minus = O.masks(golden.key, b, nj, it, [idx + 1], [1], L)
+    assert np.array_equal(add, golden.words("pre_enc_add", b))
+    assert np.array_equal(minus, golden.words("pre_enc_minus", b))
+    q = golden.words("pre_q", 32)
+    assert np.array_equal((q + add - minus) & ((1 << b) - 1), golden.words("pre_ct", b))
+    assert np.array_equal(O.encrypt(golden.key, b, nj, it, idx, "double", q), golden.words("pre_ct", b))
+    assert np.array_equal(O.masks(golden.key, b, nj, it, [n], [1], L), golden.words("pre_dec_add", b))
+    assert np.array_equal(O.masks(golden.key, b, nj, it, [0], [1], L), golden.words("pre_dec_minus", b))
+
+
+def test_sparse_single(golden):
+    c = golden.cases("sparse")[0]
+    b, nj, n, it, total = (c[k] for k in ("int_bits", "n_jobs", "n_clients", "iter", "total"))
+    idx = [golden["sparse_mask_%d" % k] for k in range(n)]
+    dense = []
+    for k in range(n):
+        q = golden.words("sparse_q_%d" % k, 32)
+        ct = O.encrypt(golden.key, b, nj, it, k, "single", q)
+        assert np.array_equal(ct, golden.words("sparse_ct_%d" % k, b))
+        dense.append(O.expand_to_dense(b, ct, idx[k], total, int(golden["sparse_zero"][k])))
+    agg = O.aggregate(b, np.stack(dense), "elementwise")
+    assert np.array_equal(agg, golden.words("sparse_agg", b))
+    dec = O.sparse_single_decrypt(golden.key, b, nj, it, idx, total, agg)
+    assert np.array_equal(dec, golden.words("sparse_dec", b))
+
+
+def test_batch120(golden):
+    c = golden.cases("batch")[0]
+    b, nj, L, n, it, e, f = (c[k] for k in ("int_bits", "n_jobs", "L", "n_clients", "iter", "element_bits", "factor"))
+    nw = c["words"]
+    q_ref = golden.words("batch_q", 32).reshape(n, L)
+    w_ref = golden.words("batch_w", b).reshape(n, nw, 2)
+    ct_ref = golden.words("batch_ct", b).reshape(n, nw, 2)
+    cts = []
+    for k in range(n):
+        q = O.quantize(golden["batch_x"][k], golden["batch_u"][k], c["alpha"], e)
+        assert np.array_equal(q, q_ref[k])
+        w = O.batch(q, b, e, f)
+        assert np.array_equal(w, w_ref[k])
+        ct = O.encrypt(golden.key, b, nj, it, k, "double", w)
+        assert np.array_equal(ct, ct_ref[k])
+        cts.append(ct)
+    agg = O.aggregate(b, np.stack(cts), "elementwise")
+    assert np.array_equal(agg, golden.words("batch_agg", b))
+    dec = O.decrypt(golden.key, b, nj, it, list(range(n)), "double", agg)
+    assert np.array_equal(dec, golden.words("batch_dec", b))
+    unb = O.unbatch(dec, b, e, f)[:L]
+    assert np.array_equal(unb, golden.words("batch_unb", 32))
+    out = O.unquantize(unb, c["alpha"], e, n)
+    assert np.array_equal(out.view(np.uint64), golden["batch_decoded"].view(np.uint64))
+
+
+def test_quant_edges_and_decode(golden):
+    c = golden.cases("quant_edges")[0]
+    L = c["L"]
+    q_ref = golden.words("qe_q", 32).reshape(3, L)
+    for k, (alpha, e) in enumerate(zip(c["alphas"], c["element_bits"])):
+        q = O.quantize(golden["qe_x"], golden["qe_u"][k], alpha, e)
+        assert np.array_equal(q, q_ref[k]), k
+    d = golden.cases("decode")[0]
+    out = O.unquantize(golden.words("qd_v", 32), d["alpha"], d["element_bits"], d["n_clients"])
+    assert np.array_equal(out.view(np.uint64), golden["qd_out"].view(np.uint64))
+
+
+def test_dynamic_masking_cost_model():
+    # jzf_flashe_block.py:89-117
+    a, b, c = [0, 1, 2, 3], [2, 3, 4], [9]
+    choice, sc, dc = O.dynamic_masking([a, b, c])
+    assert sc == 16 and dc == 32 - 2 * 2 and choice == "single"
+    choice, sc, dc = O.dynamic_masking([a, a, a])
+    assert sc == 24 and dc == 48 - 2 * 8 and choice == "single"

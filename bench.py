@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — FLASHE hot path on N B200s: encode+encrypt (all clients) -> aggregate -> decrypt+decode.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
+    python bench.py --impl reference [--gpus N] ...                # reference CPU path (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...              # N > 1, one rank per GPU
+
+Metric (BASELINE.json): client-elements/s = n_clients * L / time of one full round, whole job over all
+N GPUs.  Workload = BASELINE config 5: L = 100M float32 elements, 64 clients, int_bits 32, double
+masking, element-range sharded across the N GPUs (strong scaling: total work fixed; no data-path
+collective — every element's mask depends only on (key, iter, client, index, L, n_jobs)).
+
+One "step" = one round over synthetic gradients resident in HBM.  `value` is device-timed (CUDA
+events on the launching stream, max over ranks); `e2e` is the same round through the public API with
+HOST buffers: pinned float32 gradients copied host->device and the decoded float64 aggregate copied
+device->host inside the timed region.  Inputs (25.6 GB at N=1) are far larger than L2 (126 MB), so no
+L2 flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "client_elements_per_sec_enc_agg_dec"
+UNIT = "client-elements/s"
+KEY = bytes(range(32))
+ALPHA = 5.938345 * 0.1          # ACIQ(16 bit) * sigma, sigma = 0.1
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--elements", type=int, default=100_000_000)
+    ap.add_argument("--clients", type=int, default=64)
+    ap.add_argument("--int-bits", type=int, default=32)
+    ap.add_argument("--n-jobs", type=int, default=0, help="reference N_JOBS baked into the ciphertext format (0 = cpu_count())")
+    ap.add_argument("--share-streams", type=int, default=0, help="compute F(t,c+1) once for clients c and c+1")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-elements", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample-clients", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_round(elements, clients, int_bits, threads):
+    """One bounded round of the reference's CPU path (oracle/flashe_port.py): returns (seconds, phases)."""
+    import numpy as np
+    from oracle import flashe_port as P
+    xs = [(np.random.RandomState(1000 + c).standard_normal(elements) * 0.1).astype(np.float32) for c in range(clients)]
+    np.random.seed(2000)
+    phases = {}
+    t0 = time.perf_counter()
+    P.run_round(KEY, int_bits, 0, xs, float(ALPHA), 16, n_jobs=threads, timings=phases)
+    return time.perf_counter() - t0, phases
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (Python port, Pool over all
+    host cores, as jzf_flashe.py does), each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    elements = min(args.cpu_sample_elements, args.elements)
+    clients = min(args.cpu_sample_clients, args.clients)
+    for _ in range(args.warmup):
+        cpu_round(min(elements, 50_000), clients, args.int_bits, cores)
+    times, phases = [], {}
+    for _ in range(args.steps):
+        dt, phases = cpu_round(elements, clients, args.int_bits, cores)
+        times.append(dt)
+    total = sum(times)
+    value = clients * elements * len(times) / total
+    sample = "%d clients x %d elements per step (slice of the %d x %d workload), N_JOBS=%d" % (
+        clients, elements, args.clients, args.elements, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args, cores),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "phases_s_last_step": phases},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_jobs):
+    return {"workload": "BASELINE config 5: %dM-element float32 gradient, %d clients, encode+encrypt -> aggregate(element-wise) "
+                        "-> decrypt+decode, element-range sharded over the GPUs" % (args.elements // 1_000_000, args.clients),
+            "elements": args.elements, "clients": args.clients, "int_bits": args.int_bits, "element_bits": 16,
+            "masking": "double", "n_jobs": n_jobs, "prf": "AES-256-ECB on the fly (no precomputed masks)",
+            "share_streams": bool(args.share_streams), "noise": "device Philox4x32-10, res53",
+            "l2": "inputs (%.1f GB per round) exceed L2; no flush needed" % (args.elements * args.clients * 4 / 1e9)}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import flashe_b200 as fb
+    from flashe_b200.device import launch_count
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    L, n, bits = args.elements, args.clients, args.int_bits
+    n_jobs = args.n_jobs or (os.cpu_count() or 1)
+    # element-range shard of this rank, cut at multiples of 4 elements (16-byte aligned rows)
+    per = (L // world) // 4 * 4
+    begin = rank * per
+    count = per if rank + 1 < world else L - begin
+    span = fb.VectorSpan(L, n_jobs, begin, count)
+    ctx = fb.DeviceContext(KEY, bits, dev)
+    codec = fb.CodecSpec(alpha=float(ALPHA), element_bits=16, n_clients=n)
+    noise = fb.NoiseSpec(seed=0x5EED, stream=0)
+    scheme = fb.SCHEME_DOUBLE
+
+    # synthetic gradients N(0, 0.1^2), generated on the device
+    x = torch.empty((n, count), dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev)
+    for c in range(n):
+        g.manual_seed(1000 + c + 7919 * rank)
+        x[c].normal_(0.0, 0.1, generator=g)
+    cts = ctx.empty_words(count, rows=n)
+    agg = ctx.empty_words(count)
+    out = torch.empty(count, dtype=torch.float64, device=dev)
+
+    def round_device(ev=None):
+        if ev:
+            ev[0].record()
+        ctx.encode_encrypt_batch(0, 0, scheme, x, codec, noise, span, out=cts, share_streams=bool(args.share_streams))
+        if ev:
+            ev[1].record()
+        ctx.aggregate(cts, fb.AGG_ELEMENTWISE, out=agg)
+        if ev:
+            ev[2].record()
+        ctx.decrypt_decode(0, [n], [0], agg, codec, span, out=out)
+        if ev:
+            ev[3].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        round_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    l0 = launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for s in range(args.steps):
+        round_device(evs[s])
+    stop.record()
+    barrier()
+    launches = launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = start.elapsed_time(stop)
+    ph = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i in range(3)]
+    t = torch.tensor([ms_total] + ph, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ph = float(t[0]), [float(v) for v in t[1:]]
+    ms_step = ms_total / args.steps
+    value = n * L / (ms_step * 1e-3)
+
+    # ---------------------------------------------------------------- end to end (host buffers)
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, ctx, fb, span, codec, noise, scheme, x, cts, agg, out, world, dev, barrier)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src = peaks()
+    enc_bytes = n * count * 8                    # 4 B float in + 4 B ciphertext out per client-element
+    enc_gbs = enc_bytes / (ph[0] * 1e-3) / 1e9
+    m = 128 // bits
+    blocks = (n + 1 if args.share_streams else 2 * n) * (count / m)
+    blocks_per_s = blocks / (ph[0] * 1e-3)
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    # LDS ceiling of the T-table PRF: 212 conflict-free 4-byte lookups per block, 32 per clock per SM
+    lds_peak_blocks = 148 * sm_mhz * 1e6 * 32 / 212.0
+    agg_bytes = (n + 1) * count * 4
+    dec_bytes = count * 12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32" if bits <= 32 else ("u64" if bits <= 64 else "u128"), "data": "synthetic",
+        "config": workload_config(args, n_jobs),
+        "clocks": clocks,
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_stream<1,6,M_ENCODE> (fused encode + AES-256 PRF masks + modular add)",
+                     "achieved": enc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": enc_gbs / hbm_peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": enc_bytes, "ms_per_launch": ph[0],
+                     "note": "this kernel is bound by the PRF (shared-memory table lookups), not HBM: see roofline_prf"},
+        "roofline_prf": {"bound": "lds", "achieved": blocks_per_s / 1e9, "peak": lds_peak_blocks / 1e9, "unit": "G AES-256 blocks/s",
+                         "frac": blocks_per_s / lds_peak_blocks,
+                         "peak_source": "148 SMs x sampled SM clock x 32 conflict-free LDS/clk / 212 lookups per block"},
+        "phases": {"encode_encrypt_ms": ph[0], "aggregate_ms": ph[1], "decrypt_decode_ms": ph[2],
+                   "aggregate_gbs": agg_bytes / (ph[1] * 1e-3) / 1e9, "aggregate_frac_of_hbm": agg_bytes / (ph[1] * 1e-3) / 1e9 / hbm_peak,
+                   "decrypt_decode_gbs": dec_bytes / (ph[2] * 1e-3) / 1e9},
+        "hbm_roofline_client_elements_per_s": hbm_peak * 1e9 / (12.0 + 16.0 / n) * world,
+        "frac_of_hbm_roofline_end_to_end": value / (hbm_peak * 1e9 / (12.0 + 16.0 / n) * world),
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args, ctx, fb)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, ctx, fb, span, codec, noise, scheme, x, cts, agg, out, world, dev, barrier):
+    """The same round through the public API with HOST buffers: every step copies the float32
+    gradients from pinned host memory (client groups double-buffered against compute) and reads the
+    decoded float64 aggregate back."""
+    import torch
+    import torch.distributed as dist
+    n, count = x.shape
+    group = 8 if n % 8 == 0 else 1
+    host_x = torch.empty((n, count), dtype=torch.float32, pin_memory=True)
+    host_x.copy_(x)                               # synthetic gradients, now "on the host"
+    host_out = torch.empty(count, dtype=torch.float64, pin_memory=True)
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    stage = [torch.empty((group, count), dtype=torch.float32, device=dev) for _ in range(2)]
+    staged = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def round_host():
+        ngroups = n // group
+        for gi in range(ngroups):
+            b = gi & 1
+            with torch.cuda.stream(copy_stream):
+                if gi >= 2:
+                    copy_stream.wait_event(consumed[b])
+                stage[b].copy_(host_x[gi * group:(gi + 1) * group], non_blocking=True)
+                staged[b].record(copy_stream)
+            main.wait_event(staged[b])
+            ns = fb.NoiseSpec(seed=noise.seed, stream=gi * group)
+            ctx.encode_encrypt_batch(0, gi * group, scheme, stage[b], codec, ns, span,
+                                     out=cts[gi * group:(gi + 1) * group], share_streams=bool(args.share_streams))
+            consumed[b].record(main)
+        ctx.aggregate(cts, fb.AGG_ELEMENTWISE, out=agg)
+        ctx.decrypt_decode(0, [n], [0], agg, codec, span, out=out)
+        host_out.copy_(out, non_blocking=True)
+
+    round_host()
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.e2e_steps):
+        round_host()
+    stop.record()
+    barrier()
+    t = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / args.e2e_steps
+    return {"value": args.clients * args.elements / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "h2d_bytes_per_step": int(n * count * 4), "d2h_bytes_per_step": int(count * 8),
+            "api": "DeviceContext.encode_encrypt_batch/aggregate/decrypt_decode over the C ABI; pinned host float32 in, float64 out",
+            "steps": args.e2e_steps}
+
+
+def cpu_baseline(args, ctx, fb):
+    """Reference CPU path (oracle/flashe_port.py) on this box's host cores, bounded sample; plus a
+    bit-exactness spot check of the device path against the C oracle on whole reference chunks."""
+    import numpy as np
+    import torch
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    elements, clients = min(args.cpu_sample_elements, args.elements), min(args.cpu_sample_clients, args.clients)
+    dt, phases = cpu_round(elements, clients, 20, cores)
+    out = {"value": clients * elements / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "BASELINE config 1: %d clients x %d elements, int_bits 20, one round (encode, encrypt, aggregate, decrypt, decode), "
+                     "multiprocessing.Pool(%d) per call as jzf_flashe.py does" % (clients, elements, cores),
+           "seconds": dt, "phases_s": phases}
+    # spot check: 2 clients x 200k elements of the benchmark's own format against the oracle
+    bits, n_jobs, L = args.int_bits, args.n_jobs or cores, args.elements
+    j0, cnt = (L // 3) // 4 * 4, 200_000
+    span = fb.VectorSpan(L, n_jobs, j0, cnt)
+    xs = (np.random.RandomState(5).standard_normal((2, cnt)) * 0.1).astype(np.float32)
+    codec = fb.CodecSpec(alpha=float(ALPHA), element_bits=16, n_clients=2)
+    got = ctx.encode_encrypt_batch(0, 0, fb.SCHEME_DOUBLE, torch.from_numpy(xs).to(ctx.device), codec,
+                                   fb.NoiseSpec(seed=1, stream=0), span).cpu().numpy()
+    O.set_threads(min(cores, 32))
+    ok = True
+    for c in range(2):
+        u = ctx.rng_uniform(1, c, j0, cnt).cpu().numpy()
+        want = O.encrypt(KEY, bits, n_jobs, 0, c, "double", O.quantize(xs[c], u, float(ALPHA), 16).astype(got.dtype), L=L, j0=j0)
+        ok = ok and bool(np.array_equal(got[c], want))
+    out["device_vs_oracle_spot_check"] = "bit-exact" if ok else "MISMATCH"
+    return out
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,67 @@
+"""The arbiter's arithmetic for the FLASHE path (reference:
+federatedml/framework/homo/procedure/jzf_aggregator.py:150-165, 404-430 and
+jzf_flashe_block.py:89-117), on the GPU.  Messaging, retries and partitioning around it are FATE
+plumbing and out of scope.
+
+Arrays are 1-D numpy object arrays of Python ints (what the reference's JZFOrderDictWeights hold) or
+torch CUDA word tensors (flashe_b200.device layout); the latter stay on the device."""
+import numpy as np
+import torch
+
+from .device import AGG_ELEMENTWISE, AGG_PACKED, DeviceContext
+
+_ctx_cache = {}
+
+
+def _ctx(int_bits, device=None):
+    key = (int_bits, str(device))
+    if key not in _ctx_cache:
+        _ctx_cache[key] = DeviceContext(b"\x00", int_bits, device)   # the server holds no key
+    return _ctx_cache[key]
+
+
+def _stack(ctx, models):
+    if isinstance(models, torch.Tensor):
+        return models, True
+    if isinstance(models[0], torch.Tensor):
+        return torch.stack([m.view(torch.int64 if ctx.word_bytes > 4 else torch.int32) for m in models]), True
+    rows = [ctx.words_from_ints(m) for m in models]
+    return torch.stack([r.view(torch.int64 if ctx.word_bytes > 4 else torch.int32) for r in rows]), False
+
+
+def aggregate(models, int_bits, is_compressed=False, device=None):
+    """total = reduce(lambda x, y: (x + y) % mod, models) — jzf_aggregator.py:404-430.
+
+    is_compressed=False: element-wise mod 2^int_bits (the decompressed / sparse branch, :421-430).
+    is_compressed=True : the clients' packed wire integers are added mod 2^(int_bits*L) (:406-419);
+                         carries out of element j leak into element j-1 and are reproduced exactly.
+    `models`: list of n vectors (object arrays or device word tensors) or one [n, L] word tensor."""
+    ctx = _ctx(int_bits, device)
+    cts, on_device = _stack(ctx, models)
+    out = ctx.aggregate(cts, AGG_PACKED if is_compressed else AGG_ELEMENTWISE)
+    return out if on_device else ctx.ints_from_words(out)
+
+
+def expand_to_dense(models, masks, total, int_bits, device=None):
+    """jzf_aggregator.py:150-165: each upload is the compact ciphertext followed by that client's
+    plaintext quantised zero; scatter the compact part to `mask` and fill the rest with the zero."""
+    ctx = _ctx(int_bits, device)
+    out = []
+    for a, ma in zip(models, masks):
+        a = np.asarray(a, dtype=object)
+        zero, compact = int(a[-1]), a[:-1]
+        index = torch.as_tensor(np.asarray(ma, dtype=np.int64)).to(ctx.device)
+        dense = ctx.sparse_expand(ctx.words_from_ints(compact), index, int(total), zero)
+        out.append(ctx.ints_from_words(dense))
+    return out
+
+
+def dynamic_masking(masks, total, device=None):
+    """jzf_flashe_block.py:89-117: single = 2*sum|mask|; double = 2*single - 2*sum_i |mask_i ∩ mask_{i+1}|;
+    choose single when single <= double.  Returns the dict the arbiter broadcasts plus the costs."""
+    ctx = _ctx(32, device)
+    lists = [torch.as_tensor(np.asarray(m, dtype=np.int64)).to(ctx.device) for m in masks]
+    single_cost = 2 * sum(int(t.numel()) for t in lists)
+    double_cost = 2 * single_cost - 2 * sum(ctx.sparse_overlap(lists, int(total)))
+    choice = "single" if single_cost <= double_cost else "double"
+    return {"choice": choice, "masks": masks, "single_cost": single_cost, "double_cost": double_cost}

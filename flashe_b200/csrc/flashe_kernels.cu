@@ -1,0 +1,1537 @@
+// flashe_kernels.cu — B200 (sm_100a) kernels and C ABI of the FLASHE hot path.
+//
+// Path (SamuelGong/FLASHE, federatedml/secureprotol/jzf_flashe.py + jzf_quantize.py, and the server
+// sum of framework/homo/procedure/jzf_aggregator.py:404-430); see include/flashe_b200.h for the
+// per-entry-point citations and DESIGN.md for the layout/roofline discussion.
+//
+// Kernel families
+//   k_stream<WORDS, MMAX, MODE>   persistent, one CTA per SM, 1024 threads.  A warp owns a "warp
+//       item" = 32 consecutive AES blocks of one reference chunk (lane <-> block, so lane <-> m
+//       consecutive elements).  Lanes run AES-256 from a bank-conflict-free shared-memory T-table
+//       (4 tables x 32 replicas = 128 KB, one LDS + one PRMT per lookup), reduce the signed streams
+//       into a combined mask in registers, transpose it through a per-warp shared slab and then walk
+//       the item's elements with fully coalesced global loads/stores, fusing encode / decode.
+//   elementwise kernels           aggregate (element-wise and packed-carry), premasked add, encode,
+//       decode, lane batching, sparse expand, noise.
+//
+// No tensor cores: nothing here is a dense contraction (integer PRF + modular adds).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/flashe_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(FLASHE_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));        \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// host AES-256 (key schedule, T-table, round-1 hoisting).  FIPS-197; big-endian word convention:
+// word = b0<<24 | b1<<16 | b2<<8 | b3, so the reference's block iter(4B BE)||prf(4B BE)||ctr(8B BE)
+// (jzf_flashe.py:34,304,308) is simply the words {iter, prf, ctr>>32, ctr&0xffffffff}.
+// ------------------------------------------------------------------------------------------------
+namespace haes {
+static uint8_t sbox[256];
+static uint32_t te0[256];
+static bool ready = false;
+
+static uint8_t xtime(uint8_t a) { return (uint8_t)((a << 1) ^ ((a & 0x80) ? 0x1b : 0)); }
+static uint8_t mul(uint8_t a, uint8_t b) {
+    uint8_t p = 0;
+    while (b) { if (b & 1) p ^= a; a = xtime(a); b >>= 1; }
+    return p;
+}
+static void init() {
+    if (ready) return;
+    // multiplicative inverse via exponentiation tables on generator 3
+    uint8_t exp[256], log[256];
+    uint8_t x = 1;
+    for (int i = 0; i < 255; ++i) { exp[i] = x; log[x] = (uint8_t)i; x = (uint8_t)(x ^ xtime(x)); }
+    exp[255] = exp[0];
+    for (int v = 0; v < 256; ++v) {
+        uint8_t inv = v ? exp[(255 - log[v]) % 255] : 0;
+        uint8_t s = inv;
+        for (int i = 1; i < 5; ++i) s ^= (uint8_t)((inv << i) | (inv >> (8 - i)));
+        sbox[v] = s ^ 0x63;
+    }
+    for (int v = 0; v < 256; ++v) {
+        uint8_t s = sbox[v], s2 = xtime(s), s3 = (uint8_t)(s2 ^ s);
+        te0[v] = ((uint32_t)s2 << 24) | ((uint32_t)s << 16) | ((uint32_t)s << 8) | s3;
+    }
+    ready = true;
+}
+static inline uint32_t ror(uint32_t v, int n) { return n ? ((v >> n) | (v << (32 - n))) : v; }
+static inline uint32_t te(int t, uint32_t idx) { return ror(te0[idx & 0xff], 8 * t); }
+
+static void expand(const uint8_t key[32], uint32_t rk[60]) {
+    init();
+    for (int i = 0; i < 8; ++i)
+        rk[i] = ((uint32_t)key[4 * i] << 24) | ((uint32_t)key[4 * i + 1] << 16) | ((uint32_t)key[4 * i + 2] << 8) | key[4 * i + 3];
+    uint32_t rcon = 1;
+    for (int i = 8; i < 60; ++i) {
+        uint32_t t = rk[i - 1];
+        if (i % 8 == 0) {
+            t = (t << 8) | (t >> 24);
+            t = ((uint32_t)sbox[t >> 24] << 24) | ((uint32_t)sbox[(t >> 16) & 0xff] << 16) | ((uint32_t)sbox[(t >> 8) & 0xff] << 8) | sbox[t & 0xff];
+            t ^= rcon << 24;
+            rcon = mul((uint8_t)rcon, 2);
+        } else if (i % 8 == 4) {
+            t = ((uint32_t)sbox[t >> 24] << 24) | ((uint32_t)sbox[(t >> 16) & 0xff] << 16) | ((uint32_t)sbox[(t >> 8) & 0xff] << 8) | sbox[t & 0xff];
+        }
+        rk[i] = rk[i - 8] ^ t;
+    }
+}
+// Round-1 terms that do not depend on the low counter word (input words w0,w1,w2 fixed).
+static void hoist_round1(const uint32_t rk[60], uint32_t w0, uint32_t w1, uint32_t w2, uint32_t pre[4]) {
+    uint32_t s0 = w0 ^ rk[0], s1 = w1 ^ rk[1], s2 = w2 ^ rk[2];
+    pre[0] = te(0, s0 >> 24) ^ te(1, s1 >> 16) ^ te(2, s2 >> 8) ^ rk[4];
+    pre[1] = te(0, s1 >> 24) ^ te(1, s2 >> 16) ^ te(3, s0) ^ rk[5];
+    pre[2] = te(0, s2 >> 24) ^ te(2, s0 >> 8) ^ te(3, s1) ^ rk[6];
+    pre[3] = te(1, s0 >> 16) ^ te(2, s1 >> 8) ^ te(3, s2) ^ rk[7];
+}
+}  // namespace haes
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameter blocks (all in the constant bank)
+// ------------------------------------------------------------------------------------------------
+#define MAXS FLASHE_MAX_STREAMS
+#define MAX_INLINE_SEG 48
+#define STREAM_THREADS 512
+
+struct KeySched { uint32_t rk[60]; };
+
+struct StreamTab {
+    uint32_t n;           // entries
+    uint32_t iter;
+    uint32_t batch;       // 0: entries are the stream list of the single vector
+                          // 1: client c uses entry c (+) and, when dbl, entry c+1 (-)
+    uint32_t dbl;
+    uint32_t prf[MAXS];
+    int32_t sign[MAXS];
+    uint32_t pre[MAXS][4];
+};
+
+struct Geom {
+    uint64_t L, begin, end;  // whole length, shard [begin,end)
+    uint64_t d, r;           // divmod(L, n_jobs): first r chunks have d+1 elements
+    uint64_t nwA, nwB;       // warp items per chunk (types: d+1 / d elements)
+    uint64_t rA;             // r * nwA
+    uint64_t W_lo, W_cnt;    // warp items that intersect the shard
+    uint32_t m, b;           // slots per AES block, int_bits
+};
+
+struct Seg { uint64_t end; float a, two_a; double an, two_an; };
+
+struct CodecDev {
+    int32_t nseg;
+    int32_t ebits;
+    float scale;             // 2^e - 1 as float32
+    double den;              // (2^e - 1) * n as float64
+    const Seg* table;        // device table when nseg > MAX_INLINE_SEG, else NULL
+    Seg seg[MAX_INLINE_SEG];
+};
+
+struct NoiseDev { const double* u; uint64_t u_stride; uint32_t k0, k1; uint64_t stream; };
+
+struct IoDev {
+    const void* in;  uint64_t in_stride;    // words (or floats) between consecutive clients
+    void* out;       uint64_t out_stride;
+    void* aux;                              // q_out (encode) / p_out (decode) / index (scatter)
+    double* outf;
+    uint32_t n_clients;
+    uint32_t share;                         // batch double masking: compute each stream once
+};
+
+enum { M_MASKS = 0, M_APPLY = 1, M_ENCODE = 2, M_DECODE = 3, M_SCATTER = 4 };
+
+// ------------------------------------------------------------------------------------------------
+// device: shared-memory T-tables
+// Layout (absolute addresses in the CTA's shared window):
+//   [0x10000, 0x20000)  T0/T1 interleaved: entry e, table t, replica l at 0x10000 + e*256 + t*128 + l*4
+//   [0x20000, 0x30000)  T2/T3 likewise
+// Replica l is only ever read by lane l, so every lookup instruction hits 32 distinct banks.  The
+// address of a lookup is PRMT(state, y, sel) with y = 0x00010000 | lane*4: one ALU op builds
+// 0x0001_<byte>_<lane*4>, the table select rides in the LDS immediate.
+// Below 0x10000 (from wherever the driver starts dynamic shared memory) live the per-warp slabs.
+// ------------------------------------------------------------------------------------------------
+#define TAB_BASE 0x10000u
+#define SMEM_BYTES 0x30000u  // requested dynamic shared memory: covers [base, 0x30000) for base <= 0x10000
+
+__device__ uint32_t g_te0[256];  // filled once per process by flashe_ctx_create
+
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_tab(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t smem_window_base() {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    return (uint32_t)__cvta_generic_to_shared(dyn_smem);
+}
+
+__device__ __forceinline__ void fill_tables() {
+    // word w of the 128 KB region: region = w>>14, entry = (w>>6)&255, table-in-region = (w>>5)&1
+    for (uint32_t w = threadIdx.x; w < 32768u; w += blockDim.x) {
+        uint32_t t = ((w >> 14) << 1) | ((w >> 5) & 1u);
+        uint32_t v = g_te0[(w >> 6) & 255u];
+        v = __funnelshift_r(v, v, 8 * t);  // Te_t = ror(Te0, 8t)
+        sts32(TAB_BASE + 4u * w, v);
+    }
+}
+
+#define SEL_B3 0x7634
+#define SEL_B2 0x7624
+#define SEL_B1 0x7614
+#define SEL_B0 0x7604
+#define T0(s) lds_tab<0>(__byte_perm((s), y, SEL_B3))
+#define T1(s) lds_tab<128>(__byte_perm((s), y, SEL_B2))
+#define T2(s) lds_tab<0x10000>(__byte_perm((s), y, SEL_B1))
+#define T3(s) lds_tab<0x10080>(__byte_perm((s), y, SEL_B0))
+
+// AES-256 of the block {w0,w1,w2,w3}; `pre` = round-1 terms hoisted by the host for (w0,w1,w2=0).
+// Output o[0..3] big-endian words (o[0] most significant).
+struct Pre { uint32_t p0, p1, p2, p3; };
+__device__ __forceinline__ void aes256_block(const KeySched& ks, uint32_t y, uint32_t w0, uint32_t w1,
+                                             uint32_t w2, uint32_t w3, Pre pre, uint32_t o[4]) {
+    uint32_t s0, s1, s2, s3, t0, t1, t2, t3;
+    s3 = w3 ^ ks.rk[3];
+    if (w2 == 0) {
+        t0 = pre.p0 ^ T3(s3);
+        t1 = pre.p1 ^ T2(s3);
+        t2 = pre.p2 ^ T1(s3);
+        t3 = pre.p3 ^ T0(s3);
+    } else {
+        s0 = w0 ^ ks.rk[0]; s1 = w1 ^ ks.rk[1]; s2 = w2 ^ ks.rk[2];
+        t0 = T0(s0) ^ T1(s1) ^ T2(s2) ^ T3(s3) ^ ks.rk[4];
+        t1 = T0(s1) ^ T1(s2) ^ T2(s3) ^ T3(s0) ^ ks.rk[5];
+        t2 = T0(s2) ^ T1(s3) ^ T2(s0) ^ T3(s1) ^ ks.rk[6];
+        t3 = T0(s3) ^ T1(s0) ^ T2(s1) ^ T3(s2) ^ ks.rk[7];
+    }
+#pragma unroll
+    for (int r = 2; r < 14; r += 2) {
+        s0 = T0(t0) ^ T1(t1) ^ T2(t2) ^ T3(t3) ^ ks.rk[4 * r + 0];
+        s1 = T0(t1) ^ T1(t2) ^ T2(t3) ^ T3(t0) ^ ks.rk[4 * r + 1];
+        s2 = T0(t2) ^ T1(t3) ^ T2(t0) ^ T3(t1) ^ ks.rk[4 * r + 2];
+        s3 = T0(t3) ^ T1(t0) ^ T2(t1) ^ T3(t2) ^ ks.rk[4 * r + 3];
+        t0 = T0(s0) ^ T1(s1) ^ T2(s2) ^ T3(s3) ^ ks.rk[4 * r + 4];
+        t1 = T0(s1) ^ T1(s2) ^ T2(s3) ^ T3(s0) ^ ks.rk[4 * r + 5];
+        t2 = T0(s2) ^ T1(s3) ^ T2(s0) ^ T3(s1) ^ ks.rk[4 * r + 6];
+        t3 = T0(s3) ^ T1(s0) ^ T2(s1) ^ T3(s2) ^ ks.rk[4 * r + 7];
+    }
+    // t = state after round 13.  Final round: SubBytes + ShiftRows + AddRoundKey; the S-box byte is
+    // taken from the table whose entry carries S[x] in the wanted byte lane:
+    //   byte3 <- T2 (S<<24), byte2 <- T3 (S<<16), byte1 <- T0 (S<<8), byte0 <- T1 (S).
+#define LAST(a, b, c, d, k)                                                                         \
+    (__byte_perm(__byte_perm(lds_tab<128>(__byte_perm((d), y, SEL_B0)),                             \
+                             lds_tab<0>(__byte_perm((c), y, SEL_B1)), 0x3250),                      \
+                 __byte_perm(lds_tab<0x10080>(__byte_perm((b), y, SEL_B2)),                         \
+                             lds_tab<0x10000>(__byte_perm((a), y, SEL_B3)), 0x7210), 0x7610) ^ ks.rk[k])
+    o[0] = LAST(t0, t1, t2, t3, 56);
+    o[1] = LAST(t1, t2, t3, t0, 57);
+    o[2] = LAST(t2, t3, t0, t1, 58);
+    o[3] = LAST(t3, t0, t1, t2, 59);
+#undef LAST
+}
+
+// ------------------------------------------------------------------------------------------------
+// device: geometry of the reference's chunked counter rule (jzf_flashe.py:12-16, 24-34)
+// ------------------------------------------------------------------------------------------------
+struct Item { uint64_t cb; uint64_t clen; uint64_t i0; };  // chunk begin, chunk length, first block
+
+__device__ __forceinline__ Item decode_item(const Geom& g, uint64_t W) {
+    Item it;
+    if (W < g.rA) {
+        uint64_t k = W / g.nwA, w = W - k * g.nwA;
+        it.cb = k * (g.d + 1); it.clen = g.d + 1; it.i0 = w * 32;
+    } else {
+        uint64_t Wp = W - g.rA;
+        uint64_t k = Wp / g.nwB, w = Wp - k * g.nwB;
+        it.cb = g.r * (g.d + 1) + k * g.d; it.clen = g.d; it.i0 = w * 32;
+    }
+    return it;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device: encode / decode / noise
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ const Seg& find_seg(const CodecDev& c, uint64_t j) {
+    if (c.nseg == 1) return c.seg[0];
+    const Seg* tab = c.table ? c.table : c.seg;
+    int lo = 0, hi = c.nseg - 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (j < tab[mid].end) hi = mid; else lo = mid + 1;
+    }
+    return tab[lo];
+}
+
+// _static_quantize_padding_asymmetric, jzf_quantize.py:55-67: four float32 ops in the reference's
+// order (no FMA contraction), then float64 add of the noise, floor, int.
+__device__ __forceinline__ uint32_t encode_one(float x, double u, float a, float two_a, float scale) {
+    float v = fminf(fmaxf(x, -a), a);
+    v = __fadd_rn(v, a);
+    v = __fmul_rn(v, scale);
+    v = __fdiv_rn(v, two_a);
+    double r = floor(__dadd_rn((double)v, u));
+    return (uint32_t)(long long)r;
+}
+
+// _static_unquantize_padding_asymmetric, jzf_quantize.py:102-107 (float64, left to right).
+__device__ __forceinline__ double decode_one(double v, double two_an, double den, double an) {
+    return __dsub_rn(__ddiv_rn(__dmul_rn(v, two_an), den), an);
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter (c0,c1,c2,c3), key (k0,k1).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// u_j in [0,1): counter (j>>1 lo, j>>1 hi, stream lo, stream hi); words (2(j&1), 2(j&1)+1) feed numpy's
+// res53 construction ((a>>5)*2^26 + (b>>6)) / 2^53.
+__device__ __forceinline__ double noise_one(const NoiseDev& nz, uint64_t stream, uint64_t j) {
+    uint32_t o[4];
+    uint64_t c = j >> 1;
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), nz.k0, nz.k1, o);
+    uint32_t a = (j & 1) ? o[2] : o[0], b = (j & 1) ? o[3] : o[1];
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device: word arithmetic for the three storage widths
+// ------------------------------------------------------------------------------------------------
+template <int WORDS> struct Word;
+template <> struct Word<1> {
+    typedef uint32_t T;
+    static __host__ __device__ __forceinline__ T mask(uint32_t b) { return b >= 32 ? 0xffffffffu : ((1u << b) - 1u); }
+    static __host__ __device__ __forceinline__ T add(T a, T b) { return a + b; }
+    static __host__ __device__ __forceinline__ T sub(T a, T b) { return a - b; }
+    static __host__ __device__ __forceinline__ T band(T a, T m) { return a & m; }
+    static __host__ __device__ __forceinline__ T from_u32(uint32_t q) { return q; }
+    static __host__ __device__ __forceinline__ double to_double(T a) { return (double)a; }
+    static __host__ __device__ __forceinline__ T zero() { return 0u; }
+};
+template <> struct Word<2> {
+    typedef uint64_t T;
+    static __host__ __device__ __forceinline__ T mask(uint32_t b) { return b >= 64 ? ~0ull : ((1ull << b) - 1ull); }
+    static __host__ __device__ __forceinline__ T add(T a, T b) { return a + b; }
+    static __host__ __device__ __forceinline__ T sub(T a, T b) { return a - b; }
+    static __host__ __device__ __forceinline__ T band(T a, T m) { return a & m; }
+    static __host__ __device__ __forceinline__ T from_u32(uint32_t q) { return q; }
+    static __host__ __device__ __forceinline__ double to_double(T a) { return (double)a; }
+    static __host__ __device__ __forceinline__ T zero() { return 0ull; }
+};
+struct alignas(16) u128 { uint64_t lo, hi; };
+template <> struct Word<4> {
+    typedef u128 T;
+    static __host__ __device__ __forceinline__ T mask(uint32_t b) {
+        T m; m.lo = ~0ull; m.hi = b >= 128 ? ~0ull : ((1ull << (b - 64)) - 1ull); return m;
+    }
+    static __host__ __device__ __forceinline__ T add(T a, T b) { T r; r.lo = a.lo + b.lo; r.hi = a.hi + b.hi + (r.lo < a.lo); return r; }
+    static __host__ __device__ __forceinline__ T sub(T a, T b) { T r; r.lo = a.lo - b.lo; r.hi = a.hi - b.hi - (a.lo < b.lo); return r; }
+    static __host__ __device__ __forceinline__ T band(T a, T m) { T r; r.lo = a.lo & m.lo; r.hi = a.hi & m.hi; return r; }
+    static __host__ __device__ __forceinline__ T from_u32(uint32_t q) { T r; r.lo = q; r.hi = 0; return r; }
+    static __host__ __device__ __forceinline__ double to_double(T a) { return (double)a.lo; }
+    static __host__ __device__ __forceinline__ T zero() { T r; r.lo = 0; r.hi = 0; return r; }
+};
+
+// Slots of one AES output (jzf_flashe.py:37-43): s = big-endian 128-bit integer; slot k is
+// (s >> k*b) & mask.  acc[k] += sign * slot.
+template <int WORDS, int MMAX>
+__device__ __forceinline__ void accumulate_slots(const uint32_t o[4], uint32_t b, uint32_t m, int sign,
+                                                 typename Word<WORDS>::T (&acc)[MMAX]) {
+    if constexpr (WORDS == 1) {
+        uint32_t v0 = o[3], v1 = o[2], v2 = o[1], v3 = o[0];
+        const uint32_t mk = Word<1>::mask(b);
+#pragma unroll
+        for (int k = 0; k < MMAX; ++k) {
+            if ((uint32_t)k < m) {
+                acc[k] += (uint32_t)sign * (v0 & mk);
+                v0 = __funnelshift_rc(v0, v1, b);
+                v1 = __funnelshift_rc(v1, v2, b);
+                v2 = __funnelshift_rc(v2, v3, b);
+                v3 = __funnelshift_rc(v3, 0u, b);
+            }
+        }
+    } else if constexpr (WORDS == 2) {
+        uint64_t V0 = ((uint64_t)o[2] << 32) | o[3], V1 = ((uint64_t)o[0] << 32) | o[1];
+        const uint64_t mk = Word<2>::mask(b);
+#pragma unroll
+        for (int k = 0; k < MMAX; ++k) {
+            if ((uint32_t)k < m) {
+                const uint64_t slot = V0 & mk;
+                acc[k] = sign >= 0 ? acc[k] + slot : acc[k] - slot;
+                if (b >= 64) { V0 = V1; V1 = 0; }
+                else { V0 = (V0 >> b) | (V1 << (64 - b)); V1 >>= b; }
+            }
+        }
+    } else {
+        u128 s; s.lo = ((uint64_t)o[2] << 32) | o[3]; s.hi = ((uint64_t)o[0] << 32) | o[1];
+        s = Word<4>::band(s, Word<4>::mask(b));
+        acc[0] = sign >= 0 ? Word<4>::add(acc[0], s) : Word<4>::sub(acc[0], s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the stream kernel
+// ------------------------------------------------------------------------------------------------
+template <int WORDS>
+__device__ __forceinline__ void slab_store(uint32_t addr, typename Word<WORDS>::T v);
+template <> __device__ __forceinline__ void slab_store<1>(uint32_t addr, uint32_t v) { sts32(addr, v); }
+template <> __device__ __forceinline__ void slab_store<2>(uint32_t addr, uint64_t v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"((uint32_t)v), "r"((uint32_t)(v >> 32)) : "memory");
+}
+template <> __device__ __forceinline__ void slab_store<4>(uint32_t addr, u128 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"((uint32_t)v.lo), "r"((uint32_t)(v.lo >> 32)),
+                 "r"((uint32_t)v.hi), "r"((uint32_t)(v.hi >> 32)) : "memory");
+}
+template <int WORDS>
+__device__ __forceinline__ typename Word<WORDS>::T slab_load(uint32_t addr);
+template <> __device__ __forceinline__ uint32_t slab_load<1>(uint32_t addr) { return lds32(addr); }
+template <> __device__ __forceinline__ uint64_t slab_load<2>(uint32_t addr) {
+    uint32_t a, b;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
+    return ((uint64_t)b << 32) | a;
+}
+template <> __device__ __forceinline__ u128 slab_load<4>(uint32_t addr) {
+    uint32_t a, b, c, d;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+    u128 r; r.lo = ((uint64_t)b << 32) | a; r.hi = ((uint64_t)d << 32) | c; return r;
+}
+
+template <int WORDS, int MMAX, int MODE>
+__global__ void __launch_bounds__(STREAM_THREADS, 1)
+k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab st, const __grid_constant__ Geom g,
+         const __grid_constant__ IoDev io, const __grid_constant__ CodecDev cd, const __grid_constant__ NoiseDev nz) {
+    typedef Word<WORDS> WT;
+    typedef typename WT::T word_t;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t y = 0x00010000u | (lane << 2);
+    const uint32_t sbase = smem_window_base();
+#define PRE_OF(k) Pre{st.pre[k][0], st.pre[k][1], st.pre[k][2], st.pre[k][3]}
+    const uint32_t slab_bytes = 32u * MMAX * WORDS * 4u;
+    if (sbase + nwarps * slab_bytes > TAB_BASE) { __trap(); }
+    const uint32_t slab = sbase + warp * slab_bytes;
+
+    fill_tables();
+    __syncthreads();
+
+    const word_t mk = WT::mask(g.b);
+    const uint32_t m = g.m;
+    const uint64_t n_items = (st.batch && !io.share) ? g.W_cnt * io.n_clients : g.W_cnt;
+    const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, gstride = (uint64_t)gridDim.x * nwarps;
+
+    for (uint64_t t = gw; t < n_items; t += gstride) {
+        uint32_t c_first = 0, c_count = 1;
+        uint64_t W = t;
+        if (st.batch) {
+            if (io.share) { c_first = 0; c_count = io.n_clients; }
+            else { c_first = (uint32_t)(t / g.W_cnt); W = t - (uint64_t)c_first * g.W_cnt; }
+        }
+        const Item it = decode_item(g, g.W_lo + W);
+        const uint64_t blk = it.i0 + lane;              // local block index of this lane
+        const uint64_t e_lane = blk * m;                // first local element of this lane
+        const bool lane_on = e_lane < it.clen;
+        const uint64_t ctr = it.cb + blk;               // jzf_flashe.py:34 "(i + begin)"
+        const uint64_t item_e0 = it.cb + it.i0 * m;     // first global element of the item
+        const uint64_t rem = it.clen - it.i0 * m;
+        const uint32_t item_n = (uint32_t)(rem < 32ull * m ? rem : 32ull * m);
+
+        word_t prev[MMAX];  // shared-stream mode: F(iter, c) carried to the next client
+        if (st.batch && io.share) {
+#pragma unroll
+            for (int k = 0; k < MMAX; ++k) prev[k] = WT::zero();
+            if (lane_on) {
+                uint32_t o[4];
+                aes256_block(ks, y, st.iter, st.prf[0], (uint32_t)(ctr >> 32), (uint32_t)ctr, PRE_OF(0), o);
+                accumulate_slots<WORDS, MMAX>(o, g.b, m, +1, prev);
+            }
+        }
+
+        for (uint32_t cc = 0; cc < c_count; ++cc) {
+            const uint32_t c = c_first + cc;
+            word_t acc[MMAX];
+#pragma unroll
+            for (int k = 0; k < MMAX; ++k) acc[k] = WT::zero();
+            if (lane_on) {
+                if (!st.batch) {
+                    for (uint32_t s = 0; s < st.n; ++s) {
+                        uint32_t o[4];
+                        aes256_block(ks, y, st.iter, st.prf[s], (uint32_t)(ctr >> 32), (uint32_t)ctr, PRE_OF(s), o);
+                        accumulate_slots<WORDS, MMAX>(o, g.b, m, st.sign[s], acc);
+                    }
+                } else if (io.share) {
+                    word_t nxt[MMAX];
+#pragma unroll
+                    for (int k = 0; k < MMAX; ++k) nxt[k] = WT::zero();
+                    uint32_t o[4];
+                    aes256_block(ks, y, st.iter, st.prf[c + 1], (uint32_t)(ctr >> 32), (uint32_t)ctr, PRE_OF(c + 1), o);
+                    accumulate_slots<WORDS, MMAX>(o, g.b, m, +1, nxt);
+#pragma unroll
+                    for (int k = 0; k < MMAX; ++k) { acc[k] = WT::sub(prev[k], nxt[k]); prev[k] = nxt[k]; }
+                } else {
+                    uint32_t o[4];
+                    aes256_block(ks, y, st.iter, st.prf[c], (uint32_t)(ctr >> 32), (uint32_t)ctr, PRE_OF(c), o);
+                    accumulate_slots<WORDS, MMAX>(o, g.b, m, +1, acc);
+                    if (st.dbl) {
+                        aes256_block(ks, y, st.iter, st.prf[c + 1], (uint32_t)(ctr >> 32), (uint32_t)ctr, PRE_OF(c + 1), o);
+                        accumulate_slots<WORDS, MMAX>(o, g.b, m, -1, acc);
+                    }
+                }
+            }
+            // lane-major -> element-major through the warp's slab
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < MMAX; ++k)
+                if ((uint32_t)k < m) slab_store<WORDS>(slab + (lane * m + k) * (WORDS * 4u), acc[k]);
+            __syncwarp();
+
+            for (uint32_t e = lane; e < item_n; e += 32) {
+                const uint64_t j = item_e0 + e;
+                if (j < g.begin || j >= g.end) continue;
+                const uint64_t off = j - g.begin;
+                word_t mask_w = WT::band(slab_load<WORDS>(slab + e * (WORDS * 4u)), mk);
+                if (MODE == M_MASKS) {
+                    reinterpret_cast<word_t*>(io.out)[off] = mask_w;
+                } else if (MODE == M_APPLY) {
+                    const word_t* in = reinterpret_cast<const word_t*>(io.in) + (uint64_t)c * io.in_stride;
+                    word_t* out = reinterpret_cast<word_t*>(io.out) + (uint64_t)c * io.out_stride;
+                    out[off] = WT::band(WT::add(in[off], mask_w), mk);
+                } else if (MODE == M_ENCODE) {
+                    const float* x = reinterpret_cast<const float*>(io.in) + (uint64_t)c * io.in_stride;
+                    word_t* out = reinterpret_cast<word_t*>(io.out) + (uint64_t)c * io.out_stride;
+                    const Seg& sg = find_seg(cd, j);
+                    double u = nz.u ? nz.u[(uint64_t)c * nz.u_stride + off] : noise_one(nz, nz.stream + c, j);
+                    uint32_t q = encode_one(x[off], u, sg.a, sg.two_a, cd.scale);
+                    if (io.aux) reinterpret_cast<uint32_t*>(io.aux)[(uint64_t)c * io.out_stride + off] = q;
+                    out[off] = WT::band(WT::add(WT::from_u32(q), mask_w), mk);
+                } else if (MODE == M_DECODE) {
+                    const word_t* in = reinterpret_cast<const word_t*>(io.in);
+                    word_t p = WT::band(WT::add(in[off], mask_w), mk);
+                    if (io.aux) reinterpret_cast<word_t*>(io.aux)[off] = p;
+                    const Seg& sg = find_seg(cd, j);
+                    io.outf[off] = decode_one(WT::to_double(p), sg.two_an, cd.den, sg.an);
+                } else if (MODE == M_SCATTER) {
+                    const int64_t* index = reinterpret_cast<const int64_t*>(io.aux);
+                    word_t* dense = reinterpret_cast<word_t*>(io.out);
+                    const int64_t dst = index[off];
+                    dense[dst] = WT::band(WT::add(dense[dst], mask_w), mk);
+                }
+            }
+        }
+    }
+}
+
+// one AES block, known-answer tests (flashe_prp_block)
+__global__ void k_prp_block(const __grid_constant__ KeySched ks, const uint32_t* in, uint32_t* out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t y = 0x00010000u | (lane << 2);
+    if (smem_window_base() > TAB_BASE) { __trap(); }
+    fill_tables();
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        Pre pre; uint32_t o[4];
+        // w2 forced non-zero path is not wanted here: hoist on the device for this block
+        uint32_t w0 = in[0], w1 = in[1], w2 = in[2], w3 = in[3];
+        uint32_t s0 = w0 ^ ks.rk[0], s1 = w1 ^ ks.rk[1], s2 = w2 ^ ks.rk[2];
+        pre.p0 = T0(s0) ^ T1(s1) ^ T2(s2) ^ ks.rk[4];
+        pre.p1 = T0(s1) ^ T1(s2) ^ T3(s0) ^ ks.rk[5];
+        pre.p2 = T0(s2) ^ T2(s0) ^ T3(s1) ^ ks.rk[6];
+        pre.p3 = T1(s0) ^ T2(s1) ^ T3(s2) ^ ks.rk[7];
+        aes256_block(ks, y, w0, w1, 0u, w3, pre, o);   // fast path with the hoisted terms
+        uint32_t o2[4];
+        aes256_block(ks, y, w0, w1, w2 | 0u, w3, pre, o2);  // generic path when w2 != 0
+        if (lane == 0) {
+            for (int i = 0; i < 4; ++i) { out[i] = o[i]; out[4 + i] = o2[i]; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise kernels
+// ------------------------------------------------------------------------------------------------
+template <int WORDS>
+__global__ void k_add_premasked(const typename Word<WORDS>::T* __restrict__ in, const typename Word<WORDS>::T* __restrict__ mask,
+                                int sign, uint64_t count, uint32_t b, typename Word<WORDS>::T* __restrict__ out) {
+    typedef Word<WORDS> WT;
+    const typename WT::T mk = WT::mask(b);
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
+        typename WT::T a = in[j], mkv = mask[j];
+        out[j] = WT::band(sign >= 0 ? WT::add(a, mkv) : WT::sub(a, mkv), mk);
+    }
+}
+
+// vectorised u32 specialisation: 4 elements per thread, 128-bit accesses
+__global__ void k_add_premasked_v4(const uint4* __restrict__ in, const uint4* __restrict__ mask, int sign, uint64_t nvec,
+                                   uint32_t mk, uint4* __restrict__ out) {
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 a = __ldg(in + v), k = __ldg(mask + v), r;
+        if (sign >= 0) { r.x = a.x + k.x; r.y = a.y + k.y; r.z = a.z + k.z; r.w = a.w + k.w; }
+        else { r.x = a.x - k.x; r.y = a.y - k.y; r.z = a.z - k.z; r.w = a.w - k.w; }
+        r.x &= mk; r.y &= mk; r.z &= mk; r.w &= mk;
+        out[v] = r;
+    }
+}
+
+template <int WORDS, bool WITH_MASK>
+__global__ void k_encode(const float* __restrict__ x, const typename Word<WORDS>::T* __restrict__ mask, uint64_t begin,
+                         uint64_t count, uint32_t b, const __grid_constant__ CodecDev cd, const __grid_constant__ NoiseDev nz,
+                         uint32_t* __restrict__ q_out, typename Word<WORDS>::T* __restrict__ ct_out) {
+    typedef Word<WORDS> WT;
+    const typename WT::T mk = WT::mask(b);
+    for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < count; o += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t j = begin + o;
+        const Seg& sg = find_seg(cd, j);
+        double u = nz.u ? nz.u[o] : noise_one(nz, nz.stream, j);
+        uint32_t q = encode_one(x[o], u, sg.a, sg.two_a, cd.scale);
+        if (q_out) q_out[o] = q;
+        if (WITH_MASK) ct_out[o] = WT::band(WT::add(WT::from_u32(q), mask[o]), mk);
+    }
+}
+
+template <int WORDS>
+__global__ void k_decode(const typename Word<WORDS>::T* __restrict__ v, uint64_t begin, uint64_t count,
+                         const __grid_constant__ CodecDev cd, double* __restrict__ out) {
+    typedef Word<WORDS> WT;
+    for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < count; o += (uint64_t)gridDim.x * blockDim.x) {
+        const Seg& sg = find_seg(cd, begin + o);
+        out[o] = decode_one(WT::to_double(v[o]), sg.two_an, cd.den, sg.an);
+    }
+}
+
+__global__ void k_rng_uniform(const __grid_constant__ NoiseDev nz, uint64_t begin, uint64_t count, double* __restrict__ out) {
+    for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < count; o += (uint64_t)gridDim.x * blockDim.x)
+        out[o] = noise_one(nz, nz.stream, begin + o);
+}
+
+// Element-wise server sum (jzf_aggregator.py:421-430).  One thread owns one 16-byte column of the
+// [n][count] matrix and walks the n client rows with UNROLL independent 128-bit loads in flight.
+template <int WORDS>
+__global__ void __launch_bounds__(256)
+k_aggregate_vec(const uint4* __restrict__ cts, uint64_t stride_vec, int n, uint64_t nvec, uint32_t b, uint4* __restrict__ out) {
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4* p = cts + v;
+        if (WORDS == 1) {
+            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            int c = 0;
+            for (; c + 8 <= n; c += 8) {
+                uint4 r[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r[k] = __ldcs(p + (uint64_t)(c + k) * stride_vec);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { a0 += r[k].x; a1 += r[k].y; a2 += r[k].z; a3 += r[k].w; }
+            }
+            for (; c < n; ++c) { uint4 r = __ldcs(p + (uint64_t)c * stride_vec); a0 += r.x; a1 += r.y; a2 += r.z; a3 += r.w; }
+            const uint32_t mk = Word<1>::mask(b);
+            out[v] = make_uint4(a0 & mk, a1 & mk, a2 & mk, a3 & mk);
+        } else if (WORDS == 2) {
+            uint64_t a0 = 0, a1 = 0;
+            int c = 0;
+            for (; c + 8 <= n; c += 8) {
+                uint4 r[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r[k] = __ldcs(p + (uint64_t)(c + k) * stride_vec);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { a0 += ((uint64_t)r[k].y << 32) | r[k].x; a1 += ((uint64_t)r[k].w << 32) | r[k].z; }
+            }
+            for (; c < n; ++c) { uint4 r = __ldcs(p + (uint64_t)c * stride_vec); a0 += ((uint64_t)r.y << 32) | r.x; a1 += ((uint64_t)r.w << 32) | r.z; }
+            const uint64_t mk = Word<2>::mask(b);
+            a0 &= mk; a1 &= mk;
+            out[v] = make_uint4((uint32_t)a0, (uint32_t)(a0 >> 32), (uint32_t)a1, (uint32_t)(a1 >> 32));
+        } else {
+            u128 a = Word<4>::zero();
+            for (int c = 0; c < n; ++c) {
+                uint4 r = __ldcs(p + (uint64_t)c * stride_vec);
+                u128 w; w.lo = ((uint64_t)r.y << 32) | r.x; w.hi = ((uint64_t)r.w << 32) | r.z;
+                a = Word<4>::add(a, w);
+            }
+            a = Word<4>::band(a, Word<4>::mask(b));
+            out[v] = make_uint4((uint32_t)a.lo, (uint32_t)(a.lo >> 32), (uint32_t)a.hi, (uint32_t)(a.hi >> 32));
+        }
+    }
+}
+
+// scalar fallback for unaligned rows / tails (u32 and u64 words)
+template <int WORDS>
+__global__ void k_aggregate_scalar(const typename Word<WORDS>::T* __restrict__ cts, uint64_t stride, int n, uint64_t j0,
+                                   uint64_t count, uint32_t b, typename Word<WORDS>::T* __restrict__ out) {
+    typedef Word<WORDS> WT;
+    const typename WT::T mk = WT::mask(b);
+    for (uint64_t j = j0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
+        typename WT::T a = WT::zero();
+        for (int c = 0; c < n; ++c) a = WT::add(a, cts[(uint64_t)c * stride + j]);
+        out[j] = WT::band(a, mk);
+    }
+}
+
+// Packed-carry server sum (jzf_aggregator.py:404-419): radix-2^b addition of the n packed vectors,
+// least significant digit = LAST element.  Digit sum S_j = H_j*2^b + lo_j; the carry into element
+// j-1 is H_j + [lo_j + cin_j >= 2^b], i.e. a transfer function cin -> A + [cin >= T] with
+// (A,T) = (H_j, 2^b - lo_j).  Such functions compose into the same form, so carries are resolved
+// with a reverse scan: thread-serial over its ELEMS elements, shuffle scan across the warp, shared
+// memory across warps, and a look-ahead across tiles: a tile obtains its carry-in by composing the
+// transfer functions of the elements after it until the composition no longer depends on its own
+// carry-in (T = never) — for ciphertext-like data that happens after one element with probability
+// 1 - (n-1)/2^b — or the end of the range (carry_in) is reached.
+struct Xfer { uint32_t A; uint32_t T; };  // cin -> A + (cin >= T); T == 0xffffffff: never
+#define T_NEVER 0xffffffffu
+__device__ __forceinline__ uint32_t xfer_apply(Xfer f, uint32_t cin) { return f.A + (cin >= f.T ? 1u : 0u); }
+// h = outer ∘ inner  (inner is applied first: it belongs to the element closer to the end)
+__device__ __forceinline__ Xfer xfer_compose(Xfer outer, Xfer inner) {
+    Xfer h;
+    const uint32_t lo = inner.A, hi = inner.A + 1;  // possible outputs of inner
+    const bool lo_hit = lo >= outer.T, hi_hit = (inner.T != T_NEVER) && (hi >= outer.T);
+    if (inner.T == T_NEVER || lo_hit == hi_hit) { h.A = outer.A + (lo_hit ? 1u : 0u); h.T = T_NEVER; }
+    else { h.A = outer.A; h.T = inner.T; }  // lo misses, hi hits: depends on inner's threshold
+    return h;
+}
+template <int WORDS>
+__device__ __forceinline__ void digit_sum(const typename Word<WORDS>::T* __restrict__ cts, uint64_t stride, int n, uint64_t j,
+                                          uint32_t b, uint64_t& lo, uint32_t& H) {
+    // returns S_j = H*2^b + lo with lo < 2^b
+    if (WORDS == 1) {
+        uint64_t s = 0;
+        for (int c = 0; c < n; ++c) s += reinterpret_cast<const uint32_t*>(cts)[(uint64_t)c * stride + j];
+        lo = s & ((1ull << b) - 1ull); H = (uint32_t)(s >> b);
+    } else {
+        const uint64_t mk = Word<2>::mask(b);
+        uint64_t l = 0; uint32_t h = 0;
+        for (int c = 0; c < n; ++c) {
+            uint64_t w = reinterpret_cast<const uint64_t*>(cts)[(uint64_t)c * stride + j];
+            uint64_t s = l + w;
+            if (b >= 64) { h += (s < l); l = s; }
+            else { h += (uint32_t)(s >> b); l = s & mk; }
+        }
+        lo = l; H = h;
+    }
+}
+__device__ __forceinline__ Xfer xfer_of(uint64_t lo, uint32_t H, uint32_t b) {
+    Xfer f; f.A = H;
+    // threshold 2^b - lo, only relevant when it is small (cin <= n-1 < 2^31)
+    uint64_t thr = (b >= 64) ? (0ull - lo) : ((1ull << b) - lo);
+    f.T = (lo != 0 && thr < 0x7fffffffull) ? (uint32_t)thr : T_NEVER;
+    return f;
+}
+
+#define PK_ELEMS 4
+#define PK_THREADS 256
+template <int WORDS>
+__global__ void __launch_bounds__(PK_THREADS)
+k_aggregate_packed(const typename Word<WORDS>::T* __restrict__ cts, uint64_t stride, int n, uint64_t count, uint32_t b,
+                   uint32_t carry_in, typename Word<WORDS>::T* __restrict__ out, uint32_t* __restrict__ desc_out) {
+    typedef Word<WORDS> WT;
+    __shared__ Xfer warp_x[PK_THREADS / 32];
+    __shared__ uint32_t tile_cin;
+    const uint64_t tile_elems = (uint64_t)PK_THREADS * PK_ELEMS;
+    const uint64_t ntiles = (count + tile_elems - 1) / tile_elems;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t mk64 = (b >= 64) ? ~0ull : ((1ull << b) - 1ull);
+
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // tiles and threads are numbered from the END of the vector (carry flows towards element 0):
+        // thread q of tile t owns elements hi-1 .. hi-ELEMS with hi = count - (t*tile_elems + q*ELEMS)
+        const uint64_t base = tile * tile_elems + (uint64_t)threadIdx.x * PK_ELEMS;
+        uint64_t lo_[PK_ELEMS]; uint32_t H_[PK_ELEMS];
+        Xfer mine; mine.A = 0; mine.T = 0;  // identity: cin -> cin is not representable; track validity
+        bool have = false;
+#pragma unroll
+        for (int e = 0; e < PK_ELEMS; ++e) {
+            const uint64_t back = base + e;  // distance from the end
+            if (back < count) {
+                digit_sum<WORDS>(cts, stride, n, count - 1 - back, b, lo_[e], H_[e]);
+                Xfer f = xfer_of(lo_[e], H_[e], b);
+                mine = have ? xfer_compose(f, mine) : f;
+                have = true;
+            } else { lo_[e] = 0; H_[e] = 0; }
+        }
+        // Identity handling: a thread with no elements must pass the carry through unchanged.  That
+        // only happens in the last (partial) tile, where such threads sit AFTER all real ones in scan
+        // order (larger `back`), so their value is never consumed; give them a harmless constant.
+        if (!have) { mine.A = 0; mine.T = T_NEVER; }
+
+        // warp-level inclusive scan in `back` order (lane 0 is closest to the end):
+        // incl[l] = f_l ∘ f_{l-1} ∘ ... ∘ f_0
+        Xfer incl = mine;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            Xfer o; o.A = __shfl_up_sync(0xffffffffu, incl.A, dlt); o.T = __shfl_up_sync(0xffffffffu, incl.T, dlt);
+            if (lane >= (uint32_t)dlt) incl = xfer_compose(incl, o);
+        }
+        if (lane == 31) warp_x[warp] = incl;
+
+        // look-ahead for the tile's carry-in (elements closer to the end than this tile)
+        if (threadIdx.x == 0) {
+            uint32_t cin;
+            if (tile == 0) cin = carry_in;
+            else {
+                // compose f_{j} for j just after the tile, walking towards the end, until constant
+                const uint64_t first_back = tile * tile_elems;  // `back` of this tile's first element
+                Xfer acc; bool started = false; uint64_t bk = first_back;  // walk bk-1, bk-2, ... 0
+                cin = 0; bool resolved = false;
+                while (bk > 0) {
+                    --bk;
+                    uint64_t l; uint32_t h;
+                    digit_sum<WORDS>(cts, stride, n, count - 1 - bk, b, l, h);
+                    Xfer f = xfer_of(l, h, b);
+                    // acc currently maps (carry into element bk+1.. chain) ; new element is applied FIRST
+                    acc = started ? xfer_compose(acc, f) : f;
+                    started = true;
+                    if (acc.T == T_NEVER) { cin = acc.A; resolved = true; break; }
+                }
+                if (!resolved) cin = started ? xfer_apply(acc, carry_in) : carry_in;
+            }
+            tile_cin = cin;
+        }
+        __syncthreads();
+        // carry into this warp = composition of the previous warps applied to tile_cin
+        uint32_t cin = tile_cin;
+        for (uint32_t w = 0; w < warp; ++w) cin = xfer_apply(warp_x[w], cin);
+        // carry into this lane's first element: exclusive prefix within the warp
+        Xfer ex; ex.A = __shfl_up_sync(0xffffffffu, incl.A, 1); ex.T = __shfl_up_sync(0xffffffffu, incl.T, 1);
+        uint32_t c = lane == 0 ? cin : xfer_apply(ex, cin);
+#pragma unroll
+        for (int e = 0; e < PK_ELEMS; ++e) {
+            const uint64_t back = base + e;
+            if (back < count) {
+                uint64_t s = lo_[e] + c;   // lo < 2^b, c small
+                uint32_t extra;
+                if (b >= 64) { extra = (s < lo_[e]) ? 1u : 0u; }
+                else { extra = (uint32_t)(s >> b); s &= mk64; }
+                if (WORDS == 1) reinterpret_cast<uint32_t*>(out)[count - 1 - back] = (uint32_t)s;
+                else reinterpret_cast<uint64_t*>(out)[count - 1 - back] = s;
+                c = H_[e] + extra;
+            }
+        }
+        // Range descriptor for element-range shards (desc_out = {carry out for the given carry_in,
+        // depends, A, T}).  Word 0 comes from the thread that owns element 0.  Words 1-3 come from a
+        // walk from the END of the range: if the composed transfer function becomes constant, the
+        // carry out of the range cannot depend on carry_in (depends = 0); otherwise the walk has
+        // covered the whole range and (A, T) is its exact transfer function (depends = 1).
+        if (desc_out && tile == ntiles - 1) {
+            const uint64_t last_back = count - 1;
+            if (last_back >= base && last_back < base + PK_ELEMS) desc_out[0] = c;
+        }
+        if (desc_out && tile == 0 && threadIdx.x == 0) {
+            Xfer acc; acc.A = 0; acc.T = T_NEVER; bool started = false, resolved = false;
+            for (uint64_t bk = 0; bk < count; ++bk) {
+                uint64_t l; uint32_t h;
+                digit_sum<WORDS>(cts, stride, n, count - 1 - bk, b, l, h);
+                Xfer f = xfer_of(l, h, b);
+                acc = started ? xfer_compose(f, acc) : f;   // later elements are applied after (outer)
+                started = true;
+                if (acc.T == T_NEVER) { resolved = true; break; }
+            }
+            desc_out[1] = resolved ? 0u : 1u; desc_out[2] = acc.A; desc_out[3] = acc.T;
+        }
+        __syncthreads();
+    }
+}
+
+// Ripple a late carry-in into an already aggregated shard (multi-GPU packed sum): out is the
+// radix-2^b number whose least significant digit is the LAST element.
+template <int WORDS>
+__global__ void k_carry_fixup(typename Word<WORDS>::T* __restrict__ out, uint64_t count, uint32_t b, uint32_t carry_in) {
+    if (blockIdx.x || threadIdx.x) return;
+    uint64_t c = carry_in;
+    const uint64_t mk = (b >= 64) ? ~0ull : ((1ull << b) - 1ull);
+    for (uint64_t j = count; c && j-- > 0;) {
+        if constexpr (WORDS == 1) {
+            uint64_t v = (uint64_t)out[j] + c;
+            out[j] = (uint32_t)(v & mk); c = v >> b;
+        } else {
+            uint64_t o = out[j], v = o + c;
+            if (b >= 64) { out[j] = v; c = v < o ? 1 : 0; }
+            else { out[j] = v & mk; c = v >> b; }
+        }
+    }
+}
+
+// lane batching (jzf_quantize.py:162-185, 234-251)
+__global__ void k_batch_pack(const uint32_t* __restrict__ q, uint64_t count, uint32_t lane_bits, uint32_t bs, uint64_t nwords,
+                             u128* __restrict__ out) {
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t lo = 0, hi = 0;
+        for (uint32_t i = 0; i < bs; ++i) {
+            const uint64_t j = w * bs + i;
+            const uint64_t v = j < count ? q[j] : 0u;
+            hi = (hi << lane_bits) | (lo >> (64 - lane_bits));   // lane_bits in [1,32]
+            lo = (lo << lane_bits) + v;                          // v < 2^lane_bits: no carry
+        }
+        u128 r; r.lo = lo; r.hi = hi;
+        out[w] = r;
+    }
+}
+__global__ void k_batch_unpack(const u128* __restrict__ in, uint64_t nwords, uint32_t lane_bits, uint32_t bs, uint32_t* __restrict__ out) {
+    const uint64_t lm = (1ull << lane_bits) - 1ull;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
+        u128 t = in[w];
+        for (int i = (int)bs - 1; i >= 0; --i) {
+            out[w * bs + i] = (uint32_t)(t.lo & lm);
+            t.lo = (t.lo >> lane_bits) | (t.hi << (64 - lane_bits));
+            t.hi >>= lane_bits;
+        }
+    }
+}
+
+// expand_to_dense (jzf_aggregator.py:150-165)
+template <int WORDS>
+__global__ void k_fill(typename Word<WORDS>::T* __restrict__ out, uint64_t count, typename Word<WORDS>::T v) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x) out[j] = v;
+}
+template <int WORDS>
+__global__ void k_scatter(const typename Word<WORDS>::T* __restrict__ compact, const int64_t* __restrict__ index, uint64_t k,
+                          uint64_t total, typename Word<WORDS>::T* __restrict__ dense) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t d = index[i];
+        if (d >= 0 && (uint64_t)d < total) dense[d] = compact[i];
+    }
+}
+// |A ∩ B| for sorted unique index lists: each element of A binary-searches B
+__global__ void k_overlap(const int64_t* __restrict__ a, uint64_t ka, const int64_t* __restrict__ bq, uint64_t kb,
+                          unsigned long long* __restrict__ out) {
+    unsigned long long local = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ka; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t v = a[i];
+        uint64_t lo = 0, hi = kb;
+        while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (bq[mid] < v) lo = mid + 1; else hi = mid; }
+        local += (lo < kb && bq[lo] == v) ? 1ull : 0ull;
+    }
+    for (int dlt = 16; dlt > 0; dlt >>= 1) local += __shfl_down_sync(0xffffffffu, local, dlt);
+    if ((threadIdx.x & 31u) == 0 && local) atomicAdd(out, local);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct flashe_ctx {
+    int device;
+    int int_bits;
+    int words;       // 1, 2, 4
+    int num_sms;
+    uint32_t m;
+    uint8_t key[32];
+    KeySched ks;
+};
+
+static int words_of(int b) { return b <= 32 ? 1 : (b <= 64 ? 2 : 4); }
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(true) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int check_span(const flashe_span* s) {
+    if (!s) return fail(FLASHE_EINVAL, "span is NULL");
+    if (s->n_jobs == 0) return fail(FLASHE_EINVAL, "span.n_jobs must be >= 1");
+    if (s->reserved != 0) return fail(FLASHE_EINVAL, "span.reserved must be 0");
+    if (s->begin > s->total_len || s->count > s->total_len - s->begin)
+        return fail(FLASHE_EINVAL, "span [begin, begin+count) exceeds total_len");
+    return FLASHE_OK;
+}
+
+static uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+static void make_geom(const flashe_ctx* ctx, const flashe_span* s, Geom* g) {
+    memset(g, 0, sizeof(*g));
+    g->L = s->total_len; g->begin = s->begin; g->end = s->begin + s->count;
+    g->m = ctx->m; g->b = (uint32_t)ctx->int_bits;
+    g->d = s->total_len / s->n_jobs; g->r = s->total_len % s->n_jobs;
+    const uint64_t nbA = ceil_div(g->d + 1, g->m), nbB = g->d ? ceil_div(g->d, g->m) : 0;
+    g->nwA = ceil_div(nbA, 32); g->nwB = ceil_div(nbB, 32);
+    g->rA = g->r * g->nwA;
+    if (s->count == 0) { g->W_lo = 0; g->W_cnt = 0; return; }
+    auto item_of = [&](uint64_t j) {
+        uint64_t k, cb;
+        if (j < g->r * (g->d + 1)) { k = j / (g->d + 1); cb = k * (g->d + 1); }
+        else { k = g->r + (j - g->r * (g->d + 1)) / g->d; cb = g->r * (g->d + 1) + (k - g->r) * g->d; }
+        const uint64_t w = ((j - cb) / g->m) / 32;
+        return (k < g->r ? k * g->nwA : g->rA + (k - g->r) * g->nwB) + w;
+    };
+    g->W_lo = item_of(g->begin);
+    g->W_cnt = item_of(g->end - 1) - g->W_lo + 1;
+}
+
+static int make_streams(const flashe_ctx* ctx, uint32_t iter, const int32_t* prf, const int32_t* sign, int n, StreamTab* st) {
+    if (n < 1 || n > MAXS) return fail(FLASHE_EINVAL, "nstreams must be in [1, FLASHE_MAX_STREAMS]");
+    if (!prf) return fail(FLASHE_EINVAL, "prf_idx is NULL");
+    memset(st, 0, sizeof(*st));
+    st->n = (uint32_t)n; st->iter = iter;
+    for (int k = 0; k < n; ++k) {
+        st->prf[k] = (uint32_t)prf[k];
+        st->sign[k] = sign ? (sign[k] >= 0 ? 1 : -1) : 1;
+        haes::hoist_round1(ctx->ks.rk, iter, st->prf[k], 0u, st->pre[k]);
+    }
+    return FLASHE_OK;
+}
+
+struct CodecHost {
+    CodecDev dev;
+    Seg* table;  // device allocation to free (stream ordered) or NULL
+};
+
+static int make_codec(const flashe_ctx* ctx, const flashe_span* span, const flashe_codec* c, bool decode, cudaStream_t stream,
+                      CodecHost* out) {
+    (void)ctx;
+    memset(out, 0, sizeof(*out));
+    if (!c) return fail(FLASHE_EINVAL, "codec is NULL");
+    if (c->element_bits < 1 || c->element_bits > 24) return fail(FLASHE_EINVAL, "element_bits must be in [1, 24]");
+    if (c->nseg < 1 || !c->seg_end || !c->alpha) return fail(FLASHE_EINVAL, "codec needs nseg >= 1, seg_end and alpha");
+    if (decode && c->n_clients < 1) return fail(FLASHE_EINVAL, "codec.n_clients must be >= 1 for decode");
+    if (c->seg_end[c->nseg - 1] != span->total_len) return fail(FLASHE_EINVAL, "seg_end[nseg-1] must equal span.total_len");
+    std::vector<Seg> segs((size_t)c->nseg);
+    const int n = decode ? c->n_clients : 1;
+    for (int s = 0; s < c->nseg; ++s) {
+        if (s && c->seg_end[s] < c->seg_end[s - 1]) return fail(FLASHE_EINVAL, "seg_end must be ascending");
+        segs[s].end = c->seg_end[s];
+        segs[s].a = (float)c->alpha[s];
+        segs[s].two_a = (float)(2.0 * c->alpha[s]);
+        volatile double an = c->alpha[s] * (double)n;     // alpha *= num_clients (jzf_quantize.py:103)
+        segs[s].an = an;
+        segs[s].two_an = 2.0 * an;
+    }
+    CodecDev& d = out->dev;
+    d.nseg = c->nseg; d.ebits = c->element_bits;
+    d.scale = (float)(((int64_t)1 << c->element_bits) - 1);
+    d.den = (double)((((int64_t)1 << c->element_bits) - 1) * (int64_t)n);
+    if (c->nseg <= MAX_INLINE_SEG) {
+        memcpy(d.seg, segs.data(), sizeof(Seg) * (size_t)c->nseg);
+        d.table = nullptr;
+    } else {
+        // large layer tables travel through a stream-ordered allocation (pageable copy: the runtime
+        // stages it before returning)
+        CUDA_TRY(cudaMallocAsync((void**)&out->table, sizeof(Seg) * (size_t)c->nseg, stream));
+        CUDA_TRY(cudaMemcpyAsync(out->table, segs.data(), sizeof(Seg) * (size_t)c->nseg, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));  // segs goes out of scope
+        d.table = out->table;
+    }
+    return FLASHE_OK;
+}
+static void free_codec(CodecHost* c, cudaStream_t stream) { if (c->table) cudaFreeAsync(c->table, stream); }
+
+static void make_noise(const flashe_noise* nz, uint64_t u_stride, NoiseDev* d) {
+    memset(d, 0, sizeof(*d));
+    if (!nz) return;
+    d->u = nz->u; d->u_stride = u_stride;
+    d->k0 = (uint32_t)nz->rng_seed; d->k1 = (uint32_t)(nz->rng_seed >> 32);
+    d->stream = nz->rng_stream;
+}
+
+static int grid_1d(const flashe_ctx* ctx, uint64_t work_items, int threads, int per_sm) {
+    uint64_t blocks = ceil_div(work_items ? work_items : 1, (uint64_t)threads);
+    uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+template <int WORDS, int MMAX, int MODE>
+static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,
+                           const NoiseDev& nz, cudaStream_t stream) {
+    auto kern = k_stream<WORDS, MMAX, MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        attr_set = true;
+    }
+    const uint64_t items = (st.batch && !io.share) ? g.W_cnt * io.n_clients : g.W_cnt;
+    if (items == 0) return FLASHE_OK;
+    const int slab_bytes = 32 * MMAX * WORDS * 4;
+    int threads = STREAM_THREADS;
+    while (threads > 32 && (threads / 32) * slab_bytes > 60 * 1024) threads >>= 1;
+    const int wpb = threads / 32;
+    uint64_t blocks = ceil_div(items, (uint64_t)wpb);
+    if (blocks > (uint64_t)ctx->num_sms) blocks = (uint64_t)ctx->num_sms;
+    kern<<<(unsigned)blocks, threads, SMEM_BYTES, stream>>>(ctx->ks, st, g, io, cd, nz);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+template <int MODE>
+static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,
+                         const NoiseDev& nz, cudaStream_t stream) {
+    const int b = ctx->int_bits;
+    if (b <= 32) {
+        if (ctx->m <= 6) return launch_stream_t<1, 6, MODE>(ctx, st, g, io, cd, nz, stream);
+        return launch_stream_t<1, 16, MODE>(ctx, st, g, io, cd, nz, stream);
+    }
+    if (b <= 64) return launch_stream_t<2, 3, MODE>(ctx, st, g, io, cd, nz, stream);
+    return launch_stream_t<4, 1, MODE>(ctx, st, g, io, cd, nz, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int flashe_abi_version(void) { return FLASHE_ABI_VERSION; }
+const char* flashe_last_error(void) { return g_err.c_str(); }
+uint64_t flashe_launch_count(void) { return g_launches.load(); }
+
+int flashe_word_bytes(int int_bits) {
+    if (int_bits < 1 || int_bits > 128) return fail(FLASHE_EINVAL, "int_bits must be in [1, 128]");
+    return 4 * words_of(int_bits);
+}
+
+int flashe_ctx_create(const uint8_t* seed, size_t seed_len, int int_bits, int device, flashe_ctx** out) {
+    if (!out) return fail(FLASHE_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!seed || seed_len == 0) return fail(FLASHE_EINVAL, "seed must hold at least one byte");
+    if (int_bits < 8 || int_bits > 128)
+        return fail(FLASHE_EUNSUPPORTED, "int_bits must be in [8, 128] (the reference itself fails above 128: merge_size = 128 // int_bits = 0)");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(FLASHE_EINVAL, "no such CUDA device");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FLASHE_ECUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(FLASHE_EUNSUPPORTED, std::string("built for sm_100a (B200) only; device is ") + prop.name);
+    if ((size_t)prop.sharedMemPerBlockOptin < SMEM_BYTES) return fail(FLASHE_EUNSUPPORTED, "device lacks 192 KB of shared memory per block");
+    flashe_ctx* ctx = new (std::nothrow) flashe_ctx();
+    if (!ctx) return fail(FLASHE_ENOMEM, "out of host memory");
+    ctx->device = device; ctx->int_bits = int_bits; ctx->words = words_of(int_bits);
+    ctx->num_sms = prop.multiProcessorCount; ctx->m = (uint32_t)(128 / int_bits);
+    // low 32 bytes of the seed, left-zero-padded (jzf_aes.py:21-28)
+    memset(ctx->key, 0, 32);
+    if (seed_len >= 32) memcpy(ctx->key, seed + (seed_len - 32), 32);
+    else memcpy(ctx->key + (32 - seed_len), seed, seed_len);
+    haes::expand(ctx->key, ctx->ks.rk);
+    cudaError_t e = cudaMemcpyToSymbol(g_te0, haes::te0, sizeof(haes::te0));
+    if (e != cudaSuccess) { delete ctx; return fail(FLASHE_ECUDA, std::string("cudaMemcpyToSymbol: ") + cudaGetErrorString(e)); }
+    *out = ctx;
+    return FLASHE_OK;
+}
+
+int flashe_ctx_destroy(flashe_ctx* ctx) {
+    if (!ctx) return FLASHE_OK;
+    memset(ctx->key, 0, sizeof(ctx->key));
+    memset(&ctx->ks, 0, sizeof(ctx->ks));
+    delete ctx;
+    return FLASHE_OK;
+}
+int flashe_ctx_int_bits(const flashe_ctx* ctx) { return ctx ? ctx->int_bits : fail(FLASHE_EINVAL, "ctx is NULL"); }
+int flashe_ctx_device(const flashe_ctx* ctx) { return ctx ? ctx->device : fail(FLASHE_EINVAL, "ctx is NULL"); }
+
+#define ENTER(ctx)                                                        \
+    if (!(ctx)) return fail(FLASHE_EINVAL, "ctx is NULL");                \
+    DeviceGuard guard__((ctx)->device);                                   \
+    if (!guard__.ok) return fail(FLASHE_ECUDA, "cudaSetDevice failed");   \
+    cudaStream_t cs = (cudaStream_t)stream
+
+int flashe_prp_block(flashe_ctx* ctx, const uint8_t in16[16], uint8_t out16[16], void* stream) {
+    ENTER(ctx);
+    if (!in16 || !out16) return fail(FLASHE_EINVAL, "NULL buffer");
+    uint32_t w[4], o[8];
+    for (int i = 0; i < 4; ++i) w[i] = ((uint32_t)in16[4 * i] << 24) | ((uint32_t)in16[4 * i + 1] << 16) | ((uint32_t)in16[4 * i + 2] << 8) | in16[4 * i + 3];
+    uint32_t* d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d, 12 * sizeof(uint32_t)));
+    cudaError_t e = cudaMemcpyAsync(d, w, 16, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess) {
+        auto kern = k_prp_block;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e == cudaSuccess) {
+            kern<<<1, 256, SMEM_BYTES, cs>>>(ctx->ks, d, d + 4);
+            g_launches.fetch_add(1);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(o, d + 4, 32, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(FLASHE_ECUDA, std::string("flashe_prp_block: ") + cudaGetErrorString(e));
+    // o = hoisted round-1 path, o+4 = generic path: both must give the same block
+    const uint32_t* r = o;
+    if (memcmp(o, o + 4, 16) != 0) return fail(FLASHE_ECUDA, "internal: hoisted and generic AES paths disagree");
+    for (int i = 0; i < 4; ++i) { out16[4 * i] = (uint8_t)(r[i] >> 24); out16[4 * i + 1] = (uint8_t)(r[i] >> 16); out16[4 * i + 2] = (uint8_t)(r[i] >> 8); out16[4 * i + 3] = (uint8_t)r[i]; }
+    return FLASHE_OK;
+}
+
+int flashe_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf_idx, const int32_t* sign, int nstreams,
+                 const flashe_span* span, void* out, void* stream) {
+    ENTER(ctx);
+    int rc = check_span(span); if (rc) return rc;
+    if (span->count && !out) return fail(FLASHE_EINVAL, "out is NULL");
+    StreamTab st; rc = make_streams(ctx, iter, prf_idx, sign, nstreams, &st); if (rc) return rc;
+    Geom g; make_geom(ctx, span, &g);
+    IoDev io; memset(&io, 0, sizeof(io)); io.out = out; io.n_clients = 1;
+    CodecDev cd; memset(&cd, 0, sizeof(cd)); NoiseDev nz; memset(&nz, 0, sizeof(nz));
+    return launch_stream<M_MASKS>(ctx, st, g, io, cd, nz, cs);
+}
+
+int flashe_apply_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf_idx, const int32_t* sign, int nstreams,
+                       const flashe_span* span, const void* in, void* out, void* stream) {
+    ENTER(ctx);
+    int rc = check_span(span); if (rc) return rc;
+    if (span->count && (!in || !out)) return fail(FLASHE_EINVAL, "in/out is NULL");
+    StreamTab st; rc = make_streams(ctx, iter, prf_idx, sign, nstreams, &st); if (rc) return rc;
+    Geom g; make_geom(ctx, span, &g);
+    IoDev io; memset(&io, 0, sizeof(io)); io.in = in; io.out = out; io.n_clients = 1;
+    CodecDev cd; memset(&cd, 0, sizeof(cd)); NoiseDev nz; memset(&nz, 0, sizeof(nz));
+    return launch_stream<M_APPLY>(ctx, st, g, io, cd, nz, cs);
+}
+
+int flashe_encrypt(flashe_ctx* ctx, uint32_t iter, int32_t idx, int scheme, const flashe_span* span, const void* q_in,
+                   void* ct_out, void* stream) {
+    if (scheme != FLASHE_SCHEME_SINGLE && scheme != FLASHE_SCHEME_DOUBLE) return fail(FLASHE_EINVAL, "unknown masking scheme");
+    if (idx < 0) return fail(FLASHE_EINVAL, "client idx must be >= 0");
+    const int32_t prf[2] = {idx, idx + 1}, sg[2] = {1, -1};
+    return flashe_apply_masks(ctx, iter, prf, sg, scheme == FLASHE_SCHEME_DOUBLE ? 2 : 1, span, q_in, ct_out, stream);
+}
+
+static int build_decrypt_streams(const int32_t* add_idx, int na, const int32_t* minus_idx, int ns, int32_t* prf, int32_t* sg) {
+    if (na < 0 || ns < 0 || na + ns < 1 || na + ns > MAXS) return fail(FLASHE_EINVAL, "na + ns must be in [1, FLASHE_MAX_STREAMS]");
+    if ((na && !add_idx) || (ns && !minus_idx)) return fail(FLASHE_EINVAL, "index list is NULL");
+    for (int k = 0; k < na; ++k) { prf[k] = add_idx[k]; sg[k] = 1; }
+    for (int k = 0; k < ns; ++k) { prf[na + k] = minus_idx[k]; sg[na + k] = -1; }
+    return FLASHE_OK;
+}
+
+int flashe_decrypt(flashe_ctx* ctx, uint32_t iter, const int32_t* add_idx, int na, const int32_t* minus_idx, int ns,
+                   const flashe_span* span, const void* agg_in, void* p_out, void* stream) {
+    int32_t prf[MAXS], sg[MAXS];
+    int rc = build_decrypt_streams(add_idx, na, minus_idx, ns, prf, sg); if (rc) return rc;
+    return flashe_apply_masks(ctx, iter, prf, sg, na + ns, span, agg_in, p_out, stream);
+}
+
+int flashe_add_premasked(flashe_ctx* ctx, const void* in, const void* mask, int sign, uint64_t count, void* out, void* stream) {
+    ENTER(ctx);
+    if (count == 0) return FLASHE_OK;
+    if (!in || !mask || !out) return fail(FLASHE_EINVAL, "NULL buffer");
+    const uint32_t b = (uint32_t)ctx->int_bits;
+    if (ctx->words == 1) {
+        const bool aligned = (((uintptr_t)in | (uintptr_t)mask | (uintptr_t)out) & 15u) == 0;
+        uint64_t nvec = aligned ? count / 4 : 0;
+        if (nvec) {
+            k_add_premasked_v4<<<grid_1d(ctx, nvec, 256, 16), 256, 0, cs>>>((const uint4*)in, (const uint4*)mask, sign, nvec, Word<1>::mask(b) , (uint4*)out);
+            g_launches.fetch_add(1);
+        }
+        const uint64_t done = nvec * 4;
+        if (done < count) {
+            k_add_premasked<1><<<grid_1d(ctx, count - done, 256, 16), 256, 0, cs>>>((const uint32_t*)in + done, (const uint32_t*)mask + done, sign, count - done, b, (uint32_t*)out + done);
+            g_launches.fetch_add(1);
+        }
+    } else if (ctx->words == 2) {
+        k_add_premasked<2><<<grid_1d(ctx, count, 256, 16), 256, 0, cs>>>((const uint64_t*)in, (const uint64_t*)mask, sign, count, b, (uint64_t*)out);
+        g_launches.fetch_add(1);
+    } else {
+        k_add_premasked<4><<<grid_1d(ctx, count, 256, 16), 256, 0, cs>>>((const u128*)in, (const u128*)mask, sign, count, b, (u128*)out);
+        g_launches.fetch_add(1);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+int flashe_encode(flashe_ctx* ctx, const flashe_span* span, const float* x, const flashe_codec* codec, const flashe_noise* noise,
+                  uint32_t* q_out, void* stream) {
+    ENTER(ctx);
+    int rc = check_span(span); if (rc) return rc;
+    if (span->count == 0) return FLASHE_OK;
+    if (!x || !q_out) return fail(FLASHE_EINVAL, "NULL buffer");
+    CodecHost ch; rc = make_codec(ctx, span, codec, false, cs, &ch); if (rc) return rc;
+    NoiseDev nz; make_noise(noise, 0, &nz);
+    k_encode<1, false><<<grid_1d(ctx, span->count, 256, 16), 256, 0, cs>>>(x, nullptr, span->begin, span->count, 32, ch.dev, nz, q_out, nullptr);
+    g_launches.fetch_add(1);
+    free_codec(&ch, cs);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+static int encode_encrypt_impl(flashe_ctx* ctx, uint32_t iter, int32_t idx0, int n_clients, int scheme, const flashe_span* span,
+                               const float* x, uint64_t x_stride, const flashe_codec* codec, const flashe_noise* noise,
+                               uint64_t u_stride, void* ct_out, uint64_t ct_stride, uint32_t* q_out, int share, void* stream) {
+    ENTER(ctx);
+    int rc = check_span(span); if (rc) return rc;
+    if (scheme != FLASHE_SCHEME_SINGLE && scheme != FLASHE_SCHEME_DOUBLE) return fail(FLASHE_EINVAL, "unknown masking scheme");
+    if (idx0 < 0) return fail(FLASHE_EINVAL, "client idx must be >= 0");
+    if (n_clients < 1 || n_clients > MAXS - 1) return fail(FLASHE_EINVAL, "n_clients must be in [1, FLASHE_MAX_STREAMS-1] per call");
+    if (span->count == 0) return FLASHE_OK;
+    if (!x || !ct_out) return fail(FLASHE_EINVAL, "NULL buffer");
+    if (n_clients > 1 && (x_stride < span->count || ct_stride < span->count)) return fail(FLASHE_EINVAL, "client strides must be >= span.count");
+    const bool dbl = scheme == FLASHE_SCHEME_DOUBLE;
+    int32_t prf[MAXS];
+    const int nent = n_clients + (dbl ? 1 : 0);
+    for (int k = 0; k < nent; ++k) prf[k] = idx0 + k;
+    StreamTab st; rc = make_streams(ctx, iter, prf, nullptr, nent, &st); if (rc) return rc;
+    st.batch = 1; st.dbl = dbl ? 1u : 0u;
+    Geom g; make_geom(ctx, span, &g);
+    CodecHost ch; rc = make_codec(ctx, span, codec, false, cs, &ch); if (rc) return rc;
+    NoiseDev nz; make_noise(noise, u_stride, &nz);
+    IoDev io; memset(&io, 0, sizeof(io));
+    io.in = x; io.in_stride = x_stride; io.out = ct_out; io.out_stride = ct_stride; io.aux = q_out;
+    io.n_clients = (uint32_t)n_clients; io.share = (share && dbl) ? 1u : 0u;
+    rc = launch_stream<M_ENCODE>(ctx, st, g, io, ch.dev, nz, cs);
+    free_codec(&ch, cs);
+    return rc;
+}
+
+int flashe_encode_encrypt(flashe_ctx* ctx, uint32_t iter, int32_t idx, int scheme, const flashe_span* span, const float* x,
+                          const flashe_codec* codec, const flashe_noise* noise, void* ct_out, uint32_t* q_out, void* stream) {
+    return encode_encrypt_impl(ctx, iter, idx, 1, scheme, span, x, 0, codec, noise, 0, ct_out, 0, q_out, 0, stream);
+}
+
+int flashe_encode_encrypt_batch(flashe_ctx* ctx, uint32_t iter, int32_t idx0, int n_clients, int scheme, const flashe_span* span,
+                                const float* x, uint64_t x_stride, const flashe_codec* codec, const flashe_noise* noise,
+                                uint64_t u_stride, void* ct_out, uint64_t ct_stride, int share_streams, void* stream) {
+    return encode_encrypt_impl(ctx, iter, idx0, n_clients, scheme, span, x, x_stride, codec, noise, u_stride, ct_out, ct_stride,
+                               nullptr, share_streams, stream);
+}
+
+int flashe_encode_add_premasked(flashe_ctx* ctx, const flashe_span* span, const float* x, const flashe_codec* codec,
+                                const flashe_noise* noise, const void* mask, void* ct_out, void* stream) {
+    ENTER(ctx);
+    int rc = check_span(span); if (rc) return rc;
+    if (span->count == 0) return FLASHE_OK;
+    if (!x || !mask || !ct_out) return fail(FLASHE_EINVAL, "NULL buffer");
+    CodecHost ch; rc = make_codec(ctx, span, codec, false, cs, &ch); if (rc) return rc;
+    NoiseDev nz; make_noise(noise, 0, &nz);
+    const uint32_t b = (uint32_t)ctx->int_bits;
+    const int grid = grid_1d(ctx, span->count, 256, 16);
+    if (ctx->words == 1) k_encode<1, true><<<grid, 256, 0, cs>>>(x, (const uint32_t*)mask, span->begin, span->count, b, ch.dev, nz, nullptr, (uint32_t*)ct_out);
+    else if (ctx->words == 2) k_encode<2, true><<<grid, 256, 0, cs>>>(x, (const uint64_t*)mask, span->begin, span->count, b, ch.dev, nz, nullptr, (uint64_t*)ct_out);
+    else k_encode<4, true><<<grid, 256, 0, cs>>>(x, (const u128*)mask, span->begin, span->count, b, ch.dev, nz, nullptr, (u128*)ct_out);
+    g_launches.fetch_add(1);
+    free_codec(&ch, cs);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+int flashe_aggregate(flashe_ctx* ctx, const void* cts, uint64_t stride, int n, uint64_t count, int mode, uint32_t carry_in,
+                     void* out, uint32_t* carry_out, void* stream) {
+    ENTER(ctx);
+    if (n < 1) return fail(FLASHE_EINVAL, "n must be >= 1");
+    if (mode != FLASHE_AGG_ELEMENTWISE && mode != FLASHE_AGG_PACKED) return fail(FLASHE_EINVAL, "unknown aggregate mode");
+    if (count == 0) {
+        if (mode == FLASHE_AGG_PACKED && carry_out) {
+            // empty range: the carry passes through unchanged: cin -> 0 + (cin >= 1) only holds for
+            // cin <= 1, so report it as "given carry, no dependence" and let callers skip empty shards
+            uint32_t d[4] = {carry_in, 0u, carry_in, T_NEVER};
+            CUDA_TRY(cudaMemcpyAsync(carry_out, d, sizeof(d), cudaMemcpyHostToDevice, cs));
+        }
+        return FLASHE_OK;
+    }
+    if (!cts || !out) return fail(FLASHE_EINVAL, "NULL buffer");
+    if (n > 1 && stride < count) return fail(FLASHE_EINVAL, "stride must be >= count");
+    const uint32_t b = (uint32_t)ctx->int_bits;
+    const int wb = 4 * ctx->words;
+    if (mode == FLASHE_AGG_ELEMENTWISE) {
+        const int per_vec = 16 / wb;
+        const bool aligned = (((uintptr_t)cts | (uintptr_t)out) & 15u) == 0 && (stride % (uint64_t)per_vec) == 0;
+        const uint64_t nvec = aligned ? count / per_vec : 0;
+        if (nvec) {
+            const int grid = grid_1d(ctx, nvec, 256, 8);
+            const uint64_t sv = stride / per_vec;
+            if (ctx->words == 1) k_aggregate_vec<1><<<grid, 256, 0, cs>>>((const uint4*)cts, sv, n, nvec, b, (uint4*)out);
+            else if (ctx->words == 2) k_aggregate_vec<2><<<grid, 256, 0, cs>>>((const uint4*)cts, sv, n, nvec, b, (uint4*)out);
+            else k_aggregate_vec<4><<<grid, 256, 0, cs>>>((const uint4*)cts, sv, n, nvec, b, (uint4*)out);
+            g_launches.fetch_add(1);
+        }
+        const uint64_t done = nvec * per_vec;
+        if (done < count) {
+            const int grid = grid_1d(ctx, count - done, 256, 8);
+            if (ctx->words == 1) k_aggregate_scalar<1><<<grid, 256, 0, cs>>>((const uint32_t*)cts, stride, n, done, count, b, (uint32_t*)out);
+            else if (ctx->words == 2) k_aggregate_scalar<2><<<grid, 256, 0, cs>>>((const uint64_t*)cts, stride, n, done, count, b, (uint64_t*)out);
+            else k_aggregate_scalar<4><<<grid, 256, 0, cs>>>((const u128*)cts, stride, n, done, count, b, (u128*)out);
+            g_launches.fetch_add(1);
+        }
+    } else {
+        if (ctx->words == 4) return fail(FLASHE_EUNSUPPORTED, "packed-carry aggregate is built for int_bits <= 64");
+        const uint64_t ntiles = ceil_div(count, (uint64_t)PK_THREADS * PK_ELEMS);
+        uint64_t cap = (uint64_t)ctx->num_sms * 8;
+        const int grid = (int)(ntiles < cap ? ntiles : cap);
+        if (ctx->words == 1) k_aggregate_packed<1><<<grid, PK_THREADS, 0, cs>>>((const uint32_t*)cts, stride, n, count, b, carry_in, (uint32_t*)out, carry_out);
+        else k_aggregate_packed<2><<<grid, PK_THREADS, 0, cs>>>((const uint64_t*)cts, stride, n, count, b, carry_in, (uint64_t*)out, carry_out);
+        g_launches.fetch_add(1);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+int flashe_aggregate_carry_fixup(flashe_ctx* ctx, void* out, uint64_t count, uint32_t carry_in, void* stream) {
+    ENTER(ctx);
+    if (ctx->words == 4) return fail(FLASHE_EUNSUPPORTED, "packed-carry aggregate is built for int_bits <= 64");
+    if (count == 0 || carry_in == 0) return FLASHE_OK;
+    if (!out) return fail(FLASHE_EINVAL, "out is NULL");
+    if (ctx->words == 1) k_carry_fixup<1><<<1, 32, 0, cs>>>((uint32_t*)out, count, (uint32_t)ctx->int_bits, carry_in);
+    else k_carry_fixup<2><<<1, 32, 0, cs>>>((uint64_t*)out, count, (uint32_t)ctx->int_bits, carry_in);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+int flashe_decode(flashe_ctx* ctx, const flashe_span* span, const void* v, const flashe_codec* codec, double* out, void* stream) {
+    ENTER(ctx);
+    int rc = check_span(span); if (rc) return rc;
+    if (ctx->words == 4) return fail(FLASHE_EUNSUPPORTED, "decode takes int_bits <= 64 (unbatch 128-bit words first)");
+    if (span->count == 0) return FLASHE_OK;
+    if (!v || !out) return fail(FLASHE_EINVAL, "NULL buffer");
+    CodecHost ch; rc = make_codec(ctx, span, codec, true, cs, &ch); if (rc) return rc;
+    const int grid = grid_1d(ctx, span->count, 256, 16);
+    if (ctx->words == 1) k_decode<1><<<grid, 256, 0, cs>>>((const uint32_t*)v, span->begin, span->count, ch.dev, out);
+    else k_decode<2><<<grid, 256, 0, cs>>>((const uint64_t*)v, span->begin, span->count, ch.dev, out);
+    g_launches.fetch_add(1);
+    free_codec(&ch, cs);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+int flashe_decrypt_decode(flashe_ctx* ctx, uint32_t iter, const int32_t* add_idx, int na, const int32_t* minus_idx, int ns,
+                          const flashe_span* span, const void* agg_in, const flashe_codec* codec, double* out, void* p_out,
+                          void* stream) {
+    ENTER(ctx);
+    int rc = check_span(span); if (rc) return rc;
+    if (ctx->words == 4) return fail(FLASHE_EUNSUPPORTED, "decrypt_decode takes int_bits <= 64 (decrypt, unbatch, decode for 128-bit words)");
+    int32_t prf[MAXS], sg[MAXS];
+    rc = build_decrypt_streams(add_idx, na, minus_idx, ns, prf, sg); if (rc) return rc;
+    if (span->count == 0) return FLASHE_OK;
+    if (!agg_in || !out) return fail(FLASHE_EINVAL, "NULL buffer");
+    StreamTab st; rc = make_streams(ctx, iter, prf, sg, na + ns, &st); if (rc) return rc;
+    Geom g; make_geom(ctx, span, &g);
+    CodecHost ch; rc = make_codec(ctx, span, codec, true, cs, &ch); if (rc) return rc;
+    IoDev io; memset(&io, 0, sizeof(io)); io.in = agg_in; io.outf = out; io.aux = p_out; io.n_clients = 1;
+    NoiseDev nz; memset(&nz, 0, sizeof(nz));
+    rc = launch_stream<M_DECODE>(ctx, st, g, io, ch.dev, nz, cs);
+    free_codec(&ch, cs);
+    return rc;
+}
+
+int flashe_rng_uniform(flashe_ctx* ctx, uint64_t rng_seed, uint64_t rng_stream, uint64_t begin, uint64_t count, double* out, void* stream) {
+    ENTER(ctx);
+    if (count == 0) return FLASHE_OK;
+    if (!out) return fail(FLASHE_EINVAL, "out is NULL");
+    flashe_noise n; n.u = nullptr; n.rng_seed = rng_seed; n.rng_stream = rng_stream;
+    NoiseDev nz; make_noise(&n, 0, &nz);
+    k_rng_uniform<<<grid_1d(ctx, count, 256, 16), 256, 0, cs>>>(nz, begin, count, out);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+static int batch_geometry(const flashe_ctx* ctx, int element_bits, int factor, uint32_t* lane, uint32_t* bs) {
+    if (ctx->words != 4) return fail(FLASHE_EUNSUPPORTED, "lane batching is built for 64 < int_bits <= 128 (shipped: 120)");
+    const int l = element_bits + factor;
+    if (element_bits < 1 || factor < 0 || l > 32) return fail(FLASHE_EINVAL, "element_bits + factor must be in [1, 32]");
+    *lane = (uint32_t)l; *bs = (uint32_t)(ctx->int_bits / l);
+    if (*bs == 0) return fail(FLASHE_EINVAL, "int_bits smaller than one lane");
+    return FLASHE_OK;
+}
+
+int flashe_batch_pack(flashe_ctx* ctx, const uint32_t* q, uint64_t count, int element_bits, int factor, void* words_out, void* stream) {
+    ENTER(ctx);
+    uint32_t lane, bs; int rc = batch_geometry(ctx, element_bits, factor, &lane, &bs); if (rc) return rc;
+    if (count == 0) return FLASHE_OK;
+    if (!q || !words_out) return fail(FLASHE_EINVAL, "NULL buffer");
+    const uint64_t nw = ceil_div(count, bs);
+    k_batch_pack<<<grid_1d(ctx, nw, 256, 16), 256, 0, cs>>>(q, count, lane, bs, nw, (u128*)words_out);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+int flashe_batch_unpack(flashe_ctx* ctx, const void* words, uint64_t nwords, int element_bits, int factor, uint32_t* q_out, void* stream) {
+    ENTER(ctx);
+    uint32_t lane, bs; int rc = batch_geometry(ctx, element_bits, factor, &lane, &bs); if (rc) return rc;
+    if (nwords == 0) return FLASHE_OK;
+    if (!words || !q_out) return fail(FLASHE_EINVAL, "NULL buffer");
+    k_batch_unpack<<<grid_1d(ctx, nwords, 256, 16), 256, 0, cs>>>((const u128*)words, nwords, lane, bs, q_out);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+int flashe_sparse_expand(flashe_ctx* ctx, const void* compact, const int64_t* index, uint64_t k, uint64_t total, const void* zero_word,
+                         void* dense_out, void* stream) {
+    ENTER(ctx);
+    if (total == 0) return FLASHE_OK;
+    if (!dense_out || !zero_word || (k && (!compact || !index))) return fail(FLASHE_EINVAL, "NULL buffer");
+    if (k > total) return fail(FLASHE_EINVAL, "k exceeds total");
+    const int gf = grid_1d(ctx, total, 256, 16), gs = grid_1d(ctx, k, 256, 16);
+    if (ctx->words == 1) {
+        uint32_t z; memcpy(&z, zero_word, 4);
+        k_fill<1><<<gf, 256, 0, cs>>>((uint32_t*)dense_out, total, z);
+        if (k) k_scatter<1><<<gs, 256, 0, cs>>>((const uint32_t*)compact, index, k, total, (uint32_t*)dense_out);
+    } else if (ctx->words == 2) {
+        uint64_t z; memcpy(&z, zero_word, 8);
+        k_fill<2><<<gf, 256, 0, cs>>>((uint64_t*)dense_out, total, z);
+        if (k) k_scatter<2><<<gs, 256, 0, cs>>>((const uint64_t*)compact, index, k, total, (uint64_t*)dense_out);
+    } else {
+        u128 z; memcpy(&z, zero_word, 16);
+        k_fill<4><<<gf, 256, 0, cs>>>((u128*)dense_out, total, z);
+        if (k) k_scatter<4><<<gs, 256, 0, cs>>>((const u128*)compact, index, k, total, (u128*)dense_out);
+    }
+    g_launches.fetch_add(k ? 2 : 1);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+int flashe_sparse_apply_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf_idx, const int32_t* sign, int nstreams,
+                              const flashe_span* span, const int64_t* index, void* dense, void* stream) {
+    ENTER(ctx);
+    int rc = check_span(span); if (rc) return rc;
+    if (span->count == 0) return FLASHE_OK;
+    if (!index || !dense) return fail(FLASHE_EINVAL, "NULL buffer");
+    StreamTab st; rc = make_streams(ctx, iter, prf_idx, sign, nstreams, &st); if (rc) return rc;
+    Geom g; make_geom(ctx, span, &g);
+    IoDev io; memset(&io, 0, sizeof(io)); io.out = dense; io.aux = (void*)index; io.n_clients = 1;
+    CodecDev cd; memset(&cd, 0, sizeof(cd)); NoiseDev nz; memset(&nz, 0, sizeof(nz));
+    return launch_stream<M_SCATTER>(ctx, st, g, io, cd, nz, cs);
+}
+
+int flashe_sparse_overlap(flashe_ctx* ctx, const int64_t* const* index, const uint64_t* k, int n, uint64_t total, uint64_t* overlap_out,
+                          void* stream) {
+    ENTER(ctx);
+    (void)total;
+    if (n < 1 || !index || !k) return fail(FLASHE_EINVAL, "bad arguments");
+    if (n == 1) return FLASHE_OK;
+    if (!overlap_out) return fail(FLASHE_EINVAL, "overlap_out is NULL");
+    unsigned long long* d = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&d, sizeof(unsigned long long) * (size_t)(n - 1), cs));
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long) * (size_t)(n - 1), cs);
+    for (int i = 0; e == cudaSuccess && i + 1 < n; ++i) {
+        if (k[i] == 0 || k[i + 1] == 0) continue;
+        k_overlap<<<grid_1d(ctx, k[i], 256, 16), 256, 0, cs>>>(index[i], k[i], index[i + 1], k[i + 1], d + i);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(overlap_out, d, sizeof(unsigned long long) * (size_t)(n - 1), cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+    cudaFreeAsync(d, cs);
+    if (e != cudaSuccess) return fail(FLASHE_ECUDA, std::string("flashe_sparse_overlap: ") + cudaGetErrorString(e));
+    return FLASHE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,328 @@
+"""Tensor-native host API over the C ABI (torch supplies device memory and the current stream).
+
+This is the fast entry the benchmark and the drop-in classes share: every method enqueues CUDA
+kernels from libflashe_b200.so on torch's current stream of the context's device and returns torch
+tensors.  There is no CPU path here: constructing a DeviceContext without a CUDA device or without
+the built library raises.
+
+Word tensors: int_bits <= 32 -> torch.uint32 [L]; <= 64 -> torch.uint64 [L]; <= 128 -> torch.uint64
+[L, 2] (lo, hi).  Any tensor of the right byte size and contiguity is accepted as input (e.g. int32).
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _cabi
+from ._cabi import AGG_ELEMENTWISE, AGG_PACKED, SCHEME_DOUBLE, SCHEME_SINGLE  # noqa: F401
+
+
+@dataclass(frozen=True)
+class VectorSpan:
+    """Which elements of which chunked vector (include/flashe_b200.h: flashe_span)."""
+    total_len: int
+    n_jobs: int
+    begin: int = 0
+    count: Optional[int] = None
+
+    def c(self):
+        cnt = self.total_len - self.begin if self.count is None else self.count
+        return _cabi.Span(self.total_len, self.begin, cnt, self.n_jobs, 0)
+
+    @property
+    def n(self):
+        return self.total_len - self.begin if self.count is None else self.count
+
+
+@dataclass
+class CodecSpec:
+    """Encode/decode parameters (include/flashe_b200.h: flashe_codec).  `alpha` may be one Python
+    float (single layer) or a list with `seg_end` giving each layer's end offset in the flat vector."""
+    alpha: object
+    element_bits: int = 16
+    n_clients: int = 1
+    seg_end: Optional[Sequence[int]] = None
+
+    def c(self, total_len):
+        alphas = [float(self.alpha)] if not isinstance(self.alpha, (list, tuple)) else [float(a) for a in self.alpha]
+        ends = [int(total_len)] if self.seg_end is None else [int(e) for e in self.seg_end]
+        if len(alphas) != len(ends):
+            raise ValueError("alpha and seg_end must have the same length")
+        self._ends = (C.c_uint64 * len(ends))(*ends)        # keep alive for the call
+        self._alphas = (C.c_double * len(alphas))(*alphas)
+        return _cabi.Codec(self.element_bits, self.n_clients, len(ends), 0, self._ends, self._alphas)
+
+
+@dataclass
+class NoiseSpec:
+    """Stochastic-rounding noise: a float64 device tensor `u` (parity with np.random.random) or the
+    device generator keyed by (seed, stream)."""
+    u: Optional[torch.Tensor] = None
+    seed: int = 0
+    stream: int = 0
+
+    def c(self):
+        return _cabi.Noise(self.u.data_ptr() if self.u is not None else None, self.seed, self.stream)
+
+
+def _i32(xs):
+    return (C.c_int32 * max(1, len(xs)))(*[int(x) for x in xs])
+
+
+class DeviceContext(object):
+    """One (key, int_bits, device) context = flashe_ctx."""
+
+    def __init__(self, seed: bytes, int_bits: int, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("flashe_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _cabi.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("flashe_b200 contexts live on CUDA devices")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.empty(1, device=self.device)  # make sure the primary context exists
+        self.int_bits = int(int_bits)
+        seed = bytes(seed)
+        h = C.c_void_p()
+        buf = (C.c_uint8 * len(seed)).from_buffer_copy(seed)
+        _cabi.check(self.lib.flashe_ctx_create(buf, len(seed), self.int_bits, self.device.index, C.byref(h)))
+        self._h = h
+        self.word_bytes = self.lib.flashe_word_bytes(self.int_bits)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.flashe_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty_words(self, n, rows=None):
+        shape = [n] if rows is None else [rows, n]
+        if self.word_bytes == 4:
+            return torch.empty(shape, dtype=torch.uint32, device=self.device)
+        if self.word_bytes == 8:
+            return torch.empty(shape, dtype=torch.uint64, device=self.device)
+        return torch.empty(shape + [2], dtype=torch.uint64, device=self.device)
+
+    def zeros_words(self, n, rows=None):
+        shape = [n] if rows is None else [rows, n]
+        if self.word_bytes == 4:
+            return torch.zeros(shape, dtype=torch.int32, device=self.device).view(torch.uint32)
+        if self.word_bytes == 8:
+            return torch.zeros(shape, dtype=torch.int64, device=self.device).view(torch.uint64)
+        return torch.zeros(shape + [2], dtype=torch.int64, device=self.device).view(torch.uint64)
+
+    def words_from_ints(self, values):
+        """Sequence / object array of Python ints -> device word tensor (reduced mod 2^int_bits)."""
+        import numpy as np
+        v = np.asarray(values, dtype=object).reshape(-1) & ((1 << self.int_bits) - 1)
+        if self.word_bytes == 4:
+            host = torch.from_numpy(v.astype(np.uint32))
+        elif self.word_bytes == 8:
+            host = torch.from_numpy(v.astype(np.uint64))
+        else:
+            m64 = (1 << 64) - 1
+            host = torch.from_numpy(np.stack([(v & m64).astype(np.uint64), (v >> 64).astype(np.uint64)], axis=1))
+        return host.to(self.device)
+
+    def ints_from_words(self, t):
+        """Device word tensor -> object array of Python ints."""
+        a = t.cpu().numpy()
+        if self.word_bytes == 16:
+            a = a.reshape(-1, 2)
+            return a[:, 0].astype(object) | (a[:, 1].astype(object) << 64)
+        return a.reshape(-1).astype(object)
+
+    def _check_words(self, t, n, what):
+        if t.device != self.device:
+            raise ValueError("%s must live on %s" % (what, self.device))
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous" % what)
+        if t.numel() * t.element_size() != n * self.word_bytes:
+            raise ValueError("%s must hold %d words of %d bytes" % (what, n, self.word_bytes))
+        return t
+
+    def _check(self, t, dtype, n, what):
+        if t.device != self.device or t.dtype != dtype or not t.is_contiguous() or t.numel() != n:
+            raise ValueError("%s must be a contiguous %s tensor of %d elements on %s" % (what, dtype, n, self.device))
+        return t
+
+    # ------------------------------------------------------------------ primitives
+    def prp_block(self, block16: bytes) -> bytes:
+        out = (C.c_uint8 * 16)()
+        _cabi.check(self.lib.flashe_prp_block(self._h, (C.c_uint8 * 16).from_buffer_copy(bytes(block16)), out, self._stream()))
+        return bytes(out)
+
+    def masks(self, it, prf_idx, sign, span: VectorSpan, out=None):
+        out = self.empty_words(span.n) if out is None else self._check_words(out, span.n, "out")
+        _cabi.check(self.lib.flashe_masks(self._h, it & 0xFFFFFFFF, _i32(prf_idx), _i32(sign), len(prf_idx),
+                                          C.byref(span.c()), out.data_ptr(), self._stream()))
+        return out
+
+    def apply_masks(self, it, prf_idx, sign, words, span: VectorSpan, out=None):
+        self._check_words(words, span.n, "words")
+        out = torch.empty_like(words) if out is None else self._check_words(out, span.n, "out")
+        _cabi.check(self.lib.flashe_apply_masks(self._h, it & 0xFFFFFFFF, _i32(prf_idx), _i32(sign), len(prf_idx),
+                                                C.byref(span.c()), words.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def encrypt(self, it, idx, scheme, q, span: VectorSpan, out=None):
+        self._check_words(q, span.n, "q")
+        out = torch.empty_like(q) if out is None else self._check_words(out, span.n, "out")
+        _cabi.check(self.lib.flashe_encrypt(self._h, it & 0xFFFFFFFF, idx, scheme, C.byref(span.c()), q.data_ptr(),
+                                            out.data_ptr(), self._stream()))
+        return out
+
+    def decrypt(self, it, add_idx, minus_idx, agg, span: VectorSpan, out=None):
+        self._check_words(agg, span.n, "agg")
+        out = torch.empty_like(agg) if out is None else self._check_words(out, span.n, "out")
+        _cabi.check(self.lib.flashe_decrypt(self._h, it & 0xFFFFFFFF, _i32(add_idx), len(add_idx), _i32(minus_idx),
+                                            len(minus_idx), C.byref(span.c()), agg.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def add_premasked(self, words, mask, sign=1, out=None):
+        n = words.numel() * words.element_size() // self.word_bytes
+        self._check_words(words, n, "words"); self._check_words(mask, n, "mask")
+        out = torch.empty_like(words) if out is None else self._check_words(out, n, "out")
+        _cabi.check(self.lib.flashe_add_premasked(self._h, words.data_ptr(), mask.data_ptr(), sign, n, out.data_ptr(), self._stream()))
+        return out
+
+    def encode(self, x, codec: CodecSpec, noise: NoiseSpec, span: VectorSpan, out=None):
+        self._check(x, torch.float32, span.n, "x")
+        if noise.u is not None:
+            self._check(noise.u, torch.float64, span.n, "noise.u")
+        out = torch.empty(span.n, dtype=torch.uint32, device=self.device) if out is None else out
+        cc, nc = codec.c(span.total_len), noise.c()
+        _cabi.check(self.lib.flashe_encode(self._h, C.byref(span.c()), x.data_ptr(), C.byref(cc), C.byref(nc),
+                                           out.data_ptr(), self._stream()))
+        return out
+
+    def encode_encrypt(self, it, idx, scheme, x, codec: CodecSpec, noise: NoiseSpec, span: VectorSpan, out=None, q_out=None):
+        self._check(x, torch.float32, span.n, "x")
+        if noise.u is not None:
+            self._check(noise.u, torch.float64, span.n, "noise.u")
+        out = self.empty_words(span.n) if out is None else self._check_words(out, span.n, "out")
+        cc, nc = codec.c(span.total_len), noise.c()
+        _cabi.check(self.lib.flashe_encode_encrypt(self._h, it & 0xFFFFFFFF, idx, scheme, C.byref(span.c()), x.data_ptr(),
+                                                   C.byref(cc), C.byref(nc), out.data_ptr(),
+                                                   q_out.data_ptr() if q_out is not None else None, self._stream()))
+        return out
+
+    def encode_encrypt_batch(self, it, idx0, scheme, x, codec: CodecSpec, noise: NoiseSpec, span: VectorSpan, out=None,
+                             share_streams=False):
+        """x: float32 [n_clients, span.n]; returns words [n_clients, span.n]."""
+        if x.dim() != 2 or x.shape[1] != span.n or x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device:
+            raise ValueError("x must be a contiguous float32 [n_clients, count] tensor on %s" % self.device)
+        n = x.shape[0]
+        if noise.u is not None:
+            self._check(noise.u, torch.float64, n * span.n, "noise.u")
+        out = self.empty_words(span.n, rows=n) if out is None else self._check_words(out, n * span.n, "out")
+        cc, nc = codec.c(span.total_len), noise.c()
+        _cabi.check(self.lib.flashe_encode_encrypt_batch(self._h, it & 0xFFFFFFFF, idx0, n, scheme, C.byref(span.c()),
+                                                         x.data_ptr(), span.n, C.byref(cc), C.byref(nc), span.n,
+                                                         out.data_ptr(), span.n, 1 if share_streams else 0, self._stream()))
+        return out
+
+    def encode_add_premasked(self, x, codec: CodecSpec, noise: NoiseSpec, mask, span: VectorSpan, out=None):
+        self._check(x, torch.float32, span.n, "x")
+        self._check_words(mask, span.n, "mask")
+        out = self.empty_words(span.n) if out is None else self._check_words(out, span.n, "out")
+        cc, nc = codec.c(span.total_len), noise.c()
+        _cabi.check(self.lib.flashe_encode_add_premasked(self._h, C.byref(span.c()), x.data_ptr(), C.byref(cc), C.byref(nc),
+                                                         mask.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def aggregate(self, cts, mode=AGG_ELEMENTWISE, carry_in=0, out=None, carry_out=None):
+        """cts: words [n, L] (+[,2]); returns words [L]."""
+        n = cts.shape[0]
+        L = cts.shape[1]
+        self._check_words(cts, n * L, "cts")
+        out = self.empty_words(L) if out is None else self._check_words(out, L, "out")
+        _cabi.check(self.lib.flashe_aggregate(self._h, cts.data_ptr(), L, n, L, mode, carry_in, out.data_ptr(),
+                                              carry_out.data_ptr() if carry_out is not None else None, self._stream()))
+        return out
+
+    def aggregate_carry_fixup(self, out, carry_in):
+        n = out.numel() * out.element_size() // self.word_bytes
+        _cabi.check(self.lib.flashe_aggregate_carry_fixup(self._h, out.data_ptr(), n, carry_in, self._stream()))
+        return out
+
+    def decode(self, v, codec: CodecSpec, span: VectorSpan, out=None):
+        self._check_words(v, span.n, "v")
+        out = torch.empty(span.n, dtype=torch.float64, device=self.device) if out is None else out
+        cc = codec.c(span.total_len)
+        _cabi.check(self.lib.flashe_decode(self._h, C.byref(span.c()), v.data_ptr(), C.byref(cc), out.data_ptr(), self._stream()))
+        return out
+
+    def decrypt_decode(self, it, add_idx, minus_idx, agg, codec: CodecSpec, span: VectorSpan, out=None, p_out=None):
+        self._check_words(agg, span.n, "agg")
+        out = torch.empty(span.n, dtype=torch.float64, device=self.device) if out is None else out
+        cc = codec.c(span.total_len)
+        _cabi.check(self.lib.flashe_decrypt_decode(self._h, it & 0xFFFFFFFF, _i32(add_idx), len(add_idx), _i32(minus_idx),
+                                                   len(minus_idx), C.byref(span.c()), agg.data_ptr(), C.byref(cc),
+                                                   out.data_ptr(), p_out.data_ptr() if p_out is not None else None,
+                                                   self._stream()))
+        return out
+
+    def rng_uniform(self, seed, stream, begin, count, out=None):
+        out = torch.empty(count, dtype=torch.float64, device=self.device) if out is None else out
+        _cabi.check(self.lib.flashe_rng_uniform(self._h, seed, stream, begin, count, out.data_ptr(), self._stream()))
+        return out
+
+    def batch_pack(self, q, element_bits, factor):
+        self._check(q, torch.uint32, q.numel(), "q")
+        bs = self.int_bits // (element_bits + factor)
+        nw = (q.numel() + bs - 1) // bs
+        out = self.empty_words(nw)
+        _cabi.check(self.lib.flashe_batch_pack(self._h, q.data_ptr(), q.numel(), element_bits, factor, out.data_ptr(), self._stream()))
+        return out
+
+    def batch_unpack(self, words, element_bits, factor):
+        nw = words.shape[0]
+        self._check_words(words, nw, "words")
+        bs = self.int_bits // (element_bits + factor)
+        out = torch.empty(nw * bs, dtype=torch.uint32, device=self.device)
+        _cabi.check(self.lib.flashe_batch_unpack(self._h, words.data_ptr(), nw, element_bits, factor, out.data_ptr(), self._stream()))
+        return out
+
+    def sparse_expand(self, compact, index, total, zero: int):
+        k = index.numel()
+        self._check(index, torch.int64, k, "index")
+        self._check_words(compact, k, "compact")
+        out = self.empty_words(total)
+        z = int(zero).to_bytes(self.word_bytes, "little")
+        zb = (C.c_uint8 * self.word_bytes).from_buffer_copy(z)
+        _cabi.check(self.lib.flashe_sparse_expand(self._h, compact.data_ptr(), index.data_ptr(), k, total, zb, out.data_ptr(), self._stream()))
+        return out
+
+    def sparse_apply_masks(self, it, prf_idx, sign, span: VectorSpan, index, dense):
+        self._check(index, torch.int64, span.n, "index")
+        _cabi.check(self.lib.flashe_sparse_apply_masks(self._h, it & 0xFFFFFFFF, _i32(prf_idx), _i32(sign), len(prf_idx),
+                                                       C.byref(span.c()), index.data_ptr(), dense.data_ptr(), self._stream()))
+        return dense
+
+    def sparse_overlap(self, index_lists, total):
+        n = len(index_lists)
+        if n < 2:
+            return []
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in index_lists])
+        ks = (C.c_uint64 * n)(*[t.numel() for t in index_lists])
+        out = (C.c_uint64 * (n - 1))()
+        _cabi.check(self.lib.flashe_sparse_overlap(self._h, ptrs, ks, n, total, out, self._stream()))
+        return [int(v) for v in out]
+
+
+def launch_count():
+    return int(_cabi.load().flashe_launch_count())

@@ -1,0 +1,303 @@
+"""`FlasheCipher` — drop-in for federatedml/secureprotol/jzf_flashe.py:228-666, backed by the CUDA
+library.  Same constructor, attributes, methods, call-order state machine and error behaviour
+(encrypt/decrypt return None without a key or for a non-ndarray argument); the arithmetic runs on
+the GPU through the C ABI (flashe_b200/_cabi.py) — there is no CPU path.
+
+Inputs / outputs are what the reference traffics in: 1-D numpy object arrays of non-negative Python
+ints (< 2^int_bits).  Torch CUDA tensors holding words are accepted too and then returned as tensors
+(no host round trip): that is the fast entry the FATE glue would use once weights live on the GPU.
+
+Differences from the reference, all deliberate:
+  * `n_jobs` is explicit state.  The reference derives AES counters from the chunking of the vector
+    over N_JOBS = cpu_count() workers (jzf_flashe.py:7,12-16,33-34), so ciphertexts depend on the
+    core count of the encrypting host.  Here N_JOBS defaults to cpu_count() too (same ciphertexts as
+    the reference on the same host) but is a constructor argument / attribute.
+  * prepare_decrypt() + dropout of client 0 or n-1: the reference never retracts the precomputed
+    F(t,0) / F(t,n) terms and decrypts wrongly (SURVEY §0.5 probe P8).  Here the run-boundary rule is
+    applied exactly, so precomputed == on-the-fly always.
+  * masking_scheme "double" together with sparse masks crashes in the reference
+    (jzf_flashe.py:412-415,192); here it raises NotImplementedError naming that.
+"""
+import os
+from multiprocessing import cpu_count
+
+import numpy as np
+import torch
+
+from ..device import SCHEME_DOUBLE, SCHEME_SINGLE, DeviceContext, VectorSpan
+from .encrypt import Encrypt
+
+N_JOBS = cpu_count()          # jzf_flashe.py:7
+BITS_PER_BYTES = 8
+
+
+def collapse_runs(raw_idx_list):
+    """set_idx_list(mode="decrypt"), jzf_flashe.py:356-367: sort the survivors; every maximal run
+    [a..b] yields minus-index a and add-index b+1."""
+    idx_list = sorted(int(i) for i in raw_idx_list)
+    temp_add, temp_minus = [], []
+    for idx in idx_list:
+        if temp_add and idx == temp_add[-1]:
+            temp_add[-1] = idx + 1
+        else:
+            temp_add.append(idx + 1)
+            temp_minus.append(idx)
+    return temp_add, temp_minus
+
+
+class FlasheCipher(Encrypt):
+
+    def __init__(self, int_bits, mask="double", device=None, n_jobs=None):
+        super(FlasheCipher, self).__init__()
+        self.uuid = None
+        self.exchanged_keys = None
+        self.masking_scheme = mask
+        self.masks = None
+        self.total = None
+
+        self.prp_seed = None
+        self.prp_seed_len = 256
+        self.guest_uuid = None
+
+        self.idx = None
+        self.index_prefix_for_add = None
+        self.index_prefix_for_minus = None
+
+        self.iter_index = -1
+        self.iter_index_bytes = None
+
+        self.int_bits = int_bits
+        self.n_jobs = N_JOBS if n_jobs is None else int(n_jobs)
+        self.device = device
+
+        self.num_clients = None
+        self.next_iter_encrypt_prepared = {}
+        self.next_iter_decrypt_prepared = {}
+        self.next_iter_decrypt_prepared_idx = {}
+        self.num_params = None
+
+        self.encrypt_base = 0
+        self.decrypt_base = 0
+
+        self._ctx = None
+        self._retract = ([], [])   # (add, minus) index lists that undo precomputed decrypt terms
+
+    # ------------------------------------------------------------------ bookkeeping (jzf_flashe.py:262-304)
+    def set_num_clients(self, num_clients):
+        self.num_clients = num_clients
+
+    def set_self_uuid(self, uuid):
+        self.uuid = uuid
+
+    def set_exchanged_keys(self, exchanged_keys):
+        self.exchanged_keys = exchanged_keys
+        for k, v in exchanged_keys.items():
+            if k == self.uuid:
+                self.idx = v[0]
+            elif v[2] == "guest":
+                self.guest_uuid = k
+
+    def get_guest_uuid(self):
+        return self.guest_uuid
+
+    def generate_prp_seed(self, assigned_seed=None):
+        """jzf_flashe.py:280-295.  A fresh seed is 32 random bytes; an assigned one (int or bytes) is
+        stored as its 256-BYTE big-endian form; the AES key is the low 32 bytes either way
+        (jzf_aes.py:21-28, done inside flashe_ctx_create)."""
+        if assigned_seed is None:
+            seed = os.urandom(self.prp_seed_len // BITS_PER_BYTES)
+        elif isinstance(assigned_seed, int):
+            seed = int(assigned_seed & int(2 ** self.prp_seed_len - 1)).to_bytes(self.prp_seed_len, 'big')
+        else:
+            seed = int(int.from_bytes(assigned_seed, 'big') & int(2 ** self.prp_seed_len - 1)).to_bytes(
+                self.prp_seed_len, 'big')
+        self.prp_seed = seed
+        if self._ctx is not None:
+            self._ctx.close()
+        self._ctx = DeviceContext(seed, self.int_bits, self.device)
+
+    def get_prp_seed(self):
+        return self.prp_seed
+
+    def set_iter_index(self, iter_index):
+        self.encrypt_base = 0
+        self.decrypt_base = 0
+        self.iter_index = iter_index
+        self.iter_index_bytes = iter_index.to_bytes(4, 'big')
+
+    def get_idx_list(self):
+        return [self.idx]
+
+    def set_num_params(self, num_params):
+        self.num_params = num_params
+
+    # ------------------------------------------------------------------ array <-> device words
+    def _mask_int(self):
+        return (1 << self.int_bits) - 1
+
+    def _to_device(self, value):
+        if isinstance(value, torch.Tensor):
+            return value
+        v = np.asarray(value)
+        if not (v.dtype == object or v.dtype.kind in "iu"):
+            raise TypeError("FlasheCipher works on integer arrays")
+        return self._ctx.words_from_ints(v)
+
+    def _to_host(self, t, like):
+        if isinstance(like, torch.Tensor):
+            return t
+        return self._ctx.ints_from_words(t)
+
+    def _span(self, n):
+        return VectorSpan(total_len=int(n), n_jobs=self.n_jobs)
+
+    @staticmethod
+    def _len(value):
+        if isinstance(value, torch.Tensor):
+            return value.shape[0]
+        return len(value)
+
+    @staticmethod
+    def _prefix_idx(prefix):
+        return int.from_bytes(prefix[4:], 'big')
+
+    # ------------------------------------------------------------------ index sets (jzf_flashe.py:306-426)
+    def set_idx_list_single(self, raw_idx_list=None, mode="encrypt"):
+        if mode == "encrypt":
+            self.index_prefix_for_add = self.iter_index_bytes + self.idx.to_bytes(4, 'big')
+        elif self.masks is None:
+            self.index_prefix_for_minus = [self.iter_index_bytes + idx.to_bytes(4, 'big') for idx in raw_idx_list]
+        else:
+            # jzf_flashe.py:315-343: per client, F(t, client) over its COMPACT positions, scattered
+            # to dense and summed mod 2^b.
+            ctx = self._ctx
+            dense = ctx.zeros_words(int(self.total))
+            for client_idx, mask in enumerate(self.masks):
+                index = mask if isinstance(mask, torch.Tensor) else torch.as_tensor(np.asarray(mask, dtype=np.int64))
+                index = index.to(ctx.device)
+                ctx.sparse_apply_masks(self.iter_index, [client_idx], [1], self._span(index.numel()), index, dense)
+            self.next_iter_decrypt_prepared["minus"] = dense
+
+    def set_idx_list(self, raw_idx_list=None, mode="encrypt"):
+        if self.masking_scheme == "single":
+            return self.set_idx_list_single(raw_idx_list, mode)
+
+        if mode == "encrypt":
+            self.index_prefix_for_add = self.iter_index_bytes + self.idx.to_bytes(4, 'big')
+            self.index_prefix_for_minus = self.iter_index_bytes + (self.idx + 1).to_bytes(4, 'big')
+            return
+        if self.masks is not None:
+            raise NotImplementedError(
+                "double masking with sparse masks is unfinished in the reference (jzf_flashe.py:412-415 slices "
+                "the per-client list, :192 then fails with 'NoneType' has no attribute 'tolist'); use mask='single'")
+        temp_add, temp_minus = collapse_runs(raw_idx_list)
+        pre_add = self.next_iter_decrypt_prepared_idx.get('add', [])
+        pre_minus = self.next_iter_decrypt_prepared_idx.get('minus', [])
+        self.index_prefix_for_add = [self.iter_index_bytes + i.to_bytes(4, 'big') for i in temp_add if i not in pre_add]
+        self.index_prefix_for_minus = [self.iter_index_bytes + i.to_bytes(4, 'big') for i in temp_minus if i not in pre_minus]
+        # exact run-boundary rule: precomputed terms that the survivor set does not call for are
+        # retracted (the reference omits this and is wrong when client 0 or n-1 dropped)
+        self._retract = ([i for i in pre_minus if i not in temp_minus],   # re-add a precomputed minus
+                         [i for i in pre_add if i not in temp_add])       # subtract a precomputed add
+
+    # ------------------------------------------------------------------ encrypt (jzf_flashe.py:431-504)
+    def _multiprocessing_encrypt_single(self, value):
+        ctx = self._ctx
+        q = self._to_device(value)
+        ct = ctx.encrypt(self.iter_index, self._prefix_idx(self.index_prefix_for_add), SCHEME_SINGLE, q,
+                         self._span(self._len(value)))
+        self.next_iter_encrypt_prepared.pop('add', None)
+        return self._to_host(ct, value)
+
+    def _multiprocessing_encrypt(self, value):
+        ctx = self._ctx
+        q = self._to_device(value)
+        if 'add' not in self.next_iter_encrypt_prepared:
+            ct = ctx.encrypt(self.iter_index, self._prefix_idx(self.index_prefix_for_add), SCHEME_DOUBLE, q,
+                             self._span(self._len(value)))
+        else:
+            # masks generated ahead of time by prepare_encrypt(); 'add' holds F(t,c) - F(t,c+1)
+            ct = ctx.add_premasked(q, self.next_iter_encrypt_prepared['add'], +1)
+        self.next_iter_encrypt_prepared.pop('add', None)
+        self.next_iter_encrypt_prepared.pop('minus', None)
+        return self._to_host(ct, value)
+
+    def encrypt(self, plaintext):
+        if self.prp_seed is None:
+            return None
+        if self.masking_scheme == "double":
+            self.set_idx_list(mode="encrypt")
+        else:
+            self.set_idx_list_single(mode="encrypt")
+        if not isinstance(plaintext, (np.ndarray, torch.Tensor)):
+            return None
+        if self.masking_scheme == "double":
+            return self._multiprocessing_encrypt(plaintext)
+        return self._multiprocessing_encrypt_single(plaintext)
+
+    # ------------------------------------------------------------------ decrypt (jzf_flashe.py:506-594)
+    def _multiprocessing_decrypt_single(self, value):
+        ctx = self._ctx
+        agg = self._to_device(value)
+        if self.masks is None:
+            minus = [self._prefix_idx(p) for p in self.index_prefix_for_minus]
+            out = agg
+            # at most FLASHE_MAX_STREAMS streams per launch; an empty survivor list leaves the
+            # value unchanged, as the reference's empty sum does
+            for k in range(0, len(minus), 128):
+                out = ctx.decrypt(self.iter_index, [], minus[k:k + 128], out, self._span(self._len(value)))
+        else:
+            out = ctx.add_premasked(agg, self.next_iter_decrypt_prepared['minus'], -1)
+        self.next_iter_decrypt_prepared.pop('minus', None)
+        return self._to_host(out, value)
+
+    def _multiprocessing_decrypt(self, value):
+        if self.masks is not None:
+            raise NotImplementedError("double masking with sparse masks: see set_idx_list")
+        ctx = self._ctx
+        agg = self._to_device(value)
+        span = self._span(self._len(value))
+        add = [self._prefix_idx(p) for p in (self.index_prefix_for_add or [])] + list(self._retract[0])
+        minus = [self._prefix_idx(p) for p in (self.index_prefix_for_minus or [])] + list(self._retract[1])
+        out = agg
+        if 'add' in self.next_iter_decrypt_prepared:
+            # 'add' holds the combined precomputed term F(t,n) - F(t,0)
+            out = ctx.add_premasked(out, self.next_iter_decrypt_prepared['add'], +1)
+        elif not add and not minus:
+            raise KeyError('add')   # the reference indexes next_iter_decrypt_prepared['add'] here
+        if add or minus:
+            out = ctx.decrypt(self.iter_index, add, minus, out, span)
+        for d in (self.next_iter_decrypt_prepared, self.next_iter_decrypt_prepared_idx):
+            d.pop('add', None)
+            d.pop('minus', None)
+        self._retract = ([], [])
+        return self._to_host(out, value)
+
+    def decrypt(self, ciphertext):
+        if self.prp_seed is None:
+            return None
+        if not isinstance(ciphertext, (np.ndarray, torch.Tensor)):
+            return None
+        if self.masking_scheme == "double":
+            return self._multiprocessing_decrypt(ciphertext)
+        return self._multiprocessing_decrypt_single(ciphertext)
+
+    # ------------------------------------------------------------------ precompute (jzf_flashe.py:596-666)
+    def prepare_encrypt(self):
+        """Masks for the NEXT round (iter_index + 1) over num_params elements.  The reference keeps
+        'add' and 'minus' as two object arrays; here 'add' is the combined device buffer
+        (F(t+1,c) - F(t+1,c+1)) mod 2^b and 'minus' is None — the ciphertext is identical."""
+        it = self.iter_index + 1
+        self.next_iter_encrypt_prepared = {
+            'add': self._ctx.masks(it, [self.idx, self.idx + 1], [1, -1], self._span(self.num_params)),
+            'minus': None,
+        }
+
+    def prepare_decrypt(self):
+        """F(t, n) - F(t, 0) for THIS round, ahead of the download (jzf_flashe.py:633-666)."""
+        self.next_iter_decrypt_prepared = {
+            'add': self._ctx.masks(self.iter_index, [self.num_clients, 0], [1, -1], self._span(self.num_params)),
+            'minus': None,
+        }
+        self.next_iter_decrypt_prepared_idx['add'] = [self.num_clients]
+        self.next_iter_decrypt_prepared_idx['minus'] = [0]

@@ -1,0 +1,459 @@
+"""GPU parity: the CUDA path (through the C ABI) against the committed reference outputs
+(tests/golden) and against the CPU oracle on seeded inputs.  Bit-exact for every integer; decoded
+float64 compared bit for bit (tolerance 0)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+KEY = bytes(range(32))
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def _dev(a, device="cuda"):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import flashe_b200
+    return flashe_b200
+
+
+def ctx_for(fb, bits, key=KEY):
+    return fb.DeviceContext(key, bits)
+
+
+# ---------------------------------------------------------------------------------------- AES
+def test_prp_fips197_and_random_blocks(fb):
+    ctx = ctx_for(fb, 32)
+    pt = bytes.fromhex("00112233445566778899aabbccddeeff")
+    assert ctx.prp_block(pt).hex() == "8ea2b7ca516745bfeafc49904b496089"
+    rs = np.random.RandomState(5)
+    for _ in range(20):
+        blk = bytes(rs.randint(0, 256, 16).astype(np.uint8))
+        if rs.rand() < 0.5:
+            blk = blk[:8] + bytes(4) + blk[12:]      # word 2 == 0: the hoisted round-1 path
+        assert ctx.prp_block(blk) == O.aes256_encrypt_block(KEY, blk)
+    long_seed = bytes(224) + KEY                     # hosts carry a 256-byte padded copy of the seed
+    assert fb.DeviceContext(long_seed, 32).prp_block(pt) == ctx.prp_block(pt)
+
+
+# ---------------------------------------------------------------------------------------- masks
+def test_masks_golden(fb, golden):
+    for c in golden.cases("masks"):
+        b = c["int_bits"]
+        ctx = ctx_for(fb, b)
+        span = fb.VectorSpan(c["L"], c["n_jobs"])
+        got = _np(ctx.masks(c["iter"], [c["prf_idx"]], [1], span))
+        assert np.array_equal(got, golden.words(c["name"], b)), c
+
+
+@pytest.mark.parametrize("bits,n_jobs,L", [(20, 8, 100003), (32, 1024, 250000), (24, 3, 7777), (64, 8, 30011),
+                                           (120, 8, 20001), (12, 8, 9999), (33, 5, 5000), (20, 64, 50)])
+def test_masks_vs_oracle_multistream_and_shards(fb, bits, n_jobs, L):
+    ctx = ctx_for(fb, bits)
+    idx, sign = [3, 4, 9, 0], [1, -1, -1, 1]
+    want = O.masks(KEY, bits, n_jobs, 7, idx, sign, L)
+    got = _np(ctx.masks(7, idx, sign, fb.VectorSpan(L, n_jobs)))
+    assert np.array_equal(got, want)
+    # element-range shards (multi-GPU layout): 3 uneven pieces, arbitrary (unaligned) cuts
+    cuts = [0, L // 3 + 1, (2 * L) // 3 + 2, L]
+    for a, e in zip(cuts[:-1], cuts[1:]):
+        part = _np(ctx.masks(7, idx, sign, fb.VectorSpan(L, n_jobs, a, e - a)))
+        assert np.array_equal(part, want[a:e]), (a, e)
+    # empty shard is a no-op
+    assert ctx.masks(7, idx, sign, fb.VectorSpan(L, n_jobs, 5, 0)).numel() == 0
+
+
+def test_counter_above_2_32_uses_generic_round1(fb):
+    # chunk begins beyond 2^32: the AES counter's high word is non-zero
+    ctx = ctx_for(fb, 32)
+    L, n_jobs = (1 << 33) + 1000, 2
+    begin = (1 << 32) + 517          # inside chunk 1 (starts at 2^32 + 500)
+    got = _np(ctx.masks(1, [2], [1], fb.VectorSpan(L, n_jobs, begin, 4096)))
+    want = O.masks(KEY, 32, n_jobs, 1, [2], [1], L, begin, 4096)
+    assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------- golden round trips
+def test_roundtrip_golden(fb, golden):
+    for c in golden.cases("roundtrip"):
+        name, b, nj, L, n, it, scheme = (c[k] for k in ("name", "int_bits", "n_jobs", "L", "n_clients", "iter", "scheme"))
+        ctx = ctx_for(fb, b)
+        span = fb.VectorSpan(L, nj)
+        sch = fb.SCHEME_DOUBLE if scheme == "double" else fb.SCHEME_SINGLE
+        codec = fb.CodecSpec(alpha=c["alpha"], element_bits=c["element_bits"], n_clients=n)
+        x, u = _dev(golden[name + "_x"]), _dev(golden[name + "_u"])
+        q_ref = golden.words(name + "_q", 32).reshape(n, L)
+        ct_ref = golden.words(name + "_ct", b).reshape(n, L)
+        cts = ctx.empty_words(L, rows=n)
+        for k in range(n):
+            q_out = torch.empty(L, dtype=torch.uint32, device="cuda")
+            ctx.encode_encrypt(it, k, sch, x[k], codec, fb.NoiseSpec(u=u[k]), span, out=cts[k], q_out=q_out)
+            assert np.array_equal(_np(q_out), q_ref[k]), (name, k)
+            assert np.array_equal(_np(ctx.encode(x[k], codec, fb.NoiseSpec(u=u[k]), span)), q_ref[k])
+            assert np.array_equal(_np(ctx.encrypt(it, k, sch, _dev(q_ref[k].astype(ct_ref.dtype)), span)), ct_ref[k])
+        assert np.array_equal(_np(cts), ct_ref), name
+        # all clients in one launch, with and without stream sharing
+        for share in (False, True):
+            got = ctx.encode_encrypt_batch(it, 0, sch, x, codec, fb.NoiseSpec(u=u.reshape(-1)), span, share_streams=share)
+            assert np.array_equal(_np(got), ct_ref), (name, share)
+        agg_b = ctx.aggregate(cts, fb.AGG_ELEMENTWISE)
+        agg_a = ctx.aggregate(cts, fb.AGG_PACKED)
+        assert np.array_equal(_np(agg_b), golden.words(name + "_aggB", b)), name
+        assert np.array_equal(_np(agg_a), golden.words(name + "_aggA", b)), name
+        if scheme == "double":
+            add, minus = [n], [0]
+        else:
+            add, minus = [], list(range(n))
+        for tag, agg in (("B", agg_b), ("A", agg_a)):
+            dec = ctx.decrypt(it, add, minus, agg, span)
+            assert np.array_equal(_np(dec), golden.words(name + "_dec" + tag, b)), (name, tag)
+        p_out = ctx.empty_words(L)
+        decoded = ctx.decrypt_decode(it, add, minus, agg_b, codec, span, p_out=p_out)
+        assert np.array_equal(_np(p_out), golden.words(name + "_decB", b))
+        assert np.array_equal(_np(decoded).view(np.uint64), golden[name + "_decoded"].view(np.uint64)), name
+        assert np.array_equal(_np(ctx.decode(p_out, codec, span)).view(np.uint64), golden[name + "_decoded"].view(np.uint64))
+
+
+def test_dropout_golden(fb, golden):
+    from flashe_b200.secureprotol.flashe import collapse_runs
+    cases = golden.cases("dropout")
+    c0 = cases[0]
+    b, nj, L, n, it = (c0[k] for k in ("int_bits", "n_jobs", "L", "n_clients", "iter"))
+    ctx = ctx_for(fb, b)
+    span = fb.VectorSpan(L, nj)
+    ct = _dev(golden.words("drop_ct", b).reshape(n, L))
+    for c in cases:
+        add, minus = collapse_runs(c["survivors"])
+        assert add == c["add"] and minus == c["minus"]
+        rows = ct[sorted(c["survivors"])].contiguous()
+        agg = ctx.aggregate(rows)
+        assert np.array_equal(_np(agg), golden.words(c["name"] + "_agg", b))
+        assert np.array_equal(_np(ctx.decrypt(it, add, minus, agg, span)), golden.words(c["name"] + "_dec", b))
+
+
+def test_precompute_golden(fb, golden):
+    c = golden.cases("precompute")[0]
+    b, nj, L, n, it, idx = (c[k] for k in ("int_bits", "n_jobs", "L", "n_clients", "iter", "idx"))
+    ctx = ctx_for(fb, b)
+    span = fb.VectorSpan(L, nj)
+    assert np.array_equal(_np(ctx.masks(it, [idx], [1], span)), golden.words("pre_enc_add", b))
+    assert np.array_equal(_np(ctx.masks(it, [idx + 1], [1], span)), golden.words("pre_enc_minus", b))
+    assert np.array_equal(_np(ctx.masks(it, [n], [1], span)), golden.words("pre_dec_add", b))
+    assert np.array_equal(_np(ctx.masks(it, [0], [1], span)), golden.words("pre_dec_minus", b))
+    combined = ctx.masks(it, [idx, idx + 1], [1, -1], span)
+    q = _dev(golden.words("pre_q", 32))
+    assert np.array_equal(_np(ctx.add_premasked(q, combined, +1)), golden.words("pre_ct", b))
+    assert np.array_equal(_np(ctx.add_premasked(_dev(golden.words("pre_ct", b)), combined, -1)), golden.words("pre_q", 32))
+
+
+def test_sparse_single_golden(fb, golden):
+    c = golden.cases("sparse")[0]
+    b, nj, n, it, total = (c[k] for k in ("int_bits", "n_jobs", "n_clients", "iter", "total"))
+    ctx = ctx_for(fb, b)
+    idx = [_dev(golden["sparse_mask_%d" % k]) for k in range(n)]
+    dense = []
+    for k in range(n):
+        q = _dev(golden.words("sparse_q_%d" % k, 32))
+        ct = ctx.encrypt(it, k, fb.SCHEME_SINGLE, q, fb.VectorSpan(q.numel(), nj))
+        assert np.array_equal(_np(ct), golden.words("sparse_ct_%d" % k, b))
+        dense.append(ctx.sparse_expand(ct, idx[k], total, int(golden["sparse_zero"][k])))
+    agg = ctx.aggregate(torch.stack([d.view(torch.int32) for d in dense]))
+    assert np.array_equal(_np(agg), golden.words("sparse_agg", b))
+    minus = ctx.zeros_words(total)
+    for k in range(n):
+        ctx.sparse_apply_masks(it, [k], [1], fb.VectorSpan(idx[k].numel(), nj), idx[k], minus)
+    dec = ctx.add_premasked(agg, minus, -1)
+    assert np.array_equal(_np(dec), golden.words("sparse_dec", b))
+    # overlap counts behind dynamic_masking
+    want = [len(set(_np(idx[i]).tolist()) & set(_np(idx[i + 1]).tolist())) for i in range(n - 1)]
+    assert ctx.sparse_overlap(idx, total) == want
+
+
+def test_batch120_golden(fb, golden):
+    c = golden.cases("batch")[0]
+    b, nj, L, n, it, e, f = (c[k] for k in ("int_bits", "n_jobs", "L", "n_clients", "iter", "element_bits", "factor"))
+    nw = c["words"]
+    ctx = ctx_for(fb, b)
+    span = fb.VectorSpan(nw, nj)
+    codec = fb.CodecSpec(alpha=c["alpha"], element_bits=e, n_clients=n)
+    ct_ref = golden.words("batch_ct", b).reshape(n, nw, 2)
+    w_ref = golden.words("batch_w", b).reshape(n, nw, 2)
+    cts = ctx.empty_words(nw, rows=n)
+    for k in range(n):
+        q = ctx.encode(_dev(golden["batch_x"][k]), codec, fb.NoiseSpec(u=_dev(golden["batch_u"][k])), fb.VectorSpan(L, 1))
+        w = ctx.batch_pack(q, e, f)
+        assert np.array_equal(_np(w), w_ref[k])
+        ctx.encrypt(it, k, fb.SCHEME_DOUBLE, w, span, out=cts[k])
+    assert np.array_equal(_np(cts), ct_ref)
+    agg = ctx.aggregate(cts)
+    assert np.array_equal(_np(agg), golden.words("batch_agg", b))
+    dec = ctx.decrypt(it, [n], [0], agg, span)
+    assert np.array_equal(_np(dec), golden.words("batch_dec", b))
+    unb = ctx.batch_unpack(dec, e, f)[:L].contiguous()
+    assert np.array_equal(_np(unb), golden.words("batch_unb", 32))
+    out = fb.DeviceContext(KEY, 32).decode(unb, codec, fb.VectorSpan(L, 1))
+    assert np.array_equal(_np(out).view(np.uint64), golden["batch_decoded"].view(np.uint64))
+
+
+def test_quant_edges_golden(fb, golden):
+    c = golden.cases("quant_edges")[0]
+    L = c["L"]
+    ctx = ctx_for(fb, 32)
+    q_ref = golden.words("qe_q", 32).reshape(3, L)
+    x = _dev(golden["qe_x"])
+    for k, (alpha, e) in enumerate(zip(c["alphas"], c["element_bits"])):
+        q = ctx.encode(x, fb.CodecSpec(alpha=alpha, element_bits=e), fb.NoiseSpec(u=_dev(golden["qe_u"][k])), fb.VectorSpan(L, 1))
+        assert np.array_equal(_np(q), q_ref[k]), k
+    d = golden.cases("decode")[0]
+    v = _dev(golden.words("qd_v", 32))
+    out = ctx.decode(v, fb.CodecSpec(alpha=d["alpha"], element_bits=d["element_bits"], n_clients=d["n_clients"]), fb.VectorSpan(v.numel(), 1))
+    assert np.array_equal(_np(out).view(np.uint64), golden["qd_out"].view(np.uint64))
+
+
+# ---------------------------------------------------------------------------------------- seeded, vs oracle
+@pytest.mark.parametrize("bits,n_jobs,L,n", [(20, 8, 300007, 3), (32, 1024, 400001, 4), (22, 16, 123457, 5)])
+def test_full_path_vs_oracle(fb, bits, n_jobs, L, n):
+    """encode+encrypt (layered alphas, device noise) -> aggregate (B and A) -> decrypt+decode."""
+    ctx = ctx_for(fb, bits)
+    span = fb.VectorSpan(L, n_jobs)
+    seg_end = [L // 5, L // 2, L]
+    alphas = [0.59383450, 0.25, 1.0]
+    codec = fb.CodecSpec(alpha=alphas, element_bits=16, n_clients=n, seg_end=seg_end)
+    it = 11
+    rs = np.random.RandomState(77)
+    x = (rs.standard_normal((n, L)) * 0.2).astype(np.float32)
+    x_d = _dev(x)
+    cts = ctx.encode_encrypt_batch(it, 0, fb.SCHEME_DOUBLE, x_d, codec, fb.NoiseSpec(seed=0xABCDEF0123, stream=100), span)
+    # oracle consumes the very noise the device generated
+    ct_want = []
+    for k in range(n):
+        u = _np(ctx.rng_uniform(0xABCDEF0123, 100 + k, 0, L))
+        assert u.min() >= 0.0 and u.max() < 1.0
+        q = np.empty(L, dtype=np.uint32)
+        lo = 0
+        for hi, a in zip(seg_end, alphas):
+            q[lo:hi] = O.quantize(x[k, lo:hi], u[lo:hi], a, 16)
+            lo = hi
+        ct_want.append(O.encrypt(KEY, bits, n_jobs, it, k, "double", q))
+    ct_want = np.stack(ct_want)
+    assert np.array_equal(_np(cts), ct_want)
+    for mode, name in ((fb.AGG_ELEMENTWISE, "elementwise"), (fb.AGG_PACKED, "packed")):
+        agg = ctx.aggregate(cts, mode)
+        agg_want = O.aggregate(bits, ct_want, name)
+        assert np.array_equal(_np(agg), agg_want), name
+    agg = ctx.aggregate(cts)
+    p = ctx.empty_words(L)
+    out = ctx.decrypt_decode(it, [n], [0], agg, codec, span, p_out=p)
+    p_want = O.decrypt(KEY, bits, n_jobs, it, list(range(n)), "double", O.aggregate(bits, ct_want))
+    assert np.array_equal(_np(p), p_want)
+    want = np.empty(L, dtype=np.float64)
+    lo = 0
+    for hi, a in zip(seg_end, alphas):
+        want[lo:hi] = O.unquantize(p_want[lo:hi], a, 16, n)
+        lo = hi
+    assert np.array_equal(_np(out).view(np.uint64), want.view(np.uint64))
+    # decoded sum is the sum of the clipped inputs up to quantisation error (sanity, not parity)
+    clipped = sum(np.clip(x[k].astype(np.float64), -np.repeat(alphas, np.diff([0] + seg_end)), np.repeat(alphas, np.diff([0] + seg_end))) for k in range(n))
+    step = 2 * np.repeat(alphas, np.diff([0] + seg_end)) / 65535
+    assert np.all(np.abs(_np(out) - clipped) <= n * step * 1.01)
+
+
+def test_single_scheme_many_streams(fb):
+    """single masking decrypt subtracts one stream per survivor; > FLASHE_MAX_STREAMS needs chaining."""
+    bits, n_jobs, L, n = 32, 8, 20000, 150
+    ctx = ctx_for(fb, bits)
+    span = fb.VectorSpan(L, n_jobs)
+    agg = _dev(np.random.RandomState(3).randint(0, 2 ** 32, L, dtype=np.uint64).astype(np.uint32))
+    out = ctx.decrypt(3, [], list(range(128)), agg, span)
+    out = ctx.decrypt(3, [], list(range(128, n)), out, span)
+    want = O.decrypt(KEY, bits, n_jobs, 3, list(range(n)), "single", _np(agg))
+    assert np.array_equal(_np(out), want)
+
+
+def test_packed_aggregate_adversarial_and_shards(fb):
+    """Carry chains: all-ones digits make every element pass its carry-in on (worst case for the
+    look-ahead); element-range shards exchange carry descriptors."""
+    for bits, dtype in ((20, np.uint32), (32, np.uint32), (40, np.uint64), (64, np.uint64)):
+        ctx = ctx_for(fb, bits)
+        top = (1 << bits) - 1
+        rs = np.random.RandomState(bits)
+        L, n = 5000, 7
+        cts = rs.randint(0, 1 << min(bits, 62), size=(n, L), dtype=np.uint64).astype(dtype)
+        cts[:, 1000:3500] = 0
+        cts[0, 1000:3500] = top          # long run of digits that only propagate
+        cts[1, 3499] = 1                 # ... and one carry injected at its end
+        cts[:, 4000:4100] = top          # digits that generate and propagate
+        want, cw = O.aggregate(bits, cts, "packed", return_carry=True)
+        desc = torch.zeros(4, dtype=torch.int32, device="cuda")
+        got = ctx.aggregate(_dev(cts), fb.AGG_PACKED, carry_out=desc)
+        assert np.array_equal(_np(got), want), bits
+        assert int(desc[0]) == cw
+        # two shards, cut inside the propagate run
+        cut = 2000
+        hi_part = np.ascontiguousarray(cts[:, cut:])
+        lo_part = np.ascontiguousarray(cts[:, :cut])
+        d_hi = torch.zeros(4, dtype=torch.int32, device="cuda")
+        out_hi = ctx.aggregate(_dev(hi_part), fb.AGG_PACKED, carry_out=d_hi)
+        out_lo = ctx.aggregate(_dev(lo_part), fb.AGG_PACKED)          # carry_in unknown yet: 0
+        c_hi = int(d_hi[0])                                            # last shard: carry_in really is 0
+        ctx.aggregate_carry_fixup(out_lo, c_hi)
+        assert np.array_equal(np.concatenate([_np(out_lo), _np(out_hi)]), want), bits
+        # direct carry_in path gives the same
+        out_lo2 = ctx.aggregate(_dev(lo_part), fb.AGG_PACKED, carry_in=c_hi)
+        assert np.array_equal(_np(out_lo2), want[:cut])
+
+
+def test_aggregate_unaligned_and_tail(fb):
+    ctx = ctx_for(fb, 20)
+    rs = np.random.RandomState(8)
+    for L in (1, 3, 5, 1023, 4097):
+        cts = rs.randint(0, 1 << 20, size=(9, L), dtype=np.uint64).astype(np.uint32)
+        assert np.array_equal(_np(ctx.aggregate(_dev(cts))), O.aggregate(20, cts))
+
+
+# ---------------------------------------------------------------------------------------- the drop-in classes
+def test_flashecipher_dropin_matches_reference_outputs(fb, golden):
+    """Driven exactly like the reference's notebook / aggregator drive jzf_flashe.FlasheCipher."""
+    from flashe_b200.secureprotol import FlasheCipher
+    c = [k for k in golden.cases("roundtrip") if k["name"] == "rt_b20_n3"][0]
+    name, b, nj, L, n, it = (c[k] for k in ("name", "int_bits", "n_jobs", "L", "n_clients", "iter"))
+    q_ref = golden.words(name + "_q", 32).reshape(n, L)
+    ct_ref = golden.words(name + "_ct", b).reshape(n, L)
+    cts = []
+    for k in range(n):
+        cipher = FlasheCipher(b, n_jobs=nj)
+        assert cipher.encrypt(np.zeros(3, dtype=object)) is None          # no key yet
+        cipher.generate_prp_seed(KEY)
+        cipher.idx = k
+        cipher.set_iter_index(it)
+        assert cipher.encrypt([1, 2, 3]) is None                           # not an ndarray
+        ct = cipher.encrypt(q_ref[k].astype(object))
+        assert ct.dtype == object and isinstance(ct[0], int)
+        assert [int(v) for v in ct] == [int(v) for v in ct_ref[k]]
+        assert cipher.get_idx_list() == [k]
+        cts.append(ct)
+    from flashe_b200 import aggregate as agg_mod
+    total_b = agg_mod.aggregate(cts, b, is_compressed=False)
+    total_a = agg_mod.aggregate(cts, b, is_compressed=True)
+    assert [int(v) for v in total_b] == [int(v) for v in golden.words(name + "_aggB", b)]
+    assert [int(v) for v in total_a] == [int(v) for v in golden.words(name + "_aggA", b)]
+    cipher = FlasheCipher(b, n_jobs=nj)
+    cipher.generate_prp_seed(KEY)
+    cipher.set_num_clients(n)
+    cipher.set_iter_index(it)
+    cipher.set_idx_list(raw_idx_list=list(range(n)), mode="decrypt")
+    dec = cipher.decrypt(total_b)
+    assert [int(v) for v in dec] == [int(v) for v in golden.words(name + "_decB", b)]
+    from flashe_b200.secureprotol.quantize import _static_unquantize_padding_asymmetric
+    out = _static_unquantize_padding_asymmetric(dec, c["alpha"], 16, n)
+    assert out.dtype == object and isinstance(out[0], float)
+    assert np.array_equal(out.astype(np.float64).view(np.uint64), golden[name + "_decoded"].view(np.uint64))
+
+
+def test_flashecipher_precompute_and_dropout(fb, golden):
+    from flashe_b200.secureprotol import FlasheCipher
+    cases = golden.cases("dropout")
+    c0 = cases[0]
+    b, nj, L, n, it = (c0[k] for k in ("int_bits", "n_jobs", "L", "n_clients", "iter"))
+    q = golden.words("drop_q", 32).reshape(n, L)
+    ct_ref = golden.words("drop_ct", b).reshape(n, L)
+    # prepare_encrypt at iter-1 then encrypt at iter == on-the-fly (reference probe P9)
+    cipher = FlasheCipher(b, n_jobs=nj)
+    cipher.generate_prp_seed(KEY); cipher.idx = 2; cipher.set_num_clients(n); cipher.set_num_params(L)
+    cipher.set_iter_index(it - 1)
+    cipher.prepare_encrypt()
+    assert 'add' in cipher.next_iter_encrypt_prepared
+    cipher.set_iter_index(it)
+    ct = cipher.encrypt(q[2].astype(object))
+    assert [int(v) for v in ct] == [int(v) for v in ct_ref[2]]
+    assert 'add' not in cipher.next_iter_encrypt_prepared          # consumed, as in the reference
+    # decrypt with and without prepare_decrypt for every survivor set; the reference is wrong for
+    # [1,2,3] and [0,2] WITH precompute — here precomputed == on-the-fly == sum of plaintexts
+    for c in cases:
+        for pre in (False, True):
+            cipher = FlasheCipher(b, n_jobs=nj)
+            cipher.generate_prp_seed(KEY); cipher.set_num_clients(n); cipher.set_num_params(L)
+            cipher.set_iter_index(it)
+            if pre:
+                cipher.prepare_decrypt()
+            cipher.set_idx_list(raw_idx_list=list(c["survivors"]), mode="decrypt")
+            dec = cipher.decrypt(golden.words(c["name"] + "_agg", b).astype(object))
+            assert [int(v) for v in dec] == [int(v) for v in golden.words(c["name"] + "_dec", b)], (c["survivors"], pre)
+            assert cipher.next_iter_decrypt_prepared == {} and cipher.next_iter_decrypt_prepared_idx == {}
+
+
+def test_flashecipher_sparse_single(fb, golden):
+    from flashe_b200 import aggregate as agg_mod
+    from flashe_b200.secureprotol import FlasheCipher
+    c = golden.cases("sparse")[0]
+    b, nj, n, it, total = (c[k] for k in ("int_bits", "n_jobs", "n_clients", "iter", "total"))
+    masks = [[int(v) for v in golden["sparse_mask_%d" % k]] for k in range(n)]
+    uploads = []
+    for k in range(n):
+        cipher = FlasheCipher(b, mask="single", n_jobs=nj)
+        cipher.generate_prp_seed(KEY); cipher.idx = k; cipher.set_iter_index(it)
+        ct = cipher.encrypt(golden.words("sparse_q_%d" % k, 32).astype(object))
+        uploads.append(np.append(ct, [int(golden["sparse_zero"][k])]))      # jzf_aggregator.py:741-743
+    dense = agg_mod.expand_to_dense(uploads, masks, total, b)
+    agg = agg_mod.aggregate(dense, b)
+    assert [int(v) for v in agg] == [int(v) for v in golden.words("sparse_agg", b)]
+    cipher = FlasheCipher(b, mask="single", n_jobs=nj)
+    cipher.generate_prp_seed(KEY); cipher.set_iter_index(it)
+    cipher.masks = masks; cipher.total = total
+    cipher.set_idx_list(raw_idx_list=list(range(n)), mode="decrypt")
+    dec = cipher.decrypt(agg)
+    assert [int(v) for v in dec] == [int(v) for v in golden.words("sparse_dec", b)]
+    d = agg_mod.dynamic_masking(masks, total)
+    want_choice, sc, dc = O.dynamic_masking(masks)
+    assert (d["choice"], d["single_cost"], d["double_cost"]) == (want_choice, sc, dc)
+    dbl = FlasheCipher(b, mask="double", n_jobs=nj)
+    dbl.generate_prp_seed(KEY); dbl.set_iter_index(it); dbl.masks = masks; dbl.total = total
+    with pytest.raises(NotImplementedError):
+        dbl.set_idx_list(raw_idx_list=[0, 1, 2], mode="decrypt")
+
+
+class _W(object):
+    """Minimal stand-in for JZFOrderDictWeights (framework/jzf_weights.py:431-477): `_weights` dict +
+    `walking_order` = keys sorted as strings."""
+
+    def __init__(self, d):
+        self._weights = d
+        self.walking_order = sorted(d.keys(), key=str)
+
+
+def test_quantizing_client_seed_level_parity(fb, golden):
+    """np.random.seed(s) + QuantizingClient.quantize == the reference's outputs for the same seed."""
+    from flashe_b200.secureprotol import QuantizingClient
+    c = golden.cases("batch")[0]
+    b, L, n, e = c["int_bits"], c["L"], c["n_clients"], c["element_bits"]
+    q_ref = golden.words("batch_q", 32).reshape(n, L)
+    for batch in (False, True):
+        qc = QuantizingClient(b if batch else 20, None, None, batch, e, True, True)
+        qc.num_clients = n
+        w = _W({"layer0": golden["batch_x"][0].copy()})
+        qc.set_layer_size_list(w)
+        qc.past_layer_std_list = [0.05]           # alpha = 5.938345 * 0.05, the fixture's alpha
+        np.random.seed(6100)
+        qc.quantize(w)
+        if not batch:
+            assert [int(v) for v in w._weights["layer0"]] == [int(v) for v in q_ref[0]]
+        else:
+            w_ref = golden.words("batch_w", b).reshape(n, c["words"], 2)[0]
+            assert [int(v) for v in w._weights["layer0"]] == [int(lo) | (int(hi) << 64) for lo, hi in w_ref]
+        # unquantize round trip of the golden aggregate
+        if batch:
+            w2 = _W({"layer0": np.array([int(lo) | (int(hi) << 64) for lo, hi in golden.words("batch_dec", b)], dtype=object)})
+        else:
+            w2 = _W({"layer0": golden.words("batch_unb", 32).astype(object)})
+        qc.shape_list = [(L,)]
+        qc.unquantize(w2)
+        assert np.array_equal(np.asarray(w2._weights["layer0"], dtype=np.float64).view(np.uint64), golden["batch_decoded"].view(np.uint64))

@@ -183,3 +183,22 @@ def test_dynamic_masking_cost_model():
     assert sc == 16 and dc == 32 - 2 * 2 and choice == "single"
     choice, sc, dc = O.dynamic_masking([a, a, a])
     assert sc == 24 and dc == 48 - 2 * 8 and choice == "single"
+
+
+def test_python_port_matches_golden(golden):
+    """oracle/flashe_port.py (the timed CPU baseline) against the reference's own outputs."""
+    from oracle import flashe_port as P
+    for name in ("rt_b20_n3", "rt_b32_n5"):
+        c = [k for k in golden.cases("roundtrip") if k["name"] == name][0]
+        b, nj, L, n, it = (c[k] for k in ("int_bits", "n_jobs", "L", "n_clients", "iter"))
+        xs, us = golden[name + "_x"], golden[name + "_u"]
+        cts, agg, dec, out = P.run_round(golden.key, b, it, list(xs), c["alpha"], 16, n_jobs=nj, us=list(us))
+        ct_ref = golden.words(name + "_ct", b).reshape(n, L)
+        for k in range(n):
+            assert [int(v) for v in cts[k]] == [int(v) for v in ct_ref[k]]
+        assert [int(v) for v in agg] == [int(v) for v in golden.words(name + "_aggB", b)]
+        assert [int(v) for v in dec] == [int(v) for v in golden.words(name + "_decB", b)]
+        assert np.array_equal(np.array([float(v) for v in out]).view(np.uint64), golden[name + "_decoded"].view(np.uint64))
+        assert [int(v) for v in P.aggregate_packed(cts, b)] == [int(v) for v in golden.words(name + "_aggA", b)]
+    for c in golden.cases("dropout"):
+        assert P.collapse_runs(c["survivors"]) == (c["add"], c["minus"])

@@ -75,11 +75,12 @@ class ClockSampler(object):
         self.rows = []
         self.proc = None
         self.thread = None
+        self.first = 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -91,6 +92,10 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        """Samples before this point (warm-up) are not part of the timed region."""
+        self.first = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -100,7 +105,8 @@ class ClockSampler(object):
         except Exception:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
-        for r in self.rows:
+        rows = self.rows[self.first:] or self.rows[-3:]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
                 continue
@@ -228,12 +234,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        round_device()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        round_device()
+    barrier()
+    sampler.mark()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     l0 = launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

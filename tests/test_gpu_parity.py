@@ -134,7 +134,7 @@ def test_dropout_golden(fb, golden):
     for c in cases:
         add, minus = collapse_runs(c["survivors"])
         assert add == c["add"] and minus == c["minus"]
-        rows = ct[sorted(c["survivors"])].contiguous()
+        rows = ct.view(torch.int32)[sorted(c["survivors"])].contiguous()   # (index_cuda has no uint32 kernel)
         agg = ctx.aggregate(rows)
         assert np.array_equal(_np(agg), golden.words(c["name"] + "_agg", b))
         assert np.array_equal(_np(ctx.decrypt(it, add, minus, agg, span)), golden.words(c["name"] + "_dec", b))

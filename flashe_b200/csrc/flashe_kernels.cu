@@ -260,17 +260,18 @@ __device__ __forceinline__ void aes256_block(const KeySched& ks, uint32_t y, uin
 // ------------------------------------------------------------------------------------------------
 // device: geometry of the reference's chunked counter rule (jzf_flashe.py:12-16, 24-34)
 // ------------------------------------------------------------------------------------------------
+#define ITEM_BLOCKS 64u   // AES blocks per warp item (two per lane)
 struct Item { uint64_t cb; uint64_t clen; uint64_t i0; };  // chunk begin, chunk length, first block
 
 __device__ __forceinline__ Item decode_item(const Geom& g, uint64_t W) {
     Item it;
     if (W < g.rA) {
         uint64_t k = W / g.nwA, w = W - k * g.nwA;
-        it.cb = k * (g.d + 1); it.clen = g.d + 1; it.i0 = w * 32;
+        it.cb = k * (g.d + 1); it.clen = g.d + 1; it.i0 = w * ITEM_BLOCKS;
     } else {
         uint64_t Wp = W - g.rA;
         uint64_t k = Wp / g.nwB, w = Wp - k * g.nwB;
-        it.cb = g.r * (g.d + 1) + k * g.d; it.clen = g.d; it.i0 = w * 32;
+        it.cb = g.r * (g.d + 1) + k * g.d; it.clen = g.d; it.i0 = w * ITEM_BLOCKS;
     }
     return it;
 }
@@ -325,6 +326,14 @@ __device__ __forceinline__ double noise_one(const NoiseDev& nz, uint64_t stream,
     philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), nz.k0, nz.k1, o);
     uint32_t a = (j & 1) ? o[2] : o[0], b = (j & 1) ? o[3] : o[1];
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// Both numbers of one Philox call: u for elements 2c and 2c+1 (same values as noise_one).
+__device__ __forceinline__ void noise_pair(const NoiseDev& nz, uint64_t stream, uint64_t c, double& u0, double& u1) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), nz.k0, nz.k1, o);
+    u0 = ((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6)) * (1.0 / 9007199254740992.0);
+    u1 = ((double)(o[2] >> 5) * 67108864.0 + (double)(o[3] >> 6)) * (1.0 / 9007199254740992.0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -429,19 +438,90 @@ template <> __device__ __forceinline__ u128 slab_load<4>(uint32_t addr) {
     u128 r; r.lo = ((uint64_t)b << 32) | a; r.hi = ((uint64_t)d << 32) | c; return r;
 }
 
-template <int WORDS, int MMAX, int MODE>
+// Out-of-line single block for the rare paths (chunk tails, counters >= 2^32).
+__device__ __noinline__ void aes256_block_slow(const KeySched& ks, uint32_t y, uint32_t w0, uint32_t w1, uint32_t w2,
+                                               uint32_t w3, Pre pre, uint32_t* o) {
+    uint32_t t[4];
+    aes256_block(ks, y, w0, w1, w2, w3, pre, t);
+    o[0] = t[0]; o[1] = t[1]; o[2] = t[2]; o[3] = t[3];
+}
+
+// Two AES-256 blocks of the SAME stream (counters w3a, w3b; words 0-2 shared, word 2 == 0) computed
+// in one instruction stream: twice the independent lookups per round, so the round-boundary latency
+// (LDS ~30 clk + LOP3) of one block hides under the other's.
+__device__ __forceinline__ void aes256_x2(const KeySched& ks, uint32_t y, Pre pre, uint32_t w3a, uint32_t w3b,
+                                          uint32_t oa[4], uint32_t ob[4]) {
+    uint32_t a0, a1, a2, a3, b0, b1, b2, b3, p0, p1, p2, p3, q0, q1, q2, q3;
+    a3 = w3a ^ ks.rk[3]; b3 = w3b ^ ks.rk[3];
+    p0 = pre.p0 ^ T3(a3); q0 = pre.p0 ^ T3(b3);
+    p1 = pre.p1 ^ T2(a3); q1 = pre.p1 ^ T2(b3);
+    p2 = pre.p2 ^ T1(a3); q2 = pre.p2 ^ T1(b3);
+    p3 = pre.p3 ^ T0(a3); q3 = pre.p3 ^ T0(b3);
+#pragma unroll
+    for (int r = 2; r < 14; r += 2) {
+        a0 = T0(p0) ^ T1(p1) ^ T2(p2) ^ T3(p3) ^ ks.rk[4 * r + 0];
+        b0 = T0(q0) ^ T1(q1) ^ T2(q2) ^ T3(q3) ^ ks.rk[4 * r + 0];
+        a1 = T0(p1) ^ T1(p2) ^ T2(p3) ^ T3(p0) ^ ks.rk[4 * r + 1];
+        b1 = T0(q1) ^ T1(q2) ^ T2(q3) ^ T3(q0) ^ ks.rk[4 * r + 1];
+        a2 = T0(p2) ^ T1(p3) ^ T2(p0) ^ T3(p1) ^ ks.rk[4 * r + 2];
+        b2 = T0(q2) ^ T1(q3) ^ T2(q0) ^ T3(q1) ^ ks.rk[4 * r + 2];
+        a3 = T0(p3) ^ T1(p0) ^ T2(p1) ^ T3(p2) ^ ks.rk[4 * r + 3];
+        b3 = T0(q3) ^ T1(q0) ^ T2(q1) ^ T3(q2) ^ ks.rk[4 * r + 3];
+        p0 = T0(a0) ^ T1(a1) ^ T2(a2) ^ T3(a3) ^ ks.rk[4 * r + 4];
+        q0 = T0(b0) ^ T1(b1) ^ T2(b2) ^ T3(b3) ^ ks.rk[4 * r + 4];
+        p1 = T0(a1) ^ T1(a2) ^ T2(a3) ^ T3(a0) ^ ks.rk[4 * r + 5];
+        q1 = T0(b1) ^ T1(b2) ^ T2(b3) ^ T3(b0) ^ ks.rk[4 * r + 5];
+        p2 = T0(a2) ^ T1(a3) ^ T2(a0) ^ T3(a1) ^ ks.rk[4 * r + 6];
+        q2 = T0(b2) ^ T1(b3) ^ T2(b0) ^ T3(b1) ^ ks.rk[4 * r + 6];
+        p3 = T0(a3) ^ T1(a0) ^ T2(a1) ^ T3(a2) ^ ks.rk[4 * r + 7];
+        q3 = T0(b3) ^ T1(b0) ^ T2(b1) ^ T3(b2) ^ ks.rk[4 * r + 7];
+    }
+#define LAST(a, b, c, d, k)                                                                         \
+    (__byte_perm(__byte_perm(lds_tab<128>(__byte_perm((d), y, SEL_B0)),                             \
+                             lds_tab<0>(__byte_perm((c), y, SEL_B1)), 0x3250),                      \
+                 __byte_perm(lds_tab<0x10080>(__byte_perm((b), y, SEL_B2)),                         \
+                             lds_tab<0x10000>(__byte_perm((a), y, SEL_B3)), 0x7210), 0x7610) ^ ks.rk[k])
+    oa[0] = LAST(p0, p1, p2, p3, 56); ob[0] = LAST(q0, q1, q2, q3, 56);
+    oa[1] = LAST(p1, p2, p3, p0, 57); ob[1] = LAST(q1, q2, q3, q0, 57);
+    oa[2] = LAST(p2, p3, p0, p1, 58); ob[2] = LAST(q2, q3, q0, q1, 58);
+    oa[3] = LAST(p3, p0, p1, p2, 59); ob[3] = LAST(q3, q0, q1, q2, 59);
+#undef LAST
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_stream: persistent, one 512-thread CTA per SM (128 KB of tables + per-warp slabs).
+//
+// Work unit ("warp item") = NB*32 = 64 consecutive AES blocks of one reference chunk: lane l owns
+// blocks i0+l and i0+32+l, i.e. 2*m elements.  Per item and client:
+//   1. prefetch the item's input elements (pairs (2p, 2p+1) of the global index) into registers so the
+//      DRAM latency hides under the AES work;
+//   2. per stream: two interleaved AES-256 blocks per lane, slots accumulated with sign in registers;
+//   3. transpose lane-major -> element-major through the warp's shared slab;
+//   4. walk the item's element pairs: noise (one Philox per pair), encode / decode, modular add,
+//      coalesced stores.
+// ------------------------------------------------------------------------------------------------
+#define NB 2
+
+template <int MODE, int WORDS> struct InType { typedef typename Word<WORDS>::T T; };
+template <int WORDS> struct InType<M_ENCODE, WORDS> { typedef float T; };
+
+template <int WORDS, int MMAX, int MODE, bool SHARE>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
 k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab st, const __grid_constant__ Geom g,
          const __grid_constant__ IoDev io, const __grid_constant__ CodecDev cd, const __grid_constant__ NoiseDev nz) {
     typedef Word<WORDS> WT;
     typedef typename WT::T word_t;
+    typedef typename InType<MODE, WORDS>::T in_t;
+    constexpr bool HAS_IN = (MODE == M_APPLY || MODE == M_ENCODE || MODE == M_DECODE);
+    constexpr int PF = MMAX + 1;                 // pair iterations per item: ceil((64m + 2) / 64)
+    constexpr uint32_t WB = WORDS * 4u;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t y = 0x00010000u | (lane << 2);
     const uint32_t sbase = smem_window_base();
-#define PRE_OF(k) Pre{st.pre[k][0], st.pre[k][1], st.pre[k][2], st.pre[k][3]}
-    const uint32_t slab_bytes = 32u * MMAX * WORDS * 4u;
+    const uint32_t slab_bytes = (NB * 32u * MMAX + 2u) * WB;
     if (sbase + nwarps * slab_bytes > TAB_BASE) { __trap(); }
     const uint32_t slab = sbase + warp * slab_bytes;
+#define PRE_OF(k) Pre{st.pre[k][0], st.pre[k][1], st.pre[k][2], st.pre[k][3]}
 
     fill_tables();
     __syncthreads();
@@ -459,97 +539,160 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
             else { c_first = (uint32_t)(t / g.W_cnt); W = t - (uint64_t)c_first * g.W_cnt; }
         }
         const Item it = decode_item(g, g.W_lo + W);
-        const uint64_t blk = it.i0 + lane;              // local block index of this lane
-        const uint64_t e_lane = blk * m;                // first local element of this lane
-        const bool lane_on = e_lane < it.clen;
-        const uint64_t ctr = it.cb + blk;               // jzf_flashe.py:34 "(i + begin)"
-        const uint64_t item_e0 = it.cb + it.i0 * m;     // first global element of the item
+        const uint64_t blkA = it.i0 + lane, blkB = blkA + 32;
+        const bool onA = blkA * m < it.clen, onB = blkB * m < it.clen;
+        const uint64_t ctrA = it.cb + blkA, ctrB = it.cb + blkB;     // jzf_flashe.py:34 "(i + begin)"
+        const bool fast = ((ctrB >> 32) == 0);                       // hoisted round 1 needs word 2 == 0
+        const uint64_t item_e0 = it.cb + it.i0 * m;                  // first global element of the item
         const uint64_t rem = it.clen - it.i0 * m;
-        const uint32_t item_n = (uint32_t)(rem < 32ull * m ? rem : 32ull * m);
+        const uint32_t item_n = (uint32_t)(rem < (uint64_t)(NB * 32u) * m ? rem : (uint64_t)(NB * 32u) * m);
+        const uint32_t par = (uint32_t)(item_e0 & 1ull);
+        const uint64_t base_e = item_e0 - par;                       // even; slab index = j - base_e
+        const uint32_t npairs = (par + item_n + 1u) >> 1;
+        // shard clipping in slab-index space
+        const uint32_t lo_i = g.begin > item_e0 ? (uint32_t)(g.begin - base_e) : par;
+        const uint32_t hi_i = (item_e0 + item_n) > g.end ? (uint32_t)(g.end > base_e ? g.end - base_e : 0) : par + item_n;
+        const int64_t off0 = (int64_t)(base_e - g.begin);            // offset of slab index 0 in the shard buffers
 
-        word_t prev[MMAX];  // shared-stream mode: F(iter, c) carried to the next client
-        if (st.batch && io.share) {
-#pragma unroll
-            for (int k = 0; k < MMAX; ++k) prev[k] = WT::zero();
-            if (lane_on) {
-                uint32_t o[4];
-                aes256_block(ks, y, st.iter, st.prf[0], (uint32_t)(ctr >> 32), (uint32_t)ctr, PRE_OF(0), o);
-                accumulate_slots<WORDS, MMAX>(o, g.b, m, +1, prev);
-            }
-        }
-
-        for (uint32_t cc = 0; cc < c_count; ++cc) {
-            const uint32_t c = c_first + cc;
-            word_t acc[MMAX];
-#pragma unroll
-            for (int k = 0; k < MMAX; ++k) acc[k] = WT::zero();
-            if (lane_on) {
-                if (!st.batch) {
-                    for (uint32_t s = 0; s < st.n; ++s) {
-                        uint32_t o[4];
-                        aes256_block(ks, y, st.iter, st.prf[s], (uint32_t)(ctr >> 32), (uint32_t)ctr, PRE_OF(s), o);
-                        accumulate_slots<WORDS, MMAX>(o, g.b, m, st.sign[s], acc);
-                    }
-                } else if (io.share) {
-                    word_t nxt[MMAX];
-#pragma unroll
-                    for (int k = 0; k < MMAX; ++k) nxt[k] = WT::zero();
-                    uint32_t o[4];
-                    aes256_block(ks, y, st.iter, st.prf[c + 1], (uint32_t)(ctr >> 32), (uint32_t)ctr, PRE_OF(c + 1), o);
-                    accumulate_slots<WORDS, MMAX>(o, g.b, m, +1, nxt);
-#pragma unroll
-                    for (int k = 0; k < MMAX; ++k) { acc[k] = WT::sub(prev[k], nxt[k]); prev[k] = nxt[k]; }
-                } else {
-                    uint32_t o[4];
-                    aes256_block(ks, y, st.iter, st.prf[c], (uint32_t)(ctr >> 32), (uint32_t)ctr, PRE_OF(c), o);
-                    accumulate_slots<WORDS, MMAX>(o, g.b, m, +1, acc);
-                    if (st.dbl) {
-                        aes256_block(ks, y, st.iter, st.prf[c + 1], (uint32_t)(ctr >> 32), (uint32_t)ctr, PRE_OF(c + 1), o);
-                        accumulate_slots<WORDS, MMAX>(o, g.b, m, -1, acc);
-                    }
+        // one AES pass: F(iter, prf) for this lane's two blocks, accumulated with sign
+        auto stream_into = [&](uint32_t sidx, int sign, word_t (&acc)[NB][MMAX]) {
+            uint32_t oa[4], ob[4];
+            if (onB && fast) {
+                aes256_x2(ks, y, PRE_OF(sidx), (uint32_t)ctrA, (uint32_t)ctrB, oa, ob);
+                accumulate_slots<WORDS, MMAX>(oa, g.b, m, sign, acc[0]);
+                accumulate_slots<WORDS, MMAX>(ob, g.b, m, sign, acc[1]);
+            } else {
+                const uint32_t prf = st.prf[sidx];
+                if (onA) {
+                    aes256_block_slow(ks, y, st.iter, prf, (uint32_t)(ctrA >> 32), (uint32_t)ctrA, PRE_OF(sidx), oa);
+                    accumulate_slots<WORDS, MMAX>(oa, g.b, m, sign, acc[0]);
+                }
+                if (onB) {
+                    aes256_block_slow(ks, y, st.iter, prf, (uint32_t)(ctrB >> 32), (uint32_t)ctrB, PRE_OF(sidx), ob);
+                    accumulate_slots<WORDS, MMAX>(ob, g.b, m, sign, acc[1]);
                 }
             }
-            // lane-major -> element-major through the warp's slab
+        };
+
+        // SHARE: iteration 0 only produces F(iter, first client); iteration cc >= 1 serves client cc-1
+        // with F(c) - F(c+1), reusing F(c+1) as the next client's add term.
+        word_t prev[SHARE ? NB : 1][SHARE ? MMAX : 1];
+        const uint32_t n_iter = SHARE ? c_count + 1 : c_count;
+        for (uint32_t cc = 0; cc < n_iter; ++cc) {
+            const uint32_t c = SHARE ? (cc ? c_first + cc - 1 : 0) : c_first + cc;
+            const bool emit = !SHARE || cc > 0;
+            // ---- 1. prefetch inputs (pairs) ----
+            in_t pf[PF][2];
+            if (HAS_IN && emit) {
+                const in_t* in = reinterpret_cast<const in_t*>(io.in) + (uint64_t)c * io.in_stride;
+#pragma unroll
+                for (int k = 0; k < PF; ++k) {
+                    const uint32_t i0 = 2u * (lane + 32u * k);
+                    if (i0 >= lo_i && i0 < hi_i) pf[k][0] = in[off0 + i0];
+                    if (i0 + 1 >= lo_i && i0 + 1 < hi_i) pf[k][1] = in[off0 + i0 + 1];
+                }
+            }
+            // ---- 2. keystreams ----
+            word_t acc[NB][MMAX];
+#pragma unroll
+            for (int h = 0; h < NB; ++h)
+#pragma unroll
+                for (int k = 0; k < MMAX; ++k) acc[h][k] = WT::zero();
+            if (onA) {
+                uint32_t s_begin, s_count;
+                if (!st.batch) { s_begin = 0; s_count = st.n; }
+                else if (SHARE) { s_begin = cc; s_count = 1; }
+                else { s_begin = c; s_count = st.dbl ? 2u : 1u; }
+                for (uint32_t s = 0; s < s_count; ++s) {
+                    const int sign = st.batch ? (s == 0 ? +1 : -1) : st.sign[s_begin + s];
+                    stream_into(s_begin + s, sign, acc);
+                }
+            }
+            if (SHARE) {
+                // acc = F(cc); mask of client cc-1 = prev - acc
+#pragma unroll
+                for (int h = 0; h < NB; ++h)
+#pragma unroll
+                    for (int k = 0; k < MMAX; ++k) {
+                        const word_t cur = acc[h][k];
+                        if (cc > 0) acc[h][k] = WT::sub(prev[SHARE ? h : 0][SHARE ? k : 0], cur);
+                        prev[SHARE ? h : 0][SHARE ? k : 0] = cur;
+                    }
+                if (!emit) continue;
+            }
+            // ---- 3. lane-major -> element-major through the warp's slab ----
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < MMAX; ++k)
-                if ((uint32_t)k < m) slab_store<WORDS>(slab + (lane * m + k) * (WORDS * 4u), acc[k]);
+            for (int h = 0; h < NB; ++h)
+#pragma unroll
+                for (int k = 0; k < MMAX; ++k)
+                    if ((uint32_t)k < m) slab_store<WORDS>(slab + (par + (lane + 32u * h) * m + k) * WB, acc[h][k]);
             __syncwarp();
 
-            for (uint32_t e = lane; e < item_n; e += 32) {
-                const uint64_t j = item_e0 + e;
-                if (j < g.begin || j >= g.end) continue;
-                const uint64_t off = j - g.begin;
-                word_t mask_w = WT::band(slab_load<WORDS>(slab + e * (WORDS * 4u)), mk);
+            // ---- 4. element pairs ----
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const uint32_t p = lane + 32u * k;
+                if (p >= npairs) break;
+                const uint32_t i0 = 2u * p;
+                const bool v0 = i0 >= lo_i && i0 < hi_i, v1 = i0 + 1 >= lo_i && i0 + 1 < hi_i;
+                if (!v0 && !v1) continue;
+                const uint64_t j0 = base_e + i0;
+                word_t mw0 = WT::band(slab_load<WORDS>(slab + i0 * WB), mk);
+                word_t mw1 = WT::band(slab_load<WORDS>(slab + (i0 + 1) * WB), mk);
+                const int64_t o0 = off0 + i0;
                 if (MODE == M_MASKS) {
-                    reinterpret_cast<word_t*>(io.out)[off] = mask_w;
+                    word_t* out = reinterpret_cast<word_t*>(io.out);
+                    if (v0) out[o0] = mw0;
+                    if (v1) out[o0 + 1] = mw1;
                 } else if (MODE == M_APPLY) {
-                    const word_t* in = reinterpret_cast<const word_t*>(io.in) + (uint64_t)c * io.in_stride;
                     word_t* out = reinterpret_cast<word_t*>(io.out) + (uint64_t)c * io.out_stride;
-                    out[off] = WT::band(WT::add(in[off], mask_w), mk);
+                    if (v0) out[o0] = WT::band(WT::add(*reinterpret_cast<word_t*>(&pf[k][0]), mw0), mk);
+                    if (v1) out[o0 + 1] = WT::band(WT::add(*reinterpret_cast<word_t*>(&pf[k][1]), mw1), mk);
                 } else if (MODE == M_ENCODE) {
-                    const float* x = reinterpret_cast<const float*>(io.in) + (uint64_t)c * io.in_stride;
                     word_t* out = reinterpret_cast<word_t*>(io.out) + (uint64_t)c * io.out_stride;
-                    const Seg& sg = find_seg(cd, j);
-                    double u = nz.u ? nz.u[(uint64_t)c * nz.u_stride + off] : noise_one(nz, nz.stream + c, j);
-                    uint32_t q = encode_one(x[off], u, sg.a, sg.two_a, cd.scale);
-                    if (io.aux) reinterpret_cast<uint32_t*>(io.aux)[(uint64_t)c * io.out_stride + off] = q;
-                    out[off] = WT::band(WT::add(WT::from_u32(q), mask_w), mk);
+                    double u0, u1;
+                    if (nz.u) {
+                        const double* up = nz.u + (uint64_t)c * nz.u_stride;
+                        u0 = v0 ? up[o0] : 0.0; u1 = v1 ? up[o0 + 1] : 0.0;
+                    } else {
+                        noise_pair(nz, nz.stream + c, j0 >> 1, u0, u1);
+                    }
+                    if (v0) {
+                        const Seg& sg = find_seg(cd, j0);
+                        uint32_t q = encode_one(*reinterpret_cast<float*>(&pf[k][0]), u0, sg.a, sg.two_a, cd.scale);
+                        if (io.aux) reinterpret_cast<uint32_t*>(io.aux)[(uint64_t)c * io.out_stride + o0] = q;
+                        out[o0] = WT::band(WT::add(WT::from_u32(q), mw0), mk);
+                    }
+                    if (v1) {
+                        const Seg& sg = find_seg(cd, j0 + 1);
+                        uint32_t q = encode_one(*reinterpret_cast<float*>(&pf[k][1]), u1, sg.a, sg.two_a, cd.scale);
+                        if (io.aux) reinterpret_cast<uint32_t*>(io.aux)[(uint64_t)c * io.out_stride + o0 + 1] = q;
+                        out[o0 + 1] = WT::band(WT::add(WT::from_u32(q), mw1), mk);
+                    }
                 } else if (MODE == M_DECODE) {
-                    const word_t* in = reinterpret_cast<const word_t*>(io.in);
-                    word_t p = WT::band(WT::add(in[off], mask_w), mk);
-                    if (io.aux) reinterpret_cast<word_t*>(io.aux)[off] = p;
-                    const Seg& sg = find_seg(cd, j);
-                    io.outf[off] = decode_one(WT::to_double(p), sg.two_an, cd.den, sg.an);
+                    if (v0) {
+                        word_t pw = WT::band(WT::add(*reinterpret_cast<word_t*>(&pf[k][0]), mw0), mk);
+                        if (io.aux) reinterpret_cast<word_t*>(io.aux)[o0] = pw;
+                        const Seg& sg = find_seg(cd, j0);
+                        io.outf[o0] = decode_one(WT::to_double(pw), sg.two_an, cd.den, sg.an);
+                    }
+                    if (v1) {
+                        word_t pw = WT::band(WT::add(*reinterpret_cast<word_t*>(&pf[k][1]), mw1), mk);
+                        if (io.aux) reinterpret_cast<word_t*>(io.aux)[o0 + 1] = pw;
+                        const Seg& sg = find_seg(cd, j0 + 1);
+                        io.outf[o0 + 1] = decode_one(WT::to_double(pw), sg.two_an, cd.den, sg.an);
+                    }
                 } else if (MODE == M_SCATTER) {
                     const int64_t* index = reinterpret_cast<const int64_t*>(io.aux);
                     word_t* dense = reinterpret_cast<word_t*>(io.out);
-                    const int64_t dst = index[off];
-                    dense[dst] = WT::band(WT::add(dense[dst], mask_w), mk);
+                    if (v0) { const int64_t d = index[o0]; dense[d] = WT::band(WT::add(dense[d], mw0), mk); }
+                    if (v1) { const int64_t d = index[o0 + 1]; dense[d] = WT::band(WT::add(dense[d], mw1), mk); }
                 }
             }
         }
     }
+#undef PRE_OF
 }
 
 // one AES block, known-answer tests (flashe_prp_block)
@@ -972,14 +1115,14 @@ static void make_geom(const flashe_ctx* ctx, const flashe_span* s, Geom* g) {
     g->m = ctx->m; g->b = (uint32_t)ctx->int_bits;
     g->d = s->total_len / s->n_jobs; g->r = s->total_len % s->n_jobs;
     const uint64_t nbA = ceil_div(g->d + 1, g->m), nbB = g->d ? ceil_div(g->d, g->m) : 0;
-    g->nwA = ceil_div(nbA, 32); g->nwB = ceil_div(nbB, 32);
+    g->nwA = ceil_div(nbA, ITEM_BLOCKS); g->nwB = ceil_div(nbB, ITEM_BLOCKS);
     g->rA = g->r * g->nwA;
     if (s->count == 0) { g->W_lo = 0; g->W_cnt = 0; return; }
     auto item_of = [&](uint64_t j) {
         uint64_t k, cb;
         if (j < g->r * (g->d + 1)) { k = j / (g->d + 1); cb = k * (g->d + 1); }
         else { k = g->r + (j - g->r * (g->d + 1)) / g->d; cb = g->r * (g->d + 1) + (k - g->r) * g->d; }
-        const uint64_t w = ((j - cb) / g->m) / 32;
+        const uint64_t w = ((j - cb) / g->m) / ITEM_BLOCKS;
         return (k < g->r ? k * g->nwA : g->rA + (k - g->r) * g->nwB) + w;
     };
     g->W_lo = item_of(g->begin);
@@ -1057,10 +1200,10 @@ static int grid_1d(const flashe_ctx* ctx, uint64_t work_items, int threads, int 
     return (int)(blocks < cap ? blocks : cap);
 }
 
-template <int WORDS, int MMAX, int MODE>
+template <int WORDS, int MMAX, int MODE, bool SHARE>
 static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,
                            const NoiseDev& nz, cudaStream_t stream) {
-    auto kern = k_stream<WORDS, MMAX, MODE>;
+    auto kern = k_stream<WORDS, MMAX, MODE, SHARE>;
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -1068,7 +1211,7 @@ static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geo
     }
     const uint64_t items = (st.batch && !io.share) ? g.W_cnt * io.n_clients : g.W_cnt;
     if (items == 0) return FLASHE_OK;
-    const int slab_bytes = 32 * MMAX * WORDS * 4;
+    const int slab_bytes = (2 * 32 * MMAX + 2) * WORDS * 4;
     int threads = STREAM_THREADS;
     while (threads > 32 && (threads / 32) * slab_bytes > 60 * 1024) threads >>= 1;
     const int wpb = threads / 32;
@@ -1084,12 +1227,22 @@ template <int MODE>
 static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,
                          const NoiseDev& nz, cudaStream_t stream) {
     const int b = ctx->int_bits;
-    if (b <= 32) {
-        if (ctx->m <= 6) return launch_stream_t<1, 6, MODE>(ctx, st, g, io, cd, nz, stream);
-        return launch_stream_t<1, 16, MODE>(ctx, st, g, io, cd, nz, stream);
+    if constexpr (MODE == M_ENCODE) {
+        if (io.share) {
+            if (b <= 32) {
+                if (ctx->m <= 6) return launch_stream_t<1, 6, MODE, true>(ctx, st, g, io, cd, nz, stream);
+                return launch_stream_t<1, 16, MODE, true>(ctx, st, g, io, cd, nz, stream);
+            }
+            if (b <= 64) return launch_stream_t<2, 3, MODE, true>(ctx, st, g, io, cd, nz, stream);
+            return launch_stream_t<4, 1, MODE, true>(ctx, st, g, io, cd, nz, stream);
+        }
     }
-    if (b <= 64) return launch_stream_t<2, 3, MODE>(ctx, st, g, io, cd, nz, stream);
-    return launch_stream_t<4, 1, MODE>(ctx, st, g, io, cd, nz, stream);
+    if (b <= 32) {
+        if (ctx->m <= 6) return launch_stream_t<1, 6, MODE, false>(ctx, st, g, io, cd, nz, stream);
+        return launch_stream_t<1, 16, MODE, false>(ctx, st, g, io, cd, nz, stream);
+    }
+    if (b <= 64) return launch_stream_t<2, 3, MODE, false>(ctx, st, g, io, cd, nz, stream);
+    return launch_stream_t<4, 1, MODE, false>(ctx, st, g, io, cd, nz, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -74,7 +74,8 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB
+    # FLASHE_B200_LIB: alternative build of the same library (kernel tuning experiments)
+    return os.environ.get("FLASHE_B200_LIB") or _build.LIB
 
 
 def load():

@@ -111,7 +111,9 @@ static void hoist_round1(const uint32_t rk[60], uint32_t w0, uint32_t w1, uint32
 // ------------------------------------------------------------------------------------------------
 #define MAXS FLASHE_MAX_STREAMS
 #define MAX_INLINE_SEG 48
+#ifndef STREAM_THREADS
 #define STREAM_THREADS 512
+#endif
 
 struct KeySched { uint32_t rk[60]; };
 
@@ -155,6 +157,7 @@ struct IoDev {
     double* outf;
     uint32_t n_clients;
     uint32_t share;                         // batch double masking: compute each stream once
+    uint32_t quad;                          // every buffer / stride allows 16-byte accesses per 4 elements
 };
 
 enum { M_MASKS = 0, M_APPLY = 1, M_ENCODE = 2, M_DECODE = 3, M_SCATTER = 4 };
@@ -207,7 +210,22 @@ __device__ __forceinline__ void fill_tables() {
 #define SEL_B2 0x7624
 #define SEL_B1 0x7614
 #define SEL_B0 0x7604
-#define T0(s) lds_tab<0>(__byte_perm((s), y, SEL_B3))
+#ifndef FLASHE_IMAD_B3
+#define FLASHE_IMAD_B3 0
+#endif
+// Address of the byte-3 lookup on the FMA pipe instead of the ALU pipe: (s >> 24) via mad.hi, then
+// * 256 + y via mad.lo (the ALU pipe is as loaded as the LSU; the FMA pipe idles).
+__device__ __forceinline__ uint32_t addr_b3(uint32_t s, uint32_t y) {
+#if FLASHE_IMAD_B3
+    uint32_t hi, a;
+    asm("mul.hi.u32 %0, %1, 256;" : "=r"(hi) : "r"(s));
+    asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(a) : "r"(hi), "r"(y));
+    return a;
+#else
+    return __byte_perm(s, y, SEL_B3);
+#endif
+}
+#define T0(s) lds_tab<0>(addr_b3((s), y))
 #define T1(s) lds_tab<128>(__byte_perm((s), y, SEL_B2))
 #define T2(s) lds_tab<0x10000>(__byte_perm((s), y, SEL_B1))
 #define T3(s) lds_tab<0x10080>(__byte_perm((s), y, SEL_B0))
@@ -380,6 +398,11 @@ template <int WORDS, int MMAX>
 __device__ __forceinline__ void accumulate_slots(const uint32_t o[4], uint32_t b, uint32_t m, int sign,
                                                  typename Word<WORDS>::T (&acc)[MMAX]) {
     if constexpr (WORDS == 1) {
+        if (b == 32u) {          // four whole words: no shifting (slot k = word 3-k)
+#pragma unroll
+            for (int k = 0; k < 4 && k < MMAX; ++k) acc[k] += (uint32_t)sign * o[3 - k];
+            return;
+        }
         uint32_t v0 = o[3], v1 = o[2], v2 = o[1], v3 = o[0];
         const uint32_t mk = Word<1>::mask(b);
 #pragma unroll
@@ -436,6 +459,16 @@ template <> __device__ __forceinline__ u128 slab_load<4>(uint32_t addr) {
     uint32_t a, b, c, d;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
     u128 r; r.lo = ((uint64_t)b << 32) | a; r.hi = ((uint64_t)d << 32) | c; return r;
+}
+
+__device__ __forceinline__ void ldg_v4(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+}
+__device__ __forceinline__ void stg_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void stg_d2(double* p, double a, double b) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
 // Out-of-line single block for the rare paths (chunk tails, counters >= 2^32).
@@ -515,16 +548,21 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     constexpr bool HAS_IN = (MODE == M_APPLY || MODE == M_ENCODE || MODE == M_DECODE);
     constexpr int PF = MMAX + 1;                 // pair iterations per item: ceil((64m + 2) / 64)
     constexpr uint32_t WB = WORDS * 4u;
+    constexpr bool QUAD_OK = (WORDS == 1 && MODE != M_SCATTER && MMAX >= 4);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t y = 0x00010000u | (lane << 2);
     const uint32_t sbase = smem_window_base();
-    const uint32_t slab_bytes = (NB * 32u * MMAX + 2u) * WB;
+    const uint32_t slab_bytes = (NB * 32u * MMAX + 2u + (WORDS == 1 ? 2u * MMAX + 1u : 0u)) * WB;
     if (sbase + nwarps * slab_bytes > TAB_BASE) { __trap(); }
     const uint32_t slab = sbase + warp * slab_bytes;
 #define PRE_OF(k) Pre{st.pre[k][0], st.pre[k][1], st.pre[k][2], st.pre[k][3]}
 
     fill_tables();
     __syncthreads();
+
+    // slab word index -> byte offset; 4-byte words are skewed by one word per 32 so that the
+    // lane-major stores (stride m) and the element-major loads never pile onto one bank
+    auto sl = [&](uint32_t i) -> uint32_t { return slab + (WORDS == 1 ? (i + (i >> 5)) : i) * WB; };
 
     const word_t mk = WT::mask(g.b);
     const uint32_t m = g.m;
@@ -553,6 +591,12 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
         const uint32_t lo_i = g.begin > item_e0 ? (uint32_t)(g.begin - base_e) : par;
         const uint32_t hi_i = (item_e0 + item_n) > g.end ? (uint32_t)(g.end > base_e ? g.end - base_e : 0) : par + item_n;
         const int64_t off0 = (int64_t)(base_e - g.begin);            // offset of slab index 0 in the shard buffers
+        // Fast path (4-byte words, m = 4, full item inside the shard, 16-byte aligned): a lane's AES
+        // block IS four consecutive elements, so it loads / stores them itself with 128-bit accesses
+        // (a warp covers 512 contiguous bytes) and nothing goes through the slab.
+        const bool quad = QUAD_OK && m == 4u && io.quad && par == 0u && item_n == NB * 128u && item_e0 >= g.begin &&
+                          item_e0 + item_n <= g.end && ((item_e0 - g.begin) & 3ull) == 0ull;
+        const uint64_t qoff = (item_e0 - g.begin) + 4ull * lane;     // block A's elements; block B: +128
 
         // one AES pass: F(iter, prf) for this lane's two blocks, accumulated with sign
         auto stream_into = [&](uint32_t sidx, int sign, word_t (&acc)[NB][MMAX]) {
@@ -583,7 +627,14 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
             const bool emit = !SHARE || cc > 0;
             // ---- 1. prefetch inputs (pairs) ----
             in_t pf[PF][2];
-            if (HAS_IN && emit) {
+            if (HAS_IN && emit && QUAD_OK && quad) {
+                if constexpr (QUAD_OK && HAS_IN) {
+                    const in_t* in = reinterpret_cast<const in_t*>(io.in) + (uint64_t)c * io.in_stride + qoff;
+                    uint32_t* r = reinterpret_cast<uint32_t*>(&pf[0][0]);
+                    ldg_v4(in, r[0], r[1], r[2], r[3]);
+                    ldg_v4(in + 128, r[4], r[5], r[6], r[7]);
+                }
+            } else if (HAS_IN && emit) {
                 const in_t* in = reinterpret_cast<const in_t*>(io.in) + (uint64_t)c * io.in_stride;
 #pragma unroll
                 for (int k = 0; k < PF; ++k) {
@@ -620,13 +671,66 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                     }
                 if (!emit) continue;
             }
+            // ---- 3q. fast path: the lane applies its own blocks ----
+            if (QUAD_OK && quad) {
+                if constexpr (QUAD_OK) {
+                    const uint32_t mk32 = Word<1>::mask(g.b);
+#pragma unroll
+                    for (int h = 0; h < NB; ++h) {
+                        const uint64_t o = qoff + 128u * h;
+                        const uint64_t j = item_e0 + 4ull * lane + 128u * h;
+                        uint32_t mw[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) mw[k] = (uint32_t)acc[h][k] & mk32;
+                        const uint32_t* r = reinterpret_cast<const uint32_t*>(&pf[0][0]) + 4 * h;
+                        if (MODE == M_MASKS) {
+                            stg_v4(reinterpret_cast<uint32_t*>(io.out) + o, mw[0], mw[1], mw[2], mw[3]);
+                        } else if (MODE == M_APPLY) {
+                            uint32_t* out = reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o;
+                            stg_v4(out, (r[0] + mw[0]) & mk32, (r[1] + mw[1]) & mk32, (r[2] + mw[2]) & mk32, (r[3] + mw[3]) & mk32);
+                        } else if (MODE == M_ENCODE) {
+                            double u[4];
+                            if (nz.u) {
+                                const double* up = nz.u + (uint64_t)c * nz.u_stride + o;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) u[k] = up[k];
+                            } else {
+                                noise_pair(nz, nz.stream + c, j >> 1, u[0], u[1]);
+                                noise_pair(nz, nz.stream + c, (j >> 1) + 1, u[2], u[3]);
+                            }
+                            uint32_t q[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const Seg& sg = find_seg(cd, j + k);
+                                q[k] = encode_one(__uint_as_float(r[k]), u[k], sg.a, sg.two_a, cd.scale);
+                            }
+                            if (io.aux) stg_v4(reinterpret_cast<uint32_t*>(io.aux) + (uint64_t)c * io.out_stride + o, q[0], q[1], q[2], q[3]);
+                            uint32_t* out = reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o;
+                            stg_v4(out, (q[0] + mw[0]) & mk32, (q[1] + mw[1]) & mk32, (q[2] + mw[2]) & mk32, (q[3] + mw[3]) & mk32);
+                        } else if (MODE == M_DECODE) {
+                            uint32_t pw[4];
+                            double dv[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                pw[k] = (r[k] + mw[k]) & mk32;
+                                const Seg& sg = find_seg(cd, j + k);
+                                dv[k] = decode_one((double)pw[k], sg.two_an, cd.den, sg.an);
+                            }
+                            if (io.aux) stg_v4(reinterpret_cast<uint32_t*>(io.aux) + o, pw[0], pw[1], pw[2], pw[3]);
+                            stg_d2(io.outf + o, dv[0], dv[1]);
+                            stg_d2(io.outf + o + 2, dv[2], dv[3]);
+                        }
+                    }
+                }
+                continue;
+            }
             // ---- 3. lane-major -> element-major through the warp's slab ----
             __syncwarp();
 #pragma unroll
             for (int h = 0; h < NB; ++h)
 #pragma unroll
                 for (int k = 0; k < MMAX; ++k)
-                    if ((uint32_t)k < m) slab_store<WORDS>(slab + (par + (lane + 32u * h) * m + k) * WB, acc[h][k]);
+                    if ((uint32_t)k < m) slab_store<WORDS>(sl(par + (lane + 32u * h) * m + k), acc[h][k]);
             __syncwarp();
 
             // ---- 4. element pairs ----
@@ -638,8 +742,8 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                 const bool v0 = i0 >= lo_i && i0 < hi_i, v1 = i0 + 1 >= lo_i && i0 + 1 < hi_i;
                 if (!v0 && !v1) continue;
                 const uint64_t j0 = base_e + i0;
-                word_t mw0 = WT::band(slab_load<WORDS>(slab + i0 * WB), mk);
-                word_t mw1 = WT::band(slab_load<WORDS>(slab + (i0 + 1) * WB), mk);
+                word_t mw0 = WT::band(slab_load<WORDS>(sl(i0)), mk);
+                word_t mw1 = WT::band(slab_load<WORDS>(sl(i0 + 1)), mk);
                 const int64_t o0 = off0 + i0;
                 if (MODE == M_MASKS) {
                     word_t* out = reinterpret_cast<word_t*>(io.out);
@@ -1211,7 +1315,7 @@ static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geo
     }
     const uint64_t items = (st.batch && !io.share) ? g.W_cnt * io.n_clients : g.W_cnt;
     if (items == 0) return FLASHE_OK;
-    const int slab_bytes = (2 * 32 * MMAX + 2) * WORDS * 4;
+    const int slab_bytes = (2 * 32 * MMAX + 2 + (WORDS == 1 ? 2 * MMAX + 1 : 0)) * WORDS * 4;
     int threads = STREAM_THREADS;
     while (threads > 32 && (threads / 32) * slab_bytes > 60 * 1024) threads >>= 1;
     const int wpb = threads / 32;
@@ -1223,10 +1327,16 @@ static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geo
     return FLASHE_OK;
 }
 
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
 template <int MODE>
-static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,
+static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io_in, const CodecDev& cd,
                          const NoiseDev& nz, cudaStream_t stream) {
     const int b = ctx->int_bits;
+    IoDev io = io_in;
+    // 128-bit fast path preconditions (4-byte words): every row of every buffer starts 16-byte aligned
+    io.quad = (ctx->words == 1 && MODE != M_SCATTER && aligned16(io.in) && aligned16(io.out) && aligned16(io.aux) &&
+               aligned16(io.outf) && (io.n_clients <= 1 || ((io.in_stride | io.out_stride) & 3ull) == 0)) ? 1u : 0u;
     if constexpr (MODE == M_ENCODE) {
         if (io.share) {
             if (b <= 32) {

@@ -457,3 +457,47 @@ def test_quantizing_client_seed_level_parity(fb, golden):
         qc.shape_list = [(L,)]
         qc.unquantize(w2)
         assert np.array_equal(np.asarray(w2._weights["layer0"], dtype=np.float64).view(np.uint64), golden["batch_decoded"].view(np.uint64))
+
+
+@pytest.mark.parametrize("bits,n_jobs,L", [(32, 8, 1 << 20), (32, 16, 3_000_000), (28, 4, 600_000)])
+def test_aligned_fast_path_vs_oracle(fb, bits, n_jobs, L):
+    """m = 4 with 16-byte aligned chunk starts takes the 128-bit lane-local path; every mode must
+    agree with the oracle, for whole vectors and for shards cut on and off 4-element boundaries."""
+    ctx = ctx_for(fb, bits)
+    it, n = 9, 3
+    rs = np.random.RandomState(123)
+    x = (rs.standard_normal((n, L)) * 0.1).astype(np.float32)
+    u = rs.random_sample((n, L))
+    alpha = 0.59383450
+    codec = fb.CodecSpec(alpha=alpha, element_bits=16, n_clients=n)
+    q = np.stack([O.quantize(x[k], u[k], alpha, 16) for k in range(n)])
+    ct_want = np.stack([O.encrypt(KEY, bits, n_jobs, it, k, "double", q[k]) for k in range(n)])
+    full = fb.VectorSpan(L, n_jobs)
+    # masks / apply / encode(+q_out, given noise) / batch / share
+    assert np.array_equal(_np(ctx.masks(it, [1, 2], [1, -1], full)), O.masks(KEY, bits, n_jobs, it, [1, 2], [1, -1], L))
+    assert np.array_equal(_np(ctx.encrypt(it, 1, fb.SCHEME_DOUBLE, _dev(q[1]), full)), ct_want[1])
+    q_out = torch.empty(L, dtype=torch.uint32, device="cuda")
+    got = ctx.encode_encrypt(it, 2, fb.SCHEME_DOUBLE, _dev(x[2]), codec, fb.NoiseSpec(u=_dev(u[2])), full, q_out=q_out)
+    assert np.array_equal(_np(got), ct_want[2]) and np.array_equal(_np(q_out), q[2])
+    for share in (False, True):
+        got = ctx.encode_encrypt_batch(it, 0, fb.SCHEME_DOUBLE, _dev(x), codec, fb.NoiseSpec(u=_dev(u).reshape(-1)), full, share_streams=share)
+        assert np.array_equal(_np(got), ct_want), share
+    # device noise on the fast path equals rng_uniform
+    got = ctx.encode_encrypt(it, 0, fb.SCHEME_DOUBLE, _dev(x[0]), codec, fb.NoiseSpec(seed=99, stream=5), full)
+    ud = _np(ctx.rng_uniform(99, 5, 0, L))
+    assert np.array_equal(_np(got), O.encrypt(KEY, bits, n_jobs, it, 0, "double", O.quantize(x[0], ud, alpha, 16)))
+    # decrypt + decode
+    agg = O.aggregate(bits, ct_want)
+    p = ctx.empty_words(L)
+    out = ctx.decrypt_decode(it, [n], [0], _dev(agg), codec, full, p_out=p)
+    p_want = O.decrypt(KEY, bits, n_jobs, it, list(range(n)), "double", agg)
+    assert np.array_equal(_np(p), p_want)
+    assert np.array_equal(_np(out).view(np.uint64), O.unquantize(p_want, alpha, 16, n).view(np.uint64))
+    # shards: aligned cut, unaligned cut (falls back to the slab path at the edges), odd begin
+    for a, e in ((0, L // 2), (L // 2, L), (L // 4 + 1, L // 2 + 3), (4 * 1001, 4 * 1001 + 70001)):
+        sp = fb.VectorSpan(L, n_jobs, a, e - a)
+        got = ctx.encode_encrypt_batch(it, 0, fb.SCHEME_DOUBLE, _dev(np.ascontiguousarray(x[:, a:e])), codec,
+                                       fb.NoiseSpec(u=_dev(np.ascontiguousarray(u[:, a:e])).reshape(-1)), sp)
+        assert np.array_equal(_np(got), ct_want[:, a:e]), (a, e)
+        out = ctx.decrypt_decode(it, [n], [0], _dev(np.ascontiguousarray(agg[a:e])), codec, sp)
+        assert np.array_equal(_np(out).view(np.uint64), O.unquantize(p_want[a:e], alpha, 16, n).view(np.uint64)), (a, e)

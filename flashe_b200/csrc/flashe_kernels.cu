@@ -132,9 +132,11 @@ struct Geom {
     uint64_t L, begin, end;  // whole length, shard [begin,end)
     uint64_t d, r;           // divmod(L, n_jobs): first r chunks have d+1 elements
     uint64_t nwA, nwB;       // warp items per chunk (types: d+1 / d elements)
-    uint64_t rA;             // r * nwA
-    uint64_t W_lo, W_cnt;    // warp items that intersect the shard
+    uint64_t nsA, nsB;       // work units per chunk: ceil(nw / sup)
+    uint64_t rSA;            // r * nsA
+    uint64_t S_lo, S_cnt;    // work units that intersect the shard
     uint32_t m, b;           // slots per AES block, int_bits
+    uint32_t sup;            // warp items per work unit (consecutive items of one chunk)
 };
 
 struct Seg { uint64_t end; float a, two_a; double an, two_an; };
@@ -148,7 +150,7 @@ struct CodecDev {
     Seg seg[MAX_INLINE_SEG];
 };
 
-struct NoiseDev { const double* u; uint64_t u_stride; uint32_t k0, k1; uint64_t stream; };
+struct NoiseDev { const double* u; uint64_t u_stride; uint64_t stream; uint32_t rk[10][2]; };  // rk: Philox round keys
 
 struct IoDev {
     const void* in;  uint64_t in_stride;    // words (or floats) between consecutive clients
@@ -281,16 +283,22 @@ __device__ __forceinline__ void aes256_block(const KeySched& ks, uint32_t y, uin
 #define ITEM_BLOCKS 64u   // AES blocks per warp item (two per lane)
 struct Item { uint64_t cb; uint64_t clen; uint64_t i0; };  // chunk begin, chunk length, first block
 
-__device__ __forceinline__ Item decode_item(const Geom& g, uint64_t W) {
+// Work unit S -> first warp item of the unit and the number of items in it.  The two 64-bit divisions
+// happen once per unit; the items inside are walked incrementally.
+__device__ __forceinline__ Item decode_unit(const Geom& g, uint64_t S, uint32_t& nsub) {
     Item it;
-    if (W < g.rA) {
-        uint64_t k = W / g.nwA, w = W - k * g.nwA;
-        it.cb = k * (g.d + 1); it.clen = g.d + 1; it.i0 = w * ITEM_BLOCKS;
+    uint64_t s, nw;
+    if (S < g.rSA) {
+        const uint64_t k = S / g.nsA; s = S - k * g.nsA;
+        it.cb = k * (g.d + 1); it.clen = g.d + 1; nw = g.nwA;
     } else {
-        uint64_t Wp = W - g.rA;
-        uint64_t k = Wp / g.nwB, w = Wp - k * g.nwB;
-        it.cb = g.r * (g.d + 1) + k * g.d; it.clen = g.d; it.i0 = w * ITEM_BLOCKS;
+        const uint64_t Sp = S - g.rSA;
+        const uint64_t k = Sp / g.nsB; s = Sp - k * g.nsB;
+        it.cb = g.r * (g.d + 1) + k * g.d; it.clen = g.d; nw = g.nwB;
     }
+    const uint64_t w0 = s * g.sup, left = nw - w0;
+    it.i0 = w0 * ITEM_BLOCKS;
+    nsub = (uint32_t)(left < g.sup ? left : g.sup);
     return it;
 }
 
@@ -315,8 +323,10 @@ __device__ __forceinline__ uint32_t encode_one(float x, double u, float a, float
     v = __fadd_rn(v, a);
     v = __fmul_rn(v, scale);
     v = __fdiv_rn(v, two_a);
-    double r = floor(__dadd_rn((double)v, u));
-    return (uint32_t)(long long)r;
+    // floor(t) for 0 <= t < 2^32: t + 2^52 rounded towards -inf lands on the integer grid at
+    // 2^52 + floor(t); the integer is the low word of that double.  (v >= 0 by construction.)
+    const double t = __dadd_rn((double)v, u);
+    return (uint32_t)__double2loint(__dadd_rd(t, 4503599627370496.0));
 }
 
 // _static_unquantize_padding_asymmetric, jzf_quantize.py:102-107 (float64, left to right).
@@ -324,34 +334,40 @@ __device__ __forceinline__ double decode_one(double v, double two_an, double den
     return __dsub_rn(__ddiv_rn(__dmul_rn(v, two_an), den), an);
 }
 
-// Philox4x32-10 (Salmon et al. 2011), counter (c0,c1,c2,c3), key (k0,k1).
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t out[4]) {
+// Philox4x32-10 (Salmon et al. 2011), counter (c0,c1,c2,c3); the ten round keys
+// (k0 + i*0x9E3779B9, k1 + i*0xBB67AE85) are expanded on the host (NoiseDev.rk).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const NoiseDev& nz,
+                                              uint32_t out[4]) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
-        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ nz.rk[i][0], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ nz.rk[i][1];
         c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-// u_j in [0,1): counter (j>>1 lo, j>>1 hi, stream lo, stream hi); words (2(j&1), 2(j&1)+1) feed numpy's
-// res53 construction ((a>>5)*2^26 + (b>>6)) / 2^53.
+// numpy's res53 construction ((a>>5)*2^26 + (b>>6)) / 2^53 without integer->double conversions:
+// A = 2^25 + (a>>5)*2^-27 and B = 2^-1 + (b>>6)*2^-53 are assembled as bit patterns (exponent word |
+// mantissa low word); A - (2^25 + 2^-1) and the sum with B are exact, so the value is bit-identical.
+__device__ __forceinline__ double res53(uint32_t a, uint32_t b) {
+    const double A = __hiloint2double(0x41800000, (int)(a >> 5));
+    const double B = __hiloint2double(0x3FE00000, (int)(b >> 6));
+    return __dadd_rn(__dadd_rn(A, -33554432.5), B);
+}
+// u_j in [0,1): counter (j>>1 lo, j>>1 hi, stream lo, stream hi); words (2(j&1), 2(j&1)+1) feed res53.
 __device__ __forceinline__ double noise_one(const NoiseDev& nz, uint64_t stream, uint64_t j) {
     uint32_t o[4];
     uint64_t c = j >> 1;
-    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), nz.k0, nz.k1, o);
-    uint32_t a = (j & 1) ? o[2] : o[0], b = (j & 1) ? o[3] : o[1];
-    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), nz, o);
+    return (j & 1) ? res53(o[2], o[3]) : res53(o[0], o[1]);
 }
 
 // Both numbers of one Philox call: u for elements 2c and 2c+1 (same values as noise_one).
 __device__ __forceinline__ void noise_pair(const NoiseDev& nz, uint64_t stream, uint64_t c, double& u0, double& u1) {
     uint32_t o[4];
-    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), nz.k0, nz.k1, o);
-    u0 = ((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6)) * (1.0 / 9007199254740992.0);
-    u1 = ((double)(o[2] >> 5) * 67108864.0 + (double)(o[3] >> 6)) * (1.0 / 9007199254740992.0);
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), nz, o);
+    u0 = res53(o[0], o[1]);
+    u1 = res53(o[2], o[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -566,24 +582,29 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
 
     const word_t mk = WT::mask(g.b);
     const uint32_t m = g.m;
-    const uint64_t n_items = (st.batch && !io.share) ? g.W_cnt * io.n_clients : g.W_cnt;
+    const uint64_t n_units = (st.batch && !io.share) ? g.S_cnt * io.n_clients : g.S_cnt;
     const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, gstride = (uint64_t)gridDim.x * nwarps;
 
-    for (uint64_t t = gw; t < n_items; t += gstride) {
+    for (uint64_t t = gw; t < n_units; t += gstride) {
         uint32_t c_first = 0, c_count = 1;
-        uint64_t W = t;
+        uint64_t S = t;
         if (st.batch) {
             if (io.share) { c_first = 0; c_count = io.n_clients; }
-            else { c_first = (uint32_t)(t / g.W_cnt); W = t - (uint64_t)c_first * g.W_cnt; }
+            else { c_first = (uint32_t)(t / g.S_cnt); S = t - (uint64_t)c_first * g.S_cnt; }
         }
-        const Item it = decode_item(g, g.W_lo + W);
+        // a work unit = up to g.sup consecutive warp items of one chunk: the 64-bit divisions of the
+        // chunk rule are paid once per unit, the items inside advance by ITEM_BLOCKS
+        uint32_t nsub;
+        Item it = decode_unit(g, g.S_lo + S, nsub);
+      for (uint32_t sub = 0; sub < nsub; ++sub, it.i0 += ITEM_BLOCKS) {
+        const uint64_t item_e0 = it.cb + it.i0 * m;                  // first global element of the item
+        const uint64_t rem = it.clen - it.i0 * m;
+        const uint32_t item_n = (uint32_t)(rem < (uint64_t)(NB * 32u) * m ? rem : (uint64_t)(NB * 32u) * m);
+        if (item_e0 + item_n <= g.begin || item_e0 >= g.end) continue;   // item outside this shard
         const uint64_t blkA = it.i0 + lane, blkB = blkA + 32;
         const bool onA = blkA * m < it.clen, onB = blkB * m < it.clen;
         const uint64_t ctrA = it.cb + blkA, ctrB = it.cb + blkB;     // jzf_flashe.py:34 "(i + begin)"
         const bool fast = ((ctrB >> 32) == 0);                       // hoisted round 1 needs word 2 == 0
-        const uint64_t item_e0 = it.cb + it.i0 * m;                  // first global element of the item
-        const uint64_t rem = it.clen - it.i0 * m;
-        const uint32_t item_n = (uint32_t)(rem < (uint64_t)(NB * 32u) * m ? rem : (uint64_t)(NB * 32u) * m);
         const uint32_t par = (uint32_t)(item_e0 & 1ull);
         const uint64_t base_e = item_e0 - par;                       // even; slab index = j - base_e
         const uint32_t npairs = (par + item_n + 1u) >> 1;
@@ -795,6 +816,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                 }
             }
         }
+      }
     }
 #undef PRE_OF
 }
@@ -1213,24 +1235,36 @@ static int check_span(const flashe_span* s) {
 
 static uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
-static void make_geom(const flashe_ctx* ctx, const flashe_span* s, Geom* g) {
+static void make_geom(const flashe_ctx* ctx, const flashe_span* s, uint32_t sup, Geom* g) {
     memset(g, 0, sizeof(*g));
     g->L = s->total_len; g->begin = s->begin; g->end = s->begin + s->count;
     g->m = ctx->m; g->b = (uint32_t)ctx->int_bits;
     g->d = s->total_len / s->n_jobs; g->r = s->total_len % s->n_jobs;
     const uint64_t nbA = ceil_div(g->d + 1, g->m), nbB = g->d ? ceil_div(g->d, g->m) : 0;
     g->nwA = ceil_div(nbA, ITEM_BLOCKS); g->nwB = ceil_div(nbB, ITEM_BLOCKS);
-    g->rA = g->r * g->nwA;
-    if (s->count == 0) { g->W_lo = 0; g->W_cnt = 0; return; }
-    auto item_of = [&](uint64_t j) {
+    if (sup < 1) sup = 1;
+    g->sup = sup;
+    g->nsA = ceil_div(g->nwA, sup); g->nsB = ceil_div(g->nwB, sup);
+    g->rSA = g->r * g->nsA;
+    if (s->count == 0) { g->S_lo = 0; g->S_cnt = 0; return; }
+    auto unit_of = [&](uint64_t j) {
         uint64_t k, cb;
         if (j < g->r * (g->d + 1)) { k = j / (g->d + 1); cb = k * (g->d + 1); }
         else { k = g->r + (j - g->r * (g->d + 1)) / g->d; cb = g->r * (g->d + 1) + (k - g->r) * g->d; }
-        const uint64_t w = ((j - cb) / g->m) / ITEM_BLOCKS;
-        return (k < g->r ? k * g->nwA : g->rA + (k - g->r) * g->nwB) + w;
+        const uint64_t u = (((j - cb) / g->m) / ITEM_BLOCKS) / sup;
+        return (k < g->r ? k * g->nsA : g->rSA + (k - g->r) * g->nsB) + u;
     };
-    g->W_lo = item_of(g->begin);
-    g->W_cnt = item_of(g->end - 1) - g->W_lo + 1;
+    g->S_lo = unit_of(g->begin);
+    g->S_cnt = unit_of(g->end - 1) - g->S_lo + 1;
+}
+
+// Items per work unit: as large as possible (amortises the per-unit chunk decode) while every warp of
+// the persistent grid still gets at least ~32 units.
+static uint32_t pick_sup(const flashe_ctx* ctx, const flashe_span* s, uint64_t rows) {
+    const uint64_t items = ceil_div(ceil_div(s->count ? s->count : 1, ctx->m), ITEM_BLOCKS) * (rows ? rows : 1);
+    const uint64_t warps = (uint64_t)ctx->num_sms * (STREAM_THREADS / 32);
+    uint64_t sup = items / (warps * 32);
+    return (uint32_t)(sup < 1 ? 1 : (sup > 32 ? 32 : sup));
 }
 
 static int make_streams(const flashe_ctx* ctx, uint32_t iter, const int32_t* prf, const int32_t* sign, int n, StreamTab* st) {
@@ -1294,7 +1328,8 @@ static void make_noise(const flashe_noise* nz, uint64_t u_stride, NoiseDev* d) {
     memset(d, 0, sizeof(*d));
     if (!nz) return;
     d->u = nz->u; d->u_stride = u_stride;
-    d->k0 = (uint32_t)nz->rng_seed; d->k1 = (uint32_t)(nz->rng_seed >> 32);
+    uint32_t k0 = (uint32_t)nz->rng_seed, k1 = (uint32_t)(nz->rng_seed >> 32);
+    for (int i = 0; i < 10; ++i) { d->rk[i][0] = k0; d->rk[i][1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
     d->stream = nz->rng_stream;
 }
 
@@ -1313,7 +1348,7 @@ static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geo
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_set = true;
     }
-    const uint64_t items = (st.batch && !io.share) ? g.W_cnt * io.n_clients : g.W_cnt;
+    const uint64_t items = (st.batch && !io.share) ? g.S_cnt * io.n_clients : g.S_cnt;
     if (items == 0) return FLASHE_OK;
     const int slab_bytes = (2 * 32 * MMAX + 2 + (WORDS == 1 ? 2 * MMAX + 1 : 0)) * WORDS * 4;
     int threads = STREAM_THREADS;
@@ -1340,6 +1375,7 @@ static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom&
     if constexpr (MODE == M_ENCODE) {
         if (io.share) {
             if (b <= 32) {
+                if (ctx->m <= 4) return launch_stream_t<1, 4, MODE, true>(ctx, st, g, io, cd, nz, stream);
                 if (ctx->m <= 6) return launch_stream_t<1, 6, MODE, true>(ctx, st, g, io, cd, nz, stream);
                 return launch_stream_t<1, 16, MODE, true>(ctx, st, g, io, cd, nz, stream);
             }
@@ -1348,6 +1384,7 @@ static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom&
         }
     }
     if (b <= 32) {
+        if (ctx->m <= 4) return launch_stream_t<1, 4, MODE, false>(ctx, st, g, io, cd, nz, stream);
         if (ctx->m <= 6) return launch_stream_t<1, 6, MODE, false>(ctx, st, g, io, cd, nz, stream);
         return launch_stream_t<1, 16, MODE, false>(ctx, st, g, io, cd, nz, stream);
     }
@@ -1450,7 +1487,7 @@ int flashe_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf_idx, const i
     int rc = check_span(span); if (rc) return rc;
     if (span->count && !out) return fail(FLASHE_EINVAL, "out is NULL");
     StreamTab st; rc = make_streams(ctx, iter, prf_idx, sign, nstreams, &st); if (rc) return rc;
-    Geom g; make_geom(ctx, span, &g);
+    Geom g; make_geom(ctx, span, pick_sup(ctx, span, 1), &g);
     IoDev io; memset(&io, 0, sizeof(io)); io.out = out; io.n_clients = 1;
     CodecDev cd; memset(&cd, 0, sizeof(cd)); NoiseDev nz; memset(&nz, 0, sizeof(nz));
     return launch_stream<M_MASKS>(ctx, st, g, io, cd, nz, cs);
@@ -1462,7 +1499,7 @@ int flashe_apply_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf_idx, c
     int rc = check_span(span); if (rc) return rc;
     if (span->count && (!in || !out)) return fail(FLASHE_EINVAL, "in/out is NULL");
     StreamTab st; rc = make_streams(ctx, iter, prf_idx, sign, nstreams, &st); if (rc) return rc;
-    Geom g; make_geom(ctx, span, &g);
+    Geom g; make_geom(ctx, span, pick_sup(ctx, span, 1), &g);
     IoDev io; memset(&io, 0, sizeof(io)); io.in = in; io.out = out; io.n_clients = 1;
     CodecDev cd; memset(&cd, 0, sizeof(cd)); NoiseDev nz; memset(&nz, 0, sizeof(nz));
     return launch_stream<M_APPLY>(ctx, st, g, io, cd, nz, cs);
@@ -1551,7 +1588,7 @@ static int encode_encrypt_impl(flashe_ctx* ctx, uint32_t iter, int32_t idx0, int
     for (int k = 0; k < nent; ++k) prf[k] = idx0 + k;
     StreamTab st; rc = make_streams(ctx, iter, prf, nullptr, nent, &st); if (rc) return rc;
     st.batch = 1; st.dbl = dbl ? 1u : 0u;
-    Geom g; make_geom(ctx, span, &g);
+    Geom g; make_geom(ctx, span, pick_sup(ctx, span, (share && dbl) ? 1 : (uint64_t)n_clients), &g);
     CodecHost ch; rc = make_codec(ctx, span, codec, false, cs, &ch); if (rc) return rc;
     NoiseDev nz; make_noise(noise, u_stride, &nz);
     IoDev io; memset(&io, 0, sizeof(io));
@@ -1683,7 +1720,7 @@ int flashe_decrypt_decode(flashe_ctx* ctx, uint32_t iter, const int32_t* add_idx
     if (span->count == 0) return FLASHE_OK;
     if (!agg_in || !out) return fail(FLASHE_EINVAL, "NULL buffer");
     StreamTab st; rc = make_streams(ctx, iter, prf, sg, na + ns, &st); if (rc) return rc;
-    Geom g; make_geom(ctx, span, &g);
+    Geom g; make_geom(ctx, span, pick_sup(ctx, span, 1), &g);
     CodecHost ch; rc = make_codec(ctx, span, codec, true, cs, &ch); if (rc) return rc;
     IoDev io; memset(&io, 0, sizeof(io)); io.in = agg_in; io.outf = out; io.aux = p_out; io.n_clients = 1;
     NoiseDev nz; memset(&nz, 0, sizeof(nz));
@@ -1768,7 +1805,7 @@ int flashe_sparse_apply_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf
     if (span->count == 0) return FLASHE_OK;
     if (!index || !dense) return fail(FLASHE_EINVAL, "NULL buffer");
     StreamTab st; rc = make_streams(ctx, iter, prf_idx, sign, nstreams, &st); if (rc) return rc;
-    Geom g; make_geom(ctx, span, &g);
+    Geom g; make_geom(ctx, span, pick_sup(ctx, span, 1), &g);
     IoDev io; memset(&io, 0, sizeof(io)); io.out = dense; io.aux = (void*)index; io.n_clients = 1;
     CodecDev cd; memset(&cd, 0, sizeof(cd)); NoiseDev nz; memset(&nz, 0, sizeof(nz));
     return launch_stream<M_SCATTER>(ctx, st, g, io, cd, nz, cs);

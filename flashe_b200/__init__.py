@@ -9,6 +9,7 @@ Layout
                              (FlasheCipher, Encrypt, QuantizingClient, ACIQ)
   aggregate.py               the arbiter's arithmetic (server sums, expand_to_dense, dynamic_masking)
   sharding.py                element-range sharding over the GPUs of one box
+  precompute.py              MaskRing: masks of several future rounds (mask precomputation)
 
 There is no CPU implementation in this package; oracle/ (test infrastructure) holds one.
 """
@@ -16,3 +17,4 @@ __version__ = "0.1.0"
 
 from .device import (AGG_ELEMENTWISE, AGG_PACKED, SCHEME_DOUBLE, SCHEME_SINGLE, CodecSpec,  # noqa: F401
                      DeviceContext, NoiseSpec, VectorSpan)
+from .precompute import MaskRing  # noqa: F401,E402

@@ -48,6 +48,7 @@ SIGNATURES = {
     "flashe_ctx_device": (_int, [_vp]),
     "flashe_prp_block": (_int, [_vp, _u8p, _u8p, _vp]),
     "flashe_masks": (_int, [_vp, _u32, _i32p, _i32p, _int, _spanp, _vp, _vp]),
+    "flashe_precompute": (_int, [_vp, _u32, _int, _i32p, _i32p, _int, _spanp, _vp, _u64, _vp]),
     "flashe_apply_masks": (_int, [_vp, _u32, _i32p, _i32p, _int, _spanp, _vp, _vp, _vp]),
     "flashe_encrypt": (_int, [_vp, _u32, C.c_int32, _int, _spanp, _vp, _vp, _vp]),
     "flashe_decrypt": (_int, [_vp, _u32, _i32p, _int, _i32p, _int, _spanp, _vp, _vp, _vp]),

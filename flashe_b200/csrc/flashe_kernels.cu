@@ -139,7 +139,7 @@ struct Geom {
     uint32_t sup;            // warp items per work unit (consecutive items of one chunk)
 };
 
-struct Seg { uint64_t end; float a, two_a; double an, two_an; };
+struct Seg { uint64_t end; float a, two_a; float rcp_two_a, pad; double an, two_an; };  // rcp_two_a = RN(1/two_a), 0 = not usable
 
 struct CodecDev {
     int32_t nseg;
@@ -305,24 +305,53 @@ __device__ __forceinline__ Item decode_unit(const Geom& g, uint64_t S, uint32_t&
 // ------------------------------------------------------------------------------------------------
 // device: encode / decode / noise
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ const Seg& find_seg(const CodecDev& c, uint64_t j) {
+// Layer parameters of element j, BY VALUE: the single-layer case reads the constant bank directly,
+// an inline table is searched in the constant bank, a large one in global memory (a reference return
+// would force generic loads for all three).
+__device__ __forceinline__ Seg find_seg(const CodecDev& c, uint64_t j) {
     if (c.nseg == 1) return c.seg[0];
-    const Seg* tab = c.table ? c.table : c.seg;
     int lo = 0, hi = c.nseg - 1;
+    if (c.table) {
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (j < __ldg(&c.table[mid].end)) hi = mid; else lo = mid + 1;
+        }
+        Seg r; const Seg* t = c.table + lo;
+        r.end = __ldg(&t->end); r.a = __ldg(&t->a); r.two_a = __ldg(&t->two_a); r.rcp_two_a = __ldg(&t->rcp_two_a); r.pad = 0.f;
+        r.an = __ldg(&t->an); r.two_an = __ldg(&t->two_an);
+        return r;
+    }
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
-        if (j < tab[mid].end) hi = mid; else lo = mid + 1;
+        if (j < c.seg[mid].end) hi = mid; else lo = mid + 1;
     }
-    return tab[lo];
+    return c.seg[lo];
 }
 
 // _static_quantize_padding_asymmetric, jzf_quantize.py:55-67: four float32 ops in the reference's
 // order (no FMA contraction), then float64 add of the noise, floor, int.
-__device__ __forceinline__ uint32_t encode_one(float x, double u, float a, float two_a, float scale) {
-    float v = fminf(fmaxf(x, -a), a);
-    v = __fadd_rn(v, a);
+// IEEE-754 round-to-nearest v / d for a divisor whose correctly rounded reciprocal y = RN(1/d) is known
+// (the host computes it exactly).  q0 = RN(v*y) is within 1.5 ulp of v/d; one FMA residual correction
+// makes it faithful, and Markstein's theorem (y correctly rounded, q faithful) makes the second
+// correction the correctly rounded quotient (tests/native/div_rcp_check.c sweeps it on the CPU).
+// The residuals are exact only without underflow.  The host offers y only for alpha in [2^-41, 2^59];
+// the numerator v = fl(fl(clip(x) + alpha) * (2^e - 1)) is then 0 or >= alpha * 2^-24 * (2^e - 1) > 2^-60
+// (x + alpha is 0 or at least half an ulp of alpha), so no element needs a range check; other
+// alphas are flagged by y == 0 and take the library division.
+__device__ __forceinline__ float div_rn_known_rcp(float v, float d, float y) {
+    if (y == 0.0f) return __fdiv_rn(v, d);
+    float q = __fmul_rn(v, y);
+    float r = __fmaf_rn(-d, q, v);
+    q = __fmaf_rn(r, y, q);
+    r = __fmaf_rn(-d, q, v);
+    return __fmaf_rn(r, y, q);
+}
+
+__device__ __forceinline__ uint32_t encode_one(float x, double u, const Seg& sg, float scale) {
+    float v = fminf(fmaxf(x, -sg.a), sg.a);
+    v = __fadd_rn(v, sg.a);
     v = __fmul_rn(v, scale);
-    v = __fdiv_rn(v, two_a);
+    v = div_rn_known_rcp(v, sg.two_a, sg.rcp_two_a);
     // floor(t) for 0 <= t < 2^32: t + 2^52 rounded towards -inf lands on the integer grid at
     // 2^52 + floor(t); the integer is the low word of that double.  (v >= 0 by construction.)
     const double t = __dadd_rn((double)v, u);
@@ -495,6 +524,16 @@ __device__ __noinline__ void aes256_block_slow(const KeySched& ks, uint32_t y, u
     o[0] = t[0]; o[1] = t[1]; o[2] = t[2]; o[3] = t[3];
 }
 
+// Unroll factor of the six double-rounds of aes256_x2.  Rolled (1) is the measured optimum: the fully
+// unrolled form makes the hot loop ~40 KB of SASS and the kernel loses ~5 % to instruction-fetch stalls
+// (stall_no_inst); rolled, the round keys come from the constant bank through a uniform index.
+#define FLASHE_PRAGMA_(x) _Pragma(#x)
+#define FLASHE_PRAGMA(x) FLASHE_PRAGMA_(x)
+#ifndef FLASHE_AES_UNROLL
+#define FLASHE_AES_UNROLL 1
+#endif
+#define AES_ROUNDS_UNROLL FLASHE_PRAGMA(unroll FLASHE_AES_UNROLL)
+
 // Two AES-256 blocks of the SAME stream (counters w3a, w3b; words 0-2 shared, word 2 == 0) computed
 // in one instruction stream: twice the independent lookups per round, so the round-boundary latency
 // (LDS ~30 clk + LOP3) of one block hides under the other's.
@@ -506,7 +545,7 @@ __device__ __forceinline__ void aes256_x2(const KeySched& ks, uint32_t y, Pre pr
     p1 = pre.p1 ^ T2(a3); q1 = pre.p1 ^ T2(b3);
     p2 = pre.p2 ^ T1(a3); q2 = pre.p2 ^ T1(b3);
     p3 = pre.p3 ^ T0(a3); q3 = pre.p3 ^ T0(b3);
-#pragma unroll
+    AES_ROUNDS_UNROLL
     for (int r = 2; r < 14; r += 2) {
         a0 = T0(p0) ^ T1(p1) ^ T2(p2) ^ T3(p3) ^ ks.rk[4 * r + 0];
         b0 = T0(q0) ^ T1(q1) ^ T2(q2) ^ T3(q3) ^ ks.rk[4 * r + 0];
@@ -720,10 +759,11 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                                 noise_pair(nz, nz.stream + c, (j >> 1) + 1, u[2], u[3]);
                             }
                             uint32_t q[4];
+                            Seg sg = find_seg(cd, j);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const Seg& sg = find_seg(cd, j + k);
-                                q[k] = encode_one(__uint_as_float(r[k]), u[k], sg.a, sg.two_a, cd.scale);
+                                if (k && j + k >= sg.end) sg = find_seg(cd, j + k);
+                                q[k] = encode_one(__uint_as_float(r[k]), u[k], sg, cd.scale);
                             }
                             if (io.aux) stg_v4(reinterpret_cast<uint32_t*>(io.aux) + (uint64_t)c * io.out_stride + o, q[0], q[1], q[2], q[3]);
                             uint32_t* out = reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o;
@@ -731,10 +771,11 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                         } else if (MODE == M_DECODE) {
                             uint32_t pw[4];
                             double dv[4];
+                            Seg sg = find_seg(cd, j);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 pw[k] = (r[k] + mw[k]) & mk32;
-                                const Seg& sg = find_seg(cd, j + k);
+                                if (k && j + k >= sg.end) sg = find_seg(cd, j + k);
                                 dv[k] = decode_one((double)pw[k], sg.two_an, cd.den, sg.an);
                             }
                             if (io.aux) stg_v4(reinterpret_cast<uint32_t*>(io.aux) + o, pw[0], pw[1], pw[2], pw[3]);
@@ -784,14 +825,14 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                         noise_pair(nz, nz.stream + c, j0 >> 1, u0, u1);
                     }
                     if (v0) {
-                        const Seg& sg = find_seg(cd, j0);
-                        uint32_t q = encode_one(*reinterpret_cast<float*>(&pf[k][0]), u0, sg.a, sg.two_a, cd.scale);
+                        const Seg sg = find_seg(cd, j0);
+                        uint32_t q = encode_one(*reinterpret_cast<float*>(&pf[k][0]), u0, sg, cd.scale);
                         if (io.aux) reinterpret_cast<uint32_t*>(io.aux)[(uint64_t)c * io.out_stride + o0] = q;
                         out[o0] = WT::band(WT::add(WT::from_u32(q), mw0), mk);
                     }
                     if (v1) {
-                        const Seg& sg = find_seg(cd, j0 + 1);
-                        uint32_t q = encode_one(*reinterpret_cast<float*>(&pf[k][1]), u1, sg.a, sg.two_a, cd.scale);
+                        const Seg sg = find_seg(cd, j0 + 1);
+                        uint32_t q = encode_one(*reinterpret_cast<float*>(&pf[k][1]), u1, sg, cd.scale);
                         if (io.aux) reinterpret_cast<uint32_t*>(io.aux)[(uint64_t)c * io.out_stride + o0 + 1] = q;
                         out[o0 + 1] = WT::band(WT::add(WT::from_u32(q), mw1), mk);
                     }
@@ -799,13 +840,13 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                     if (v0) {
                         word_t pw = WT::band(WT::add(*reinterpret_cast<word_t*>(&pf[k][0]), mw0), mk);
                         if (io.aux) reinterpret_cast<word_t*>(io.aux)[o0] = pw;
-                        const Seg& sg = find_seg(cd, j0);
+                        const Seg sg = find_seg(cd, j0);
                         io.outf[o0] = decode_one(WT::to_double(pw), sg.two_an, cd.den, sg.an);
                     }
                     if (v1) {
                         word_t pw = WT::band(WT::add(*reinterpret_cast<word_t*>(&pf[k][1]), mw1), mk);
                         if (io.aux) reinterpret_cast<word_t*>(io.aux)[o0 + 1] = pw;
-                        const Seg& sg = find_seg(cd, j0 + 1);
+                        const Seg sg = find_seg(cd, j0 + 1);
                         io.outf[o0 + 1] = decode_one(WT::to_double(pw), sg.two_an, cd.den, sg.an);
                     }
                 } else if (MODE == M_SCATTER) {
@@ -880,9 +921,9 @@ __global__ void k_encode(const float* __restrict__ x, const typename Word<WORDS>
     const typename WT::T mk = WT::mask(b);
     for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < count; o += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t j = begin + o;
-        const Seg& sg = find_seg(cd, j);
+        const Seg sg = find_seg(cd, j);
         double u = nz.u ? nz.u[o] : noise_one(nz, nz.stream, j);
-        uint32_t q = encode_one(x[o], u, sg.a, sg.two_a, cd.scale);
+        uint32_t q = encode_one(x[o], u, sg, cd.scale);
         if (q_out) q_out[o] = q;
         if (WITH_MASK) ct_out[o] = WT::band(WT::add(WT::from_u32(q), mask[o]), mk);
     }
@@ -893,7 +934,7 @@ __global__ void k_decode(const typename Word<WORDS>::T* __restrict__ v, uint64_t
                          const __grid_constant__ CodecDev cd, double* __restrict__ out) {
     typedef Word<WORDS> WT;
     for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < count; o += (uint64_t)gridDim.x * blockDim.x) {
-        const Seg& sg = find_seg(cd, begin + o);
+        const Seg sg = find_seg(cd, begin + o);
         out[o] = decode_one(WT::to_double(v[o]), sg.two_an, cd.den, sg.an);
     }
 }
@@ -1301,6 +1342,11 @@ static int make_codec(const flashe_ctx* ctx, const flashe_span* span, const flas
         segs[s].end = c->seg_end[s];
         segs[s].a = (float)c->alpha[s];
         segs[s].two_a = (float)(2.0 * c->alpha[s]);
+        // RN(1/two_a): the double quotient is at least 2^-49 (relative) away from any float rounding
+        // boundary, so rounding it to float cannot double-round
+        const float ta = segs[s].two_a;
+        segs[s].rcp_two_a = (ta >= 9.094947017729282e-13f /* 2^-40 */ && ta <= 1.152921504606847e18f /* 2^60 */) ? (float)(1.0 / (double)ta) : 0.0f;
+        segs[s].pad = 0.0f;
         volatile double an = c->alpha[s] * (double)n;     // alpha *= num_clients (jzf_quantize.py:103)
         segs[s].an = an;
         segs[s].two_an = 2.0 * an;
@@ -1491,6 +1537,20 @@ int flashe_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf_idx, const i
     IoDev io; memset(&io, 0, sizeof(io)); io.out = out; io.n_clients = 1;
     CodecDev cd; memset(&cd, 0, sizeof(cd)); NoiseDev nz; memset(&nz, 0, sizeof(nz));
     return launch_stream<M_MASKS>(ctx, st, g, io, cd, nz, cs);
+}
+
+int flashe_precompute(flashe_ctx* ctx, uint32_t iter_from, int n_rounds, const int32_t* prf_idx, const int32_t* sign, int nstreams,
+                      const flashe_span* span, void* out, uint64_t round_stride, void* stream) {
+    if (!ctx) return fail(FLASHE_EINVAL, "ctx is NULL");
+    if (n_rounds < 0) return fail(FLASHE_EINVAL, "n_rounds must be >= 0");
+    int rc = check_span(span); if (rc) return rc;
+    if (n_rounds > 1 && round_stride < span->count) return fail(FLASHE_EINVAL, "round_stride must be >= span.count");
+    for (int r = 0; r < n_rounds; ++r) {
+        rc = flashe_masks(ctx, iter_from + (uint32_t)r, prf_idx, sign, nstreams, span,
+                          (uint8_t*)out + (size_t)r * round_stride * 4u * (size_t)ctx->words, stream);
+        if (rc) return rc;
+    }
+    return FLASHE_OK;
 }
 
 int flashe_apply_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf_idx, const int32_t* sign, int nstreams,

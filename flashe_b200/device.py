@@ -171,6 +171,13 @@ class DeviceContext(object):
                                           C.byref(span.c()), out.data_ptr(), self._stream()))
         return out
 
+    def precompute(self, iter_from, n_rounds, prf_idx, sign, span: VectorSpan, out=None):
+        """Combined keystreams of rounds iter_from .. iter_from+n_rounds-1 -> words [n_rounds, span.n]."""
+        out = self.empty_words(span.n, rows=n_rounds) if out is None else self._check_words(out, n_rounds * span.n, "out")
+        _cabi.check(self.lib.flashe_precompute(self._h, iter_from & 0xFFFFFFFF, n_rounds, _i32(prf_idx), _i32(sign),
+                                               len(prf_idx), C.byref(span.c()), out.data_ptr(), span.n, self._stream()))
+        return out
+
     def apply_masks(self, it, prf_idx, sign, words, span: VectorSpan, out=None):
         self._check_words(words, span.n, "words")
         out = torch.empty_like(words) if out is None else self._check_words(out, span.n, "out")

@@ -81,6 +81,7 @@ class FlasheCipher(Encrypt):
 
         self._ctx = None
         self._retract = ([], [])   # (add, minus) index lists that undo precomputed decrypt terms
+        self._ring = None          # MaskRing: encrypt masks for several future rounds (prepare_encrypt(rounds=k))
 
     # ------------------------------------------------------------------ bookkeeping (jzf_flashe.py:262-304)
     def set_num_clients(self, num_clients):
@@ -212,7 +213,10 @@ class FlasheCipher(Encrypt):
     def _multiprocessing_encrypt(self, value):
         ctx = self._ctx
         q = self._to_device(value)
-        if 'add' not in self.next_iter_encrypt_prepared:
+        if 'add' not in self.next_iter_encrypt_prepared and self._ring is not None and \
+                self._ring.has(self.iter_index) and self._ring.span.n == self._len(value):
+            ct = self._ring.encrypt(self.iter_index, q)          # a round prepared further ahead
+        elif 'add' not in self.next_iter_encrypt_prepared:
             ct = ctx.encrypt(self.iter_index, self._prefix_idx(self.index_prefix_for_add), SCHEME_DOUBLE, q,
                              self._span(self._len(value)))
         else:
@@ -283,11 +287,22 @@ class FlasheCipher(Encrypt):
         return self._multiprocessing_decrypt_single(ciphertext)
 
     # ------------------------------------------------------------------ precompute (jzf_flashe.py:596-666)
-    def prepare_encrypt(self):
+    def prepare_encrypt(self, rounds=1):
         """Masks for the NEXT round (iter_index + 1) over num_params elements.  The reference keeps
         'add' and 'minus' as two object arrays; here 'add' is the combined device buffer
-        (F(t+1,c) - F(t+1,c+1)) mod 2^b and 'minus' is None — the ciphertext is identical."""
+        (F(t+1,c) - F(t+1,c+1)) mod 2^b and 'minus' is None — the ciphertext is identical.
+
+        rounds > 1 (extension, BASELINE config 3): rounds iter_index+1 .. iter_index+rounds are
+        generated into a MaskRing; encrypt() consumes the slot of its iter_index when it is there and
+        falls back to on-the-fly generation otherwise, exactly like the reference does when
+        'add' is absent (jzf_flashe.py:457)."""
         it = self.iter_index + 1
+        if rounds > 1:
+            from ..precompute import MaskRing
+            if self._ring is None or self._ring.rounds != rounds or self._ring.span.n != self.num_params:
+                self._ring = MaskRing.for_encrypt(self._ctx, self.idx, self._span(self.num_params), rounds, "double")
+            self._ring.fill(it, rounds)
+            return
         self.next_iter_encrypt_prepared = {
             'add': self._ctx.masks(it, [self.idx, self.idx + 1], [1, -1], self._span(self.num_params)),
             'minus': None,

@@ -107,6 +107,13 @@ int flashe_prp_block(flashe_ctx* ctx, const uint8_t in16[16], uint8_t out16[16],
 int flashe_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf_idx, const int32_t* sign, int nstreams,
                  const flashe_span* span, void* out, void* stream);
 
+/* Mask precomputation for several future rounds in one call (prepare_encrypt looks one round ahead,
+ * sp/jzf_flashe.py:599-631; BASELINE config 3 looks 16 ahead): for r in [0, n_rounds) the combined
+ * keystream of round iter_from + r is written to out + r*round_stride words.  Same stream list for
+ * every round (e.g. {idx, idx+1} with signs {+1, -1} for a client's double-masking term). */
+int flashe_precompute(flashe_ctx* ctx, uint32_t iter_from, int n_rounds, const int32_t* prf_idx, const int32_t* sign,
+                      int nstreams, const flashe_span* span, void* out, uint64_t round_stride, void* stream);
+
 /* out[j] = (in[j] + sum_k sign[k] * F(iter, prf_idx[k])[j]) mod 2^b.  in may equal out.
  * The arithmetic of _multiprocessing_encrypt(_single) / _multiprocessing_decrypt(_single)
  * (sp/jzf_flashe.py:431-488, 506-582) for an arbitrary stream list. */

@@ -254,3 +254,38 @@ def dynamic_masking(index_lists):
     sc, dc = C.c_uint64(), C.c_uint64()
     r = lib().fo_dynamic_masking(ptrs, ks, n, C.byref(sc), C.byref(dc))
     return ("single" if r == 0 else "double"), sc.value, dc.value
+
+
+# ---------------------------------------------------------------------------------------------------
+# Device noise generator, restated (throughput mode; include/flashe_b200.h: flashe_noise).  The
+# reference draws np.random.random (MT19937, never seeded); the device library instead documents a
+# counter-based stream: Philox4x32-10 (Salmon et al., SC'11; Random123 known answers in
+# tests/test_oracle_golden.py), key = the 64-bit seed, counter = (j >> 1, stream), and the two
+# word pairs of the output mapped to [0, 1) by numpy's res53 construction.
+# ---------------------------------------------------------------------------------------------------
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised over numpy uint64 arrays holding 32-bit values; returns four uint64 arrays."""
+    m32 = np.uint64(0xFFFFFFFF)
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) for c in (c0, c1, c2, c3))
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        n0 = (p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0)
+        n2 = (p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1)
+        c1, c3, c0, c2 = p1 & m32, p0 & m32, n0, n2
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def noise_uniform(seed, stream, begin, count):
+    """u_j for j in [begin, begin+count): what flashe_rng_uniform / the fused encode kernels draw."""
+    j = np.arange(begin, begin + count, dtype=np.uint64)
+    c = j >> np.uint64(1)
+    z = np.zeros_like(c)
+    o = philox4x32_10(c & np.uint64(0xFFFFFFFF), c >> np.uint64(32), z + np.uint64(int(stream) & 0xFFFFFFFF),
+                      z + np.uint64((int(stream) >> 32) & 0xFFFFFFFF), int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF)
+    odd = (j & np.uint64(1)).astype(bool)
+    a = np.where(odd, o[2], o[0])
+    b = np.where(odd, o[3], o[1])
+    return ((a >> np.uint64(5)).astype(np.float64) * 67108864.0 + (b >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0

@@ -501,3 +501,40 @@ def test_aligned_fast_path_vs_oracle(fb, bits, n_jobs, L):
         assert np.array_equal(_np(got), ct_want[:, a:e]), (a, e)
         out = ctx.decrypt_decode(it, [n], [0], _dev(np.ascontiguousarray(agg[a:e])), codec, sp)
         assert np.array_equal(_np(out).view(np.uint64), O.unquantize(p_want[a:e], alpha, 16, n).view(np.uint64)), (a, e)
+
+
+def test_device_noise_is_the_documented_philox_stream(fb):
+    """flashe_rng_uniform == oracle restatement (Philox4x32-10, counter (j>>1, stream), res53), incl.
+    odd begins, 64-bit seeds/streams and counters beyond 2^32."""
+    ctx = ctx_for(fb, 32)
+    for seed, stream, begin, cnt in [(0, 0, 0, 4097), (0x0123456789ABCDEF, 7, 5, 100001), (0xFFFFFFFFFFFFFFFF, 1 << 40, (1 << 33) + 3, 5000),
+                                     (42, 63, 99_999_999, 2)]:
+        got = _np(ctx.rng_uniform(seed, stream, begin, cnt))
+        want = O.noise_uniform(seed, stream, begin, cnt)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (seed, stream, begin)
+
+
+def test_encode_division_and_floor_tricks_dense_sweep(fb):
+    """The encode kernel divides through a host-computed reciprocal + FMA corrections and floors through
+    a round-down add; sweep a dense grid of float32 inputs (every 997th bit pattern across the clip
+    range, plus the clip edges, zeros and denormals) for many alphas and noise values against the
+    oracle's plain C arithmetic."""
+    ctx = ctx_for(fb, 32)
+    rs = np.random.RandomState(123)
+    for alpha in [0.5938345, 1.0, 0.1, 3.3e-4, 7.77e3, 1e-20, 2.5e15, float(np.float32(1.0) / 3)]:
+        a32 = np.float32(alpha)
+        hi = np.float32(a32 * np.float32(1.5)).view(np.uint32)
+        pos = np.arange(0, int(hi), 997, dtype=np.uint32)
+        bits = np.concatenate([pos, pos | np.uint32(0x80000000), np.array([0, 0x80000000, 1, 0x807FFFFF, 0x7F800000, 0xFF800000], dtype=np.uint32)])
+        x = bits.view(np.float32)
+        L = x.size
+        for mode in ("zero", "almost_one", "random"):
+            u = {"zero": np.zeros(L), "almost_one": np.full(L, 1.0 - 2.0 ** -53), "random": rs.random_sample(L)}[mode]
+            span = fb.VectorSpan(L, 8)
+            codec = fb.CodecSpec(alpha=float(alpha), element_bits=16)
+            got = _np(ctx.encode(_dev(x), codec, fb.NoiseSpec(u=_dev(u)), span))
+            want = O.quantize(x, u, float(alpha), 16)
+            assert np.array_equal(got, want), (alpha, mode)
+            # the fused kernel (quad path) agrees too
+            ct = _np(ctx.encode_encrypt(3, 1, fb.SCHEME_DOUBLE, _dev(x), codec, fb.NoiseSpec(u=_dev(u)), span))
+            assert np.array_equal(ct, O.encrypt(KEY, 32, 8, 3, 1, "double", want)), (alpha, mode)

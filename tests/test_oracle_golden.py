@@ -202,3 +202,25 @@ def test_python_port_matches_golden(golden):
         assert [int(v) for v in P.aggregate_packed(cts, b)] == [int(v) for v in golden.words(name + "_aggA", b)]
     for c in golden.cases("dropout"):
         assert P.collapse_runs(c["survivors"]) == (c["add"], c["minus"])
+
+
+def test_philox4x32_10_random123_known_answers():
+    """Random123 kat_vectors for philox4x32-10 pin the restated device noise generator."""
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        got = O.philox4x32_10(*[np.array([c], dtype=np.uint64) for c in ctr], key[0], key[1])
+        assert tuple(int(g[0]) for g in got) == want
+
+
+def test_noise_uniform_is_res53_of_philox():
+    u = O.noise_uniform(0x0123456789ABCDEF, 7, 5, 1001)
+    assert u.dtype == np.float64 and (u >= 0).all() and (u < 1).all()
+    # element j uses counter j>>1: elements 6 and 7 come from one Philox call
+    o = O.philox4x32_10(np.array([3], dtype=np.uint64), np.array([0], dtype=np.uint64), np.array([7], dtype=np.uint64),
+                        np.array([0], dtype=np.uint64), 0x89ABCDEF, 0x01234567)
+    w = [int(x[0]) for x in o]
+    assert u[1] == ((w[0] >> 5) * 67108864.0 + (w[1] >> 6)) / 9007199254740992.0
+    assert u[2] == ((w[2] >> 5) * 67108864.0 + (w[3] >> 6)) / 9007199254740992.0

@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--n-jobs", type=int, default=0, help="reference N_JOBS baked into the ciphertext format (0 = cpu_count())")
     ap.add_argument("--share-streams", type=int, default=0, help="compute F(t,c+1) once for clients c and c+1")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the share-streams and precomputed-mask rounds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-elements", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-clients", type=int, default=3)
@@ -261,6 +262,11 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = n * L / (ms_step * 1e-3)
 
+    # ---------------------------------------------------------------- same round, other legitimate schedules
+    variants = None
+    if not args.no_variants:
+        variants = run_variants(args, ctx, fb, span, codec, noise, scheme, x, cts, agg, out, world, dev, barrier)
+
     # ---------------------------------------------------------------- end to end (host buffers)
     e2e = None
     if not args.no_e2e:
@@ -305,11 +311,104 @@ def run_ours(args):
     }
     if e2e:
         line["e2e"] = e2e
+    if variants:
+        for v in variants.values():
+            if "ms_per_step" in v:
+                v["value"] = n * L / (v["ms_per_step"] * 1e-3)
+                v["frac_of_hbm_roofline_end_to_end"] = v["value"] / (hbm_peak * 1e9 / v["hbm_bytes_per_client_element"] * world)
+        pm = variants.get("precomputed_masks")
+        if pm and "online_encrypt_ms" in pm:
+            pm["online_encrypt_gbs"] = n * count * 12 / (pm["online_encrypt_ms"] * 1e-3) / 1e9
+            pm["online_encrypt_frac_of_hbm"] = pm["online_encrypt_gbs"] / hbm_peak
+        line["variants"] = variants
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, ctx, fb)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_variants(args, ctx, fb, span, codec, noise, scheme, x, cts, agg, out, world, dev, barrier):
+    """The same round under the two other schedules the path offers; outputs are bit-identical to the
+    headline round (checked here on the aggregate and on one client's ciphertext).
+      share_streams      F(t,c+1) computed once for clients c and c+1 hosted on the same GPU.
+      precomputed_masks  FLASHE's mask precomputation (jzf_flashe.py:596-666): the combined masks of the
+                         round are generated ahead of time (fill, timed separately, off the critical
+                         path in the reference's design) and the ONLINE round is encode + add of the
+                         stored mask -> aggregate -> decrypt+decode: HBM-bound."""
+    import torch
+    import torch.distributed as dist
+    n, count = x.shape
+    res = {}
+
+    def timed(fn, steps):
+        fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # reference outputs of the headline (on-the-fly, unshared) round
+    ctx.encode_encrypt_batch(0, 0, scheme, x, codec, noise, span, out=cts, share_streams=False)
+    ctx.aggregate(cts, fb.AGG_ELEMENTWISE, out=agg)
+    probe = min(5, n - 1)
+    agg_ref, row_ref = agg.clone(), cts[probe].clone()
+
+    def round_shared():
+        ctx.encode_encrypt_batch(0, 0, scheme, x, codec, noise, span, out=cts, share_streams=True)
+        ctx.aggregate(cts, fb.AGG_ELEMENTWISE, out=agg)
+        ctx.decrypt_decode(0, [n], [0], agg, codec, span, out=out)
+
+    ms = timed(round_shared, args.steps)
+    same = bool(torch.equal(agg.view(torch.int32), agg_ref.view(torch.int32)) and
+                torch.equal(cts[probe].view(torch.int32), row_ref.view(torch.int32)))
+    res["share_streams"] = {"ms_per_step": ms, "bit_exact_vs_headline_round": same, "hbm_bytes_per_client_element": 12.0 + 16.0 / n,
+                            "aes_blocks_per_round": (n + 1) * count * world // (128 // args.int_bits)}
+
+    try:
+        masks = ctx.empty_words(count, rows=n)
+    except RuntimeError as e:                                   # not enough HBM for the mask buffer
+        res["precomputed_masks"] = {"skipped": str(e)[:120]}
+        return res
+
+    def fill():
+        for c in range(n):
+            ctx.masks(0, [c, c + 1], [1, -1], span, out=masks[c])
+
+    fill_ms = timed(fill, 1)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    enc_ms = []
+
+    def round_online():
+        ev[0].record()
+        for c in range(n):
+            ctx.encode_add_premasked(x[c], codec, fb.NoiseSpec(seed=noise.seed, stream=noise.stream + c), masks[c], span, out=cts[c])
+        ev[1].record()
+        ctx.aggregate(cts, fb.AGG_ELEMENTWISE, out=agg)
+        ctx.decrypt_decode(0, [n], [0], agg, codec, span, out=out)
+
+    ms = timed(round_online, args.steps)
+    torch.cuda.synchronize()
+    enc_ms = ev[0].elapsed_time(ev[1])
+    same = bool(torch.equal(agg.view(torch.int32), agg_ref.view(torch.int32)) and
+                torch.equal(cts[probe].view(torch.int32), row_ref.view(torch.int32)))
+    t = torch.tensor([enc_ms, fill_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res["precomputed_masks"] = {"ms_per_step": ms, "online_encrypt_ms": float(t[0]), "fill_ms": float(t[1]),
+                                "fill_g_aes_blocks_per_s": 2 * n * count * world / (128 // args.int_bits) / (float(t[1]) * 1e-3) / 1e9,
+                                "mask_buffer_bytes_per_gpu": int(masks.numel() * masks.element_size()),
+                                "bit_exact_vs_headline_round": same, "hbm_bytes_per_client_element": 16.0 + 16.0 / n,
+                                "gpu_launches_per_round": n + 2}
+    del masks
+    return res
 
 
 def run_e2e(args, ctx, fb, span, codec, noise, scheme, x, cts, agg, out, world, dev, barrier):

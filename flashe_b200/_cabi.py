@@ -68,6 +68,11 @@ SIGNATURES = {
     "flashe_sparse_expand": (_int, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "flashe_sparse_apply_masks": (_int, [_vp, _u32, _i32p, _i32p, _int, _spanp, _vp, _vp, _vp]),
     "flashe_sparse_overlap": (_int, [_vp, C.POINTER(_vp), C.POINTER(_u64), _int, _u64, C.POINTER(_u64), _vp]),
+    "flashe_wire_nbytes": (_int, [_int, _u64, C.POINTER(_u64)]),
+    "flashe_wire_pack": (_int, [_vp, _vp, _int, _u64, _int, _vp, _vp]),
+    "flashe_wire_unpack": (_int, [_vp, _vp, _u64, _int, _int, _vp, _vp]),
+    "flashe_topk_sparsify": (_int, [_vp, _vp, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64), _int, _vp, _vp, _vp, _vp]),
+    "flashe_segment_stats": (_int, [_vp, _vp, _vp, _u64, C.POINTER(_u64), C.POINTER(C.c_double), _int, _vp, _vp]),
     "flashe_launch_count": (_u64, []),
 }
 

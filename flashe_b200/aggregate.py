@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from .device import AGG_ELEMENTWISE, AGG_PACKED, DeviceContext
+from .weights import _to_bytes
 
 _ctx_cache = {}
 
@@ -65,3 +66,48 @@ def dynamic_masking(masks, total, device=None):
     double_cost = 2 * single_cost - 2 * sum(ctx.sparse_overlap(lists, int(total)))
     choice = "single" if single_cost <= double_cost else "double"
     return {"choice": choice, "masks": masks, "single_cost": single_cost, "double_cost": double_cost}
+
+
+class SparsifyingClient(object):
+    """The sparsification state and step of the reference's aggregator Client
+    (jzf_aggregator.py:560-623): `_sparsity`, `remain_weights` (per-layer residuals carried across
+    rounds), `shape_dict_used_for_sparsification`.  `weights` is the reference's
+    JZFOrderDictWeights-shaped object (`walking_order`, `_weights` dict of float32 ndarrays).
+
+    All layers are handed to the GPU as one flat vector with a segment table (no per-layer launches of
+    argsort): radix-select top-k per layer, ordered compaction, residual update in the same pass."""
+
+    def __init__(self, sparsity=1.0, device=None):
+        self._sparsity = sparsity
+        self.remain_weights = None
+        self.shape_dict_used_for_sparsification = None
+        self.device = device
+        self._remain_dev = None          # flat float32 residual, kept on the device between rounds
+
+    def sparsify(self, weights):
+        """Returns (encoded_locations, le, bits, base) and replaces every layer of `weights` by its compact
+        top-k values, exactly like jzf_aggregator.py:578-623."""
+        ctx = _ctx(32, self.device)
+        keys = list(weights.walking_order)
+        shapes = {k: weights._weights[k].shape for k in keys}
+        sizes = [int(np.prod(shapes[k])) for k in keys]
+        ends = np.cumsum(sizes)
+        ks = [max(1, int(np.floor(self._sparsity * np.int64(n)))) for n in sizes]       # :598
+        flat = np.concatenate([np.asarray(weights._weights[k], dtype=np.float32).reshape(-1) for k in keys])
+        values, index, self._remain_dev = ctx.topk_sparsify(torch.from_numpy(flat).to(ctx.device), ends, ks,
+                                                            residual=self._remain_dev)
+        v = values.cpu().numpy()
+        rem = self._remain_dev.cpu().numpy()
+        self.remain_weights = {}
+        o = b = 0
+        for k, n, kk in zip(keys, sizes, ks):
+            weights._weights[k] = v[o:o + kk]
+            self.remain_weights[k] = rem[b:b + n]
+            o += kk
+            b += n
+        if self.shape_dict_used_for_sparsification is None:
+            self.shape_dict_used_for_sparsification = shapes
+        base = int(ends[-1]) if len(ends) else 0
+        bits = base.bit_length()
+        encoded_locations, le = _to_bytes(index.view(torch.uint64), bits, self.device)
+        return encoded_locations, le, bits, base

@@ -8,7 +8,8 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "flashe_kernels.cu")
+SRCS = [os.path.join(HERE, "csrc", f) for f in ("flashe_kernels.cu", "flashe_wire.cu")]
+DEPS = SRCS + [os.path.join(HERE, "csrc", "flashe_internal.h")]
 HDR = os.path.join(os.path.dirname(HERE), "include", "flashe_b200.h")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIB_DIR, "libflashe_b200.so")
@@ -28,14 +29,14 @@ def is_stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(p) > t for p in (SRC, HDR))
+    return any(os.path.getmtime(p) > t for p in DEPS + [HDR])
 
 
 def build_library(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SRCS
     subprocess.check_call(cmd)
     return LIB
 

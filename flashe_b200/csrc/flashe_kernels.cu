@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/flashe_b200.h"
+#include "flashe_internal.h"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -33,6 +34,8 @@ static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int flashe_fail(int code, const std::string& msg) { return fail(code, msg); }
+void flashe_count_launches(int n) { g_launches.fetch_add((uint64_t)n); }
 #define CUDA_TRY(expr)                                                                             \
     do {                                                                                           \
         cudaError_t e__ = (expr);                                                                  \
@@ -929,6 +932,35 @@ __global__ void k_encode(const float* __restrict__ x, const typename Word<WORDS>
     }
 }
 
+// Online step after mask precomputation, 4-byte words: one thread = 4 consecutive elements (begin and
+// every pointer 16-byte aligned), 128-bit loads of x and of the precomputed mask, two Philox calls for
+// the four noise values, one 128-bit store.  12 algorithmic bytes per element: HBM-bound.
+__global__ void __launch_bounds__(256)
+k_encode_premasked_v4(const uint4* __restrict__ x, const uint4* __restrict__ mask, uint64_t begin, uint64_t nvec, uint32_t mk,
+                      const __grid_constant__ CodecDev cd, const __grid_constant__ NoiseDev nz, uint4* __restrict__ ct_out) {
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t j = begin + 4ull * v;
+        const uint4 xv = __ldcs(x + v), mv = __ldcs(mask + v);
+        double u[4];
+        if (nz.u) {
+            const double2 a = __ldcs(reinterpret_cast<const double2*>(nz.u) + 2 * v), b = __ldcs(reinterpret_cast<const double2*>(nz.u) + 2 * v + 1);
+            u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y;
+        } else {
+            noise_pair(nz, nz.stream, j >> 1, u[0], u[1]);
+            noise_pair(nz, nz.stream, (j >> 1) + 1, u[2], u[3]);
+        }
+        const uint32_t xr[4] = {xv.x, xv.y, xv.z, xv.w};
+        uint32_t q[4];
+        Seg sg = find_seg(cd, j);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k && j + k >= sg.end) sg = find_seg(cd, j + k);
+            q[k] = encode_one(__uint_as_float(xr[k]), u[k], sg, cd.scale);
+        }
+        __stcs(ct_out + v, make_uint4((q[0] + mv.x) & mk, (q[1] + mv.y) & mk, (q[2] + mv.z) & mk, (q[3] + mv.w) & mk));
+    }
+}
+
 template <int WORDS>
 __global__ void k_decode(const typename Word<WORDS>::T* __restrict__ v, uint64_t begin, uint64_t count,
                          const __grid_constant__ CodecDev cd, double* __restrict__ out) {
@@ -1254,6 +1286,12 @@ struct flashe_ctx {
 };
 
 static int words_of(int b) { return b <= 32 ? 1 : (b <= 64 ? 2 : 4); }
+
+int flashe_ctx_get_info(const flashe_ctx* ctx, flashe_ctx_info* out) {
+    if (!ctx) return fail(FLASHE_EINVAL, "ctx is NULL");
+    out->device = ctx->device; out->int_bits = ctx->int_bits; out->words = ctx->words; out->num_sms = ctx->num_sms;
+    return FLASHE_OK;
+}
 
 struct DeviceGuard {
     int prev;
@@ -1681,7 +1719,18 @@ int flashe_encode_add_premasked(flashe_ctx* ctx, const flashe_span* span, const 
     NoiseDev nz; make_noise(noise, 0, &nz);
     const uint32_t b = (uint32_t)ctx->int_bits;
     const int grid = grid_1d(ctx, span->count, 256, 16);
-    if (ctx->words == 1) k_encode<1, true><<<grid, 256, 0, cs>>>(x, (const uint32_t*)mask, span->begin, span->count, b, ch.dev, nz, nullptr, (uint32_t*)ct_out);
+    const bool v4 = ctx->words == 1 && (span->begin & 3ull) == 0 &&
+                    ((((uintptr_t)x | (uintptr_t)mask | (uintptr_t)ct_out | (uintptr_t)nz.u) & 15u) == 0);
+    if (v4) {
+        const uint64_t nvec = span->count / 4, done = nvec * 4;
+        if (nvec) k_encode_premasked_v4<<<grid_1d(ctx, nvec, 256, 8), 256, 0, cs>>>((const uint4*)x, (const uint4*)mask, span->begin, nvec, Word<1>::mask(b), ch.dev, nz, (uint4*)ct_out);
+        if (done < span->count) {
+            NoiseDev nt = nz; if (nt.u) nt.u += done;
+            k_encode<1, true><<<1, 32, 0, cs>>>(x + done, (const uint32_t*)mask + done, span->begin + done, span->count - done, b, ch.dev, nt, nullptr, (uint32_t*)ct_out + done);
+            g_launches.fetch_add(nvec ? 1 : 0);
+        }
+    }
+    else if (ctx->words == 1) k_encode<1, true><<<grid, 256, 0, cs>>>(x, (const uint32_t*)mask, span->begin, span->count, b, ch.dev, nz, nullptr, (uint32_t*)ct_out);
     else if (ctx->words == 2) k_encode<2, true><<<grid, 256, 0, cs>>>(x, (const uint64_t*)mask, span->begin, span->count, b, ch.dev, nz, nullptr, (uint64_t*)ct_out);
     else k_encode<4, true><<<grid, 256, 0, cs>>>(x, (const u128*)mask, span->begin, span->count, b, ch.dev, nz, nullptr, (u128*)ct_out);
     g_launches.fetch_add(1);

@@ -1,0 +1,554 @@
+// flashe_wire.cu — the callers and data formats either side of the FLASHE hot path:
+//
+//   f1  wire bit-packing          framework/jzf_weights.py:45-137 (_to_bytes / _from_bytes), 155-231
+//   f2  top-k sparsify + residual framework/homo/procedure/jzf_aggregator.py:578-623 (Client.sparsify)
+//   f3  per-layer statistics      secureprotol/jzf_quantize.py:542-564 (normalize / unnormalize)
+//
+// All three are HBM-bound byte / integer / reduction work: grid-stride kernels with grids capped at a
+// multiple of the SM count, wide accesses where the layout allows.  No tensor cores.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "flashe_internal.h"
+
+typedef unsigned __int128 u128_t;
+
+static uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+static int grid_cap(int num_sms, uint64_t blocks, int per_sm) {
+    uint64_t cap = (uint64_t)num_sms * per_sm;
+    if (blocks < 1) blocks = 1;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+#define WIRE_ENTER(ctx)                                                                   \
+    flashe_ctx_info info;                                                                 \
+    { int rc__ = flashe_ctx_get_info((ctx), &info); if (rc__) return rc__; }              \
+    FlasheDeviceGuard guard__(info.device);                                               \
+    if (!guard__.ok) return flashe_fail(FLASHE_ECUDA, "cudaSetDevice failed");            \
+    cudaStream_t cs = (cudaStream_t)stream
+
+// =================================================================================================
+// f1  wire bit-packing
+//
+// _to_bytes(flatten_array, num_bits) (jzf_weights.py:45-84) builds the Python integer
+//     s = sum_j  a[j] << ((L-1-j) * num_bits)            (first element most significant)
+// batch by batch; the batching (lcm(num_bits, 8) bits at a time) only bounds the size of the
+// intermediate integers and does not change s.  On the wire s travels as a big integer; here it is the
+// big-endian byte string of length ceil(L*num_bits/8) (int.to_bytes(nbytes, 'big')), i.e. output byte k
+// holds bits [8*(nbytes-1-k), 8*(nbytes-k)) of s, with zero bits above L*num_bits.
+// _from_bytes (jzf_weights.py:98-137) + the reverse() in decompress (:224) is the inverse.
+// =================================================================================================
+template <int WB> struct WireWord;
+template <> struct WireWord<4> {
+    static __device__ __forceinline__ u128_t load(const void* p, uint64_t j) { return reinterpret_cast<const uint32_t*>(p)[j]; }
+    static __device__ __forceinline__ void store(void* p, uint64_t j, u128_t v) { reinterpret_cast<uint32_t*>(p)[j] = (uint32_t)v; }
+};
+template <> struct WireWord<8> {
+    static __device__ __forceinline__ u128_t load(const void* p, uint64_t j) { return reinterpret_cast<const uint64_t*>(p)[j]; }
+    static __device__ __forceinline__ void store(void* p, uint64_t j, u128_t v) { reinterpret_cast<uint64_t*>(p)[j] = (uint64_t)v; }
+};
+template <> struct WireWord<16> {
+    static __device__ __forceinline__ u128_t load(const void* p, uint64_t j) {
+        const uint4 r = reinterpret_cast<const uint4*>(p)[j];
+        return ((u128_t)(((uint64_t)r.w << 32) | r.z) << 64) | (((uint64_t)r.y << 32) | r.x);
+    }
+    static __device__ __forceinline__ void store(void* p, uint64_t j, u128_t v) {
+        const uint64_t lo = (uint64_t)v, hi = (uint64_t)(v >> 64);
+        reinterpret_cast<uint4*>(p)[j] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+    }
+};
+
+__device__ __forceinline__ u128_t field_mask(uint32_t bits) { return bits >= 128 ? ~(u128_t)0 : (((u128_t)1 << bits) - 1); }
+
+// One thread = one 16-byte chunk of the output stream (chunk k = bytes [16k, 16k+16)).  The chunk is the
+// 128-bit window [lo_bit, lo_bit+128) of s with lo_bit = 8*(nbytes - 16k) - 128 (negative only for a
+// short final chunk); the window is assembled from the <= 128/bits + 2 fields that intersect it.
+// Consecutive threads read consecutive elements and write consecutive 16-byte chunks.
+template <int WB>
+__global__ void __launch_bounds__(256)
+k_wire_pack(const void* __restrict__ words, uint64_t count, uint32_t bits, uint64_t nbytes, uint8_t* __restrict__ out) {
+    const uint64_t nchunks = (nbytes + 15) >> 4;
+    const u128_t fm = field_mask(bits);
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nchunks; k += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t hi_bit = (int64_t)(8 * (nbytes - 16 * k));     // exclusive, > 0
+        const int64_t lo_bit = hi_bit - 128;
+        // fields are numbered from the END: field e holds element count-1-e at bits [e*bits, (e+1)*bits)
+        const uint64_t e_lo = lo_bit > 0 ? (uint64_t)lo_bit / bits : 0;
+        uint64_t e_hi = (uint64_t)(hi_bit - 1) / bits;
+        if (e_hi >= count) e_hi = count - 1;                          // zero padding above the top field
+        u128_t v = 0;
+        for (uint64_t e = e_hi + 1; e-- > e_lo;) {                    // ascending element index
+            const u128_t a = WireWord<WB>::load(words, count - 1 - e) & fm;
+            const int64_t sh = (int64_t)(e * bits) - lo_bit;
+            if (sh >= 128 || sh <= -128) continue;
+            v |= sh >= 0 ? (a << sh) : (a >> (-sh));
+        }
+        // big-endian bytes of the window
+        const uint64_t vh = (uint64_t)(v >> 64), vl = (uint64_t)v;
+        const uint32_t w0 = __byte_perm((uint32_t)(vh >> 32), 0, 0x0123), w1 = __byte_perm((uint32_t)vh, 0, 0x0123);
+        const uint32_t w2 = __byte_perm((uint32_t)(vl >> 32), 0, 0x0123), w3 = __byte_perm((uint32_t)vl, 0, 0x0123);
+        if (16 * k + 16 <= nbytes) {
+            reinterpret_cast<uint4*>(out)[k] = make_uint4(w0, w1, w2, w3);
+        } else {
+            const uint32_t w[4] = {w0, w1, w2, w3};
+            for (uint64_t i = 0; 16 * k + i < nbytes; ++i) out[16 * k + i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+        }
+    }
+}
+
+// One thread = one element: field e = count-1-j lives at bits [p, p+bits), p = e*bits, of s; its bytes
+// are gathered most significant first.  Neighbouring threads read neighbouring (overlapping) bytes.
+template <int WB>
+__global__ void __launch_bounds__(256)
+k_wire_unpack(const uint8_t* __restrict__ in, uint64_t count, uint32_t bits, uint64_t nbytes, void* __restrict__ words) {
+    const u128_t fm = field_mask(bits);
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t p = (count - 1 - j) * (uint64_t)bits;
+        const uint64_t b_lo = p >> 3, b_hi = (p + bits - 1) >> 3;    // little-endian byte numbers of s
+        const uint32_t sh = (uint32_t)(p & 7);
+        u128_t v = 0;
+        uint32_t top = 0;                                            // 17th byte when bits + sh > 128
+        for (uint64_t bn = b_hi + 1; bn-- > b_lo;) {
+            const uint32_t byte = __ldg(in + (nbytes - 1 - bn));
+            const uint64_t rel = bn - b_lo;
+            if (rel >= 16) top = byte; else v |= (u128_t)byte << (8 * rel);
+        }
+        v = sh ? ((v >> sh) | ((u128_t)top << (128 - sh))) : v;
+        WireWord<WB>::store(words, j, v & fm);
+    }
+}
+
+// =================================================================================================
+// f2  layer-wise top-s% sparsification with residual accumulation (Client.sparsify,
+// proc/jzf_aggregator.py:578-623).  Per layer, in the reference's order:
+//     abs_flatten = |x|                                  (:594, BEFORE the residual is added)
+//     flatten     = x + remain                           (:595-596, float32)
+//     location    = sorted(abs_flatten.argsort()[-k:])   (:598-599)   k = max(1, floor(s * size))
+//     compact     = flatten[location]; flatten[location] = 0; remain = flatten   (:600-604)
+//     locations  += location + base                      (:606)
+// The set `location` is the k largest |x|; elements tied with the k-th largest are taken from the
+// HIGHEST indices first (what a stable ascending argsort followed by [-k:] yields; numpy's default
+// introsort leaves the choice among exact ties unspecified).
+//
+// Selection = 3-pass MSD radix select on key = bits(|x|) (monotone for non-negative floats, NaN above
+// inf as numpy sorts it): 11 + 11 + 9 bits, block-private shared-memory histograms merged with global
+// atomics, one small block picks the bucket.  Compaction keeps index order (= sorted locations): tile
+// counts, one-block scan, ordered write.  x is read 5 times (L2-resident for layers up to ~30 M).
+// =================================================================================================
+struct TopkState { uint32_t prefix; uint32_t k_rem; uint32_t c_eq; uint32_t pad; };
+
+#define TK_THREADS 256
+#define TK_PER 16
+#define TK_TILE (TK_THREADS * TK_PER)
+#define TK_BINS 2048
+
+__device__ __forceinline__ uint32_t key_of(float x) { return __float_as_uint(x) & 0x7fffffffu; }
+
+// pass 0: shift 20 / 11 bits; pass 1: shift 9 / 11 bits; pass 2: shift 0 / 9 bits
+__global__ void __launch_bounds__(TK_THREADS)
+k_topk_hist(const float* __restrict__ x, uint64_t n, const TopkState* __restrict__ st, uint32_t shift, uint32_t nbits,
+            uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[TK_BINS];
+    for (uint32_t i = threadIdx.x; i < TK_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint32_t hi_shift = shift + nbits;               // bits above the digit must equal the prefix
+    const uint32_t prefix = st->prefix;
+    const uint32_t dmask = (1u << nbits) - 1u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t key = key_of(x[i]);
+        if (hi_shift >= 31u || (key >> hi_shift) == (prefix >> hi_shift)) atomicAdd(&sh[(key >> shift) & dmask], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < TK_BINS; i += blockDim.x) {
+        const uint32_t c = sh[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+// One block of 1024 threads: suffix sums of the histogram from the top bin; the bucket holding the
+// k_rem-th largest key extends the prefix.  Clears the histogram for the next pass.
+__global__ void __launch_bounds__(1024)
+k_topk_pick(uint32_t* __restrict__ hist, TopkState* __restrict__ st, uint32_t shift) {
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    // thread t owns bins hi = TK_BINS-1-2t and hi-1 (descending order)
+    const uint32_t b0 = TK_BINS - 1 - 2 * t, b1 = b0 - 1;
+    const uint32_t c0 = hist[b0], c1 = hist[b1];
+    hist[b0] = 0; hist[b1] = 0;
+    uint32_t incl = c0 + c1;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_tot[lane];
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, w, d); if (lane >= (uint32_t)d) w += o; }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t before = (warp ? warp_tot[warp - 1] : 0u) + incl - (c0 + c1);   // keys in higher bins
+    const uint32_t k_rem = st->k_rem;
+    __syncthreads();
+    // the k_rem-th largest lies in the first bin (from the top) whose inclusive count reaches k_rem
+    if (before < k_rem && k_rem <= before + c0) {
+        st->prefix |= b0 << shift; st->k_rem = k_rem - before; st->c_eq = c0;
+    } else if (before + c0 < k_rem && k_rem <= before + c0 + c1) {
+        st->prefix |= b1 << shift; st->k_rem = k_rem - before - c0; st->c_eq = c1;
+    }
+}
+
+// per-tile counts of (key > T, key == T)
+__global__ void __launch_bounds__(TK_THREADS)
+k_topk_count(const float* __restrict__ x, uint64_t n, const TopkState* __restrict__ st, uint2* __restrict__ tile_counts) {
+    __shared__ uint32_t sg[TK_THREADS / 32], se[TK_THREADS / 32];
+    const uint32_t T = st->prefix;
+    const uint64_t ntiles = (n + TK_TILE - 1) / TK_TILE;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t base = tile * TK_TILE;
+        uint32_t g = 0, e = 0;
+#pragma unroll 4
+        for (int r = 0; r < TK_PER; ++r) {
+            const uint64_t i = base + (uint64_t)r * TK_THREADS + threadIdx.x;   // counts do not need index order
+            if (i < n) { const uint32_t key = key_of(x[i]); g += key > T; e += key == T; }
+        }
+        for (int d = 16; d > 0; d >>= 1) { g += __shfl_down_sync(0xffffffffu, g, d); e += __shfl_down_sync(0xffffffffu, e, d); }
+        if ((threadIdx.x & 31u) == 0) { sg[threadIdx.x >> 5] = g; se[threadIdx.x >> 5] = e; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t G = 0, E = 0;
+            for (int w = 0; w < TK_THREADS / 32; ++w) { G += sg[w]; E += se[w]; }
+            tile_counts[tile] = make_uint2(G, E);
+        }
+        __syncthreads();
+    }
+}
+
+// exclusive scan of the tile counts in place (one block; ntiles is small: n / 4096)
+__global__ void __launch_bounds__(1024)
+k_topk_scan(uint2* __restrict__ tile_counts, uint64_t ntiles) {
+    __shared__ uint32_t wg[32], we[32];
+    __shared__ uint32_t carry_g, carry_e;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    if (t == 0) { carry_g = 0; carry_e = 0; }
+    __syncthreads();
+    for (uint64_t base = 0; base < ntiles; base += 1024) {
+        const uint64_t i = base + t;
+        const uint2 c = i < ntiles ? tile_counts[i] : make_uint2(0, 0);
+        uint32_t g = c.x, e = c.y;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t og = __shfl_up_sync(0xffffffffu, g, d), oe = __shfl_up_sync(0xffffffffu, e, d);
+            if (lane >= (uint32_t)d) { g += og; e += oe; }
+        }
+        if (lane == 31) { wg[warp] = g; we[warp] = e; }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t a = wg[lane], b = we[lane];
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t oa = __shfl_up_sync(0xffffffffu, a, d), ob = __shfl_up_sync(0xffffffffu, b, d);
+                if (lane >= (uint32_t)d) { a += oa; b += ob; }
+            }
+            wg[lane] = a; we[lane] = b;
+        }
+        __syncthreads();
+        const uint32_t pg = carry_g + (warp ? wg[warp - 1] : 0u) + g - c.x;
+        const uint32_t pe = carry_e + (warp ? we[warp - 1] : 0u) + e - c.y;
+        if (i < ntiles) tile_counts[i] = make_uint2(pg, pe);
+        __syncthreads();
+        if (t == 1023) { carry_g = pg + c.x; carry_e = pe + c.y; }
+        __syncthreads();
+    }
+}
+
+// Ordered write.  Thread t of a tile owns the TK_PER consecutive elements [t*TK_PER, (t+1)*TK_PER) so
+// that positions follow the index order.  An element is selected when key > T, or key == T and at least
+// c_eq - k_rem tied elements precede it.  Output slot = (#selected before it).
+__global__ void __launch_bounds__(TK_THREADS)
+k_topk_write(const float* __restrict__ x, const float* __restrict__ res_in, uint64_t n, uint64_t seg_base,
+             const TopkState* __restrict__ st, const uint2* __restrict__ tile_prefix, float* __restrict__ values,
+             int64_t* __restrict__ index, float* __restrict__ res_out) {
+    __shared__ uint32_t wg[TK_THREADS / 32], we[TK_THREADS / 32];
+    const uint32_t T = st->prefix, skip_eq = st->c_eq - st->k_rem;   // ties with rank < skip_eq are not taken
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t ntiles = (n + TK_TILE - 1) / TK_TILE;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t i0 = tile * TK_TILE + (uint64_t)threadIdx.x * TK_PER;
+        float xv[TK_PER];
+        uint32_t g = 0, e = 0;
+        if (i0 + TK_PER <= n && ((reinterpret_cast<uintptr_t>(x + i0) & 15u) == 0)) {
+#pragma unroll
+            for (int r = 0; r < TK_PER; r += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(x + i0 + r);
+                xv[r] = v.x; xv[r + 1] = v.y; xv[r + 2] = v.z; xv[r + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < TK_PER; ++r) xv[r] = (i0 + r < n) ? x[i0 + r] : 0.0f;
+        }
+#pragma unroll
+        for (int r = 0; r < TK_PER; ++r)
+            if (i0 + r < n) { const uint32_t key = key_of(xv[r]); g += key > T; e += key == T; }
+        // block-exclusive scan of (g, e) in thread order
+        uint32_t sg = g, se = e;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t og = __shfl_up_sync(0xffffffffu, sg, d), oe = __shfl_up_sync(0xffffffffu, se, d);
+            if (lane >= (uint32_t)d) { sg += og; se += oe; }
+        }
+        if (lane == 31) { wg[warp] = sg; we[warp] = se; }
+        __syncthreads();
+        uint32_t bg = 0, be = 0;
+        for (uint32_t w = 0; w < warp; ++w) { bg += wg[w]; be += we[w]; }
+        const uint2 tp = tile_prefix[tile];
+        uint32_t gt_before = tp.x + bg + sg - g;      // key > T before this thread's first element
+        uint32_t eq_before = tp.y + be + se - e;      // key == T before it
+#pragma unroll
+        for (int r = 0; r < TK_PER; ++r) {
+            const uint64_t i = i0 + r;
+            if (i < n) {
+                const uint32_t key = key_of(xv[r]);
+                const bool is_eq = key == T;
+                const bool sel = key > T || (is_eq && eq_before >= skip_eq);
+                const float f = res_in ? __fadd_rn(xv[r], res_in[i]) : xv[r];
+                if (sel) {
+                    const uint32_t taken_eq = eq_before > skip_eq ? eq_before - skip_eq : 0u;   // selected ties before i
+                    const uint64_t pos = (uint64_t)gt_before + taken_eq;
+                    values[pos] = f;
+                    index[pos] = (int64_t)(seg_base + i);
+                }
+                if (res_out) res_out[i] = sel ? 0.0f : f;
+                gt_before += key > T; eq_before += is_eq;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =================================================================================================
+// f3  per-layer statistics around decode (QuantizingClient.unnormalize, sp/jzf_quantize.py:549-564):
+//     w += past_mean[layer];  past_mean[layer] = mean(w);  past_std[layer] = std(w)   (population std)
+// Two deterministic passes (np.std is two-pass: mean first, then mean of squared deviations):
+// fixed tile -> block-partial -> per-layer serial sum of the partials in tile order.  Floating point:
+// the summation ORDER differs from numpy's (pairwise for float64 arrays, sequential for the object
+// arrays the reference actually holds), so parity is to a stated tolerance, not bit-exact.
+// =================================================================================================
+#define ST_THREADS 256
+#define ST_PER 16
+#define ST_TILE (ST_THREADS * ST_PER)
+
+struct StatSeg { uint64_t begin, end, tile0; double shift; };   // tile0 = first tile number of the segment
+
+__device__ __forceinline__ int seg_of_tile(const StatSeg* __restrict__ segs, int nseg, uint64_t tile) {
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (segs[mid].tile0 <= tile) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31u) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0) for (int w = 0; w < ST_THREADS / 32; ++w) r += sh[w];
+    __syncthreads();
+    return r;   // valid in thread 0
+}
+
+// PASS 0: w_out = w + shift, partial = sum(w_out).  PASS 1: partial = sum((w - mean)^2); add_shift says
+// whether w still lacks the shift (no w_out was written).
+template <int PASS>
+__global__ void __launch_bounds__(ST_THREADS)
+k_stats_partial(const double* w, double* w_out, const StatSeg* __restrict__ segs, int nseg, uint64_t ntiles,
+                int add_shift, const double* __restrict__ stats, double* __restrict__ partial) {
+    __shared__ double sh[ST_THREADS / 32];
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int s = seg_of_tile(segs, nseg, tile);
+        const StatSeg sg = segs[s];
+        const uint64_t base = sg.begin + (tile - sg.tile0) * ST_TILE;
+        const double mean = PASS == 1 ? stats[2 * s] : 0.0;
+        double acc = 0.0;
+#pragma unroll 4
+        for (int r = 0; r < ST_PER; ++r) {
+            const uint64_t i = base + (uint64_t)r * ST_THREADS + threadIdx.x;
+            if (i < sg.end) {
+                if (PASS == 0) {
+                    const double v = __dadd_rn(w[i], sg.shift);
+                    if (w_out) w_out[i] = v;
+                    acc += v;
+                } else {
+                    const double d = (add_shift ? __dadd_rn(w[i], sg.shift) : w[i]) - mean;
+                    acc += d * d;
+                }
+            }
+        }
+        const double tot = block_sum(acc, sh);
+        if (threadIdx.x == 0) partial[tile] = tot;
+    }
+}
+
+// one warp per segment: partials summed in tile order (lane-strided, then a fixed shuffle tree)
+template <int PASS>
+__global__ void k_stats_final(const StatSeg* __restrict__ segs, int nseg, uint64_t ntiles, const double* __restrict__ partial,
+                              double* __restrict__ stats) {
+    const int s = blockIdx.x;
+    if (s >= nseg) return;
+    const uint64_t t0 = segs[s].tile0, t1 = s + 1 < nseg ? segs[s + 1].tile0 : ntiles;
+    double acc = 0.0;
+    for (uint64_t t = t0 + threadIdx.x; t < t1; t += 32) acc += partial[t];
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    if (threadIdx.x == 0) {
+        const double n = (double)(segs[s].end - segs[s].begin);
+        if (PASS == 0) stats[2 * s] = n > 0 ? acc / n : 0.0;
+        else stats[2 * s + 1] = n > 0 ? sqrt(acc / n) : 0.0;
+    }
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int flashe_wire_nbytes(int bits, uint64_t count, uint64_t* nbytes_out) {
+    if (!nbytes_out) return flashe_fail(FLASHE_EINVAL, "nbytes_out is NULL");
+    if (bits < 1 || bits > 128) return flashe_fail(FLASHE_EINVAL, "bits must be in [1, 128]");
+    if (count > (UINT64_MAX - 7) / (uint64_t)bits) return flashe_fail(FLASHE_EINVAL, "count * bits overflows");
+    *nbytes_out = (count * (uint64_t)bits + 7) / 8;
+    return FLASHE_OK;
+}
+
+static int wire_check(int bits, int word_bytes) {
+    if (bits < 1 || bits > 128) return flashe_fail(FLASHE_EINVAL, "bits must be in [1, 128]");
+    if (word_bytes != 4 && word_bytes != 8 && word_bytes != 16) return flashe_fail(FLASHE_EINVAL, "word_bytes must be 4, 8 or 16");
+    if (bits > 8 * word_bytes) return flashe_fail(FLASHE_EINVAL, "bits exceeds the word width");
+    return FLASHE_OK;
+}
+
+int flashe_wire_pack(flashe_ctx* ctx, const void* words, int word_bytes, uint64_t count, int bits, uint8_t* out, void* stream) {
+    WIRE_ENTER(ctx);
+    int rc = wire_check(bits, word_bytes); if (rc) return rc;
+    if (count == 0) return FLASHE_OK;
+    if (!words || !out) return flashe_fail(FLASHE_EINVAL, "NULL buffer");
+    if (((uintptr_t)out & 15u) != 0) return flashe_fail(FLASHE_EINVAL, "out must be 16-byte aligned");
+    uint64_t nbytes; rc = flashe_wire_nbytes(bits, count, &nbytes); if (rc) return rc;
+    const int grid = grid_cap(info.num_sms, ceil_div_u64((nbytes + 15) / 16, 256), 8);
+    if (word_bytes == 4) k_wire_pack<4><<<grid, 256, 0, cs>>>(words, count, (uint32_t)bits, nbytes, out);
+    else if (word_bytes == 8) k_wire_pack<8><<<grid, 256, 0, cs>>>(words, count, (uint32_t)bits, nbytes, out);
+    else k_wire_pack<16><<<grid, 256, 0, cs>>>(words, count, (uint32_t)bits, nbytes, out);
+    flashe_count_launches(1);
+    FLASHE_CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+int flashe_wire_unpack(flashe_ctx* ctx, const uint8_t* in, uint64_t count, int bits, int word_bytes, void* words_out, void* stream) {
+    WIRE_ENTER(ctx);
+    int rc = wire_check(bits, word_bytes); if (rc) return rc;
+    if (count == 0) return FLASHE_OK;
+    if (!in || !words_out) return flashe_fail(FLASHE_EINVAL, "NULL buffer");
+    uint64_t nbytes; rc = flashe_wire_nbytes(bits, count, &nbytes); if (rc) return rc;
+    const int grid = grid_cap(info.num_sms, ceil_div_u64(count, 256), 8);
+    if (word_bytes == 4) k_wire_unpack<4><<<grid, 256, 0, cs>>>(in, count, (uint32_t)bits, nbytes, words_out);
+    else if (word_bytes == 8) k_wire_unpack<8><<<grid, 256, 0, cs>>>(in, count, (uint32_t)bits, nbytes, words_out);
+    else k_wire_unpack<16><<<grid, 256, 0, cs>>>(in, count, (uint32_t)bits, nbytes, words_out);
+    flashe_count_launches(1);
+    FLASHE_CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_in, uint64_t total, const uint64_t* seg_end,
+                         const uint64_t* k, int nseg, float* values_out, int64_t* index_out, float* residual_out, void* stream) {
+    WIRE_ENTER(ctx);
+    if (nseg < 1 || !seg_end || !k) return flashe_fail(FLASHE_EINVAL, "need nseg >= 1, seg_end and k");
+    if (seg_end[nseg - 1] != total) return flashe_fail(FLASHE_EINVAL, "seg_end[nseg-1] must equal total");
+    uint64_t prev = 0, max_n = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (seg_end[s] < prev) return flashe_fail(FLASHE_EINVAL, "seg_end must be ascending");
+        const uint64_t n = seg_end[s] - prev;
+        if (k[s] > n) return flashe_fail(FLASHE_EINVAL, "k[s] exceeds the layer size");
+        if (n && k[s] == 0) return flashe_fail(FLASHE_EINVAL, "k[s] must be >= 1 for a non-empty layer (max(1, floor(s*size)))");
+        if (n >= (1ull << 32)) return flashe_fail(FLASHE_EUNSUPPORTED, "layers of 2^32 or more elements");
+        if (n > max_n) max_n = n;
+        prev = seg_end[s];
+    }
+    if (total == 0) return FLASHE_OK;
+    if (!x || !values_out || !index_out) return flashe_fail(FLASHE_EINVAL, "NULL buffer");
+    // workspace: state | histogram | tile counts
+    const uint64_t max_tiles = ceil_div_u64(max_n, TK_TILE);
+    const size_t ws_bytes = 256 + sizeof(uint32_t) * TK_BINS + sizeof(uint2) * (size_t)max_tiles;
+    uint8_t* ws = nullptr;
+    FLASHE_CUDA_TRY(cudaMallocAsync((void**)&ws, ws_bytes, cs));
+    TopkState* st = reinterpret_cast<TopkState*>(ws);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(ws + 256);
+    uint2* tiles = reinterpret_cast<uint2*>(ws + 256 + sizeof(uint32_t) * TK_BINS);
+    cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * TK_BINS, cs);
+    uint64_t begin = 0, out_off = 0;
+    int launches = 0;
+    for (int s = 0; e == cudaSuccess && s < nseg; ++s) {
+        const uint64_t n = seg_end[s] - begin;
+        if (n == 0) continue;
+        const TopkState init = {0u, (uint32_t)k[s], 0u, 0u};
+        e = cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, cs);   // pageable: staged before return
+        if (e != cudaSuccess) break;
+        const float* xs = x + begin;
+        const int gh = grid_cap(info.num_sms, ceil_div_u64(n, TK_THREADS * 8), 8);
+        const uint32_t shifts[3] = {20u, 9u, 0u}, nbits[3] = {11u, 11u, 9u};
+        for (int p = 0; p < 3; ++p) {
+            k_topk_hist<<<gh, TK_THREADS, 0, cs>>>(xs, n, st, shifts[p], nbits[p], hist);
+            k_topk_pick<<<1, 1024, 0, cs>>>(hist, st, shifts[p]);
+        }
+        const uint64_t ntiles = ceil_div_u64(n, TK_TILE);
+        const int gt = grid_cap(info.num_sms, ntiles, 8);
+        k_topk_count<<<gt, TK_THREADS, 0, cs>>>(xs, n, st, tiles);
+        k_topk_scan<<<1, 1024, 0, cs>>>(tiles, ntiles);
+        k_topk_write<<<gt, TK_THREADS, 0, cs>>>(xs, residual_in ? residual_in + begin : nullptr, n, begin, st, tiles,
+                                                values_out + out_off, index_out + out_off,
+                                                residual_out ? residual_out + begin : nullptr);
+        launches += 9;
+        e = cudaGetLastError();
+        begin = seg_end[s];
+        out_off += k[s];
+    }
+    flashe_count_launches(launches);
+    cudaFreeAsync(ws, cs);
+    if (e != cudaSuccess) return flashe_fail(FLASHE_ECUDA, std::string("flashe_topk_sparsify: ") + cudaGetErrorString(e));
+    return FLASHE_OK;
+}
+
+int flashe_segment_stats(flashe_ctx* ctx, const double* w, double* w_out, uint64_t total, const uint64_t* seg_end,
+                         const double* shift, int nseg, double* stats_out, void* stream) {
+    WIRE_ENTER(ctx);
+    if (nseg < 1 || !seg_end) return flashe_fail(FLASHE_EINVAL, "need nseg >= 1 and seg_end");
+    if (seg_end[nseg - 1] != total) return flashe_fail(FLASHE_EINVAL, "seg_end[nseg-1] must equal total");
+    if (!stats_out) return flashe_fail(FLASHE_EINVAL, "stats_out is NULL");
+    if (total && !w) return flashe_fail(FLASHE_EINVAL, "w is NULL");
+    std::vector<StatSeg> segs((size_t)nseg);
+    uint64_t prev = 0, ntiles = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (seg_end[s] < prev) return flashe_fail(FLASHE_EINVAL, "seg_end must be ascending");
+        segs[s].begin = prev; segs[s].end = seg_end[s]; segs[s].tile0 = ntiles; segs[s].shift = shift ? shift[s] : 0.0;
+        ntiles += ceil_div_u64(seg_end[s] - prev, ST_TILE);
+        prev = seg_end[s];
+    }
+    const size_t seg_bytes = sizeof(StatSeg) * (size_t)nseg;
+    const size_t seg_pad = (seg_bytes + 255) & ~(size_t)255;
+    uint8_t* ws = nullptr;
+    FLASHE_CUDA_TRY(cudaMallocAsync((void**)&ws, seg_pad + sizeof(double) * (size_t)(ntiles ? ntiles : 1), cs));
+    StatSeg* dseg = reinterpret_cast<StatSeg*>(ws);
+    double* partial = reinterpret_cast<double*>(ws + seg_pad);
+    cudaError_t e = cudaMemcpyAsync(dseg, segs.data(), seg_bytes, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);   // segs (pageable host memory) goes out of scope
+    if (e == cudaSuccess) {
+        const int grid = grid_cap(info.num_sms, ntiles, 8);
+        if (ntiles) k_stats_partial<0><<<grid, ST_THREADS, 0, cs>>>(w, w_out, dseg, nseg, ntiles, 0, stats_out, partial);
+        k_stats_final<0><<<nseg, 32, 0, cs>>>(dseg, nseg, ntiles, partial, stats_out);
+        if (ntiles) k_stats_partial<1><<<grid, ST_THREADS, 0, cs>>>(w_out ? w_out : w, nullptr, dseg, nseg, ntiles, w_out ? 0 : 1, stats_out, partial);
+        k_stats_final<1><<<nseg, 32, 0, cs>>>(dseg, nseg, ntiles, partial, stats_out);
+        flashe_count_launches(ntiles ? 4 : 2);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(ws, cs);
+    if (e != cudaSuccess) return flashe_fail(FLASHE_ECUDA, std::string("flashe_segment_stats: ") + cudaGetErrorString(e));
+    return FLASHE_OK;
+}
+
+}  // extern "C"

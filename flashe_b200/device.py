@@ -330,6 +330,76 @@ class DeviceContext(object):
         _cabi.check(self.lib.flashe_sparse_overlap(self._h, ptrs, ks, n, total, out, self._stream()))
         return [int(v) for v in out]
 
+    # ------------------------------------------------------------------ wire format, sparsify, statistics
+    @staticmethod
+    def _word_bytes_of(t):
+        """Storage width of one element of a word tensor: uint32/int32 -> 4, uint64/int64 -> 8, [L, 2] uint64 -> 16."""
+        if t.dim() == 2 and t.shape[1] == 2 and t.element_size() == 8:
+            return 16
+        if t.element_size() not in (4, 8):
+            raise ValueError("word tensors hold 4-, 8- or 16-byte elements")
+        return t.element_size()
+
+    def wire_pack(self, words, bits=None, out=None):
+        """_to_bytes (jzf_weights.py:45-84) as a big-endian byte string: uint8 [ceil(L*bits/8)]."""
+        bits = self.int_bits if bits is None else int(bits)
+        wb = self._word_bytes_of(words)
+        L = words.shape[0]
+        if words.device != self.device or not words.is_contiguous():
+            raise ValueError("words must be contiguous on %s" % self.device)
+        nb = C.c_uint64()
+        _cabi.check(self.lib.flashe_wire_nbytes(bits, L, C.byref(nb)))
+        out = torch.empty(nb.value, dtype=torch.uint8, device=self.device) if out is None else self._check(out, torch.uint8, nb.value, "out")
+        _cabi.check(self.lib.flashe_wire_pack(self._h, words.data_ptr(), wb, L, bits, out.data_ptr(), self._stream()))
+        return out
+
+    def wire_unpack(self, data, count, bits=None, word_bytes=None, out=None):
+        """_from_bytes + reverse (jzf_weights.py:98-137, 224): uint8 stream -> word tensor of `count` elements."""
+        bits = self.int_bits if bits is None else int(bits)
+        wb = (4 if bits <= 32 else (8 if bits <= 64 else 16)) if word_bytes is None else int(word_bytes)
+        nb = C.c_uint64()
+        _cabi.check(self.lib.flashe_wire_nbytes(bits, count, C.byref(nb)))
+        self._check(data, torch.uint8, nb.value, "data")
+        if out is None:
+            out = (torch.empty(count, dtype=torch.uint32, device=self.device) if wb == 4 else
+                   torch.empty(count, dtype=torch.uint64, device=self.device) if wb == 8 else
+                   torch.empty((count, 2), dtype=torch.uint64, device=self.device))
+        _cabi.check(self.lib.flashe_wire_unpack(self._h, data.data_ptr(), count, bits, wb, out.data_ptr(), self._stream()))
+        return out
+
+    def topk_sparsify(self, x, seg_end, k, residual=None, residual_out=None):
+        """Client.sparsify (jzf_aggregator.py:578-623) on a flat float32 vector of concatenated layers.
+        Returns (values float32 [sum k], index int64 [sum k] global ascending, new residual float32 [L])."""
+        L = x.numel()
+        self._check(x, torch.float32, L, "x")
+        if residual is not None:
+            self._check(residual, torch.float32, L, "residual")
+        residual_out = torch.empty(L, dtype=torch.float32, device=self.device) if residual_out is None else self._check(residual_out, torch.float32, L, "residual_out")
+        ends = (C.c_uint64 * len(seg_end))(*[int(e) for e in seg_end])
+        ks = (C.c_uint64 * len(k))(*[int(v) for v in k])
+        K = sum(int(v) for v in k)
+        values = torch.empty(K, dtype=torch.float32, device=self.device)
+        index = torch.empty(K, dtype=torch.int64, device=self.device)
+        _cabi.check(self.lib.flashe_topk_sparsify(self._h, x.data_ptr(), residual.data_ptr() if residual is not None else None, L,
+                                                  ends, ks, len(seg_end), values.data_ptr(), index.data_ptr(),
+                                                  residual_out.data_ptr(), self._stream()))
+        return values, index, residual_out
+
+    def segment_stats(self, w, seg_end, shift=None, out=None, inplace=False):
+        """unnormalize (jzf_quantize.py:549-564): w + shift per layer, then (mean, std) per layer.
+        Returns (shifted w or None, stats float64 [nseg, 2] on the device)."""
+        L = w.numel()
+        self._check(w, torch.float64, L, "w")
+        nseg = len(seg_end)
+        ends = (C.c_uint64 * nseg)(*[int(e) for e in seg_end])
+        sh = None if shift is None else (C.c_double * nseg)(*[float(v) for v in shift])
+        if inplace:
+            out = w
+        stats = torch.empty((nseg, 2), dtype=torch.float64, device=self.device)
+        _cabi.check(self.lib.flashe_segment_stats(self._h, w.data_ptr(), out.data_ptr() if out is not None else None, L, ends, sh,
+                                                  nseg, stats.data_ptr(), self._stream()))
+        return out, stats
+
 
 def launch_count():
     return int(_cabi.load().flashe_launch_count())

@@ -234,6 +234,48 @@ int flashe_sparse_apply_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf
 int flashe_sparse_overlap(flashe_ctx* ctx, const int64_t* const* index, const uint64_t* k, int n,
                           uint64_t total, uint64_t* overlap_out, void* stream);
 
+/* ---- wire bit-packing --------------------------------------------------------------
+ * _to_bytes(flatten_array, num_bits) (framework/jzf_weights.py:45-84, used by
+ * JZFTransferableWeights.compress :155-198 and by Client.sparsify for the index list,
+ * proc/jzf_aggregator.py:617) builds the integer s = sum_j a[j] << ((L-1-j)*bits): first element most
+ * significant.  Here s is the big-endian byte string of ceil(L*bits/8) bytes (int.to_bytes(n, 'big');
+ * zero bits above L*bits).  `bits` is the field width (int_bits for ciphertexts,
+ * total.bit_length() for index lists), word_bytes (4, 8 or 16) the storage width of one element;
+ * elements must be < 2^bits (they are masked).  `out` must be 16-byte aligned. */
+int flashe_wire_nbytes(int bits, uint64_t count, uint64_t* nbytes_out);
+int flashe_wire_pack(flashe_ctx* ctx, const void* words, int word_bytes, uint64_t count, int bits,
+                     uint8_t* out, void* stream);
+/* _from_bytes(s, l, num_bits) followed by the reverse() of decompress (framework/jzf_weights.py:98-137,
+ * 224): element j = (s >> ((L-1-j)*bits)) & (2^bits - 1). */
+int flashe_wire_unpack(flashe_ctx* ctx, const uint8_t* in, uint64_t count, int bits, int word_bytes,
+                       void* words_out, void* stream);
+
+/* ---- layer-wise top-k sparsification with residual accumulation -------------------
+ * Client.sparsify (proc/jzf_aggregator.py:578-623).  The flat float32 vector x is a concatenation of
+ * nseg layers ending at seg_end[s] (HOST array); layer s keeps k[s] = max(1, floor(sparsity*size))
+ * elements (HOST array, computed by the caller as the reference does, :598).  Per layer:
+ *   selection  the k[s] largest |x| (the residual is NOT part of the ranking, :594-596); elements tied
+ *              with the k-th largest are taken from the highest indices first (stable-argsort order;
+ *              numpy's default sort leaves exact ties unspecified);
+ *   values_out float32 (x + residual_in) at the selected positions, in ascending index order (:599-600);
+ *   index_out  their GLOBAL positions (location + base, :606), ascending, int64;
+ *   residual_out  x + residual_in with the selected positions zeroed (:603-604).
+ * residual_in may be NULL (first round: no residual yet); residual_out may be NULL or alias
+ * residual_in.  values_out / index_out hold sum(k) entries, layer after layer. */
+int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_in, uint64_t total,
+                         const uint64_t* seg_end, const uint64_t* k, int nseg, float* values_out,
+                         int64_t* index_out, float* residual_out, void* stream);
+
+/* ---- per-layer statistics around decode -------------------------------------------
+ * QuantizingClient.unnormalize (sp/jzf_quantize.py:549-564): per layer s, w += shift[s] (the past
+ * mean), then stats_out[2s] = mean(w), stats_out[2s+1] = std(w) (population, two-pass as np.std).
+ * w / w_out: device float64 [total] (w_out may be NULL = statistics only, or alias w); seg_end / shift:
+ * HOST arrays (shift may be NULL = 0); stats_out: DEVICE double[2*nseg].  Deterministic summation
+ * order, but not numpy's: parity with the reference is to 1e-12 relative, not bit-exact. */
+int flashe_segment_stats(flashe_ctx* ctx, const double* w, double* w_out, uint64_t total,
+                         const uint64_t* seg_end, const double* shift, int nseg, double* stats_out,
+                         void* stream);
+
 /* Number of kernels this library has launched on the calling process since load (bench bookkeeping). */
 uint64_t flashe_launch_count(void);
 

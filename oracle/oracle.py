@@ -289,3 +289,81 @@ def noise_uniform(seed, stream, begin, count):
     a = np.where(odd, o[2], o[0])
     b = np.where(odd, o[3], o[1])
     return ((a >> np.uint64(5)).astype(np.float64) * 67108864.0 + (b >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# SURVEY §8 "next" rows, restated with numpy (test infrastructure like everything above).
+# ---------------------------------------------------------------------------------------------------
+def wire_pack(words, bits):
+    """_to_bytes (framework/jzf_weights.py:45-84): s = sum_j a[j] << ((L-1-j)*bits), returned as the
+    big-endian byte string of ceil(L*bits/8) bytes.  words: uint32/uint64 [L] or uint64 [L, 2] (lo, hi).
+    The reference's per-batch loop only bounds its intermediate integers; the bits of s are the
+    concatenation of the fields, first element first, right-aligned in the byte string."""
+    w = np.ascontiguousarray(words)
+    L = w.shape[0]
+    nbytes = (L * bits + 7) // 8
+    if L == 0:
+        return np.zeros(0, dtype=np.uint8)
+    if w.ndim == 2:
+        lo, hi = w[:, 0].astype(np.uint64), w[:, 1].astype(np.uint64)
+    else:
+        lo, hi = w.astype(np.uint64), np.zeros(L, dtype=np.uint64)
+    pos = np.arange(bits - 1, -1, -1, dtype=np.uint64)             # most significant bit of a field first
+    src = np.where(pos >= 64, hi[:, None], lo[:, None])
+    field_bits = ((src >> (pos % np.uint64(64))[None, :]) & np.uint64(1)).astype(np.uint8)
+    stream = np.concatenate([np.zeros(8 * nbytes - L * bits, dtype=np.uint8), field_bits.reshape(-1)])
+    return np.packbits(stream)
+
+
+def wire_unpack(data, count, bits):
+    """_from_bytes + reverse (framework/jzf_weights.py:98-137, 224) on the byte string; returns uint64 [L]
+    (bits <= 64) or uint64 [L, 2]."""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    nbytes = (count * bits + 7) // 8
+    assert data.shape[0] == nbytes
+    stream = np.unpackbits(data)[8 * nbytes - count * bits:].reshape(count, bits).astype(np.uint64)
+    pos = np.arange(bits - 1, -1, -1, dtype=np.uint64)
+    lo = (stream[:, pos < 64] << pos[pos < 64][None, :]).sum(axis=1, dtype=np.uint64)
+    if bits <= 64:
+        return lo
+    hi = (stream[:, pos >= 64] << (pos[pos >= 64] - np.uint64(64))[None, :]).sum(axis=1, dtype=np.uint64)
+    return np.stack([lo, hi], axis=1)
+
+
+def sparsify_k(sparsity, size):
+    """idx = max(1, int(np.floor(self._sparsity * size))) — jzf_aggregator.py:598."""
+    return max(1, int(np.floor(sparsity * np.int64(size))))
+
+
+def sparsify(layers, remain, sparsity):
+    """Client.sparsify (proc/jzf_aggregator.py:578-623) over a list of float32 layers in walking order.
+    Returns (compact values per layer, new residual per layer, global locations int64, base).  Ties at the
+    k-th largest |x| are resolved as a STABLE ascending argsort followed by [-k:] does (highest indices
+    win); the reference's default introsort leaves that choice unspecified."""
+    out_vals, out_rem, locations, base = [], [], [], 0
+    for i, layer in enumerate(layers):
+        flatten = np.array(layer, dtype=np.float32).flatten()
+        size = flatten.size
+        abs_flatten = np.abs(flatten)
+        if remain is not None:
+            flatten += remain[i]
+        k = sparsify_k(sparsity, size)
+        location = sorted(abs_flatten.argsort(kind="stable")[-k:][::-1])
+        out_vals.append(flatten[location].copy())
+        flatten[location] = 0.0
+        out_rem.append(flatten)
+        locations += [int(l) + base for l in location]
+        base += size
+    return out_vals, out_rem, np.array(locations, dtype=np.int64), base
+
+
+def unnormalize_stats(w, seg_end, shift):
+    """QuantizingClient.unnormalize (sp/jzf_quantize.py:549-564) on a flat float64 vector of layers:
+    returns (w + shift per layer, [(mean, std)] per layer) with numpy's own mean / std."""
+    w = np.array(w, dtype=np.float64)
+    stats, b = [], 0
+    for e, s in zip(seg_end, shift):
+        w[b:e] += s
+        stats.append((np.mean(w[b:e]) if e > b else 0.0, np.std(w[b:e]) if e > b else 0.0))
+        b = e
+    return w, np.array(stats, dtype=np.float64)

@@ -54,6 +54,20 @@ def parse_args():
     return ap.parse_args()
 
 
+def measured_traffic(n_client_elements):
+    """DRAM bytes of the encode kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch), scaled to
+    this launch's client-elements when the shapes differ.  None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))["k_stream_encode"]
+        per = float(d["dram_bytes"]) / float(d["client_elements"])
+        return per * n_client_elements, "%s (%.3f B per client-element, captured on %d client-elements)" % (
+            d["source"], per, int(d["client_elements"]))
+    except Exception:
+        return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -288,6 +302,7 @@ def run_ours(args):
     lds_peak_blocks = 148 * sm_mhz * 1e6 * 32 / 212.0
     agg_bytes = (n + 1) * count * 4
     dec_bytes = count * 12
+    traffic, traffic_src = measured_traffic(n * count)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -295,9 +310,10 @@ def run_ours(args):
         "config": workload_config(args, n_jobs),
         "clocks": clocks,
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "k_stream<1,6,M_ENCODE> (fused encode + AES-256 PRF masks + modular add)",
+        "roofline": {"bound": "hbm", "kernel": "k_stream<WORDS=%d, MMAX=%d, M_ENCODE, SHARE=%d> (fused encode + AES-256 PRF masks + modular add)"
+                               % (1 if bits <= 32 else (2 if bits <= 64 else 4), 4 if m <= 4 else (6 if m <= 6 else 16), int(bool(args.share_streams))),
                      "achieved": enc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": enc_gbs / hbm_peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": enc_bytes, "ms_per_launch": ph[0],
                      "note": "this kernel is bound by the PRF (shared-memory table lookups), not HBM: see roofline_prf"},
         "roofline_prf": {"bound": "lds", "achieved": blocks_per_s / 1e9, "peak": lds_peak_blocks / 1e9, "unit": "G AES-256 blocks/s",
@@ -497,10 +513,20 @@ def cpu_baseline(args, ctx, fb):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly one JSON line: anything a library prints there while we run (NCCL's version
+    # banner, torchrun notices) is sent to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout, sys.stdout = sys.stdout, os.fdopen(json_fd, "w")
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+        sys.stdout.flush()
+    finally:
+        sys.stdout = real_stdout
 
 
 if __name__ == "__main__":

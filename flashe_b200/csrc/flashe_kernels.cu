@@ -519,6 +519,48 @@ __device__ __forceinline__ void stg_d2(double* p, double a, double b) {
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
+// Four consecutive 4-byte elements whose first element sits `r` elements past a 16-byte boundary
+// (r is warp-uniform: it is a property of the reference chunk the item belongs to).  r = 0: one
+// 128-bit access; r = 2: two 64-bit accesses; r odd: 32 + 64 + 32 bits.  The narrower loads allocate
+// in L1 (the lane's accesses share sectors), the stores merge in L2.
+__device__ __forceinline__ void ldg_quad(const void* p, uint32_t r, uint32_t (&v)[4]) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+    if (r == 0u) {
+        ldg_v4(q, v[0], v[1], v[2], v[3]);
+    } else if (r == 2u) {
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "l"(q));
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v[2]), "=r"(v[3]) : "l"(q + 2));
+    } else {
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v[0]) : "l"(q));
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v[1]), "=r"(v[2]) : "l"(q + 1));
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v[3]) : "l"(q + 3));
+    }
+}
+__device__ __forceinline__ void stg_quad(void* p, uint32_t r, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t* q = reinterpret_cast<uint32_t*>(p);
+    if (r == 0u) {
+        stg_v4(q, a, b, c, d);
+    } else if (r == 2u) {
+        asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(q), "r"(a), "r"(b) : "memory");
+        asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(q + 2), "r"(c), "r"(d) : "memory");
+    } else {
+        asm volatile("st.global.u32 [%0], %1;" ::"l"(q), "r"(a) : "memory");
+        asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(q + 1), "r"(b), "r"(c) : "memory");
+        asm volatile("st.global.u32 [%0], %1;" ::"l"(q + 3), "r"(d) : "memory");
+    }
+}
+// four consecutive float64 outputs, first one `r` elements past a 32-byte boundary of the element grid
+__device__ __forceinline__ void stg_quad_f64(double* p, uint32_t r, const double (&v)[4]) {
+    if ((r & 1u) == 0u) {
+        stg_d2(p, v[0], v[1]);
+        stg_d2(p + 2, v[2], v[3]);
+    } else {
+        asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v[0]) : "memory");
+        stg_d2(p + 1, v[1], v[2]);
+        asm volatile("st.global.f64 [%0], %1;" ::"l"(p + 3), "d"(v[3]) : "memory");
+    }
+}
+
 // Out-of-line single block for the rare paths (chunk tails, counters >= 2^32).
 __device__ __noinline__ void aes256_block_slow(const KeySched& ks, uint32_t y, uint32_t w0, uint32_t w1, uint32_t w2,
                                                uint32_t w3, Pre pre, uint32_t* o) {
@@ -657,8 +699,9 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
         // Fast path (4-byte words, m = 4, full item inside the shard, 16-byte aligned): a lane's AES
         // block IS four consecutive elements, so it loads / stores them itself with 128-bit accesses
         // (a warp covers 512 contiguous bytes) and nothing goes through the slab.
-        const bool quad = QUAD_OK && m == 4u && io.quad && par == 0u && item_n == NB * 128u && item_e0 >= g.begin &&
-                          item_e0 + item_n <= g.end && ((item_e0 - g.begin) & 3ull) == 0ull;
+        const bool quad = QUAD_OK && m == 4u && io.quad && item_n == NB * 128u && item_e0 >= g.begin &&
+                          item_e0 + item_n <= g.end;
+        const uint32_t qr = (uint32_t)(item_e0 - g.begin) & 3u;      // misalignment of the chunk in the buffers
         const uint64_t qoff = (item_e0 - g.begin) + 4ull * lane;     // block A's elements; block B: +128
 
         // one AES pass: F(iter, prf) for this lane's two blocks, accumulated with sign
@@ -693,9 +736,9 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
             if (HAS_IN && emit && QUAD_OK && quad) {
                 if constexpr (QUAD_OK && HAS_IN) {
                     const in_t* in = reinterpret_cast<const in_t*>(io.in) + (uint64_t)c * io.in_stride + qoff;
-                    uint32_t* r = reinterpret_cast<uint32_t*>(&pf[0][0]);
-                    ldg_v4(in, r[0], r[1], r[2], r[3]);
-                    ldg_v4(in + 128, r[4], r[5], r[6], r[7]);
+                    uint32_t (*r)[4] = reinterpret_cast<uint32_t (*)[4]>(&pf[0][0]);
+                    ldg_quad(in, qr, r[0]);
+                    ldg_quad(in + 128, qr, r[1]);
                 }
             } else if (HAS_IN && emit) {
                 const in_t* in = reinterpret_cast<const in_t*>(io.in) + (uint64_t)c * io.in_stride;
@@ -747,19 +790,24 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                         for (int k = 0; k < 4; ++k) mw[k] = (uint32_t)acc[h][k] & mk32;
                         const uint32_t* r = reinterpret_cast<const uint32_t*>(&pf[0][0]) + 4 * h;
                         if (MODE == M_MASKS) {
-                            stg_v4(reinterpret_cast<uint32_t*>(io.out) + o, mw[0], mw[1], mw[2], mw[3]);
+                            stg_quad(reinterpret_cast<uint32_t*>(io.out) + o, qr, mw[0], mw[1], mw[2], mw[3]);
                         } else if (MODE == M_APPLY) {
                             uint32_t* out = reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o;
-                            stg_v4(out, (r[0] + mw[0]) & mk32, (r[1] + mw[1]) & mk32, (r[2] + mw[2]) & mk32, (r[3] + mw[3]) & mk32);
+                            stg_quad(out, qr, (r[0] + mw[0]) & mk32, (r[1] + mw[1]) & mk32, (r[2] + mw[2]) & mk32, (r[3] + mw[3]) & mk32);
                         } else if (MODE == M_ENCODE) {
                             double u[4];
                             if (nz.u) {
                                 const double* up = nz.u + (uint64_t)c * nz.u_stride + o;
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) u[k] = up[k];
-                            } else {
+                            } else if ((j & 1ull) == 0ull) {
                                 noise_pair(nz, nz.stream + c, j >> 1, u[0], u[1]);
                                 noise_pair(nz, nz.stream + c, (j >> 1) + 1, u[2], u[3]);
+                            } else {                      // odd chunk start: the four elements touch three pairs
+                                double lo, hi;
+                                noise_pair(nz, nz.stream + c, j >> 1, lo, u[0]);
+                                noise_pair(nz, nz.stream + c, (j >> 1) + 1, u[1], u[2]);
+                                noise_pair(nz, nz.stream + c, (j >> 1) + 2, u[3], hi);
                             }
                             uint32_t q[4];
                             Seg sg = find_seg(cd, j);
@@ -768,9 +816,9 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                                 if (k && j + k >= sg.end) sg = find_seg(cd, j + k);
                                 q[k] = encode_one(__uint_as_float(r[k]), u[k], sg, cd.scale);
                             }
-                            if (io.aux) stg_v4(reinterpret_cast<uint32_t*>(io.aux) + (uint64_t)c * io.out_stride + o, q[0], q[1], q[2], q[3]);
+                            if (io.aux) stg_quad(reinterpret_cast<uint32_t*>(io.aux) + (uint64_t)c * io.out_stride + o, qr, q[0], q[1], q[2], q[3]);
                             uint32_t* out = reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o;
-                            stg_v4(out, (q[0] + mw[0]) & mk32, (q[1] + mw[1]) & mk32, (q[2] + mw[2]) & mk32, (q[3] + mw[3]) & mk32);
+                            stg_quad(out, qr, (q[0] + mw[0]) & mk32, (q[1] + mw[1]) & mk32, (q[2] + mw[2]) & mk32, (q[3] + mw[3]) & mk32);
                         } else if (MODE == M_DECODE) {
                             uint32_t pw[4];
                             double dv[4];
@@ -781,9 +829,8 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                                 if (k && j + k >= sg.end) sg = find_seg(cd, j + k);
                                 dv[k] = decode_one((double)pw[k], sg.two_an, cd.den, sg.an);
                             }
-                            if (io.aux) stg_v4(reinterpret_cast<uint32_t*>(io.aux) + o, pw[0], pw[1], pw[2], pw[3]);
-                            stg_d2(io.outf + o, dv[0], dv[1]);
-                            stg_d2(io.outf + o + 2, dv[2], dv[3]);
+                            if (io.aux) stg_quad(reinterpret_cast<uint32_t*>(io.aux) + o, qr, pw[0], pw[1], pw[2], pw[3]);
+                            stg_quad_f64(io.outf + o, qr, dv);
                         }
                     }
                 }

@@ -70,10 +70,10 @@ __device__ __forceinline__ u128_t field_mask(uint32_t bits) { return bits >= 128
 // Consecutive threads read consecutive elements and write consecutive 16-byte chunks.
 template <int WB>
 __global__ void __launch_bounds__(256)
-k_wire_pack(const void* __restrict__ words, uint64_t count, uint32_t bits, uint64_t nbytes, uint8_t* __restrict__ out) {
+k_wire_pack(const void* __restrict__ words, uint64_t count, uint32_t bits, uint64_t nbytes, uint8_t* __restrict__ out, uint64_t k0) {
     const uint64_t nchunks = (nbytes + 15) >> 4;
     const u128_t fm = field_mask(bits);
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nchunks; k += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t k = k0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nchunks; k += (uint64_t)gridDim.x * blockDim.x) {
         const int64_t hi_bit = (int64_t)(8 * (nbytes - 16 * k));     // exclusive, > 0
         const int64_t lo_bit = hi_bit - 128;
         // fields are numbered from the END: field e holds element count-1-e at bits [e*bits, (e+1)*bits)
@@ -119,6 +119,114 @@ k_wire_unpack(const uint8_t* __restrict__ in, uint64_t count, uint32_t bits, uin
         }
         v = sh ? ((v >> sh) | ((u128_t)top << (128 - sh))) : v;
         WireWord<WB>::store(words, j, v & fm);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Fast forms for 4-byte words (8 <= bits <= 32, the ciphertext widths FLASHE ships).  Seen from its
+// first byte the wire string is a big-endian BIT stream: `pad` = 8*nbytes - count*bits zero bits, then
+// the elements in index order, most significant bit first; element j occupies stream bits
+// [pad + j*bits, pad + (j+1)*bits).  A CTA converts one tile through shared memory so that both the
+// global reads and the global writes are 16 bytes per thread and fully coalesced, and every thread
+// only touches the <= 32/bits + 2 fields (pack) or the two stream words (unpack) it needs.
+// -------------------------------------------------------------------------------------------------
+#define WP_THREADS 256
+#define WP_WORDS (WP_THREADS * 4)                 // stream words (32 bit) per pack tile
+#define WP_MAX_FIELDS (WP_WORDS * 32 / 8 + 2)     // bits >= 8
+
+// pack: tile t = stream words [t*WP_WORDS, (t+1)*WP_WORDS); only whole 16-byte chunks (nvec of them)
+__global__ void __launch_bounds__(WP_THREADS)
+k_wire_pack32(const uint32_t* __restrict__ words, uint64_t count, uint32_t bits, uint32_t pad, uint64_t nvec,
+              uint4* __restrict__ out) {
+    __shared__ uint32_t sf[WP_MAX_FIELDS];
+    const uint32_t fm = bits >= 32u ? 0xffffffffu : ((1u << bits) - 1u);
+    const uint64_t ntiles = (nvec + WP_THREADS - 1) / WP_THREADS;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t bit0 = t * (uint64_t)(WP_WORDS * 32);                 // stream bit of the tile's first word
+        const uint64_t f_lo = bit0 > pad ? (bit0 - pad) / bits : 0;         // first field that reaches into the tile
+        uint64_t f_hi = (bit0 + (uint64_t)(WP_WORDS * 32) - 1 - pad) / bits;   // pad < 8 <= tile bits
+        if (f_hi >= count) f_hi = count - 1;
+        const uint32_t nf = (uint32_t)(f_hi - f_lo + 1);
+        // rel0 = stream position of field f_lo relative to the tile, in (-bits, 32); kept as rel0 + 32 > 0
+        const uint32_t rel0p = (uint32_t)((int64_t)(pad + f_lo * bits) - (int64_t)bit0 + 32);
+        __syncthreads();                                                    // previous tile's readers are done
+        // staged loads: 16 bytes per thread where the source is aligned, element-wise at the edges
+        const uint32_t* src = words + f_lo;
+        const uint32_t head = (uint32_t)((4u - ((uintptr_t)src >> 2)) & 3u);
+        for (uint32_t i = threadIdx.x; i < head && i < nf; i += WP_THREADS) sf[i] = src[i] & fm;
+        const uint32_t nq = nf > head ? (nf - head) >> 2 : 0;
+        for (uint32_t q = threadIdx.x; q < nq; q += WP_THREADS) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src + head) + q);
+            const uint32_t i = head + 4u * q;
+            sf[i] = v.x & fm; sf[i + 1] = v.y & fm; sf[i + 2] = v.z & fm; sf[i + 3] = v.w & fm;
+        }
+        for (uint32_t i = head + 4u * nq + threadIdx.x; i < nf; i += WP_THREADS) sf[i] = src[i] & fm;
+        __syncthreads();
+        const uint64_t vec = t * WP_THREADS + threadIdx.x;
+        if (vec < nvec) {
+            uint32_t w[4];
+            const uint32_t wbit0 = 128u * threadIdx.x + 32u;                 // first word's start, in the rel0p frame
+            uint32_t i = wbit0 >= rel0p ? (wbit0 - rel0p) / bits : 0u;       // the field that holds that bit
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t wbit = wbit0 + 32u * k;
+                uint64_t acc = 0;
+                for (; i < nf; ++i) {                                        // fields that intersect [wbit, wbit + 32)
+                    const uint32_t pos = rel0p + i * bits;                   // field start (frame: tile bit + 32)
+                    if (pos >= wbit + 32u) break;
+                    // 64-bit window = stream bits [wbit - 32, wbit + 32); the field's top bit sits at pos - (wbit - 32)
+                    const int sh = 64 - (int)bits - (int)(pos + 32u - wbit);
+                    acc |= sh >= 0 ? ((uint64_t)sf[i] << sh) : ((uint64_t)sf[i] >> (-sh));
+                }
+                if (i > 0u && rel0p + i * bits > wbit + 32u) --i;            // the last field runs on into the next word
+                w[k] = __byte_perm((uint32_t)acc, 0, 0x0123);                // first stream byte first
+            }
+            __stcs(out + vec, make_uint4(w[0], w[1], w[2], w[3]));
+        }
+    }
+}
+
+// unpack: tile = WP_WORDS consecutive elements, thread = 4 of them (one 16-byte store)
+#define WU_ELEMS (WP_THREADS * 4)
+__global__ void __launch_bounds__(WP_THREADS)
+k_wire_unpack32(const uint8_t* __restrict__ in, uint64_t count, uint32_t bits, uint32_t pad, uint64_t nbytes,
+                uint32_t* __restrict__ words) {
+    __shared__ uint32_t sw[WU_ELEMS + 8];
+    const uint32_t fm = bits >= 32u ? 0xffffffffu : ((1u << bits) - 1u);
+    const uint64_t ntiles = (count + WU_ELEMS - 1) / WU_ELEMS;
+    const uint64_t nwords_in = nbytes >> 2;                                  // whole stream words
+    const bool in_al4 = ((uintptr_t)in & 3u) == 0;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t j0 = t * WU_ELEMS;
+        const uint32_t ne = (uint32_t)(count - j0 < WU_ELEMS ? count - j0 : WU_ELEMS);
+        const uint64_t b_lo = pad + j0 * bits, b_hi = b_lo + (uint64_t)ne * bits;   // stream bits [b_lo, b_hi)
+        const uint64_t w_lo = b_lo >> 5, w_hi = (b_hi + 31) >> 5;                    // stream words [w_lo, w_hi)
+        const uint32_t nw = (uint32_t)(w_hi - w_lo);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i <= nw; i += WP_THREADS) {           // one extra (zero) word for the window
+            const uint64_t w = w_lo + i;
+            uint32_t v = 0;
+            if (i < nw) {
+                if (w < nwords_in && in_al4) v = __byte_perm(__ldcs(reinterpret_cast<const uint32_t*>(in) + w), 0, 0x0123);
+                else for (uint32_t b = 0; b < 4; ++b) { const uint64_t a = 4 * w + b; v = (v << 8) | (a < nbytes ? in[a] : 0u); }
+            }
+            sw[i] = v;
+        }
+        __syncthreads();
+        const uint32_t e0 = 4u * threadIdx.x;
+        if (e0 < ne) {
+            uint32_t r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t o = (uint32_t)(b_lo - (w_lo << 5)) + (e0 + k) * bits;
+                const uint32_t wi = o >> 5;
+                const uint64_t win = ((uint64_t)sw[wi < nw ? wi : nw] << 32) | sw[wi + 1 <= nw ? wi + 1 : nw];
+                r[k] = (uint32_t)(win >> (64u - bits - (o & 31u))) & fm;
+            }
+            uint32_t* dst = words + j0 + e0;
+            if (e0 + 4u <= ne && ((uintptr_t)dst & 15u) == 0) __stcs(reinterpret_cast<uint4*>(dst), make_uint4(r[0], r[1], r[2], r[3]));
+            else for (uint32_t k = 0; k < 4u && e0 + k < ne; ++k) dst[k] = r[k];
+        }
     }
 }
 
@@ -431,10 +539,26 @@ int flashe_wire_pack(flashe_ctx* ctx, const void* words, int word_bytes, uint64_
     if (!words || !out) return flashe_fail(FLASHE_EINVAL, "NULL buffer");
     if (((uintptr_t)out & 15u) != 0) return flashe_fail(FLASHE_EINVAL, "out must be 16-byte aligned");
     uint64_t nbytes; rc = flashe_wire_nbytes(bits, count, &nbytes); if (rc) return rc;
+    if (word_bytes == 4 && bits >= 8) {
+        // whole 16-byte chunks through the tiled kernel, a short final chunk through the generic one
+        const uint64_t nvec = nbytes >> 4;
+        const uint32_t pad = (uint32_t)(8 * nbytes - count * (uint64_t)bits);
+        int launches = 0;
+        if (nvec) {
+            const int grid = grid_cap(info.num_sms, ceil_div_u64(nvec, WP_THREADS), 8);
+            k_wire_pack32<<<grid, WP_THREADS, 0, cs>>>(reinterpret_cast<const uint32_t*>(words), count, (uint32_t)bits, pad, nvec,
+                                                        reinterpret_cast<uint4*>(out));
+            ++launches;
+        }
+        if (nbytes & 15u) { k_wire_pack<4><<<1, 32, 0, cs>>>(words, count, (uint32_t)bits, nbytes, out, nvec); ++launches; }
+        flashe_count_launches(launches);
+        FLASHE_CUDA_TRY(cudaGetLastError());
+        return FLASHE_OK;
+    }
     const int grid = grid_cap(info.num_sms, ceil_div_u64((nbytes + 15) / 16, 256), 8);
-    if (word_bytes == 4) k_wire_pack<4><<<grid, 256, 0, cs>>>(words, count, (uint32_t)bits, nbytes, out);
-    else if (word_bytes == 8) k_wire_pack<8><<<grid, 256, 0, cs>>>(words, count, (uint32_t)bits, nbytes, out);
-    else k_wire_pack<16><<<grid, 256, 0, cs>>>(words, count, (uint32_t)bits, nbytes, out);
+    if (word_bytes == 4) k_wire_pack<4><<<grid, 256, 0, cs>>>(words, count, (uint32_t)bits, nbytes, out, 0);
+    else if (word_bytes == 8) k_wire_pack<8><<<grid, 256, 0, cs>>>(words, count, (uint32_t)bits, nbytes, out, 0);
+    else k_wire_pack<16><<<grid, 256, 0, cs>>>(words, count, (uint32_t)bits, nbytes, out, 0);
     flashe_count_launches(1);
     FLASHE_CUDA_TRY(cudaGetLastError());
     return FLASHE_OK;
@@ -446,6 +570,14 @@ int flashe_wire_unpack(flashe_ctx* ctx, const uint8_t* in, uint64_t count, int b
     if (count == 0) return FLASHE_OK;
     if (!in || !words_out) return flashe_fail(FLASHE_EINVAL, "NULL buffer");
     uint64_t nbytes; rc = flashe_wire_nbytes(bits, count, &nbytes); if (rc) return rc;
+    if (word_bytes == 4 && ((uintptr_t)words_out & 3u) == 0) {
+        const uint32_t pad = (uint32_t)(8 * nbytes - count * (uint64_t)bits);
+        const int grid = grid_cap(info.num_sms, ceil_div_u64(count, WU_ELEMS), 8);
+        k_wire_unpack32<<<grid, WP_THREADS, 0, cs>>>(in, count, (uint32_t)bits, pad, nbytes, reinterpret_cast<uint32_t*>(words_out));
+        flashe_count_launches(1);
+        FLASHE_CUDA_TRY(cudaGetLastError());
+        return FLASHE_OK;
+    }
     const int grid = grid_cap(info.num_sms, ceil_div_u64(count, 256), 8);
     if (word_bytes == 4) k_wire_unpack<4><<<grid, 256, 0, cs>>>(in, count, (uint32_t)bits, nbytes, words_out);
     else if (word_bytes == 8) k_wire_unpack<8><<<grid, 256, 0, cs>>>(in, count, (uint32_t)bits, nbytes, words_out);

@@ -459,10 +459,13 @@ def test_quantizing_client_seed_level_parity(fb, golden):
         assert np.array_equal(np.asarray(w2._weights["layer0"], dtype=np.float64).view(np.uint64), golden["batch_decoded"].view(np.uint64))
 
 
-@pytest.mark.parametrize("bits,n_jobs,L", [(32, 8, 1 << 20), (32, 16, 3_000_000), (28, 4, 600_000)])
+@pytest.mark.parametrize("bits,n_jobs,L", [(32, 8, 1 << 20), (32, 16, 3_000_000), (28, 4, 600_000),
+                                           (32, 7, 7 * 150_001), (32, 24, 2_000_003), (27, 3, 3 * 100_002)])
 def test_aligned_fast_path_vs_oracle(fb, bits, n_jobs, L):
-    """m = 4 with 16-byte aligned chunk starts takes the 128-bit lane-local path; every mode must
-    agree with the oracle, for whole vectors and for shards cut on and off 4-element boundaries."""
+    """m = 4 takes the lane-local path: 128-bit accesses when the chunk starts on a 16-byte boundary of
+    the buffers, 64/32-bit pieces otherwise (odd chunk lengths put chunk starts at every residue mod 4:
+    the last three cases); every mode must agree with the oracle, for whole vectors and for shards cut
+    on and off 4-element boundaries."""
     ctx = ctx_for(fb, bits)
     it, n = 9, 3
     rs = np.random.RandomState(123)

@@ -61,7 +61,10 @@ def test_wire_golden(fb, gold):
 @pytest.mark.parametrize("bits,L,wb", [(20, 1, 4), (20, 2, 4), (20, 1000003, 4), (32, 999999, 4), (24, 65537, 4), (8, 4097, 4),
                                        (1, 77, 4), (31, 12345, 4), (26, 500000, 8), (27, 300001, 8), (33, 70001, 8),
                                        (64, 50001, 8), (7, 1000, 8), (120, 40001, 16), (128, 5003, 16), (65, 9999, 16),
-                                       (100, 3, 16), (20, 999, 16)])
+                                       (100, 3, 16), (20, 999, 16),
+                                       # tiled 4-byte kernels: several tiles, every tail length, narrow and odd widths
+                                       (12, 100001, 4), (9, 33333, 4), (17, 262149, 4), (32, 4096, 4), (16, 16384, 4),
+                                       (25, 1, 4), (3, 5000, 4), (20, 4096 * 3 + 1, 4), (29, 8191, 4), (8, 16, 4), (13, 7, 4)])
 def test_wire_vs_oracle(fb, bits, L, wb):
     rs = np.random.RandomState(bits * 1000 + L % 1000)
     ctx = fb.DeviceContext(KEY, 32)
@@ -79,6 +82,17 @@ def test_wire_vs_oracle(fb, bits, L, wb):
     assert np.array_equal(_np(got), want)
     back = _np(ctx.wire_unpack(got, L, bits, word_bytes=wb))
     assert np.array_equal(back, w)
+
+
+def test_wire_unaligned_views(fb):
+    # source / destination views that start off a 16-byte boundary
+    ctx = fb.DeviceContext(KEY, 32)
+    for bits, L, off in ((20, 70001, 1), (24, 9000, 3), (32, 5001, 2)):
+        w = np.random.RandomState(L).randint(0, 1 << bits, L + off, dtype=np.int64).astype(np.uint32)
+        t = _dev(w)[off:]
+        got = ctx.wire_pack(t, bits)
+        assert np.array_equal(_np(got), O.wire_pack(w[off:], bits)), (bits, L, off)
+        assert np.array_equal(_np(ctx.wire_unpack(got, L, bits)), w[off:])
 
 
 def test_wire_ciphertext_roundtrip_matches_python_bigint(fb):

@@ -118,7 +118,7 @@ static void hoist_round1(const uint32_t rk[60], uint32_t w0, uint32_t w1, uint32
 #define STREAM_THREADS 512
 #endif
 
-struct KeySched { uint32_t rk[60]; };
+struct alignas(16) KeySched { uint32_t rk[60]; };
 
 struct StreamTab {
     uint32_t n;           // entries
@@ -140,6 +140,7 @@ struct Geom {
     uint64_t S_lo, S_cnt;    // work units that intersect the shard
     uint32_t m, b;           // slots per AES block, int_bits
     uint32_t sup;            // warp items per work unit (consecutive items of one chunk)
+    uint32_t aligned4;       // every chunk begin and the shard begin are multiples of 4 elements
 };
 
 struct Seg { uint64_t end; float a, two_a; float rcp_two_a, pad; double an, two_an; };  // rcp_two_a = RN(1/two_a), 0 = not usable
@@ -284,7 +285,11 @@ __device__ __forceinline__ void aes256_block(const KeySched& ks, uint32_t y, uin
 // device: geometry of the reference's chunked counter rule (jzf_flashe.py:12-16, 24-34)
 // ------------------------------------------------------------------------------------------------
 #define ITEM_BLOCKS 64u   // AES blocks per warp item (two per lane)
-struct Item { uint64_t cb; uint64_t clen; uint64_t i0; };  // chunk begin, chunk length, first block
+// Items are cut on multiples of 64 of the AES COUNTER (counter = chunk begin + block, jzf_flashe.py:34),
+// not of the block number: item 0 of a chunk holds its first 64 - (cb & 63) blocks, item w >= 1 the
+// blocks [64w - (cb & 63), +64).  All counters of an item then share their upper 56 bits, which is
+// what lets the first two AES rounds be factored per item (window_consts below).
+struct Item { uint64_t cb; uint64_t clen; uint64_t w; uint32_t off; };  // chunk begin, chunk length, first item, cb & 63
 
 // Work unit S -> first warp item of the unit and the number of items in it.  The two 64-bit divisions
 // happen once per unit; the items inside are walked incrementally.
@@ -300,7 +305,8 @@ __device__ __forceinline__ Item decode_unit(const Geom& g, uint64_t S, uint32_t&
         it.cb = g.r * (g.d + 1) + k * g.d; it.clen = g.d; nw = g.nwB;
     }
     const uint64_t w0 = s * g.sup, left = nw - w0;
-    it.i0 = w0 * ITEM_BLOCKS;
+    it.w = w0;
+    it.off = (uint32_t)(it.cb & (ITEM_BLOCKS - 1u));
     nsub = (uint32_t)(left < g.sup ? left : g.sup);
     return it;
 }
@@ -635,10 +641,80 @@ __device__ __forceinline__ void aes256_x2(const KeySched& ks, uint32_t y, Pre pr
 // ------------------------------------------------------------------------------------------------
 #define NB 2
 
+// Counter-window factoring.  The AES input is iter || prf || ctr_hi || ctr_lo and only ctr_lo's low
+// byte differs between the counters of one 256-aligned window.  After round 1 that byte has reached
+// column 0 only (p0); columns 1-3 are window constants.  In round 2 every output column takes exactly
+// one byte of column 0, so three of its four lookups are window constants too: c0..c3 below (round key
+// folded in).  Per block, rounds 1-2 then cost 1 + 4 lookups instead of 4 + 16 (197 per block instead
+// of 212); the 15 lookups of window_consts are paid once per window and stream, or once per lane pair.
+struct WinC { uint32_t c0, c1, c2, c3; };
+__device__ __forceinline__ WinC window_consts(const KeySched& ks, uint32_t y, Pre pre, uint32_t w3) {
+    const uint32_t s3 = w3 ^ ks.rk[3];
+    const uint32_t p1 = pre.p1 ^ T2(s3), p2 = pre.p2 ^ T1(s3), p3 = pre.p3 ^ T0(s3);
+    WinC c;
+    c.c0 = T1(p1) ^ T2(p2) ^ T3(p3) ^ ks.rk[8];
+    c.c1 = T0(p1) ^ T1(p2) ^ T2(p3) ^ ks.rk[9];
+    c.c2 = T0(p2) ^ T1(p3) ^ T3(p1) ^ ks.rk[10];
+    c.c3 = T0(p3) ^ T2(p1) ^ T3(p2) ^ ks.rk[11];
+    return c;
+}
+
+// Two blocks of the same stream and the same counter window (see aes256_x2 for the interleaving).
+__device__ __forceinline__ void aes256_x2w(const KeySched& ks, uint32_t y, uint32_t pre_p0, WinC c, uint32_t w3a, uint32_t w3b,
+                                           uint32_t oa[4], uint32_t ob[4]) {
+    uint32_t a0, a1, a2, a3, b0, b1, b2, b3, p0, p1, p2, p3, q0, q1, q2, q3;
+    p0 = pre_p0 ^ T3(w3a ^ ks.rk[3]); q0 = pre_p0 ^ T3(w3b ^ ks.rk[3]);      // round 1, column 0
+    a0 = c.c0 ^ T0(p0); b0 = c.c0 ^ T0(q0);                                   // round 2
+    a1 = c.c1 ^ T3(p0); b1 = c.c1 ^ T3(q0);
+    a2 = c.c2 ^ T2(p0); b2 = c.c2 ^ T2(q0);
+    a3 = c.c3 ^ T1(p0); b3 = c.c3 ^ T1(q0);
+    p0 = T0(a0) ^ T1(a1) ^ T2(a2) ^ T3(a3) ^ ks.rk[12];                       // round 3
+    q0 = T0(b0) ^ T1(b1) ^ T2(b2) ^ T3(b3) ^ ks.rk[12];
+    p1 = T0(a1) ^ T1(a2) ^ T2(a3) ^ T3(a0) ^ ks.rk[13];
+    q1 = T0(b1) ^ T1(b2) ^ T2(b3) ^ T3(b0) ^ ks.rk[13];
+    p2 = T0(a2) ^ T1(a3) ^ T2(a0) ^ T3(a1) ^ ks.rk[14];
+    q2 = T0(b2) ^ T1(b3) ^ T2(b0) ^ T3(b1) ^ ks.rk[14];
+    p3 = T0(a3) ^ T1(a0) ^ T2(a1) ^ T3(a2) ^ ks.rk[15];
+    q3 = T0(b3) ^ T1(b0) ^ T2(b1) ^ T3(b2) ^ ks.rk[15];
+    AES_ROUNDS_UNROLL
+    for (int r = 4; r < 14; r += 2) {                                         // rounds 4..13
+        // both round keys of the iteration as two 128-bit constant-bank loads (the rolled loop indexes them)
+        const uint4 k0 = *reinterpret_cast<const uint4*>(&ks.rk[4 * r]), k1 = *reinterpret_cast<const uint4*>(&ks.rk[4 * r + 4]);
+        a0 = T0(p0) ^ T1(p1) ^ T2(p2) ^ T3(p3) ^ k0.x;
+        b0 = T0(q0) ^ T1(q1) ^ T2(q2) ^ T3(q3) ^ k0.x;
+        a1 = T0(p1) ^ T1(p2) ^ T2(p3) ^ T3(p0) ^ k0.y;
+        b1 = T0(q1) ^ T1(q2) ^ T2(q3) ^ T3(q0) ^ k0.y;
+        a2 = T0(p2) ^ T1(p3) ^ T2(p0) ^ T3(p1) ^ k0.z;
+        b2 = T0(q2) ^ T1(q3) ^ T2(q0) ^ T3(q1) ^ k0.z;
+        a3 = T0(p3) ^ T1(p0) ^ T2(p1) ^ T3(p2) ^ k0.w;
+        b3 = T0(q3) ^ T1(q0) ^ T2(q1) ^ T3(q2) ^ k0.w;
+        p0 = T0(a0) ^ T1(a1) ^ T2(a2) ^ T3(a3) ^ k1.x;
+        q0 = T0(b0) ^ T1(b1) ^ T2(b2) ^ T3(b3) ^ k1.x;
+        p1 = T0(a1) ^ T1(a2) ^ T2(a3) ^ T3(a0) ^ k1.y;
+        q1 = T0(b1) ^ T1(b2) ^ T2(b3) ^ T3(b0) ^ k1.y;
+        p2 = T0(a2) ^ T1(a3) ^ T2(a0) ^ T3(a1) ^ k1.z;
+        q2 = T0(b2) ^ T1(b3) ^ T2(b0) ^ T3(b1) ^ k1.z;
+        p3 = T0(a3) ^ T1(a0) ^ T2(a1) ^ T3(a2) ^ k1.w;
+        q3 = T0(b3) ^ T1(b0) ^ T2(b1) ^ T3(b2) ^ k1.w;
+    }
+#define LAST(a, b, c, d, k)                                                                         \
+    (__byte_perm(__byte_perm(lds_tab<128>(__byte_perm((d), y, SEL_B0)),                             \
+                             lds_tab<0>(__byte_perm((c), y, SEL_B1)), 0x3250),                      \
+                 __byte_perm(lds_tab<0x10080>(__byte_perm((b), y, SEL_B2)),                         \
+                             lds_tab<0x10000>(__byte_perm((a), y, SEL_B3)), 0x7210), 0x7610) ^ ks.rk[k])
+    oa[0] = LAST(p0, p1, p2, p3, 56); ob[0] = LAST(q0, q1, q2, q3, 56);
+    oa[1] = LAST(p1, p2, p3, p0, 57); ob[1] = LAST(q1, q2, q3, q0, 57);
+    oa[2] = LAST(p2, p3, p0, p1, 58); ob[2] = LAST(q2, q3, q0, q1, 58);
+    oa[3] = LAST(p3, p0, p1, p2, 59); ob[3] = LAST(q3, q0, q1, q2, 59);
+#undef LAST
+}
+
 template <int MODE, int WORDS> struct InType { typedef typename Word<WORDS>::T T; };
 template <int WORDS> struct InType<M_ENCODE, WORDS> { typedef float T; };
 
-template <int WORDS, int MMAX, int MODE, bool SHARE>
+// ALIGNED (4-byte words, m = 4 only): the host has checked that every chunk of the span starts on a
+// multiple of 4 elements, so the lane-local path is 128-bit accesses without an alignment switch.
+template <int WORDS, int MMAX, int MODE, bool SHARE, bool ALIGNED>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
 k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab st, const __grid_constant__ Geom g,
          const __grid_constant__ IoDev io, const __grid_constant__ CodecDev cd, const __grid_constant__ NoiseDev nz) {
@@ -655,6 +731,10 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     const uint32_t slab_bytes = (NB * 32u * MMAX + 2u + (WORDS == 1 ? 2u * MMAX + 1u : 0u)) * WB;
     if (sbase + nwarps * slab_bytes > TAB_BASE) { __trap(); }
     const uint32_t slab = sbase + warp * slab_bytes;
+    // per-warp cache of window terms: one 16-byte slot per stream-table entry, above the slabs
+    const uint32_t wcache_all = (sbase + nwarps * slab_bytes + 15u) & ~15u;
+    const bool cache_ok = wcache_all + nwarps * (MAXS * 16u) <= TAB_BASE;
+    const uint32_t wcache = wcache_all + warp * (MAXS * 16u);
 #define PRE_OF(k) Pre{st.pre[k][0], st.pre[k][1], st.pre[k][2], st.pre[k][3]}
 
     fill_tables();
@@ -680,15 +760,21 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
         // chunk rule are paid once per unit, the items inside advance by ITEM_BLOCKS
         uint32_t nsub;
         Item it = decode_unit(g, g.S_lo + S, nsub);
-      for (uint32_t sub = 0; sub < nsub; ++sub, it.i0 += ITEM_BLOCKS) {
-        const uint64_t item_e0 = it.cb + it.i0 * m;                  // first global element of the item
-        const uint64_t rem = it.clen - it.i0 * m;
-        const uint32_t item_n = (uint32_t)(rem < (uint64_t)(NB * 32u) * m ? rem : (uint64_t)(NB * 32u) * m);
+      uint32_t cached_win = 0xffffffffu;                             // counter window the cached round-2 terms belong to
+      for (uint32_t sub = 0; sub < nsub; ++sub, ++it.w) {
+        const uint64_t blk0 = it.w ? it.w * ITEM_BLOCKS - it.off : 0;  // first block of the item
+        const uint32_t nblk = it.w ? ITEM_BLOCKS : ITEM_BLOCKS - it.off;
+        if (blk0 * m >= it.clen) break;                                // past the chunk's last item
+        const uint64_t item_e0 = it.cb + blk0 * m;                     // first global element of the item
+        const uint64_t rem = it.clen - blk0 * m;
+        const uint32_t item_n = (uint32_t)(rem < (uint64_t)nblk * m ? rem : (uint64_t)nblk * m);
         if (item_e0 + item_n <= g.begin || item_e0 >= g.end) continue;   // item outside this shard
-        const uint64_t blkA = it.i0 + lane, blkB = blkA + 32;
-        const bool onA = blkA * m < it.clen, onB = blkB * m < it.clen;
-        const uint64_t ctrA = it.cb + blkA, ctrB = it.cb + blkB;     // jzf_flashe.py:34 "(i + begin)"
-        const bool fast = ((ctrB >> 32) == 0);                       // hoisted round 1 needs word 2 == 0
+        const uint64_t blkA = blk0 + lane, blkB = blkA + 32;
+        const bool onA = lane < nblk && blkA * m < it.clen, onB = lane + 32u < nblk && blkB * m < it.clen;
+        const uint64_t ctr0 = it.cb + blk0;                            // jzf_flashe.py:34 "(i + begin)"
+        const uint64_t ctrA = ctr0 + lane, ctrB = ctrA + 32;
+        const bool fast = (((ctr0 + ITEM_BLOCKS - 1u) >> 32) == 0);  // hoisted round 1 needs word 2 == 0
+        const uint32_t win = (uint32_t)(ctr0 >> 8);                  // same for every counter of the item
         const uint32_t par = (uint32_t)(item_e0 & 1ull);
         const uint64_t base_e = item_e0 - par;                       // even; slab index = j - base_e
         const uint32_t npairs = (par + item_n + 1u) >> 1;
@@ -699,16 +785,34 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
         // Fast path (4-byte words, m = 4, full item inside the shard, 16-byte aligned): a lane's AES
         // block IS four consecutive elements, so it loads / stores them itself with 128-bit accesses
         // (a warp covers 512 contiguous bytes) and nothing goes through the slab.
+        const uint32_t qr = ALIGNED ? 0u : ((uint32_t)(item_e0 - g.begin) & 3u);   // misalignment of the chunk in the buffers
         const bool quad = QUAD_OK && m == 4u && io.quad && item_n == NB * 128u && item_e0 >= g.begin &&
-                          item_e0 + item_n <= g.end;
-        const uint32_t qr = (uint32_t)(item_e0 - g.begin) & 3u;      // misalignment of the chunk in the buffers
+                          item_e0 + item_n <= g.end && (!ALIGNED || ((item_e0 - g.begin) & 3ull) == 0ull);
         const uint64_t qoff = (item_e0 - g.begin) + 4ull * lane;     // block A's elements; block B: +128
 
         // one AES pass: F(iter, prf) for this lane's two blocks, accumulated with sign
+        // The window terms of stream `sidx` live in the warp's cache slot `sidx` (shared memory, read by
+        // broadcast) and are recomputed by every lane (same inputs, same result) when the item enters a
+        // new counter window; called by all lanes: `fast` and `stale` are warp-uniform.
+        const bool stale = !cache_ok || win != cached_win;
         auto stream_into = [&](uint32_t sidx, int sign, word_t (&acc)[NB][MMAX]) {
             uint32_t oa[4], ob[4];
+            WinC wc = {0u, 0u, 0u, 0u};
+            if (fast) {
+                const uint32_t slot = wcache + sidx * 16u;
+                if (stale) {
+                    wc = window_consts(ks, y, PRE_OF(sidx), (uint32_t)ctr0);
+                    if (cache_ok) {
+                        if (lane == 0) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"(wc.c0), "r"(wc.c1), "r"(wc.c2), "r"(wc.c3) : "memory");
+                        __syncwarp();
+                    }
+                } else {
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wc.c0), "=r"(wc.c1), "=r"(wc.c2), "=r"(wc.c3) : "r"(slot) : "memory");
+                }
+            }
+            if (!onA) return;
             if (onB && fast) {
-                aes256_x2(ks, y, PRE_OF(sidx), (uint32_t)ctrA, (uint32_t)ctrB, oa, ob);
+                aes256_x2w(ks, y, st.pre[sidx][0], wc, (uint32_t)ctrA, (uint32_t)ctrB, oa, ob);
                 accumulate_slots<WORDS, MMAX>(oa, g.b, m, sign, acc[0]);
                 accumulate_slots<WORDS, MMAX>(ob, g.b, m, sign, acc[1]);
             } else {
@@ -755,7 +859,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
             for (int h = 0; h < NB; ++h)
 #pragma unroll
                 for (int k = 0; k < MMAX; ++k) acc[h][k] = WT::zero();
-            if (onA) {
+            {
                 uint32_t s_begin, s_count;
                 if (!st.batch) { s_begin = 0; s_count = st.n; }
                 else if (SHARE) { s_begin = cc; s_count = 1; }
@@ -800,7 +904,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                                 const double* up = nz.u + (uint64_t)c * nz.u_stride + o;
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) u[k] = up[k];
-                            } else if ((j & 1ull) == 0ull) {
+                            } else if (ALIGNED || (j & 1ull) == 0ull) {
                                 noise_pair(nz, nz.stream + c, j >> 1, u[0], u[1]);
                                 noise_pair(nz, nz.stream + c, (j >> 1) + 1, u[2], u[3]);
                             } else {                      // odd chunk start: the four elements touch three pairs
@@ -907,6 +1011,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                 }
             }
         }
+        if (fast) cached_win = win;                                  // every stream of the unit now has this window cached
       }
     }
 #undef PRE_OF
@@ -1367,17 +1472,21 @@ static void make_geom(const flashe_ctx* ctx, const flashe_span* s, uint32_t sup,
     g->m = ctx->m; g->b = (uint32_t)ctx->int_bits;
     g->d = s->total_len / s->n_jobs; g->r = s->total_len % s->n_jobs;
     const uint64_t nbA = ceil_div(g->d + 1, g->m), nbB = g->d ? ceil_div(g->d, g->m) : 0;
-    g->nwA = ceil_div(nbA, ITEM_BLOCKS); g->nwB = ceil_div(nbB, ITEM_BLOCKS);
+    // items per chunk: ceil((blocks + (cb & 63)) / 64) depends on the chunk; the bound for cb & 63 = 63 is
+    // used for every chunk (at most one empty trailing item, skipped by the kernel)
+    g->nwA = ceil_div(nbA + ITEM_BLOCKS - 1, ITEM_BLOCKS); g->nwB = nbB ? ceil_div(nbB + ITEM_BLOCKS - 1, ITEM_BLOCKS) : 0;
     if (sup < 1) sup = 1;
     g->sup = sup;
     g->nsA = ceil_div(g->nwA, sup); g->nsB = ceil_div(g->nwB, sup);
     g->rSA = g->r * g->nsA;
+    g->aligned4 = ((s->begin & 3u) == 0 && (g->r <= 1 || ((g->d + 1) & 3u) == 0) && ((g->r * (g->d + 1)) & 3u) == 0 &&
+                   ((g->d & 3u) == 0 || s->n_jobs - g->r <= 1)) ? 1u : 0u;
     if (s->count == 0) { g->S_lo = 0; g->S_cnt = 0; return; }
     auto unit_of = [&](uint64_t j) {
         uint64_t k, cb;
         if (j < g->r * (g->d + 1)) { k = j / (g->d + 1); cb = k * (g->d + 1); }
         else { k = g->r + (j - g->r * (g->d + 1)) / g->d; cb = g->r * (g->d + 1) + (k - g->r) * g->d; }
-        const uint64_t u = (((j - cb) / g->m) / ITEM_BLOCKS) / sup;
+        const uint64_t u = (((j - cb) / g->m + (cb & (ITEM_BLOCKS - 1))) / ITEM_BLOCKS) / sup;
         return (k < g->r ? k * g->nsA : g->rSA + (k - g->r) * g->nsB) + u;
     };
     g->S_lo = unit_of(g->begin);
@@ -1470,10 +1579,10 @@ static int grid_1d(const flashe_ctx* ctx, uint64_t work_items, int threads, int 
     return (int)(blocks < cap ? blocks : cap);
 }
 
-template <int WORDS, int MMAX, int MODE, bool SHARE>
+template <int WORDS, int MMAX, int MODE, bool SHARE, bool ALIGNED = false>
 static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,
                            const NoiseDev& nz, cudaStream_t stream) {
-    auto kern = k_stream<WORDS, MMAX, MODE, SHARE>;
+    auto kern = k_stream<WORDS, MMAX, MODE, SHARE, ALIGNED>;
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -1506,6 +1615,7 @@ static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom&
     if constexpr (MODE == M_ENCODE) {
         if (io.share) {
             if (b <= 32) {
+                if (ctx->m == 4 && g.aligned4 && io.quad) return launch_stream_t<1, 4, MODE, true, true>(ctx, st, g, io, cd, nz, stream);
                 if (ctx->m <= 4) return launch_stream_t<1, 4, MODE, true>(ctx, st, g, io, cd, nz, stream);
                 if (ctx->m <= 6) return launch_stream_t<1, 6, MODE, true>(ctx, st, g, io, cd, nz, stream);
                 return launch_stream_t<1, 16, MODE, true>(ctx, st, g, io, cd, nz, stream);
@@ -1515,6 +1625,7 @@ static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom&
         }
     }
     if (b <= 32) {
+        if (ctx->m == 4 && g.aligned4 && io.quad && MODE != M_SCATTER) return launch_stream_t<1, 4, MODE, false, true>(ctx, st, g, io, cd, nz, stream);
         if (ctx->m <= 4) return launch_stream_t<1, 4, MODE, false>(ctx, st, g, io, cd, nz, stream);
         if (ctx->m <= 6) return launch_stream_t<1, 6, MODE, false>(ctx, st, g, io, cd, nz, stream);
         return launch_stream_t<1, 16, MODE, false>(ctx, st, g, io, cd, nz, stream);

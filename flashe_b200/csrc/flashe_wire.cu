@@ -133,35 +133,68 @@ k_wire_unpack(const uint8_t* __restrict__ in, uint64_t count, uint32_t bits, uin
 #define WP_THREADS 256
 #define WP_WORDS (WP_THREADS * 4)                 // stream words (32 bit) per pack tile
 #define WP_MAX_FIELDS (WP_WORDS * 32 / 8 + 2)     // bits >= 8
+#define WP_BUF (WP_MAX_FIELDS + 6)                // + alignment shift of the staged fields
 
-// pack: tile t = stream words [t*WP_WORDS, (t+1)*WP_WORDS); only whole 16-byte chunks (nvec of them)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct PackTile { uint64_t f_lo; uint32_t nf, rel0p, pre; };
+
+// pack: tile t = stream words [t*WP_WORDS, (t+1)*WP_WORDS); only whole 16-byte chunks (nvec of them).
+// The fields of tile t+gridDim.x travel global -> shared with cp.async while tile t is converted
+// (two buffers), so a CTA always has a whole tile of loads in flight.
 __global__ void __launch_bounds__(WP_THREADS)
 k_wire_pack32(const uint32_t* __restrict__ words, uint64_t count, uint32_t bits, uint32_t pad, uint64_t nvec,
               uint4* __restrict__ out) {
-    __shared__ uint32_t sf[WP_MAX_FIELDS];
+    __shared__ __align__(16) uint32_t sf[2][WP_BUF];
     const uint32_t fm = bits >= 32u ? 0xffffffffu : ((1u << bits) - 1u);
     const uint64_t ntiles = (nvec + WP_THREADS - 1) / WP_THREADS;
-    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+
+    auto geom = [&](uint64_t t) {
+        PackTile g;
         const uint64_t bit0 = t * (uint64_t)(WP_WORDS * 32);                 // stream bit of the tile's first word
-        const uint64_t f_lo = bit0 > pad ? (bit0 - pad) / bits : 0;         // first field that reaches into the tile
-        uint64_t f_hi = (bit0 + (uint64_t)(WP_WORDS * 32) - 1 - pad) / bits;   // pad < 8 <= tile bits
+        g.f_lo = bit0 > pad ? (bit0 - pad) / bits : 0;                       // first field that reaches into the tile
+        uint64_t f_hi = (bit0 + (uint64_t)(WP_WORDS * 32) - 1 - pad) / bits; // pad < 8 <= tile bits
         if (f_hi >= count) f_hi = count - 1;
-        const uint32_t nf = (uint32_t)(f_hi - f_lo + 1);
-        // rel0 = stream position of field f_lo relative to the tile, in (-bits, 32); kept as rel0 + 32 > 0
-        const uint32_t rel0p = (uint32_t)((int64_t)(pad + f_lo * bits) - (int64_t)bit0 + 32);
-        __syncthreads();                                                    // previous tile's readers are done
-        // staged loads: 16 bytes per thread where the source is aligned, element-wise at the edges
-        const uint32_t* src = words + f_lo;
-        const uint32_t head = (uint32_t)((4u - ((uintptr_t)src >> 2)) & 3u);
-        for (uint32_t i = threadIdx.x; i < head && i < nf; i += WP_THREADS) sf[i] = src[i] & fm;
-        const uint32_t nq = nf > head ? (nf - head) >> 2 : 0;
-        for (uint32_t q = threadIdx.x; q < nq; q += WP_THREADS) {
-            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src + head) + q);
-            const uint32_t i = head + 4u * q;
-            sf[i] = v.x & fm; sf[i + 1] = v.y & fm; sf[i + 2] = v.z & fm; sf[i + 3] = v.w & fm;
+        g.nf = (uint32_t)(f_hi - g.f_lo + 1);
+        // stream position of field f_lo relative to the tile, in (-bits, 32); kept as rel0 + 32 > 0
+        g.rel0p = (uint32_t)((int64_t)(pad + g.f_lo * bits) - (int64_t)bit0 + 32);
+        // field i is staged at index pre + i so that the 16-byte aligned part of the source lands 16-byte aligned
+        const uint32_t head = (uint32_t)((4u - ((uintptr_t)(words + g.f_lo) >> 2)) & 3u);
+        g.pre = (4u - head) & 3u;
+        return g;
+    };
+    auto issue = [&](const PackTile& g, int buf) {
+        const uint32_t* src = words + g.f_lo;
+        const uint32_t base = smem_u32(&sf[buf][g.pre]);
+        const uint32_t head = (4u - g.pre) & 3u;
+        const uint32_t nq = g.nf > head ? (g.nf - head) >> 2 : 0;
+        for (uint32_t q = threadIdx.x; q < nq; q += WP_THREADS) cp_async16(base + 4u * (head + 4u * q), src + head + 4u * q);
+        const uint32_t rest = g.nf - 4u * nq;                                // head fields + tail fields
+        for (uint32_t e = threadIdx.x; e < rest; e += WP_THREADS) {
+            const uint32_t i = e < head && e < g.nf ? e : 4u * nq + e;       // (nf <= head: all fields are "head")
+            if (i < g.nf) cp_async4(base + 4u * i, src + i);
         }
-        for (uint32_t i = head + 4u * nq + threadIdx.x; i < nf; i += WP_THREADS) sf[i] = src[i] & fm;
-        __syncthreads();
+        cp_async_commit();
+    };
+
+    uint64_t t = blockIdx.x;
+    if (t >= ntiles) return;
+    PackTile cur = geom(t), nxt = cur;
+    issue(cur, 0);
+    for (int buf = 0; t < ntiles; t += gridDim.x, buf ^= 1, cur = nxt) {
+        const bool more = t + gridDim.x < ntiles;
+        if (more) { nxt = geom(t + gridDim.x); issue(nxt, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();                                                    // tile t's fields are visible
+        const uint32_t* f = &sf[buf][cur.pre];
+        const uint32_t nf = cur.nf, rel0p = cur.rel0p;
         const uint64_t vec = t * WP_THREADS + threadIdx.x;
         if (vec < nvec) {
             uint32_t w[4];
@@ -176,57 +209,78 @@ k_wire_pack32(const uint32_t* __restrict__ words, uint64_t count, uint32_t bits,
                     if (pos >= wbit + 32u) break;
                     // 64-bit window = stream bits [wbit - 32, wbit + 32); the field's top bit sits at pos - (wbit - 32)
                     const int sh = 64 - (int)bits - (int)(pos + 32u - wbit);
-                    acc |= sh >= 0 ? ((uint64_t)sf[i] << sh) : ((uint64_t)sf[i] >> (-sh));
+                    const uint64_t v = f[i] & fm;
+                    acc |= sh >= 0 ? (v << sh) : (v >> (-sh));
                 }
                 if (i > 0u && rel0p + i * bits > wbit + 32u) --i;            // the last field runs on into the next word
                 w[k] = __byte_perm((uint32_t)acc, 0, 0x0123);                // first stream byte first
             }
             __stcs(out + vec, make_uint4(w[0], w[1], w[2], w[3]));
         }
+        __syncthreads();                                                    // buffer `buf` may be refilled next round
     }
 }
 
-// unpack: tile = WP_WORDS consecutive elements, thread = 4 of them (one 16-byte store)
+// unpack: tile = WU_ELEMS consecutive elements, thread = 4 of them (one 16-byte store); the stream
+// words of the next tile are in flight (cp.async, two buffers) while this one is converted.
 #define WU_ELEMS (WP_THREADS * 4)
+#define WU_BUF (WU_ELEMS + 8)
 __global__ void __launch_bounds__(WP_THREADS)
 k_wire_unpack32(const uint8_t* __restrict__ in, uint64_t count, uint32_t bits, uint32_t pad, uint64_t nbytes,
                 uint32_t* __restrict__ words) {
-    __shared__ uint32_t sw[WU_ELEMS + 8];
+    __shared__ __align__(16) uint32_t sw[2][WU_BUF];
     const uint32_t fm = bits >= 32u ? 0xffffffffu : ((1u << bits) - 1u);
     const uint64_t ntiles = (count + WU_ELEMS - 1) / WU_ELEMS;
     const uint64_t nwords_in = nbytes >> 2;                                  // whole stream words
-    const bool in_al4 = ((uintptr_t)in & 3u) == 0;
-    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+
+    // stream words [w_lo, w_lo + nw) of tile t -> sw[buf][0..nw), as stored (big-endian); nw <= WU_ELEMS + 2
+    auto issue = [&](uint64_t t, int buf) {
         const uint64_t j0 = t * WU_ELEMS;
         const uint32_t ne = (uint32_t)(count - j0 < WU_ELEMS ? count - j0 : WU_ELEMS);
-        const uint64_t b_lo = pad + j0 * bits, b_hi = b_lo + (uint64_t)ne * bits;   // stream bits [b_lo, b_hi)
-        const uint64_t w_lo = b_lo >> 5, w_hi = (b_hi + 31) >> 5;                    // stream words [w_lo, w_hi)
-        const uint32_t nw = (uint32_t)(w_hi - w_lo);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i <= nw; i += WP_THREADS) {           // one extra (zero) word for the window
+        const uint64_t b_lo = pad + j0 * bits, b_hi = b_lo + (uint64_t)ne * bits;
+        const uint64_t w_lo = b_lo >> 5;
+        const uint32_t nw = (uint32_t)(((b_hi + 31) >> 5) - w_lo);
+        const uint32_t base = smem_u32(&sw[buf][0]);
+        for (uint32_t i = threadIdx.x; i < nw; i += WP_THREADS) {
             const uint64_t w = w_lo + i;
-            uint32_t v = 0;
-            if (i < nw) {
-                if (w < nwords_in && in_al4) v = __byte_perm(__ldcs(reinterpret_cast<const uint32_t*>(in) + w), 0, 0x0123);
-                else for (uint32_t b = 0; b < 4; ++b) { const uint64_t a = 4 * w + b; v = (v << 8) | (a < nbytes ? in[a] : 0u); }
+            if (w < nwords_in) {
+                cp_async4(base + 4u * i, in + 4 * w);
+            } else {                                                         // the stream's last, partial word
+                uint32_t v = 0;
+                for (uint32_t b = 0; b < 4; ++b) { const uint64_t a = 4 * w + b; v |= (a < nbytes ? (uint32_t)in[a] : 0u) << (8 * b); }
+                sw[buf][i] = v;
             }
-            sw[i] = v;
         }
+        cp_async_commit();
+    };
+
+    uint64_t t = blockIdx.x;
+    if (t >= ntiles) return;
+    issue(t, 0);
+    for (int buf = 0; t < ntiles; t += gridDim.x, buf ^= 1) {
+        if (t + gridDim.x < ntiles) { issue(t + gridDim.x, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncthreads();
+        const uint64_t j0 = t * WU_ELEMS;
+        const uint32_t ne = (uint32_t)(count - j0 < WU_ELEMS ? count - j0 : WU_ELEMS);
+        const uint64_t b_lo = pad + j0 * bits;
+        const uint32_t nw = (uint32_t)(((b_lo + (uint64_t)ne * bits + 31) >> 5) - (b_lo >> 5));
         const uint32_t e0 = 4u * threadIdx.x;
         if (e0 < ne) {
             uint32_t r[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t o = (uint32_t)(b_lo - (w_lo << 5)) + (e0 + k) * bits;
+                const uint32_t o = (uint32_t)(b_lo & 31u) + (e0 + k) * bits;
                 const uint32_t wi = o >> 5;
-                const uint64_t win = ((uint64_t)sw[wi < nw ? wi : nw] << 32) | sw[wi + 1 <= nw ? wi + 1 : nw];
+                const uint32_t hi = wi < nw ? __byte_perm(sw[buf][wi], 0, 0x0123) : 0u;
+                const uint32_t lo = wi + 1u < nw ? __byte_perm(sw[buf][wi + 1u], 0, 0x0123) : 0u;
+                const uint64_t win = ((uint64_t)hi << 32) | lo;
                 r[k] = (uint32_t)(win >> (64u - bits - (o & 31u))) & fm;
             }
             uint32_t* dst = words + j0 + e0;
             if (e0 + 4u <= ne && ((uintptr_t)dst & 15u) == 0) __stcs(reinterpret_cast<uint4*>(dst), make_uint4(r[0], r[1], r[2], r[3]));
             else for (uint32_t k = 0; k < 4u && e0 + k < ne; ++k) dst[k] = r[k];
         }
+        __syncthreads();
     }
 }
 
@@ -248,6 +302,8 @@ k_wire_unpack32(const uint8_t* __restrict__ in, uint64_t count, uint32_t bits, u
 // counts, one-block scan, ordered write.  x is read 5 times (L2-resident for layers up to ~30 M).
 // =================================================================================================
 struct TopkState { uint32_t prefix; uint32_t k_rem; uint32_t c_eq; uint32_t pad; };
+// one layer: elements [begin, begin+n) of x, k to keep, first tile number, first output slot
+struct TopkSeg { uint64_t begin; uint64_t tile0; uint64_t out_off; uint32_t n; uint32_t k; };
 
 #define TK_THREADS 256
 #define TK_PER 16
@@ -256,32 +312,72 @@ struct TopkState { uint32_t prefix; uint32_t k_rem; uint32_t c_eq; uint32_t pad;
 
 __device__ __forceinline__ uint32_t key_of(float x) { return __float_as_uint(x) & 0x7fffffffu; }
 
-// pass 0: shift 20 / 11 bits; pass 1: shift 9 / 11 bits; pass 2: shift 0 / 9 bits
+// All layers are processed by the same launches: the tiles (TK_TILE elements, never across a layer
+// boundary) of every layer are numbered consecutively and a tile finds its layer by binary search.
+__device__ __forceinline__ int topk_seg_of_tile(const TopkSeg* __restrict__ segs, int nseg, uint64_t tile) {
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (segs[mid].tile0 <= tile) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+__global__ void k_topk_init(const TopkSeg* __restrict__ segs, int nseg, TopkState* __restrict__ st) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nseg) { TopkState v; v.prefix = 0u; v.k_rem = segs[s].k; v.c_eq = 0u; v.pad = 0u; st[s] = v; }
+}
+
+// pass 0: shift 20 / 11 bits; pass 1: shift 9 / 11 bits; pass 2: shift 0 / 9 bits.
+// A block owns a contiguous run of tiles; its shared histogram is merged into the layer's global one
+// whenever the run crosses into the next layer (and at the end).
 __global__ void __launch_bounds__(TK_THREADS)
-k_topk_hist(const float* __restrict__ x, uint64_t n, const TopkState* __restrict__ st, uint32_t shift, uint32_t nbits,
-            uint32_t* __restrict__ hist) {
+k_topk_hist(const float* __restrict__ x, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles, uint64_t tiles_per_block,
+            const TopkState* __restrict__ st, uint32_t shift, uint32_t nbits, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[TK_BINS];
+    const uint64_t t_begin = (uint64_t)blockIdx.x * tiles_per_block;
+    uint64_t t_end = t_begin + tiles_per_block;
+    if (t_end > ntiles) t_end = ntiles;
+    if (t_begin >= t_end) return;
     for (uint32_t i = threadIdx.x; i < TK_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const uint32_t hi_shift = shift + nbits;               // bits above the digit must equal the prefix
-    const uint32_t prefix = st->prefix;
     const uint32_t dmask = (1u << nbits) - 1u;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t key = key_of(x[i]);
-        if (hi_shift >= 31u || (key >> hi_shift) == (prefix >> hi_shift)) atomicAdd(&sh[(key >> shift) & dmask], 1u);
+    int s = topk_seg_of_tile(segs, nseg, t_begin);
+    for (uint64_t tile = t_begin; tile < t_end; ++tile) {
+        while (s + 1 < nseg && segs[s + 1].tile0 <= tile) {           // the run enters the next (non-empty) layer
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < TK_BINS; i += blockDim.x) {
+                const uint32_t c = sh[i];
+                if (c) { atomicAdd(&hist[(size_t)s * TK_BINS + i], c); sh[i] = 0; }
+            }
+            __syncthreads();
+            ++s;
+        }
+        const TopkSeg sg = segs[s];
+        const uint32_t prefix = st[s].prefix;
+        const uint64_t base = (tile - sg.tile0) * TK_TILE;
+        const float* xs = x + sg.begin;
+#pragma unroll 4
+        for (int r = 0; r < TK_PER; ++r) {
+            const uint64_t i = base + (uint64_t)r * TK_THREADS + threadIdx.x;
+            if (i < sg.n) {
+                const uint32_t key = key_of(xs[i]);
+                if (hi_shift >= 31u || (key >> hi_shift) == (prefix >> hi_shift)) atomicAdd(&sh[(key >> shift) & dmask], 1u);
+            }
+        }
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < TK_BINS; i += blockDim.x) {
         const uint32_t c = sh[i];
-        if (c) atomicAdd(&hist[i], c);
+        if (c) atomicAdd(&hist[(size_t)s * TK_BINS + i], c);
     }
 }
 
-// One block of 1024 threads: suffix sums of the histogram from the top bin; the bucket holding the
-// k_rem-th largest key extends the prefix.  Clears the histogram for the next pass.
+// One block of 1024 threads per layer: suffix sums of the histogram from the top bin; the bucket holding
+// the k_rem-th largest key extends the prefix.  Clears the histogram for the next pass.
 __global__ void __launch_bounds__(1024)
-k_topk_pick(uint32_t* __restrict__ hist, TopkState* __restrict__ st, uint32_t shift) {
+k_topk_pick(uint32_t* __restrict__ hist_all, TopkState* __restrict__ st_all, uint32_t shift) {
     __shared__ uint32_t warp_tot[32];
+    uint32_t* hist = hist_all + (size_t)blockIdx.x * TK_BINS;
+    TopkState* st = st_all + blockIdx.x;
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     // thread t owns bins hi = TK_BINS-1-2t and hi-1 (descending order)
     const uint32_t b0 = TK_BINS - 1 - 2 * t, b1 = b0 - 1;
@@ -310,35 +406,42 @@ k_topk_pick(uint32_t* __restrict__ hist, TopkState* __restrict__ st, uint32_t sh
 
 // per-tile counts of (key > T, key == T)
 __global__ void __launch_bounds__(TK_THREADS)
-k_topk_count(const float* __restrict__ x, uint64_t n, const TopkState* __restrict__ st, uint2* __restrict__ tile_counts) {
-    __shared__ uint32_t sg[TK_THREADS / 32], se[TK_THREADS / 32];
-    const uint32_t T = st->prefix;
-    const uint64_t ntiles = (n + TK_TILE - 1) / TK_TILE;
+k_topk_count(const float* __restrict__ x, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles,
+             const TopkState* __restrict__ st, uint2* __restrict__ tile_counts) {
+    __shared__ uint32_t sg_[TK_THREADS / 32], se_[TK_THREADS / 32];
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t base = tile * TK_TILE;
+        const int s = topk_seg_of_tile(segs, nseg, tile);
+        const TopkSeg sg = segs[s];
+        const uint32_t T = st[s].prefix;
+        const uint64_t base = (tile - sg.tile0) * TK_TILE;
+        const float* xs = x + sg.begin;
         uint32_t g = 0, e = 0;
 #pragma unroll 4
         for (int r = 0; r < TK_PER; ++r) {
             const uint64_t i = base + (uint64_t)r * TK_THREADS + threadIdx.x;   // counts do not need index order
-            if (i < n) { const uint32_t key = key_of(x[i]); g += key > T; e += key == T; }
+            if (i < sg.n) { const uint32_t key = key_of(xs[i]); g += key > T; e += key == T; }
         }
         for (int d = 16; d > 0; d >>= 1) { g += __shfl_down_sync(0xffffffffu, g, d); e += __shfl_down_sync(0xffffffffu, e, d); }
-        if ((threadIdx.x & 31u) == 0) { sg[threadIdx.x >> 5] = g; se[threadIdx.x >> 5] = e; }
+        if ((threadIdx.x & 31u) == 0) { sg_[threadIdx.x >> 5] = g; se_[threadIdx.x >> 5] = e; }
         __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t G = 0, E = 0;
-            for (int w = 0; w < TK_THREADS / 32; ++w) { G += sg[w]; E += se[w]; }
+            for (int w = 0; w < TK_THREADS / 32; ++w) { G += sg_[w]; E += se_[w]; }
             tile_counts[tile] = make_uint2(G, E);
         }
         __syncthreads();
     }
 }
 
-// exclusive scan of the tile counts in place (one block; ntiles is small: n / 4096)
+// exclusive scan of each layer's tile counts in place (one block per layer)
 __global__ void __launch_bounds__(1024)
-k_topk_scan(uint2* __restrict__ tile_counts, uint64_t ntiles) {
+k_topk_scan(uint2* __restrict__ tile_counts_all, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles_all) {
     __shared__ uint32_t wg[32], we[32];
     __shared__ uint32_t carry_g, carry_e;
+    const int s = blockIdx.x;
+    const uint64_t t0 = segs[s].tile0, t1 = s + 1 < nseg ? segs[s + 1].tile0 : ntiles_all;
+    uint2* tile_counts = tile_counts_all + t0;
+    const uint64_t ntiles = t1 - t0;
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     if (t == 0) { carry_g = 0; carry_e = 0; }
     __syncthreads();
@@ -372,28 +475,34 @@ k_topk_scan(uint2* __restrict__ tile_counts, uint64_t ntiles) {
 
 // Ordered write.  Thread t of a tile owns the TK_PER consecutive elements [t*TK_PER, (t+1)*TK_PER) so
 // that positions follow the index order.  An element is selected when key > T, or key == T and at least
-// c_eq - k_rem tied elements precede it.  Output slot = (#selected before it).
+// c_eq - k_rem tied elements precede it.  Output slot = (#selected before it in its layer) + out_off.
 __global__ void __launch_bounds__(TK_THREADS)
-k_topk_write(const float* __restrict__ x, const float* __restrict__ res_in, uint64_t n, uint64_t seg_base,
-             const TopkState* __restrict__ st, const uint2* __restrict__ tile_prefix, float* __restrict__ values,
-             int64_t* __restrict__ index, float* __restrict__ res_out) {
+k_topk_write(const float* __restrict__ x, const float* __restrict__ res_in, const TopkSeg* __restrict__ segs, int nseg,
+             uint64_t ntiles, const TopkState* __restrict__ st_all, const uint2* __restrict__ tile_prefix,
+             float* __restrict__ values_all, int64_t* __restrict__ index_all, float* __restrict__ res_out) {
     __shared__ uint32_t wg[TK_THREADS / 32], we[TK_THREADS / 32];
-    const uint32_t T = st->prefix, skip_eq = st->c_eq - st->k_rem;   // ties with rank < skip_eq are not taken
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint64_t ntiles = (n + TK_TILE - 1) / TK_TILE;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t i0 = tile * TK_TILE + (uint64_t)threadIdx.x * TK_PER;
+        const int s = topk_seg_of_tile(segs, nseg, tile);
+        const TopkSeg sgm = segs[s];
+        const TopkState st = st_all[s];
+        const uint32_t T = st.prefix, skip_eq = st.c_eq - st.k_rem;   // ties with rank < skip_eq are not taken
+        const uint64_t n = sgm.n;
+        const float* xs = x + sgm.begin;
+        float* values = values_all + sgm.out_off;
+        int64_t* index = index_all + sgm.out_off;
+        const uint64_t i0 = (tile - sgm.tile0) * TK_TILE + (uint64_t)threadIdx.x * TK_PER;
         float xv[TK_PER];
         uint32_t g = 0, e = 0;
-        if (i0 + TK_PER <= n && ((reinterpret_cast<uintptr_t>(x + i0) & 15u) == 0)) {
+        if (i0 + TK_PER <= n && ((reinterpret_cast<uintptr_t>(xs + i0) & 15u) == 0)) {
 #pragma unroll
             for (int r = 0; r < TK_PER; r += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(x + i0 + r);
+                const float4 v = *reinterpret_cast<const float4*>(xs + i0 + r);
                 xv[r] = v.x; xv[r + 1] = v.y; xv[r + 2] = v.z; xv[r + 3] = v.w;
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < TK_PER; ++r) xv[r] = (i0 + r < n) ? x[i0 + r] : 0.0f;
+            for (int r = 0; r < TK_PER; ++r) xv[r] = (i0 + r < n) ? xs[i0 + r] : 0.0f;
         }
 #pragma unroll
         for (int r = 0; r < TK_PER; ++r)
@@ -418,14 +527,14 @@ k_topk_write(const float* __restrict__ x, const float* __restrict__ res_in, uint
                 const uint32_t key = key_of(xv[r]);
                 const bool is_eq = key == T;
                 const bool sel = key > T || (is_eq && eq_before >= skip_eq);
-                const float f = res_in ? __fadd_rn(xv[r], res_in[i]) : xv[r];
+                const float f = res_in ? __fadd_rn(xv[r], res_in[sgm.begin + i]) : xv[r];
                 if (sel) {
                     const uint32_t taken_eq = eq_before > skip_eq ? eq_before - skip_eq : 0u;   // selected ties before i
                     const uint64_t pos = (uint64_t)gt_before + taken_eq;
                     values[pos] = f;
-                    index[pos] = (int64_t)(seg_base + i);
+                    index[pos] = (int64_t)(sgm.begin + i);
                 }
-                if (res_out) res_out[i] = sel ? 0.0f : f;
+                if (res_out) res_out[sgm.begin + i] = sel ? 0.0f : f;
                 gt_before += key > T; eq_before += is_eq;
             }
         }
@@ -570,7 +679,7 @@ int flashe_wire_unpack(flashe_ctx* ctx, const uint8_t* in, uint64_t count, int b
     if (count == 0) return FLASHE_OK;
     if (!in || !words_out) return flashe_fail(FLASHE_EINVAL, "NULL buffer");
     uint64_t nbytes; rc = flashe_wire_nbytes(bits, count, &nbytes); if (rc) return rc;
-    if (word_bytes == 4 && ((uintptr_t)words_out & 3u) == 0) {
+    if (word_bytes == 4 && ((uintptr_t)words_out & 3u) == 0 && ((uintptr_t)in & 3u) == 0) {
         const uint32_t pad = (uint32_t)(8 * nbytes - count * (uint64_t)bits);
         const int grid = grid_cap(info.num_sms, ceil_div_u64(count, WU_ELEMS), 8);
         k_wire_unpack32<<<grid, WP_THREADS, 0, cs>>>(in, count, (uint32_t)bits, pad, nbytes, reinterpret_cast<uint32_t*>(words_out));
@@ -604,44 +713,63 @@ int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_
     }
     if (total == 0) return FLASHE_OK;
     if (!x || !values_out || !index_out) return flashe_fail(FLASHE_EINVAL, "NULL buffer");
-    // workspace: state | histogram | tile counts
-    const uint64_t max_tiles = ceil_div_u64(max_n, TK_TILE);
-    const size_t ws_bytes = 256 + sizeof(uint32_t) * TK_BINS + sizeof(uint2) * (size_t)max_tiles;
+    // Layers are processed in groups of at most TK_GROUP by the same nine launches (the per-layer
+    // histograms of a group are 8 KB each).  Empty layers are dropped from the table.
+    const int TK_GROUP = 4096;
+    std::vector<TopkSeg> segs;
+    segs.reserve((size_t)(nseg < TK_GROUP ? nseg : TK_GROUP));
     uint8_t* ws = nullptr;
-    FLASHE_CUDA_TRY(cudaMallocAsync((void**)&ws, ws_bytes, cs));
-    TopkState* st = reinterpret_cast<TopkState*>(ws);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(ws + 256);
-    uint2* tiles = reinterpret_cast<uint2*>(ws + 256 + sizeof(uint32_t) * TK_BINS);
-    cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * TK_BINS, cs);
-    uint64_t begin = 0, out_off = 0;
+    cudaError_t e = cudaSuccess;
     int launches = 0;
-    for (int s = 0; e == cudaSuccess && s < nseg; ++s) {
-        const uint64_t n = seg_end[s] - begin;
-        if (n == 0) continue;
-        const TopkState init = {0u, (uint32_t)k[s], 0u, 0u};
-        e = cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, cs);   // pageable: staged before return
-        if (e != cudaSuccess) break;
-        const float* xs = x + begin;
-        const int gh = grid_cap(info.num_sms, ceil_div_u64(n, TK_THREADS * 8), 8);
-        const uint32_t shifts[3] = {20u, 9u, 0u}, nbits[3] = {11u, 11u, 9u};
-        for (int p = 0; p < 3; ++p) {
-            k_topk_hist<<<gh, TK_THREADS, 0, cs>>>(xs, n, st, shifts[p], nbits[p], hist);
-            k_topk_pick<<<1, 1024, 0, cs>>>(hist, st, shifts[p]);
+    uint64_t begin = 0, out_off = 0;
+    int s = 0;
+    while (e == cudaSuccess && s < nseg) {
+        segs.clear();
+        uint64_t ntiles = 0;
+        for (; s < nseg && (int)segs.size() < TK_GROUP; ++s) {
+            const uint64_t n = seg_end[s] - begin;
+            if (n) {
+                TopkSeg g; g.begin = begin; g.tile0 = ntiles; g.out_off = out_off; g.n = (uint32_t)n; g.k = (uint32_t)k[s];
+                segs.push_back(g);
+                ntiles += ceil_div_u64(n, TK_TILE);
+            }
+            begin = seg_end[s];
+            out_off += k[s];
         }
-        const uint64_t ntiles = ceil_div_u64(n, TK_TILE);
-        const int gt = grid_cap(info.num_sms, ntiles, 8);
-        k_topk_count<<<gt, TK_THREADS, 0, cs>>>(xs, n, st, tiles);
-        k_topk_scan<<<1, 1024, 0, cs>>>(tiles, ntiles);
-        k_topk_write<<<gt, TK_THREADS, 0, cs>>>(xs, residual_in ? residual_in + begin : nullptr, n, begin, st, tiles,
-                                                values_out + out_off, index_out + out_off,
-                                                residual_out ? residual_out + begin : nullptr);
-        launches += 9;
-        e = cudaGetLastError();
-        begin = seg_end[s];
-        out_off += k[s];
+        const int ng = (int)segs.size();
+        if (ng == 0) continue;
+        // workspace: layer table | states | histograms | tile counts
+        const size_t seg_bytes = (sizeof(TopkSeg) * (size_t)ng + 255) & ~(size_t)255;
+        const size_t st_bytes = (sizeof(TopkState) * (size_t)ng + 255) & ~(size_t)255;
+        const size_t hist_bytes = sizeof(uint32_t) * TK_BINS * (size_t)ng;
+        e = cudaMallocAsync((void**)&ws, seg_bytes + st_bytes + hist_bytes + sizeof(uint2) * (size_t)ntiles, cs);
+        if (e != cudaSuccess) break;
+        TopkSeg* dseg = reinterpret_cast<TopkSeg*>(ws);
+        TopkState* st = reinterpret_cast<TopkState*>(ws + seg_bytes);
+        uint32_t* hist = reinterpret_cast<uint32_t*>(ws + seg_bytes + st_bytes);
+        uint2* tiles = reinterpret_cast<uint2*>(ws + seg_bytes + st_bytes + hist_bytes);
+        e = cudaMemcpyAsync(dseg, segs.data(), sizeof(TopkSeg) * (size_t)ng, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cs);          // segs (pageable) is reused by the next group
+        if (e == cudaSuccess) e = cudaMemsetAsync(hist, 0, hist_bytes, cs);
+        if (e == cudaSuccess) {
+            k_topk_init<<<(ng + 255) / 256, 256, 0, cs>>>(dseg, ng, st);
+            const int gh = grid_cap(info.num_sms, ntiles, 8);
+            const uint64_t tpb = ceil_div_u64(ntiles, (uint64_t)gh);
+            const uint32_t shifts[3] = {20u, 9u, 0u}, nbits[3] = {11u, 11u, 9u};
+            for (int p = 0; p < 3; ++p) {
+                k_topk_hist<<<gh, TK_THREADS, 0, cs>>>(x, dseg, ng, ntiles, tpb, st, shifts[p], nbits[p], hist);
+                k_topk_pick<<<ng, 1024, 0, cs>>>(hist, st, shifts[p]);
+            }
+            k_topk_count<<<gh, TK_THREADS, 0, cs>>>(x, dseg, ng, ntiles, st, tiles);
+            k_topk_scan<<<ng, 1024, 0, cs>>>(tiles, dseg, ng, ntiles);
+            k_topk_write<<<gh, TK_THREADS, 0, cs>>>(x, residual_in, dseg, ng, ntiles, st, tiles, values_out, index_out, residual_out);
+            launches += 10;
+            e = cudaGetLastError();
+        }
+        cudaFreeAsync(ws, cs);
+        ws = nullptr;
     }
     flashe_count_launches(launches);
-    cudaFreeAsync(ws, cs);
     if (e != cudaSuccess) return flashe_fail(FLASHE_ECUDA, std::string("flashe_topk_sparsify: ") + cudaGetErrorString(e));
     return FLASHE_OK;
 }

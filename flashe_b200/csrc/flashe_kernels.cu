@@ -724,7 +724,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     constexpr bool HAS_IN = (MODE == M_APPLY || MODE == M_ENCODE || MODE == M_DECODE);
     constexpr int PF = MMAX + 1;                 // pair iterations per item: ceil((64m + 2) / 64)
     constexpr uint32_t WB = WORDS * 4u;
-    constexpr bool QUAD_OK = (WORDS == 1 && MODE != M_SCATTER && MMAX >= 4);
+    constexpr bool QUAD_OK = (WORDS == 1 && MODE != M_SCATTER && MMAX == 4);   // 4-byte words and m == 4
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t y = 0x00010000u | (lane << 2);
     const uint32_t sbase = smem_window_base();
@@ -761,7 +761,146 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
         uint32_t nsub;
         Item it = decode_unit(g, g.S_lo + S, nsub);
       uint32_t cached_win = 0xffffffffu;                             // counter window the cached round-2 terms belong to
+      const uint32_t n_iter = SHARE ? c_count + 1 : c_count;
+      // ---- lane-local items ------------------------------------------------------------------------
+      // Items [wf_lo, wf_hi) of the unit's chunk are FULL (64 blocks of m = 4 elements), lie inside the
+      // shard and have 32-bit counters: a lane's AES block IS four consecutive elements, so the lane
+      // loads / stores them itself (a warp covers 512 contiguous bytes per access), nothing goes
+      // through the slab, and all per-item geometry is a handful of additions.  The bounds are
+      // computed once per unit.
+      uint64_t wf_lo = 1, wf_hi = 0;
+      if (QUAD_OK && io.quad) {
+          const uint64_t shift = 4ull * it.off;                     // e0(w) = cb - shift + 256 w
+          const uint64_t full_end = it.cb + (it.clen & ~3ull);      // end of the chunk's last whole block
+          const uint64_t hi_e = (full_end < g.end ? full_end : g.end) + shift;
+          const uint64_t lo_e = (g.begin > it.cb ? g.begin : it.cb) + shift;   // w = 0 is lane-local only when off == 0
+          wf_lo = lo_e > it.cb ? (lo_e - it.cb + 255ull) >> 8 : 0;
+          wf_hi = hi_e > it.cb ? (hi_e - it.cb) >> 8 : 0;            // items w with 256 (w+1) <= hi_e - cb
+          const uint64_t c0 = it.cb - it.off;                       // counter of item 0's (virtual) first block
+          const uint64_t w32 = c0 < (1ull << 32) ? ((1ull << 32) - c0) >> 6 : 0;   // 64 (w+1) <= 2^32 - c0
+          if (wf_hi > w32) wf_hi = w32;
+      }
+      auto fast_item = [&](uint64_t w) {
+        if constexpr (QUAD_OK) {
+          const uint64_t e0 = it.cb - 4ull * it.off + (w << 8);     // first global element of the item
+          const uint32_t ctr0 = (uint32_t)(it.cb - it.off) + ((uint32_t)w << 6);   // jzf_flashe.py:34 "(i + begin)"
+          const uint64_t o0 = e0 - g.begin;
+          const uint32_t qr = ALIGNED ? 0u : ((uint32_t)o0 & 3u);    // misalignment of the chunk in the buffers
+          const uint64_t qoff = o0 + 4u * lane;                     // block A's elements; block B: +128
+          const uint64_t j0 = e0 + 4u * lane;
+          const uint32_t ctrA = ctr0 + lane, ctrB = ctrA + 32u;
+          const uint32_t win = ctr0 >> 8;                           // same for every counter of the item
+          const bool stale = !cache_ok || win != cached_win;
+          const uint32_t mk32 = Word<1>::mask(g.b);
+          const bool one_seg = cd.nseg == 1;
+          uint32_t prev[NB][4];
+          for (uint32_t cc = 0; cc < n_iter; ++cc) {
+              const uint32_t c = SHARE ? (cc ? c_first + cc - 1 : 0) : c_first + cc;
+              const bool emit = !SHARE || cc > 0;
+              uint32_t r[NB][4];
+              if (HAS_IN && emit) {                                  // inputs first: their latency hides under the AES rounds
+                  const uint32_t* in = reinterpret_cast<const uint32_t*>(io.in) + (uint64_t)c * io.in_stride + qoff;
+                  ldg_quad(in, qr, r[0]);
+                  ldg_quad(in + 128, qr, r[1]);
+              }
+              uint32_t acc[NB][4];
+#pragma unroll
+              for (int h = 0; h < NB; ++h)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) acc[h][k] = 0u;
+              uint32_t s_begin, s_count;
+              if (!st.batch) { s_begin = 0; s_count = st.n; }
+              else if (SHARE) { s_begin = cc; s_count = 1; }
+              else { s_begin = c; s_count = st.dbl ? 2u : 1u; }
+              for (uint32_t si = 0; si < s_count; ++si) {
+                  const uint32_t sidx = s_begin + si;
+                  const int sign = st.batch ? (si == 0 ? +1 : -1) : st.sign[sidx];
+                  // window terms of stream sidx: the warp's cache slot (broadcast read), or recomputed by
+                  // every lane (same inputs, same result) when the item opens a new counter window
+                  WinC wc;
+                  const uint32_t slot = wcache + sidx * 16u;
+                  if (stale) {
+                      wc = window_consts(ks, y, PRE_OF(sidx), ctr0);
+                      if (cache_ok) {
+                          if (lane == 0) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"(wc.c0), "r"(wc.c1), "r"(wc.c2), "r"(wc.c3) : "memory");
+                          __syncwarp();
+                      }
+                  } else {
+                      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wc.c0), "=r"(wc.c1), "=r"(wc.c2), "=r"(wc.c3) : "r"(slot) : "memory");
+                  }
+                  uint32_t oa[4], ob[4];
+                  aes256_x2w(ks, y, st.pre[sidx][0], wc, ctrA, ctrB, oa, ob);
+                  accumulate_slots<1, 4>(oa, g.b, 4u, sign, acc[0]);
+                  accumulate_slots<1, 4>(ob, g.b, 4u, sign, acc[1]);
+              }
+              if (SHARE) {                                           // acc = F(cc); mask of client cc-1 = prev - acc
+#pragma unroll
+                  for (int h = 0; h < NB; ++h)
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) {
+                          const uint32_t cur = acc[h][k];
+                          if (cc > 0) acc[h][k] = prev[h][k] - cur;
+                          prev[h][k] = cur;
+                      }
+                  if (!emit) continue;
+              }
+#pragma unroll
+              for (int h = 0; h < NB; ++h) {
+                  const uint64_t o = qoff + 128u * h;
+                  const uint64_t j = j0 + 128u * h;
+                  uint32_t mw[4];
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) mw[k] = acc[h][k] & mk32;
+                  if (MODE == M_MASKS) {
+                      stg_quad(reinterpret_cast<uint32_t*>(io.out) + o, qr, mw[0], mw[1], mw[2], mw[3]);
+                  } else if (MODE == M_APPLY) {
+                      uint32_t* out = reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o;
+                      stg_quad(out, qr, (r[h][0] + mw[0]) & mk32, (r[h][1] + mw[1]) & mk32, (r[h][2] + mw[2]) & mk32, (r[h][3] + mw[3]) & mk32);
+                  } else if (MODE == M_ENCODE) {
+                      double u[4];
+                      if (nz.u) {
+                          const double* up = nz.u + (uint64_t)c * nz.u_stride + o;
+#pragma unroll
+                          for (int k = 0; k < 4; ++k) u[k] = up[k];
+                      } else if (ALIGNED || (j & 1ull) == 0ull) {
+                          noise_pair(nz, nz.stream + c, j >> 1, u[0], u[1]);
+                          noise_pair(nz, nz.stream + c, (j >> 1) + 1, u[2], u[3]);
+                      } else {                      // odd chunk start: the four elements touch three pairs
+                          double lo, hi;
+                          noise_pair(nz, nz.stream + c, j >> 1, lo, u[0]);
+                          noise_pair(nz, nz.stream + c, (j >> 1) + 1, u[1], u[2]);
+                          noise_pair(nz, nz.stream + c, (j >> 1) + 2, u[3], hi);
+                      }
+                      uint32_t q[4];
+                      Seg sg = find_seg(cd, j);
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) {
+                          if (k && !one_seg && j + k >= sg.end) sg = find_seg(cd, j + k);
+                          q[k] = encode_one(__uint_as_float(r[h][k]), u[k], sg, cd.scale);
+                      }
+                      if (io.aux) stg_quad(reinterpret_cast<uint32_t*>(io.aux) + (uint64_t)c * io.out_stride + o, qr, q[0], q[1], q[2], q[3]);
+                      uint32_t* out = reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o;
+                      stg_quad(out, qr, (q[0] + mw[0]) & mk32, (q[1] + mw[1]) & mk32, (q[2] + mw[2]) & mk32, (q[3] + mw[3]) & mk32);
+                  } else if (MODE == M_DECODE) {
+                      uint32_t pw[4];
+                      double dv[4];
+                      Seg sg = find_seg(cd, j);
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) {
+                          pw[k] = (r[h][k] + mw[k]) & mk32;
+                          if (k && !one_seg && j + k >= sg.end) sg = find_seg(cd, j + k);
+                          dv[k] = decode_one((double)pw[k], sg.two_an, cd.den, sg.an);
+                      }
+                      if (io.aux) stg_quad(reinterpret_cast<uint32_t*>(io.aux) + o, qr, pw[0], pw[1], pw[2], pw[3]);
+                      stg_quad_f64(io.outf + o, qr, dv);
+                  }
+              }
+          }
+          cached_win = win;                                          // every stream of the unit now has this window cached
+        }
+      };
       for (uint32_t sub = 0; sub < nsub; ++sub, ++it.w) {
+        if (QUAD_OK && it.w >= wf_lo && it.w < wf_hi) { fast_item(it.w); continue; }
         const uint64_t blk0 = it.w ? it.w * ITEM_BLOCKS - it.off : 0;  // first block of the item
         const uint32_t nblk = it.w ? ITEM_BLOCKS : ITEM_BLOCKS - it.off;
         if (blk0 * m >= it.clen) break;                                // past the chunk's last item
@@ -774,7 +913,6 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
         const uint64_t ctr0 = it.cb + blk0;                            // jzf_flashe.py:34 "(i + begin)"
         const uint64_t ctrA = ctr0 + lane, ctrB = ctrA + 32;
         const bool fast = (((ctr0 + ITEM_BLOCKS - 1u) >> 32) == 0);  // hoisted round 1 needs word 2 == 0
-        const uint32_t win = (uint32_t)(ctr0 >> 8);                  // same for every counter of the item
         const uint32_t par = (uint32_t)(item_e0 & 1ull);
         const uint64_t base_e = item_e0 - par;                       // even; slab index = j - base_e
         const uint32_t npairs = (par + item_n + 1u) >> 1;
@@ -782,34 +920,12 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
         const uint32_t lo_i = g.begin > item_e0 ? (uint32_t)(g.begin - base_e) : par;
         const uint32_t hi_i = (item_e0 + item_n) > g.end ? (uint32_t)(g.end > base_e ? g.end - base_e : 0) : par + item_n;
         const int64_t off0 = (int64_t)(base_e - g.begin);            // offset of slab index 0 in the shard buffers
-        // Fast path (4-byte words, m = 4, full item inside the shard, 16-byte aligned): a lane's AES
-        // block IS four consecutive elements, so it loads / stores them itself with 128-bit accesses
-        // (a warp covers 512 contiguous bytes) and nothing goes through the slab.
-        const uint32_t qr = ALIGNED ? 0u : ((uint32_t)(item_e0 - g.begin) & 3u);   // misalignment of the chunk in the buffers
-        const bool quad = QUAD_OK && m == 4u && io.quad && item_n == NB * 128u && item_e0 >= g.begin &&
-                          item_e0 + item_n <= g.end && (!ALIGNED || ((item_e0 - g.begin) & 3ull) == 0ull);
-        const uint64_t qoff = (item_e0 - g.begin) + 4ull * lane;     // block A's elements; block B: +128
-
         // one AES pass: F(iter, prf) for this lane's two blocks, accumulated with sign
-        // The window terms of stream `sidx` live in the warp's cache slot `sidx` (shared memory, read by
-        // broadcast) and are recomputed by every lane (same inputs, same result) when the item enters a
-        // new counter window; called by all lanes: `fast` and `stale` are warp-uniform.
-        const bool stale = !cache_ok || win != cached_win;
+        // (edge items and layouts without a lane-local path: the window terms are recomputed per call)
         auto stream_into = [&](uint32_t sidx, int sign, word_t (&acc)[NB][MMAX]) {
             uint32_t oa[4], ob[4];
             WinC wc = {0u, 0u, 0u, 0u};
-            if (fast) {
-                const uint32_t slot = wcache + sidx * 16u;
-                if (stale) {
-                    wc = window_consts(ks, y, PRE_OF(sidx), (uint32_t)ctr0);
-                    if (cache_ok) {
-                        if (lane == 0) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"(wc.c0), "r"(wc.c1), "r"(wc.c2), "r"(wc.c3) : "memory");
-                        __syncwarp();
-                    }
-                } else {
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wc.c0), "=r"(wc.c1), "=r"(wc.c2), "=r"(wc.c3) : "r"(slot) : "memory");
-                }
-            }
+            if (fast) wc = window_consts(ks, y, PRE_OF(sidx), (uint32_t)ctr0);
             if (!onA) return;
             if (onB && fast) {
                 aes256_x2w(ks, y, st.pre[sidx][0], wc, (uint32_t)ctrA, (uint32_t)ctrB, oa, ob);
@@ -831,20 +947,12 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
         // SHARE: iteration 0 only produces F(iter, first client); iteration cc >= 1 serves client cc-1
         // with F(c) - F(c+1), reusing F(c+1) as the next client's add term.
         word_t prev[SHARE ? NB : 1][SHARE ? MMAX : 1];
-        const uint32_t n_iter = SHARE ? c_count + 1 : c_count;
         for (uint32_t cc = 0; cc < n_iter; ++cc) {
             const uint32_t c = SHARE ? (cc ? c_first + cc - 1 : 0) : c_first + cc;
             const bool emit = !SHARE || cc > 0;
             // ---- 1. prefetch inputs (pairs) ----
             in_t pf[PF][2];
-            if (HAS_IN && emit && QUAD_OK && quad) {
-                if constexpr (QUAD_OK && HAS_IN) {
-                    const in_t* in = reinterpret_cast<const in_t*>(io.in) + (uint64_t)c * io.in_stride + qoff;
-                    uint32_t (*r)[4] = reinterpret_cast<uint32_t (*)[4]>(&pf[0][0]);
-                    ldg_quad(in, qr, r[0]);
-                    ldg_quad(in + 128, qr, r[1]);
-                }
-            } else if (HAS_IN && emit) {
+            if (HAS_IN && emit) {
                 const in_t* in = reinterpret_cast<const in_t*>(io.in) + (uint64_t)c * io.in_stride;
 #pragma unroll
                 for (int k = 0; k < PF; ++k) {
@@ -880,65 +988,6 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                         prev[SHARE ? h : 0][SHARE ? k : 0] = cur;
                     }
                 if (!emit) continue;
-            }
-            // ---- 3q. fast path: the lane applies its own blocks ----
-            if (QUAD_OK && quad) {
-                if constexpr (QUAD_OK) {
-                    const uint32_t mk32 = Word<1>::mask(g.b);
-#pragma unroll
-                    for (int h = 0; h < NB; ++h) {
-                        const uint64_t o = qoff + 128u * h;
-                        const uint64_t j = item_e0 + 4ull * lane + 128u * h;
-                        uint32_t mw[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) mw[k] = (uint32_t)acc[h][k] & mk32;
-                        const uint32_t* r = reinterpret_cast<const uint32_t*>(&pf[0][0]) + 4 * h;
-                        if (MODE == M_MASKS) {
-                            stg_quad(reinterpret_cast<uint32_t*>(io.out) + o, qr, mw[0], mw[1], mw[2], mw[3]);
-                        } else if (MODE == M_APPLY) {
-                            uint32_t* out = reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o;
-                            stg_quad(out, qr, (r[0] + mw[0]) & mk32, (r[1] + mw[1]) & mk32, (r[2] + mw[2]) & mk32, (r[3] + mw[3]) & mk32);
-                        } else if (MODE == M_ENCODE) {
-                            double u[4];
-                            if (nz.u) {
-                                const double* up = nz.u + (uint64_t)c * nz.u_stride + o;
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) u[k] = up[k];
-                            } else if (ALIGNED || (j & 1ull) == 0ull) {
-                                noise_pair(nz, nz.stream + c, j >> 1, u[0], u[1]);
-                                noise_pair(nz, nz.stream + c, (j >> 1) + 1, u[2], u[3]);
-                            } else {                      // odd chunk start: the four elements touch three pairs
-                                double lo, hi;
-                                noise_pair(nz, nz.stream + c, j >> 1, lo, u[0]);
-                                noise_pair(nz, nz.stream + c, (j >> 1) + 1, u[1], u[2]);
-                                noise_pair(nz, nz.stream + c, (j >> 1) + 2, u[3], hi);
-                            }
-                            uint32_t q[4];
-                            Seg sg = find_seg(cd, j);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (k && j + k >= sg.end) sg = find_seg(cd, j + k);
-                                q[k] = encode_one(__uint_as_float(r[k]), u[k], sg, cd.scale);
-                            }
-                            if (io.aux) stg_quad(reinterpret_cast<uint32_t*>(io.aux) + (uint64_t)c * io.out_stride + o, qr, q[0], q[1], q[2], q[3]);
-                            uint32_t* out = reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o;
-                            stg_quad(out, qr, (q[0] + mw[0]) & mk32, (q[1] + mw[1]) & mk32, (q[2] + mw[2]) & mk32, (q[3] + mw[3]) & mk32);
-                        } else if (MODE == M_DECODE) {
-                            uint32_t pw[4];
-                            double dv[4];
-                            Seg sg = find_seg(cd, j);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                pw[k] = (r[k] + mw[k]) & mk32;
-                                if (k && j + k >= sg.end) sg = find_seg(cd, j + k);
-                                dv[k] = decode_one((double)pw[k], sg.two_an, cd.den, sg.an);
-                            }
-                            if (io.aux) stg_quad(reinterpret_cast<uint32_t*>(io.aux) + o, qr, pw[0], pw[1], pw[2], pw[3]);
-                            stg_quad_f64(io.outf + o, qr, dv);
-                        }
-                    }
-                }
-                continue;
             }
             // ---- 3. lane-major -> element-major through the warp's slab ----
             __syncwarp();
@@ -1011,7 +1060,6 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                 }
             }
         }
-        if (fast) cached_win = win;                                  // every stream of the unit now has this window cached
       }
     }
 #undef PRE_OF

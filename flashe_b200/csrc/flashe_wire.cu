@@ -145,6 +145,14 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// floor(x / d) for d <= 32 and x < 2^48 (stream bit positions; the host routes longer streams to the
+// generic kernel): the exact quotient is an integer or at least 1/32 away from one, the rounding error of
+// the double division is below 2^48 * 2^-53 = 2^-5, so truncation cannot cross an integer.  Far cheaper
+// than a 64-bit integer division.
+__device__ __forceinline__ uint64_t div_small(uint64_t x, uint32_t d) {
+    return (uint64_t)__double2ull_rz(__ddiv_rn(__ull2double_rn(x), (double)d));
+}
+
 struct PackTile { uint64_t f_lo; uint32_t nf, rel0p, pre; };
 
 // pack: tile t = stream words [t*WP_WORDS, (t+1)*WP_WORDS); only whole 16-byte chunks (nvec of them).
@@ -160,8 +168,8 @@ k_wire_pack32(const uint32_t* __restrict__ words, uint64_t count, uint32_t bits,
     auto geom = [&](uint64_t t) {
         PackTile g;
         const uint64_t bit0 = t * (uint64_t)(WP_WORDS * 32);                 // stream bit of the tile's first word
-        g.f_lo = bit0 > pad ? (bit0 - pad) / bits : 0;                       // first field that reaches into the tile
-        uint64_t f_hi = (bit0 + (uint64_t)(WP_WORDS * 32) - 1 - pad) / bits; // pad < 8 <= tile bits
+        g.f_lo = bit0 > pad ? div_small(bit0 - pad, bits) : 0;               // first field that reaches into the tile
+        uint64_t f_hi = div_small(bit0 + (uint64_t)(WP_WORDS * 32) - 1 - pad, bits);   // pad < 8 <= tile bits
         if (f_hi >= count) f_hi = count - 1;
         g.nf = (uint32_t)(f_hi - g.f_lo + 1);
         // stream position of field f_lo relative to the tile, in (-bits, 32); kept as rel0 + 32 > 0
@@ -648,13 +656,13 @@ int flashe_wire_pack(flashe_ctx* ctx, const void* words, int word_bytes, uint64_
     if (!words || !out) return flashe_fail(FLASHE_EINVAL, "NULL buffer");
     if (((uintptr_t)out & 15u) != 0) return flashe_fail(FLASHE_EINVAL, "out must be 16-byte aligned");
     uint64_t nbytes; rc = flashe_wire_nbytes(bits, count, &nbytes); if (rc) return rc;
-    if (word_bytes == 4 && bits >= 8) {
+    if (word_bytes == 4 && bits >= 8 && nbytes < (1ull << 45)) {
         // whole 16-byte chunks through the tiled kernel, a short final chunk through the generic one
         const uint64_t nvec = nbytes >> 4;
         const uint32_t pad = (uint32_t)(8 * nbytes - count * (uint64_t)bits);
         int launches = 0;
         if (nvec) {
-            const int grid = grid_cap(info.num_sms, ceil_div_u64(nvec, WP_THREADS), 8);
+            const int grid = grid_cap(info.num_sms, ceil_div_u64(nvec, WP_THREADS), 6);   // 6 CTAs of 32.8 KB fit one SM: a single wave
             k_wire_pack32<<<grid, WP_THREADS, 0, cs>>>(reinterpret_cast<const uint32_t*>(words), count, (uint32_t)bits, pad, nvec,
                                                         reinterpret_cast<uint4*>(out));
             ++launches;

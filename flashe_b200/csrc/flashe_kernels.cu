@@ -356,11 +356,22 @@ __device__ __forceinline__ float div_rn_known_rcp(float v, float d, float y) {
     return __fmaf_rn(r, y, q);
 }
 
+// RCP = true: the caller has checked sg.rcp_two_a != 0 (one test per layer run instead of one per element).
+template <bool RCP = false>
 __device__ __forceinline__ uint32_t encode_one(float x, double u, const Seg& sg, float scale) {
     float v = fminf(fmaxf(x, -sg.a), sg.a);
     v = __fadd_rn(v, sg.a);
     v = __fmul_rn(v, scale);
-    v = div_rn_known_rcp(v, sg.two_a, sg.rcp_two_a);
+    if (RCP) {
+        const float d = sg.two_a, y = sg.rcp_two_a;
+        float q = __fmul_rn(v, y);
+        float r = __fmaf_rn(-d, q, v);
+        q = __fmaf_rn(r, y, q);
+        r = __fmaf_rn(-d, q, v);
+        v = __fmaf_rn(r, y, q);
+    } else {
+        v = div_rn_known_rcp(v, sg.two_a, sg.rcp_two_a);
+    }
     // floor(t) for 0 <= t < 2^32: t + 2^52 rounded towards -inf lands on the integer grid at
     // 2^52 + floor(t); the integer is the low word of that double.  (v >= 0 by construction.)
     const double t = __dadd_rn((double)v, u);
@@ -575,57 +586,16 @@ __device__ __noinline__ void aes256_block_slow(const KeySched& ks, uint32_t y, u
     o[0] = t[0]; o[1] = t[1]; o[2] = t[2]; o[3] = t[3];
 }
 
-// Unroll factor of the six double-rounds of aes256_x2.  Rolled (1) is the measured optimum: the fully
-// unrolled form makes the hot loop ~40 KB of SASS and the kernel loses ~5 % to instruction-fetch stalls
-// (stall_no_inst); rolled, the round keys come from the constant bank through a uniform index.
+// Unroll factor of the double-round loop of aes256_x2w (5 iterations).  Fully unrolled (5) is the measured
+// optimum now that the hot loop holds ONE inlined copy (~13 KB of SASS; round keys become constant-bank
+// operands): 77.2 ms vs 78.7 ms rolled for the 64-client encode.  With several inlined copies (the kernel
+// before the lane-local item loop) the unrolled form lost ~5 % to instruction-fetch stalls.
 #define FLASHE_PRAGMA_(x) _Pragma(#x)
 #define FLASHE_PRAGMA(x) FLASHE_PRAGMA_(x)
 #ifndef FLASHE_AES_UNROLL
-#define FLASHE_AES_UNROLL 1
+#define FLASHE_AES_UNROLL 5
 #endif
 #define AES_ROUNDS_UNROLL FLASHE_PRAGMA(unroll FLASHE_AES_UNROLL)
-
-// Two AES-256 blocks of the SAME stream (counters w3a, w3b; words 0-2 shared, word 2 == 0) computed
-// in one instruction stream: twice the independent lookups per round, so the round-boundary latency
-// (LDS ~30 clk + LOP3) of one block hides under the other's.
-__device__ __forceinline__ void aes256_x2(const KeySched& ks, uint32_t y, Pre pre, uint32_t w3a, uint32_t w3b,
-                                          uint32_t oa[4], uint32_t ob[4]) {
-    uint32_t a0, a1, a2, a3, b0, b1, b2, b3, p0, p1, p2, p3, q0, q1, q2, q3;
-    a3 = w3a ^ ks.rk[3]; b3 = w3b ^ ks.rk[3];
-    p0 = pre.p0 ^ T3(a3); q0 = pre.p0 ^ T3(b3);
-    p1 = pre.p1 ^ T2(a3); q1 = pre.p1 ^ T2(b3);
-    p2 = pre.p2 ^ T1(a3); q2 = pre.p2 ^ T1(b3);
-    p3 = pre.p3 ^ T0(a3); q3 = pre.p3 ^ T0(b3);
-    AES_ROUNDS_UNROLL
-    for (int r = 2; r < 14; r += 2) {
-        a0 = T0(p0) ^ T1(p1) ^ T2(p2) ^ T3(p3) ^ ks.rk[4 * r + 0];
-        b0 = T0(q0) ^ T1(q1) ^ T2(q2) ^ T3(q3) ^ ks.rk[4 * r + 0];
-        a1 = T0(p1) ^ T1(p2) ^ T2(p3) ^ T3(p0) ^ ks.rk[4 * r + 1];
-        b1 = T0(q1) ^ T1(q2) ^ T2(q3) ^ T3(q0) ^ ks.rk[4 * r + 1];
-        a2 = T0(p2) ^ T1(p3) ^ T2(p0) ^ T3(p1) ^ ks.rk[4 * r + 2];
-        b2 = T0(q2) ^ T1(q3) ^ T2(q0) ^ T3(q1) ^ ks.rk[4 * r + 2];
-        a3 = T0(p3) ^ T1(p0) ^ T2(p1) ^ T3(p2) ^ ks.rk[4 * r + 3];
-        b3 = T0(q3) ^ T1(q0) ^ T2(q1) ^ T3(q2) ^ ks.rk[4 * r + 3];
-        p0 = T0(a0) ^ T1(a1) ^ T2(a2) ^ T3(a3) ^ ks.rk[4 * r + 4];
-        q0 = T0(b0) ^ T1(b1) ^ T2(b2) ^ T3(b3) ^ ks.rk[4 * r + 4];
-        p1 = T0(a1) ^ T1(a2) ^ T2(a3) ^ T3(a0) ^ ks.rk[4 * r + 5];
-        q1 = T0(b1) ^ T1(b2) ^ T2(b3) ^ T3(b0) ^ ks.rk[4 * r + 5];
-        p2 = T0(a2) ^ T1(a3) ^ T2(a0) ^ T3(a1) ^ ks.rk[4 * r + 6];
-        q2 = T0(b2) ^ T1(b3) ^ T2(b0) ^ T3(b1) ^ ks.rk[4 * r + 6];
-        p3 = T0(a3) ^ T1(a0) ^ T2(a1) ^ T3(a2) ^ ks.rk[4 * r + 7];
-        q3 = T0(b3) ^ T1(b0) ^ T2(b1) ^ T3(b2) ^ ks.rk[4 * r + 7];
-    }
-#define LAST(a, b, c, d, k)                                                                         \
-    (__byte_perm(__byte_perm(lds_tab<128>(__byte_perm((d), y, SEL_B0)),                             \
-                             lds_tab<0>(__byte_perm((c), y, SEL_B1)), 0x3250),                      \
-                 __byte_perm(lds_tab<0x10080>(__byte_perm((b), y, SEL_B2)),                         \
-                             lds_tab<0x10000>(__byte_perm((a), y, SEL_B3)), 0x7210), 0x7610) ^ ks.rk[k])
-    oa[0] = LAST(p0, p1, p2, p3, 56); ob[0] = LAST(q0, q1, q2, q3, 56);
-    oa[1] = LAST(p1, p2, p3, p0, 57); ob[1] = LAST(q1, q2, q3, q0, 57);
-    oa[2] = LAST(p2, p3, p0, p1, 58); ob[2] = LAST(q2, q3, q0, q1, 58);
-    oa[3] = LAST(p3, p0, p1, p2, 59); ob[3] = LAST(q3, q0, q1, q2, 59);
-#undef LAST
-}
 
 // ------------------------------------------------------------------------------------------------
 // k_stream: persistent, one 512-thread CTA per SM (128 KB of tables + per-warp slabs).
@@ -659,7 +629,9 @@ __device__ __forceinline__ WinC window_consts(const KeySched& ks, uint32_t y, Pr
     return c;
 }
 
-// Two blocks of the same stream and the same counter window (see aes256_x2 for the interleaving).
+// Two AES-256 blocks of the SAME stream and the same counter window (counters w3a, w3b; words 0-2 shared,
+// word 2 == 0) computed in one instruction stream: twice the independent lookups per round, so the
+// round-boundary latency (LDS ~30 clk + LOP3) of one block hides under the other's.
 __device__ __forceinline__ void aes256_x2w(const KeySched& ks, uint32_t y, uint32_t pre_p0, WinC c, uint32_t w3a, uint32_t w3b,
                                            uint32_t oa[4], uint32_t ob[4]) {
     uint32_t a0, a1, a2, a3, b0, b1, b2, b3, p0, p1, p2, p3, q0, q1, q2, q3;
@@ -793,8 +765,10 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
           const bool stale = !cache_ok || win != cached_win;
           const uint32_t mk32 = Word<1>::mask(g.b);
           const bool one_seg = cd.nseg == 1;
+          const bool one_rcp = one_seg && MODE == M_ENCODE && cd.seg[0].rcp_two_a != 0.0f;
           uint32_t prev[NB][4];
-          for (uint32_t cc = 0; cc < n_iter; ++cc) {
+          const uint32_t n_iter_here = SHARE ? n_iter : 1u;          // without SHARE a unit serves exactly one client
+          for (uint32_t cc = 0; cc < n_iter_here; ++cc) {
               const uint32_t c = SHARE ? (cc ? c_first + cc - 1 : 0) : c_first + cc;
               const bool emit = !SHARE || cc > 0;
               uint32_t r[NB][4];
@@ -872,11 +846,16 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                           noise_pair(nz, nz.stream + c, (j >> 1) + 2, u[3], hi);
                       }
                       uint32_t q[4];
-                      Seg sg = find_seg(cd, j);
+                      if (one_rcp) {                                 // single layer with a usable reciprocal (warp-uniform)
 #pragma unroll
-                      for (int k = 0; k < 4; ++k) {
-                          if (k && !one_seg && j + k >= sg.end) sg = find_seg(cd, j + k);
-                          q[k] = encode_one(__uint_as_float(r[h][k]), u[k], sg, cd.scale);
+                          for (int k = 0; k < 4; ++k) q[k] = encode_one<true>(__uint_as_float(r[h][k]), u[k], cd.seg[0], cd.scale);
+                      } else {
+                          Seg sg = find_seg(cd, j);
+#pragma unroll
+                          for (int k = 0; k < 4; ++k) {
+                              if (k && !one_seg && j + k >= sg.end) sg = find_seg(cd, j + k);
+                              q[k] = encode_one(__uint_as_float(r[h][k]), u[k], sg, cd.scale);
+                          }
                       }
                       if (io.aux) stg_quad(reinterpret_cast<uint32_t*>(io.aux) + (uint64_t)c * io.out_stride + o, qr, q[0], q[1], q[2], q[3]);
                       uint32_t* out = reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o;

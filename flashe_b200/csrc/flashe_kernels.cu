@@ -150,6 +150,7 @@ struct CodecDev {
     int32_t ebits;
     float scale;             // 2^e - 1 as float32
     double den;              // (2^e - 1) * n as float64
+    double den_rcp;          // RN(1 / den), or 0: use the library division
     const Seg* table;        // device table when nseg > MAX_INLINE_SEG, else NULL
     Seg seg[MAX_INLINE_SEG];
 };
@@ -379,8 +380,21 @@ __device__ __forceinline__ uint32_t encode_one(float x, double u, const Seg& sg,
 }
 
 // _static_unquantize_padding_asymmetric, jzf_quantize.py:102-107 (float64, left to right).
-__device__ __forceinline__ double decode_one(double v, double two_an, double den, double an) {
-    return __dsub_rn(__ddiv_rn(__dmul_rn(v, two_an), den), an);
+// The division uses the host-computed y = RN(1/den) when the host offers it (den_rcp != 0): q0 = RN(n*y)
+// is within 2 ulp of n/den, one FMA residual correction makes it faithful and, y being correctly rounded,
+// Markstein's theorem makes the second one the IEEE quotient (tests/native/ddiv_rcp_check.c sweeps it on
+// the CPU, 2^28 cases).  The host withholds y when a layer's 2*alpha*n lies outside [2^-400, 2^400]
+// (the residuals must not underflow).  Six float64 operations instead of the ~30 of the library division.
+__device__ __forceinline__ double ddiv_rn_known_rcp(double n, double d, double y) {
+    if (y == 0.0) return __ddiv_rn(n, d);
+    double q = __dmul_rn(n, y);
+    double r = __fma_rn(-d, q, n);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-d, q, n);
+    return __fma_rn(r, y, q);
+}
+__device__ __forceinline__ double decode_one(double v, double two_an, double den, double den_rcp, double an) {
+    return __dsub_rn(ddiv_rn_known_rcp(__dmul_rn(v, two_an), den, den_rcp), an);
 }
 
 // Philox4x32-10 (Salmon et al. 2011), counter (c0,c1,c2,c3); the ten round keys
@@ -868,7 +882,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                       for (int k = 0; k < 4; ++k) {
                           pw[k] = (r[h][k] + mw[k]) & mk32;
                           if (k && !one_seg && j + k >= sg.end) sg = find_seg(cd, j + k);
-                          dv[k] = decode_one((double)pw[k], sg.two_an, cd.den, sg.an);
+                          dv[k] = decode_one((double)pw[k], sg.two_an, cd.den, cd.den_rcp, sg.an);
                       }
                       if (io.aux) stg_quad(reinterpret_cast<uint32_t*>(io.aux) + o, qr, pw[0], pw[1], pw[2], pw[3]);
                       stg_quad_f64(io.outf + o, qr, dv);
@@ -1023,13 +1037,13 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                         word_t pw = WT::band(WT::add(*reinterpret_cast<word_t*>(&pf[k][0]), mw0), mk);
                         if (io.aux) reinterpret_cast<word_t*>(io.aux)[o0] = pw;
                         const Seg sg = find_seg(cd, j0);
-                        io.outf[o0] = decode_one(WT::to_double(pw), sg.two_an, cd.den, sg.an);
+                        io.outf[o0] = decode_one(WT::to_double(pw), sg.two_an, cd.den, cd.den_rcp, sg.an);
                     }
                     if (v1) {
                         word_t pw = WT::band(WT::add(*reinterpret_cast<word_t*>(&pf[k][1]), mw1), mk);
                         if (io.aux) reinterpret_cast<word_t*>(io.aux)[o0 + 1] = pw;
                         const Seg sg = find_seg(cd, j0 + 1);
-                        io.outf[o0 + 1] = decode_one(WT::to_double(pw), sg.two_an, cd.den, sg.an);
+                        io.outf[o0 + 1] = decode_one(WT::to_double(pw), sg.two_an, cd.den, cd.den_rcp, sg.an);
                     }
                 } else if (MODE == M_SCATTER) {
                     const int64_t* index = reinterpret_cast<const int64_t*>(io.aux);
@@ -1146,7 +1160,27 @@ __global__ void k_decode(const typename Word<WORDS>::T* __restrict__ v, uint64_t
     typedef Word<WORDS> WT;
     for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < count; o += (uint64_t)gridDim.x * blockDim.x) {
         const Seg sg = find_seg(cd, begin + o);
-        out[o] = decode_one(WT::to_double(v[o]), sg.two_an, cd.den, sg.an);
+        out[o] = decode_one(WT::to_double(v[o]), sg.two_an, cd.den, cd.den_rcp, sg.an);
+    }
+}
+
+// 4-byte words, 16-byte aligned buffers and begin: one thread = 4 elements (128-bit load, two 128-bit stores)
+__global__ void __launch_bounds__(256)
+k_decode_v4(const uint4* __restrict__ v, uint64_t begin, uint64_t nvec, const __grid_constant__ CodecDev cd, double* __restrict__ out) {
+    const bool one_seg = cd.nseg == 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 w = __ldcs(v + i);
+        const uint32_t p[4] = {w.x, w.y, w.z, w.w};
+        const uint64_t j = begin + 4ull * i;
+        double d[4];
+        Seg sg = find_seg(cd, j);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k && !one_seg && j + k >= sg.end) sg = find_seg(cd, j + k);
+            d[k] = decode_one((double)p[k], sg.two_an, cd.den, cd.den_rcp, sg.an);
+        }
+        stg_d2(out + 4ull * i, d[0], d[1]);
+        stg_d2(out + 4ull * i + 2, d[2], d[3]);
     }
 }
 
@@ -1576,6 +1610,15 @@ static int make_codec(const flashe_ctx* ctx, const flashe_span* span, const flas
     d.nseg = c->nseg; d.ebits = c->element_bits;
     d.scale = (float)(((int64_t)1 << c->element_bits) - 1);
     d.den = (double)((((int64_t)1 << c->element_bits) - 1) * (int64_t)n);
+    {
+        bool ok = decode;
+        for (int s = 0; ok && s < c->nseg; ++s) {
+            const double t = fabs(segs[s].two_an);
+            ok = (t == 0.0) || (t >= 0x1p-400 && t <= 0x1p400);
+        }
+        volatile double y = 1.0 / d.den;                  // IEEE division: correctly rounded
+        d.den_rcp = ok ? y : 0.0;
+    }
     if (c->nseg <= MAX_INLINE_SEG) {
         memcpy(d.seg, segs.data(), sizeof(Seg) * (size_t)c->nseg);
         d.table = nullptr;
@@ -1700,6 +1743,17 @@ int flashe_ctx_create(const uint8_t* seed, size_t seed_len, int int_bits, int de
     if (seed_len >= 32) memcpy(ctx->key, seed + (seed_len - 32), 32);
     else memcpy(ctx->key + (32 - seed_len), seed, seed_len);
     haes::expand(ctx->key, ctx->ks.rk);
+    // Workspaces come from the device's default stream-ordered pool; keep freed blocks cached across
+    // synchronisation points (the default threshold of 0 returns them to the driver at every sync, and
+    // the next cudaMallocAsync then costs milliseconds).
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     cudaError_t e = cudaMemcpyToSymbol(g_te0, haes::te0, sizeof(haes::te0));
     if (e != cudaSuccess) { delete ctx; return fail(FLASHE_ECUDA, std::string("cudaMemcpyToSymbol: ") + cudaGetErrorString(e)); }
     *out = ctx;
@@ -1995,7 +2049,16 @@ int flashe_decode(flashe_ctx* ctx, const flashe_span* span, const void* v, const
     if (!v || !out) return fail(FLASHE_EINVAL, "NULL buffer");
     CodecHost ch; rc = make_codec(ctx, span, codec, true, cs, &ch); if (rc) return rc;
     const int grid = grid_1d(ctx, span->count, 256, 16);
-    if (ctx->words == 1) k_decode<1><<<grid, 256, 0, cs>>>((const uint32_t*)v, span->begin, span->count, ch.dev, out);
+    if (ctx->words == 1 && (((uintptr_t)v | (uintptr_t)out) & 15u) == 0) {
+        const uint64_t nvec = span->count / 4, done = nvec * 4;
+        if (nvec) k_decode_v4<<<grid_1d(ctx, nvec, 256, 8), 256, 0, cs>>>((const uint4*)v, span->begin, nvec, ch.dev, out);
+        if (done < span->count) {
+            k_decode<1><<<1, 32, 0, cs>>>((const uint32_t*)v + done, span->begin + done, span->count - done, ch.dev, out + done);
+            g_launches.fetch_add(1);
+        }
+        if (!nvec) g_launches.fetch_sub(1);
+    }
+    else if (ctx->words == 1) k_decode<1><<<grid, 256, 0, cs>>>((const uint32_t*)v, span->begin, span->count, ch.dev, out);
     else k_decode<2><<<grid, 256, 0, cs>>>((const uint64_t*)v, span->begin, span->count, ch.dev, out);
     g_launches.fetch_add(1);
     free_codec(&ch, cs);

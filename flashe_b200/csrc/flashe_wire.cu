@@ -123,140 +123,116 @@ k_wire_unpack(const uint8_t* __restrict__ in, uint64_t count, uint32_t bits, uin
 }
 
 // -------------------------------------------------------------------------------------------------
-// Fast forms for 4-byte words (8 <= bits <= 32, the ciphertext widths FLASHE ships).  Seen from its
-// first byte the wire string is a big-endian BIT stream: `pad` = 8*nbytes - count*bits zero bits, then
-// the elements in index order, most significant bit first; element j occupies stream bits
-// [pad + j*bits, pad + (j+1)*bits).  A CTA converts one tile through shared memory so that both the
-// global reads and the global writes are 16 bytes per thread and fully coalesced, and every thread
-// only touches the <= 32/bits + 2 fields (pack) or the two stream words (unpack) it needs.
+// Fast forms for 4-byte words (8 <= bits <= 32 for pack: the ciphertext widths FLASHE ships).  Seen from
+// its first byte the wire string is a big-endian BIT stream: `pad` = 8*nbytes - count*bits zero bits,
+// then the elements in index order, most significant bit first; element j occupies stream bits
+// [pad + j*bits, pad + (j+1)*bits), i.e. at most two 32-bit stream words.
+//   pack    a CTA owns a tile of 1024 stream words; every thread reads its elements straight from global
+//           memory (coalesced 4-byte loads, ~6 in flight per thread), ORs the one or two word pieces into
+//           the tile image in shared memory (shared atomics), and the image leaves as 16-byte stores.
+//   unpack  the stream words of a tile of 1024 elements are staged in shared memory with 16-byte
+//           cp.async (next tile in flight while this one is converted); an element is one funnel shift
+//           of two staged words.
+// Both are a few tens of instructions per 16 bytes moved, so HBM, not the issue rate, bounds them.
 // -------------------------------------------------------------------------------------------------
 #define WP_THREADS 256
 #define WP_WORDS (WP_THREADS * 4)                 // stream words (32 bit) per pack tile
-#define WP_MAX_FIELDS (WP_WORDS * 32 / 8 + 2)     // bits >= 8
-#define WP_BUF (WP_MAX_FIELDS + 6)                // + alignment shift of the staged fields
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// floor(x / d) for d <= 32 and x < 2^48 (stream bit positions; the host routes longer streams to the
-// generic kernel): the exact quotient is an integer or at least 1/32 away from one, the rounding error of
-// the double division is below 2^48 * 2^-53 = 2^-5, so truncation cannot cross an integer.  Far cheaper
-// than a 64-bit integer division.
-__device__ __forceinline__ uint64_t div_small(uint64_t x, uint32_t d) {
-    return (uint64_t)__double2ull_rz(__ddiv_rn(__ull2double_rn(x), (double)d));
-}
+struct PackTile { uint64_t f_lo; uint32_t nf; int32_t rel0; };
 
-struct PackTile { uint64_t f_lo; uint32_t nf, rel0p, pre; };
-
-// pack: tile t = stream words [t*WP_WORDS, (t+1)*WP_WORDS); only whole 16-byte chunks (nvec of them).
-// The fields of tile t+gridDim.x travel global -> shared with cp.async while tile t is converted
-// (two buffers), so a CTA always has a whole tile of loads in flight.
+// pack: tile t = stream words [t*WP_WORDS, (t+1)*WP_WORDS); only whole 16-byte chunks (nvec of them)
 __global__ void __launch_bounds__(WP_THREADS)
 k_wire_pack32(const uint32_t* __restrict__ words, uint64_t count, uint32_t bits, uint32_t pad, uint64_t nvec,
               uint4* __restrict__ out) {
-    __shared__ __align__(16) uint32_t sf[2][WP_BUF];
+    __shared__ __align__(16) uint32_t so[2][WP_WORDS];
+    __shared__ PackTile sg[2];
     const uint32_t fm = bits >= 32u ? 0xffffffffu : ((1u << bits) - 1u);
     const uint64_t ntiles = (nvec + WP_THREADS - 1) / WP_THREADS;
-
-    auto geom = [&](uint64_t t) {
-        PackTile g;
-        const uint64_t bit0 = t * (uint64_t)(WP_WORDS * 32);                 // stream bit of the tile's first word
-        g.f_lo = bit0 > pad ? div_small(bit0 - pad, bits) : 0;               // first field that reaches into the tile
-        uint64_t f_hi = div_small(bit0 + (uint64_t)(WP_WORDS * 32) - 1 - pad, bits);   // pad < 8 <= tile bits
-        if (f_hi >= count) f_hi = count - 1;
-        g.nf = (uint32_t)(f_hi - g.f_lo + 1);
-        // stream position of field f_lo relative to the tile, in (-bits, 32); kept as rel0 + 32 > 0
-        g.rel0p = (uint32_t)((int64_t)(pad + g.f_lo * bits) - (int64_t)bit0 + 32);
-        // field i is staged at index pre + i so that the 16-byte aligned part of the source lands 16-byte aligned
-        const uint32_t head = (uint32_t)((4u - ((uintptr_t)(words + g.f_lo) >> 2)) & 3u);
-        g.pre = (4u - head) & 3u;
-        return g;
-    };
-    auto issue = [&](const PackTile& g, int buf) {
-        const uint32_t* src = words + g.f_lo;
-        const uint32_t base = smem_u32(&sf[buf][g.pre]);
-        const uint32_t head = (4u - g.pre) & 3u;
-        const uint32_t nq = g.nf > head ? (g.nf - head) >> 2 : 0;
-        for (uint32_t q = threadIdx.x; q < nq; q += WP_THREADS) cp_async16(base + 4u * (head + 4u * q), src + head + 4u * q);
-        const uint32_t rest = g.nf - 4u * nq;                                // head fields + tail fields
-        for (uint32_t e = threadIdx.x; e < rest; e += WP_THREADS) {
-            const uint32_t i = e < head && e < g.nf ? e : 4u * nq + e;       // (nf <= head: all fields are "head")
-            if (i < g.nf) cp_async4(base + 4u * i, src + i);
-        }
-        cp_async_commit();
-    };
-
     uint64_t t = blockIdx.x;
     if (t >= ntiles) return;
-    PackTile cur = geom(t), nxt = cur;
-    issue(cur, 0);
-    for (int buf = 0; t < ntiles; t += gridDim.x, buf ^= 1, cur = nxt) {
-        const bool more = t + gridDim.x < ntiles;
-        if (more) { nxt = geom(t + gridDim.x); issue(nxt, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-        __syncthreads();                                                    // tile t's fields are visible
-        const uint32_t* f = &sf[buf][cur.pre];
-        const uint32_t nf = cur.nf, rel0p = cur.rel0p;
-        const uint64_t vec = t * WP_THREADS + threadIdx.x;
-        if (vec < nvec) {
-            uint32_t w[4];
-            const uint32_t wbit0 = 128u * threadIdx.x + 32u;                 // first word's start, in the rel0p frame
-            uint32_t i = wbit0 >= rel0p ? (wbit0 - rel0p) / bits : 0u;       // the field that holds that bit
+
+    // thread 0 prepares the geometry of a tile one step ahead (the only 64-bit divisions of the kernel)
+    auto geom = [&](uint64_t tile, int slot) {
+        const uint64_t bit0 = tile * (uint64_t)(WP_WORDS * 32);             // stream bit of the tile's first word
+        PackTile g;
+        g.f_lo = bit0 > pad ? (bit0 - pad) / bits : 0;                       // first element that reaches into the tile
+        uint64_t f_hi = (bit0 + (uint64_t)(WP_WORDS * 32) - 1 - pad) / bits; // last element that starts inside it
+        if (f_hi >= count) f_hi = count - 1;
+        g.nf = (uint32_t)(f_hi - g.f_lo + 1);
+        g.rel0 = (int32_t)((int64_t)(pad + g.f_lo * bits) - (int64_t)bit0);  // in (-bits, 32)
+        sg[slot] = g;
+    };
+    for (uint32_t i = threadIdx.x; i < 2 * WP_WORDS; i += WP_THREADS) (&so[0][0])[i] = 0u;
+    if (threadIdx.x == 0) geom(t, 0);
+    __syncthreads();
+    for (int buf = 0; t < ntiles; t += gridDim.x, buf ^= 1) {
+        const PackTile g = sg[buf];
+        if (threadIdx.x == 0 && t + gridDim.x < ntiles) geom(t + gridDim.x, buf ^ 1);
+        const uint32_t* src = words + g.f_lo;
+        uint32_t* img = so[buf];
+        for (uint32_t i0 = threadIdx.x; i0 < g.nf; i0 += 4u * WP_THREADS) {  // four independent loads in flight per thread
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const uint32_t i = i0 + k * WP_THREADS; v[k] = i < g.nf ? __ldcs(src + i) & fm : 0u; }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t wbit = wbit0 + 32u * k;
-                uint64_t acc = 0;
-                for (; i < nf; ++i) {                                        // fields that intersect [wbit, wbit + 32)
-                    const uint32_t pos = rel0p + i * bits;                   // field start (frame: tile bit + 32)
-                    if (pos >= wbit + 32u) break;
-                    // 64-bit window = stream bits [wbit - 32, wbit + 32); the field's top bit sits at pos - (wbit - 32)
-                    const int sh = 64 - (int)bits - (int)(pos + 32u - wbit);
-                    const uint64_t v = f[i] & fm;
-                    acc |= sh >= 0 ? (v << sh) : (v >> (-sh));
-                }
-                if (i > 0u && rel0p + i * bits > wbit + 32u) --i;            // the last field runs on into the next word
-                w[k] = __byte_perm((uint32_t)acc, 0, 0x0123);                // first stream byte first
+                const uint32_t i = i0 + k * WP_THREADS;
+                const int32_t rel = g.rel0 + (int32_t)(i * bits);           // element start, in tile bits
+                const int32_t wi = rel >> 5;                                // -1 for an element that begins before the tile
+                const uint64_t V = (uint64_t)v[k] << (64u - bits - ((uint32_t)rel & 31u));   // placed in the word pair (wi, wi+1)
+                const uint32_t hi = (uint32_t)(V >> 32), lo = (uint32_t)V;
+                if (hi && (uint32_t)wi < (uint32_t)WP_WORDS) atomicOr(img + wi, hi);
+                if (lo && (uint32_t)(wi + 1) < (uint32_t)WP_WORDS) atomicOr(img + wi + 1, lo);
             }
-            __stcs(out + vec, make_uint4(w[0], w[1], w[2], w[3]));
         }
-        __syncthreads();                                                    // buffer `buf` may be refilled next round
+        __syncthreads();                                                    // the tile image is complete
+        const uint64_t vec = t * WP_THREADS + threadIdx.x;
+        uint4* cell = reinterpret_cast<uint4*>(img) + threadIdx.x;
+        const uint4 w = *cell;
+        *cell = make_uint4(0u, 0u, 0u, 0u);                                 // ready for the tile after next
+        if (vec < nvec)
+            __stcs(out + vec, make_uint4(__byte_perm(w.x, 0, 0x0123), __byte_perm(w.y, 0, 0x0123),
+                                         __byte_perm(w.z, 0, 0x0123), __byte_perm(w.w, 0, 0x0123)));   // first stream byte first
+        // no second barrier: the next tile ORs into the other image (cleared one round ago, before the
+        // barrier above) and reads the other geometry slot
     }
 }
 
-// unpack: tile = WU_ELEMS consecutive elements, thread = 4 of them (one 16-byte store); the stream
-// words of the next tile are in flight (cp.async, two buffers) while this one is converted.
+// unpack: tile = WU_ELEMS consecutive elements, thread = 4 of them (one 16-byte store)
 #define WU_ELEMS (WP_THREADS * 4)
-#define WU_BUF (WU_ELEMS + 8)
+#define WU_BUF (WU_ELEMS + 16)
 __global__ void __launch_bounds__(WP_THREADS)
 k_wire_unpack32(const uint8_t* __restrict__ in, uint64_t count, uint32_t bits, uint32_t pad, uint64_t nbytes,
                 uint32_t* __restrict__ words) {
     __shared__ __align__(16) uint32_t sw[2][WU_BUF];
     const uint32_t fm = bits >= 32u ? 0xffffffffu : ((1u << bits) - 1u);
     const uint64_t ntiles = (count + WU_ELEMS - 1) / WU_ELEMS;
-    const uint64_t nwords_in = nbytes >> 2;                                  // whole stream words
 
-    // stream words [w_lo, w_lo + nw) of tile t -> sw[buf][0..nw), as stored (big-endian); nw <= WU_ELEMS + 2
-    auto issue = [&](uint64_t t, int buf) {
-        const uint64_t j0 = t * WU_ELEMS;
+    // stream words [w_al, w_hi) of tile t -> sw[buf], as stored (big-endian); w_al = 16-byte aligned start
+    auto issue = [&](uint64_t tile, int buf) {
+        const uint64_t j0 = tile * WU_ELEMS;
         const uint32_t ne = (uint32_t)(count - j0 < WU_ELEMS ? count - j0 : WU_ELEMS);
         const uint64_t b_lo = pad + j0 * bits, b_hi = b_lo + (uint64_t)ne * bits;
-        const uint64_t w_lo = b_lo >> 5;
-        const uint32_t nw = (uint32_t)(((b_hi + 31) >> 5) - w_lo);
+        const uint64_t w_al = (b_lo >> 5) & ~3ull;
+        const uint32_t nq = (uint32_t)((((b_hi + 31) >> 5) - w_al + 3) >> 2);    // 16-byte pieces, <= WU_ELEMS / 4 + 2
         const uint32_t base = smem_u32(&sw[buf][0]);
-        for (uint32_t i = threadIdx.x; i < nw; i += WP_THREADS) {
-            const uint64_t w = w_lo + i;
-            if (w < nwords_in) {
-                cp_async4(base + 4u * i, in + 4 * w);
-            } else {                                                         // the stream's last, partial word
-                uint32_t v = 0;
-                for (uint32_t b = 0; b < 4; ++b) { const uint64_t a = 4 * w + b; v |= (a < nbytes ? (uint32_t)in[a] : 0u) << (8 * b); }
-                sw[buf][i] = v;
+        for (uint32_t q = threadIdx.x; q < nq; q += WP_THREADS) {
+            const uint64_t byte0 = 4 * (w_al + 4ull * q);
+            if (byte0 + 16 <= nbytes) {
+                cp_async16(base + 16u * q, in + byte0);
+            } else {                                                         // the stream's last, partial piece
+                for (uint32_t k = 0; k < 4; ++k) {
+                    uint32_t v = 0;
+                    for (uint32_t b = 0; b < 4; ++b) { const uint64_t a = byte0 + 4 * k + b; v |= (a < nbytes ? (uint32_t)in[a] : 0u) << (8 * b); }
+                    sw[buf][4 * q + k] = v;
+                }
             }
         }
         cp_async_commit();
@@ -271,18 +247,18 @@ k_wire_unpack32(const uint8_t* __restrict__ in, uint64_t count, uint32_t bits, u
         const uint64_t j0 = t * WU_ELEMS;
         const uint32_t ne = (uint32_t)(count - j0 < WU_ELEMS ? count - j0 : WU_ELEMS);
         const uint64_t b_lo = pad + j0 * bits;
-        const uint32_t nw = (uint32_t)(((b_lo + (uint64_t)ne * bits + 31) >> 5) - (b_lo >> 5));
+        const uint32_t o_base = (uint32_t)(b_lo - (((b_lo >> 5) & ~3ull) << 5));   // bit offset of element j0 in sw[buf]
         const uint32_t e0 = 4u * threadIdx.x;
         if (e0 < ne) {
+            const uint32_t* w = sw[buf];
             uint32_t r[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t o = (uint32_t)(b_lo & 31u) + (e0 + k) * bits;
+                const uint32_t o = o_base + (e0 + k) * bits;
                 const uint32_t wi = o >> 5;
-                const uint32_t hi = wi < nw ? __byte_perm(sw[buf][wi], 0, 0x0123) : 0u;
-                const uint32_t lo = wi + 1u < nw ? __byte_perm(sw[buf][wi + 1u], 0, 0x0123) : 0u;
-                const uint64_t win = ((uint64_t)hi << 32) | lo;
-                r[k] = (uint32_t)(win >> (64u - bits - (o & 31u))) & fm;
+                const uint32_t hi = __byte_perm(w[wi], 0, 0x0123), lo = __byte_perm(w[wi + 1], 0, 0x0123);
+                // 32 stream bits from bit (o & 31) of hi:lo; a word past the staged ones only feeds bits that are shifted out
+                r[k] = (__funnelshift_l(lo, hi, o & 31u) >> (32u - bits)) & fm;
             }
             uint32_t* dst = words + j0 + e0;
             if (e0 + 4u <= ne && ((uintptr_t)dst & 15u) == 0) __stcs(reinterpret_cast<uint4*>(dst), make_uint4(r[0], r[1], r[2], r[3]));
@@ -656,13 +632,13 @@ int flashe_wire_pack(flashe_ctx* ctx, const void* words, int word_bytes, uint64_
     if (!words || !out) return flashe_fail(FLASHE_EINVAL, "NULL buffer");
     if (((uintptr_t)out & 15u) != 0) return flashe_fail(FLASHE_EINVAL, "out must be 16-byte aligned");
     uint64_t nbytes; rc = flashe_wire_nbytes(bits, count, &nbytes); if (rc) return rc;
-    if (word_bytes == 4 && bits >= 8 && nbytes < (1ull << 45)) {
+    if (word_bytes == 4 && bits >= 8) {
         // whole 16-byte chunks through the tiled kernel, a short final chunk through the generic one
         const uint64_t nvec = nbytes >> 4;
         const uint32_t pad = (uint32_t)(8 * nbytes - count * (uint64_t)bits);
         int launches = 0;
         if (nvec) {
-            const int grid = grid_cap(info.num_sms, ceil_div_u64(nvec, WP_THREADS), 6);   // 6 CTAs of 32.8 KB fit one SM: a single wave
+            const int grid = grid_cap(info.num_sms, ceil_div_u64(nvec, WP_THREADS), 8);
             k_wire_pack32<<<grid, WP_THREADS, 0, cs>>>(reinterpret_cast<const uint32_t*>(words), count, (uint32_t)bits, pad, nvec,
                                                         reinterpret_cast<uint4*>(out));
             ++launches;
@@ -687,7 +663,7 @@ int flashe_wire_unpack(flashe_ctx* ctx, const uint8_t* in, uint64_t count, int b
     if (count == 0) return FLASHE_OK;
     if (!in || !words_out) return flashe_fail(FLASHE_EINVAL, "NULL buffer");
     uint64_t nbytes; rc = flashe_wire_nbytes(bits, count, &nbytes); if (rc) return rc;
-    if (word_bytes == 4 && ((uintptr_t)words_out & 3u) == 0 && ((uintptr_t)in & 3u) == 0) {
+    if (word_bytes == 4 && ((uintptr_t)words_out & 3u) == 0 && ((uintptr_t)in & 15u) == 0) {
         const uint32_t pad = (uint32_t)(8 * nbytes - count * (uint64_t)bits);
         const int grid = grid_cap(info.num_sms, ceil_div_u64(count, WU_ELEMS), 8);
         k_wire_unpack32<<<grid, WP_THREADS, 0, cs>>>(in, count, (uint32_t)bits, pad, nbytes, reinterpret_cast<uint32_t*>(words_out));

@@ -541,3 +541,35 @@ def test_encode_division_and_floor_tricks_dense_sweep(fb):
             # the fused kernel (quad path) agrees too
             ct = _np(ctx.encode_encrypt(3, 1, fb.SCHEME_DOUBLE, _dev(x), codec, fb.NoiseSpec(u=_dev(u)), span))
             assert np.array_equal(ct, O.encrypt(KEY, 32, 8, 3, 1, "double", want)), (alpha, mode)
+
+
+def test_decode_division_sweep(fb):
+    """decode divides through RN(1/den) + two FMA corrections (library division when a layer's scale is
+    out of the guarded range): sweep element widths, client counts and alphas (incl. tiny / huge ones that
+    take the fallback) against the oracle, float64 bit patterns, standalone and fused with decrypt."""
+    rs = np.random.RandomState(77)
+    L = 40_003
+    for bits, wdt in ((32, np.uint32), (64, np.uint64)):
+        ctx = ctx_for(fb, bits)
+        span = fb.VectorSpan(L, 8)
+        for e, n, alpha in ((16, 3, 0.5938345), (16, 64, 0.0123), (8, 1, 7.25), (20, 10, 1e-3), (24, 1000, 3.0e5), (12, 7, 1e-200),
+                            (16, 5, 1e180), (1, 2, 0.1), (16, 4096, 2.0 ** -30), (23, 33, 1.0 / 3.0)):
+            top = min((1 << e) * n, (1 << min(bits, 63)) - 1)
+            v = rs.randint(0, top + 1, L, dtype=np.int64).astype(wdt)
+            v[:4] = (0, 1, top, top - 1)
+            codec = fb.CodecSpec(alpha=alpha, element_bits=e, n_clients=n)
+            want = O.unquantize(v, alpha, e, n)
+            got = _np(ctx.decode(_dev(v), codec, span))
+            assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (bits, e, n, alpha)
+            off = _np(ctx.decode(_dev(v)[1:], codec, fb.VectorSpan(L, 8, 1, L - 1)))   # not 16-byte aligned: scalar kernel
+            assert np.array_equal(off.view(np.uint64), want[1:].view(np.uint64)), (bits, e, n, alpha)
+    # fused with decrypt, lane-local and slab paths
+    for bits, n_jobs in ((32, 8), (20, 8)):
+        ctx = ctx_for(fb, bits)
+        span = fb.VectorSpan(L, n_jobs)
+        agg = rs.randint(0, 1 << 20, L, dtype=np.int64).astype(np.uint32)
+        for e, n, alpha in ((16, 3, 0.5938345), (12, 7, 1e-200), (16, 12, 41.5)):
+            codec = fb.CodecSpec(alpha=alpha, element_bits=e, n_clients=n)
+            p_want = O.decrypt(KEY, bits, n_jobs, 4, list(range(n)), "double", agg)
+            got = _np(ctx.decrypt_decode(4, [n], [0], _dev(agg), codec, span))
+            assert np.array_equal(got.view(np.uint64), O.unquantize(p_want, alpha, e, n).view(np.uint64)), (bits, e, n, alpha)

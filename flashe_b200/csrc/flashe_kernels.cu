@@ -710,7 +710,8 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     constexpr bool HAS_IN = (MODE == M_APPLY || MODE == M_ENCODE || MODE == M_DECODE);
     constexpr int PF = MMAX + 1;                 // pair iterations per item: ceil((64m + 2) / 64)
     constexpr uint32_t WB = WORDS * 4u;
-    constexpr bool QUAD_OK = (WORDS == 1 && MODE != M_SCATTER && MMAX == 4);   // 4-byte words and m == 4
+    constexpr bool QUAD_OK = (WORDS == 1 && MODE != M_SCATTER && MMAX <= 6);   // 4-byte words, m = 4 (b 25..32) or 5, 6 (b 20..25)
+    constexpr int NQ = (MMAX + 1) / 2;            // 16-byte element quads per lane and item: 64 m / 4 / 32, rounded up
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t y = 0x00010000u | (lane << 2);
     const uint32_t sbase = smem_window_base();
@@ -755,47 +756,53 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
       // through the slab, and all per-item geometry is a handful of additions.  The bounds are
       // computed once per unit.
       uint64_t wf_lo = 1, wf_hi = 0;
+      const uint32_t mm = MMAX == 4 ? 4u : m;                       // compile-time 4 in the m = 4 instantiation
+      const uint32_t item_elems = ITEM_BLOCKS * mm;
       if (QUAD_OK && io.quad) {
-          const uint64_t shift = 4ull * it.off;                     // e0(w) = cb - shift + 256 w
-          const uint64_t full_end = it.cb + (it.clen & ~3ull);      // end of the chunk's last whole block
+          const uint64_t shift = (uint64_t)mm * it.off;             // e0(w) = cb - shift + 64 m w
+          const uint64_t full_end = it.cb + (MMAX == 4 ? (it.clen & ~3ull) : (it.clen / mm) * mm);   // end of the chunk's last whole block
           const uint64_t hi_e = (full_end < g.end ? full_end : g.end) + shift;
           const uint64_t lo_e = (g.begin > it.cb ? g.begin : it.cb) + shift;   // w = 0 is lane-local only when off == 0
-          wf_lo = lo_e > it.cb ? (lo_e - it.cb + 255ull) >> 8 : 0;
-          wf_hi = hi_e > it.cb ? (hi_e - it.cb) >> 8 : 0;            // items w with 256 (w+1) <= hi_e - cb
+          wf_lo = lo_e > it.cb ? (lo_e - it.cb + item_elems - 1u) / item_elems : 0;
+          wf_hi = hi_e > it.cb ? (hi_e - it.cb) / item_elems : 0;    // items w with 64 m (w+1) <= hi_e - cb
           const uint64_t c0 = it.cb - it.off;                       // counter of item 0's (virtual) first block
           const uint64_t w32 = c0 < (1ull << 32) ? ((1ull << 32) - c0) >> 6 : 0;   // 64 (w+1) <= 2^32 - c0
           if (wf_hi > w32) wf_hi = w32;
       }
+      // m = 5, 6: the lane-major masks are turned element-major through the warp's slab (16-byte aligned part)
+      const uint32_t fslab = (slab + 15u) & ~15u;
       auto fast_item = [&](uint64_t w) {
         if constexpr (QUAD_OK) {
-          const uint64_t e0 = it.cb - 4ull * it.off + (w << 8);     // first global element of the item
+          const uint64_t e0 = it.cb - (uint64_t)mm * it.off + w * item_elems;   // first global element of the item
           const uint32_t ctr0 = (uint32_t)(it.cb - it.off) + ((uint32_t)w << 6);   // jzf_flashe.py:34 "(i + begin)"
           const uint64_t o0 = e0 - g.begin;
           const uint32_t qr = ALIGNED ? 0u : ((uint32_t)o0 & 3u);    // misalignment of the chunk in the buffers
-          const uint64_t qoff = o0 + 4u * lane;                     // block A's elements; block B: +128
-          const uint64_t j0 = e0 + 4u * lane;
+          const uint32_t nquads = item_elems >> 2;                  // 16 m; lane owns quads lane + 32 k
           const uint32_t ctrA = ctr0 + lane, ctrB = ctrA + 32u;
           const uint32_t win = ctr0 >> 8;                           // same for every counter of the item
           const bool stale = !cache_ok || win != cached_win;
           const uint32_t mk32 = Word<1>::mask(g.b);
           const bool one_seg = cd.nseg == 1;
           const bool one_rcp = one_seg && MODE == M_ENCODE && cd.seg[0].rcp_two_a != 0.0f;
-          uint32_t prev[NB][4];
+          uint32_t prev[NB][MMAX];
           const uint32_t n_iter_here = SHARE ? n_iter : 1u;          // without SHARE a unit serves exactly one client
           for (uint32_t cc = 0; cc < n_iter_here; ++cc) {
               const uint32_t c = SHARE ? (cc ? c_first + cc - 1 : 0) : c_first + cc;
               const bool emit = !SHARE || cc > 0;
-              uint32_t r[NB][4];
+              uint32_t r[NQ][4];
               if (HAS_IN && emit) {                                  // inputs first: their latency hides under the AES rounds
-                  const uint32_t* in = reinterpret_cast<const uint32_t*>(io.in) + (uint64_t)c * io.in_stride + qoff;
-                  ldg_quad(in, qr, r[0]);
-                  ldg_quad(in + 128, qr, r[1]);
+                  const uint32_t* in = reinterpret_cast<const uint32_t*>(io.in) + (uint64_t)c * io.in_stride + o0;
+#pragma unroll
+                  for (int k = 0; k < NQ; ++k) {
+                      const uint32_t q = lane + 32u * k;
+                      if (MMAX == 4 || q < nquads) ldg_quad(in + 4u * q, qr, r[k]);
+                  }
               }
-              uint32_t acc[NB][4];
+              uint32_t acc[NB][MMAX];
 #pragma unroll
               for (int h = 0; h < NB; ++h)
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) acc[h][k] = 0u;
+                  for (int k = 0; k < MMAX; ++k) acc[h][k] = 0u;
               uint32_t s_begin, s_count;
               if (!st.batch) { s_begin = 0; s_count = st.n; }
               else if (SHARE) { s_begin = cc; s_count = 1; }
@@ -818,27 +825,55 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                   }
                   uint32_t oa[4], ob[4];
                   aes256_x2w(ks, y, st.pre[sidx][0], wc, ctrA, ctrB, oa, ob);
-                  accumulate_slots<1, 4>(oa, g.b, 4u, sign, acc[0]);
-                  accumulate_slots<1, 4>(ob, g.b, 4u, sign, acc[1]);
+                  accumulate_slots<1, MMAX>(oa, g.b, mm, sign, acc[0]);
+                  accumulate_slots<1, MMAX>(ob, g.b, mm, sign, acc[1]);
               }
               if (SHARE) {                                           // acc = F(cc); mask of client cc-1 = prev - acc
 #pragma unroll
                   for (int h = 0; h < NB; ++h)
 #pragma unroll
-                      for (int k = 0; k < 4; ++k) {
+                      for (int k = 0; k < MMAX; ++k) {
                           const uint32_t cur = acc[h][k];
                           if (cc > 0) acc[h][k] = prev[h][k] - cur;
                           prev[h][k] = cur;
                       }
                   if (!emit) continue;
               }
+              if (MMAX != 4) {
+                  // lane-major -> element-major: block (lane + 32 h) holds elements [(lane + 32 h) m, +m).  Stride m
+                  // words (m = 5: odd; m = 6: written as 64-bit pairs, 16 lanes x 24 bytes hit 32 distinct banks):
+                  // conflict-free.  Read back as 16-byte quads.
+                  __syncwarp();                                      // the previous round's quads have been read
 #pragma unroll
-              for (int h = 0; h < NB; ++h) {
-                  const uint64_t o = qoff + 128u * h;
-                  const uint64_t j = j0 + 128u * h;
+                  for (int h = 0; h < NB; ++h) {
+                      const uint32_t a0 = fslab + (lane + 32u * h) * mm * 4u;
+                      if (mm == 6u) {
+#pragma unroll
+                          for (int k = 0; k + 1 < MMAX; k += 2)
+                              asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a0 + 4u * k), "r"(acc[h][k]), "r"(acc[h][k + 1]) : "memory");
+                      } else {
+#pragma unroll
+                          for (int k = 0; k < MMAX; ++k)
+                              if ((uint32_t)k < mm) sts32(a0 + 4u * k, acc[h][k]);
+                      }
+                  }
+                  __syncwarp();
+              }
+#pragma unroll
+              for (int h = 0; h < NQ; ++h) {
+                  const uint32_t q = lane + 32u * h;                 // this lane's h-th quad of the item
+                  if (MMAX != 4 && q >= nquads) break;
+                  const uint64_t o = o0 + 4u * q;
+                  const uint64_t j = e0 + 4u * q;
                   uint32_t mw[4];
+                  if (MMAX == 4) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) mw[k] = acc[h][k] & mk32;
+                      for (int k = 0; k < 4; ++k) mw[k] = acc[h < NB ? h : 0][k] & mk32;
+                  } else {
+                      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(mw[0]), "=r"(mw[1]), "=r"(mw[2]), "=r"(mw[3]) : "r"(fslab + 16u * q) : "memory");
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) mw[k] &= mk32;
+                  }
                   if (MODE == M_MASKS) {
                       stg_quad(reinterpret_cast<uint32_t*>(io.out) + o, qr, mw[0], mw[1], mw[2], mw[3]);
                   } else if (MODE == M_APPLY) {
@@ -859,21 +894,21 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                           noise_pair(nz, nz.stream + c, (j >> 1) + 1, u[1], u[2]);
                           noise_pair(nz, nz.stream + c, (j >> 1) + 2, u[3], hi);
                       }
-                      uint32_t q[4];
+                      uint32_t q4[4];
                       if (one_rcp) {                                 // single layer with a usable reciprocal (warp-uniform)
 #pragma unroll
-                          for (int k = 0; k < 4; ++k) q[k] = encode_one<true>(__uint_as_float(r[h][k]), u[k], cd.seg[0], cd.scale);
+                          for (int k = 0; k < 4; ++k) q4[k] = encode_one<true>(__uint_as_float(r[h][k]), u[k], cd.seg[0], cd.scale);
                       } else {
                           Seg sg = find_seg(cd, j);
 #pragma unroll
                           for (int k = 0; k < 4; ++k) {
                               if (k && !one_seg && j + k >= sg.end) sg = find_seg(cd, j + k);
-                              q[k] = encode_one(__uint_as_float(r[h][k]), u[k], sg, cd.scale);
+                              q4[k] = encode_one(__uint_as_float(r[h][k]), u[k], sg, cd.scale);
                           }
                       }
-                      if (io.aux) stg_quad(reinterpret_cast<uint32_t*>(io.aux) + (uint64_t)c * io.out_stride + o, qr, q[0], q[1], q[2], q[3]);
+                      if (io.aux) stg_quad(reinterpret_cast<uint32_t*>(io.aux) + (uint64_t)c * io.out_stride + o, qr, q4[0], q4[1], q4[2], q4[3]);
                       uint32_t* out = reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o;
-                      stg_quad(out, qr, (q[0] + mw[0]) & mk32, (q[1] + mw[1]) & mk32, (q[2] + mw[2]) & mk32, (q[3] + mw[3]) & mk32);
+                      stg_quad(out, qr, (q4[0] + mw[0]) & mk32, (q4[1] + mw[1]) & mk32, (q4[2] + mw[2]) & mk32, (q4[3] + mw[3]) & mk32);
                   } else if (MODE == M_DECODE) {
                       uint32_t pw[4];
                       double dv[4];

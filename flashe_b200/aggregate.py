@@ -57,6 +57,20 @@ def expand_to_dense(models, masks, total, int_bits, device=None):
     return out
 
 
+def aggregate_sparse(models, masks, total, int_bits, device=None):
+    """expand_to_dense (jzf_aggregator.py:150-165) of every upload followed by the element-wise reduce
+    (:421-430), fused: the n dense vectors are never built.  Same result as
+    aggregate(expand_to_dense(models, masks, total, int_bits), int_bits)."""
+    ctx = _ctx(int_bits, device)
+    compacts, indexes, zeros = [], [], []
+    for a, ma in zip(models, masks):
+        a = np.asarray(a, dtype=object)
+        zeros.append(int(a[-1]))
+        compacts.append(ctx.words_from_ints(a[:-1]))
+        indexes.append(torch.as_tensor(np.asarray(ma, dtype=np.int64)).to(ctx.device))
+    return ctx.ints_from_words(ctx.sparse_sum(compacts, indexes, int(total), zeros))
+
+
 def dynamic_masking(masks, total, device=None):
     """jzf_flashe_block.py:89-117: single = 2*sum|mask|; double = 2*single - 2*sum_i |mask_i ∩ mask_{i+1}|;
     choose single when single <= double.  Returns the dict the arbiter broadcasts plus the costs."""

@@ -1739,6 +1739,42 @@ static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom&
     return launch_stream_t<4, 1, MODE, false>(ctx, st, g, io, cd, nz, stream);
 }
 
+// dense[index[i]] += compact[i] - zero  (mod 2^b): one client's contribution to the sum of the expanded
+// vectors once `dense` holds the sum of every client's zero word (index sorted unique: no conflicts)
+template <int WORDS>
+__global__ void k_scatter_add(const typename Word<WORDS>::T* __restrict__ compact, const int64_t* __restrict__ index, uint64_t k,
+                              uint64_t total, typename Word<WORDS>::T zero, uint32_t b, typename Word<WORDS>::T* __restrict__ dense) {
+    typedef Word<WORDS> WT;
+    const typename WT::T mk = WT::mask(b);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t d = (uint64_t)index[i];
+        if (d < total) dense[d] = WT::band(WT::add(dense[d], WT::sub(compact[i], zero)), mk);
+    }
+}
+
+template <int WORDS>
+static int sparse_sum_t(flashe_ctx* ctx, const void* const* compacts, const int64_t* const* indexes, const uint64_t* ks,
+                        const void* zero_words, int n, uint64_t total, void* dense_out, cudaStream_t cs) {
+    typedef Word<WORDS> WT;
+    typedef typename WT::T word_t;
+    std::vector<word_t> zeros((size_t)n);                              // the caller's buffer need not be aligned
+    memcpy(zeros.data(), zero_words, sizeof(word_t) * (size_t)n);
+    const word_t mk = WT::mask((uint32_t)ctx->int_bits);
+    word_t zsum = WT::zero();
+    for (int c = 0; c < n; ++c) zsum = WT::band(WT::add(zsum, WT::band(zeros[c], mk)), mk);
+    k_fill<WORDS><<<grid_1d(ctx, total, 256, 16), 256, 0, cs>>>((word_t*)dense_out, total, zsum);
+    int launches = 1;
+    for (int c = 0; c < n; ++c) {
+        if (!ks[c]) continue;
+        k_scatter_add<WORDS><<<grid_1d(ctx, ks[c], 256, 16), 256, 0, cs>>>((const word_t*)compacts[c], indexes[c], ks[c], total,
+                                                                           WT::band(zeros[c], mk), (uint32_t)ctx->int_bits, (word_t*)dense_out);
+        ++launches;
+    }
+    g_launches.fetch_add(launches);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
@@ -2163,6 +2199,21 @@ int flashe_batch_unpack(flashe_ctx* ctx, const void* words, uint64_t nwords, int
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return FLASHE_OK;
+}
+
+int flashe_sparse_sum(flashe_ctx* ctx, const void* const* compacts, const int64_t* const* indexes, const uint64_t* ks,
+                      const void* zero_words, int n_clients, uint64_t total, void* dense_out, void* stream) {
+    ENTER(ctx);
+    if (n_clients < 1 || !ks || !zero_words) return fail(FLASHE_EINVAL, "need n_clients >= 1, ks and zero_words");
+    if (total == 0) return FLASHE_OK;
+    if (!dense_out) return fail(FLASHE_EINVAL, "dense_out is NULL");
+    for (int c = 0; c < n_clients; ++c) {
+        if (ks[c] > total) return fail(FLASHE_EINVAL, "k exceeds total");
+        if (ks[c] && (!compacts || !indexes || !compacts[c] || !indexes[c])) return fail(FLASHE_EINVAL, "NULL compact / index buffer");
+    }
+    if (ctx->words == 1) return sparse_sum_t<1>(ctx, compacts, indexes, ks, zero_words, n_clients, total, dense_out, cs);
+    if (ctx->words == 2) return sparse_sum_t<2>(ctx, compacts, indexes, ks, zero_words, n_clients, total, dense_out, cs);
+    return sparse_sum_t<4>(ctx, compacts, indexes, ks, zero_words, n_clients, total, dense_out, cs);
 }
 
 int flashe_sparse_expand(flashe_ctx* ctx, const void* compact, const int64_t* index, uint64_t k, uint64_t total, const void* zero_word,

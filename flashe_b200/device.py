@@ -314,6 +314,24 @@ class DeviceContext(object):
         _cabi.check(self.lib.flashe_sparse_expand(self._h, compact.data_ptr(), index.data_ptr(), k, total, zb, out.data_ptr(), self._stream()))
         return out
 
+    def sparse_sum(self, compacts, indexes, total, zeros, out=None):
+        """Sum over clients of expand_to_dense(compact_c, index_c, zero_c) mod 2^b without the n dense
+        vectors (fill with the sum of the zero words, one scatter-add per client)."""
+        n = len(compacts)
+        if n < 1 or len(indexes) != n or len(zeros) != n:
+            raise ValueError("compacts, indexes and zeros must have the same non-zero length")
+        for a, ix in zip(compacts, indexes):
+            self._check(ix, torch.int64, ix.numel(), "index")
+            self._check_words(a, ix.numel(), "compact")
+        out = self.empty_words(total) if out is None else self._check_words(out, total, "out")
+        cp = (C.c_void_p * n)(*[t.data_ptr() for t in compacts])
+        ip = (C.c_void_p * n)(*[t.data_ptr() for t in indexes])
+        ks = (C.c_uint64 * n)(*[t.numel() for t in indexes])
+        zb = b"".join(int(z).to_bytes(self.word_bytes, "little") for z in zeros)
+        zbuf = (C.c_uint8 * len(zb)).from_buffer_copy(zb)
+        _cabi.check(self.lib.flashe_sparse_sum(self._h, cp, ip, ks, zbuf, n, total, out.data_ptr(), self._stream()))
+        return out
+
     def sparse_apply_masks(self, it, prf_idx, sign, span: VectorSpan, index, dense):
         self._check(index, torch.int64, span.n, "index")
         _cabi.check(self.lib.flashe_sparse_apply_masks(self._h, it & 0xFFFFFFFF, _i32(prf_idx), _i32(sign), len(prf_idx),

@@ -221,6 +221,16 @@ int flashe_batch_unpack(flashe_ctx* ctx, const void* words, uint64_t nwords, int
 int flashe_sparse_expand(flashe_ctx* ctx, const void* compact, const int64_t* index, uint64_t k,
                          uint64_t total, const void* zero_word, void* dense_out, void* stream);
 
+/* The arbiter's sum of the expanded uploads (expand_to_dense for every client, then the element-wise
+ * reduce of proc/jzf_aggregator.py:421-430) without materialising the n dense vectors:
+ *   dense_out[j] = sum_c (j in index_c ? compact_c[.] : zero_c)   mod 2^int_bits
+ * computed as fill(sum_c zero_c) followed by one scatter-add of (compact_c - zero_c) per client: O(total +
+ * sum k_c) instead of O(n * total) bytes.  compacts / indexes: HOST arrays of n device pointers (words
+ * and int64_t, index sorted unique); ks: HOST uint64_t[n]; zero_words: HOST array of n words. */
+int flashe_sparse_sum(flashe_ctx* ctx, const void* const* compacts, const int64_t* const* indexes,
+                      const uint64_t* ks, const void* zero_words, int n_clients, uint64_t total,
+                      void* dense_out, void* stream);
+
 /* Sparse single-mask decrypt term (sp/jzf_flashe.py:315-343, 528-535): regenerate
  * sum_k sign[k]*F(iter, prf_idx[k]) over the COMPACT positions described by `span` (total_len = k) and
  * add it into dense[index[i]]. */

@@ -111,6 +111,9 @@ def sparse_c4(dev, total=50_000_000, n=32, bits=32, n_jobs=16, frac=0.01):
         return a
 
     sum_ms = timed(server_sum, steps=2, warmup=1)
+    fused = ctx.empty_words(total)
+    fused_ms = timed(lambda: ctx.sparse_sum([ct] * n, idxs, total, [32768] * n, out=fused), steps=3, warmup=1)
+    assert torch.equal(fused.view(torch.int32), server_sum().view(torch.int32))
     p = acc.clone()
 
     def unmask():
@@ -121,8 +124,8 @@ def sparse_c4(dev, total=50_000_000, n=32, bits=32, n_jobs=16, frac=0.01):
     ov_ms = timed(lambda: ctx.sparse_overlap(idxs, total), steps=2, warmup=1)
     print(json.dumps({"config": "C4 index-sparse top-1% of 50M, 32 clients, single masking", "total": total, "k": k, "clients": n, "int_bits": bits,
                       "client_topk_sparsify_ms": topk_ms, "client_encode_encrypt_compact_ms": enc_ms,
-                      "server_expand_and_sum_32_clients_ms": sum_ms, "server_unmask_32_clients_ms": unmask_ms, "overlap_counts_ms": ov_ms,
-                      "client_elements_per_s_dense_equivalent": n * total / ((n * (topk_ms + enc_ms) + sum_ms + unmask_ms) * 1e-3)}), flush=True)
+                      "server_expand_and_sum_32_clients_ms": sum_ms, "server_fused_sparse_sum_32_clients_ms": fused_ms, "server_unmask_32_clients_ms": unmask_ms, "overlap_counts_ms": ov_ms,
+                      "client_elements_per_s_dense_equivalent": n * total / ((n * (topk_ms + enc_ms) + fused_ms + unmask_ms) * 1e-3)}), flush=True)
 
 
 def main():

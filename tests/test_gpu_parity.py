@@ -573,3 +573,37 @@ def test_decode_division_sweep(fb):
             p_want = O.decrypt(KEY, bits, n_jobs, 4, list(range(n)), "double", agg)
             got = _np(ctx.decrypt_decode(4, [n], [0], _dev(agg), codec, span))
             assert np.array_equal(got.view(np.uint64), O.unquantize(p_want, alpha, e, n).view(np.uint64)), (bits, e, n, alpha)
+
+
+@pytest.mark.parametrize("bits", [32, 20, 64, 120])
+def test_sparse_sum_equals_expand_then_aggregate(fb, bits):
+    """flashe_sparse_sum (fill with the sum of the zero words + one scatter-add per client) against the
+    reference's own order of operations: expand_to_dense per client, then the element-wise reduce."""
+    ctx = ctx_for(fb, bits)
+    rs = np.random.RandomState(bits)
+    total, n = 200_003, 7
+    compacts, indexes, zeros, dense = [], [], [], []
+    for c in range(n):
+        k = int(rs.randint(0, 5000)) if c else 0                           # one client with an empty upload
+        idx = np.sort(rs.choice(total, size=k, replace=False)).astype(np.int64)
+        vals = [int.from_bytes(rs.bytes(16), "little") & ((1 << bits) - 1) for _ in range(k)]
+        zero = int.from_bytes(rs.bytes(16), "little") & ((1 << bits) - 1)
+        w = ctx.words_from_ints(np.array(vals, dtype=object)) if k else ctx.empty_words(0)
+        ix = _dev(idx)
+        compacts.append(w); indexes.append(ix); zeros.append(zero)
+        dense.append(ctx.sparse_expand(w, ix, total, zero))
+    signed = {torch.uint32: torch.int32, torch.uint64: torch.int64}
+    want = dense[0]
+    for d in dense[1:]:
+        want = ctx.aggregate(torch.stack([want.view(signed[want.dtype]), d.view(signed[d.dtype])]).view(want.dtype))
+    got = ctx.sparse_sum(compacts, indexes, total, zeros)
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+    # python big-int cross-check on a few positions
+    gi = ctx.ints_from_words(got)
+    for j in (0, int(indexes[1][0]) if indexes[1].numel() else 1, total - 1):
+        s_ = 0
+        for c in range(n):
+            pos = np.searchsorted(_np(indexes[c]), j)
+            hit = pos < indexes[c].numel() and int(indexes[c][pos]) == j
+            s_ += int(ctx.ints_from_words(compacts[c][pos:pos + 1])[0]) if hit else zeros[c]
+        assert int(gi[j]) == s_ % (1 << bits), j

@@ -1166,6 +1166,7 @@ __global__ void k_encode(const float* __restrict__ x, const typename Word<WORDS>
 __global__ void __launch_bounds__(256)
 k_encode_premasked_v4(const uint4* __restrict__ x, const uint4* __restrict__ mask, uint64_t begin, uint64_t nvec, uint32_t mk,
                       const __grid_constant__ CodecDev cd, const __grid_constant__ NoiseDev nz, uint4* __restrict__ ct_out) {
+    const bool one_seg = cd.nseg == 1, one_rcp = one_seg && cd.seg[0].rcp_two_a != 0.0f;
     for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t j = begin + 4ull * v;
         const uint4 xv = __ldcs(x + v), mv = __ldcs(mask + v);
@@ -1179,11 +1180,16 @@ k_encode_premasked_v4(const uint4* __restrict__ x, const uint4* __restrict__ mas
         }
         const uint32_t xr[4] = {xv.x, xv.y, xv.z, xv.w};
         uint32_t q[4];
-        Seg sg = find_seg(cd, j);
+        if (one_rcp) {                                                 // single layer with a usable reciprocal (uniform)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k && j + k >= sg.end) sg = find_seg(cd, j + k);
-            q[k] = encode_one(__uint_as_float(xr[k]), u[k], sg, cd.scale);
+            for (int k = 0; k < 4; ++k) q[k] = encode_one<true>(__uint_as_float(xr[k]), u[k], cd.seg[0], cd.scale);
+        } else {
+            Seg sg = find_seg(cd, j);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k && !one_seg && j + k >= sg.end) sg = find_seg(cd, j + k);
+                q[k] = encode_one(__uint_as_float(xr[k]), u[k], sg, cd.scale);
+            }
         }
         __stcs(ct_out + v, make_uint4((q[0] + mv.x) & mk, (q[1] + mv.y) & mk, (q[2] + mv.z) & mk, (q[3] + mv.w) & mk));
     }
@@ -1688,10 +1694,12 @@ template <int WORDS, int MMAX, int MODE, bool SHARE, bool ALIGNED = false>
 static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,
                            const NoiseDev& nz, cudaStream_t stream) {
     auto kern = k_stream<WORDS, MMAX, MODE, SHARE, ALIGNED>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in shared-memory size is a per-device property of the function: set it once per device
+    static std::atomic<uint64_t> attr_set{0};
+    const uint64_t dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_set.load(std::memory_order_acquire) & dev_bit)) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        attr_set = true;
+        attr_set.fetch_or(dev_bit, std::memory_order_release);
     }
     const uint64_t items = (st.batch && !io.share) ? g.S_cnt * io.n_clients : g.S_cnt;
     if (items == 0) return FLASHE_OK;

@@ -868,14 +868,13 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                   uint32_t mw[4];
                   if (MMAX == 4) {
 #pragma unroll
-                      for (int k = 0; k < 4; ++k) mw[k] = acc[h < NB ? h : 0][k] & mk32;
+                      for (int k = 0; k < 4; ++k) mw[k] = acc[h < NB ? h : 0][k];
                   } else {
                       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(mw[0]), "=r"(mw[1]), "=r"(mw[2]), "=r"(mw[3]) : "r"(fslab + 16u * q) : "memory");
-#pragma unroll
-                      for (int k = 0; k < 4; ++k) mw[k] &= mk32;
                   }
+                  // (mw is reduced mod 2^b together with the sum below; only the mask output needs it by itself)
                   if (MODE == M_MASKS) {
-                      stg_quad(reinterpret_cast<uint32_t*>(io.out) + o, qr, mw[0], mw[1], mw[2], mw[3]);
+                      stg_quad(reinterpret_cast<uint32_t*>(io.out) + o, qr, mw[0] & mk32, mw[1] & mk32, mw[2] & mk32, mw[3] & mk32);
                   } else if (MODE == M_APPLY) {
                       uint32_t* out = reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o;
                       stg_quad(out, qr, (r[h][0] + mw[0]) & mk32, (r[h][1] + mw[1]) & mk32, (r[h][2] + mw[2]) & mk32, (r[h][3] + mw[3]) & mk32);
@@ -1344,7 +1343,7 @@ __device__ __forceinline__ Xfer xfer_of(uint64_t lo, uint32_t H, uint32_t b) {
 template <int WORDS>
 __global__ void __launch_bounds__(PK_THREADS)
 k_aggregate_packed(const typename Word<WORDS>::T* __restrict__ cts, uint64_t stride, int n, uint64_t count, uint32_t b,
-                   uint32_t carry_in, typename Word<WORDS>::T* __restrict__ out, uint32_t* __restrict__ desc_out) {
+                   uint32_t carry_in, typename Word<WORDS>::T* __restrict__ out, uint32_t* __restrict__ desc_out, int vec_ok) {
     typedef Word<WORDS> WT;
     __shared__ Xfer warp_x[PK_THREADS / 32];
     __shared__ uint32_t tile_cin;
@@ -1360,15 +1359,38 @@ k_aggregate_packed(const typename Word<WORDS>::T* __restrict__ cts, uint64_t str
         uint64_t lo_[PK_ELEMS]; uint32_t H_[PK_ELEMS];
         Xfer mine; mine.A = 0; mine.T = 0;  // identity: cin -> cin is not representable; track validity
         bool have = false;
+        // 4-byte words, count and every row 16-byte aligned: the thread's four elements are one 128-bit
+        // column of the [n, count] matrix; walk the rows with independent streaming loads in flight
+        const bool quad = WORDS == 1 && vec_ok && base + PK_ELEMS <= count;
+        if (quad) {
+            const uint4* col = reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(cts) + (count - PK_ELEMS - base));
+            const uint64_t sv = stride >> 2;
+            uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll 8
+            for (int c = 0; c < n; ++c) {
+                const uint4 v = __ldcs(col + (uint64_t)c * sv);
+                s0 += v.w; s1 += v.z; s2 += v.y; s3 += v.x;          // element e sits `e` places before the end: .w first
+            }
+            const uint64_t mkb = (1ull << b) - 1ull;
+            lo_[0] = s0 & mkb; H_[0] = (uint32_t)(s0 >> b); lo_[1] = s1 & mkb; H_[1] = (uint32_t)(s1 >> b);
+            lo_[2] = s2 & mkb; H_[2] = (uint32_t)(s2 >> b); lo_[3] = s3 & mkb; H_[3] = (uint32_t)(s3 >> b);
 #pragma unroll
-        for (int e = 0; e < PK_ELEMS; ++e) {
-            const uint64_t back = base + e;  // distance from the end
-            if (back < count) {
-                digit_sum<WORDS>(cts, stride, n, count - 1 - back, b, lo_[e], H_[e]);
+            for (int e = 0; e < PK_ELEMS; ++e) {
                 Xfer f = xfer_of(lo_[e], H_[e], b);
                 mine = have ? xfer_compose(f, mine) : f;
                 have = true;
-            } else { lo_[e] = 0; H_[e] = 0; }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < PK_ELEMS; ++e) {
+                const uint64_t back = base + e;  // distance from the end
+                if (back < count) {
+                    digit_sum<WORDS>(cts, stride, n, count - 1 - back, b, lo_[e], H_[e]);
+                    Xfer f = xfer_of(lo_[e], H_[e], b);
+                    mine = have ? xfer_compose(f, mine) : f;
+                    have = true;
+                } else { lo_[e] = 0; H_[e] = 0; }
+            }
         }
         // Identity handling: a thread with no elements must pass the carry through unchanged.  That
         // only happens in the last (partial) tile, where such threads sit AFTER all real ones in scan
@@ -1415,17 +1437,28 @@ k_aggregate_packed(const typename Word<WORDS>::T* __restrict__ cts, uint64_t str
         // carry into this lane's first element: exclusive prefix within the warp
         Xfer ex; ex.A = __shfl_up_sync(0xffffffffu, incl.A, 1); ex.T = __shfl_up_sync(0xffffffffu, incl.T, 1);
         uint32_t c = lane == 0 ? cin : xfer_apply(ex, cin);
+        if (quad && vec_ok > 1) {                                          // out is 16-byte aligned too: one 128-bit store
+            uint32_t r[PK_ELEMS];
 #pragma unroll
-        for (int e = 0; e < PK_ELEMS; ++e) {
-            const uint64_t back = base + e;
-            if (back < count) {
-                uint64_t s = lo_[e] + c;   // lo < 2^b, c small
-                uint32_t extra;
-                if (b >= 64) { extra = (s < lo_[e]) ? 1u : 0u; }
-                else { extra = (uint32_t)(s >> b); s &= mk64; }
-                if (WORDS == 1) reinterpret_cast<uint32_t*>(out)[count - 1 - back] = (uint32_t)s;
-                else reinterpret_cast<uint64_t*>(out)[count - 1 - back] = s;
-                c = H_[e] + extra;
+            for (int e = 0; e < PK_ELEMS; ++e) {
+                const uint64_t sum = lo_[e] + c;                           // lo < 2^b <= 2^32, c small
+                r[e] = (uint32_t)(sum & mk64);
+                c = H_[e] + (uint32_t)(sum >> b);
+            }
+            __stcs(reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(out) + (count - PK_ELEMS - base)), make_uint4(r[3], r[2], r[1], r[0]));
+        } else {
+#pragma unroll
+            for (int e = 0; e < PK_ELEMS; ++e) {
+                const uint64_t back = base + e;
+                if (back < count) {
+                    uint64_t s = lo_[e] + c;   // lo < 2^b, c small
+                    uint32_t extra;
+                    if (b >= 64) { extra = (s < lo_[e]) ? 1u : 0u; }
+                    else { extra = (uint32_t)(s >> b); s &= mk64; }
+                    if (WORDS == 1) reinterpret_cast<uint32_t*>(out)[count - 1 - back] = (uint32_t)s;
+                    else reinterpret_cast<uint64_t*>(out)[count - 1 - back] = s;
+                    c = H_[e] + extra;
+                }
             }
         }
         // Range descriptor for element-range shards (desc_out = {carry out for the given carry_in,
@@ -2100,8 +2133,10 @@ int flashe_aggregate(flashe_ctx* ctx, const void* cts, uint64_t stride, int n, u
         const uint64_t ntiles = ceil_div(count, (uint64_t)PK_THREADS * PK_ELEMS);
         uint64_t cap = (uint64_t)ctx->num_sms * 8;
         const int grid = (int)(ntiles < cap ? ntiles : cap);
-        if (ctx->words == 1) k_aggregate_packed<1><<<grid, PK_THREADS, 0, cs>>>((const uint32_t*)cts, stride, n, count, b, carry_in, (uint32_t*)out, carry_out);
-        else k_aggregate_packed<2><<<grid, PK_THREADS, 0, cs>>>((const uint64_t*)cts, stride, n, count, b, carry_in, (uint64_t*)out, carry_out);
+        // 1: rows are 128-bit columns; 2: the output too
+        const int vec_ok = (ctx->words == 1 && (count & 3u) == 0 && (stride & 3u) == 0 && aligned16(cts)) ? (aligned16(out) ? 2 : 1) : 0;
+        if (ctx->words == 1) k_aggregate_packed<1><<<grid, PK_THREADS, 0, cs>>>((const uint32_t*)cts, stride, n, count, b, carry_in, (uint32_t*)out, carry_out, vec_ok);
+        else k_aggregate_packed<2><<<grid, PK_THREADS, 0, cs>>>((const uint64_t*)cts, stride, n, count, b, carry_in, (uint64_t*)out, carry_out, 0);
         g_launches.fetch_add(1);
     }
     CUDA_TRY(cudaGetLastError());

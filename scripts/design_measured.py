@@ -62,6 +62,15 @@ try:
               n2["value"] / 1e9, n2["ms_per_step"], n2["e2e"]["value"] / 1e9))
 except Exception:
     pass
+try:
+    n8 = json.load(open(P("r1p_bench_n8.json")))
+    t += ("\n8 GPUs (`profiles/r1p_bench_n8.json`, n_jobs = %d on that box): %.1f G client-elements/s (%.2f ms per round: encode %.2f, "
+          "aggregate %.2f, decrypt+decode %.2f) = %.2fx one GPU; e2e %.1f G (host memory / PCIe bound); precomputed-mask schedule %.0f G; NCCL parity "
+          "run on 8 ranks `profiles/r1p_multi_check_n8.json`.\n" % (
+              n8["config"]["n_jobs"], n8["value"] / 1e9, n8["ms_per_step"], n8["phases"]["encode_encrypt_ms"], n8["phases"]["aggregate_ms"],
+              n8["phases"]["decrypt_decode_ms"], n8["value"] / d["value"], n8["e2e"]["value"] / 1e9, n8["variants"]["precomputed_masks"]["value"] / 1e9))
+except Exception:
+    pass
 if cfg:
     g = lambda k: next(x for n, x in cfg.items() if n.startswith(k))
     c1, c2, c2b, b20, b24, b64, c3, c4 = (g("C1"), g("C2 2.5M"), g("C2 at"), g("25M elements, 10 clients, int_bits 20"),

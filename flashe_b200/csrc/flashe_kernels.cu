@@ -712,6 +712,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     constexpr uint32_t WB = WORDS * 4u;
     constexpr bool QUAD_OK = (WORDS == 1 && MODE != M_SCATTER && MMAX <= 6);   // 4-byte words, m = 4 (b 25..32) or 5, 6 (b 20..25)
     constexpr int NQ = (MMAX + 1) / 2;            // 16-byte element quads per lane and item: 64 m / 4 / 32, rounded up
+    constexpr bool W4_OK = (WORDS == 4 && (MODE == M_MASKS || MODE == M_APPLY));   // 16-byte words (the shipped 120-bit batch mode): m = 1
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t y = 0x00010000u | (lane << 2);
     const uint32_t sbase = smem_window_base();
@@ -756,9 +757,9 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
       // through the slab, and all per-item geometry is a handful of additions.  The bounds are
       // computed once per unit.
       uint64_t wf_lo = 1, wf_hi = 0;
-      const uint32_t mm = MMAX == 4 ? 4u : m;                       // compile-time 4 in the m = 4 instantiation
+      const uint32_t mm = (WORDS == 1 && MMAX == 4) ? 4u : (WORDS == 4 ? 1u : m);   // compile-time where the instantiation fixes it
       const uint32_t item_elems = ITEM_BLOCKS * mm;
-      if (QUAD_OK && io.quad) {
+      if ((QUAD_OK || W4_OK) && io.quad) {
           const uint64_t shift = (uint64_t)mm * it.off;             // e0(w) = cb - shift + 64 m w
           const uint64_t full_end = it.cb + (MMAX == 4 ? (it.clen & ~3ull) : (it.clen / mm) * mm);   // end of the chunk's last whole block
           const uint64_t hi_e = (full_end < g.end ? full_end : g.end) + shift;
@@ -926,8 +927,65 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
           cached_win = win;                                          // every stream of the unit now has this window cached
         }
       };
+      // 16-byte words, m = 1: a lane's AES block masks exactly one word (words lane and lane + 32 of the item)
+      auto fast_item_w4 = [&](uint64_t w) {
+        if constexpr (W4_OK) {
+          const uint64_t e0 = it.cb - it.off + (w << 6);            // first word (= first block) of the item
+          const uint32_t ctr0 = (uint32_t)(it.cb - it.off) + ((uint32_t)w << 6);
+          const uint64_t o0 = e0 - g.begin;
+          const uint32_t ctrA = ctr0 + lane, ctrB = ctrA + 32u;
+          const uint32_t win = ctr0 >> 8;
+          const bool stale = !cache_ok || win != cached_win;
+          const u128 mk128 = Word<4>::mask(g.b);
+          const uint32_t c = c_first;                               // (SHARE exists for the encode mode only)
+          uint32_t r[NB][4];
+          if (HAS_IN) {
+              const u128* in = reinterpret_cast<const u128*>(io.in) + (uint64_t)c * io.in_stride + o0 + lane;
+              ldg_v4(in, r[0][0], r[0][1], r[0][2], r[0][3]);
+              ldg_v4(in + 32, r[1][0], r[1][1], r[1][2], r[1][3]);
+          }
+          u128 acc[NB][1];
+          acc[0][0] = Word<4>::zero(); acc[1][0] = Word<4>::zero();
+          uint32_t s_begin, s_count;
+          if (!st.batch) { s_begin = 0; s_count = st.n; }
+          else { s_begin = c; s_count = st.dbl ? 2u : 1u; }
+          for (uint32_t si = 0; si < s_count; ++si) {
+              const uint32_t sidx = s_begin + si;
+              const int sign = st.batch ? (si == 0 ? +1 : -1) : st.sign[sidx];
+              WinC wc;
+              const uint32_t slot = wcache + sidx * 16u;
+              if (stale) {
+                  wc = window_consts(ks, y, PRE_OF(sidx), ctr0);
+                  if (cache_ok) {
+                      if (lane == 0) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"(wc.c0), "r"(wc.c1), "r"(wc.c2), "r"(wc.c3) : "memory");
+                      __syncwarp();
+                  }
+              } else {
+                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wc.c0), "=r"(wc.c1), "=r"(wc.c2), "=r"(wc.c3) : "r"(slot) : "memory");
+              }
+              uint32_t oa[4], ob[4];
+              aes256_x2w(ks, y, st.pre[sidx][0], wc, ctrA, ctrB, oa, ob);
+              accumulate_slots<4, 1>(oa, g.b, 1u, sign, acc[0]);
+              accumulate_slots<4, 1>(ob, g.b, 1u, sign, acc[1]);
+          }
+#pragma unroll
+          for (int h = 0; h < NB; ++h) {
+              u128 v = acc[h][0];
+              if (MODE == M_APPLY) {
+                  u128 x;
+                  x.lo = ((uint64_t)r[h][1] << 32) | r[h][0]; x.hi = ((uint64_t)r[h][3] << 32) | r[h][2];
+                  v = Word<4>::add(x, v);
+              }
+              v = Word<4>::band(v, mk128);
+              u128* out = reinterpret_cast<u128*>(io.out) + (MODE == M_APPLY ? (uint64_t)c * io.out_stride : 0ull) + o0 + lane + 32u * h;
+              stg_v4(out, (uint32_t)v.lo, (uint32_t)(v.lo >> 32), (uint32_t)v.hi, (uint32_t)(v.hi >> 32));
+          }
+          cached_win = win;
+        }
+      };
       for (uint32_t sub = 0; sub < nsub; ++sub, ++it.w) {
         if (QUAD_OK && it.w >= wf_lo && it.w < wf_hi) { fast_item(it.w); continue; }
+        if (W4_OK && it.w >= wf_lo && it.w < wf_hi) { fast_item_w4(it.w); continue; }
         const uint64_t blk0 = it.w ? it.w * ITEM_BLOCKS - it.off : 0;  // first block of the item
         const uint32_t nblk = it.w ? ITEM_BLOCKS : ITEM_BLOCKS - it.off;
         if (blk0 * m >= it.clen) break;                                // past the chunk's last item
@@ -1756,8 +1814,9 @@ static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom&
     const int b = ctx->int_bits;
     IoDev io = io_in;
     // 128-bit fast path preconditions (4-byte words): every row of every buffer starts 16-byte aligned
-    io.quad = (ctx->words == 1 && MODE != M_SCATTER && aligned16(io.in) && aligned16(io.out) && aligned16(io.aux) &&
-               aligned16(io.outf) && (io.n_clients <= 1 || ((io.in_stride | io.out_stride) & 3ull) == 0)) ? 1u : 0u;
+    // (16-byte words: every word is aligned as soon as the base pointers are)
+    io.quad = (MODE != M_SCATTER && aligned16(io.in) && aligned16(io.out) && aligned16(io.aux) && aligned16(io.outf) &&
+               ((ctx->words == 1 && (io.n_clients <= 1 || ((io.in_stride | io.out_stride) & 3ull) == 0)) || ctx->words == 4)) ? 1u : 0u;
     if constexpr (MODE == M_ENCODE) {
         if (io.share) {
             if (b <= 32) {

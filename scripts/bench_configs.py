@@ -51,6 +51,40 @@ def dense_round(name, L, n, bits, n_jobs, dev):
                       "g_aes_blocks_per_s": (2 * n + 2) * -(-L // m) / (ms * 1e-3) / 1e9}), flush=True)
 
 
+def batched_round(dev, L=25_000_000, n=10, n_jobs=16, bits=120, element_bits=16):
+    """The shipped batch configuration (int_bits 120, batch: true): encode -> 6 lanes per 120-bit word
+    (jzf_quantize.py:162-185) -> encrypt (one AES block per word and stream) -> aggregate -> decrypt ->
+    unbatch -> decode."""
+    ctx = fb.DeviceContext(KEY, bits, dev)
+    ctx32 = fb.DeviceContext(KEY, 32, dev)
+    factor = (n - 1).bit_length()
+    bs = bits // (element_bits + factor)
+    nw = -(-L // bs)
+    span_e, span_w = fb.VectorSpan(L, n_jobs), fb.VectorSpan(nw, n_jobs)
+    codec = fb.CodecSpec(alpha=ALPHA, element_bits=element_bits, n_clients=n)
+    x = torch.randn(n, L, device=dev) * 0.1
+    cts = ctx.empty_words(nw, rows=n)
+
+    def rnd():
+        for c in range(n):
+            q = ctx32.encode(x[c], codec, fb.NoiseSpec(seed=7, stream=c), span_e)
+            w = ctx.batch_pack(q, element_bits, factor)
+            ctx.encrypt(0, c, fb.SCHEME_DOUBLE, w, span_w, out=cts[c])
+        agg = ctx.aggregate(cts, fb.AGG_ELEMENTWISE)
+        p = ctx.decrypt(0, [n], [0], agg, span_w)
+        ctx32.decode(ctx.batch_unpack(p, element_bits, factor)[:L].contiguous(), codec, span_e)
+
+    def enc_only():
+        for c in range(n):
+            ctx.encrypt(0, c, fb.SCHEME_DOUBLE, cts[c], span_w, out=cts[c])
+
+    ms = timed(rnd, steps=3, warmup=2)
+    enc_ms = timed(enc_only, steps=3, warmup=1)
+    print(json.dumps({"config": "batched: 25M elements as 120-bit words (6 lanes), 10 clients, full round", "elements": L, "words": nw, "clients": n,
+                      "int_bits": bits, "n_jobs": n_jobs, "ms_per_round": ms, "client_elements_per_s": n * L / (ms * 1e-3),
+                      "encrypt_only_ms_10_clients": enc_ms, "encrypt_g_aes_blocks_per_s": 2 * n * nw / (enc_ms * 1e-3) / 1e9}), flush=True)
+
+
 def precompute_c3(dev, L=25_000_000, rounds=16, n=10, bits=20, n_jobs=16):
     """C3: one client fills the combined masks of 16 future rounds, then the online round of each
     (encode + add of the stored mask); the server decrypts under 20 % dropout (8 survivors, 3 runs)."""
@@ -138,6 +172,7 @@ def main():
     dense_round("25M elements, 10 clients, int_bits 20 (C3-sized dense round)", 25_000_000, 10, 20, n_jobs, dev)
     dense_round("25M elements, 10 clients, int_bits 24", 25_000_000, 10, 24, n_jobs, dev)
     dense_round("25M elements, 10 clients, int_bits 64", 25_000_000, 10, 64, n_jobs, dev)
+    batched_round(dev, n_jobs=n_jobs)
     precompute_c3(dev, n_jobs=n_jobs)
     sparse_c4(dev, n_jobs=n_jobs)
 

@@ -84,6 +84,14 @@ if cfg:
     t += ("| 25 M x 10 clients, b = 20 / 24 / 64, full round | %.2f / %.2f / %.2f ms = %.1f / %.1f / %.1f G AES blocks/s "
           "(22.6 / 24.4 / 33.0 before m = 5, 6 joined the lane-local loop) |\n" % (
               b20["ms_per_round"], b24["ms_per_round"], b64["ms_per_round"], b20["g_aes_blocks_per_s"], b24["g_aes_blocks_per_s"], b64["g_aes_blocks_per_s"]))
+    try:
+        bt = g("batched")
+        t += ("| shipped batch mode: 25 M elements as 120-bit words (6 lanes of 20 bit), 10 clients, full round (encode, lane pack, encrypt, "
+              "aggregate, decrypt, unpack, decode as separate launches) | %.2f ms, %.1f G client-elements/s; encrypt alone %.2f ms = %.1f G AES "
+              "blocks/s (one block per word and stream, lane-local 16-byte words) |\n" % (
+                  bt["ms_per_round"], bt["client_elements_per_s"] / 1e9, bt["encrypt_only_ms_10_clients"], bt["encrypt_g_aes_blocks_per_s"]))
+    except StopIteration:
+        pass
     t += ("| C3: mask precomputation, 16 rounds x 25 M, b = 20 | fill %.2f ms (%.1f G AES blocks/s, 1.6 GB ring); online encode + add of "
           "the stored masks, 16 rounds: %.2f ms (%.2f TB/s); decrypt+decode under dropout (3 runs = 6 streams): %.2f ms |\n" % (
               c3["fill_ms"], c3["fill_g_aes_blocks_per_s"], c3["online_ms_16_rounds"], c3["online_gbs"] / 1e3, c3["decrypt_decode_3_runs_ms"]))

@@ -406,6 +406,8 @@ def test_flashecipher_sparse_single(fb, golden):
     dense = agg_mod.expand_to_dense(uploads, masks, total, b)
     agg = agg_mod.aggregate(dense, b)
     assert [int(v) for v in agg] == [int(v) for v in golden.words("sparse_agg", b)]
+    fused = agg_mod.aggregate_sparse(uploads, masks, total, b)              # expand + reduce without the dense vectors
+    assert [int(v) for v in fused] == [int(v) for v in golden.words("sparse_agg", b)]
     cipher = FlasheCipher(b, mask="single", n_jobs=nj)
     cipher.generate_prp_seed(KEY); cipher.set_iter_index(it)
     cipher.masks = masks; cipher.total = total

@@ -5,14 +5,18 @@
 // per-entry-point citations and DESIGN.md for the layout/roofline discussion.
 //
 // Kernel families
-//   k_stream<WORDS, MMAX, MODE>   persistent, one CTA per SM, 1024 threads.  A warp owns a "warp
-//       item" = 32 consecutive AES blocks of one reference chunk (lane <-> block, so lane <-> m
-//       consecutive elements).  Lanes run AES-256 from a bank-conflict-free shared-memory T-table
-//       (4 tables x 32 replicas = 128 KB, one LDS + one PRMT per lookup), reduce the signed streams
-//       into a combined mask in registers, transpose it through a per-warp shared slab and then walk
-//       the item's elements with fully coalesced global loads/stores, fusing encode / decode.
+//   k_stream<WORDS, MMAX, MODE, SHARE, ALIGNED>   persistent, one 512-thread CTA per SM.  A warp owns
+//       work units of consecutive "items" of one reference chunk; an item = 64 AES blocks whose
+//       counters share their upper 56 bits (lane <-> blocks lane and lane + 32).  Lanes run AES-256
+//       from a bank-conflict-free shared-memory T-table (4 tables x 32 replicas = 128 KB, one LDS + one
+//       PRMT per lookup, 197 lookups per block: round 1 hoisted on the host, rounds 1-2 factored per
+//       counter window), reduce the signed streams into a combined mask in registers and apply it,
+//       fused with encode / decode.  Full items of the common layouts (4-byte words with m = 4, 5, 6;
+//       16-byte words) run in a lane-local loop with 16-byte global accesses; everything else (edge
+//       items, other widths, unaligned buffers) goes through a per-warp slab and element pairs.
 //   elementwise kernels           aggregate (element-wise and packed-carry), premasked add, encode,
-//       decode, lane batching, sparse expand, noise.
+//       decode, lane batching, sparse expand / sum, noise.
+//   flashe_wire.cu                wire bit-packing, layer-wise top-k sparsify, per-layer statistics.
 //
 // No tensor cores: nothing here is a dense contraction (integer PRF + modular adds).
 #include <cuda_runtime.h>

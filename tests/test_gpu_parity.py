@@ -609,3 +609,29 @@ def test_sparse_sum_equals_expand_then_aggregate(fb, bits):
             hit = pos < indexes[c].numel() and int(indexes[c][pos]) == j
             s_ += int(ctx.ints_from_words(compacts[c][pos:pos + 1])[0]) if hit else zeros[c]
         assert int(gi[j]) == s_ % (1 << bits), j
+
+
+@pytest.mark.parametrize("bits", [32, 20, 24, 64, 120])
+def test_item_geometry_every_counter_offset(fb, bits):
+    """Items are cut on multiples of 64 of the AES counter (chunk begin + block): with an odd chunk length
+    and many chunks, chunk begins take every value mod 64 and mod 256, items straddle counter windows at
+    every position, and chunks end with every partial-item length.  Masks, encrypt and shards against
+    the oracle."""
+    ctx = ctx_for(fb, bits)
+    n_jobs = 131
+    L = n_jobs * 5003 + 17                       # chunks of 5004 / 5003 elements
+    it = 11
+    want = O.masks(KEY, bits, n_jobs, it, [5, 6], [1, -1], L)
+    full = fb.VectorSpan(L, n_jobs)
+    assert np.array_equal(_np(ctx.masks(it, [5, 6], [1, -1], full)), want)
+    for a, e in ((4 * 777, 4 * 777 + 100_000), (12345, 12345 + 77_777), (L - 50_001, L)):
+        got = _np(ctx.masks(it, [5, 6], [1, -1], fb.VectorSpan(L, n_jobs, a, e - a)))
+        assert np.array_equal(got, want[a:e]), (a, e)
+    rs = np.random.RandomState(bits)
+    if bits <= 32:
+        q = rs.randint(0, 65536, L).astype(np.uint32)
+    elif bits <= 64:
+        q = rs.randint(0, 65536, L).astype(np.uint64)
+    else:
+        q = np.stack([rs.randint(0, 2 ** 62, L).astype(np.uint64), rs.randint(0, 2 ** 50, L).astype(np.uint64)], axis=1)
+    assert np.array_equal(_np(ctx.encrypt(it, 5, fb.SCHEME_DOUBLE, _dev(q), full)), O.encrypt(KEY, bits, n_jobs, it, 5, "double", q))

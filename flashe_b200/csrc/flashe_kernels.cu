@@ -486,12 +486,31 @@ __device__ __forceinline__ void accumulate_slots(const uint32_t o[4], uint32_t b
             for (int k = 0; k < 4 && k < MMAX; ++k) acc[k] += (uint32_t)sign * o[3 - k];
             return;
         }
+        // The accumulators are only meaningful mod 2^b (every consumer masks the final sum), so the bits a
+        // slot word carries above bit b need not be cleared here.
         uint32_t v0 = o[3], v1 = o[2], v2 = o[1], v3 = o[0];
-        const uint32_t mk = Word<1>::mask(b);
+        const uint32_t sg = (uint32_t)sign;
+        if (MMAX >= 6 && b == 20u) {             // the shipped un-batched width: slots at bits 0, 20, .. 100
+            acc[0] += sg * v0;
+            acc[1] += sg * __funnelshift_r(v0, v1, 20);
+            acc[2] += sg * (v1 >> 8);
+            acc[3] += sg * __funnelshift_r(v1, v2, 28);
+            acc[MMAX >= 6 ? 4 : 0] += sg * __funnelshift_r(v2, v3, 16);
+            acc[MMAX >= 6 ? 5 : 0] += sg * (v3 >> 4);           // (index guarded for the narrower instantiations)
+            return;
+        }
+        if (MMAX >= 5 && b == 24u) {             // slots at bits 0, 24, 48, 72, 96
+            acc[0] += sg * v0;
+            acc[1] += sg * __funnelshift_r(v0, v1, 24);
+            acc[2] += sg * __funnelshift_r(v1, v2, 16);
+            acc[3] += sg * __funnelshift_r(v2, v3, 8);
+            acc[MMAX >= 5 ? 4 : 0] += sg * v3;
+            return;
+        }
 #pragma unroll
         for (int k = 0; k < MMAX; ++k) {
             if ((uint32_t)k < m) {
-                acc[k] += (uint32_t)sign * (v0 & mk);
+                acc[k] += sg * v0;
                 v0 = __funnelshift_rc(v0, v1, b);
                 v1 = __funnelshift_rc(v1, v2, b);
                 v2 = __funnelshift_rc(v2, v3, b);

@@ -736,6 +736,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     constexpr bool QUAD_OK = (WORDS == 1 && MODE != M_SCATTER && MMAX <= 6);   // 4-byte words, m = 4 (b 25..32) or 5, 6 (b 20..25)
     constexpr int NQ = (MMAX + 1) / 2;            // 16-byte element quads per lane and item: 64 m / 4 / 32, rounded up
     constexpr bool W4_OK = (WORDS == 4 && (MODE == M_MASKS || MODE == M_APPLY));   // 16-byte words (the shipped 120-bit batch mode): m = 1
+    constexpr bool W2_OK = (WORDS == 2 && MODE != M_SCATTER);                      // 8-byte words with m = 2 (b = 43..64)
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t y = 0x00010000u | (lane << 2);
     const uint32_t sbase = smem_window_base();
@@ -782,7 +783,10 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
       uint64_t wf_lo = 1, wf_hi = 0;
       const uint32_t mm = (WORDS == 1 && MMAX == 4) ? 4u : (WORDS == 4 ? 1u : m);   // compile-time where the instantiation fixes it
       const uint32_t item_elems = ITEM_BLOCKS * mm;
-      if ((QUAD_OK || W4_OK) && io.quad) {
+      // (8-byte words: only m = 2, and only chunks that start on an even element of an even shard, so that a
+      //  block is one aligned 16-byte pair and one noise pair)
+      const bool w2_here = W2_OK && m == 2u && ((it.cb | g.begin) & 1ull) == 0ull;
+      if ((QUAD_OK || W4_OK || w2_here) && io.quad) {
           const uint64_t shift = (uint64_t)mm * it.off;             // e0(w) = cb - shift + 64 m w
           const uint64_t full_end = it.cb + (MMAX == 4 ? (it.clen & ~3ull) : (it.clen / mm) * mm);   // end of the chunk's last whole block
           const uint64_t hi_e = (full_end < g.end ? full_end : g.end) + shift;
@@ -1006,8 +1010,117 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
           cached_win = win;
         }
       };
+      // 8-byte words, m = 2: a lane's AES block masks one aligned pair of elements
+      auto fast_item_w2 = [&](uint64_t w) {
+        if constexpr (W2_OK) {
+          const uint64_t e0 = it.cb - 2ull * it.off + (w << 7);     // first element of the item (even)
+          const uint32_t ctr0 = (uint32_t)(it.cb - it.off) + ((uint32_t)w << 6);
+          const uint64_t o0 = e0 - g.begin;
+          const uint32_t ctrA = ctr0 + lane, ctrB = ctrA + 32u;
+          const uint32_t win = ctr0 >> 8;
+          const bool stale = !cache_ok || win != cached_win;
+          const uint64_t mk64 = Word<2>::mask(g.b);
+          const bool one_seg = cd.nseg == 1;
+          uint64_t prev[NB][2];
+          const uint32_t n_iter_here = SHARE ? n_iter : 1u;
+          for (uint32_t cc = 0; cc < n_iter_here; ++cc) {
+              const uint32_t c = SHARE ? (cc ? c_first + cc - 1 : 0) : c_first + cc;
+              const bool emit = !SHARE || cc > 0;
+              uint32_t r[NB][4];                                     // two 8-byte words, or two floats in r[h][0..1]
+              if (HAS_IN && emit) {
+                  if (MODE == M_ENCODE) {
+                      const float* in = reinterpret_cast<const float*>(io.in) + (uint64_t)c * io.in_stride + o0 + 2u * lane;
+                      asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r[0][0]), "=r"(r[0][1]) : "l"(in));
+                      asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r[1][0]), "=r"(r[1][1]) : "l"(in + 64));
+                  } else {
+                      const uint64_t* in = reinterpret_cast<const uint64_t*>(io.in) + (uint64_t)c * io.in_stride + o0 + 2u * lane;
+                      ldg_v4(in, r[0][0], r[0][1], r[0][2], r[0][3]);
+                      ldg_v4(in + 64, r[1][0], r[1][1], r[1][2], r[1][3]);
+                  }
+              }
+              uint64_t acc[NB][MMAX];
+#pragma unroll
+              for (int h = 0; h < NB; ++h)
+#pragma unroll
+                  for (int k = 0; k < MMAX; ++k) acc[h][k] = 0ull;
+              uint32_t s_begin, s_count;
+              if (!st.batch) { s_begin = 0; s_count = st.n; }
+              else if (SHARE) { s_begin = cc; s_count = 1; }
+              else { s_begin = c; s_count = st.dbl ? 2u : 1u; }
+              for (uint32_t si = 0; si < s_count; ++si) {
+                  const uint32_t sidx = s_begin + si;
+                  const int sign = st.batch ? (si == 0 ? +1 : -1) : st.sign[sidx];
+                  WinC wc;
+                  const uint32_t slot = wcache + sidx * 16u;
+                  if (stale) {
+                      wc = window_consts(ks, y, PRE_OF(sidx), ctr0);
+                      if (cache_ok) {
+                          if (lane == 0) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"(wc.c0), "r"(wc.c1), "r"(wc.c2), "r"(wc.c3) : "memory");
+                          __syncwarp();
+                      }
+                  } else {
+                      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wc.c0), "=r"(wc.c1), "=r"(wc.c2), "=r"(wc.c3) : "r"(slot) : "memory");
+                  }
+                  uint32_t oa[4], ob[4];
+                  aes256_x2w(ks, y, st.pre[sidx][0], wc, ctrA, ctrB, oa, ob);
+                  accumulate_slots<2, MMAX>(oa, g.b, 2u, sign, acc[0]);
+                  accumulate_slots<2, MMAX>(ob, g.b, 2u, sign, acc[1]);
+              }
+              if (SHARE) {
+#pragma unroll
+                  for (int h = 0; h < NB; ++h)
+#pragma unroll
+                      for (int k = 0; k < 2; ++k) {
+                          const uint64_t cur = acc[h][k];
+                          if (cc > 0) acc[h][k] = prev[h][k] - cur;
+                          prev[h][k] = cur;
+                      }
+                  if (!emit) continue;
+              }
+#pragma unroll
+              for (int h = 0; h < NB; ++h) {
+                  const uint64_t o = o0 + 2u * lane + 64u * h;
+                  const uint64_t j = e0 + 2u * lane + 64u * h;
+                  const uint64_t m0 = acc[h][0], m1 = acc[h][1];
+                  uint64_t w0, w1;                                   // the two output words
+                  if (MODE == M_MASKS) {
+                      w0 = m0 & mk64; w1 = m1 & mk64;
+                  } else if (MODE == M_ENCODE) {
+                      double u0, u1;
+                      if (nz.u) { const double* up = nz.u + (uint64_t)c * nz.u_stride + o; u0 = up[0]; u1 = up[1]; }
+                      else noise_pair(nz, nz.stream + c, j >> 1, u0, u1);
+                      Seg sg = find_seg(cd, j);
+                      const uint32_t q0 = encode_one(__uint_as_float(r[h][0]), u0, sg, cd.scale);
+                      if (!one_seg && j + 1 >= sg.end) sg = find_seg(cd, j + 1);
+                      const uint32_t q1 = encode_one(__uint_as_float(r[h][1]), u1, sg, cd.scale);
+                      if (io.aux) {
+                          uint32_t* qo = reinterpret_cast<uint32_t*>(io.aux) + (uint64_t)c * io.out_stride + o;
+                          asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(qo), "r"(q0), "r"(q1) : "memory");
+                      }
+                      w0 = ((uint64_t)q0 + m0) & mk64; w1 = ((uint64_t)q1 + m1) & mk64;
+                  } else {                                           // M_APPLY, M_DECODE
+                      w0 = ((((uint64_t)r[h][1] << 32) | r[h][0]) + m0) & mk64;
+                      w1 = ((((uint64_t)r[h][3] << 32) | r[h][2]) + m1) & mk64;
+                  }
+                  if (MODE == M_DECODE) {
+                      Seg sg = find_seg(cd, j);
+                      const double d0 = decode_one((double)w0, sg.two_an, cd.den, cd.den_rcp, sg.an);
+                      if (!one_seg && j + 1 >= sg.end) sg = find_seg(cd, j + 1);
+                      const double d1 = decode_one((double)w1, sg.two_an, cd.den, cd.den_rcp, sg.an);
+                      if (io.aux) stg_v4(reinterpret_cast<uint64_t*>(io.aux) + o, (uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
+                      stg_d2(io.outf + o, d0, d1);
+                  } else {
+                      uint64_t* out = reinterpret_cast<uint64_t*>(io.out) + (MODE == M_MASKS ? 0ull : (uint64_t)c * io.out_stride) + o;
+                      stg_v4(out, (uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
+                  }
+              }
+          }
+          cached_win = win;
+        }
+      };
       for (uint32_t sub = 0; sub < nsub; ++sub, ++it.w) {
         if (QUAD_OK && it.w >= wf_lo && it.w < wf_hi) { fast_item(it.w); continue; }
+        if (W2_OK && it.w >= wf_lo && it.w < wf_hi) { fast_item_w2(it.w); continue; }
         if (W4_OK && it.w >= wf_lo && it.w < wf_hi) { fast_item_w4(it.w); continue; }
         const uint64_t blk0 = it.w ? it.w * ITEM_BLOCKS - it.off : 0;  // first block of the item
         const uint32_t nblk = it.w ? ITEM_BLOCKS : ITEM_BLOCKS - it.off;
@@ -1839,7 +1952,8 @@ static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom&
     // 128-bit fast path preconditions (4-byte words): every row of every buffer starts 16-byte aligned
     // (16-byte words: every word is aligned as soon as the base pointers are)
     io.quad = (MODE != M_SCATTER && aligned16(io.in) && aligned16(io.out) && aligned16(io.aux) && aligned16(io.outf) &&
-               ((ctx->words == 1 && (io.n_clients <= 1 || ((io.in_stride | io.out_stride) & 3ull) == 0)) || ctx->words == 4)) ? 1u : 0u;
+               ((ctx->words == 1 && (io.n_clients <= 1 || ((io.in_stride | io.out_stride) & 3ull) == 0)) ||
+                (ctx->words == 2 && (io.n_clients <= 1 || ((io.in_stride | io.out_stride) & 1ull) == 0)) || ctx->words == 4)) ? 1u : 0u;
     if constexpr (MODE == M_ENCODE) {
         if (io.share) {
             if (b <= 32) {

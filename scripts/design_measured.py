@@ -82,7 +82,7 @@ if cfg:
     t += "| C2: 2.5 M x 10 clients, b = 20, full round | %.3f ms, %.1f G client-elements/s (%.3f ms at b = 32) |\n" % (
         c2["ms_per_round"], c2["client_elements_per_s"] / 1e9, c2b["ms_per_round"])
     t += ("| 25 M x 10 clients, b = 20 / 24 / 64, full round | %.2f / %.2f / %.2f ms = %.1f / %.1f / %.1f G AES blocks/s "
-          "(22.6 / 24.4 / 33.0 before m = 5, 6 joined the lane-local loop) |\n" % (
+          "(22.6 / 24.4 / 33.0 before these widths joined the lane-local loop) |\n" % (
               b20["ms_per_round"], b24["ms_per_round"], b64["ms_per_round"], b20["g_aes_blocks_per_s"], b24["g_aes_blocks_per_s"], b64["g_aes_blocks_per_s"]))
     try:
         bt = g("batched")

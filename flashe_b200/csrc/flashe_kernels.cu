@@ -633,6 +633,12 @@ __device__ __noinline__ void aes256_block_slow(const KeySched& ks, uint32_t y, u
 #define FLASHE_AES_UNROLL 5
 #endif
 #define AES_ROUNDS_UNROLL FLASHE_PRAGMA(unroll FLASHE_AES_UNROLL)
+#ifndef FLASHE_AES_UNROLL_M6
+// The m = 5, 6 instantiation has three unrolled quad bodies in its hot loop; with the rounds unrolled as
+// well it lost 12 % of its issue slots to instruction fetch (ncu stall_no_inst).  Rolled rounds there:
+// 25M x 10 clients at int_bits 20, encode 2.60 -> 2.45 ms.
+#define FLASHE_AES_UNROLL_M6 1
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // k_stream: persistent, one 512-thread CTA per SM (128 KB of tables + per-warp slabs).
@@ -669,6 +675,7 @@ __device__ __forceinline__ WinC window_consts(const KeySched& ks, uint32_t y, Pr
 // Two AES-256 blocks of the SAME stream and the same counter window (counters w3a, w3b; words 0-2 shared,
 // word 2 == 0) computed in one instruction stream: twice the independent lookups per round, so the
 // round-boundary latency (LDS ~30 clk + LOP3) of one block hides under the other's.
+template <int UNROLL = FLASHE_AES_UNROLL>
 __device__ __forceinline__ void aes256_x2w(const KeySched& ks, uint32_t y, uint32_t pre_p0, WinC c, uint32_t w3a, uint32_t w3b,
                                            uint32_t oa[4], uint32_t ob[4]) {
     uint32_t a0, a1, a2, a3, b0, b1, b2, b3, p0, p1, p2, p3, q0, q1, q2, q3;
@@ -685,7 +692,7 @@ __device__ __forceinline__ void aes256_x2w(const KeySched& ks, uint32_t y, uint3
     q2 = T0(b2) ^ T1(b3) ^ T2(b0) ^ T3(b1) ^ ks.rk[14];
     p3 = T0(a3) ^ T1(a0) ^ T2(a1) ^ T3(a2) ^ ks.rk[15];
     q3 = T0(b3) ^ T1(b0) ^ T2(b1) ^ T3(b2) ^ ks.rk[15];
-    AES_ROUNDS_UNROLL
+#pragma unroll UNROLL
     for (int r = 4; r < 14; r += 2) {                                         // rounds 4..13
         // both round keys of the iteration as two 128-bit constant-bank loads (the rolled loop indexes them)
         const uint4 k0 = *reinterpret_cast<const uint4*>(&ks.rk[4 * r]), k1 = *reinterpret_cast<const uint4*>(&ks.rk[4 * r + 4]);
@@ -852,7 +859,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wc.c0), "=r"(wc.c1), "=r"(wc.c2), "=r"(wc.c3) : "r"(slot) : "memory");
                   }
                   uint32_t oa[4], ob[4];
-                  aes256_x2w(ks, y, st.pre[sidx][0], wc, ctrA, ctrB, oa, ob);
+                  aes256_x2w<(MMAX == 4 ? FLASHE_AES_UNROLL : FLASHE_AES_UNROLL_M6)>(ks, y, st.pre[sidx][0], wc, ctrA, ctrB, oa, ob);
                   accumulate_slots<1, MMAX>(oa, g.b, mm, sign, acc[0]);
                   accumulate_slots<1, MMAX>(ob, g.b, mm, sign, acc[1]);
               }

@@ -25,7 +25,7 @@ t += ("Workload = BASELINE config 5 on one GPU: L = 100 M float32, n = 64 client
       "n_jobs = %d (the box's `cpu_count()`), device noise.  Clocks %d MHz, throttle reasons %s.  Files:\n"
       "`profiles/%s_bench.json`, `%s_bench_reference_arm.json`, `%s_launches.csv` (ncu launch list),\n"
       "`%s_ncu_encode_full_size_summary.csv` (ncu --set full of the timed-size encode launch), `%s_rows.jsonl`,\n"
-      "`%s_pytest_gpu.log` (GPU parity tests), `r1k_*` (2 GPUs).\n\n" % (
+      "`%s_pytest_gpu.log` (GPU parity tests), `r1x_*` (2 and 4 GPUs), `r1p_*` (8 GPUs).\n\n" % (
           d["config"]["n_jobs"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"] or "none", tag, tag, tag, tag, tag, tag))
 t += "| Phase | ms | Rate | Bound |\n|---|---|---|---|\n"
 t += ("| encode+encrypt, 64 clients (1 launch) | %.1f | %.1f G AES blocks/s = %.0f %% of the 197-lookup LDS ceiling (%.0f %% of the "
@@ -55,13 +55,15 @@ t += "| reference CPU path (Python port, %d cores, 3 clients x 1 M sample of the
 t += ("\nOther chunk layouts (same round, `--n-jobs`): n_jobs = 24 (chunks start at every residue mod 4) 70.2 G\n"
       "client-elements/s with the lane-local path on 64/32-bit pieces, against 56.9 G when such chunks took the slab path\n"
       "(`profiles/r1f_bench_njobs*.json` and the A/B runs named in the commit log).\n")
-try:
-    n2 = json.load(open(P("r1k_bench_n2.json")))
-    t += ("\n2 GPUs (element-range shards, no data-path collective; `profiles/r1k_bench_n2.json`, n_jobs = 24 on that box): "
-          "%.1f G client-elements/s (%.1f ms per round), e2e %.1f G; NCCL parity run `profiles/r1k_multi_check_n2.json`.\n" % (
-              n2["value"] / 1e9, n2["ms_per_step"], n2["e2e"]["value"] / 1e9))
-except Exception:
-    pass
+for ng in (2, 4):
+    try:
+        nn = json.load(open(P("r1x_bench_n%d.json" % ng)))
+        t += ("\n%d GPUs (element-range shards, no data-path collective; `profiles/r1x_bench_n%d.json`, n_jobs = %d on that box%s): "
+              "%.1f G client-elements/s (%.1f ms per round) = %.2fx one GPU, e2e %.1f G; NCCL parity run `profiles/r1x_multi_check_n%d.json`.\n" % (
+                  ng, ng, nn["config"]["n_jobs"], " (chunks start at every residue mod 4)" if nn["config"]["n_jobs"] % 8 and (100_000_000 // nn["config"]["n_jobs"]) % 4 else "",
+                  nn["value"] / 1e9, nn["ms_per_step"], nn["value"] / d["value"], nn["e2e"]["value"] / 1e9, ng))
+    except Exception:
+        pass
 try:
     n8 = json.load(open(P("r1p_bench_n8.json")))
     t += ("\n8 GPUs (`profiles/r1p_bench_n8.json`, n_jobs = %d on that box): %.1f G client-elements/s (%.2f ms per round: encode %.2f, "

@@ -55,12 +55,18 @@ t += "| reference CPU path (Python port, %d cores, 3 clients x 1 M sample of the
 t += ("\nOther chunk layouts (same round, `--n-jobs`): n_jobs = 24 (chunks start at every residue mod 4) 70.2 G\n"
       "client-elements/s with the lane-local path on 64/32-bit pieces, against 56.9 G when such chunks took the slab path\n"
       "(`profiles/r1f_bench_njobs*.json` and the A/B runs named in the commit log).\n")
+def aligned4(L, nj):
+    """every reference chunk starts on a multiple of 4 elements (the ALIGNED kernel instantiation)"""
+    dd, rr = divmod(L, nj)
+    return (rr <= 1 or (dd + 1) % 4 == 0) and (rr * (dd + 1)) % 4 == 0 and (dd % 4 == 0 or nj - rr <= 1)
+
+
 for ng in (2, 4):
     try:
         nn = json.load(open(P("r1x_bench_n%d.json" % ng)))
         t += ("\n%d GPUs (element-range shards, no data-path collective; `profiles/r1x_bench_n%d.json`, n_jobs = %d on that box%s): "
               "%.1f G client-elements/s (%.1f ms per round) = %.2fx one GPU, e2e %.1f G; NCCL parity run `profiles/r1x_multi_check_n%d.json`.\n" % (
-                  ng, ng, nn["config"]["n_jobs"], " (chunks start at every residue mod 4)" if nn["config"]["n_jobs"] % 8 and (100_000_000 // nn["config"]["n_jobs"]) % 4 else "",
+                  ng, ng, nn["config"]["n_jobs"], "" if aligned4(nn["config"]["elements"], nn["config"]["n_jobs"]) else ": odd chunk lengths, the lane-local path runs on 64/32-bit pieces, 70 G per GPU",
                   nn["value"] / 1e9, nn["ms_per_step"], nn["value"] / d["value"], nn["e2e"]["value"] / 1e9, ng))
     except Exception:
         pass

@@ -15,7 +15,7 @@ LIB_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIB_DIR, "libflashe_b200.so")
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "--shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
+              "--shared", "-Xcompiler", "-fPIC", "-cudart", "static", "--threads", "0"]
 
 
 def nvcc_path():

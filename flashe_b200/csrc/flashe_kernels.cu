@@ -742,6 +742,9 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     constexpr uint32_t WB = WORDS * 4u;
     constexpr bool QUAD_OK = (WORDS == 1 && MODE != M_SCATTER && MMAX <= 6);   // 4-byte words, m = 4 (b 25..32) or 5, 6 (b 20..25)
     constexpr int NQ = (MMAX + 1) / 2;            // 16-byte element quads per lane and item: 64 m / 4 / 32, rounded up
+    // m = 4, chunk starts off a 16-byte boundary: instead of 64/32-bit pieces the lanes own the memory-ALIGNED
+    // quads and receive the 1-3 mask words that belong to the neighbouring block by shuffle (see fast_item)
+    constexpr bool SHIFT_OK = (WORDS == 1 && MMAX == 4 && !ALIGNED && !SHARE && MODE != M_SCATTER);
     constexpr bool W4_OK = (WORDS == 4 && (MODE == M_MASKS || MODE == M_APPLY));   // 16-byte words (the shipped 120-bit batch mode): m = 1
     constexpr bool W2_OK = (WORDS == 2 && MODE != M_SCATTER);                      // 8-byte words with m = 2 (b = 43..64)
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -793,7 +796,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
       // (8-byte words: only m = 2, and only chunks that start on an even element of an even shard, so that a
       //  block is one aligned 16-byte pair and one noise pair)
       const bool w2_here = W2_OK && m == 2u && ((it.cb | g.begin) & 1ull) == 0ull;
-      if ((QUAD_OK || W4_OK || w2_here) && io.quad) {
+      if ((QUAD_OK || W4_OK || w2_here) && io.quad && !(SHIFT_OK && (g.begin & 1ull))) {
           const uint64_t shift = (uint64_t)mm * it.off;             // e0(w) = cb - shift + 64 m w
           const uint64_t full_end = it.cb + (MMAX == 4 ? (it.clen & ~3ull) : (it.clen / mm) * mm);   // end of the chunk's last whole block
           const uint64_t hi_e = (full_end < g.end ? full_end : g.end) + shift;
@@ -806,12 +809,25 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
       }
       // m = 5, 6: the lane-major masks are turned element-major through the warp's slab (16-byte aligned part)
       const uint32_t fslab = (slab + 15u) & ~15u;
+      // shifted mode (SHIFT_OK, misaligned chunk): the unit's lane-local items [wA, wBx) form one run; the last
+      // qr mask words of an item travel to the next item in lane 31's `carry` registers
+      const uint64_t wA = it.w > wf_lo ? it.w : wf_lo, wBx = it.w + nsub < wf_hi ? it.w + nsub : wf_hi;
+      uint32_t carry0 = 0u, carry1 = 0u, carry2 = 0u;
       auto fast_item = [&](uint64_t w) {
         if constexpr (QUAD_OK) {
           const uint64_t e0 = it.cb - (uint64_t)mm * it.off + w * item_elems;   // first global element of the item
           const uint32_t ctr0 = (uint32_t)(it.cb - it.off) + ((uint32_t)w << 6);   // jzf_flashe.py:34 "(i + begin)"
           const uint64_t o0 = e0 - g.begin;
-          const uint32_t qr = ALIGNED ? 0u : ((uint32_t)o0 & 3u);    // misalignment of the chunk in the buffers
+          const uint32_t qr0 = ALIGNED ? 0u : ((uint32_t)o0 & 3u);   // misalignment of the chunk in the buffers
+          // Shifted mode: quads start qr0 elements BEFORE the item (aligned in memory, aligned noise pairs); quad
+          // q's first qr0 mask words come from the block before it.  Quad 0 of the run's first item is partial
+          // (lane 0 handles its own elements one by one), and so are the qr0 elements after the run's last quad.
+          const bool shifted = SHIFT_OK && qr0 != 0u;
+          const bool run_first = shifted && w == wA, run_last = shifted && w + 1 == wBx;
+          // alignment switch of the 16-byte accesses: with SHIFT_OK every quad is aligned (qr0 != 0 => shifted),
+          // which removes the 64/32-bit piece code from this instantiation's hot loop
+          const uint32_t qr = SHIFT_OK ? 0u : qr0;
+          const uint64_t o0q = shifted ? o0 - qr0 : o0, e0q = shifted ? e0 - qr0 : e0;
           const uint32_t nquads = item_elems >> 2;                  // 16 m; lane owns quads lane + 32 k
           const uint32_t ctrA = ctr0 + lane, ctrB = ctrA + 32u;
           const uint32_t win = ctr0 >> 8;                           // same for every counter of the item
@@ -826,11 +842,11 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
               const bool emit = !SHARE || cc > 0;
               uint32_t r[NQ][4];
               if (HAS_IN && emit) {                                  // inputs first: their latency hides under the AES rounds
-                  const uint32_t* in = reinterpret_cast<const uint32_t*>(io.in) + (uint64_t)c * io.in_stride + o0;
+                  const uint32_t* in = reinterpret_cast<const uint32_t*>(io.in) + (uint64_t)c * io.in_stride + o0q;
 #pragma unroll
                   for (int k = 0; k < NQ; ++k) {
                       const uint32_t q = lane + 32u * k;
-                      if (MMAX == 4 || q < nquads) ldg_quad(in + 4u * q, qr, r[k]);
+                      if ((MMAX == 4 || q < nquads) && !(run_first && q == 0u)) ldg_quad(in + 4u * q, qr, r[k]);
                   }
               }
               uint32_t acc[NB][MMAX];
@@ -894,12 +910,44 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                   }
                   __syncwarp();
               }
+              uint32_t e4[4] = {0u, 0u, 0u, 0u};                     // shifted mode: the words of the run's edge elements
+              if constexpr (SHIFT_OK) {
+                  if (shifted) {
+                      const bool head = run_first && lane == 0u;     // lane 0: its block A; lane 31: its block B
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) e4[k] = head ? acc[0][k] : acc[1][k];
+                      const uint32_t srcl = (lane + 31u) & 31u;      // every lane reads its left neighbour, lane 0 reads lane 31
+                      const bool l31 = lane == 31u;                  // ... which forwards the tail of the block BEFORE lane 0's
+#define ROT(own, before) __shfl_sync(0xffffffffu, l31 ? (before) : (own), srcl)
+                      uint32_t n0[4], n1[4];
+                      if (qr0 == 1u) {
+                          n0[0] = ROT(acc[0][3], carry0); n1[0] = ROT(acc[1][3], acc[0][3]);
+                          n0[1] = acc[0][0]; n0[2] = acc[0][1]; n0[3] = acc[0][2];
+                          n1[1] = acc[1][0]; n1[2] = acc[1][1]; n1[3] = acc[1][2];
+                          carry0 = acc[1][3];
+                      } else if (qr0 == 2u) {
+                          n0[0] = ROT(acc[0][2], carry0); n0[1] = ROT(acc[0][3], carry1);
+                          n1[0] = ROT(acc[1][2], acc[0][2]); n1[1] = ROT(acc[1][3], acc[0][3]);
+                          n0[2] = acc[0][0]; n0[3] = acc[0][1]; n1[2] = acc[1][0]; n1[3] = acc[1][1];
+                          carry0 = acc[1][2]; carry1 = acc[1][3];
+                      } else {
+                          n0[0] = ROT(acc[0][1], carry0); n0[1] = ROT(acc[0][2], carry1); n0[2] = ROT(acc[0][3], carry2);
+                          n1[0] = ROT(acc[1][1], acc[0][1]); n1[1] = ROT(acc[1][2], acc[0][2]); n1[2] = ROT(acc[1][3], acc[0][3]);
+                          n0[3] = acc[0][0]; n1[3] = acc[1][0];
+                          carry0 = acc[1][1]; carry1 = acc[1][2]; carry2 = acc[1][3];
+                      }
+#undef ROT
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) { acc[0][k] = n0[k]; acc[1][k] = n1[k]; }
+                  }
+              }
 #pragma unroll
               for (int h = 0; h < NQ; ++h) {
                   const uint32_t q = lane + 32u * h;                 // this lane's h-th quad of the item
                   if (MMAX != 4 && q >= nquads) break;
-                  const uint64_t o = o0 + 4u * q;
-                  const uint64_t j = e0 + 4u * q;
+                  if (SHIFT_OK && run_first && q == 0u) continue;    // partial quad: handled element-wise below
+                  const uint64_t o = o0q + 4u * q;
+                  const uint64_t j = e0q + 4u * q;
                   uint32_t mw[4];
                   if (MMAX == 4) {
 #pragma unroll
@@ -919,7 +967,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                           const double* up = nz.u + (uint64_t)c * nz.u_stride + o;
 #pragma unroll
                           for (int k = 0; k < 4; ++k) u[k] = up[k];
-                      } else if (ALIGNED || (j & 1ull) == 0ull) {
+                      } else if (ALIGNED || SHIFT_OK || (j & 1ull) == 0ull) {   // (SHIFT_OK: quads start at begin + 4k, begin even)
                           noise_pair(nz, nz.stream + c, j >> 1, u[0], u[1]);
                           noise_pair(nz, nz.stream + c, (j >> 1) + 1, u[2], u[3]);
                       } else {                      // odd chunk start: the four elements touch three pairs
@@ -955,6 +1003,39 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                       }
                       if (io.aux) stg_quad(reinterpret_cast<uint32_t*>(io.aux) + o, qr, pw[0], pw[1], pw[2], pw[3]);
                       stg_quad_f64(io.outf + o, qr, dv);
+                  }
+              }
+              if constexpr (SHIFT_OK) {
+                  // edges of a shifted run, one element at a time: the 4 - qr0 elements of the first item's block 0
+                  // (lane 0) and the last qr0 elements of the last item's block 63 (lane 31)
+                  const bool head = run_first && lane == 0u, tail = run_last && lane == 31u;
+                  if (head || tail) {
+                      const uint32_t i_lo = head ? 0u : 4u - qr0, i_hi = head ? 4u - qr0 : 4u;
+                      const uint64_t ob = o0 + (head ? 0u : 252u), jb = e0 + (head ? 0u : 252u);
+#pragma unroll 1
+                      for (uint32_t i = i_lo; i < i_hi; ++i) {
+                          const uint32_t mword = i == 0u ? e4[0] : (i == 1u ? e4[1] : (i == 2u ? e4[2] : e4[3]));
+                          const uint64_t o = ob + i, j = jb + i;
+                          if (MODE == M_MASKS) {
+                              reinterpret_cast<uint32_t*>(io.out)[o] = mword & mk32;
+                          } else if (MODE == M_APPLY) {
+                              const uint64_t oc = (uint64_t)c * io.out_stride + o;
+                              reinterpret_cast<uint32_t*>(io.out)[oc] = (reinterpret_cast<const uint32_t*>(io.in)[(uint64_t)c * io.in_stride + o] + mword) & mk32;
+                          } else if (MODE == M_ENCODE) {
+                              const float x = reinterpret_cast<const float*>(io.in)[(uint64_t)c * io.in_stride + o];
+                              const double u = nz.u ? nz.u[(uint64_t)c * nz.u_stride + o] : noise_one(nz, nz.stream + c, j);
+                              const Seg sg = find_seg(cd, j);
+                              const uint32_t qv = encode_one(x, u, sg, cd.scale);
+                              const uint64_t oc = (uint64_t)c * io.out_stride + o;
+                              if (io.aux) reinterpret_cast<uint32_t*>(io.aux)[oc] = qv;
+                              reinterpret_cast<uint32_t*>(io.out)[oc] = (qv + mword) & mk32;
+                          } else if (MODE == M_DECODE) {
+                              const uint32_t pw = (reinterpret_cast<const uint32_t*>(io.in)[o] + mword) & mk32;
+                              if (io.aux) reinterpret_cast<uint32_t*>(io.aux)[o] = pw;
+                              const Seg sg = find_seg(cd, j);
+                              io.outf[o] = decode_one((double)pw, sg.two_an, cd.den, cd.den_rcp, sg.an);
+                          }
+                      }
                   }
               }
           }

@@ -52,8 +52,9 @@ t += "| e2e (pinned host float32 in, float64 out) | %.1f | %.1f G client-element
     d["e2e"]["ms_per_step"], d["e2e"]["value"] / 1e9, 25.6 / (d["e2e"]["ms_per_step"] * 1e-3))
 t += "| reference CPU path (Python port, %d cores, 3 clients x 1 M sample of the same workload) | %.0f | %.2f M client-elements/s | — |\n" % (
     r["cpu_baseline"]["cores"], r["ms_per_step"], r["value"] / 1e6)
-t += ("\nOther chunk layouts (same round, `--n-jobs`): n_jobs = 24 (chunks start at every residue mod 4) 70.2 G\n"
-      "client-elements/s with the lane-local path on 64/32-bit pieces, against 56.9 G when such chunks took the slab path\n"
+t += ("\nOther chunk layouts (same round, `--n-jobs`, `profiles/r2c_bench_njobs*.json`, one box): n_jobs = 16 (every chunk\n"
+      "16-byte aligned) 77.4 G client-elements/s; n_jobs = 24 / 7 / 13 (chunks start at every residue mod 4) 74.6 / 74.7 /\n"
+      "75.4 G with the shuffled-mask path, against 70.2 G with 64/32-bit pieces and 56.9 G when such chunks took the slab path\n"
       "(`profiles/r1f_bench_njobs*.json` and the A/B runs named in the commit log).\n")
 def aligned4(L, nj):
     """every reference chunk starts on a multiple of 4 elements (the ALIGNED kernel instantiation)"""
@@ -66,7 +67,7 @@ for ng in (2, 4):
         nn = json.load(open(P("r1x_bench_n%d.json" % ng)))
         t += ("\n%d GPUs (element-range shards, no data-path collective; `profiles/r1x_bench_n%d.json`, n_jobs = %d on that box%s): "
               "%.1f G client-elements/s (%.1f ms per round) = %.2fx one GPU, e2e %.1f G; NCCL parity run `profiles/r1x_multi_check_n%d.json`.\n" % (
-                  ng, ng, nn["config"]["n_jobs"], "" if aligned4(nn["config"]["elements"], nn["config"]["n_jobs"]) else ": odd chunk lengths, the lane-local path runs on 64/32-bit pieces, 70 G per GPU",
+                  ng, ng, nn["config"]["n_jobs"], "" if aligned4(nn["config"]["elements"], nn["config"]["n_jobs"]) else ": odd chunk lengths, measured before the shuffled-mask path: 70 G per GPU then, 74.6 G now",
                   nn["value"] / 1e9, nn["ms_per_step"], nn["value"] / d["value"], nn["e2e"]["value"] / 1e9, ng))
     except Exception:
         pass

@@ -11,6 +11,7 @@ OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 SCHEME_SINGLE, SCHEME_DOUBLE = 0, 1
 AGG_ELEMENTWISE, AGG_PACKED = 0, 1
 MAX_STREAMS = 128
+ABI_VERSION = 2
 
 
 class Span(C.Structure):
@@ -67,7 +68,7 @@ SIGNATURES = {
     "flashe_batch_unpack": (_int, [_vp, _vp, _u64, _int, _int, _vp, _vp]),
     "flashe_sparse_expand": (_int, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "flashe_sparse_sum": (_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_u64), _vp, _int, _u64, _vp, _vp]),
-    "flashe_sparse_apply_masks": (_int, [_vp, _u32, _i32p, _i32p, _int, _spanp, _vp, _vp, _vp]),
+    "flashe_sparse_apply_masks": (_int, [_vp, _u32, _i32p, _i32p, _int, _spanp, _vp, _vp, _u64, _vp]),
     "flashe_sparse_overlap": (_int, [_vp, C.POINTER(_vp), C.POINTER(_u64), _int, _u64, C.POINTER(_u64), _vp]),
     "flashe_wire_nbytes": (_int, [_int, _u64, C.POINTER(_u64)]),
     "flashe_wire_pack": (_int, [_vp, _vp, _int, _u64, _int, _vp, _vp]),
@@ -106,7 +107,7 @@ def load():
             raise RuntimeError("libflashe_b200.so does not export %s (stale build?)" % name)
         fn.restype = res
         fn.argtypes = args
-    if lib.flashe_abi_version() != 1:
+    if lib.flashe_abi_version() != ABI_VERSION:
         raise RuntimeError("libflashe_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -169,6 +169,7 @@ struct IoDev {
     uint32_t n_clients;
     uint32_t share;                         // batch double masking: compute each stream once
     uint32_t quad;                          // every buffer / stride allows 16-byte accesses per 4 elements
+    uint64_t dense_len;                     // scatter: words in the dense target (indices outside are skipped)
 };
 
 enum { M_MASKS = 0, M_APPLY = 1, M_ENCODE = 2, M_DECODE = 3, M_SCATTER = 4 };
@@ -1364,8 +1365,9 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                 } else if (MODE == M_SCATTER) {
                     const int64_t* index = reinterpret_cast<const int64_t*>(io.aux);
                     word_t* dense = reinterpret_cast<word_t*>(io.out);
-                    if (v0) { const int64_t d = index[o0]; dense[d] = WT::band(WT::add(dense[d], mw0), mk); }
-                    if (v1) { const int64_t d = index[o0 + 1]; dense[d] = WT::band(WT::add(dense[d], mw1), mk); }
+                    // indices come from other parties: anything outside [0, dense_len) is skipped (k_scatter does the same)
+                    if (v0) { const uint64_t d = (uint64_t)index[o0]; if (d < io.dense_len) dense[d] = WT::band(WT::add(dense[d], mw0), mk); }
+                    if (v1) { const uint64_t d = (uint64_t)index[o0 + 1]; if (d < io.dense_len) dense[d] = WT::band(WT::add(dense[d], mw1), mk); }
                 }
             }
         }
@@ -1592,15 +1594,19 @@ __device__ __forceinline__ Xfer xfer_compose(Xfer outer, Xfer inner) {
     else { h.A = outer.A; h.T = inner.T; }  // lo misses, hi hits: depends on inner's threshold
     return h;
 }
+// The low part of a digit sum (S_j mod 2^b) in the width of the word; H_j = S_j >> b <= n - 1 fits 32 bits.
+template <int WORDS> struct Dig { typedef uint64_t lo_t; };
+template <> struct Dig<4> { typedef u128 lo_t; };
+
 template <int WORDS>
 __device__ __forceinline__ void digit_sum(const typename Word<WORDS>::T* __restrict__ cts, uint64_t stride, int n, uint64_t j,
-                                          uint32_t b, uint64_t& lo, uint32_t& H) {
+                                          uint32_t b, typename Dig<WORDS>::lo_t& lo, uint32_t& H) {
     // returns S_j = H*2^b + lo with lo < 2^b
-    if (WORDS == 1) {
+    if constexpr (WORDS == 1) {
         uint64_t s = 0;
         for (int c = 0; c < n; ++c) s += reinterpret_cast<const uint32_t*>(cts)[(uint64_t)c * stride + j];
         lo = s & ((1ull << b) - 1ull); H = (uint32_t)(s >> b);
-    } else {
+    } else if constexpr (WORDS == 2) {
         const uint64_t mk = Word<2>::mask(b);
         uint64_t l = 0; uint32_t h = 0;
         for (int c = 0; c < n; ++c) {
@@ -1610,6 +1616,31 @@ __device__ __forceinline__ void digit_sum(const typename Word<WORDS>::T* __restr
             else { h += (uint32_t)(s >> b); l = s & mk; }
         }
         lo = l; H = h;
+    } else {
+        // 16-byte words (b = 65..128): three-limb accumulator (lo64, hi64, top), rows read as 128-bit
+        // streaming loads with eight of them in flight
+        const uint4* col = reinterpret_cast<const uint4*>(cts) + j;
+        uint64_t l0 = 0, l1 = 0; uint32_t top = 0;
+#pragma unroll 8
+        for (int c = 0; c < n; ++c) {
+            const uint4 v = __ldcs(col + (uint64_t)c * stride);
+            const uint64_t w0 = ((uint64_t)v.y << 32) | v.x, w1 = ((uint64_t)v.w << 32) | v.z;
+            const uint64_t s0 = l0 + w0;
+            const uint64_t c0 = s0 < l0 ? 1ull : 0ull;
+            const uint64_t t1 = l1 + w1;
+            const uint32_t ca = t1 < l1 ? 1u : 0u;
+            const uint64_t s1 = t1 + c0;
+            const uint32_t cb = s1 < t1 ? 1u : 0u;
+            l0 = s0; l1 = s1; top += ca + cb;
+        }
+        u128 r; r.lo = l0;
+        if (b >= 128) { r.hi = l1; H = top; }
+        else {
+            const uint32_t sh = b - 64u;                               // 1..63
+            r.hi = l1 & ((1ull << sh) - 1ull);
+            H = (uint32_t)(((uint64_t)top << (64u - sh)) | (l1 >> sh));
+        }
+        lo = r;
     }
 }
 __device__ __forceinline__ Xfer xfer_of(uint64_t lo, uint32_t H, uint32_t b) {
@@ -1619,14 +1650,47 @@ __device__ __forceinline__ Xfer xfer_of(uint64_t lo, uint32_t H, uint32_t b) {
     f.T = (lo != 0 && thr < 0x7fffffffull) ? (uint32_t)thr : T_NEVER;
     return f;
 }
+__device__ __forceinline__ Xfer xfer_of(u128 lo, uint32_t H, uint32_t b) {
+    Xfer f; f.A = H;
+    // 2^b - lo = (-lo) mod 2^b for 0 < lo < 2^b
+    u128 neg; neg.lo = 0ull - lo.lo; neg.hi = ~lo.hi + (lo.lo == 0ull ? 1ull : 0ull);
+    neg = Word<4>::band(neg, Word<4>::mask(b));
+    const bool nz = (lo.lo | lo.hi) != 0ull;
+    f.T = (nz && neg.hi == 0ull && neg.lo < 0x7fffffffull) ? (uint32_t)neg.lo : T_NEVER;
+    return f;
+}
+// lo + c (c small) -> value mod 2^b, carry out of b bits
+__device__ __forceinline__ uint64_t add_small(uint64_t lo, uint32_t c, uint32_t b, uint32_t& extra) {
+    uint64_t s = lo + c;
+    if (b >= 64) { extra = (s < lo) ? 1u : 0u; return s; }
+    extra = (uint32_t)(s >> b);
+    return s & ((1ull << b) - 1ull);
+}
+__device__ __forceinline__ u128 add_small(u128 lo, uint32_t c, uint32_t b, uint32_t& extra) {
+    u128 s; s.lo = lo.lo + c; s.hi = lo.hi + (s.lo < lo.lo ? 1ull : 0ull);
+    if (b >= 128) { extra = (s.hi < lo.hi) ? 1u : 0u; return s; }
+    const uint32_t sh = b - 64u;
+    extra = (uint32_t)(s.hi >> sh);
+    s.hi &= (1ull << sh) - 1ull;
+    return s;
+}
+template <int WORDS> __device__ __forceinline__ typename Word<WORDS>::T word_of(typename Dig<WORDS>::lo_t v);
+template <> __device__ __forceinline__ uint32_t word_of<1>(uint64_t v) { return (uint32_t)v; }
+template <> __device__ __forceinline__ uint64_t word_of<2>(uint64_t v) { return v; }
+template <> __device__ __forceinline__ u128 word_of<4>(u128 v) { return v; }
+template <int WORDS> __device__ __forceinline__ typename Dig<WORDS>::lo_t lo_zero() { return 0ull; }
+template <> __device__ __forceinline__ u128 lo_zero<4>() { return Word<4>::zero(); }
 
-#define PK_ELEMS 4
 #define PK_THREADS 256
+// elements per thread: four 4- or 8-byte words (one 16- or 32-byte column), one 16-byte word
+template <int WORDS> struct PkElems { static constexpr int V = WORDS == 4 ? 1 : 4; };
 template <int WORDS>
 __global__ void __launch_bounds__(PK_THREADS)
 k_aggregate_packed(const typename Word<WORDS>::T* __restrict__ cts, uint64_t stride, int n, uint64_t count, uint32_t b,
                    uint32_t carry_in, typename Word<WORDS>::T* __restrict__ out, uint32_t* __restrict__ desc_out, int vec_ok) {
     typedef Word<WORDS> WT;
+    typedef typename Dig<WORDS>::lo_t lo_t;
+    constexpr int PK_ELEMS = PkElems<WORDS>::V;
     __shared__ Xfer warp_x[PK_THREADS / 32];
     __shared__ uint32_t tile_cin;
     const uint64_t tile_elems = (uint64_t)PK_THREADS * PK_ELEMS;
@@ -1638,13 +1702,14 @@ k_aggregate_packed(const typename Word<WORDS>::T* __restrict__ cts, uint64_t str
         // tiles and threads are numbered from the END of the vector (carry flows towards element 0):
         // thread q of tile t owns elements hi-1 .. hi-ELEMS with hi = count - (t*tile_elems + q*ELEMS)
         const uint64_t base = tile * tile_elems + (uint64_t)threadIdx.x * PK_ELEMS;
-        uint64_t lo_[PK_ELEMS]; uint32_t H_[PK_ELEMS];
+        lo_t lo_[PK_ELEMS]; uint32_t H_[PK_ELEMS];
         Xfer mine; mine.A = 0; mine.T = 0;  // identity: cin -> cin is not representable; track validity
         bool have = false;
         // 4-byte words, count and every row 16-byte aligned: the thread's four elements are one 128-bit
         // column of the [n, count] matrix; walk the rows with independent streaming loads in flight
         const bool quad = WORDS == 1 && vec_ok && base + PK_ELEMS <= count;
-        if (quad) {
+        if constexpr (WORDS == 1) {
+          if (quad) {
             const uint4* col = reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(cts) + (count - PK_ELEMS - base));
             const uint64_t sv = stride >> 2;
             uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -1662,7 +1727,9 @@ k_aggregate_packed(const typename Word<WORDS>::T* __restrict__ cts, uint64_t str
                 mine = have ? xfer_compose(f, mine) : f;
                 have = true;
             }
-        } else {
+          }
+        }
+        if (!quad) {
 #pragma unroll
             for (int e = 0; e < PK_ELEMS; ++e) {
                 const uint64_t back = base + e;  // distance from the end
@@ -1671,7 +1738,7 @@ k_aggregate_packed(const typename Word<WORDS>::T* __restrict__ cts, uint64_t str
                     Xfer f = xfer_of(lo_[e], H_[e], b);
                     mine = have ? xfer_compose(f, mine) : f;
                     have = true;
-                } else { lo_[e] = 0; H_[e] = 0; }
+                } else { lo_[e] = lo_zero<WORDS>(); H_[e] = 0; }
             }
         }
         // Identity handling: a thread with no elements must pass the carry through unchanged.  That
@@ -1700,7 +1767,7 @@ k_aggregate_packed(const typename Word<WORDS>::T* __restrict__ cts, uint64_t str
                 cin = 0; bool resolved = false;
                 while (bk > 0) {
                     --bk;
-                    uint64_t l; uint32_t h;
+                    lo_t l; uint32_t h;
                     digit_sum<WORDS>(cts, stride, n, count - 1 - bk, b, l, h);
                     Xfer f = xfer_of(l, h, b);
                     // acc currently maps (carry into element bk+1.. chain) ; new element is applied FIRST
@@ -1719,7 +1786,9 @@ k_aggregate_packed(const typename Word<WORDS>::T* __restrict__ cts, uint64_t str
         // carry into this lane's first element: exclusive prefix within the warp
         Xfer ex; ex.A = __shfl_up_sync(0xffffffffu, incl.A, 1); ex.T = __shfl_up_sync(0xffffffffu, incl.T, 1);
         uint32_t c = lane == 0 ? cin : xfer_apply(ex, cin);
-        if (quad && vec_ok > 1) {                                          // out is 16-byte aligned too: one 128-bit store
+        bool stored = false;
+        if constexpr (WORDS == 1) {
+          if (quad && vec_ok > 1) {                                          // out is 16-byte aligned too: one 128-bit store
             uint32_t r[PK_ELEMS];
 #pragma unroll
             for (int e = 0; e < PK_ELEMS; ++e) {
@@ -1728,17 +1797,22 @@ k_aggregate_packed(const typename Word<WORDS>::T* __restrict__ cts, uint64_t str
                 c = H_[e] + (uint32_t)(sum >> b);
             }
             __stcs(reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(out) + (count - PK_ELEMS - base)), make_uint4(r[3], r[2], r[1], r[0]));
-        } else {
+            stored = true;
+          }
+        }
+        if (!stored) {
 #pragma unroll
             for (int e = 0; e < PK_ELEMS; ++e) {
                 const uint64_t back = base + e;
                 if (back < count) {
-                    uint64_t s = lo_[e] + c;   // lo < 2^b, c small
                     uint32_t extra;
-                    if (b >= 64) { extra = (s < lo_[e]) ? 1u : 0u; }
-                    else { extra = (uint32_t)(s >> b); s &= mk64; }
-                    if (WORDS == 1) reinterpret_cast<uint32_t*>(out)[count - 1 - back] = (uint32_t)s;
-                    else reinterpret_cast<uint64_t*>(out)[count - 1 - back] = s;
+                    const lo_t s = add_small(lo_[e], c, b, extra);   // lo < 2^b, c small
+                    if constexpr (WORDS == 4) {
+                        __stcs(reinterpret_cast<uint4*>(out) + (count - 1 - back),
+                               make_uint4((uint32_t)s.lo, (uint32_t)(s.lo >> 32), (uint32_t)s.hi, (uint32_t)(s.hi >> 32)));
+                    } else {
+                        out[count - 1 - back] = word_of<WORDS>(s);
+                    }
                     c = H_[e] + extra;
                 }
             }
@@ -1755,7 +1829,7 @@ k_aggregate_packed(const typename Word<WORDS>::T* __restrict__ cts, uint64_t str
         if (desc_out && tile == 0 && threadIdx.x == 0) {
             Xfer acc; acc.A = 0; acc.T = T_NEVER; bool started = false, resolved = false;
             for (uint64_t bk = 0; bk < count; ++bk) {
-                uint64_t l; uint32_t h;
+                lo_t l; uint32_t h;
                 digit_sum<WORDS>(cts, stride, n, count - 1 - bk, b, l, h);
                 Xfer f = xfer_of(l, h, b);
                 acc = started ? xfer_compose(f, acc) : f;   // later elements are applied after (outer)
@@ -1773,17 +1847,16 @@ k_aggregate_packed(const typename Word<WORDS>::T* __restrict__ cts, uint64_t str
 template <int WORDS>
 __global__ void k_carry_fixup(typename Word<WORDS>::T* __restrict__ out, uint64_t count, uint32_t b, uint32_t carry_in) {
     if (blockIdx.x || threadIdx.x) return;
-    uint64_t c = carry_in;
-    const uint64_t mk = (b >= 64) ? ~0ull : ((1ull << b) - 1ull);
+    uint32_t c = carry_in;
     for (uint64_t j = count; c && j-- > 0;) {
+        uint32_t extra;
         if constexpr (WORDS == 1) {
-            uint64_t v = (uint64_t)out[j] + c;
-            out[j] = (uint32_t)(v & mk); c = v >> b;
+            const uint64_t v = add_small((uint64_t)out[j], c, b, extra);
+            out[j] = (uint32_t)v;
         } else {
-            uint64_t o = out[j], v = o + c;
-            if (b >= 64) { out[j] = v; c = v < o ? 1 : 0; }
-            else { out[j] = v & mk; c = v >> b; }
+            out[j] = add_small(out[j], c, b, extra);
         }
+        c = extra;
     }
 }
 
@@ -2413,14 +2486,20 @@ int flashe_aggregate(flashe_ctx* ctx, const void* cts, uint64_t stride, int n, u
             g_launches.fetch_add(1);
         }
     } else {
-        if (ctx->words == 4) return fail(FLASHE_EUNSUPPORTED, "packed-carry aggregate is built for int_bits <= 64");
-        const uint64_t ntiles = ceil_div(count, (uint64_t)PK_THREADS * PK_ELEMS);
+        // The carry transfer of one digit is modelled as cin -> A + (cin >= T): at most +1, which needs
+        // cin <= n - 1 < 2^b (with more clients than digit values a digit could hand on +2).
+        if (b < 31u && (uint64_t)n > (1ull << b))
+            return fail(FLASHE_EINVAL, "packed-carry aggregate needs n <= 2^int_bits");
+        const uint64_t per_tile = (uint64_t)PK_THREADS * (ctx->words == 4 ? PkElems<4>::V : PkElems<1>::V);
+        const uint64_t ntiles = ceil_div(count, per_tile);
         uint64_t cap = (uint64_t)ctx->num_sms * 8;
         const int grid = (int)(ntiles < cap ? ntiles : cap);
         // 1: rows are 128-bit columns; 2: the output too
         const int vec_ok = (ctx->words == 1 && (count & 3u) == 0 && (stride & 3u) == 0 && aligned16(cts)) ? (aligned16(out) ? 2 : 1) : 0;
+        if (ctx->words == 4 && !(aligned16(cts) && aligned16(out))) return fail(FLASHE_EINVAL, "16-byte words must be 16-byte aligned");
         if (ctx->words == 1) k_aggregate_packed<1><<<grid, PK_THREADS, 0, cs>>>((const uint32_t*)cts, stride, n, count, b, carry_in, (uint32_t*)out, carry_out, vec_ok);
-        else k_aggregate_packed<2><<<grid, PK_THREADS, 0, cs>>>((const uint64_t*)cts, stride, n, count, b, carry_in, (uint64_t*)out, carry_out, 0);
+        else if (ctx->words == 2) k_aggregate_packed<2><<<grid, PK_THREADS, 0, cs>>>((const uint64_t*)cts, stride, n, count, b, carry_in, (uint64_t*)out, carry_out, 0);
+        else k_aggregate_packed<4><<<grid, PK_THREADS, 0, cs>>>((const u128*)cts, stride, n, count, b, carry_in, (u128*)out, carry_out, 0);
         g_launches.fetch_add(1);
     }
     CUDA_TRY(cudaGetLastError());
@@ -2429,11 +2508,11 @@ int flashe_aggregate(flashe_ctx* ctx, const void* cts, uint64_t stride, int n, u
 
 int flashe_aggregate_carry_fixup(flashe_ctx* ctx, void* out, uint64_t count, uint32_t carry_in, void* stream) {
     ENTER(ctx);
-    if (ctx->words == 4) return fail(FLASHE_EUNSUPPORTED, "packed-carry aggregate is built for int_bits <= 64");
     if (count == 0 || carry_in == 0) return FLASHE_OK;
     if (!out) return fail(FLASHE_EINVAL, "out is NULL");
     if (ctx->words == 1) k_carry_fixup<1><<<1, 32, 0, cs>>>((uint32_t*)out, count, (uint32_t)ctx->int_bits, carry_in);
-    else k_carry_fixup<2><<<1, 32, 0, cs>>>((uint64_t*)out, count, (uint32_t)ctx->int_bits, carry_in);
+    else if (ctx->words == 2) k_carry_fixup<2><<<1, 32, 0, cs>>>((uint64_t*)out, count, (uint32_t)ctx->int_bits, carry_in);
+    else k_carry_fixup<4><<<1, 32, 0, cs>>>((u128*)out, count, (uint32_t)ctx->int_bits, carry_in);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return FLASHE_OK;
@@ -2569,14 +2648,15 @@ int flashe_sparse_expand(flashe_ctx* ctx, const void* compact, const int64_t* in
 }
 
 int flashe_sparse_apply_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf_idx, const int32_t* sign, int nstreams,
-                              const flashe_span* span, const int64_t* index, void* dense, void* stream) {
+                              const flashe_span* span, const int64_t* index, void* dense, uint64_t dense_len, void* stream) {
     ENTER(ctx);
     int rc = check_span(span); if (rc) return rc;
     if (span->count == 0) return FLASHE_OK;
     if (!index || !dense) return fail(FLASHE_EINVAL, "NULL buffer");
+    if (span->count > dense_len) return fail(FLASHE_EINVAL, "more compact positions than dense words");
     StreamTab st; rc = make_streams(ctx, iter, prf_idx, sign, nstreams, &st); if (rc) return rc;
     Geom g; make_geom(ctx, span, pick_sup(ctx, span, 1), &g);
-    IoDev io; memset(&io, 0, sizeof(io)); io.out = dense; io.aux = (void*)index; io.n_clients = 1;
+    IoDev io; memset(&io, 0, sizeof(io)); io.out = dense; io.aux = (void*)index; io.n_clients = 1; io.dense_len = dense_len;
     CodecDev cd; memset(&cd, 0, sizeof(cd)); NoiseDev nz; memset(&nz, 0, sizeof(nz));
     return launch_stream<M_SCATTER>(ctx, st, g, io, cd, nz, cs);
 }

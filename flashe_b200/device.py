@@ -66,6 +66,15 @@ class NoiseSpec:
         return _cabi.Noise(self.u.data_ptr() if self.u is not None else None, self.seed, self.stream)
 
 
+def _iter32(it):
+    """The round counter is 4 big-endian bytes of the AES input (jzf_flashe.py:304: iter_index.to_bytes(4, 'big')
+    raises OverflowError outside [0, 2^32)); same here instead of wrapping silently."""
+    it = int(it)
+    if not 0 <= it < (1 << 32):
+        raise OverflowError("iter_index %d does not fit 4 bytes" % it)
+    return it
+
+
 def _i32(xs):
     return (C.c_int32 * max(1, len(xs)))(*[int(x) for x in xs])
 
@@ -167,35 +176,35 @@ class DeviceContext(object):
 
     def masks(self, it, prf_idx, sign, span: VectorSpan, out=None):
         out = self.empty_words(span.n) if out is None else self._check_words(out, span.n, "out")
-        _cabi.check(self.lib.flashe_masks(self._h, it & 0xFFFFFFFF, _i32(prf_idx), _i32(sign), len(prf_idx),
+        _cabi.check(self.lib.flashe_masks(self._h, _iter32(it), _i32(prf_idx), _i32(sign), len(prf_idx),
                                           C.byref(span.c()), out.data_ptr(), self._stream()))
         return out
 
     def precompute(self, iter_from, n_rounds, prf_idx, sign, span: VectorSpan, out=None):
         """Combined keystreams of rounds iter_from .. iter_from+n_rounds-1 -> words [n_rounds, span.n]."""
         out = self.empty_words(span.n, rows=n_rounds) if out is None else self._check_words(out, n_rounds * span.n, "out")
-        _cabi.check(self.lib.flashe_precompute(self._h, iter_from & 0xFFFFFFFF, n_rounds, _i32(prf_idx), _i32(sign),
+        _cabi.check(self.lib.flashe_precompute(self._h, _iter32(iter_from), n_rounds, _i32(prf_idx), _i32(sign),
                                                len(prf_idx), C.byref(span.c()), out.data_ptr(), span.n, self._stream()))
         return out
 
     def apply_masks(self, it, prf_idx, sign, words, span: VectorSpan, out=None):
         self._check_words(words, span.n, "words")
         out = torch.empty_like(words) if out is None else self._check_words(out, span.n, "out")
-        _cabi.check(self.lib.flashe_apply_masks(self._h, it & 0xFFFFFFFF, _i32(prf_idx), _i32(sign), len(prf_idx),
+        _cabi.check(self.lib.flashe_apply_masks(self._h, _iter32(it), _i32(prf_idx), _i32(sign), len(prf_idx),
                                                 C.byref(span.c()), words.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
     def encrypt(self, it, idx, scheme, q, span: VectorSpan, out=None):
         self._check_words(q, span.n, "q")
         out = torch.empty_like(q) if out is None else self._check_words(out, span.n, "out")
-        _cabi.check(self.lib.flashe_encrypt(self._h, it & 0xFFFFFFFF, idx, scheme, C.byref(span.c()), q.data_ptr(),
+        _cabi.check(self.lib.flashe_encrypt(self._h, _iter32(it), idx, scheme, C.byref(span.c()), q.data_ptr(),
                                             out.data_ptr(), self._stream()))
         return out
 
     def decrypt(self, it, add_idx, minus_idx, agg, span: VectorSpan, out=None):
         self._check_words(agg, span.n, "agg")
         out = torch.empty_like(agg) if out is None else self._check_words(out, span.n, "out")
-        _cabi.check(self.lib.flashe_decrypt(self._h, it & 0xFFFFFFFF, _i32(add_idx), len(add_idx), _i32(minus_idx),
+        _cabi.check(self.lib.flashe_decrypt(self._h, _iter32(it), _i32(add_idx), len(add_idx), _i32(minus_idx),
                                             len(minus_idx), C.byref(span.c()), agg.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
@@ -222,7 +231,7 @@ class DeviceContext(object):
             self._check(noise.u, torch.float64, span.n, "noise.u")
         out = self.empty_words(span.n) if out is None else self._check_words(out, span.n, "out")
         cc, nc = codec.c(span.total_len), noise.c()
-        _cabi.check(self.lib.flashe_encode_encrypt(self._h, it & 0xFFFFFFFF, idx, scheme, C.byref(span.c()), x.data_ptr(),
+        _cabi.check(self.lib.flashe_encode_encrypt(self._h, _iter32(it), idx, scheme, C.byref(span.c()), x.data_ptr(),
                                                    C.byref(cc), C.byref(nc), out.data_ptr(),
                                                    q_out.data_ptr() if q_out is not None else None, self._stream()))
         return out
@@ -237,7 +246,7 @@ class DeviceContext(object):
             self._check(noise.u, torch.float64, n * span.n, "noise.u")
         out = self.empty_words(span.n, rows=n) if out is None else self._check_words(out, n * span.n, "out")
         cc, nc = codec.c(span.total_len), noise.c()
-        _cabi.check(self.lib.flashe_encode_encrypt_batch(self._h, it & 0xFFFFFFFF, idx0, n, scheme, C.byref(span.c()),
+        _cabi.check(self.lib.flashe_encode_encrypt_batch(self._h, _iter32(it), idx0, n, scheme, C.byref(span.c()),
                                                          x.data_ptr(), span.n, C.byref(cc), C.byref(nc), span.n,
                                                          out.data_ptr(), span.n, 1 if share_streams else 0, self._stream()))
         return out
@@ -277,7 +286,7 @@ class DeviceContext(object):
         self._check_words(agg, span.n, "agg")
         out = torch.empty(span.n, dtype=torch.float64, device=self.device) if out is None else out
         cc = codec.c(span.total_len)
-        _cabi.check(self.lib.flashe_decrypt_decode(self._h, it & 0xFFFFFFFF, _i32(add_idx), len(add_idx), _i32(minus_idx),
+        _cabi.check(self.lib.flashe_decrypt_decode(self._h, _iter32(it), _i32(add_idx), len(add_idx), _i32(minus_idx),
                                                    len(minus_idx), C.byref(span.c()), agg.data_ptr(), C.byref(cc),
                                                    out.data_ptr(), p_out.data_ptr() if p_out is not None else None,
                                                    self._stream()))
@@ -332,10 +341,21 @@ class DeviceContext(object):
         _cabi.check(self.lib.flashe_sparse_sum(self._h, cp, ip, ks, zbuf, n, total, out.data_ptr(), self._stream()))
         return out
 
-    def sparse_apply_masks(self, it, prf_idx, sign, span: VectorSpan, index, dense):
+    def sparse_apply_masks(self, it, prf_idx, sign, span: VectorSpan, index, dense, validate=True):
+        """dense[index[i]] += sum_k sign_k F(it, prf_k)[i] over the compact positions.  `index` comes from
+        other parties (the arbiter's mask lists): validate=True checks on the device that it is sorted,
+        unique and inside [0, len(dense)) and raises IndexError otherwise, as the reference's fancy
+        indexing would (jzf_flashe.py:333); the kernel itself skips out-of-range entries."""
         self._check(index, torch.int64, span.n, "index")
-        _cabi.check(self.lib.flashe_sparse_apply_masks(self._h, it & 0xFFFFFFFF, _i32(prf_idx), _i32(sign), len(prf_idx),
-                                                       C.byref(span.c()), index.data_ptr(), dense.data_ptr(), self._stream()))
+        total = dense.numel() * dense.element_size() // self.word_bytes
+        if dense.device != self.device or not dense.is_contiguous():
+            raise ValueError("dense must be contiguous on %s" % self.device)
+        if validate and span.n:
+            bad = bool((index[0] < 0) | (index[-1] >= total)) or (span.n > 1 and not bool((index[1:] > index[:-1]).all()))
+            if bad:
+                raise IndexError("sparse index list must be sorted, unique and inside [0, %d)" % total)
+        _cabi.check(self.lib.flashe_sparse_apply_masks(self._h, _iter32(it), _i32(prf_idx), _i32(sign), len(prf_idx),
+                                                       C.byref(span.c()), index.data_ptr(), dense.data_ptr(), total, self._stream()))
         return dense
 
     def sparse_overlap(self, index_lists, total):

@@ -24,6 +24,7 @@ from multiprocessing import cpu_count
 import numpy as np
 import torch
 
+from .._cabi import MAX_STREAMS
 from ..device import SCHEME_DOUBLE, SCHEME_SINGLE, DeviceContext, VectorSpan
 from .encrypt import Encrypt
 
@@ -116,6 +117,12 @@ class FlasheCipher(Encrypt):
         if self._ctx is not None:
             self._ctx.close()
         self._ctx = DeviceContext(seed, self.int_bits, self.device)
+        # everything derived from the old key / bound to the old context goes with it
+        self._ring = None
+        self._retract = ([], [])
+        self.next_iter_encrypt_prepared = {}
+        self.next_iter_decrypt_prepared = {}
+        self.next_iter_decrypt_prepared_idx = {}
 
     def get_prp_seed(self):
         return self.prp_seed
@@ -248,8 +255,8 @@ class FlasheCipher(Encrypt):
             out = agg
             # at most FLASHE_MAX_STREAMS streams per launch; an empty survivor list leaves the
             # value unchanged, as the reference's empty sum does
-            for k in range(0, len(minus), 128):
-                out = ctx.decrypt(self.iter_index, [], minus[k:k + 128], out, self._span(self._len(value)))
+            for k in range(0, len(minus), MAX_STREAMS):
+                out = ctx.decrypt(self.iter_index, [], minus[k:k + MAX_STREAMS], out, self._span(self._len(value)))
         else:
             out = ctx.add_premasked(agg, self.next_iter_decrypt_prepared['minus'], -1)
         self.next_iter_decrypt_prepared.pop('minus', None)
@@ -269,8 +276,12 @@ class FlasheCipher(Encrypt):
             out = ctx.add_premasked(out, self.next_iter_decrypt_prepared['add'], +1)
         elif not add and not minus:
             raise KeyError('add')   # the reference indexes next_iter_decrypt_prepared['add'] here
-        if add or minus:
-            out = ctx.decrypt(self.iter_index, add, minus, out, span)
+        # at most FLASHE_MAX_STREAMS index terms per launch (many clients with alternating dropouts need
+        # more): chain the calls, each one's output feeding the next, as the single-mask path does
+        terms = [(i, +1) for i in add] + [(i, -1) for i in minus]
+        for k in range(0, len(terms), MAX_STREAMS):
+            part = terms[k:k + MAX_STREAMS]
+            out = ctx.decrypt(self.iter_index, [i for i, sg in part if sg > 0], [i for i, sg in part if sg < 0], out, span)
         for d in (self.next_iter_decrypt_prepared, self.next_iter_decrypt_prepared_idx):
             d.pop('add', None)
             d.pop('minus', None)
@@ -301,7 +312,18 @@ class FlasheCipher(Encrypt):
             from ..precompute import MaskRing
             if self._ring is None or self._ring.rounds != rounds or self._ring.span.n != self.num_params:
                 self._ring = MaskRing.for_encrypt(self._ctx, self.idx, self._span(self.num_params), rounds, "double")
-            self._ring.fill(it, rounds)
+            # only the slots that do not already hold their round: a per-round call regenerates ONE round
+            # (the slot the previous encrypt consumed), not all of them
+            t = it
+            while t < it + rounds:
+                if self._ring.has(t):
+                    t += 1
+                    continue
+                run = 1
+                while t + run < it + rounds and not self._ring.has(t + run):
+                    run += 1
+                self._ring.fill(t, run)
+                t += run
             return
         self.next_iter_encrypt_prepared = {
             'add': self._ctx.masks(it, [self.idx, self.idx + 1], [1, -1], self._span(self.num_params)),

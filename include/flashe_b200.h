@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FLASHE_ABI_VERSION 1
+#define FLASHE_ABI_VERSION 2
 
 enum {
     FLASHE_OK = 0,
@@ -179,7 +179,8 @@ int flashe_encode_add_premasked(flashe_ctx* ctx, const flashe_span* span, const 
  *                           the given carry_in; depends = 0 when that carry cannot depend on carry_in
  *                           (always, for ciphertext-like data), else the exact transfer function of the
  *                           range is carry_out = A + (carry_in >= T).  Shards must be non-empty.
- * int_bits <= 64 for FLASHE_AGG_PACKED. */
+ *                           Every width up to 128 bits (the shipped int_bits = 120 batch mode included);
+ *                           n <= 2^int_bits (a digit hands on at most +1 beyond its own quotient). */
 int flashe_aggregate(flashe_ctx* ctx, const void* cts, uint64_t stride, int n, uint64_t count, int mode,
                      uint32_t carry_in, void* out, uint32_t* carry_out, void* stream);
 
@@ -233,10 +234,12 @@ int flashe_sparse_sum(flashe_ctx* ctx, const void* const* compacts, const int64_
 
 /* Sparse single-mask decrypt term (sp/jzf_flashe.py:315-343, 528-535): regenerate
  * sum_k sign[k]*F(iter, prf_idx[k]) over the COMPACT positions described by `span` (total_len = k) and
- * add it into dense[index[i]]. */
+ * add it into dense[index[i]].  `dense` holds dense_len words; index must be sorted unique (a repeated
+ * index would be a racy read-modify-write); entries outside [0, dense_len) are skipped (the reference
+ * raises IndexError there; the Python mirror validates the list before launching). */
 int flashe_sparse_apply_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf_idx, const int32_t* sign,
                               int nstreams, const flashe_span* span, const int64_t* index, void* dense,
-                              void* stream);
+                              uint64_t dense_len, void* stream);
 
 /* dynamic_masking cost model (proc/jzf_flashe_block.py:89-117): overlap[i] = |mask_i ∩ mask_{i+1}| for
  * the n-1 adjacent pairs; index lists are device int64_t arrays (sorted unique); `index` and `k` are

@@ -318,15 +318,21 @@ int fo_aggregate_elementwise(int int_bits, int n, uint64_t L, uint64_t stride, c
  * the shard tests), *carry_out receives the carry out of element 0. */
 int fo_aggregate_packed(int int_bits, int n, uint64_t L, uint64_t stride, const void* cts, void* out,
                         uint32_t carry_in, uint32_t* carry_out) {
-    if (int_bits < 1 || int_bits > 120 || n < 1) return FO_EINVAL;  /* headroom for the digit sums */
+    if (int_bits < 1 || int_bits > 128 || n < 1) return FO_EINVAL;
     int wb = word_bytes(int_bits);
     u128 msk = mask_of(int_bits);
     u128 carry = carry_in;
     for (uint64_t jj = L; jj-- > 0;) {
-        u128 lo = carry, hi = 0;           /* digit sum kept as hi*2^b + lo to stay inside 128 bits */
-        for (int c = 0; c < n; ++c) {
-            lo += load_word(cts, (uint64_t)c * stride + jj, wb);
-            hi += lo >> int_bits; lo &= msk;
+        /* digit sum kept as hi*2^b + lo with lo < 2^b; for b = 128 the overflow of the u128 addition
+         * IS the unit of hi */
+        u128 lo = 0, hi = 0;
+        for (int c = -1; c < n; ++c) {
+            u128 w = c < 0 ? carry : load_word(cts, (uint64_t)c * stride + jj, wb);
+            if (int_bits == 128) { u128 s = lo + w; hi += (s < lo) ? 1 : 0; lo = s; }
+            else {
+                hi += w >> int_bits; w &= msk;       /* (the carry may exceed 2^b only for tiny b) */
+                lo += w; hi += lo >> int_bits; lo &= msk;
+            }
         }
         store_word(out, jj, wb, lo);
         carry = hi;

@@ -94,6 +94,19 @@ def main():
     report("aggregate elementwise n=16", ms, (nC + 1) * Ls * 4, nC * Ls, "client-elements/s")
     ms = timed(lambda: ctx.aggregate(cts, fb.AGG_PACKED, out=agg))
     report("aggregate packed-carry n=16", ms, (nC + 1) * Ls * 4, nC * Ls, "client-elements/s")
+    del cts, agg
+    # 16-byte words (the shipped int_bits = 120 batch mode): 16 clients x 12.5 M words = the same bytes
+    ctx120 = fb.DeviceContext(KEY, 120, dev)
+    Lw = Ls // 4
+    ctw = torch.randint(-2 ** 63, 2 ** 63 - 1, (nC, Lw, 2), device=dev, generator=g, dtype=torch.int64)
+    ctw[:, :, 1] &= (1 << 56) - 1
+    ctw = ctw.view(torch.uint64)
+    aggw = ctx120.empty_words(Lw)
+    ms = timed(lambda: ctx120.aggregate(ctw, fb.AGG_ELEMENTWISE, out=aggw))
+    report("aggregate elementwise n=16, int_bits 120", ms, (nC + 1) * Lw * 16, nC * Lw, "client-words/s")
+    ms = timed(lambda: ctx120.aggregate(ctw, fb.AGG_PACKED, out=aggw))
+    report("aggregate packed-carry n=16, int_bits 120", ms, (nC + 1) * Lw * 16, nC * Lw, "client-words/s")
+    del ctw, aggw
     # ---- online step after precompute, masks of one client
     x = torch.empty(L, dtype=torch.float32, device=dev).normal_(0.0, 0.1, generator=g)
     span = fb.VectorSpan(L, 16)

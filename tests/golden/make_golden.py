@@ -295,6 +295,12 @@ def case_batch():
     cipher = make_cipher(b, 0, it, nj)
     cipher.set_idx_list(raw_idx_list=list(range(n)), mode="decrypt")
     dec = cipher.decrypt(agg.copy())
+    # the dense path really sums the PACKED uploads (jzf_aggregator.py:404-419): carries leak between words
+    agg_a = obj(aggregate_packed(cts, b))
+    cipher = make_cipher(b, 0, it, nj)
+    cipher.set_idx_list(raw_idx_list=list(range(n)), mode="decrypt")
+    dec_a = cipher.decrypt(agg_a.copy())
+    put_ints("batch_aggA", agg_a, b); put_ints("batch_decA", dec_a, b)
     unb = ref_quant._static_unbatching_padding_asymmetric(dec, b, ebits, factor)[:L]
     decoded = ref_quant._static_unquantize_padding_asymmetric(unb, float(alpha), ebits, n)
     put("batch_x", np.stack(xs)); put("batch_u", np.stack(us))
@@ -351,9 +357,31 @@ def case_runs():
     MANIFEST["cases"].append(dict(kind="runs", name="runs", rows=rows))
 
 
+# ------------------------------------------------------------------ I. packed sum of wide words
+def case_packed_wide():
+    """jzf_aggregator.py:406-419 on words wider than 64 bits (the shipped int_bits = 120 batch mode uploads
+    those): random words plus runs of all-ones digits so that carries ripple across many words."""
+    cfgs = [(65, 3, 200), (100, 16, 257), (120, 16, 300), (120, 2, 64), (127, 7, 130), (128, 5, 128), (128, 16, 300)]
+    for i, (b, n, L) in enumerate(cfgs):
+        rs = np.random.RandomState(7000 + i)
+        full = (1 << b) - 1
+        cts = [[int.from_bytes(rs.bytes(16), "little") & full for _ in range(L)] for _ in range(n)]
+        lo, hi = L // 3, L // 3 + L // 4
+        for j in range(lo, hi):                 # digit sums of exactly 2^b - 1: a carry entering at hi ripples to lo
+            for c in range(n):
+                cts[c][j] = full if c == 0 else 0
+        cts[n - 1][hi] = full                   # and one enters: digit hi sums past 2^b
+        cts[0][hi] = 1 if n > 1 else full
+        name = "pkw_%d" % i
+        agg = aggregate_packed(cts, b)
+        put_ints(name + "_ct", [v for ct in cts for v in ct], b)
+        put_ints(name + "_aggA", agg, b)
+        MANIFEST["cases"].append(dict(kind="packed_wide", name=name, int_bits=b, n_clients=n, L=L))
+
+
 def main():
     case_masks(); case_roundtrip(); case_dropout(); case_precompute(); case_sparse()
-    case_batch(); case_quant_edges(); case_runs()
+    case_batch(); case_quant_edges(); case_runs(); case_packed_wide()
     MANIFEST["generator"] = dict(numpy=np.__version__, python=sys.version.split()[0],
                                  reference="/root/reference (SamuelGong/FLASHE)")
     OUT["manifest"] = np.frombuffer(json.dumps(MANIFEST).encode(), dtype=np.uint8)

@@ -38,7 +38,7 @@ def test_ctypes_signatures_cover_header(lib_path):
     from flashe_b200 import _cabi
     assert sorted(_cabi.SIGNATURES) == declared_functions()
     lib = _cabi.load()
-    assert lib.flashe_abi_version() == 1
+    assert lib.flashe_abi_version() == 2
     assert lib.flashe_word_bytes(20) == 4 and lib.flashe_word_bytes(64) == 8 and lib.flashe_word_bytes(120) == 16
     assert lib.flashe_word_bytes(0) < 0 and b"int_bits" in lib.flashe_last_error()
 

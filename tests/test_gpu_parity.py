@@ -202,6 +202,85 @@ def test_batch120_golden(fb, golden):
     assert np.array_equal(_np(unb), golden.words("batch_unb", 32))
     out = fb.DeviceContext(KEY, 32).decode(unb, codec, fb.VectorSpan(L, 1))
     assert np.array_equal(_np(out).view(np.uint64), golden["batch_decoded"].view(np.uint64))
+    # the shipped dense path: packed-carry sum of the 120-bit words (jzf_aggregator.py:404-419)
+    agg_a = ctx.aggregate(cts, fb.AGG_PACKED)
+    assert np.array_equal(_np(agg_a), golden.words("batch_aggA", b))
+    dec_a = ctx.decrypt(it, [n], [0], agg_a, span)
+    assert np.array_equal(_np(dec_a), golden.words("batch_decA", b))
+
+
+def test_packed_aggregate_wide_words_golden(fb, golden):
+    for c in golden.cases("packed_wide"):
+        b, n, L = c["int_bits"], c["n_clients"], c["L"]
+        ctx = ctx_for(fb, b)
+        cts = golden.words(c["name"] + "_ct", b).reshape(n, L, 2)
+        got = ctx.aggregate(_dev(cts), fb.AGG_PACKED)
+        assert np.array_equal(_np(got), golden.words(c["name"] + "_aggA", b)), c["name"]
+
+
+@pytest.mark.parametrize("bits", [65, 96, 120, 127, 128])
+def test_packed_aggregate_wide_adversarial_and_shards(fb, bits):
+    """16-byte words: all-ones digits (every word passes its carry-in on, across tile boundaries),
+    digits that generate and propagate, two element-range shards with the descriptor exchange."""
+    ctx = ctx_for(fb, bits)
+    rs = np.random.RandomState(bits)
+    L, n = 3000, 7
+    full = (1 << bits) - 1
+    m64 = (1 << 64) - 1
+    cts = rs.randint(0, 1 << 62, size=(n, L, 2), dtype=np.uint64)
+    cts[:, :, 0] |= rs.randint(0, 4, size=(n, L), dtype=np.uint64) << np.uint64(62)
+    cts[:, :, 1] &= np.uint64(full >> 64)
+    cts[:, 500:2200] = 0
+    cts[0, 500:2200, 0] = np.uint64(m64); cts[0, 500:2200, 1] = np.uint64(full >> 64)   # only propagate
+    cts[1, 2199, 0] = 1                                                                  # one carry enters
+    cts[:, 2500:2600, 0] = np.uint64(m64); cts[:, 2500:2600, 1] = np.uint64(full >> 64)  # generate and propagate
+    want, cw = O.aggregate(bits, cts, "packed", return_carry=True)
+    desc = torch.zeros(4, dtype=torch.int32, device="cuda")
+    got = ctx.aggregate(_dev(cts), fb.AGG_PACKED, carry_out=desc)
+    assert np.array_equal(_np(got), want)
+    assert int(desc[0]) == cw
+    for cut in (1000, 2199, 2200):
+        hi_part, lo_part = np.ascontiguousarray(cts[:, cut:]), np.ascontiguousarray(cts[:, :cut])
+        d_hi = torch.zeros(4, dtype=torch.int32, device="cuda")
+        out_hi = ctx.aggregate(_dev(hi_part), fb.AGG_PACKED, carry_out=d_hi)
+        out_lo = ctx.aggregate(_dev(lo_part), fb.AGG_PACKED)
+        ctx.aggregate_carry_fixup(out_lo, int(d_hi[0]))
+        assert np.array_equal(np.concatenate([_np(out_lo), _np(out_hi)]), want), cut
+        out_lo2 = ctx.aggregate(_dev(lo_part), fb.AGG_PACKED, carry_in=int(d_hi[0]))
+        assert np.array_equal(_np(out_lo2), want[:cut])
+    # a shard made of propagate-only words: its carry out DEPENDS on the carry in (descriptor words 1-3)
+    mid = np.ascontiguousarray(cts[:, 600:900])
+    d_mid = torch.zeros(4, dtype=torch.int32, device="cuda")
+    ctx.aggregate(_dev(mid), fb.AGG_PACKED, carry_out=d_mid)
+    dm = [int(v) & 0xffffffff for v in d_mid.cpu()]
+    assert dm[1] == 1 and dm[2] == 0 and dm[3] == 1          # carry_out = 0 + (carry_in >= 1)
+
+
+def test_packed_aggregate_rejects_more_clients_than_digit_values(fb):
+    ctx = ctx_for(fb, 8)
+    cts = torch.zeros((300, 64), dtype=torch.int32, device="cuda").view(torch.uint32)
+    with pytest.raises(fb._cabi.FlasheError):
+        ctx.aggregate(cts, fb.AGG_PACKED)
+    ctx.aggregate(cts, fb.AGG_ELEMENTWISE)
+
+
+def test_sparse_apply_masks_rejects_bad_index_lists(fb):
+    """Index lists come from other parties: out of range / unsorted / repeated entries must not reach the
+    scatter (the reference raises IndexError at jzf_flashe.py:333)."""
+    ctx = ctx_for(fb, 32)
+    total = 1000
+    dense = ctx.zeros_words(total)
+    for bad in ([0, 5, 1000], [-1, 2, 3], [1, 3, 3, 4], [5, 4, 6]):
+        idx = torch.tensor(bad, dtype=torch.int64, device="cuda")
+        with pytest.raises(IndexError):
+            ctx.sparse_apply_masks(0, [0], [1], fb.VectorSpan(len(bad), 8), idx, dense)
+    # the kernel itself skips entries outside the dense vector
+    idx = torch.tensor([3, 999, 1000, 5000], dtype=torch.int64, device="cuda")
+    ctx.sparse_apply_masks(0, [0], [1], fb.VectorSpan(4, 8), idx, dense, validate=False)
+    torch.cuda.synchronize()
+    got = _np(dense)
+    want = O.masks(KEY, 32, 8, 0, [0], [1], 4)
+    assert got[3] == want[0] and got[999] == want[1] and np.count_nonzero(got) <= 2
 
 
 def test_quant_edges_golden(fb, golden):
@@ -321,6 +400,60 @@ def test_aggregate_unaligned_and_tail(fb):
 
 
 # ---------------------------------------------------------------------------------------- the drop-in classes
+def test_flashecipher_double_mask_many_dropout_runs(fb):
+    """300 clients with every other one dropped: 150 runs = 300 PRF index terms, more than one launch
+    takes (FLASHE_MAX_STREAMS); the drop-in chains the calls.  Also: a re-keyed cipher forgets what the
+    old key prepared, and an iteration index that does not fit 4 bytes raises like the reference."""
+    from flashe_b200.secureprotol import FlasheCipher
+    b, nj, L, it = 32, 8, 777, 3
+    survivors = list(range(0, 300, 2))
+    agg = np.random.RandomState(3).randint(0, 1 << 32, size=L, dtype=np.uint64).astype(np.uint32)
+    cipher = FlasheCipher(b, n_jobs=nj)
+    cipher.generate_prp_seed(KEY)
+    cipher.set_num_clients(300)
+    cipher.set_iter_index(it)
+    cipher.set_idx_list(raw_idx_list=survivors, mode="decrypt")
+    assert len(cipher.index_prefix_for_add) + len(cipher.index_prefix_for_minus) == 300
+    dec = cipher.decrypt(agg.astype(object))
+    want = O.decrypt(KEY, b, nj, it, survivors, "double", agg)
+    assert [int(v) for v in dec] == [int(v) for v in want]
+    # re-keying drops the prepared buffers and the ring of the old key
+    cipher.idx = 1
+    cipher.set_num_params(L)
+    cipher.prepare_encrypt()
+    cipher.prepare_encrypt(rounds=3)
+    assert cipher.next_iter_encrypt_prepared and cipher._ring is not None
+    cipher.generate_prp_seed(bytes(range(1, 33)))
+    assert cipher.next_iter_encrypt_prepared == {} and cipher._ring is None
+    cipher.set_iter_index(it)
+    ct = cipher.encrypt(agg.astype(object))
+    want_ct = O.encrypt(bytes(range(1, 33)), b, nj, it, 1, "double", agg)
+    assert [int(v) for v in ct] == [int(v) for v in want_ct]
+    with pytest.raises(OverflowError):
+        cipher.set_iter_index(1 << 32)
+    with pytest.raises(OverflowError):
+        cipher.set_iter_index(-1)
+
+
+def test_prepare_encrypt_ring_refills_only_consumed_slots(fb):
+    from flashe_b200.secureprotol import FlasheCipher
+    from flashe_b200.device import launch_count
+    b, nj, L = 20, 8, 5000
+    cipher = FlasheCipher(b, n_jobs=nj)
+    cipher.generate_prp_seed(KEY)
+    cipher.idx = 2
+    cipher.set_num_params(L)
+    q = np.random.RandomState(4).randint(0, 65536, size=L).astype(np.uint32)
+    cipher.prepare_encrypt(rounds=4)                     # iter_index = -1: rounds 0..3
+    for it in range(6):
+        cipher.set_iter_index(it)
+        ct = cipher.encrypt(_dev(q))
+        assert np.array_equal(_np(ct), O.encrypt(KEY, b, nj, it, 2, "double", q)), it
+        l0 = launch_count()
+        cipher.prepare_encrypt(rounds=4)                 # look-ahead: rounds it+1 .. it+4
+        assert launch_count() - l0 == 1, "one consumed slot -> one round regenerated"
+
+
 def test_flashecipher_dropin_matches_reference_outputs(fb, golden):
     """Driven exactly like the reference's notebook / aggregator drive jzf_flashe.FlasheCipher."""
     from flashe_b200.secureprotol import FlasheCipher

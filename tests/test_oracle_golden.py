@@ -162,6 +162,22 @@ def test_batch120(golden):
     assert np.array_equal(unb, golden.words("batch_unb", 32))
     out = O.unquantize(unb, c["alpha"], e, n)
     assert np.array_equal(out.view(np.uint64), golden["batch_decoded"].view(np.uint64))
+    # the shipped dense path sums the packed uploads (jzf_aggregator.py:404-419): 120-bit digits
+    agg_a = O.aggregate(b, np.stack(cts), "packed")
+    assert np.array_equal(agg_a, golden.words("batch_aggA", b))
+    assert not np.array_equal(agg_a, agg)
+    dec_a = O.decrypt(golden.key, b, nj, it, list(range(n)), "double", agg_a)
+    assert np.array_equal(dec_a, golden.words("batch_decA", b))
+
+
+def test_packed_aggregate_wide_words(golden):
+    """int_bits 65..128: big-int sums of the packed wire integers with long carry ripples."""
+    cases = golden.cases("packed_wide")
+    assert len(cases) >= 6
+    for c in cases:
+        b, n, L = c["int_bits"], c["n_clients"], c["L"]
+        cts = golden.words(c["name"] + "_ct", b).reshape(n, L, 2)
+        assert np.array_equal(O.aggregate(b, cts, "packed"), golden.words(c["name"] + "_aggA", b)), c["name"]
 
 
 def test_quant_edges_and_decode(golden):

@@ -2,7 +2,7 @@
 """bench.py — FLASHE hot path on N B200s: encode+encrypt (all clients) -> aggregate -> decrypt+decode.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
-    python bench.py --impl reference [--gpus N] ...                # reference CPU path (oracle port)
+    python bench.py --impl reference [--gpus N] ...                # the reference's own CPU code (oracle/_ref)
     torchrun --nproc-per-node N bench.py --gpus N ...              # N > 1, one rank per GPU
 
 Metric (BASELINE.json): client-elements/s = n_clients * L / time of one full round, whole job over all
@@ -138,21 +138,33 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def cpu_round(elements, clients, int_bits, threads):
-    """One bounded round of the reference's CPU path (oracle/flashe_port.py): returns (seconds, phases)."""
+def cpu_round(elements, clients, int_bits, threads, keep=False):
+    """One bounded round of the reference's CPU path on this host.  With oracle/_ref present (staged by
+    oracle/make_ref.py from /root/reference) this is the reference's OWN code — jzf_flashe.FlasheCipher
+    .encrypt / .decrypt with its multiprocessing.Pool(N_JOBS), jzf_quantize's encode / decode — driven like
+    encrypt_test/final_big_table.ipynb:222-233, 408-411 (kind "reference"); otherwise the Python port
+    oracle/flashe_port.py (kind "port").  Returns (seconds, phases, kind, outputs or None)."""
     import numpy as np
-    from oracle import flashe_port as P
     xs = [(np.random.RandomState(1000 + c).standard_normal(elements) * 0.1).astype(np.float32) for c in range(clients)]
-    np.random.seed(2000)
+    seeds = [2000 + c for c in range(clients)]
     phases = {}
+    from oracle import ref_driver as R
+    if R.available():
+        t0 = time.perf_counter()
+        res = R.run_round(KEY, int_bits, 0, xs, float(ALPHA), 16, n_jobs=threads, seeds=seeds, timings=phases)
+        dt = time.perf_counter() - t0
+        return dt, phases, "reference", ((xs, seeds) + res if keep else None)
+    from oracle import flashe_port as P
+    np.random.seed(2000)
     t0 = time.perf_counter()
     P.run_round(KEY, int_bits, 0, xs, float(ALPHA), 16, n_jobs=threads, timings=phases)
-    return time.perf_counter() - t0, phases
+    return time.perf_counter() - t0, phases, "port", None
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (Python port, Pool over all
-    host cores, as jzf_flashe.py does), each step a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores
+    (all of them: N_JOBS = cpu_count(), as jzf_flashe.py:7 does), each step a bounded sample of the
+    workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -161,20 +173,22 @@ def run_reference(args):
     clients = min(args.cpu_sample_clients, args.clients)
     for _ in range(args.warmup):
         cpu_round(min(elements, 50_000), clients, args.int_bits, cores)
-    times, phases = [], {}
+    times, phases, kind = [], {}, "port"
     for _ in range(args.steps):
-        dt, phases = cpu_round(elements, clients, args.int_bits, cores)
+        dt, phases, kind, _ = cpu_round(elements, clients, args.int_bits, cores)
         times.append(dt)
     total = sum(times)
     value = clients * elements * len(times) / total
-    sample = "%d clients x %d elements per step (slice of the %d x %d workload), N_JOBS=%d" % (
-        clients, elements, args.clients, args.elements, cores)
+    sample = "%d clients x %d elements per step (slice of the %d x %d workload), N_JOBS=%d, %s" % (
+        clients, elements, args.clients, args.elements, cores,
+        "the reference's own modules staged under oracle/_ref (FlasheCipher.encrypt/decrypt, multiprocessing.Pool per call)"
+        if kind == "reference" else "Python port of the reference's loops (oracle/_ref absent)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(args, cores),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                          "phases_s_last_step": phases},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -499,33 +513,48 @@ def run_e2e(args, ctx, fb, span, codec, noise, scheme, x, cts, agg, out, world, 
 
 
 def cpu_baseline(args, ctx, fb):
-    """Reference CPU path (oracle/flashe_port.py) on this box's host cores, bounded sample; plus a
-    bit-exactness spot check of the device path against the C oracle on whole reference chunks."""
+    """BASELINE config 1 (1 M elements x 3 clients, int_bits 20, double masking) through the reference's CPU
+    path on this box's host cores, timed — and the SAME run re-done on the device from the same inputs and
+    the same rounding noise, every ciphertext, the aggregate, the decrypted integers and the decoded
+    float64 compared with what the reference produced ("this config also is the CPU reference
+    timing run")."""
     import numpy as np
     import torch
-    from oracle import oracle as O
     cores = os.cpu_count() or 1
     elements, clients = min(args.cpu_sample_elements, args.elements), min(args.cpu_sample_clients, args.clients)
-    dt, phases = cpu_round(elements, clients, 20, cores)
-    out = {"value": clients * elements / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    bits = 20
+    dt, phases, kind, kept = cpu_round(elements, clients, bits, cores, keep=True)
+    out = {"value": clients * elements / dt, "unit": UNIT, "cores": cores, "kind": kind,
            "sample": "BASELINE config 1: %d clients x %d elements, int_bits 20, one round (encode, encrypt, aggregate, decrypt, decode), "
-                     "multiprocessing.Pool(%d) per call as jzf_flashe.py does" % (clients, elements, cores),
+                     "%s, multiprocessing.Pool(%d) per call as jzf_flashe.py does" % (
+                         clients, elements, "the reference's own modules (oracle/_ref)" if kind == "reference" else "Python port", cores),
            "seconds": dt, "phases_s": phases}
-    # spot check: 2 clients x 200k elements of the benchmark's own format against the oracle
-    bits, n_jobs, L = args.int_bits, args.n_jobs or cores, args.elements
-    j0, cnt = (L // 3) // 4 * 4, 200_000
-    span = fb.VectorSpan(L, n_jobs, j0, cnt)
-    xs = (np.random.RandomState(5).standard_normal((2, cnt)) * 0.1).astype(np.float32)
-    codec = fb.CodecSpec(alpha=float(ALPHA), element_bits=16, n_clients=2)
-    got = ctx.encode_encrypt_batch(0, 0, fb.SCHEME_DOUBLE, torch.from_numpy(xs).to(ctx.device), codec,
-                                   fb.NoiseSpec(seed=1, stream=0), span).cpu().numpy()
-    O.set_threads(min(cores, 32))
-    ok = True
-    for c in range(2):
-        u = ctx.rng_uniform(1, c, j0, cnt).cpu().numpy()
-        want = O.encrypt(KEY, bits, n_jobs, 0, c, "double", O.quantize(xs[c], u, float(ALPHA), 16).astype(got.dtype), L=L, j0=j0)
-        ok = ok and bool(np.array_equal(got[c], want))
-    out["device_vs_oracle_spot_check"] = "bit-exact" if ok else "MISMATCH"
+    if kept is not None:
+        xs, seeds, qs, cts, agg, dec, decoded = kept
+        c20 = fb.DeviceContext(KEY, bits, ctx.device)
+        span = fb.VectorSpan(elements, cores)
+        codec = fb.CodecSpec(alpha=float(ALPHA), element_bits=16, n_clients=clients)
+        us = []
+        for sd in seeds:
+            np.random.seed(sd)
+            us.append(np.random.random(elements))
+        x_d = torch.from_numpy(np.stack(xs)).to(ctx.device)
+        u_d = torch.from_numpy(np.stack(us)).to(ctx.device)
+        got_ct = c20.encode_encrypt_batch(0, 0, fb.SCHEME_DOUBLE, x_d, codec, fb.NoiseSpec(u=u_d.reshape(-1)), span)
+        got_agg = c20.aggregate(got_ct, fb.AGG_ELEMENTWISE)
+        got_p = c20.empty_words(elements)
+        got_out = c20.decrypt_decode(0, [clients], [0], got_agg, codec, span, p_out=got_p)
+        torch.cuda.synchronize()
+        want_ct = np.stack([np.asarray(ct, dtype=object).astype(np.uint32) for ct in cts])
+        checks = {
+            "ciphertexts": bool(np.array_equal(got_ct.cpu().numpy(), want_ct)),
+            "aggregate": bool(np.array_equal(got_agg.cpu().numpy(), np.asarray(agg, dtype=object).astype(np.uint32))),
+            "decrypted": bool(np.array_equal(got_p.cpu().numpy(), np.asarray(dec, dtype=object).astype(np.uint32))),
+            "decoded_float64_bits": bool(np.array_equal(got_out.cpu().numpy().view(np.uint64),
+                                                        np.asarray(decoded, dtype=np.float64).view(np.uint64))),
+        }
+        out["device_vs_reference_on_the_timed_run"] = "bit-exact" if all(checks.values()) else "MISMATCH"
+        out["device_vs_reference_checks"] = checks
     return out
 
 

@@ -18,6 +18,29 @@ void flashe_count_launches(int n);
 struct flashe_ctx_info { int device; int int_bits; int words; int num_sms; };
 int flashe_ctx_get_info(const flashe_ctx* ctx, flashe_ctx_info* out);
 
+struct alignas(16) KeySched { uint32_t rk[60]; };   // AES-256 round keys, big-endian words
+
+struct flashe_ctx {
+    int device;
+    int int_bits;
+    int words;       // 1, 2, 4
+    int num_sms;
+    uint32_t m;
+    uint8_t key[32];
+    KeySched ks;
+    uint32_t* d_te0;   // device copy of the Te0 table (256 words): source of the kernels' shared-memory tables
+};
+
+
+int flashe_check_span(const flashe_span* s);
+static inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+static inline int grid_1d(const flashe_ctx* ctx, uint64_t work_items, int threads, int per_sm) {
+    uint64_t blocks = ceil_div(work_items ? work_items : 1, (uint64_t)threads);
+    uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
 #define FLASHE_CUDA_TRY(expr)                                                                            \
     do {                                                                                                 \
         cudaError_t e__ = (expr);                                                                        \
@@ -34,5 +57,12 @@ struct FlasheDeviceGuard {
     }
     ~FlasheDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+#define CUDA_TRY(expr) FLASHE_CUDA_TRY(expr)
+#define ENTER(ctx)                                                                 \
+    if (!(ctx)) return flashe_fail(FLASHE_EINVAL, "ctx is NULL");                  \
+    FlasheDeviceGuard guard__((ctx)->device);                                      \
+    if (!guard__.ok) return flashe_fail(FLASHE_ECUDA, "cudaSetDevice failed");     \
+    cudaStream_t cs = (cudaStream_t)stream
 
 #endif

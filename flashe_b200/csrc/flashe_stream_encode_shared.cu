@@ -1,0 +1,7 @@
+// flashe_stream_encode_shared.cu — instantiations of k_stream for one mode (see flashe_stream.cuh).
+#include "flashe_stream.cuh"
+
+int flashe_launch_stream_encode_shared(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,
+        const NoiseDev& nz, cudaStream_t stream) {
+    return launch_stream<M_ENCODE, true>(ctx, st, g, io, cd, nz, stream);
+}

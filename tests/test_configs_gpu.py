@@ -1,6 +1,6 @@
-"""BASELINE.json configs C2-C5 at their FULL sizes on the GPU.
+"""BASELINE.json configs C1-C5 at their FULL sizes on the GPU.
 
-C2 is checked bit for bit against the oracle in full.  C3-C5 are too large for the CPU oracle to
+C1 and C2 are checked bit for bit against the oracle in full.  C3-C5 are too large for the CPU oracle to
 redo in seconds, so they combine (i) oracle checks of whole reference chunks / whole compact vectors
 sampled from the full-size run with (ii) size-independent properties evaluated on the whole vectors
 on the device: decrypt(aggregate(encrypt(q_c))) == sum_c q_c mod 2^b, precomputed == on-the-fly,
@@ -35,6 +35,53 @@ def fb():
 def _i64(words):
     """uint32 word tensor -> int64 tensor (torch has no uint32 arithmetic)."""
     return words.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+
+
+# ------------------------------------------------------------------------------------------------ C1
+def test_c1_reference_cpu_case_1m_3_clients_bit_exact(fb):
+    """BASELINE config 1 exactly: 1M-element float32 gradient, 3 clients, int_bits 20, double masking —
+    the reference's own CPU-runnable case.  Every ciphertext, BOTH server sums (element-wise and the
+    packed-carry sum of the wire integers), the decrypted integers and the decoded float64 against the C
+    oracle; and, when the reference's own modules are staged (oracle/_ref, built by oracle/make_ref.py in
+    the build container), against jzf_flashe.FlasheCipher / jzf_quantize themselves on the same inputs."""
+    L, n, bits, n_jobs, it = 1_000_000, 3, 20, 8, 0
+    ctx = fb.DeviceContext(KEY, bits)
+    span = fb.VectorSpan(L, n_jobs)
+    codec = fb.CodecSpec(alpha=ALPHA, element_bits=16, n_clients=n)
+    xs = [(np.random.RandomState(1000 + c).standard_normal(L) * 0.1).astype(np.float32) for c in range(n)]
+    seeds = [2000 + c for c in range(n)]
+    u = np.empty((n, L), dtype=np.float64)
+    for c in range(n):
+        np.random.seed(seeds[c])
+        u[c] = np.random.random(L)
+    q_out = torch.empty((n, L), dtype=torch.int32, device="cuda").view(torch.uint32)
+    cts = ctx.empty_words(L, rows=n)
+    for c in range(n):                     # client by client, as the parties would (one launch each)
+        ctx.encode_encrypt(it, c, fb.SCHEME_DOUBLE, _dev(xs[c]), codec, fb.NoiseSpec(u=_dev(u[c])), span, out=cts[c], q_out=q_out[c])
+    O.set_threads(8)
+    q = np.stack([O.quantize(xs[c], u[c], ALPHA, 16) for c in range(n)])
+    ct_want = np.stack([O.encrypt(KEY, bits, n_jobs, it, c, "double", q[c]) for c in range(n)])
+    assert np.array_equal(_np(q_out), q)
+    assert np.array_equal(_np(cts), ct_want)
+    got = {}
+    for mode, name in ((fb.AGG_ELEMENTWISE, "elementwise"), (fb.AGG_PACKED, "packed")):
+        agg = ctx.aggregate(cts, mode)
+        agg_want = O.aggregate(bits, ct_want, name)
+        assert np.array_equal(_np(agg), agg_want), name
+        p = ctx.empty_words(L)
+        out = ctx.decrypt_decode(it, [n], [0], agg, codec, span, p_out=p)
+        p_want = O.decrypt(KEY, bits, n_jobs, it, list(range(n)), "double", agg_want)
+        assert np.array_equal(_np(p), p_want), name
+        assert np.array_equal(_np(out).view(np.uint64), O.unquantize(p_want, ALPHA, 16, n).view(np.uint64)), name
+        got[name] = (_np(agg), _np(p), _np(out))
+    assert np.array_equal(got["elementwise"][1].astype(np.int64), q.astype(np.int64).sum(axis=0))
+    from oracle import ref_driver as R
+    if R.available():                      # the reference itself (in-process pool: this process holds a CUDA context)
+        qs_r, cts_r, agg_r, dec_r, out_r = R.run_round(KEY, bits, it, xs, ALPHA, 16, n_jobs=n_jobs, seeds=seeds, inline_pool=True)
+        assert np.array_equal(np.stack([np.asarray(v, dtype=object).astype(np.uint32) for v in cts_r]), _np(cts))
+        assert np.array_equal(np.asarray(agg_r, dtype=object).astype(np.uint32), got["elementwise"][0])
+        assert np.array_equal(np.asarray(dec_r, dtype=object).astype(np.uint32), got["elementwise"][1])
+        assert np.array_equal(np.asarray(out_r, dtype=np.float64).view(np.uint64), got["elementwise"][2].view(np.uint64))
 
 
 # ------------------------------------------------------------------------------------------------ C2

@@ -240,3 +240,26 @@ def test_noise_uniform_is_res53_of_philox():
     w = [int(x[0]) for x in o]
     assert u[1] == ((w[0] >> 5) * 67108864.0 + (w[1] >> 6)) / 9007199254740992.0
     assert u[2] == ((w[2] >> 5) * 67108864.0 + (w[3] >> 6)) / 9007199254740992.0
+
+
+def test_reference_itself_agrees_with_the_oracle_when_staged():
+    """oracle/_ref (the reference's own modules, staged by oracle/make_ref.py) driven through a full round
+    equals the C oracle on the same seeded inputs — the pin of the oracle that needs no fixture."""
+    from oracle import ref_driver as R
+    if not R.available():
+        pytest.skip("oracle/_ref not staged (python oracle/make_ref.py in the build container)")
+    key, b, nj, L, n, it, alpha = bytes(range(32)), 20, 5, 20011, 4, 3, 0.25
+    xs = [(np.random.RandomState(50 + c).standard_normal(L) * 0.1).astype(np.float32) for c in range(n)]
+    seeds = [60 + c for c in range(n)]
+    survivors = [0, 1, 3]
+    qs, cts, agg, dec, out = R.run_round(key, b, it, xs, alpha, 16, n_jobs=nj, seeds=seeds, inline_pool=True, survivors=survivors)
+    for c in range(n):
+        np.random.seed(seeds[c])
+        q = O.quantize(xs[c], np.random.random(L), alpha, 16)
+        assert np.array_equal(q, np.asarray(qs[c], dtype=object).astype(np.uint32))
+        assert np.array_equal(O.encrypt(key, b, nj, it, c, "double", q), np.asarray(cts[c], dtype=object).astype(np.uint32))
+    a = O.aggregate(b, np.stack([np.asarray(cts[c], dtype=object).astype(np.uint32) for c in survivors]))
+    assert np.array_equal(a, np.asarray(agg, dtype=object).astype(np.uint32))
+    d = O.decrypt(key, b, nj, it, survivors, "double", a)
+    assert np.array_equal(d, np.asarray(dec, dtype=object).astype(np.uint32))
+    assert np.array_equal(O.unquantize(d, alpha, 16, len(survivors)).view(np.uint64), np.asarray(out, dtype=np.float64).view(np.uint64))

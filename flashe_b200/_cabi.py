@@ -10,6 +10,7 @@ from . import build as _build
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 SCHEME_SINGLE, SCHEME_DOUBLE = 0, 1
 AGG_ELEMENTWISE, AGG_PACKED = 0, 1
+SUM_PAIRWISE, SUM_SEQUENTIAL = 0, 1
 MAX_STREAMS = 128
 ABI_VERSION = 2
 
@@ -66,6 +67,9 @@ SIGNATURES = {
     "flashe_rng_uniform": (_int, [_vp, _u64, _u64, _u64, _u64, _vp, _vp]),
     "flashe_batch_pack": (_int, [_vp, _vp, _u64, _int, _int, _vp, _vp]),
     "flashe_batch_unpack": (_int, [_vp, _vp, _u64, _int, _int, _vp, _vp]),
+    "flashe_batch_layout": (_int, [_int, _int, _int, C.POINTER(_u64), _int, C.POINTER(_u64)]),
+    "flashe_batch_pack_layers": (_int, [_vp, _vp, C.POINTER(_u64), _int, _int, _int, _vp, _vp]),
+    "flashe_batch_unpack_layers": (_int, [_vp, _vp, C.POINTER(_u64), _int, _int, _int, _vp, _vp]),
     "flashe_sparse_expand": (_int, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "flashe_sparse_sum": (_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_u64), _vp, _int, _u64, _vp, _vp]),
     "flashe_sparse_apply_masks": (_int, [_vp, _u32, _i32p, _i32p, _int, _spanp, _vp, _vp, _u64, _vp]),
@@ -74,7 +78,7 @@ SIGNATURES = {
     "flashe_wire_pack": (_int, [_vp, _vp, _int, _u64, _int, _vp, _vp]),
     "flashe_wire_unpack": (_int, [_vp, _vp, _u64, _int, _int, _vp, _vp]),
     "flashe_topk_sparsify": (_int, [_vp, _vp, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64), _int, _vp, _vp, _vp, _vp]),
-    "flashe_segment_stats": (_int, [_vp, _vp, _vp, _u64, C.POINTER(_u64), C.POINTER(C.c_double), _int, _vp, _vp]),
+    "flashe_segment_stats": (_int, [_vp, _vp, _vp, _u64, C.POINTER(_u64), C.POINTER(C.c_double), _int, _int, _vp, _vp]),
     "flashe_launch_count": (_u64, []),
 }
 

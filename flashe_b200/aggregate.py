@@ -82,6 +82,65 @@ def dynamic_masking(masks, total, device=None):
     return {"choice": choice, "masks": masks, "single_cost": single_cost, "double_cost": double_cost}
 
 
+def flatten_weights(weights):
+    """Client.flatten_weights (jzf_aggregator.py:625-650): the layers, in walking order, become ONE flat
+    vector stored under the first key; returns (weights, shape_dict) — the reference keeps shape_dict on the
+    client object; the sentinel layer 'zzz' has no shape entry (:637-641).  One concatenation instead of the
+    reference's repeated np.append (which re-copies the growing vector per layer)."""
+    shape_dict = {}
+    keys = list(weights.walking_order)
+    if not keys:
+        return weights, shape_dict
+    parts = [np.array([])]                       # the reference starts from an empty float64 array (:626-627)
+    for k in keys:
+        layer = weights._weights[k]
+        if k != "zzz":
+            shape_dict[k] = layer.shape
+        parts.append(layer.flatten())
+        del weights._weights[k]
+    weights._weights[keys[0]] = np.concatenate(parts)
+    weights.walking_order = sorted(weights._weights.keys(), key=str)
+    return weights, shape_dict
+
+
+def unflatten_weights(weights, shape_dict):
+    """Client.unflatten_weights (jzf_aggregator.py:652-671): split the single flat vector back into the layers
+    of shape_dict (views of the flat vector, like the reference's slices)."""
+    only_key = None
+    for k in weights.walking_order:
+        only_key = k
+        break
+    flat = weights._weights[only_key]
+    for k, shape in shape_dict.items():
+        size = int(np.prod(shape))
+        weights._weights[k] = flat[:size].reshape(shape)
+        flat = flat[size:]
+    weights.walking_order = sorted(weights._weights.keys(), key=str)
+    return weights
+
+
+def flatten_layers(layers):
+    """Device form of flatten_weights: a list of per-layer CUDA tensors -> (flat tensor, seg_end), the segment
+    table every kernel of the path takes (flashe_codec.seg_end, flashe_batch_pack_layers, flashe_segment_stats,
+    flashe_topk_sparsify), so that a caller can hand over per-layer tensors."""
+    flat = torch.cat([t.reshape(-1) for t in layers])
+    ends, tot = [], 0
+    for t in layers:
+        tot += t.numel()
+        ends.append(tot)
+    return flat, ends
+
+
+def unflatten_layers(flat, seg_end, shapes=None):
+    """Inverse of flatten_layers: views of `flat` per layer (reshaped when `shapes` is given)."""
+    out, b = [], 0
+    for i, e in enumerate(seg_end):
+        t = flat[b:e]
+        out.append(t.reshape(shapes[i]) if shapes is not None else t)
+        b = e
+    return out
+
+
 class SparsifyingClient(object):
     """The sparsification state and step of the reference's aggregator Client
     (jzf_aggregator.py:560-623): `_sparsity`, `remain_weights` (per-layer residuals carried across

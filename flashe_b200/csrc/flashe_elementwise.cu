@@ -505,6 +505,45 @@ __global__ void k_batch_unpack(const u128* __restrict__ in, uint64_t nwords, uin
     }
 }
 
+// Per-layer lane batching through a segment table: QuantizingClient.quantize batches every
+// layer by itself (jzf_quantize.py:447-452), so each layer is zero-padded to a multiple of batch_size and the
+// flat word vector is the concatenation of the layers' words (flatten_weights, jzf_aggregator.py:625-650).
+// ebeg / wbeg: first element / first word of layer s (nseg + 1 entries).
+__device__ __forceinline__ int layer_of_word(const uint64_t* __restrict__ wbeg, int nseg, uint64_t w) {
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (__ldg(wbeg + mid) <= w) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+__global__ void k_batch_pack_layers(const uint32_t* __restrict__ q, const uint64_t* __restrict__ ebeg, const uint64_t* __restrict__ wbeg,
+                                    int nseg, uint32_t lane_bits, uint32_t bs, uint64_t nwords, u128* __restrict__ out) {
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
+        const int s = layer_of_word(wbeg, nseg, w);
+        const uint64_t e0 = __ldg(ebeg + s) + (w - __ldg(wbeg + s)) * bs, eend = __ldg(ebeg + s + 1);
+        uint64_t lo = 0, hi = 0;
+        for (uint32_t i = 0; i < bs; ++i) {
+            const uint64_t v = e0 + i < eend ? q[e0 + i] : 0u;
+            hi = (hi << lane_bits) | (lo >> (64 - lane_bits));
+            lo = (lo << lane_bits) + v;
+        }
+        u128 r; r.lo = lo; r.hi = hi;
+        out[w] = r;
+    }
+}
+__global__ void k_batch_unpack_layers(const u128* __restrict__ in, const uint64_t* __restrict__ ebeg, const uint64_t* __restrict__ wbeg,
+                                      int nseg, uint32_t lane_bits, uint32_t bs, uint64_t nwords, uint32_t* __restrict__ out) {
+    const uint64_t lm = (1ull << lane_bits) - 1ull;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
+        const int s = layer_of_word(wbeg, nseg, w);
+        const uint64_t e0 = __ldg(ebeg + s) + (w - __ldg(wbeg + s)) * bs, eend = __ldg(ebeg + s + 1);
+        u128 t = in[w];
+        for (int i = (int)bs - 1; i >= 0; --i) {
+            if (e0 + i < eend) out[e0 + i] = (uint32_t)(t.lo & lm);         // padding lanes are dropped
+            t.lo = (t.lo >> lane_bits) | (t.hi << (64 - lane_bits));
+            t.hi >>= lane_bits;
+        }
+    }
+}
+
 // expand_to_dense (jzf_aggregator.py:150-165)
 template <int WORDS>
 __global__ void k_fill(typename Word<WORDS>::T* __restrict__ out, uint64_t count, typename Word<WORDS>::T v) {
@@ -787,6 +826,69 @@ int flashe_batch_unpack(flashe_ctx* ctx, const void* words, uint64_t nwords, int
     if (!words || !q_out) return fail(FLASHE_EINVAL, "NULL buffer");
     k_batch_unpack<<<grid_1d(ctx, nwords, 256, 16), 256, 0, cs>>>((const u128*)words, nwords, lane, bs, q_out);
     count_launch();
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+int flashe_batch_layout(int int_bits, int element_bits, int factor, const uint64_t* seg_end, int nseg, uint64_t* word_end_out) {
+    const int l = element_bits + factor;
+    if (int_bits < 1 || int_bits > 128 || element_bits < 1 || factor < 0 || l > 32) return fail(FLASHE_EINVAL, "bad lane geometry");
+    const uint64_t bs = (uint64_t)(int_bits / l);
+    if (bs == 0) return fail(FLASHE_EINVAL, "int_bits smaller than one lane");
+    if (nseg < 1 || !seg_end || !word_end_out) return fail(FLASHE_EINVAL, "need nseg >= 1, seg_end and word_end_out");
+    uint64_t prev = 0, words = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (seg_end[s] < prev) return fail(FLASHE_EINVAL, "seg_end must be ascending");
+        words += ceil_div(seg_end[s] - prev, bs);
+        word_end_out[s] = words;
+        prev = seg_end[s];
+    }
+    return FLASHE_OK;
+}
+
+// device copy of the layer table {first element, first word} (nseg + 1 entries each)
+static int upload_layer_table(flashe_ctx* ctx, const uint64_t* seg_end, int nseg, int element_bits, int factor, cudaStream_t cs,
+                              uint64_t** d_out, uint64_t* nwords) {
+    std::vector<uint64_t> tab(2 * (size_t)(nseg + 1));
+    std::vector<uint64_t> wend((size_t)nseg);
+    int rc = flashe_batch_layout(ctx->int_bits, element_bits, factor, seg_end, nseg, wend.data()); if (rc) return rc;
+    tab[0] = 0; tab[nseg + 1] = 0;
+    for (int s = 0; s < nseg; ++s) { tab[s + 1] = seg_end[s]; tab[nseg + 1 + s + 1] = wend[s]; }
+    *nwords = wend[nseg - 1];
+    CUDA_TRY(cudaMallocAsync((void**)d_out, sizeof(uint64_t) * tab.size(), cs));
+    CUDA_TRY(cudaMemcpyAsync(*d_out, tab.data(), sizeof(uint64_t) * tab.size(), cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaStreamSynchronize(cs));   // tab (pageable) goes out of scope
+    return FLASHE_OK;
+}
+
+int flashe_batch_pack_layers(flashe_ctx* ctx, const uint32_t* q, const uint64_t* seg_end, int nseg, int element_bits, int factor,
+                             void* words_out, void* stream) {
+    ENTER(ctx);
+    uint32_t lane, bs; int rc = batch_geometry(ctx, element_bits, factor, &lane, &bs); if (rc) return rc;
+    uint64_t* tab = nullptr; uint64_t nw = 0;
+    rc = upload_layer_table(ctx, seg_end, nseg, element_bits, factor, cs, &tab, &nw); if (rc) return rc;
+    if (nw) {
+        if (!q || !words_out) { cudaFreeAsync(tab, cs); return fail(FLASHE_EINVAL, "NULL buffer"); }
+        k_batch_pack_layers<<<grid_1d(ctx, nw, 256, 16), 256, 0, cs>>>(q, tab, tab + nseg + 1, nseg, lane, bs, nw, (u128*)words_out);
+        count_launch();
+    }
+    cudaFreeAsync(tab, cs);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+int flashe_batch_unpack_layers(flashe_ctx* ctx, const void* words, const uint64_t* seg_end, int nseg, int element_bits, int factor,
+                               uint32_t* q_out, void* stream) {
+    ENTER(ctx);
+    uint32_t lane, bs; int rc = batch_geometry(ctx, element_bits, factor, &lane, &bs); if (rc) return rc;
+    uint64_t* tab = nullptr; uint64_t nw = 0;
+    rc = upload_layer_table(ctx, seg_end, nseg, element_bits, factor, cs, &tab, &nw); if (rc) return rc;
+    if (nw) {
+        if (!words || !q_out) { cudaFreeAsync(tab, cs); return fail(FLASHE_EINVAL, "NULL buffer"); }
+        k_batch_unpack_layers<<<grid_1d(ctx, nw, 256, 16), 256, 0, cs>>>((const u128*)words, tab, tab + nseg + 1, nseg, lane, bs, nw, q_out);
+        count_launch();
+    }
+    cudaFreeAsync(tab, cs);
     CUDA_TRY(cudaGetLastError());
     return FLASHE_OK;
 }

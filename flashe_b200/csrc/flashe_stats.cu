@@ -1,0 +1,299 @@
+// flashe_stats.cu — per-layer statistics around decode, BIT-EXACT with numpy.
+//
+//   QuantizingClient.unnormalize (secureprotol/jzf_quantize.py:549-564), per layer:
+//       w += past_mean[layer];  past_mean[layer] = np.mean(w);  past_std[layer] = np.std(w)
+//   The standard deviation of one round defines the clipping range alpha of the next
+//   (jzf_quantize.py:403-413), and alpha is part of every ciphertext: a last-bit difference in std can move
+//   float32(alpha) and with it the quantised values of a GPU party against a numpy party.  The sums are
+//   therefore evaluated in numpy's own order:
+//
+//   FLASHE_SUM_PAIRWISE    float64 ndarrays (what the batched mode holds after unbatch -> unquantize):
+//       np.add.reduce = 0.0 + pairwise_sum(a, n) with numpy's fixed recursion (loops_utils.h.src,
+//       @TYPE@_pairwise_sum, unchanged since numpy 1.9; the reference pins 1.17.2):
+//           n < 8        sequential from 0.0
+//           n <= 128     eight accumulators r[j] = a[j] + a[8+j] + a[16+j] + ..., combined as
+//                        ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)), then the n % 8 tail added one by one
+//           n > 128      split at n2 = (n/2) - (n/2) % 8 and add the two halves' sums
+//       mean = sum / n;  std = sqrt( (0.0 + pairwise_sum((a - mean)^2)) / n )      (numpy/core/_methods.py)
+//   FLASHE_SUM_SEQUENTIAL  object arrays of Python floats (what the un-batched mode holds: unquantize of an
+//       object array yields Python floats): no identity, a[0] + a[1] + ... left to right; same mean / std
+//       formulas.  Inherently serial per layer (one lane adds, the warp stages the data).
+//
+// The pairwise tree depends only on the sizes, so it is cut into three levels that are each enumerated
+// where that is cheap: the HOST walks the recursion down to nodes of at most GROUP_ELEMS elements ("groups")
+// and MID_ELEMS elements ("mid nodes"); one WARP per group walks the rest of the recursion down to the
+// <= 128-element leaves, evaluates them eight lanes per leaf exactly as numpy's unrolled loop does, and
+// combines them; one thread per mid node combines its groups, one thread per layer its mid nodes.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "flashe_internal.h"
+
+#define GROUP_ELEMS 8192u       // a group is a tree node with <= 8192 elements whose parent has more
+#define MID_ELEMS 262144u
+#define MAX_LEAVES 128          // leaves of a group: sizes are in [64, 128] as soon as the group has > 128 elements
+#define SG_WARPS 8
+
+struct StatGroup { uint64_t begin; uint32_t n; uint32_t seg; };
+struct StatMid { uint64_t n; uint32_t first_group; uint32_t seg; };
+struct StatSegD { uint64_t begin, n; uint32_t first_mid, n_mid; double shift; };
+
+static __host__ __device__ __forceinline__ uint64_t pw_left(uint64_t n) { uint64_t h = n >> 1; return h - (h & 7ull); }
+
+// numpy's <= 128-element block on 8 lanes: lane j owns accumulator r[j]; returns the block sum in every lane
+// of the 8-lane group.  VAL(i) yields element i of the block.
+template <typename F>
+__device__ __forceinline__ double pw_leaf(uint32_t n, uint32_t j, uint32_t gmask, F val) {
+    if (n < 8u) {                               // (only a whole layer can be this small)
+        double r = 0.0;
+        for (uint32_t i = 0; i < n; ++i) r = __dadd_rn(r, val(i));
+        return r;
+    }
+    const uint32_t n8 = n - (n & 7u);
+    double r = val(j);
+    for (uint32_t i = 8u; i < n8; i += 8u) r = __dadd_rn(r, val(i + j));
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));          // r0+r1 | r2+r3 | r4+r5 | r6+r7
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));          // (r0+r1)+(r2+r3) | (r4+r5)+(r6+r7)
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+    for (uint32_t i = n8; i < n; ++i) r = __dadd_rn(r, val(i));
+    return r;
+}
+
+// combine the sums of consecutive sub-nodes of a node with `n` elements: sub-nodes are the nodes of the
+// recursion with at most `cut` elements; *cur walks their sums in depth-first order
+__device__ double pw_combine(uint64_t n, uint64_t cut, const double* sums, uint32_t* cur) {
+    if (n <= cut) return sums[(*cur)++];
+    const uint64_t n2 = pw_left(n);
+    const double a = pw_combine(n2, cut, sums, cur);
+    const double b = pw_combine(n - n2, cut, sums, cur);
+    return __dadd_rn(a, b);
+}
+
+// PASS 0: v = w + shift (stored to w_out when given), group sum of v.
+// PASS 1: group sum of (x - mean)^2, x = w_out, or w + shift when no w_out was written.
+template <int PASS>
+__global__ void __launch_bounds__(SG_WARPS * 32)
+k_stats_groups(const double* __restrict__ w, double* __restrict__ w_out, const StatGroup* __restrict__ groups, uint32_t ngroups,
+               const StatSegD* __restrict__ segs, int add_shift, const double* __restrict__ stats, double* __restrict__ gsum) {
+    __shared__ uint32_t leaf_off[SG_WARPS][MAX_LEAVES];
+    __shared__ uint8_t leaf_n[SG_WARPS][MAX_LEAVES];
+    __shared__ double leaf_sum[SG_WARPS][MAX_LEAVES];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t sub = lane >> 3, j = lane & 7u;            // four 8-lane groups per warp
+    const uint32_t gmask = 0xffu << (8u * sub);
+    for (uint32_t g = blockIdx.x * SG_WARPS + warp; g < ngroups; g += gridDim.x * SG_WARPS) {
+        const StatGroup gr = groups[g];
+        const double shift = segs[gr.seg].shift;
+        const double mean = PASS == 1 ? stats[2 * gr.seg] : 0.0;
+        // leaves of the group, depth first (lane 0 walks the size recursion with a small stack)
+        uint32_t nleaf = 0;
+        if (lane == 0) {
+            uint32_t st_n[16], st_o[16]; int sp = 0;
+            st_n[0] = gr.n; st_o[0] = 0; sp = 1;
+            while (sp) {
+                --sp;
+                const uint32_t n = st_n[sp], o = st_o[sp];
+                if (n <= 128u) { leaf_off[warp][nleaf] = o; leaf_n[warp][nleaf] = (uint8_t)(n == 128u ? 0u : n) ; ++nleaf; }
+                else {
+                    const uint32_t n2 = (uint32_t)pw_left(n);
+                    st_n[sp] = n - n2; st_o[sp] = o + n2; ++sp;       // right half: visited after the left
+                    st_n[sp] = n2; st_o[sp] = o; ++sp;
+                }
+            }
+        }
+        nleaf = __shfl_sync(0xffffffffu, nleaf, 0);
+        __syncwarp();
+        const double* src = w + gr.begin;
+        double* dst = (PASS == 0 && w_out) ? w_out + gr.begin : nullptr;
+        for (uint32_t l0 = 0; l0 < nleaf; l0 += 4u) {
+            const uint32_t l = l0 + sub;
+            const bool on = l < nleaf;
+            const uint32_t off = on ? leaf_off[warp][l] : 0u;
+            uint32_t n = on ? leaf_n[warp][l] : 0u;
+            if (on && n == 0u) n = 128u;
+            auto val = [&](uint32_t i) -> double {
+                if (PASS == 0) {
+                    const double v = __dadd_rn(src[off + i], shift);
+                    if (dst) dst[off + i] = v;
+                    return v;
+                } else {
+                    const double x = add_shift ? __dadd_rn(src[off + i], shift) : src[off + i];
+                    const double d = __dsub_rn(x, mean);
+                    return __dmul_rn(d, d);
+                }
+            };
+            double s = 0.0;
+            if (on) s = pw_leaf(n, j, gmask, val);
+            if (on && j == 0u) leaf_sum[warp][l] = s;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            uint32_t cur = 0;
+            gsum[g] = pw_combine(gr.n, 128u, leaf_sum[warp], &cur);
+        }
+        __syncwarp();
+    }
+}
+
+// n < 8 leaves store every element redundantly from the 8 lanes of the group when w_out is written: harmless
+// (same value), and such layers have fewer than 8 elements.
+
+__global__ void k_stats_mids(const StatMid* __restrict__ mids, uint32_t nmid, const double* __restrict__ gsum, double* __restrict__ msum) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmid) return;
+    uint32_t cur = 0;
+    msum[m] = pw_combine(mids[m].n, GROUP_ELEMS, gsum + mids[m].first_group, &cur);
+}
+
+template <int PASS>
+__global__ void k_stats_top(const StatSegD* __restrict__ segs, int nseg, const double* __restrict__ msum, double* __restrict__ stats) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    const StatSegD sg = segs[s];
+    if (sg.n == 0) {                        // np.mean / np.std of an empty array: nan (with a RuntimeWarning)
+        stats[2 * s + PASS] = __longlong_as_double(0x7ff8000000000000ll);
+        return;
+    }
+    uint32_t cur = 0;
+    const double tot = __dadd_rn(0.0, pw_combine(sg.n, MID_ELEMS, msum + sg.first_mid, &cur));   // identity + pairwise sum
+    const double q = __ddiv_rn(tot, (double)sg.n);
+    stats[2 * s + PASS] = PASS == 0 ? q : __dsqrt_rn(q);
+}
+
+// Object-array order: a[0] + a[1] + ... left to right.  One warp per layer: the warp stages 256 elements at a
+// time in shared memory (coalesced), lane 0 adds them in order.
+#define SEQ_CHUNK 256
+__global__ void __launch_bounds__(32)
+k_stats_sequential(const double* __restrict__ w, double* __restrict__ w_out, const StatSegD* __restrict__ segs, int nseg,
+                   double* __restrict__ stats) {
+    __shared__ double buf[2][SEQ_CHUNK];
+    const int s = blockIdx.x;
+    if (s >= nseg) return;
+    const StatSegD sg = segs[s];
+    const uint32_t lane = threadIdx.x;
+    if (sg.n == 0) { if (lane == 0) { stats[2 * s] = stats[2 * s + 1] = __longlong_as_double(0x7ff8000000000000ll); } return; }
+    double mean = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        double acc = 0.0;
+        const double* src = (pass == 1 && w_out) ? w_out + sg.begin : w + sg.begin;
+        const bool shift_here = pass == 0 || !w_out;
+        auto stage = [&](uint64_t c0, int b) {
+            for (uint32_t i = lane; i < SEQ_CHUNK; i += 32u) {
+                const uint64_t e = c0 + i;
+                if (e < sg.n) {
+                    double v = shift_here ? __dadd_rn(src[e], sg.shift) : src[e];
+                    if (pass == 0) { if (w_out) w_out[sg.begin + e] = v; }
+                    else { const double d = __dsub_rn(v, mean); v = __dmul_rn(d, d); }
+                    buf[b][i] = v;
+                }
+            }
+        };
+        stage(0, 0);
+        __syncwarp();
+        int b = 0;
+        for (uint64_t c0 = 0; c0 < sg.n; c0 += SEQ_CHUNK, b ^= 1) {
+            if (c0 + SEQ_CHUNK < sg.n) stage(c0 + SEQ_CHUNK, b ^ 1);           // next chunk in flight while lane 0 adds
+            if (lane == 0) {
+                const uint32_t m = (uint32_t)(sg.n - c0 < SEQ_CHUNK ? sg.n - c0 : SEQ_CHUNK);
+                uint32_t i = 0;
+                if (c0 == 0) { acc = buf[b][0]; i = 1; }                        // no identity: the sum starts at a[0]
+                for (; i < m; ++i) acc = __dadd_rn(acc, buf[b][i]);
+            }
+            __syncwarp();
+        }
+        if (pass == 0) {
+            mean = __ddiv_rn(__shfl_sync(0xffffffffu, acc, 0), (double)sg.n);
+            if (lane == 0) stats[2 * s] = mean;
+        } else if (lane == 0) {
+            stats[2 * s + 1] = __dsqrt_rn(__ddiv_rn(acc, (double)sg.n));
+        }
+        __syncwarp();
+    }
+}
+
+// host: walk the recursion of one layer down to the groups, recording the mid nodes on the way
+static void plan_node(uint64_t begin, uint64_t n, uint32_t seg, bool in_mid, std::vector<StatGroup>& groups, std::vector<StatMid>& mids) {
+    if (!in_mid && n <= MID_ELEMS) {
+        StatMid m; m.n = n; m.first_group = (uint32_t)groups.size(); m.seg = seg;
+        mids.push_back(m);
+        in_mid = true;
+    }
+    if (n <= GROUP_ELEMS) {
+        StatGroup g; g.begin = begin; g.n = (uint32_t)n; g.seg = seg;
+        groups.push_back(g);
+        return;
+    }
+    const uint64_t n2 = pw_left(n);
+    plan_node(begin, n2, seg, in_mid, groups, mids);
+    plan_node(begin + n2, n - n2, seg, in_mid, groups, mids);
+}
+
+extern "C" int flashe_segment_stats(flashe_ctx* ctx, const double* w, double* w_out, uint64_t total, const uint64_t* seg_end,
+                                    const double* shift, int nseg, int order, double* stats_out, void* stream) {
+    flashe_ctx_info info;
+    { int rc = flashe_ctx_get_info(ctx, &info); if (rc) return rc; }
+    FlasheDeviceGuard guard(info.device);
+    if (!guard.ok) return flashe_fail(FLASHE_ECUDA, "cudaSetDevice failed");
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (nseg < 1 || !seg_end) return flashe_fail(FLASHE_EINVAL, "need nseg >= 1 and seg_end");
+    if (seg_end[nseg - 1] != total) return flashe_fail(FLASHE_EINVAL, "seg_end[nseg-1] must equal total");
+    if (!stats_out) return flashe_fail(FLASHE_EINVAL, "stats_out is NULL");
+    if (total && !w) return flashe_fail(FLASHE_EINVAL, "w is NULL");
+    if (order != FLASHE_SUM_PAIRWISE && order != FLASHE_SUM_SEQUENTIAL) return flashe_fail(FLASHE_EINVAL, "unknown summation order");
+    std::vector<StatSegD> segs((size_t)nseg);
+    std::vector<StatGroup> groups;
+    std::vector<StatMid> mids;
+    uint64_t prev = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (seg_end[s] < prev) return flashe_fail(FLASHE_EINVAL, "seg_end must be ascending");
+        segs[s].begin = prev; segs[s].n = seg_end[s] - prev; segs[s].shift = shift ? shift[s] : 0.0;
+        segs[s].first_mid = (uint32_t)mids.size();
+        if (order == FLASHE_SUM_PAIRWISE && segs[s].n) plan_node(prev, segs[s].n, (uint32_t)s, false, groups, mids);
+        segs[s].n_mid = (uint32_t)mids.size() - segs[s].first_mid;
+        prev = seg_end[s];
+    }
+    if (groups.size() > 0xfffffff0ull) return flashe_fail(FLASHE_EUNSUPPORTED, "vector too long for one statistics call");
+    auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_seg = pad(sizeof(StatSegD) * segs.size()), b_grp = pad(sizeof(StatGroup) * groups.size()),
+                 b_mid = pad(sizeof(StatMid) * mids.size()), b_gs = pad(8 * groups.size()), b_ms = pad(8 * mids.size());
+    uint8_t* ws = nullptr;
+    FLASHE_CUDA_TRY(cudaMallocAsync((void**)&ws, b_seg + b_grp + b_mid + b_gs + b_ms + 256, cs));
+    StatSegD* dseg = reinterpret_cast<StatSegD*>(ws);
+    StatGroup* dgrp = reinterpret_cast<StatGroup*>(ws + b_seg);
+    StatMid* dmid = reinterpret_cast<StatMid*>(ws + b_seg + b_grp);
+    double* gsum = reinterpret_cast<double*>(ws + b_seg + b_grp + b_mid);
+    double* msum = reinterpret_cast<double*>(ws + b_seg + b_grp + b_mid + b_gs);
+    cudaError_t e = cudaMemcpyAsync(dseg, segs.data(), sizeof(StatSegD) * segs.size(), cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess && !groups.empty()) e = cudaMemcpyAsync(dgrp, groups.data(), sizeof(StatGroup) * groups.size(), cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess && !mids.empty()) e = cudaMemcpyAsync(dmid, mids.data(), sizeof(StatMid) * mids.size(), cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);   // the host vectors (pageable memory) go out of scope
+    int launches = 0;
+    if (e == cudaSuccess && order == FLASHE_SUM_SEQUENTIAL) {
+        k_stats_sequential<<<nseg, 32, 0, cs>>>(w, w_out, dseg, nseg, stats_out);
+        launches = 1;
+        e = cudaGetLastError();
+    } else if (e == cudaSuccess) {
+        const uint32_t ng = (uint32_t)groups.size(), nm = (uint32_t)mids.size();
+        const uint64_t cap = (uint64_t)info.num_sms * 8;
+        const uint64_t want = (ng + SG_WARPS - 1) / SG_WARPS;
+        const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+        const unsigned gm = nm ? (nm + 127) / 128 : 1, gt = (unsigned)((nseg + 127) / 128);
+        if (ng) k_stats_groups<0><<<grid, SG_WARPS * 32, 0, cs>>>(w, w_out, dgrp, ng, dseg, 0, stats_out, gsum);
+        if (nm) k_stats_mids<<<gm, 128, 0, cs>>>(dmid, nm, gsum, msum);
+        k_stats_top<0><<<gt, 128, 0, cs>>>(dseg, nseg, msum, stats_out);
+        if (ng) k_stats_groups<1><<<grid, SG_WARPS * 32, 0, cs>>>(w_out ? w_out : w, nullptr, dgrp, ng, dseg, w_out ? 0 : 1, stats_out, gsum);
+        if (nm) k_stats_mids<<<gm, 128, 0, cs>>>(dmid, nm, gsum, msum);
+        k_stats_top<1><<<gt, 128, 0, cs>>>(dseg, nseg, msum, stats_out);
+        launches = 2 + (ng ? 2 : 0) + (nm ? 2 : 0);
+        e = cudaGetLastError();
+    }
+    flashe_count_launches(launches);
+    cudaFreeAsync(ws, cs);
+    if (e != cudaSuccess) return flashe_fail(FLASHE_ECUDA, std::string("flashe_segment_stats: ") + cudaGetErrorString(e));
+    return FLASHE_OK;
+}

@@ -2,7 +2,7 @@
 //
 //   f1  wire bit-packing          framework/jzf_weights.py:45-137 (_to_bytes / _from_bytes), 155-231
 //   f2  top-k sparsify + residual framework/homo/procedure/jzf_aggregator.py:578-623 (Client.sparsify)
-//   f3  per-layer statistics      secureprotol/jzf_quantize.py:542-564 (normalize / unnormalize)
+//   (f3, the per-layer statistics of secureprotol/jzf_quantize.py:542-564, lives in flashe_stats.cu)
 //
 // All three are HBM-bound byte / integer / reduction work: grid-stride kernels with grids capped at a
 // multiple of the SM count, wide accesses where the layout allows.  No tensor cores.
@@ -527,85 +527,6 @@ k_topk_write(const float* __restrict__ x, const float* __restrict__ res_in, cons
 }
 
 // =================================================================================================
-// f3  per-layer statistics around decode (QuantizingClient.unnormalize, sp/jzf_quantize.py:549-564):
-//     w += past_mean[layer];  past_mean[layer] = mean(w);  past_std[layer] = std(w)   (population std)
-// Two deterministic passes (np.std is two-pass: mean first, then mean of squared deviations):
-// fixed tile -> block-partial -> per-layer serial sum of the partials in tile order.  Floating point:
-// the summation ORDER differs from numpy's (pairwise for float64 arrays, sequential for the object
-// arrays the reference actually holds), so parity is to a stated tolerance, not bit-exact.
-// =================================================================================================
-#define ST_THREADS 256
-#define ST_PER 16
-#define ST_TILE (ST_THREADS * ST_PER)
-
-struct StatSeg { uint64_t begin, end, tile0; double shift; };   // tile0 = first tile number of the segment
-
-__device__ __forceinline__ int seg_of_tile(const StatSeg* __restrict__ segs, int nseg, uint64_t tile) {
-    int lo = 0, hi = nseg - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (segs[mid].tile0 <= tile) lo = mid; else hi = mid - 1; }
-    return lo;
-}
-
-__device__ __forceinline__ double block_sum(double v, double* sh) {
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-    if ((threadIdx.x & 31u) == 0) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double r = 0.0;
-    if (threadIdx.x == 0) for (int w = 0; w < ST_THREADS / 32; ++w) r += sh[w];
-    __syncthreads();
-    return r;   // valid in thread 0
-}
-
-// PASS 0: w_out = w + shift, partial = sum(w_out).  PASS 1: partial = sum((w - mean)^2); add_shift says
-// whether w still lacks the shift (no w_out was written).
-template <int PASS>
-__global__ void __launch_bounds__(ST_THREADS)
-k_stats_partial(const double* w, double* w_out, const StatSeg* __restrict__ segs, int nseg, uint64_t ntiles,
-                int add_shift, const double* __restrict__ stats, double* __restrict__ partial) {
-    __shared__ double sh[ST_THREADS / 32];
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int s = seg_of_tile(segs, nseg, tile);
-        const StatSeg sg = segs[s];
-        const uint64_t base = sg.begin + (tile - sg.tile0) * ST_TILE;
-        const double mean = PASS == 1 ? stats[2 * s] : 0.0;
-        double acc = 0.0;
-#pragma unroll 4
-        for (int r = 0; r < ST_PER; ++r) {
-            const uint64_t i = base + (uint64_t)r * ST_THREADS + threadIdx.x;
-            if (i < sg.end) {
-                if (PASS == 0) {
-                    const double v = __dadd_rn(w[i], sg.shift);
-                    if (w_out) w_out[i] = v;
-                    acc += v;
-                } else {
-                    const double d = (add_shift ? __dadd_rn(w[i], sg.shift) : w[i]) - mean;
-                    acc += d * d;
-                }
-            }
-        }
-        const double tot = block_sum(acc, sh);
-        if (threadIdx.x == 0) partial[tile] = tot;
-    }
-}
-
-// one warp per segment: partials summed in tile order (lane-strided, then a fixed shuffle tree)
-template <int PASS>
-__global__ void k_stats_final(const StatSeg* __restrict__ segs, int nseg, uint64_t ntiles, const double* __restrict__ partial,
-                              double* __restrict__ stats) {
-    const int s = blockIdx.x;
-    if (s >= nseg) return;
-    const uint64_t t0 = segs[s].tile0, t1 = s + 1 < nseg ? segs[s + 1].tile0 : ntiles;
-    double acc = 0.0;
-    for (uint64_t t = t0 + threadIdx.x; t < t1; t += 32) acc += partial[t];
-    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
-    if (threadIdx.x == 0) {
-        const double n = (double)(segs[s].end - segs[s].begin);
-        if (PASS == 0) stats[2 * s] = n > 0 ? acc / n : 0.0;
-        else stats[2 * s + 1] = n > 0 ? sqrt(acc / n) : 0.0;
-    }
-}
-
-// =================================================================================================
 // C ABI
 // =================================================================================================
 extern "C" {
@@ -755,43 +676,6 @@ int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_
     }
     flashe_count_launches(launches);
     if (e != cudaSuccess) return flashe_fail(FLASHE_ECUDA, std::string("flashe_topk_sparsify: ") + cudaGetErrorString(e));
-    return FLASHE_OK;
-}
-
-int flashe_segment_stats(flashe_ctx* ctx, const double* w, double* w_out, uint64_t total, const uint64_t* seg_end,
-                         const double* shift, int nseg, double* stats_out, void* stream) {
-    WIRE_ENTER(ctx);
-    if (nseg < 1 || !seg_end) return flashe_fail(FLASHE_EINVAL, "need nseg >= 1 and seg_end");
-    if (seg_end[nseg - 1] != total) return flashe_fail(FLASHE_EINVAL, "seg_end[nseg-1] must equal total");
-    if (!stats_out) return flashe_fail(FLASHE_EINVAL, "stats_out is NULL");
-    if (total && !w) return flashe_fail(FLASHE_EINVAL, "w is NULL");
-    std::vector<StatSeg> segs((size_t)nseg);
-    uint64_t prev = 0, ntiles = 0;
-    for (int s = 0; s < nseg; ++s) {
-        if (seg_end[s] < prev) return flashe_fail(FLASHE_EINVAL, "seg_end must be ascending");
-        segs[s].begin = prev; segs[s].end = seg_end[s]; segs[s].tile0 = ntiles; segs[s].shift = shift ? shift[s] : 0.0;
-        ntiles += ceil_div_u64(seg_end[s] - prev, ST_TILE);
-        prev = seg_end[s];
-    }
-    const size_t seg_bytes = sizeof(StatSeg) * (size_t)nseg;
-    const size_t seg_pad = (seg_bytes + 255) & ~(size_t)255;
-    uint8_t* ws = nullptr;
-    FLASHE_CUDA_TRY(cudaMallocAsync((void**)&ws, seg_pad + sizeof(double) * (size_t)(ntiles ? ntiles : 1), cs));
-    StatSeg* dseg = reinterpret_cast<StatSeg*>(ws);
-    double* partial = reinterpret_cast<double*>(ws + seg_pad);
-    cudaError_t e = cudaMemcpyAsync(dseg, segs.data(), seg_bytes, cudaMemcpyHostToDevice, cs);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);   // segs (pageable host memory) goes out of scope
-    if (e == cudaSuccess) {
-        const int grid = grid_cap(info.num_sms, ntiles, 8);
-        if (ntiles) k_stats_partial<0><<<grid, ST_THREADS, 0, cs>>>(w, w_out, dseg, nseg, ntiles, 0, stats_out, partial);
-        k_stats_final<0><<<nseg, 32, 0, cs>>>(dseg, nseg, ntiles, partial, stats_out);
-        if (ntiles) k_stats_partial<1><<<grid, ST_THREADS, 0, cs>>>(w_out ? w_out : w, nullptr, dseg, nseg, ntiles, w_out ? 0 : 1, stats_out, partial);
-        k_stats_final<1><<<nseg, 32, 0, cs>>>(dseg, nseg, ntiles, partial, stats_out);
-        flashe_count_launches(ntiles ? 4 : 2);
-        e = cudaGetLastError();
-    }
-    cudaFreeAsync(ws, cs);
-    if (e != cudaSuccess) return flashe_fail(FLASHE_ECUDA, std::string("flashe_segment_stats: ") + cudaGetErrorString(e));
     return FLASHE_OK;
 }
 

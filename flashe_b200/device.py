@@ -313,6 +313,33 @@ class DeviceContext(object):
         _cabi.check(self.lib.flashe_batch_unpack(self._h, words.data_ptr(), nw, element_bits, factor, out.data_ptr(), self._stream()))
         return out
 
+    def batch_layout(self, seg_end, element_bits, factor):
+        """word_end[s] of the per-layer lane batching (each layer padded to a multiple of batch_size)."""
+        n = len(seg_end)
+        ends = (C.c_uint64 * n)(*[int(e) for e in seg_end])
+        out = (C.c_uint64 * n)()
+        _cabi.check(self.lib.flashe_batch_layout(self.int_bits, element_bits, factor, ends, n, out))
+        return [int(x) for x in out]
+
+    def batch_pack_layers(self, q, seg_end, element_bits, factor):
+        """Whole quantised model (uint32 [total], layers ending at seg_end) -> words [sum ceil(size/bs)]."""
+        self._check(q, torch.uint32, int(seg_end[-1]), "q")
+        n = len(seg_end)
+        ends = (C.c_uint64 * n)(*[int(e) for e in seg_end])
+        out = self.empty_words(self.batch_layout(seg_end, element_bits, factor)[-1])
+        _cabi.check(self.lib.flashe_batch_pack_layers(self._h, q.data_ptr(), ends, n, element_bits, factor, out.data_ptr(), self._stream()))
+        return out
+
+    def batch_unpack_layers(self, words, seg_end, element_bits, factor):
+        """Inverse of batch_pack_layers: words -> uint32 [total] (padding lanes dropped)."""
+        n = len(seg_end)
+        nw = self.batch_layout(seg_end, element_bits, factor)[-1]
+        self._check_words(words, nw, "words")
+        ends = (C.c_uint64 * n)(*[int(e) for e in seg_end])
+        out = torch.empty(int(seg_end[-1]), dtype=torch.uint32, device=self.device)
+        _cabi.check(self.lib.flashe_batch_unpack_layers(self._h, words.data_ptr(), ends, n, element_bits, factor, out.data_ptr(), self._stream()))
+        return out
+
     def sparse_expand(self, compact, index, total, zero: int):
         k = index.numel()
         self._check(index, torch.int64, k, "index")
@@ -423,9 +450,10 @@ class DeviceContext(object):
                                                   residual_out.data_ptr(), self._stream()))
         return values, index, residual_out
 
-    def segment_stats(self, w, seg_end, shift=None, out=None, inplace=False):
-        """unnormalize (jzf_quantize.py:549-564): w + shift per layer, then (mean, std) per layer.
-        Returns (shifted w or None, stats float64 [nseg, 2] on the device)."""
+    def segment_stats(self, w, seg_end, shift=None, out=None, inplace=False, order=_cabi.SUM_PAIRWISE):
+        """unnormalize (jzf_quantize.py:549-564): w + shift per layer, then (np.mean, np.std) per layer,
+        bit-exact in numpy's summation order (order = SUM_PAIRWISE for float64 ndarrays, SUM_SEQUENTIAL for
+        object arrays of Python floats).  Returns (shifted w or None, stats float64 [nseg, 2] on the device)."""
         L = w.numel()
         self._check(w, torch.float64, L, "w")
         nseg = len(seg_end)
@@ -435,7 +463,7 @@ class DeviceContext(object):
             out = w
         stats = torch.empty((nseg, 2), dtype=torch.float64, device=self.device)
         _cabi.check(self.lib.flashe_segment_stats(self._h, w.data_ptr(), out.data_ptr() if out is not None else None, L, ends, sh,
-                                                  nseg, stats.data_ptr(), self._stream()))
+                                                  nseg, int(order), stats.data_ptr(), self._stream()))
         return out, stats
 
 

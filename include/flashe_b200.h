@@ -215,6 +215,19 @@ int flashe_batch_pack(flashe_ctx* ctx, const uint32_t* q, uint64_t count, int el
 int flashe_batch_unpack(flashe_ctx* ctx, const void* words, uint64_t nwords, int element_bits, int factor,
                         uint32_t* q_out, void* stream);
 
+/* Lane batching of a whole model through its layer table: QuantizingClient.quantize batches
+ * each layer by itself (sp/jzf_quantize.py:447-452) and flatten_weights concatenates the layers
+ * (proc/jzf_aggregator.py:625-650), so layer s — elements [seg_end[s-1], seg_end[s]) of the flat quantised
+ * vector — is zero-padded to a multiple of batch_size and owns words [word_end[s-1], word_end[s]).
+ * flashe_batch_layout (pure host arithmetic) returns word_end[nseg]; pack reads q[seg_end[nseg-1]] and writes
+ * word_end[nseg-1] words; unpack is the inverse and drops the padding lanes.  seg_end: HOST array. */
+int flashe_batch_layout(int int_bits, int element_bits, int factor, const uint64_t* seg_end, int nseg,
+                        uint64_t* word_end_out);
+int flashe_batch_pack_layers(flashe_ctx* ctx, const uint32_t* q, const uint64_t* seg_end, int nseg,
+                             int element_bits, int factor, void* words_out, void* stream);
+int flashe_batch_unpack_layers(flashe_ctx* ctx, const void* words, const uint64_t* seg_end, int nseg,
+                               int element_bits, int factor, uint32_t* q_out, void* stream);
+
 /* Index-sparse path, masking scheme "single" (the only one that works in the reference).
  * expand_to_dense (proc/jzf_aggregator.py:150-165): dense[j] = zero_word for every j, then
  * dense[index[i]] = compact[i].  index: device int64_t[k], sorted unique, < total.  zero_word: HOST
@@ -281,12 +294,18 @@ int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_
 
 /* ---- per-layer statistics around decode -------------------------------------------
  * QuantizingClient.unnormalize (sp/jzf_quantize.py:549-564): per layer s, w += shift[s] (the past
- * mean), then stats_out[2s] = mean(w), stats_out[2s+1] = std(w) (population, two-pass as np.std).
+ * mean), then stats_out[2s] = np.mean(w), stats_out[2s+1] = np.std(w) — BIT-EXACT: the sums run in numpy's
+ * own order, because this round's std becomes next round's clipping range alpha (sp/jzf_quantize.py:403-413)
+ * and alpha enters every ciphertext.
+ *   FLASHE_SUM_PAIRWISE    float64 ndarray semantics (the batched mode's arrays): 0.0 + numpy's pairwise
+ *                          summation (blocks of <= 128 with eight accumulators, halves split at multiples of 8)
+ *   FLASHE_SUM_SEQUENTIAL  object-array semantics (the un-batched mode holds Python floats): a[0] + a[1] + ...
+ * mean = sum / n; std = sqrt(sum((w - mean)^2) / n), every operation correctly rounded, no FMA contraction.
  * w / w_out: device float64 [total] (w_out may be NULL = statistics only, or alias w); seg_end / shift:
- * HOST arrays (shift may be NULL = 0); stats_out: DEVICE double[2*nseg].  Deterministic summation
- * order, but not numpy's: parity with the reference is to 1e-12 relative, not bit-exact. */
+ * HOST arrays (shift may be NULL = 0); stats_out: DEVICE double[2*nseg]; an empty layer yields nan, nan. */
+enum { FLASHE_SUM_PAIRWISE = 0, FLASHE_SUM_SEQUENTIAL = 1 };
 int flashe_segment_stats(flashe_ctx* ctx, const double* w, double* w_out, uint64_t total,
-                         const uint64_t* seg_end, const double* shift, int nseg, double* stats_out,
+                         const uint64_t* seg_end, const double* shift, int nseg, int order, double* stats_out,
                          void* stream);
 
 /* Number of kernels this library has launched on the calling process since load (bench bookkeeping). */

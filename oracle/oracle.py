@@ -357,13 +357,19 @@ def sparsify(layers, remain, sparsity):
     return out_vals, out_rem, np.array(locations, dtype=np.int64), base
 
 
-def unnormalize_stats(w, seg_end, shift):
+def unnormalize_stats(w, seg_end, shift, order="pairwise"):
     """QuantizingClient.unnormalize (sp/jzf_quantize.py:549-564) on a flat float64 vector of layers:
-    returns (w + shift per layer, [(mean, std)] per layer) with numpy's own mean / std."""
+    returns (w + shift per layer, [(mean, std)] per layer) with numpy's own np.mean / np.std — the very
+    functions the reference calls.  order="pairwise": float64 ndarrays (the batched mode); "sequential":
+    object arrays of Python floats (the un-batched mode), which numpy sums left to right."""
     w = np.array(w, dtype=np.float64)
     stats, b = [], 0
     for e, s in zip(seg_end, shift):
         w[b:e] += s
-        stats.append((np.mean(w[b:e]) if e > b else 0.0, np.std(w[b:e]) if e > b else 0.0))
+        layer = w[b:e] if order == "pairwise" else w[b:e].astype(object)
+        if e > b:
+            stats.append((float(np.mean(layer)), float(np.std(layer))))
+        else:
+            stats.append((float("nan"), float("nan")))
         b = e
     return w, np.array(stats, dtype=np.float64)

@@ -178,6 +178,70 @@ def case_stats():
     put("stats_w_out", np.concatenate([w._weights[k] for k in keys]))
     put("stats_mean", np.array([float(v) for v in qc.past_layer_mean_list], dtype=np.float64))
     put("stats_std", np.array([float(v) for v in qc.past_layer_std_list], dtype=np.float64))
+    # the un-batched mode holds OBJECT arrays of Python floats at this point (unquantize of an object array,
+    # jzf_quantize.py:102-107): numpy then sums them left to right instead of pairwise
+    qo = ref_quant.QuantizingClient(int_bits=32, from_arbiter=None, to_arbiter=None, batch=False, element_bits=16,
+                                    padding=True, secure=True)
+    wo = _W({k: v.copy().astype(object) for k, v in layers.items()})
+    qo.past_layer_mean_list = list(shift)
+    qo.past_layer_std_list = [1.0] * len(sizes)
+    qo.unnormalize(wo)
+    put("stats_obj_w_out", np.concatenate([np.asarray(wo._weights[k], dtype=np.float64) for k in keys]))
+    put("stats_obj_mean", np.array([float(v) for v in qo.past_layer_mean_list], dtype=np.float64))
+    put("stats_obj_std", np.array([float(v) for v in qo.past_layer_std_list], dtype=np.float64))
+
+
+def case_model(flatten_weights, unflatten_weights):
+    """A whole multi-layer model through the reference's QuantizingClient (quantize -> [n-client sum] ->
+    unquantize -> unnormalize) and Client.flatten_weights / unflatten_weights, un-batched and batched.
+    Inputs and every intermediate the reference produced are stored per layer, in walking order."""
+    import federatedml.secureprotol.jzf_quantize as ref_quant
+    rng = np.random.RandomState(2024)
+    shapes = {"conv1": (3, 3, 4, 8), "dense1": (50, 17), "dense1_b": (17,), "out": (17, 3), "zzz": (1,)}
+    n = 5
+    for batch in (False, True):
+        tag = "model_b" if batch else "model_u"
+        qc = ref_quant.QuantizingClient(int_bits=120 if batch else 20, from_arbiter=None, to_arbiter=None, batch=batch,
+                                        element_bits=16, padding=True, secure=True)
+        qc.num_clients = n
+        layers = {k: (rng.standard_normal(shapes[k]) * 0.05).astype(np.float32) for k in shapes}
+        layers["zzz"] = np.zeros(1, dtype=np.float32)
+        w = _W({k: v.copy() for k, v in layers.items()})
+        keys = list(w.walking_order)
+        qc.set_layer_size_list(w)
+        qc.past_layer_std_list = [0.05, 0.07, 0.0, 0.031, 1.0]          # one zero std: alpha falls back to 0.1
+        qc.past_layer_mean_list = [0.01, -0.02, 0.0, 0.003, 0.0]
+        mean_in = list(qc.past_layer_mean_list)
+        np.random.seed(777 + int(batch))
+        qc.normalize(w)
+        qc.quantize(w)
+        put(tag + "_x", np.concatenate([layers[k].reshape(-1) for k in keys]))
+        put(tag + "_std_in", np.array(qc.past_layer_std_list, dtype=np.float64))
+        put(tag + "_mean_in", np.array(mean_in, dtype=np.float64))
+        qflat = [int(v) for k in keys for v in np.asarray(w._weights[k], dtype=object).reshape(-1)]
+        m64 = (1 << 64) - 1
+        put(tag + "_q_lo", np.array([v & m64 for v in qflat], dtype=np.uint64))
+        put(tag + "_q_hi", np.array([v >> 64 for v in qflat], dtype=np.uint64))
+        put(tag + "_q_sizes", np.array([int(np.asarray(w._weights[k]).size) for k in keys], dtype=np.int64))
+        # flatten (client side, jzf_aggregator.py:723) ... the n-client sum stands in for the server ...
+        me = types.SimpleNamespace(shape_dict=None)
+        flat = flatten_weights(me, w)
+        only = flat.walking_order[0]
+        put(tag + "_flat_len", np.array([len(flat._weights[only])], dtype=np.int64))
+        assert [int(v) for v in flat._weights[only]] == qflat
+        flat._weights[only] = flat._weights[only] * n                    # every client sent the same vector
+        # ... unflatten + unquantize + unnormalize (client side, jzf_aggregator.py:896-904).  shape_dict holds the
+        # shapes flatten saw: the word counts per layer in batched mode, no entry for the sentinel 'zzz'
+        back = unflatten_weights(me, flat)
+        qc.unquantize(back)
+        qc.unnormalize(back)
+        okeys = list(back.walking_order)
+        put(tag + "_out", np.concatenate([np.asarray(back._weights[k], dtype=np.float64).reshape(-1) for k in okeys]))
+        put(tag + "_out_is_object", np.array([int(np.asarray(back._weights[k]).dtype == object) for k in okeys], dtype=np.int64))
+        put(tag + "_mean_out", np.array([float(v) for v in qc.past_layer_mean_list], dtype=np.float64))
+        put(tag + "_std_out", np.array([float(v) for v in qc.past_layer_std_list], dtype=np.float64))
+        MANIFEST["cases"].append({"name": tag, "batch": batch, "n_clients": n, "keys": keys, "out_keys": okeys,
+                                  "shapes": [list(shapes[k]) for k in keys], "int_bits": 120 if batch else 20})
 
 
 def main():
@@ -187,6 +251,8 @@ def main():
                        extra={"LOGGER": _Log(), "_to_bytes": to_bytes, "_from_bytes": from_bytes})
     case_sparsify(sparsify)
     case_stats()
+    fw, uw = lift("federatedml/framework/homo/procedure/jzf_aggregator.py", ["flatten_weights", "unflatten_weights"], cls="Client")
+    case_model(fw, uw)
     OUT["manifest"] = np.frombuffer(json.dumps(MANIFEST).encode(), dtype=np.uint8)
     path = os.path.join(HERE, "flashe_golden_f.npz")
     np.savez_compressed(path, **OUT)

@@ -194,36 +194,61 @@ def test_sparse_round_c4_shape_end_to_end(fb):
 
 # ------------------------------------------------------------------------------------------- f3
 def test_segment_stats_golden(fb, gold):
+    """Bit-exact against what the reference's QuantizingClient.unnormalize left in past_layer_mean_list /
+    past_layer_std_list, for float64 layers (pairwise order) and for object layers (sequential order)."""
     d, _ = gold
     ctx = fb.DeviceContext(KEY, 32)
     ends = np.cumsum(d["stats_sizes"])
-    w_out, stats = ctx.segment_stats(_dev(d["stats_w"]), ends, d["stats_shift"], out=torch.empty(int(ends[-1]), dtype=torch.float64, device="cuda"))
-    assert np.array_equal(_np(w_out).view(np.uint64), d["stats_w_out"].view(np.uint64))     # w + past_mean: exact
-    s = _np(stats)
-    np.testing.assert_allclose(s[:, 0], d["stats_mean"], rtol=1e-12, atol=1e-15)
-    np.testing.assert_allclose(s[:, 1], d["stats_std"], rtol=1e-12, atol=1e-15)
-    # statistics only (no output vector) and in place give the same numbers
-    _, s2 = ctx.segment_stats(_dev(d["stats_w"]), ends, d["stats_shift"])
-    assert np.array_equal(_np(s2), s)
-    w_in = _dev(d["stats_w"])
-    _, s3 = ctx.segment_stats(w_in, ends, d["stats_shift"], inplace=True)
-    assert np.array_equal(_np(s3), s) and np.array_equal(_np(w_in), _np(w_out))
+    for order, tag in ((fb.SUM_PAIRWISE, "stats"), (fb.SUM_SEQUENTIAL, "stats_obj")):
+        w_out, stats = ctx.segment_stats(_dev(d["stats_w"]), ends, d["stats_shift"], order=order,
+                                         out=torch.empty(int(ends[-1]), dtype=torch.float64, device="cuda"))
+        assert np.array_equal(_np(w_out).view(np.uint64), d[tag + "_w_out"].view(np.uint64))     # w + past_mean
+        s = _np(stats)
+        assert np.array_equal(s[:, 0].view(np.uint64), d[tag + "_mean"].view(np.uint64)), tag
+        assert np.array_equal(s[:, 1].view(np.uint64), d[tag + "_std"].view(np.uint64)), tag
+        # statistics only (no output vector) and in place give the same numbers
+        _, s2 = ctx.segment_stats(_dev(d["stats_w"]), ends, d["stats_shift"], order=order)
+        assert np.array_equal(_np(s2).view(np.uint64), s.view(np.uint64))
+        w_in = _dev(d["stats_w"])
+        _, s3 = ctx.segment_stats(w_in, ends, d["stats_shift"], inplace=True, order=order)
+        assert np.array_equal(_np(s3).view(np.uint64), s.view(np.uint64)) and np.array_equal(_np(w_in), _np(w_out))
 
 
-def test_segment_stats_large_vs_numpy(fb):
+def test_segment_stats_bit_exact_vs_numpy_all_tree_shapes(fb):
+    """numpy's pairwise recursion at every level of the device decomposition: layers below 8 elements, around
+    the 128-element block, around the group (8192) and mid-node (262144) cuts, a 3 M-element layer, an empty
+    layer; plus the sequential (object-array) order."""
     rs = np.random.RandomState(8)
-    sizes = [3000001, 1, 999999, 4096 * 5]
+    sizes = [3000001, 1, 999999, 4096 * 5, 0, 7, 8, 9, 127, 128, 129, 255, 257, 8191, 8192, 8193, 16385, 262143, 262144, 262145,
+             524289, 2, 100003]
     ends = np.cumsum(sizes)
     w = rs.standard_normal(int(ends[-1])) * 0.3 + 1.5
-    shift = [0.0, -2.0, 0.25, 1e-3]
+    w[:1000] *= 1e6                                           # wide dynamic range: the order of the adds shows
+    shift = [float(v) for v in rs.standard_normal(len(sizes)) * 0.01]
     ctx = fb.DeviceContext(KEY, 32)
-    want_w, want = O.unnormalize_stats(w, ends, shift)
-    got_w, stats = ctx.segment_stats(_dev(w), ends, shift, out=torch.empty(w.shape[0], dtype=torch.float64, device="cuda"))
-    assert np.array_equal(_np(got_w).view(np.uint64), want_w.view(np.uint64))
-    np.testing.assert_allclose(_np(stats), want, rtol=1e-12, atol=1e-15)
-    # deterministic: same bits on a second run
-    _, again = ctx.segment_stats(_dev(w), ends, shift)
-    assert np.array_equal(_np(again), _np(stats))
+    for order, name in ((fb.SUM_PAIRWISE, "pairwise"), (fb.SUM_SEQUENTIAL, "sequential")):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")                    # numpy warns on the empty layer
+            want_w, want = O.unnormalize_stats(w, ends, shift, order=name)
+        got_w, stats = ctx.segment_stats(_dev(w), ends, shift, order=order, out=torch.empty(w.shape[0], dtype=torch.float64, device="cuda"))
+        assert np.array_equal(_np(got_w).view(np.uint64), want_w.view(np.uint64))
+        got = _np(stats)
+        live = np.array(sizes) > 0
+        assert np.array_equal(got[live].view(np.uint64), want[live].view(np.uint64)), name
+        assert np.isnan(got[~live]).all()
+
+
+def test_segment_stats_many_small_layers(fb):
+    rs = np.random.RandomState(9)
+    sizes = [int(v) for v in rs.randint(1, 700, size=400)]
+    ends = np.cumsum(sizes)
+    w = rs.standard_normal(int(ends[-1]))
+    shift = [0.0] * len(sizes)
+    ctx = fb.DeviceContext(KEY, 32)
+    _, want = O.unnormalize_stats(w, ends, shift)
+    _, stats = ctx.segment_stats(_dev(w), ends, shift)
+    assert np.array_equal(_np(stats).view(np.uint64), want.view(np.uint64))
 
 
 # ------------------------------------------------------------------------------------------- mirrors
@@ -231,6 +256,71 @@ class _W(object):
     def __init__(self, layers):
         self._weights = dict(layers)
         self.walking_order = sorted(self._weights.keys(), key=str)
+
+
+def test_quantizing_client_whole_model_matches_reference(fb, gold):
+    """The drop-in QuantizingClient + flatten / unflatten mirrors driven like the client code drives the
+    reference's (jzf_aggregator.py:714-723, 896-904) on a five-layer model with the sparse sentinel layer,
+    un-batched and batched: every quantised integer / 120-bit word, the flat vector, the decoded layers (dtype
+    included: Python floats un-batched, float64 batched) and the refreshed per-layer mean / std lists —
+    bit for bit against what the reference's own classes produced (tests/golden/make_golden_f.py)."""
+    from flashe_b200.aggregate import flatten_weights, unflatten_weights
+    from flashe_b200.secureprotol import QuantizingClient
+    d, man = gold
+    for c in [c for c in man["cases"] if c["name"].startswith("model_")]:
+        tag, batch, n, keys = c["name"], c["batch"], c["n_clients"], c["keys"]
+        shapes = {k: tuple(sh) for k, sh in zip(keys, c["shapes"])}
+        x = d[tag + "_x"]
+        offs = np.cumsum([0] + [int(np.prod(shapes[k])) for k in keys])
+        w = _W({k: x[offs[i]:offs[i + 1]].reshape(shapes[k]).copy() for i, k in enumerate(keys)})
+        qc = QuantizingClient(c["int_bits"], None, None, batch, 16, True, True)
+        qc.num_clients = n
+        qc.set_layer_size_list(w)
+        qc.past_layer_std_list = [float(v) for v in d[tag + "_std_in"]]
+        qc.past_layer_mean_list = [float(v) for v in d[tag + "_mean_in"]]
+        np.random.seed(777 + int(batch))
+        qc.normalize(w)
+        qc.quantize(w)
+        want_q = [int(lo) | (int(hi) << 64) for lo, hi in zip(d[tag + "_q_lo"], d[tag + "_q_hi"])]
+        got_q = [int(v) for k in keys for v in np.asarray(w._weights[k], dtype=object).reshape(-1)]
+        assert got_q == want_q, tag
+        assert [int(np.asarray(w._weights[k]).size) for k in keys] == [int(v) for v in d[tag + "_q_sizes"]]
+        w, shape_dict = flatten_weights(w)
+        only = w.walking_order[0]
+        assert len(w._weights[only]) == int(d[tag + "_flat_len"][0]) and "zzz" not in shape_dict
+        w._weights[only] = w._weights[only] * n
+        back = unflatten_weights(w, shape_dict)
+        assert list(back.walking_order) == c["out_keys"]
+        qc.unquantize(back)
+        qc.unnormalize(back)
+        got = np.concatenate([np.asarray(back._weights[k], dtype=np.float64).reshape(-1) for k in c["out_keys"]])
+        assert np.array_equal(got.view(np.uint64), d[tag + "_out"].view(np.uint64)), tag
+        assert [int(np.asarray(back._weights[k]).dtype == object) for k in c["out_keys"]] == [int(v) for v in d[tag + "_out_is_object"]]
+        assert [tuple(back._weights[k].shape) for k in c["out_keys"]] == [shapes[k] for k in c["out_keys"]]
+        assert np.array_equal(np.array([float(v) for v in qc.past_layer_mean_list]).view(np.uint64), d[tag + "_mean_out"].view(np.uint64)), tag
+        assert np.array_equal(np.array([float(v) for v in qc.past_layer_std_list]).view(np.uint64), d[tag + "_std_out"].view(np.uint64)), tag
+
+
+def test_batch_pack_layers_equals_per_layer_pack(fb):
+    """The layer table version packs every layer by itself (zero padding per layer), in one launch."""
+    ctx = fb.DeviceContext(KEY, 120)
+    rs = np.random.RandomState(12)
+    sizes = [1, 6, 7, 0, 600, 12, 5, 100003]
+    ends = [int(v) for v in np.cumsum(sizes)]
+    q = rs.randint(0, 65536, size=ends[-1]).astype(np.uint32)
+    e, f = 16, 4                                              # lanes of 20 bits, 6 per word
+    words = ctx.batch_pack_layers(_dev(q), ends, e, f)
+    wend = ctx.batch_layout(ends, e, f)
+    assert wend == [int(v) for v in np.cumsum([(n + 5) // 6 for n in sizes])]
+    got = _np(words)
+    b = wb = 0
+    for n_, e_, we in zip(sizes, ends, wend):
+        if n_:
+            want = O.batch(q[b:e_], 120, e, f)
+            assert np.array_equal(got[wb:we], want)
+        b, wb = e_, we
+    back = ctx.batch_unpack_layers(words, ends, e, f)
+    assert np.array_equal(_np(back), q)
 
 
 def test_reference_shaped_mirrors(fb, gold):

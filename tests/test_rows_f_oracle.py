@@ -87,3 +87,9 @@ def test_unnormalize_stats_match_reference(gold):
     assert np.array_equal(w_out.view(np.uint64), d["stats_w_out"].view(np.uint64))
     assert np.array_equal(stats[:, 0].view(np.uint64), d["stats_mean"].view(np.uint64))
     assert np.array_equal(stats[:, 1].view(np.uint64), d["stats_std"].view(np.uint64))
+    # object arrays (Python floats): the reference's un-batched mode; numpy sums those left to right
+    w_out, stats = O.unnormalize_stats(d["stats_w"], ends, d["stats_shift"], order="sequential")
+    assert np.array_equal(w_out.view(np.uint64), d["stats_obj_w_out"].view(np.uint64))
+    assert np.array_equal(stats[:, 0].view(np.uint64), d["stats_obj_mean"].view(np.uint64))
+    assert np.array_equal(stats[:, 1].view(np.uint64), d["stats_obj_std"].view(np.uint64))
+    assert not np.array_equal(d["stats_obj_std"].view(np.uint64), d["stats_std"].view(np.uint64))   # the order matters

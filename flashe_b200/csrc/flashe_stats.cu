@@ -21,48 +21,31 @@
 //
 // The pairwise tree depends only on the sizes, so it is cut into three levels that are each enumerated
 // where that is cheap: the HOST walks the recursion down to nodes of at most GROUP_ELEMS elements ("groups")
-// and MID_ELEMS elements ("mid nodes"); one WARP per group walks the rest of the recursion down to the
-// <= 128-element leaves, evaluates them eight lanes per leaf exactly as numpy's unrolled loop does, and
-// combines them; one thread per mid node combines its groups, one thread per layer its mid nodes.
+// and MID_ELEMS elements ("mid nodes") and lists the <= 128-element leaves below a group once per distinct
+// group size; one WARP per group evaluates its leaves eight lanes per leaf exactly as numpy's unrolled loop
+// does and folds them up the group's tree; one thread per mid node combines its groups, one thread per layer
+// its mid nodes.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
 
 #include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "flashe_internal.h"
 
 #define GROUP_ELEMS 8192u       // a group is a tree node with <= 8192 elements whose parent has more
 #define MID_ELEMS 262144u
-#define MAX_LEAVES 128          // leaves of a group: sizes are in [64, 128] as soon as the group has > 128 elements
 #define SG_WARPS 8
 
-struct StatGroup { uint64_t begin; uint32_t n; uint32_t seg; };
+struct StatGroup { uint64_t begin; uint32_t n; uint32_t seg; uint32_t shape; uint32_t nleaf; };   // shape: first leaf descriptor
 struct StatMid { uint64_t n; uint32_t first_group; uint32_t seg; };
 struct StatSegD { uint64_t begin, n; uint32_t first_mid, n_mid; double shift; };
 
 static __host__ __device__ __forceinline__ uint64_t pw_left(uint64_t n) { uint64_t h = n >> 1; return h - (h & 7ull); }
-
-// numpy's <= 128-element block on 8 lanes: lane j owns accumulator r[j]; returns the block sum in every lane
-// of the 8-lane group.  VAL(i) yields element i of the block.
-template <typename F>
-__device__ __forceinline__ double pw_leaf(uint32_t n, uint32_t j, uint32_t gmask, F val) {
-    if (n < 8u) {                               // (only a whole layer can be this small)
-        double r = 0.0;
-        for (uint32_t i = 0; i < n; ++i) r = __dadd_rn(r, val(i));
-        return r;
-    }
-    const uint32_t n8 = n - (n & 7u);
-    double r = val(j);
-    for (uint32_t i = 8u; i < n8; i += 8u) r = __dadd_rn(r, val(i + j));
-    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));          // r0+r1 | r2+r3 | r4+r5 | r6+r7
-    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));          // (r0+r1)+(r2+r3) | (r4+r5)+(r6+r7)
-    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
-    for (uint32_t i = n8; i < n; ++i) r = __dadd_rn(r, val(i));
-    return r;
-}
 
 // combine the sums of consecutive sub-nodes of a node with `n` elements: sub-nodes are the nodes of the
 // recursion with at most `cut` elements; *cur walks their sums in depth-first order
@@ -74,15 +57,25 @@ __device__ double pw_combine(uint64_t n, uint64_t cut, const double* sums, uint3
     return __dadd_rn(a, b);
 }
 
+// Leaf descriptors of a group shape (the tree below a group depends only on its size, so groups of equal size
+// share one list, built by the host): bits 0-12 offset of the leaf in the group, 13-19 its size - 1, 20-27 its
+// heap index in the group's tree (root 1, children 2i and 2i+1; depth <= 7 because sizes halve down to <= 128).
+#define LEAF_OFF(d) ((d) & 0x1fffu)
+#define LEAF_N(d) ((((d) >> 13) & 0x7fu) + 1u)
+#define LEAF_HEAP(d) (((d) >> 20) & 0xffu)
+
 // PASS 0: v = w + shift (stored to w_out when given), group sum of v.
 // PASS 1: group sum of (x - mean)^2, x = w_out, or w + shift when no w_out was written.
+// One warp per group.  Leaves go four at a time, eight lanes each: lane j of a leaf owns numpy's accumulator
+// r[j] (all of its <= 16 loads are issued before the adds).  Leaf sums land in the group's heap-indexed node
+// array in shared memory, which is then folded level by level (children 2i, 2i+1 -> i), 32 nodes per step.
 template <int PASS>
 __global__ void __launch_bounds__(SG_WARPS * 32)
 k_stats_groups(const double* __restrict__ w, double* __restrict__ w_out, const StatGroup* __restrict__ groups, uint32_t ngroups,
-               const StatSegD* __restrict__ segs, int add_shift, const double* __restrict__ stats, double* __restrict__ gsum) {
-    __shared__ uint32_t leaf_off[SG_WARPS][MAX_LEAVES];
-    __shared__ uint8_t leaf_n[SG_WARPS][MAX_LEAVES];
-    __shared__ double leaf_sum[SG_WARPS][MAX_LEAVES];
+               const StatSegD* __restrict__ segs, const uint32_t* __restrict__ shapes, int add_shift,
+               const double* __restrict__ stats, double* __restrict__ gsum) {
+    __shared__ double node[SG_WARPS][256];
+    __shared__ uint8_t present[SG_WARPS][256];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t sub = lane >> 3, j = lane & 7u;            // four 8-lane groups per warp
     const uint32_t gmask = 0xffu << (8u * sub);
@@ -90,58 +83,64 @@ k_stats_groups(const double* __restrict__ w, double* __restrict__ w_out, const S
         const StatGroup gr = groups[g];
         const double shift = segs[gr.seg].shift;
         const double mean = PASS == 1 ? stats[2 * gr.seg] : 0.0;
-        // leaves of the group, depth first (lane 0 walks the size recursion with a small stack)
-        uint32_t nleaf = 0;
-        if (lane == 0) {
-            uint32_t st_n[16], st_o[16]; int sp = 0;
-            st_n[0] = gr.n; st_o[0] = 0; sp = 1;
-            while (sp) {
-                --sp;
-                const uint32_t n = st_n[sp], o = st_o[sp];
-                if (n <= 128u) { leaf_off[warp][nleaf] = o; leaf_n[warp][nleaf] = (uint8_t)(n == 128u ? 0u : n) ; ++nleaf; }
-                else {
-                    const uint32_t n2 = (uint32_t)pw_left(n);
-                    st_n[sp] = n - n2; st_o[sp] = o + n2; ++sp;       // right half: visited after the left
-                    st_n[sp] = n2; st_o[sp] = o; ++sp;
-                }
-            }
-        }
-        nleaf = __shfl_sync(0xffffffffu, nleaf, 0);
-        __syncwarp();
         const double* src = w + gr.begin;
         double* dst = (PASS == 0 && w_out) ? w_out + gr.begin : nullptr;
-        for (uint32_t l0 = 0; l0 < nleaf; l0 += 4u) {
+        reinterpret_cast<uint64_t*>(present[warp])[lane] = 0ull;
+        __syncwarp();
+        auto val = [&](uint32_t idx) -> double {               // element idx of the group, as the pass sees it
+            if (PASS == 0) {
+                const double v = __dadd_rn(src[idx], shift);
+                if (dst) dst[idx] = v;
+                return v;
+            } else {
+                const double x = add_shift ? __dadd_rn(src[idx], shift) : src[idx];
+                const double d = __dsub_rn(x, mean);
+                return __dmul_rn(d, d);
+            }
+        };
+        for (uint32_t l0 = 0; l0 < gr.nleaf; l0 += 4u) {
             const uint32_t l = l0 + sub;
-            const bool on = l < nleaf;
-            const uint32_t off = on ? leaf_off[warp][l] : 0u;
-            uint32_t n = on ? leaf_n[warp][l] : 0u;
-            if (on && n == 0u) n = 128u;
-            auto val = [&](uint32_t i) -> double {
-                if (PASS == 0) {
-                    const double v = __dadd_rn(src[off + i], shift);
-                    if (dst) dst[off + i] = v;
-                    return v;
+            if (l < gr.nleaf) {                                 // uniform over the 8 lanes of a leaf
+                const uint32_t desc = __ldg(shapes + gr.shape + l);
+                const uint32_t off = LEAF_OFF(desc), n = LEAF_N(desc);
+                double r;
+                if (n < 8u) {                                   // (only a whole layer can be this small)
+                    r = 0.0;
+                    for (uint32_t i = 0; i < n; ++i) r = __dadd_rn(r, val(off + i));
                 } else {
-                    const double x = add_shift ? __dadd_rn(src[off + i], shift) : src[off + i];
-                    const double d = __dsub_rn(x, mean);
-                    return __dmul_rn(d, d);
+                    const uint32_t n8 = n - (n & 7u);
+                    double v[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] = (uint32_t)(8 * k) < n8 ? val(off + 8u * k + j) : 0.0;
+                    r = v[0];
+#pragma unroll
+                    for (int k = 1; k < 16; ++k) if ((uint32_t)(8 * k) < n8) r = __dadd_rn(r, v[k]);
+                    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));          // r0+r1 | r2+r3 | r4+r5 | r6+r7
+                    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));          // (r0+r1)+(r2+r3) | (r4+r5)+(r6+r7)
+                    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+                    for (uint32_t i = n8; i < n; ++i) r = __dadd_rn(r, val(off + i));   // the n % 8 tail, one by one
                 }
-            };
-            double s = 0.0;
-            if (on) s = pw_leaf(n, j, gmask, val);
-            if (on && j == 0u) leaf_sum[warp][l] = s;
+                if (j == 0u) { node[warp][LEAF_HEAP(desc)] = r; present[warp][LEAF_HEAP(desc)] = 1; }
+            }
         }
         __syncwarp();
-        if (lane == 0) {
-            uint32_t cur = 0;
-            gsum[g] = pw_combine(gr.n, 128u, leaf_sum[warp], &cur);
+        // fold the tree bottom-up: every internal node has both children
+#pragma unroll 1
+        for (int lvl = 7; lvl >= 1; --lvl) {
+            const uint32_t first = 1u << lvl, cnt = 1u << (lvl - 1);       // pairs at this level
+            for (uint32_t p = lane; p < cnt; p += 32u) {
+                const uint32_t a = first + 2u * p;
+                if (present[warp][a]) {
+                    node[warp][a >> 1] = __dadd_rn(node[warp][a], node[warp][a + 1u]);
+                    present[warp][a >> 1] = 1;
+                }
+            }
+            __syncwarp();
         }
+        if (lane == 0) gsum[g] = node[warp][1];
         __syncwarp();
     }
 }
-
-// n < 8 leaves store every element redundantly from the 8 lanes of the group when w_out is written: harmless
-// (same value), and such layers have fewer than 8 elements.
 
 __global__ void k_stats_mids(const StatMid* __restrict__ mids, uint32_t nmid, const double* __restrict__ gsum, double* __restrict__ msum) {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,6 +216,13 @@ k_stats_sequential(const double* __restrict__ w, double* __restrict__ w_out, con
 }
 
 // host: walk the recursion of one layer down to the groups, recording the mid nodes on the way
+static void shape_leaves(uint32_t off, uint32_t n, uint32_t heap, std::vector<uint32_t>& out) {
+    if (n <= 128u) { out.push_back(off | ((n - 1u) << 13) | (heap << 20)); return; }
+    const uint32_t n2 = (uint32_t)pw_left(n);
+    shape_leaves(off, n2, 2u * heap, out);
+    shape_leaves(off + n2, n - n2, 2u * heap + 1u, out);
+}
+
 static void plan_node(uint64_t begin, uint64_t n, uint32_t seg, bool in_mid, std::vector<StatGroup>& groups, std::vector<StatMid>& mids) {
     if (!in_mid && n <= MID_ELEMS) {
         StatMid m; m.n = n; m.first_group = (uint32_t)groups.size(); m.seg = seg;
@@ -224,7 +230,7 @@ static void plan_node(uint64_t begin, uint64_t n, uint32_t seg, bool in_mid, std
         in_mid = true;
     }
     if (n <= GROUP_ELEMS) {
-        StatGroup g; g.begin = begin; g.n = (uint32_t)n; g.seg = seg;
+        StatGroup g; g.begin = begin; g.n = (uint32_t)n; g.seg = seg; g.shape = 0; g.nleaf = 0;
         groups.push_back(g);
         return;
     }
@@ -258,19 +264,36 @@ extern "C" int flashe_segment_stats(flashe_ctx* ctx, const double* w, double* w_
         prev = seg_end[s];
     }
     if (groups.size() > 0xfffffff0ull) return flashe_fail(FLASHE_EUNSUPPORTED, "vector too long for one statistics call");
+    // one leaf list per distinct group size
+    std::vector<uint32_t> shapes;
+    {
+        std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> seen;
+        for (auto& g : groups) {
+            auto it = seen.find(g.n);
+            if (it == seen.end()) {
+                const uint32_t first = (uint32_t)shapes.size();
+                shape_leaves(0u, g.n, 1u, shapes);
+                it = seen.emplace(g.n, std::make_pair(first, (uint32_t)shapes.size() - first)).first;
+            }
+            g.shape = it->second.first; g.nleaf = it->second.second;
+        }
+    }
     auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_seg = pad(sizeof(StatSegD) * segs.size()), b_grp = pad(sizeof(StatGroup) * groups.size()),
-                 b_mid = pad(sizeof(StatMid) * mids.size()), b_gs = pad(8 * groups.size()), b_ms = pad(8 * mids.size());
+                 b_mid = pad(sizeof(StatMid) * mids.size()), b_gs = pad(8 * groups.size()), b_ms = pad(8 * mids.size()),
+                 b_sh = pad(4 * shapes.size());
     uint8_t* ws = nullptr;
-    FLASHE_CUDA_TRY(cudaMallocAsync((void**)&ws, b_seg + b_grp + b_mid + b_gs + b_ms + 256, cs));
+    FLASHE_CUDA_TRY(cudaMallocAsync((void**)&ws, b_seg + b_grp + b_mid + b_gs + b_ms + b_sh + 256, cs));
     StatSegD* dseg = reinterpret_cast<StatSegD*>(ws);
     StatGroup* dgrp = reinterpret_cast<StatGroup*>(ws + b_seg);
     StatMid* dmid = reinterpret_cast<StatMid*>(ws + b_seg + b_grp);
     double* gsum = reinterpret_cast<double*>(ws + b_seg + b_grp + b_mid);
     double* msum = reinterpret_cast<double*>(ws + b_seg + b_grp + b_mid + b_gs);
+    uint32_t* dshape = reinterpret_cast<uint32_t*>(ws + b_seg + b_grp + b_mid + b_gs + b_ms);
     cudaError_t e = cudaMemcpyAsync(dseg, segs.data(), sizeof(StatSegD) * segs.size(), cudaMemcpyHostToDevice, cs);
     if (e == cudaSuccess && !groups.empty()) e = cudaMemcpyAsync(dgrp, groups.data(), sizeof(StatGroup) * groups.size(), cudaMemcpyHostToDevice, cs);
     if (e == cudaSuccess && !mids.empty()) e = cudaMemcpyAsync(dmid, mids.data(), sizeof(StatMid) * mids.size(), cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess && !shapes.empty()) e = cudaMemcpyAsync(dshape, shapes.data(), 4 * shapes.size(), cudaMemcpyHostToDevice, cs);
     if (e == cudaSuccess) e = cudaStreamSynchronize(cs);   // the host vectors (pageable memory) go out of scope
     int launches = 0;
     if (e == cudaSuccess && order == FLASHE_SUM_SEQUENTIAL) {
@@ -283,10 +306,10 @@ extern "C" int flashe_segment_stats(flashe_ctx* ctx, const double* w, double* w_
         const uint64_t want = (ng + SG_WARPS - 1) / SG_WARPS;
         const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
         const unsigned gm = nm ? (nm + 127) / 128 : 1, gt = (unsigned)((nseg + 127) / 128);
-        if (ng) k_stats_groups<0><<<grid, SG_WARPS * 32, 0, cs>>>(w, w_out, dgrp, ng, dseg, 0, stats_out, gsum);
+        if (ng) k_stats_groups<0><<<grid, SG_WARPS * 32, 0, cs>>>(w, w_out, dgrp, ng, dseg, dshape, 0, stats_out, gsum);
         if (nm) k_stats_mids<<<gm, 128, 0, cs>>>(dmid, nm, gsum, msum);
         k_stats_top<0><<<gt, 128, 0, cs>>>(dseg, nseg, msum, stats_out);
-        if (ng) k_stats_groups<1><<<grid, SG_WARPS * 32, 0, cs>>>(w_out ? w_out : w, nullptr, dgrp, ng, dseg, w_out ? 0 : 1, stats_out, gsum);
+        if (ng) k_stats_groups<1><<<grid, SG_WARPS * 32, 0, cs>>>(w_out ? w_out : w, nullptr, dgrp, ng, dseg, dshape, w_out ? 0 : 1, stats_out, gsum);
         if (nm) k_stats_mids<<<gm, 128, 0, cs>>>(dmid, nm, gsum, msum);
         k_stats_top<1><<<gt, 128, 0, cs>>>(dseg, nseg, msum, stats_out);
         launches = 2 + (ng ? 2 : 0) + (nm ? 2 : 0);

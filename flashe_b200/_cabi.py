@@ -22,7 +22,7 @@ class Span(C.Structure):
 
 class Codec(C.Structure):
     _fields_ = [("element_bits", C.c_int32), ("n_clients", C.c_int32), ("nseg", C.c_int32),
-                ("reserved", C.c_int32), ("seg_end", C.POINTER(C.c_uint64)), ("alpha", C.POINTER(C.c_double))]
+                ("batch_lane_bits", C.c_int32), ("seg_end", C.POINTER(C.c_uint64)), ("alpha", C.POINTER(C.c_double))]
 
 
 class Noise(C.Structure):

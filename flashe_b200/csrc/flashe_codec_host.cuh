@@ -13,6 +13,7 @@
 
 struct CodecHost {
     CodecDev dev;
+    uint64_t elem0;   // lane batching: first element of the span's first word
     Seg* table;  // device allocation to free (stream ordered) or NULL
 };
 
@@ -24,12 +25,25 @@ static inline int make_codec(const flashe_ctx* ctx, const flashe_span* span, con
     if (c->element_bits < 1 || c->element_bits > 24) return flashe_fail(FLASHE_EINVAL, "element_bits must be in [1, 24]");
     if (c->nseg < 1 || !c->seg_end || !c->alpha) return flashe_fail(FLASHE_EINVAL, "codec needs nseg >= 1, seg_end and alpha");
     if (decode && c->n_clients < 1) return flashe_fail(FLASHE_EINVAL, "codec.n_clients must be >= 1 for decode");
-    if (c->seg_end[c->nseg - 1] != span->total_len) return flashe_fail(FLASHE_EINVAL, "seg_end[nseg-1] must equal span.total_len");
+    // lane batching: the span counts WORDS, seg_end counts ELEMENTS; every layer is padded by itself
+    const int lane_bits = c->batch_lane_bits;
+    uint32_t bs = 0;
+    if (lane_bits) {
+        if (ctx->words != 4) return flashe_fail(FLASHE_EUNSUPPORTED, "lane batching is built for 64 < int_bits <= 128 (shipped: 120)");
+        if (lane_bits < c->element_bits || lane_bits > 32) return flashe_fail(FLASHE_EINVAL, "batch_lane_bits must be in [element_bits, 32]");
+        bs = (uint32_t)(ctx->int_bits / lane_bits);
+        if (bs == 0) return flashe_fail(FLASHE_EINVAL, "int_bits smaller than one lane");
+    } else if (c->seg_end[c->nseg - 1] != span->total_len) {
+        return flashe_fail(FLASHE_EINVAL, "seg_end[nseg-1] must equal span.total_len");
+    }
     std::vector<Seg> segs((size_t)c->nseg);
+    uint64_t words = 0;
     const int n = decode ? c->n_clients : 1;
     for (int s = 0; s < c->nseg; ++s) {
         if (s && c->seg_end[s] < c->seg_end[s - 1]) return flashe_fail(FLASHE_EINVAL, "seg_end must be ascending");
         segs[s].end = c->seg_end[s];
+        if (bs) words += (c->seg_end[s] - (s ? c->seg_end[s - 1] : 0) + bs - 1) / bs;
+        segs[s].wend = words;
         segs[s].a = (float)c->alpha[s];
         segs[s].two_a = (float)(2.0 * c->alpha[s]);
         // RN(1/two_a): the double quotient is at least 2^-49 (relative) away from any float rounding
@@ -41,8 +55,17 @@ static inline int make_codec(const flashe_ctx* ctx, const flashe_span* span, con
         segs[s].an = an;
         segs[s].two_an = 2.0 * an;
     }
+    if (bs && words != span->total_len) return flashe_fail(FLASHE_EINVAL, "span.total_len must equal the number of batched words of the layers");
     CodecDev& d = out->dev;
     d.nseg = c->nseg; d.ebits = c->element_bits;
+    d.lane_bits = (uint32_t)lane_bits; d.bs = bs;
+    out->elem0 = 0;
+    if (bs) {                     // first element of word span->begin: what every element-indexed pointer of the call addresses
+        int lo = 0;
+        while (lo < c->nseg - 1 && span->begin >= segs[lo].wend) ++lo;
+        const uint64_t ebeg = lo ? segs[lo - 1].end : 0, wbeg = lo ? segs[lo - 1].wend : 0;
+        out->elem0 = span->begin >= words ? segs[c->nseg - 1].end : ebeg + (span->begin - wbeg) * bs;
+    }
     d.scale = (float)(((int64_t)1 << c->element_bits) - 1);
     d.den = (double)((((int64_t)1 << c->element_bits) - 1) * (int64_t)n);
     {

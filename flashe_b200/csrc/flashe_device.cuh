@@ -9,7 +9,8 @@
 
 #define MAX_INLINE_SEG 48
 
-struct Seg { uint64_t end; float a, two_a; float rcp_two_a, pad; double an, two_an; };  // rcp_two_a = RN(1/two_a), 0 = not usable
+struct Seg { uint64_t end; float a, two_a; float rcp_two_a, pad; double an, two_an; uint64_t wend; };  // rcp_two_a = RN(1/two_a), 0 = not usable;
+                                                   // wend: cumulative words up to and including this layer (lane batching)
 
 struct CodecDev {
     int32_t nseg;
@@ -17,6 +18,8 @@ struct CodecDev {
     float scale;             // 2^e - 1 as float32
     double den;              // (2^e - 1) * n as float64
     double den_rcp;          // RN(1 / den), or 0: use the library division
+    uint32_t lane_bits;      // lane batching (jzf_quantize.py:162-185): lane width, 0 = one element per word
+    uint32_t bs;             // lanes per word = int_bits / lane_bits
     const Seg* table;        // device table when nseg > MAX_INLINE_SEG, else NULL
     Seg seg[MAX_INLINE_SEG];
 };
@@ -40,7 +43,7 @@ __device__ __forceinline__ Seg find_seg(const CodecDev& c, uint64_t j) {
         }
         Seg r; const Seg* t = c.table + lo;
         r.end = __ldg(&t->end); r.a = __ldg(&t->a); r.two_a = __ldg(&t->two_a); r.rcp_two_a = __ldg(&t->rcp_two_a); r.pad = 0.f;
-        r.an = __ldg(&t->an); r.two_an = __ldg(&t->two_an);
+        r.an = __ldg(&t->an); r.two_an = __ldg(&t->two_an); r.wend = __ldg(&t->wend);
         return r;
     }
     while (lo < hi) {
@@ -48,6 +51,29 @@ __device__ __forceinline__ Seg find_seg(const CodecDev& c, uint64_t j) {
         if (j < c.seg[mid].end) hi = mid; else lo = mid + 1;
     }
     return c.seg[lo];
+}
+
+// Lane batching: the layer that owns WORD jw of the batched vector, the first element of that word and the
+// end of the layer (elements of the word at or past `eend` are the zero padding of jzf_quantize.py:166-171).
+struct WordPos { Seg sg; uint64_t e0, eend; };
+__device__ __forceinline__ WordPos locate_word(const CodecDev& c, uint64_t jw) {
+    WordPos p;
+    if (c.nseg == 1) { p.sg = c.seg[0]; p.e0 = jw * c.bs; p.eend = p.sg.end; return p; }
+    int lo = 0, hi = c.nseg - 1;
+    uint64_t ebeg = 0, wbeg = 0;
+    if (c.table) {
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (jw < __ldg(&c.table[mid].wend)) hi = mid; else lo = mid + 1; }
+        const Seg* t = c.table + lo;
+        p.sg.end = __ldg(&t->end); p.sg.a = __ldg(&t->a); p.sg.two_a = __ldg(&t->two_a); p.sg.rcp_two_a = __ldg(&t->rcp_two_a); p.sg.pad = 0.f;
+        p.sg.an = __ldg(&t->an); p.sg.two_an = __ldg(&t->two_an); p.sg.wend = __ldg(&t->wend);
+        if (lo) { ebeg = __ldg(&t[-1].end); wbeg = __ldg(&t[-1].wend); }
+    } else {
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (jw < c.seg[mid].wend) hi = mid; else lo = mid + 1; }
+        p.sg = c.seg[lo];
+        if (lo) { ebeg = c.seg[lo - 1].end; wbeg = c.seg[lo - 1].wend; }
+    }
+    p.e0 = ebeg + (jw - wbeg) * c.bs; p.eend = p.sg.end;
+    return p;
 }
 
 // _static_quantize_padding_asymmetric, jzf_quantize.py:55-67: four float32 ops in the reference's

@@ -645,6 +645,7 @@ int flashe_encode(flashe_ctx* ctx, const flashe_span* span, const float* x, cons
     int rc = flashe_check_span(span); if (rc) return rc;
     if (span->count == 0) return FLASHE_OK;
     if (!x || !q_out) return fail(FLASHE_EINVAL, "NULL buffer");
+    if (codec && codec->batch_lane_bits) return fail(FLASHE_EINVAL, "lane batching is fused into flashe_encode_encrypt / flashe_decrypt_decode (or use flashe_batch_pack_layers)");
     CodecHost ch; rc = make_codec(ctx, span, codec, false, cs, &ch); if (rc) return rc;
     NoiseDev nz; make_noise(noise, 0, &nz);
     k_encode<1, false><<<grid_1d(ctx, span->count, 256, 16), 256, 0, cs>>>(x, nullptr, span->begin, span->count, 32, ch.dev, nz, q_out, nullptr);
@@ -660,6 +661,7 @@ int flashe_encode_add_premasked(flashe_ctx* ctx, const flashe_span* span, const 
     int rc = flashe_check_span(span); if (rc) return rc;
     if (span->count == 0) return FLASHE_OK;
     if (!x || !mask || !ct_out) return fail(FLASHE_EINVAL, "NULL buffer");
+    if (codec && codec->batch_lane_bits) return fail(FLASHE_EINVAL, "lane batching is fused into flashe_encode_encrypt / flashe_decrypt_decode (or use flashe_batch_pack_layers)");
     CodecHost ch; rc = make_codec(ctx, span, codec, false, cs, &ch); if (rc) return rc;
     NoiseDev nz; make_noise(noise, 0, &nz);
     const uint32_t b = (uint32_t)ctx->int_bits;
@@ -767,6 +769,7 @@ int flashe_decode(flashe_ctx* ctx, const flashe_span* span, const void* v, const
     if (ctx->words == 4) return fail(FLASHE_EUNSUPPORTED, "decode takes int_bits <= 64 (unbatch 128-bit words first)");
     if (span->count == 0) return FLASHE_OK;
     if (!v || !out) return fail(FLASHE_EINVAL, "NULL buffer");
+    if (codec && codec->batch_lane_bits) return fail(FLASHE_EINVAL, "lane batching is fused into flashe_encode_encrypt / flashe_decrypt_decode (or use flashe_batch_pack_layers)");
     CodecHost ch; rc = make_codec(ctx, span, codec, true, cs, &ch); if (rc) return rc;
     const int grid = grid_1d(ctx, span->count, 256, 16);
     if (ctx->words == 1 && (((uintptr_t)v | (uintptr_t)out) & 15u) == 0) {

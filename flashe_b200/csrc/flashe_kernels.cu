@@ -355,7 +355,7 @@ static int encode_encrypt_impl(flashe_ctx* ctx, uint32_t iter, int32_t idx0, int
     NoiseDev nz; make_noise(noise, u_stride, &nz);
     IoDev io; memset(&io, 0, sizeof(io));
     io.in = x; io.in_stride = x_stride; io.out = ct_out; io.out_stride = ct_stride; io.aux = q_out;
-    io.n_clients = (uint32_t)n_clients; io.share = (share && dbl) ? 1u : 0u;
+    io.n_clients = (uint32_t)n_clients; io.share = (share && dbl) ? 1u : 0u; io.elem0 = ch.elem0;
     rc = io.share ? flashe_launch_stream_encode_shared(ctx, st, g, io, ch.dev, nz, cs)
                   : flashe_launch_stream_encode(ctx, st, g, io, ch.dev, nz, cs);
     free_codec(&ch, cs);
@@ -383,7 +383,8 @@ int flashe_decrypt_decode(flashe_ctx* ctx, uint32_t iter, const int32_t* add_idx
                           void* stream) {
     ENTER(ctx);
     int rc = flashe_check_span(span); if (rc) return rc;
-    if (ctx->words == 4) return fail(FLASHE_EUNSUPPORTED, "decrypt_decode takes int_bits <= 64 (decrypt, unbatch, decode for 128-bit words)");
+    if (ctx->words == 4 && !(codec && codec->batch_lane_bits))
+        return fail(FLASHE_EUNSUPPORTED, "decrypt_decode of 16-byte words needs a lane-batching codec (batch_lane_bits): one element per 128-bit word has no decode");
     int32_t prf[MAXS], sg[MAXS];
     rc = build_decrypt_streams(add_idx, na, minus_idx, ns, prf, sg); if (rc) return rc;
     if (span->count == 0) return FLASHE_OK;
@@ -391,7 +392,7 @@ int flashe_decrypt_decode(flashe_ctx* ctx, uint32_t iter, const int32_t* add_idx
     StreamTab st; rc = make_streams(ctx, iter, prf, sg, na + ns, &st); if (rc) return rc;
     Geom g; make_geom(ctx, span, pick_sup(ctx, span, 1), &g);
     CodecHost ch; rc = make_codec(ctx, span, codec, true, cs, &ch); if (rc) return rc;
-    IoDev io; memset(&io, 0, sizeof(io)); io.in = agg_in; io.outf = out; io.aux = p_out; io.n_clients = 1;
+    IoDev io; memset(&io, 0, sizeof(io)); io.in = agg_in; io.outf = out; io.aux = p_out; io.n_clients = 1; io.elem0 = ch.elem0;
     NoiseDev nz; memset(&nz, 0, sizeof(nz));
     rc = flashe_launch_stream_decode(ctx, st, g, io, ch.dev, nz, cs);
     free_codec(&ch, cs);

@@ -415,7 +415,11 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     // m = 4, chunk starts off a 16-byte boundary: instead of 64/32-bit pieces the lanes own the memory-ALIGNED
     // quads and receive the 1-3 mask words that belong to the neighbouring block by shuffle (see fast_item)
     constexpr bool SHIFT_OK = (WORDS == 1 && MMAX == 4 && !ALIGNED && !SHARE && MODE != M_SCATTER);
-    constexpr bool W4_OK = (WORDS == 4 && (MODE == M_MASKS || MODE == M_APPLY));   // 16-byte words (the shipped 120-bit batch mode): m = 1
+    // 16-byte words (the shipped 120-bit batch mode), m = 1: masks / apply always; encode / decode when the codec
+    // batches lanes into the word (cd.bs != 0: encode -> pack -> mask and unmask -> unpack -> decode fused)
+    constexpr bool W4_OK = (WORDS == 4 && !SHARE && MODE != M_SCATTER);
+    constexpr bool W4_CODEC = (WORDS == 4 && (MODE == M_ENCODE || MODE == M_DECODE));
+    const bool w4_batched = W4_CODEC && cd.bs != 0u;
     constexpr bool W2_OK = (WORDS == 2 && MODE != M_SCATTER);                      // 8-byte words with m = 2 (b = 43..64)
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t y = 0x00010000u | (lane << 2);
@@ -466,7 +470,8 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
       // (8-byte words: only m = 2, and only chunks that start on an even element of an even shard, so that a
       //  block is one aligned 16-byte pair and one noise pair)
       const bool w2_here = W2_OK && m == 2u && ((it.cb | g.begin) & 1ull) == 0ull;
-      if ((QUAD_OK || W4_OK || w2_here) && io.quad && !(SHIFT_OK && (g.begin & 1ull))) {
+      const bool w4_here = W4_OK && (!W4_CODEC || w4_batched);
+      if ((QUAD_OK || w4_here || w2_here) && io.quad && !(SHIFT_OK && (g.begin & 1ull))) {
           const uint64_t shift = (uint64_t)mm * it.off;             // e0(w) = cb - shift + 64 m w
           const uint64_t full_end = it.cb + (MMAX == 4 ? (it.clen & ~3ull) : (it.clen / mm) * mm);   // end of the chunk's last whole block
           const uint64_t hi_e = (full_end < g.end ? full_end : g.end) + shift;
@@ -712,6 +717,56 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
           cached_win = win;                                          // every stream of the unit now has this window cached
         }
       };
+      // Lane-batched word jw (offset o in the shard) of client c, given its combined mask:
+      //   encode: the word's <= 8 lanes are quantised (jzf_quantize.py:55-67), packed first element most significant
+      //           (:162-185; lanes past the layer's end are the zero padding), masked and stored;
+      //   decode: the aggregate word is unmasked, split into its lanes (:234-251) and every real lane decoded (:102-107).
+      auto codec_word = [&](uint32_t c, uint64_t jw, uint64_t o, u128 mask) {
+        if constexpr (W4_CODEC) {
+          const WordPos wp = locate_word(cd, jw);
+          const uint32_t lb = cd.lane_bits;
+          const u128 mk128 = Word<4>::mask(g.b);
+          if (MODE == M_ENCODE) {
+              const float* xin = reinterpret_cast<const float*>(io.in) + (uint64_t)c * io.in_stride;
+              uint64_t plo = 0ull, phi = 0ull, pc = ~0ull;
+              double u0 = 0.0, u1 = 0.0;
+#pragma unroll 1
+              for (uint32_t i = 0; i < cd.bs; ++i) {
+                  const uint64_t e = wp.e0 + i;
+                  uint32_t q = 0u;
+                  if (e < wp.eend) {
+                      double u;
+                      if (nz.u) u = nz.u[(uint64_t)c * nz.u_stride + (e - io.elem0)];
+                      else {
+                          if ((e >> 1) != pc) { pc = e >> 1; noise_pair(nz, nz.stream + c, pc, u0, u1); }
+                          u = (e & 1ull) ? u1 : u0;
+                      }
+                      q = encode_one(xin[e - io.elem0], u, wp.sg, cd.scale);
+                      if (io.aux) reinterpret_cast<uint32_t*>(io.aux)[(uint64_t)c * io.in_stride + (e - io.elem0)] = q;
+                  }
+                  phi = (phi << lb) | (plo >> (64u - lb));
+                  plo = (plo << lb) | q;
+              }
+              u128 v; v.lo = plo; v.hi = phi;
+              v = Word<4>::band(Word<4>::add(v, mask), mk128);
+              stg_v4(reinterpret_cast<u128*>(io.out) + (uint64_t)c * io.out_stride + o, (uint32_t)v.lo, (uint32_t)(v.lo >> 32), (uint32_t)v.hi, (uint32_t)(v.hi >> 32));
+          } else {
+              uint32_t r0, r1, r2, r3;
+              ldg_v4(reinterpret_cast<const u128*>(io.in) + o, r0, r1, r2, r3);
+              u128 v; v.lo = ((uint64_t)r1 << 32) | r0; v.hi = ((uint64_t)r3 << 32) | r2;
+              v = Word<4>::band(Word<4>::add(v, mask), mk128);
+              if (io.aux) stg_v4(reinterpret_cast<u128*>(io.aux) + o, (uint32_t)v.lo, (uint32_t)(v.lo >> 32), (uint32_t)v.hi, (uint32_t)(v.hi >> 32));
+              const uint64_t lm = (1ull << lb) - 1ull;
+#pragma unroll 1
+              for (int i = (int)cd.bs - 1; i >= 0; --i) {
+                  const uint64_t e = wp.e0 + (uint32_t)i;
+                  if (e < wp.eend) io.outf[e - io.elem0] = decode_one((double)(v.lo & lm), wp.sg.two_an, cd.den, cd.den_rcp, wp.sg.an);
+                  v.lo = (v.lo >> lb) | (v.hi << (64u - lb));
+                  v.hi >>= lb;
+              }
+          }
+        }
+      };
       // 16-byte words, m = 1: a lane's AES block masks exactly one word (words lane and lane + 32 of the item)
       auto fast_item_w4 = [&](uint64_t w) {
         if constexpr (W4_OK) {
@@ -724,7 +779,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
           const u128 mk128 = Word<4>::mask(g.b);
           const uint32_t c = c_first;                               // (SHARE exists for the encode mode only)
           uint32_t r[NB][4];
-          if (HAS_IN) {
+          if (MODE == M_APPLY) {
               const u128* in = reinterpret_cast<const u128*>(io.in) + (uint64_t)c * io.in_stride + o0 + lane;
               ldg_v4(in, r[0][0], r[0][1], r[0][2], r[0][3]);
               ldg_v4(in + 32, r[1][0], r[1][1], r[1][2], r[1][3]);
@@ -756,6 +811,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
 #pragma unroll
           for (int h = 0; h < NB; ++h) {
               u128 v = acc[h][0];
+              if (W4_CODEC) { codec_word(c, e0 + lane + 32u * h, o0 + lane + 32u * h, v); continue; }
               if (MODE == M_APPLY) {
                   u128 x;
                   x.lo = ((uint64_t)r[h][1] << 32) | r[h][0]; x.hi = ((uint64_t)r[h][3] << 32) | r[h][2];
@@ -879,7 +935,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
       for (uint32_t sub = 0; sub < nsub; ++sub, ++it.w) {
         if (QUAD_OK && it.w >= wf_lo && it.w < wf_hi) { fast_item(it.w); continue; }
         if (W2_OK && it.w >= wf_lo && it.w < wf_hi) { fast_item_w2(it.w); continue; }
-        if (W4_OK && it.w >= wf_lo && it.w < wf_hi) { fast_item_w4(it.w); continue; }
+        if (w4_here && it.w >= wf_lo && it.w < wf_hi) { fast_item_w4(it.w); continue; }
         const uint64_t blk0 = it.w ? it.w * ITEM_BLOCKS - it.off : 0;  // first block of the item
         const uint32_t nblk = it.w ? ITEM_BLOCKS : ITEM_BLOCKS - it.off;
         if (blk0 * m >= it.clen) break;                                // past the chunk's last item
@@ -931,7 +987,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
             const bool emit = !SHARE || cc > 0;
             // ---- 1. prefetch inputs (pairs) ----
             in_t pf[PF][2];
-            if (HAS_IN && emit) {
+            if (HAS_IN && emit && !w4_batched) {
                 const in_t* in = reinterpret_cast<const in_t*>(io.in) + (uint64_t)c * io.in_stride;
 #pragma unroll
                 for (int k = 0; k < PF; ++k) {
@@ -989,6 +1045,13 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                 word_t mw0 = WT::band(slab_load<WORDS>(sl(i0)), mk);
                 word_t mw1 = WT::band(slab_load<WORDS>(sl(i0 + 1)), mk);
                 const int64_t o0 = off0 + i0;
+                if constexpr (W4_CODEC) {
+                    if (w4_batched) {                                  // lane-batched words of an edge item
+                        if (v0) codec_word(c, j0, (uint64_t)o0, mw0);
+                        if (v1) codec_word(c, j0 + 1, (uint64_t)(o0 + 1), mw1);
+                        continue;
+                    }
+                }
                 if (MODE == M_MASKS) {
                     word_t* out = reinterpret_cast<word_t*>(io.out);
                     if (v0) out[o0] = mw0;
@@ -1080,6 +1143,9 @@ static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom&
     io.te0 = ctx->d_te0;
     // 128-bit fast path preconditions (4-byte words): every row of every buffer starts 16-byte aligned
     // (16-byte words: every word is aligned as soon as the base pointers are)
+    const bool batched = cd.bs != 0u && (MODE == M_ENCODE || MODE == M_DECODE);   // element-indexed pointers need no alignment
+    if (batched) io.quad = (MODE == M_ENCODE ? aligned16(io.out) : (aligned16(io.in) && aligned16(io.aux))) ? 1u : 0u;
+    else
     io.quad = (MODE != M_SCATTER && aligned16(io.in) && aligned16(io.out) && aligned16(io.aux) && aligned16(io.outf) &&
                ((ctx->words == 1 && (io.n_clients <= 1 || ((io.in_stride | io.out_stride) & 3ull) == 0)) ||
                 (ctx->words == 2 && (io.n_clients <= 1 || ((io.in_stride | io.out_stride) & 1ull) == 0)) || ctx->words == 4)) ? 1u : 0u;

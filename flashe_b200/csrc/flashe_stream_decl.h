@@ -50,6 +50,7 @@ struct IoDev {
     uint32_t share;                         // batch double masking: compute each stream once
     uint32_t quad;                          // every buffer / stride allows 16-byte accesses per 4 elements
     uint64_t dense_len;                     // scatter: words in the dense target (indices outside are skipped)
+    uint64_t elem0;                         // lane batching: first element of the shard's first word (x / u / q / outf offsets)
     const uint32_t* te0;                    // Te0 table in global memory (flashe_ctx::d_te0), source of the shared-memory tables
 };
 

@@ -43,15 +43,48 @@ class CodecSpec:
     element_bits: int = 16
     n_clients: int = 1
     seg_end: Optional[Sequence[int]] = None
+    batch_lane_bits: int = 0     # lane batching (int_bits 65..128): lanes of element_bits + ceil(log2(num_clients)) bits;
+                                 # spans then count WORDS and seg_end (required) counts ELEMENTS
 
     def c(self, total_len):
         alphas = [float(self.alpha)] if not isinstance(self.alpha, (list, tuple)) else [float(a) for a in self.alpha]
+        if self.batch_lane_bits and self.seg_end is None:
+            raise ValueError("lane batching needs seg_end (layer ends in elements)")
         ends = [int(total_len)] if self.seg_end is None else [int(e) for e in self.seg_end]
         if len(alphas) != len(ends):
             raise ValueError("alpha and seg_end must have the same length")
         self._ends = (C.c_uint64 * len(ends))(*ends)        # keep alive for the call
         self._alphas = (C.c_double * len(alphas))(*alphas)
-        return _cabi.Codec(self.element_bits, self.n_clients, len(ends), 0, self._ends, self._alphas)
+        return _cabi.Codec(self.element_bits, self.n_clients, len(ends), int(self.batch_lane_bits), self._ends, self._alphas)
+
+    def word_ends(self, int_bits):
+        """Lane batching: cumulative words per layer (every layer padded to a multiple of int_bits // lane)."""
+        bs = int_bits // self.batch_lane_bits
+        out, prev, words = [], 0, 0
+        for e in self.seg_end:
+            words += (int(e) - prev + bs - 1) // bs
+            out.append(words)
+            prev = int(e)
+        return out
+
+    def span_elements(self, int_bits, span):
+        """Elements covered by the words [span.begin, span.begin + span.n): (first element, count).  Without
+        lane batching words are elements."""
+        if not self.batch_lane_bits:
+            return span.begin, span.n
+        bs = int_bits // self.batch_lane_bits
+        wends = self.word_ends(int_bits)
+
+        def elem_of(word):
+            prev_e = prev_w = 0
+            for e, w in zip(self.seg_end, wends):
+                if word < w:
+                    return min(prev_e + (word - prev_w) * bs, int(e))
+                prev_e, prev_w = int(e), w
+            return int(self.seg_end[-1])
+        first = elem_of(span.begin)
+        last = elem_of(span.begin + span.n)
+        return first, last - first
 
 
 @dataclass
@@ -226,9 +259,12 @@ class DeviceContext(object):
         return out
 
     def encode_encrypt(self, it, idx, scheme, x, codec: CodecSpec, noise: NoiseSpec, span: VectorSpan, out=None, q_out=None):
-        self._check(x, torch.float32, span.n, "x")
+        """Fused encode + encrypt.  With codec.batch_lane_bits (int_bits 65..128) the span counts WORDS and x
+        holds the span's ELEMENTS (the flattened layers): encode -> lane pack -> mask in one launch."""
+        ne = codec.span_elements(self.int_bits, span)[1]
+        self._check(x, torch.float32, ne, "x")
         if noise.u is not None:
-            self._check(noise.u, torch.float64, span.n, "noise.u")
+            self._check(noise.u, torch.float64, ne, "noise.u")
         out = self.empty_words(span.n) if out is None else self._check_words(out, span.n, "out")
         cc, nc = codec.c(span.total_len), noise.c()
         _cabi.check(self.lib.flashe_encode_encrypt(self._h, _iter32(it), idx, scheme, C.byref(span.c()), x.data_ptr(),
@@ -239,15 +275,16 @@ class DeviceContext(object):
     def encode_encrypt_batch(self, it, idx0, scheme, x, codec: CodecSpec, noise: NoiseSpec, span: VectorSpan, out=None,
                              share_streams=False):
         """x: float32 [n_clients, span.n]; returns words [n_clients, span.n]."""
-        if x.dim() != 2 or x.shape[1] != span.n or x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device:
-            raise ValueError("x must be a contiguous float32 [n_clients, count] tensor on %s" % self.device)
+        ne = codec.span_elements(self.int_bits, span)[1]
+        if x.dim() != 2 or x.shape[1] != ne or x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device:
+            raise ValueError("x must be a contiguous float32 [n_clients, %d] tensor on %s" % (ne, self.device))
         n = x.shape[0]
         if noise.u is not None:
-            self._check(noise.u, torch.float64, n * span.n, "noise.u")
+            self._check(noise.u, torch.float64, n * ne, "noise.u")
         out = self.empty_words(span.n, rows=n) if out is None else self._check_words(out, n * span.n, "out")
         cc, nc = codec.c(span.total_len), noise.c()
         _cabi.check(self.lib.flashe_encode_encrypt_batch(self._h, _iter32(it), idx0, n, scheme, C.byref(span.c()),
-                                                         x.data_ptr(), span.n, C.byref(cc), C.byref(nc), span.n,
+                                                         x.data_ptr(), ne, C.byref(cc), C.byref(nc), ne,
                                                          out.data_ptr(), span.n, 1 if share_streams else 0, self._stream()))
         return out
 
@@ -283,8 +320,11 @@ class DeviceContext(object):
         return out
 
     def decrypt_decode(self, it, add_idx, minus_idx, agg, codec: CodecSpec, span: VectorSpan, out=None, p_out=None):
+        """Fused decrypt + decode.  With codec.batch_lane_bits the aggregate holds lane-batched words and `out`
+        one float64 per ELEMENT of the span (unmask -> unbatch -> decode in one launch)."""
         self._check_words(agg, span.n, "agg")
-        out = torch.empty(span.n, dtype=torch.float64, device=self.device) if out is None else out
+        ne = codec.span_elements(self.int_bits, span)[1]
+        out = torch.empty(ne, dtype=torch.float64, device=self.device) if out is None else self._check(out, torch.float64, ne, "out")
         cc = codec.c(span.total_len)
         _cabi.check(self.lib.flashe_decrypt_decode(self._h, _iter32(it), _i32(add_idx), len(add_idx), _i32(minus_idx),
                                                    len(minus_idx), C.byref(span.c()), agg.data_ptr(), C.byref(cc),

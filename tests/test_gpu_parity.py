@@ -209,6 +209,102 @@ def test_batch120_golden(fb, golden):
     assert np.array_equal(_np(dec_a), golden.words("batch_decA", b))
 
 
+def test_batch120_fused_golden(fb, golden):
+    """The shipped batch mode through the FUSED entries: float32 layer -> encode -> 6-lane pack -> mask in one
+    launch per client (flashe_encode_encrypt with a lane-batching codec), and unmask -> unbatch -> decode in one
+    launch (flashe_decrypt_decode on 128-bit words) — against the reference's own outputs."""
+    c = golden.cases("batch")[0]
+    b, nj, L, n, it, e, f = (c[k] for k in ("int_bits", "n_jobs", "L", "n_clients", "iter", "element_bits", "factor"))
+    nw = c["words"]
+    ctx = ctx_for(fb, b)
+    span = fb.VectorSpan(nw, nj)
+    codec = fb.CodecSpec(alpha=[c["alpha"]], element_bits=e, n_clients=n, seg_end=[L], batch_lane_bits=e + f)
+    ct_ref = golden.words("batch_ct", b).reshape(n, nw, 2)
+    cts = ctx.empty_words(nw, rows=n)
+    for k in range(n):
+        q = torch.empty(L, dtype=torch.int32, device="cuda").view(torch.uint32)
+        ctx.encode_encrypt(it, k, fb.SCHEME_DOUBLE, _dev(golden["batch_x"][k]), codec, fb.NoiseSpec(u=_dev(golden["batch_u"][k])), span,
+                           out=cts[k], q_out=q)
+        assert np.array_equal(_np(q), golden.words("batch_q", 32).reshape(n, L)[k])
+    assert np.array_equal(_np(cts), ct_ref)
+    # all clients in one launch, with and without shared streams
+    x_all, u_all = _dev(golden["batch_x"]), _dev(golden["batch_u"]).reshape(-1)
+    for share in (False, True):
+        got = ctx.encode_encrypt_batch(it, 0, fb.SCHEME_DOUBLE, x_all, codec, fb.NoiseSpec(u=u_all), span, share_streams=share)
+        assert np.array_equal(_np(got), ct_ref), share
+    for mode, tag in ((fb.AGG_ELEMENTWISE, ""), (fb.AGG_PACKED, "A")):
+        agg = ctx.aggregate(cts, mode)
+        assert np.array_equal(_np(agg), golden.words("batch_agg" + tag, b))
+        p = ctx.empty_words(nw)
+        out = ctx.decrypt_decode(it, [n], [0], agg, codec, span, p_out=p)
+        assert np.array_equal(_np(p), golden.words("batch_dec" + tag, b))
+        if not tag:
+            assert np.array_equal(_np(out).view(np.uint64), golden["batch_decoded"].view(np.uint64))
+
+
+@pytest.mark.parametrize("n_jobs,sizes", [(8, [100, 7, 4097, 1, 3000, 6, 12]), (3, [250_001, 5, 120_000]), (16, [5]), (5, [2_000_000])])
+def test_batch_fused_multi_layer_vs_oracle(fb, n_jobs, sizes):
+    """Lane-batched model of several layers (each padded by itself): fused encode+pack+encrypt of 3 clients,
+    fused decrypt+unbatch+decode, whole vector and two word-range shards, seeded and device noise — against the
+    oracle's quantize / batch / encrypt / decrypt / unbatch / unquantize chain per layer."""
+    b, e, n, it = 120, 16, 3, 5
+    f = int(np.ceil(np.log2(n)))
+    bs = b // (e + f)
+    ends = [int(v) for v in np.cumsum(sizes)]
+    total = ends[-1]
+    alphas = [0.3 + 0.05 * i for i in range(len(sizes))]
+    ctx = ctx_for(fb, b)
+    codec = fb.CodecSpec(alpha=alphas, element_bits=e, n_clients=n, seg_end=ends, batch_lane_bits=e + f)
+    wends = codec.word_ends(b)
+    nw = wends[-1]
+    assert wends == ctx.batch_layout(ends, e, f)
+    span = fb.VectorSpan(nw, n_jobs)
+    rs = np.random.RandomState(total % 1000)
+    x = (rs.standard_normal((n, total)) * 0.2).astype(np.float32)
+    u = rs.random_sample((n, total))
+    O.set_threads(8)
+
+    def oracle_words(xc, uc):
+        parts, bgn = [], 0
+        for en, a in zip(ends, alphas):
+            parts.append(O.batch(O.quantize(xc[bgn:en], uc[bgn:en], a, e), b, e, f))
+            bgn = en
+        return np.concatenate(parts)
+
+    want_ct = np.stack([O.encrypt(KEY, b, n_jobs, it, k, "double", oracle_words(x[k], u[k])) for k in range(n)])
+    got = ctx.encode_encrypt_batch(it, 0, fb.SCHEME_DOUBLE, _dev(x), codec, fb.NoiseSpec(u=_dev(u).reshape(-1)), span)
+    assert np.array_equal(_np(got), want_ct)
+    # device noise: the documented Philox stream, one stream id per client
+    got_dn = ctx.encode_encrypt_batch(it, 0, fb.SCHEME_DOUBLE, _dev(x), codec, fb.NoiseSpec(seed=9, stream=4), span)
+    for k in range(n):
+        uk = _np(ctx.rng_uniform(9, 4 + k, 0, total))
+        assert np.array_equal(_np(got_dn[k]), O.encrypt(KEY, b, n_jobs, it, k, "double", oracle_words(x[k], uk))), k
+    want_agg = O.aggregate(b, want_ct)
+    want_p = O.decrypt(KEY, b, n_jobs, it, list(range(n)), "double", want_agg)
+    want_out, bgn, wb = [], 0, 0
+    for en, we, a in zip(ends, wends, alphas):
+        lanes = O.unbatch(want_p[wb:we], b, e, f)[:en - bgn]
+        want_out.append(O.unquantize(lanes, a, e, n))
+        bgn, wb = en, we
+    want_out = np.concatenate(want_out)
+    agg = ctx.aggregate(got)
+    p = ctx.empty_words(nw)
+    out = ctx.decrypt_decode(it, [n], [0], agg, codec, span, p_out=p)
+    assert np.array_equal(_np(p), want_p)
+    assert np.array_equal(_np(out).view(np.uint64), want_out.view(np.uint64))
+    # two word-range shards: element-indexed buffers start at the shard's first element
+    if nw >= 4:
+        cut = nw // 2 + 1
+        for lo, cnt in ((0, cut), (cut, nw - cut)):
+            sp = fb.VectorSpan(nw, n_jobs, lo, cnt)
+            e0, ne = codec.span_elements(b, sp)
+            xs = np.ascontiguousarray(x[:, e0:e0 + ne]); us = np.ascontiguousarray(u[:, e0:e0 + ne])
+            part = ctx.encode_encrypt_batch(it, 0, fb.SCHEME_DOUBLE, _dev(xs), codec, fb.NoiseSpec(u=_dev(us).reshape(-1)), sp)
+            assert np.array_equal(_np(part), want_ct[:, lo:lo + cnt]), (lo, cnt)
+            o2 = ctx.decrypt_decode(it, [n], [0], _dev(want_agg[lo:lo + cnt]), codec, sp)
+            assert np.array_equal(_np(o2).view(np.uint64), want_out[e0:e0 + ne].view(np.uint64)), (lo, cnt)
+
+
 def test_packed_aggregate_wide_words_golden(fb, golden):
     for c in golden.cases("packed_wide"):
         b, n, L = c["int_bits"], c["n_clients"], c["L"]

@@ -134,6 +134,7 @@ __global__ void k_rng_uniform(const __grid_constant__ NoiseDev nz, uint64_t begi
 template <int WORDS>
 __global__ void __launch_bounds__(256)
 k_aggregate_vec(const uint4* __restrict__ cts, uint64_t stride_vec, int n, uint64_t nvec, uint32_t b, uint4* __restrict__ out) {
+    asm volatile("griddepcontrol.launch_dependents;");   // a following k_stream may build its tables meanwhile (it waits before reading)
     for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (uint64_t)gridDim.x * blockDim.x) {
         const uint4* p = cts + v;
         if (WORDS == 1) {

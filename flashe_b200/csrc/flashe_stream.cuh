@@ -7,6 +7,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <atomic>
 #include <string>
 
@@ -433,7 +436,12 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     const uint32_t wcache = wcache_all + warp * (MAXS * 16u);
 #define PRE_OF(k) Pre{st.pre[k][0], st.pre[k][1], st.pre[k][2], st.pre[k][3]}
 
+    // Programmatic dependent launch: this grid may have been started while the previous kernel of the stream was
+    // still draining (launch_stream_t sets the attribute).  Let OUR successor start as early as it can, build the
+    // tables (they depend on nothing a predecessor writes), and only then wait for the predecessor's memory.
+    asm volatile("griddepcontrol.launch_dependents;");
     fill_tables(io.te0);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
 
     // slab word index -> byte offset; 4-byte words are skewed by one word per 32 so that the
@@ -445,7 +453,19 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     const uint64_t n_units = (st.batch && !io.share) ? g.S_cnt * io.n_clients : g.S_cnt;
     const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, gstride = (uint64_t)gridDim.x * nwarps;
 
-    for (uint64_t t = gw; t < n_units; t += gstride) {
+    // Units are dealt round-robin, one per warp and wave.  The LAST full wave and the leftover units behind it are
+    // cut into `fine` pieces of consecutive items each and dealt the same way, so that the warps finish within
+    // one piece (sup / 8 items) of each other instead of one unit (at 12.5 M elements x 64 clients per GPU a
+    // unit is ~240 us of a ~10 ms launch).
+    const uint64_t full_waves = n_units / gstride;
+    const uint64_t n_main = full_waves >= 1 ? (full_waves - 1) * gstride : 0;
+    const uint32_t fine = g.sup < 8u ? g.sup : 8u;
+    const uint32_t piece_items = (g.sup + fine - 1u) / fine;
+    const uint64_t n_virtual = n_main + (n_units - n_main) * fine;
+    for (uint64_t v = gw; v < n_virtual; v += gstride) {
+        const bool whole = v < n_main;
+        const uint64_t t = whole ? v : n_main + (v - n_main) / fine;
+        const uint32_t piece = whole ? 0u : (uint32_t)((v - n_main) % fine);
         uint32_t c_first = 0, c_count = 1;
         uint64_t S = t;
         if (st.batch) {
@@ -456,6 +476,12 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
         // chunk rule are paid once per unit, the items inside advance by ITEM_BLOCKS
         uint32_t nsub;
         Item it = decode_unit(g, g.S_lo + S, nsub);
+        if (!whole) {                                                  // this warp's piece of the unit's items
+            const uint32_t lo = piece * piece_items;
+            if (lo >= nsub) continue;
+            it.w += lo;
+            nsub = nsub - lo < piece_items ? nsub - lo : piece_items;
+        }
       uint32_t cached_win = 0xffffffffu;                             // counter window the cached round-2 terms belong to
       const uint32_t n_iter = SHARE ? c_count + 1 : c_count;
       // ---- lane-local items ------------------------------------------------------------------------
@@ -1127,7 +1153,17 @@ static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geo
     const int wpb = threads / 32;
     uint64_t blocks = ceil_div(items, (uint64_t)wpb);
     if (blocks > (uint64_t)ctx->num_sms) blocks = (uint64_t)ctx->num_sms;
-    kern<<<(unsigned)blocks, threads, SMEM_BYTES, stream>>>(ctx->ks, st, g, io, cd, nz);
+    // programmatic stream serialization: the grid may start (table fill) before the previous kernel has drained;
+    // the kernel waits (griddepcontrol.wait) before it touches global data.  FLASHE_PDL=0 turns it off.
+    static const bool pdl = [] { const char* e = getenv("FLASHE_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1u : 0u;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ctx->ks, st, g, io, cd, nz));
     flashe_count_launches(1);
     CUDA_TRY(cudaGetLastError());
     return FLASHE_OK;

@@ -146,6 +146,23 @@ class DeviceContext(object):
         except Exception:
             pass
 
+    # ------------------------------------------------------------------ CUDA graphs
+    def capture(self, fn, warmup=2):
+        """Record everything `fn()` enqueues (calls of this or other contexts on torch's current stream) into a
+        CUDA graph and return a zero-argument callable that replays it: one graph launch instead of one kernel
+        launch plus host-side argument marshalling per call — what small vectors (BASELINE configs 1-2, where a
+        round is three ~10-30 us kernels) are bound by.  `fn` must write into pre-allocated `out=` tensors and use
+        fixed arguments (iteration index, index lists): they are baked into the graph.  Layer tables with more
+        than 48 layers are uploaded with a synchronising copy and cannot be captured."""
+        for _ in range(max(1, warmup)):
+            fn()
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fn()
+        self._graphs = getattr(self, "_graphs", []) + [graph]     # keep alive as long as the context
+        return graph.replay
+
     # ------------------------------------------------------------------ helpers
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -442,6 +442,39 @@ def test_full_path_vs_oracle(fb, bits, n_jobs, L, n):
     assert np.all(np.abs(_np(out) - clipped) <= n * step * 1.01)
 
 
+def test_cuda_graph_replay_of_a_round(fb):
+    """DeviceContext.capture: the three kernels of a round recorded once, replayed on new inputs written into
+    the same buffers — same bits as the call-by-call round and as the oracle."""
+    L, n, bits, n_jobs, it = 100_003, 3, 20, 8, 1
+    ctx = ctx_for(fb, bits)
+    span = fb.VectorSpan(L, n_jobs)
+    codec = fb.CodecSpec(alpha=0.4, element_bits=16, n_clients=n)
+    noise = fb.NoiseSpec(seed=3, stream=0)
+    x = torch.zeros((n, L), dtype=torch.float32, device="cuda")
+    cts, agg = ctx.empty_words(L, rows=n), ctx.empty_words(L)
+    out = torch.empty(L, dtype=torch.float64, device="cuda")
+
+    def rnd():
+        ctx.encode_encrypt_batch(it, 0, fb.SCHEME_DOUBLE, x, codec, noise, span, out=cts)
+        ctx.aggregate(cts, fb.AGG_ELEMENTWISE, out=agg)
+        ctx.decrypt_decode(it, [n], [0], agg, codec, span, out=out)
+
+    replay = ctx.capture(rnd)
+    xs = (np.random.RandomState(2).standard_normal((n, L)) * 0.2).astype(np.float32)
+    x.copy_(_dev(xs))
+    replay()
+    torch.cuda.synchronize()
+    got_ct, got_out = _np(cts).copy(), _np(out).copy()
+    rnd()
+    torch.cuda.synchronize()
+    assert np.array_equal(got_ct, _np(cts)) and np.array_equal(got_out.view(np.uint64), _np(out).view(np.uint64))
+    q = np.stack([O.quantize(xs[c], _np(ctx.rng_uniform(3, c, 0, L)), 0.4, 16) for c in range(n)])
+    want = np.stack([O.encrypt(KEY, bits, n_jobs, it, c, "double", q[c]) for c in range(n)])
+    assert np.array_equal(got_ct, want)
+    p_want = O.decrypt(KEY, bits, n_jobs, it, list(range(n)), "double", O.aggregate(bits, want))
+    assert np.array_equal(got_out.view(np.uint64), O.unquantize(p_want, 0.4, 16, n).view(np.uint64))
+
+
 def test_single_scheme_many_streams(fb):
     """single masking decrypt subtracts one stream per survivor; > FLASHE_MAX_STREAMS needs chaining."""
     bits, n_jobs, L, n = 32, 8, 20000, 150

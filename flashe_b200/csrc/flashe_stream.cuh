@@ -79,10 +79,24 @@ __device__ __forceinline__ uint32_t addr_b3(uint32_t s, uint32_t y) {
     return __byte_perm(s, y, SEL_B3);
 #endif
 }
+#ifndef FLASHE_IMAD_B0
+#define FLASHE_IMAD_B0 0
+#endif
+// Same for the byte-0 lookup: (s << 24) via mul.lo, then ((s << 24) >> 16) + y via mad.hi.
+__device__ __forceinline__ uint32_t addr_b0(uint32_t s, uint32_t y) {
+#if FLASHE_IMAD_B0
+    uint32_t t, a;
+    asm("mul.lo.u32 %0, %1, 0x1000000;" : "=r"(t) : "r"(s));
+    asm("mad.hi.u32 %0, %1, 0x10000, %2;" : "=r"(a) : "r"(t), "r"(y));
+    return a;
+#else
+    return __byte_perm(s, y, SEL_B0);
+#endif
+}
 #define T0(s) lds_tab<0>(addr_b3((s), y))
 #define T1(s) lds_tab<128>(__byte_perm((s), y, SEL_B2))
 #define T2(s) lds_tab<0x10000>(__byte_perm((s), y, SEL_B1))
-#define T3(s) lds_tab<0x10080>(__byte_perm((s), y, SEL_B0))
+#define T3(s) lds_tab<0x10080>(addr_b0((s), y))
 
 // AES-256 of the block {w0,w1,w2,w3}; `pre` = round-1 terms hoisted by the host for (w0,w1,w2=0).
 // Output o[0..3] big-endian words (o[0] most significant).
@@ -451,7 +465,10 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     const word_t mk = WT::mask(g.b);
     const uint32_t m = g.m;
     const uint64_t n_units = (st.batch && !io.share) ? g.S_cnt * io.n_clients : g.S_cnt;
-    const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, gstride = (uint64_t)gridDim.x * nwarps;
+    // CTA-minor numbering of the warps: consecutive units go to DIFFERENT SMs first, so the units of a partial
+    // last wave spread evenly over the SMs instead of filling the first CTAs' warps (at 1 M elements x 3 clients
+    // that was 64 items on 45 SMs against 48 on the rest)
+    const uint64_t gw = (uint64_t)warp * gridDim.x + blockIdx.x, gstride = (uint64_t)gridDim.x * nwarps;
 
     // Units are dealt round-robin, one per warp and wave.  The LAST full wave and the leftover units behind it are
     // cut into `fine` pieces of consecutive items each and dealt the same way, so that the warps finish within

@@ -11,6 +11,7 @@ OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 SCHEME_SINGLE, SCHEME_DOUBLE = 0, 1
 AGG_ELEMENTWISE, AGG_PACKED = 0, 1
 SUM_PAIRWISE, SUM_SEQUENTIAL = 0, 1
+NOISE_53, NOISE_32 = 0, 1
 MAX_STREAMS = 128
 ABI_VERSION = 2
 
@@ -26,7 +27,7 @@ class Codec(C.Structure):
 
 
 class Noise(C.Structure):
-    _fields_ = [("u", C.c_void_p), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64)]
+    _fields_ = [("u", C.c_void_p), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64), ("resolution", C.c_int32), ("reserved", C.c_int32)]
 
 
 class FlasheError(RuntimeError):
@@ -60,11 +61,12 @@ SIGNATURES = {
     "flashe_encode_encrypt_batch": (_int, [_vp, _u32, C.c_int32, _int, _int, _spanp, _vp, _u64, _codecp, _noisep,
                                            _u64, _vp, _u64, _int, _vp]),
     "flashe_encode_add_premasked": (_int, [_vp, _spanp, _vp, _codecp, _noisep, _vp, _vp, _vp]),
+    "flashe_encode_add_premasked_batch": (_int, [_vp, _spanp, _int, _vp, _u64, _codecp, _noisep, _u64, _vp, _u64, _vp, _u64, _vp]),
     "flashe_aggregate": (_int, [_vp, _vp, _u64, _int, _u64, _int, _u32, _vp, _vp, _vp]),
     "flashe_aggregate_carry_fixup": (_int, [_vp, _vp, _u64, _u32, _vp]),
     "flashe_decode": (_int, [_vp, _spanp, _vp, _codecp, _vp, _vp]),
     "flashe_decrypt_decode": (_int, [_vp, _u32, _i32p, _int, _i32p, _int, _spanp, _vp, _codecp, _vp, _vp, _vp]),
-    "flashe_rng_uniform": (_int, [_vp, _u64, _u64, _u64, _u64, _vp, _vp]),
+    "flashe_rng_uniform": (_int, [_vp, _u64, _u64, _int, _u64, _u64, _vp, _vp]),
     "flashe_batch_pack": (_int, [_vp, _vp, _u64, _int, _int, _vp, _vp]),
     "flashe_batch_unpack": (_int, [_vp, _vp, _u64, _int, _int, _vp, _vp]),
     "flashe_batch_layout": (_int, [_int, _int, _int, C.POINTER(_u64), _int, C.POINTER(_u64)]),

@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRCS = [os.path.join(HERE, "csrc", f) for f in ("flashe_kernels.cu", "flashe_stream_masks.cu", "flashe_stream_apply.cu", "flashe_stream_encode.cu",
-                                                    "flashe_stream_encode_shared.cu", "flashe_stream_decode.cu", "flashe_stream_scatter.cu",
+                                                    "flashe_stream_encode_shared.cu", "flashe_stream_encode_n32.cu", "flashe_stream_decode.cu", "flashe_stream_scatter.cu",
                                                     "flashe_elementwise.cu", "flashe_wire.cu", "flashe_stats.cu")]
 DEPS = SRCS + [os.path.join(HERE, "csrc", f) for f in ("flashe_internal.h", "flashe_device.cuh", "flashe_codec_host.cuh", "flashe_stream.cuh",
                                                            "flashe_stream_decl.h")]

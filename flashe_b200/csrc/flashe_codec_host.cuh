@@ -92,6 +92,11 @@ static inline int make_codec(const flashe_ctx* ctx, const flashe_span* span, con
 }
 static inline void free_codec(CodecHost* c, cudaStream_t stream) { if (c->table) cudaFreeAsync(c->table, stream); }
 
+static inline int check_noise(const flashe_noise* nz) {
+    if (nz && nz->resolution != FLASHE_NOISE_53 && nz->resolution != FLASHE_NOISE_32) return flashe_fail(FLASHE_EINVAL, "unknown noise resolution");
+    if (nz && nz->reserved != 0) return flashe_fail(FLASHE_EINVAL, "noise.reserved must be 0");
+    return FLASHE_OK;
+}
 static inline void make_noise(const flashe_noise* nz, uint64_t u_stride, NoiseDev* d) {
     memset(d, 0, sizeof(*d));
     if (!nz) return;
@@ -99,6 +104,7 @@ static inline void make_noise(const flashe_noise* nz, uint64_t u_stride, NoiseDe
     uint32_t k0 = (uint32_t)nz->rng_seed, k1 = (uint32_t)(nz->rng_seed >> 32);
     for (int i = 0; i < 10; ++i) { d->rk[i][0] = k0; d->rk[i][1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
     d->stream = nz->rng_stream;
+    d->res32 = nz->resolution == FLASHE_NOISE_32 ? 1u : 0u;
 }
 
 

@@ -24,7 +24,7 @@ struct CodecDev {
     Seg seg[MAX_INLINE_SEG];
 };
 
-struct NoiseDev { const double* u; uint64_t u_stride; uint64_t stream; uint32_t rk[10][2]; };  // rk: Philox round keys
+struct NoiseDev { const double* u; uint64_t u_stride; uint64_t stream; uint32_t rk[10][2]; uint32_t res32; uint32_t pad; };  // rk: Philox round keys; res32: one 32-bit word per element
 
 
 // ------------------------------------------------------------------------------------------------
@@ -155,20 +155,55 @@ __device__ __forceinline__ double res53(uint32_t a, uint32_t b) {
     const double B = __hiloint2double(0x3FE00000, (int)(b >> 6));
     return __dadd_rn(__dadd_rn(A, -33554432.5), B);
 }
-// u_j in [0,1): counter (j>>1 lo, j>>1 hi, stream lo, stream hi); words (2(j&1), 2(j&1)+1) feed res53.
+// Throughput-mode resolution (flashe_noise.resolution = FLASHE_NOISE_32): u = w * 2^-32 from ONE 32-bit word, built
+// as the bit pattern of 1 + w * 2^-32 minus 1 (exact).  One Philox call then serves four elements instead of two.
+__device__ __forceinline__ double unit32(uint32_t w) {
+    return __dadd_rn(__hiloint2double((int)(0x3FF00000u | (w >> 12)), (int)(w << 20)), -1.0);
+}
+// u_j in [0,1).  53-bit resolution: counter (j>>1 lo, j>>1 hi, stream lo, stream hi), words (2(j&1), 2(j&1)+1) feed
+// res53.  32-bit resolution (N32): counter (j>>2, stream), word j&3.  The resolution is a TEMPLATE parameter: the
+// encode loop of k_stream is instruction-cache sensitive, a run-time branch around a second generator cost it 5 %.
+template <bool N32>
 __device__ __forceinline__ double noise_one(const NoiseDev& nz, uint64_t stream, uint64_t j) {
     uint32_t o[4];
+    if (N32) {
+        const uint64_t c = j >> 2;
+        philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), nz, o);
+        const uint32_t k = (uint32_t)j & 3u;
+        return unit32(k == 0u ? o[0] : (k == 1u ? o[1] : (k == 2u ? o[2] : o[3])));
+    }
     uint64_t c = j >> 1;
     philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), nz, o);
     return (j & 1) ? res53(o[2], o[3]) : res53(o[0], o[1]);
 }
 
-// Both numbers of one Philox call: u for elements 2c and 2c+1 (same values as noise_one).
+// u for elements 2c and 2c+1 (same values as noise_one).
+template <bool N32>
 __device__ __forceinline__ void noise_pair(const NoiseDev& nz, uint64_t stream, uint64_t c, double& u0, double& u1) {
     uint32_t o[4];
+    if (N32) {
+        const uint64_t q = c >> 1;
+        philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), nz, o);
+        const bool hi = (c & 1ull) != 0ull;
+        u0 = unit32(hi ? o[2] : o[0]);
+        u1 = unit32(hi ? o[3] : o[1]);
+        return;
+    }
     philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), nz, o);
     u0 = res53(o[0], o[1]);
     u1 = res53(o[2], o[3]);
+}
+// u for elements 4q .. 4q+3: one Philox call at 32-bit resolution, two at 53-bit.
+template <bool N32>
+__device__ __forceinline__ void noise_quad(const NoiseDev& nz, uint64_t stream, uint64_t q, double (&u)[4]) {
+    if (N32) {
+        uint32_t o[4];
+        philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), nz, o);
+        u[0] = unit32(o[0]); u[1] = unit32(o[1]); u[2] = unit32(o[2]); u[3] = unit32(o[3]);
+        return;
+    }
+    noise_pair<false>(nz, stream, 2ull * q, u[0], u[1]);
+    noise_pair<false>(nz, stream, 2ull * q + 1ull, u[2], u[3]);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -43,7 +43,7 @@ __global__ void k_add_premasked_v4(const uint4* __restrict__ in, const uint4* __
     }
 }
 
-template <int WORDS, bool WITH_MASK>
+template <int WORDS, bool WITH_MASK, bool N32 = false>
 __global__ void k_encode(const float* __restrict__ x, const typename Word<WORDS>::T* __restrict__ mask, uint64_t begin,
                          uint64_t count, uint32_t b, const __grid_constant__ CodecDev cd, const __grid_constant__ NoiseDev nz,
                          uint32_t* __restrict__ q_out, typename Word<WORDS>::T* __restrict__ ct_out) {
@@ -52,7 +52,7 @@ __global__ void k_encode(const float* __restrict__ x, const typename Word<WORDS>
     for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < count; o += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t j = begin + o;
         const Seg sg = find_seg(cd, j);
-        double u = nz.u ? nz.u[o] : noise_one(nz, nz.stream, j);
+        double u = nz.u ? nz.u[o] : noise_one<N32>(nz, nz.stream, j);
         uint32_t q = encode_one(x[o], u, sg, cd.scale);
         if (q_out) q_out[o] = q;
         if (WITH_MASK) ct_out[o] = WT::band(WT::add(WT::from_u32(q), mask[o]), mk);
@@ -62,20 +62,26 @@ __global__ void k_encode(const float* __restrict__ x, const typename Word<WORDS>
 // Online step after mask precomputation, 4-byte words: one thread = 4 consecutive elements (begin and
 // every pointer 16-byte aligned), 128-bit loads of x and of the precomputed mask, two Philox calls for
 // the four noise values, one 128-bit store.  12 algorithmic bytes per element: HBM-bound.
+// n_clients rows in one launch: blockIdx.y = client (row c: x + c*xs, mask + c*ms, ct_out + c*cs vectors, noise stream
+// id + c).
+template <bool N32>
 __global__ void __launch_bounds__(256)
 k_encode_premasked_v4(const uint4* __restrict__ x, const uint4* __restrict__ mask, uint64_t begin, uint64_t nvec, uint32_t mk,
-                      const __grid_constant__ CodecDev cd, const __grid_constant__ NoiseDev nz, uint4* __restrict__ ct_out) {
+                      const __grid_constant__ CodecDev cd, const __grid_constant__ NoiseDev nz, uint4* __restrict__ ct_out,
+                      uint64_t xs, uint64_t ms, uint64_t cs, uint64_t us) {
     const bool one_seg = cd.nseg == 1, one_rcp = one_seg && cd.seg[0].rcp_two_a != 0.0f;
+    const uint32_t c = blockIdx.y;
+    x += c * xs; mask += c * ms; ct_out += c * cs;
     for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t j = begin + 4ull * v;
         const uint4 xv = __ldcs(x + v), mv = __ldcs(mask + v);
         double u[4];
         if (nz.u) {
-            const double2 a = __ldcs(reinterpret_cast<const double2*>(nz.u) + 2 * v), b = __ldcs(reinterpret_cast<const double2*>(nz.u) + 2 * v + 1);
+            const double2* up = reinterpret_cast<const double2*>(nz.u + c * us) + 2 * v;
+            const double2 a = __ldcs(up), b = __ldcs(up + 1);
             u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y;
         } else {
-            noise_pair(nz, nz.stream, j >> 1, u[0], u[1]);
-            noise_pair(nz, nz.stream, (j >> 1) + 1, u[2], u[3]);
+            noise_quad<N32>(nz, nz.stream + c, j >> 2, u);                  // begin is a multiple of 4
         }
         const uint32_t xr[4] = {xv.x, xv.y, xv.z, xv.w};
         uint32_t q[4];
@@ -108,25 +114,38 @@ __global__ void k_decode(const typename Word<WORDS>::T* __restrict__ v, uint64_t
 __global__ void __launch_bounds__(256)
 k_decode_v4(const uint4* __restrict__ v, uint64_t begin, uint64_t nvec, const __grid_constant__ CodecDev cd, double* __restrict__ out) {
     const bool one_seg = cd.nseg == 1;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4 w = __ldcs(v + i);
-        const uint32_t p[4] = {w.x, w.y, w.z, w.w};
-        const uint64_t j = begin + 4ull * i;
-        double d[4];
-        Seg sg = find_seg(cd, j);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    // two independent 16-byte loads in flight per thread (the kernel is pure streaming: 4 B in, 8 B out per element)
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += 2 * stride) {
+        const uint64_t i1 = i0 + stride;
+        const bool two = i1 < nvec;
+        const uint4 wa = __ldcs(v + i0);
+        uint4 wb = make_uint4(0u, 0u, 0u, 0u);
+        if (two) wb = __ldcs(v + i1);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k && !one_seg && j + k >= sg.end) sg = find_seg(cd, j + k);
-            d[k] = decode_one((double)p[k], sg.two_an, cd.den, cd.den_rcp, sg.an);
+        for (int h = 0; h < 2; ++h) {
+            if (h && !two) break;
+            const uint64_t i = h ? i1 : i0;
+            const uint4 w = h ? wb : wa;
+            const uint32_t p[4] = {w.x, w.y, w.z, w.w};
+            const uint64_t j = begin + 4ull * i;
+            double d[4];
+            Seg sg = find_seg(cd, j);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k && !one_seg && j + k >= sg.end) sg = find_seg(cd, j + k);
+                d[k] = decode_one((double)p[k], sg.two_an, cd.den, cd.den_rcp, sg.an);
+            }
+            stg_d2(out + 4ull * i, d[0], d[1]);
+            stg_d2(out + 4ull * i + 2, d[2], d[3]);
         }
-        stg_d2(out + 4ull * i, d[0], d[1]);
-        stg_d2(out + 4ull * i + 2, d[2], d[3]);
     }
 }
 
+template <bool N32>
 __global__ void k_rng_uniform(const __grid_constant__ NoiseDev nz, uint64_t begin, uint64_t count, double* __restrict__ out) {
     for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < count; o += (uint64_t)gridDim.x * blockDim.x)
-        out[o] = noise_one(nz, nz.stream, begin + o);
+        out[o] = noise_one<N32>(nz, nz.stream, begin + o);
 }
 
 // Element-wise server sum (jzf_aggregator.py:421-430).  One thread owns one 16-byte column of the
@@ -596,11 +615,11 @@ static int sparse_sum_t(flashe_ctx* ctx, const void* const* compacts, const int6
     const word_t mk = WT::mask((uint32_t)ctx->int_bits);
     word_t zsum = WT::zero();
     for (int c = 0; c < n; ++c) zsum = WT::band(WT::add(zsum, WT::band(zeros[c], mk)), mk);
-    k_fill<WORDS><<<grid_1d(ctx, total, 256, 16), 256, 0, cs>>>((word_t*)dense_out, total, zsum);
+    k_fill<WORDS><<<GRID_OCC(ctx, k_fill<WORDS>, total, 256), 256, 0, cs>>>((word_t*)dense_out, total, zsum);
     int launches = 1;
     for (int c = 0; c < n; ++c) {
         if (!ks[c]) continue;
-        k_scatter_add<WORDS><<<grid_1d(ctx, ks[c], 256, 16), 256, 0, cs>>>((const word_t*)compacts[c], indexes[c], ks[c], total,
+        k_scatter_add<WORDS><<<GRID_OCC(ctx, k_scatter_add<WORDS>, ks[c], 256), 256, 0, cs>>>((const word_t*)compacts[c], indexes[c], ks[c], total,
                                                                            WT::band(zeros[c], mk), (uint32_t)ctx->int_bits, (word_t*)dense_out);
         ++launches;
     }
@@ -621,19 +640,19 @@ int flashe_add_premasked(flashe_ctx* ctx, const void* in, const void* mask, int 
         const bool aligned = (((uintptr_t)in | (uintptr_t)mask | (uintptr_t)out) & 15u) == 0;
         uint64_t nvec = aligned ? count / 4 : 0;
         if (nvec) {
-            k_add_premasked_v4<<<grid_1d(ctx, nvec, 256, 16), 256, 0, cs>>>((const uint4*)in, (const uint4*)mask, sign, nvec, Word<1>::mask(b) , (uint4*)out);
+            k_add_premasked_v4<<<GRID_OCC(ctx, k_add_premasked_v4, nvec, 256), 256, 0, cs>>>((const uint4*)in, (const uint4*)mask, sign, nvec, Word<1>::mask(b) , (uint4*)out);
             count_launch();
         }
         const uint64_t done = nvec * 4;
         if (done < count) {
-            k_add_premasked<1><<<grid_1d(ctx, count - done, 256, 16), 256, 0, cs>>>((const uint32_t*)in + done, (const uint32_t*)mask + done, sign, count - done, b, (uint32_t*)out + done);
+            k_add_premasked<1><<<GRID_OCC(ctx, k_add_premasked<1>, count - done, 256), 256, 0, cs>>>((const uint32_t*)in + done, (const uint32_t*)mask + done, sign, count - done, b, (uint32_t*)out + done);
             count_launch();
         }
     } else if (ctx->words == 2) {
-        k_add_premasked<2><<<grid_1d(ctx, count, 256, 16), 256, 0, cs>>>((const uint64_t*)in, (const uint64_t*)mask, sign, count, b, (uint64_t*)out);
+        k_add_premasked<2><<<GRID_OCC(ctx, k_add_premasked<2>, count, 256), 256, 0, cs>>>((const uint64_t*)in, (const uint64_t*)mask, sign, count, b, (uint64_t*)out);
         count_launch();
     } else {
-        k_add_premasked<4><<<grid_1d(ctx, count, 256, 16), 256, 0, cs>>>((const u128*)in, (const u128*)mask, sign, count, b, (u128*)out);
+        k_add_premasked<4><<<GRID_OCC(ctx, k_add_premasked<4>, count, 256), 256, 0, cs>>>((const u128*)in, (const u128*)mask, sign, count, b, (u128*)out);
         count_launch();
     }
     CUDA_TRY(cudaGetLastError());
@@ -648,8 +667,10 @@ int flashe_encode(flashe_ctx* ctx, const flashe_span* span, const float* x, cons
     if (!x || !q_out) return fail(FLASHE_EINVAL, "NULL buffer");
     if (codec && codec->batch_lane_bits) return fail(FLASHE_EINVAL, "lane batching is fused into flashe_encode_encrypt / flashe_decrypt_decode (or use flashe_batch_pack_layers)");
     CodecHost ch; rc = make_codec(ctx, span, codec, false, cs, &ch); if (rc) return rc;
+    rc = check_noise(noise); if (rc) { free_codec(&ch, cs); return rc; }
     NoiseDev nz; make_noise(noise, 0, &nz);
-    k_encode<1, false><<<grid_1d(ctx, span->count, 256, 16), 256, 0, cs>>>(x, nullptr, span->begin, span->count, 32, ch.dev, nz, q_out, nullptr);
+    if (nz.res32) k_encode<1, false, true><<<GRID_OCC(ctx, (k_encode<1, false, true>), span->count, 256), 256, 0, cs>>>(x, nullptr, span->begin, span->count, 32, ch.dev, nz, q_out, nullptr);
+    else k_encode<1, false><<<GRID_OCC(ctx, (k_encode<1, false>), span->count, 256), 256, 0, cs>>>(x, nullptr, span->begin, span->count, 32, ch.dev, nz, q_out, nullptr);
     count_launch();
     free_codec(&ch, cs);
     CUDA_TRY(cudaGetLastError());
@@ -664,23 +685,73 @@ int flashe_encode_add_premasked(flashe_ctx* ctx, const flashe_span* span, const 
     if (!x || !mask || !ct_out) return fail(FLASHE_EINVAL, "NULL buffer");
     if (codec && codec->batch_lane_bits) return fail(FLASHE_EINVAL, "lane batching is fused into flashe_encode_encrypt / flashe_decrypt_decode (or use flashe_batch_pack_layers)");
     CodecHost ch; rc = make_codec(ctx, span, codec, false, cs, &ch); if (rc) return rc;
+    rc = check_noise(noise); if (rc) { free_codec(&ch, cs); return rc; }
     NoiseDev nz; make_noise(noise, 0, &nz);
     const uint32_t b = (uint32_t)ctx->int_bits;
-    const int grid = grid_1d(ctx, span->count, 256, 16);
+    const int grid = ctx->words == 1 ? GRID_OCC(ctx, (k_encode<1, true>), span->count, 256)
+                   : (ctx->words == 2 ? GRID_OCC(ctx, (k_encode<2, true>), span->count, 256) : GRID_OCC(ctx, (k_encode<4, true>), span->count, 256));
     const bool v4 = ctx->words == 1 && (span->begin & 3ull) == 0 &&
                     ((((uintptr_t)x | (uintptr_t)mask | (uintptr_t)ct_out | (uintptr_t)nz.u) & 15u) == 0);
     if (v4) {
         const uint64_t nvec = span->count / 4, done = nvec * 4;
-        if (nvec) k_encode_premasked_v4<<<grid_1d(ctx, nvec, 256, 8), 256, 0, cs>>>((const uint4*)x, (const uint4*)mask, span->begin, nvec, Word<1>::mask(b), ch.dev, nz, (uint4*)ct_out);
+        auto kpm = nz.res32 ? k_encode_premasked_v4<true> : k_encode_premasked_v4<false>;
+        if (nvec) kpm<<<GRID_OCC(ctx, kpm, nvec, 256), 256, 0, cs>>>((const uint4*)x, (const uint4*)mask, span->begin, nvec, Word<1>::mask(b), ch.dev, nz, (uint4*)ct_out, 0, 0, 0, 0);
         if (done < span->count) {
             NoiseDev nt = nz; if (nt.u) nt.u += done;
-            k_encode<1, true><<<1, 32, 0, cs>>>(x + done, (const uint32_t*)mask + done, span->begin + done, span->count - done, b, ch.dev, nt, nullptr, (uint32_t*)ct_out + done);
+            if (nz.res32) k_encode<1, true, true><<<1, 32, 0, cs>>>(x + done, (const uint32_t*)mask + done, span->begin + done, span->count - done, b, ch.dev, nt, nullptr, (uint32_t*)ct_out + done);
+            else k_encode<1, true><<<1, 32, 0, cs>>>(x + done, (const uint32_t*)mask + done, span->begin + done, span->count - done, b, ch.dev, nt, nullptr, (uint32_t*)ct_out + done);
             count_launch(nvec ? 1 : 0);
         }
+    }
+    else if (nz.res32) {
+        if (ctx->words == 1) k_encode<1, true, true><<<grid, 256, 0, cs>>>(x, (const uint32_t*)mask, span->begin, span->count, b, ch.dev, nz, nullptr, (uint32_t*)ct_out);
+        else if (ctx->words == 2) k_encode<2, true, true><<<grid, 256, 0, cs>>>(x, (const uint64_t*)mask, span->begin, span->count, b, ch.dev, nz, nullptr, (uint64_t*)ct_out);
+        else k_encode<4, true, true><<<grid, 256, 0, cs>>>(x, (const u128*)mask, span->begin, span->count, b, ch.dev, nz, nullptr, (u128*)ct_out);
     }
     else if (ctx->words == 1) k_encode<1, true><<<grid, 256, 0, cs>>>(x, (const uint32_t*)mask, span->begin, span->count, b, ch.dev, nz, nullptr, (uint32_t*)ct_out);
     else if (ctx->words == 2) k_encode<2, true><<<grid, 256, 0, cs>>>(x, (const uint64_t*)mask, span->begin, span->count, b, ch.dev, nz, nullptr, (uint64_t*)ct_out);
     else k_encode<4, true><<<grid, 256, 0, cs>>>(x, (const u128*)mask, span->begin, span->count, b, ch.dev, nz, nullptr, (u128*)ct_out);
+    count_launch();
+    free_codec(&ch, cs);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+int flashe_encode_add_premasked_batch(flashe_ctx* ctx, const flashe_span* span, int n_clients, const float* x, uint64_t x_stride,
+                                      const flashe_codec* codec, const flashe_noise* noise, uint64_t u_stride, const void* mask,
+                                      uint64_t mask_stride, void* ct_out, uint64_t ct_stride, void* stream) {
+    ENTER(ctx);
+    int rc = flashe_check_span(span); if (rc) return rc;
+    if (n_clients < 1) return fail(FLASHE_EINVAL, "n_clients must be >= 1");
+    if (span->count == 0) return FLASHE_OK;
+    if (!x || !mask || !ct_out) return fail(FLASHE_EINVAL, "NULL buffer");
+    if (n_clients > 1 && (x_stride < span->count || mask_stride < span->count || ct_stride < span->count))
+        return fail(FLASHE_EINVAL, "client strides must be >= span.count");
+    const bool v4 = ctx->words == 1 && (span->begin & 3ull) == 0 && (span->count & 3ull) == 0 &&
+                    ((((uintptr_t)x | (uintptr_t)mask | (uintptr_t)ct_out | (uintptr_t)(noise ? noise->u : nullptr)) & 15u) == 0) &&
+                    (n_clients == 1 || ((x_stride | mask_stride | ct_stride | u_stride) & 3ull) == 0);
+    if (!v4) {                                                         // other layouts: one launch per client
+        for (int c = 0; c < n_clients; ++c) {
+            flashe_noise nc; if (noise) { nc = *noise; if (nc.u) nc.u += (uint64_t)c * u_stride; nc.rng_stream += (uint64_t)c; }
+            const size_t wb = 4u * (size_t)ctx->words;
+            rc = flashe_encode_add_premasked(ctx, span, x + (uint64_t)c * x_stride, codec, noise ? &nc : nullptr,
+                                             (const uint8_t*)mask + (uint64_t)c * mask_stride * wb, (uint8_t*)ct_out + (uint64_t)c * ct_stride * wb, stream);
+            if (rc) return rc;
+        }
+        return FLASHE_OK;
+    }
+    if (codec && codec->batch_lane_bits) return fail(FLASHE_EINVAL, "lane batching is fused into flashe_encode_encrypt / flashe_decrypt_decode");
+    CodecHost ch; rc = make_codec(ctx, span, codec, false, cs, &ch); if (rc) return rc;
+    rc = check_noise(noise); if (rc) { free_codec(&ch, cs); return rc; }
+    NoiseDev nz; make_noise(noise, u_stride, &nz);
+    const uint64_t nvec = span->count / 4;
+    if (n_clients > 65535) { free_codec(&ch, cs); return fail(FLASHE_EINVAL, "at most 65535 clients per launch"); }
+    auto kpm = nz.res32 ? k_encode_premasked_v4<true> : k_encode_premasked_v4<false>;
+    int gx = GRID_OCC(ctx, kpm, nvec * (uint64_t)n_clients, 256) / n_clients;     // resident CTAs, split over the rows
+    if (gx < 1) gx = 1;
+    kpm<<<dim3((unsigned)gx, (unsigned)n_clients), 256, 0, cs>>>(
+        (const uint4*)x, (const uint4*)mask, span->begin, nvec, Word<1>::mask((uint32_t)ctx->int_bits), ch.dev, nz, (uint4*)ct_out,
+        x_stride / 4, mask_stride / 4, ct_stride / 4, u_stride);
     count_launch();
     free_codec(&ch, cs);
     CUDA_TRY(cudaGetLastError());
@@ -710,7 +781,8 @@ int flashe_aggregate(flashe_ctx* ctx, const void* cts, uint64_t stride, int n, u
         const bool aligned = (((uintptr_t)cts | (uintptr_t)out) & 15u) == 0 && (stride % (uint64_t)per_vec) == 0;
         const uint64_t nvec = aligned ? count / per_vec : 0;
         if (nvec) {
-            const int grid = grid_1d(ctx, nvec, 256, 8);
+            const int grid = ctx->words == 1 ? GRID_OCC(ctx, k_aggregate_vec<1>, nvec, 256)
+                           : (ctx->words == 2 ? GRID_OCC(ctx, k_aggregate_vec<2>, nvec, 256) : GRID_OCC(ctx, k_aggregate_vec<4>, nvec, 256));
             const uint64_t sv = stride / per_vec;
             if (ctx->words == 1) k_aggregate_vec<1><<<grid, 256, 0, cs>>>((const uint4*)cts, sv, n, nvec, b, (uint4*)out);
             else if (ctx->words == 2) k_aggregate_vec<2><<<grid, 256, 0, cs>>>((const uint4*)cts, sv, n, nvec, b, (uint4*)out);
@@ -772,10 +844,10 @@ int flashe_decode(flashe_ctx* ctx, const flashe_span* span, const void* v, const
     if (!v || !out) return fail(FLASHE_EINVAL, "NULL buffer");
     if (codec && codec->batch_lane_bits) return fail(FLASHE_EINVAL, "lane batching is fused into flashe_encode_encrypt / flashe_decrypt_decode (or use flashe_batch_pack_layers)");
     CodecHost ch; rc = make_codec(ctx, span, codec, true, cs, &ch); if (rc) return rc;
-    const int grid = grid_1d(ctx, span->count, 256, 16);
+    const int grid = ctx->words == 1 ? GRID_OCC(ctx, k_decode<1>, span->count, 256) : GRID_OCC(ctx, k_decode<2>, span->count, 256);
     if (ctx->words == 1 && (((uintptr_t)v | (uintptr_t)out) & 15u) == 0) {
         const uint64_t nvec = span->count / 4, done = nvec * 4;
-        if (nvec) k_decode_v4<<<grid_1d(ctx, nvec, 256, 8), 256, 0, cs>>>((const uint4*)v, span->begin, nvec, ch.dev, out);
+        if (nvec) k_decode_v4<<<GRID_OCC(ctx, k_decode_v4, nvec, 256), 256, 0, cs>>>((const uint4*)v, span->begin, nvec, ch.dev, out);
         if (done < span->count) {
             k_decode<1><<<1, 32, 0, cs>>>((const uint32_t*)v + done, span->begin + done, span->count - done, ch.dev, out + done);
             count_launch();
@@ -790,13 +862,15 @@ int flashe_decode(flashe_ctx* ctx, const flashe_span* span, const void* v, const
     return FLASHE_OK;
 }
 
-int flashe_rng_uniform(flashe_ctx* ctx, uint64_t rng_seed, uint64_t rng_stream, uint64_t begin, uint64_t count, double* out, void* stream) {
+int flashe_rng_uniform(flashe_ctx* ctx, uint64_t rng_seed, uint64_t rng_stream, int resolution, uint64_t begin, uint64_t count, double* out, void* stream) {
     ENTER(ctx);
     if (count == 0) return FLASHE_OK;
     if (!out) return fail(FLASHE_EINVAL, "out is NULL");
-    flashe_noise n; n.u = nullptr; n.rng_seed = rng_seed; n.rng_stream = rng_stream;
+    if (resolution != FLASHE_NOISE_53 && resolution != FLASHE_NOISE_32) return fail(FLASHE_EINVAL, "unknown noise resolution");
+    flashe_noise n; n.u = nullptr; n.rng_seed = rng_seed; n.rng_stream = rng_stream; n.resolution = resolution; n.reserved = 0;
     NoiseDev nz; make_noise(&n, 0, &nz);
-    k_rng_uniform<<<grid_1d(ctx, count, 256, 16), 256, 0, cs>>>(nz, begin, count, out);
+    if (nz.res32) k_rng_uniform<true><<<GRID_OCC(ctx, k_rng_uniform<true>, count, 256), 256, 0, cs>>>(nz, begin, count, out);
+    else k_rng_uniform<false><<<GRID_OCC(ctx, k_rng_uniform<false>, count, 256), 256, 0, cs>>>(nz, begin, count, out);
     count_launch();
     CUDA_TRY(cudaGetLastError());
     return FLASHE_OK;
@@ -817,7 +891,7 @@ int flashe_batch_pack(flashe_ctx* ctx, const uint32_t* q, uint64_t count, int el
     if (count == 0) return FLASHE_OK;
     if (!q || !words_out) return fail(FLASHE_EINVAL, "NULL buffer");
     const uint64_t nw = ceil_div(count, bs);
-    k_batch_pack<<<grid_1d(ctx, nw, 256, 16), 256, 0, cs>>>(q, count, lane, bs, nw, (u128*)words_out);
+    k_batch_pack<<<GRID_OCC(ctx, k_batch_pack, nw, 256), 256, 0, cs>>>(q, count, lane, bs, nw, (u128*)words_out);
     count_launch();
     CUDA_TRY(cudaGetLastError());
     return FLASHE_OK;
@@ -828,7 +902,7 @@ int flashe_batch_unpack(flashe_ctx* ctx, const void* words, uint64_t nwords, int
     uint32_t lane, bs; int rc = batch_geometry(ctx, element_bits, factor, &lane, &bs); if (rc) return rc;
     if (nwords == 0) return FLASHE_OK;
     if (!words || !q_out) return fail(FLASHE_EINVAL, "NULL buffer");
-    k_batch_unpack<<<grid_1d(ctx, nwords, 256, 16), 256, 0, cs>>>((const u128*)words, nwords, lane, bs, q_out);
+    k_batch_unpack<<<GRID_OCC(ctx, k_batch_unpack, nwords, 256), 256, 0, cs>>>((const u128*)words, nwords, lane, bs, q_out);
     count_launch();
     CUDA_TRY(cudaGetLastError());
     return FLASHE_OK;
@@ -873,7 +947,7 @@ int flashe_batch_pack_layers(flashe_ctx* ctx, const uint32_t* q, const uint64_t*
     rc = upload_layer_table(ctx, seg_end, nseg, element_bits, factor, cs, &tab, &nw); if (rc) return rc;
     if (nw) {
         if (!q || !words_out) { cudaFreeAsync(tab, cs); return fail(FLASHE_EINVAL, "NULL buffer"); }
-        k_batch_pack_layers<<<grid_1d(ctx, nw, 256, 16), 256, 0, cs>>>(q, tab, tab + nseg + 1, nseg, lane, bs, nw, (u128*)words_out);
+        k_batch_pack_layers<<<GRID_OCC(ctx, k_batch_pack_layers, nw, 256), 256, 0, cs>>>(q, tab, tab + nseg + 1, nseg, lane, bs, nw, (u128*)words_out);
         count_launch();
     }
     cudaFreeAsync(tab, cs);
@@ -889,7 +963,7 @@ int flashe_batch_unpack_layers(flashe_ctx* ctx, const void* words, const uint64_
     rc = upload_layer_table(ctx, seg_end, nseg, element_bits, factor, cs, &tab, &nw); if (rc) return rc;
     if (nw) {
         if (!words || !q_out) { cudaFreeAsync(tab, cs); return fail(FLASHE_EINVAL, "NULL buffer"); }
-        k_batch_unpack_layers<<<grid_1d(ctx, nw, 256, 16), 256, 0, cs>>>((const u128*)words, tab, tab + nseg + 1, nseg, lane, bs, nw, q_out);
+        k_batch_unpack_layers<<<GRID_OCC(ctx, k_batch_unpack_layers, nw, 256), 256, 0, cs>>>((const u128*)words, tab, tab + nseg + 1, nseg, lane, bs, nw, q_out);
         count_launch();
     }
     cudaFreeAsync(tab, cs);
@@ -949,7 +1023,7 @@ int flashe_sparse_overlap(flashe_ctx* ctx, const int64_t* const* index, const ui
     cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long) * (size_t)(n - 1), cs);
     for (int i = 0; e == cudaSuccess && i + 1 < n; ++i) {
         if (k[i] == 0 || k[i + 1] == 0) continue;
-        k_overlap<<<grid_1d(ctx, k[i], 256, 16), 256, 0, cs>>>(index[i], k[i], index[i + 1], k[i + 1], d + i);
+        k_overlap<<<GRID_OCC(ctx, k_overlap, k[i], 256), 256, 0, cs>>>(index[i], k[i], index[i + 1], k[i + 1], d + i);
         count_launch();
         e = cudaGetLastError();
     }

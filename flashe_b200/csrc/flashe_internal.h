@@ -41,6 +41,18 @@ static inline int grid_1d(const flashe_ctx* ctx, uint64_t work_items, int thread
     return (int)(blocks < cap ? blocks : cap);
 }
 
+// Grid of a grid-stride kernel: exactly the CTAs that are resident at once (occupancy x SMs), or fewer when the
+// work is small.  A fixed "SMs x 8" grid with a kernel that fits only 5 CTAs per SM runs 1.6 waves, the second
+// at 60 % occupancy (decode lost 20 % to that).  The occupancy is queried once per kernel and device.
+int flashe_resident_ctas(const void* kernel, int threads, size_t dyn_smem, int device, int num_sms);
+static inline int grid_occ(int num_sms, int device, const void* kernel, uint64_t work_items, int threads, size_t dyn_smem = 0) {
+    uint64_t blocks = (work_items + (uint64_t)threads - 1) / (uint64_t)threads;
+    if (blocks < 1) blocks = 1;
+    const uint64_t cap = (uint64_t)flashe_resident_ctas(kernel, threads, dyn_smem, device, num_sms);
+    return (int)(blocks < cap ? blocks : cap);
+}
+#define GRID_OCC(ctx, kernel, work, threads) grid_occ((ctx)->num_sms, (ctx)->device, (const void*)(kernel), (work), (threads))
+
 #define FLASHE_CUDA_TRY(expr)                                                                            \
     do {                                                                                                 \
         cudaError_t e__ = (expr);                                                                        \

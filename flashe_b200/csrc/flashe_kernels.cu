@@ -25,6 +25,9 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -119,6 +122,20 @@ int flashe_ctx_get_info(const flashe_ctx* ctx, flashe_ctx_info* out) {
     if (!ctx) return fail(FLASHE_EINVAL, "ctx is NULL");
     out->device = ctx->device; out->int_bits = ctx->int_bits; out->words = ctx->words; out->num_sms = ctx->num_sms;
     return FLASHE_OK;
+}
+
+int flashe_resident_ctas(const void* kernel, int threads, size_t dyn_smem, int device, int num_sms) {
+    static std::mutex mu;
+    static std::map<std::tuple<const void*, int, size_t, int>, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_tuple(kernel, threads, dyn_smem, device);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, dyn_smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+        it = cache.emplace(key, occ * num_sms).first;
+    }
+    return it->second;
 }
 
 int flashe_check_span(const flashe_span* s) {
@@ -352,12 +369,16 @@ static int encode_encrypt_impl(flashe_ctx* ctx, uint32_t iter, int32_t idx0, int
     st.batch = 1; st.dbl = dbl ? 1u : 0u;
     Geom g; make_geom(ctx, span, pick_sup(ctx, span, (share && dbl) ? 1 : (uint64_t)n_clients), &g);
     CodecHost ch; rc = make_codec(ctx, span, codec, false, cs, &ch); if (rc) return rc;
+    rc = check_noise(noise); if (rc) { free_codec(&ch, cs); return rc; }
     NoiseDev nz; make_noise(noise, u_stride, &nz);
     IoDev io; memset(&io, 0, sizeof(io));
     io.in = x; io.in_stride = x_stride; io.out = ct_out; io.out_stride = ct_stride; io.aux = q_out;
     io.n_clients = (uint32_t)n_clients; io.share = (share && dbl) ? 1u : 0u; io.elem0 = ch.elem0;
-    rc = io.share ? flashe_launch_stream_encode_shared(ctx, st, g, io, ch.dev, nz, cs)
-                  : flashe_launch_stream_encode(ctx, st, g, io, ch.dev, nz, cs);
+    const bool n32 = nz.res32 != 0u && nz.u == nullptr;
+    if (n32) rc = io.share ? flashe_launch_stream_encode_shared_n32(ctx, st, g, io, ch.dev, nz, cs)
+                           : flashe_launch_stream_encode_n32(ctx, st, g, io, ch.dev, nz, cs);
+    else rc = io.share ? flashe_launch_stream_encode_shared(ctx, st, g, io, ch.dev, nz, cs)
+                       : flashe_launch_stream_encode(ctx, st, g, io, ch.dev, nz, cs);
     free_codec(&ch, cs);
     return rc;
 }

@@ -417,7 +417,7 @@ template <int WORDS> struct InType<M_ENCODE, WORDS> { typedef float T; };
 
 // ALIGNED (4-byte words, m = 4 only): the host has checked that every chunk of the span starts on a
 // multiple of 4 elements, so the lane-local path is 128-bit accesses without an alignment switch.
-template <int WORDS, int MMAX, int MODE, bool SHARE, bool ALIGNED>
+template <int WORDS, int MMAX, int MODE, bool SHARE, bool ALIGNED, bool N32 = false>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
 k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab st, const __grid_constant__ Geom g,
          const __grid_constant__ IoDev io, const __grid_constant__ CodecDev cd, const __grid_constant__ NoiseDev nz) {
@@ -685,14 +685,16 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                           const double* up = nz.u + (uint64_t)c * nz.u_stride + o;
 #pragma unroll
                           for (int k = 0; k < 4; ++k) u[k] = up[k];
+                      } else if (N32 && (j & 3ull) == 0ull) {                // 32-bit resolution: the quad is one generator call
+                          noise_quad<true>(nz, nz.stream + c, j >> 2, u);
                       } else if (ALIGNED || SHIFT_OK || (j & 1ull) == 0ull) {   // (SHIFT_OK: quads start at begin + 4k, begin even)
-                          noise_pair(nz, nz.stream + c, j >> 1, u[0], u[1]);
-                          noise_pair(nz, nz.stream + c, (j >> 1) + 1, u[2], u[3]);
+                          noise_pair<N32>(nz, nz.stream + c, j >> 1, u[0], u[1]);
+                          noise_pair<N32>(nz, nz.stream + c, (j >> 1) + 1, u[2], u[3]);
                       } else {                      // odd chunk start: the four elements touch three pairs
                           double lo, hi;
-                          noise_pair(nz, nz.stream + c, j >> 1, lo, u[0]);
-                          noise_pair(nz, nz.stream + c, (j >> 1) + 1, u[1], u[2]);
-                          noise_pair(nz, nz.stream + c, (j >> 1) + 2, u[3], hi);
+                          noise_pair<N32>(nz, nz.stream + c, j >> 1, lo, u[0]);
+                          noise_pair<N32>(nz, nz.stream + c, (j >> 1) + 1, u[1], u[2]);
+                          noise_pair<N32>(nz, nz.stream + c, (j >> 1) + 2, u[3], hi);
                       }
                       uint32_t q4[4];
                       if (one_rcp) {                                 // single layer with a usable reciprocal (warp-uniform)
@@ -741,7 +743,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                               reinterpret_cast<uint32_t*>(io.out)[oc] = (reinterpret_cast<const uint32_t*>(io.in)[(uint64_t)c * io.in_stride + o] + mword) & mk32;
                           } else if (MODE == M_ENCODE) {
                               const float x = reinterpret_cast<const float*>(io.in)[(uint64_t)c * io.in_stride + o];
-                              const double u = nz.u ? nz.u[(uint64_t)c * nz.u_stride + o] : noise_one(nz, nz.stream + c, j);
+                              const double u = nz.u ? nz.u[(uint64_t)c * nz.u_stride + o] : noise_one<N32>(nz, nz.stream + c, j);
                               const Seg sg = find_seg(cd, j);
                               const uint32_t qv = encode_one(x, u, sg, cd.scale);
                               const uint64_t oc = (uint64_t)c * io.out_stride + o;
@@ -781,7 +783,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                       double u;
                       if (nz.u) u = nz.u[(uint64_t)c * nz.u_stride + (e - io.elem0)];
                       else {
-                          if ((e >> 1) != pc) { pc = e >> 1; noise_pair(nz, nz.stream + c, pc, u0, u1); }
+                          if ((e >> 1) != pc) { pc = e >> 1; noise_pair<N32>(nz, nz.stream + c, pc, u0, u1); }
                           u = (e & 1ull) ? u1 : u0;
                       }
                       q = encode_one(xin[e - io.elem0], u, wp.sg, cd.scale);
@@ -945,7 +947,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                   } else if (MODE == M_ENCODE) {
                       double u0, u1;
                       if (nz.u) { const double* up = nz.u + (uint64_t)c * nz.u_stride + o; u0 = up[0]; u1 = up[1]; }
-                      else noise_pair(nz, nz.stream + c, j >> 1, u0, u1);
+                      else noise_pair<N32>(nz, nz.stream + c, j >> 1, u0, u1);
                       Seg sg = find_seg(cd, j);
                       const uint32_t q0 = encode_one(__uint_as_float(r[h][0]), u0, sg, cd.scale);
                       if (!one_seg && j + 1 >= sg.end) sg = find_seg(cd, j + 1);
@@ -1110,7 +1112,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                         const double* up = nz.u + (uint64_t)c * nz.u_stride;
                         u0 = v0 ? up[o0] : 0.0; u1 = v1 ? up[o0 + 1] : 0.0;
                     } else {
-                        noise_pair(nz, nz.stream + c, j0 >> 1, u0, u1);
+                        noise_pair<N32>(nz, nz.stream + c, j0 >> 1, u0, u1);
                     }
                     if (v0) {
                         const Seg sg = find_seg(cd, j0);
@@ -1151,10 +1153,10 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
 #undef PRE_OF
 }
 
-template <int WORDS, int MMAX, int MODE, bool SHARE, bool ALIGNED = false>
+template <int WORDS, int MMAX, int MODE, bool SHARE, bool ALIGNED = false, bool N32 = false>
 static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,
                            const NoiseDev& nz, cudaStream_t stream) {
-    auto kern = k_stream<WORDS, MMAX, MODE, SHARE, ALIGNED>;
+    auto kern = k_stream<WORDS, MMAX, MODE, SHARE, ALIGNED, N32>;
     // the opt-in shared-memory size is a per-device property of the function: set it once per device
     static std::atomic<uint64_t> attr_set{0};
     const uint64_t dev_bit = 1ull << (ctx->device & 63);
@@ -1188,7 +1190,7 @@ static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geo
 
 
 // SHARED = true instantiates only the shared-stream encode kernels (their own translation unit)
-template <int MODE, bool SHARED = false>
+template <int MODE, bool SHARED = false, bool N32 = false>
 static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io_in, const CodecDev& cd,
                          const NoiseDev& nz, cudaStream_t stream) {
     const int b = ctx->int_bits;
@@ -1205,23 +1207,23 @@ static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom&
     if constexpr (MODE == M_ENCODE && SHARED) {
         {
             if (b <= 32) {
-                if (ctx->m == 4 && g.aligned4 && io.quad) return launch_stream_t<1, 4, MODE, true, true>(ctx, st, g, io, cd, nz, stream);
-                if (ctx->m <= 4) return launch_stream_t<1, 4, MODE, true>(ctx, st, g, io, cd, nz, stream);
-                if (ctx->m <= 6) return launch_stream_t<1, 6, MODE, true>(ctx, st, g, io, cd, nz, stream);
-                return launch_stream_t<1, 16, MODE, true>(ctx, st, g, io, cd, nz, stream);
+                if (ctx->m == 4 && g.aligned4 && io.quad) return launch_stream_t<1, 4, MODE, true, true, N32>(ctx, st, g, io, cd, nz, stream);
+                if (ctx->m <= 4) return launch_stream_t<1, 4, MODE, true, false, N32>(ctx, st, g, io, cd, nz, stream);
+                if (ctx->m <= 6) return launch_stream_t<1, 6, MODE, true, false, N32>(ctx, st, g, io, cd, nz, stream);
+                return launch_stream_t<1, 16, MODE, true, false, N32>(ctx, st, g, io, cd, nz, stream);
             }
-            if (b <= 64) return launch_stream_t<2, 3, MODE, true>(ctx, st, g, io, cd, nz, stream);
-            return launch_stream_t<4, 1, MODE, true>(ctx, st, g, io, cd, nz, stream);
+            if (b <= 64) return launch_stream_t<2, 3, MODE, true, false, N32>(ctx, st, g, io, cd, nz, stream);
+            return launch_stream_t<4, 1, MODE, true, false, N32>(ctx, st, g, io, cd, nz, stream);
         }
     } else {
     if (b <= 32) {
-        if (ctx->m == 4 && g.aligned4 && io.quad && MODE != M_SCATTER) return launch_stream_t<1, 4, MODE, false, true>(ctx, st, g, io, cd, nz, stream);
-        if (ctx->m <= 4) return launch_stream_t<1, 4, MODE, false>(ctx, st, g, io, cd, nz, stream);
-        if (ctx->m <= 6) return launch_stream_t<1, 6, MODE, false>(ctx, st, g, io, cd, nz, stream);
-        return launch_stream_t<1, 16, MODE, false>(ctx, st, g, io, cd, nz, stream);
+        if (ctx->m == 4 && g.aligned4 && io.quad && MODE != M_SCATTER) return launch_stream_t<1, 4, MODE, false, true, N32>(ctx, st, g, io, cd, nz, stream);
+        if (ctx->m <= 4) return launch_stream_t<1, 4, MODE, false, false, N32>(ctx, st, g, io, cd, nz, stream);
+        if (ctx->m <= 6) return launch_stream_t<1, 6, MODE, false, false, N32>(ctx, st, g, io, cd, nz, stream);
+        return launch_stream_t<1, 16, MODE, false, false, N32>(ctx, st, g, io, cd, nz, stream);
     }
-    if (b <= 64) return launch_stream_t<2, 3, MODE, false>(ctx, st, g, io, cd, nz, stream);
-    return launch_stream_t<4, 1, MODE, false>(ctx, st, g, io, cd, nz, stream);
+    if (b <= 64) return launch_stream_t<2, 3, MODE, false, false, N32>(ctx, st, g, io, cd, nz, stream);
+    return launch_stream_t<4, 1, MODE, false, false, N32>(ctx, st, g, io, cd, nz, stream);
     }
 }
 

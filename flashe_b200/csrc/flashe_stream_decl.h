@@ -65,6 +65,10 @@ int flashe_launch_stream_encode(const flashe_ctx* ctx, const StreamTab& st, cons
                                 const NoiseDev& nz, cudaStream_t stream);
 int flashe_launch_stream_encode_shared(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io,
                                        const CodecDev& cd, const NoiseDev& nz, cudaStream_t stream);
+int flashe_launch_stream_encode_n32(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,
+                                    const NoiseDev& nz, cudaStream_t stream);
+int flashe_launch_stream_encode_shared_n32(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io,
+                                           const CodecDev& cd, const NoiseDev& nz, cudaStream_t stream);
 int flashe_launch_stream_decode(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,
                                 const NoiseDev& nz, cudaStream_t stream);
 int flashe_launch_stream_scatter(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,

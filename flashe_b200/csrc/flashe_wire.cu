@@ -205,6 +205,122 @@ k_wire_pack32(const uint32_t* __restrict__ words, uint64_t count, uint32_t bits,
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// pack, second form (the one flashe_wire_pack launches when `words` is 16-byte aligned): no shared-memory
+// atomics.  A CTA walks tiles of WB_WORDS stream words.  The elements that reach into a tile are ONE contiguous
+// run of the input, so thread 0 fetches them with a single bulk asynchronous copy (cp.async.bulk global ->
+// shared, completion counted in bytes on an mbarrier: the TMA path, no per-thread load instructions), two tiles
+// in flight.  Every thread then builds runs of four consecutive stream words from the staged elements (the
+// first one is found with one multiply-high, the rest are walked once through a 64-bit bit accumulator) and
+// writes each as one 16-byte store.
+// -------------------------------------------------------------------------------------------------
+#define WB_THREADS 256
+#define WB_RUN 4                                     // consecutive stream words per run (one 16-byte store)
+#define WB_WORDS (WB_THREADS * WB_RUN * 4)            // stream words per tile (16 KB of output): four runs per thread
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(WB_THREADS)
+k_wire_pack32_bulk(const uint32_t* __restrict__ words, uint64_t count, uint32_t bits, uint32_t pad, uint64_t nwords,
+                   uint32_t magic, uint32_t stage_words, uint32_t* __restrict__ out) {
+    extern __shared__ __align__(128) uint32_t stage[];            // 2 x stage_words
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ int64_t s_rel[2];                                   // stream bit of staged element 0 minus the tile's first bit
+    const uint32_t la = 32u - bits;                                // left-alignment shift of an element
+    const uint64_t ntiles = (nwords + WB_WORDS - 1) / WB_WORDS;
+    uint64_t t = blockIdx.x;
+    if (t >= ntiles) return;
+    const uint32_t bar0 = smem_u32(&bars[0]), st0 = smem_u32(stage);
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // thread 0: stage the elements that intersect tile `tile` (run [f_al, f_al + n), f_al a multiple of 4 elements)
+    auto issue = [&](uint64_t tile, int buf) {
+        const uint64_t bit0 = tile * (uint64_t)(WB_WORDS * 32);
+        const uint64_t f_lo = bit0 > pad ? (bit0 - pad) / bits : 0;
+        uint64_t f_hi = (bit0 + (uint64_t)(WB_WORDS * 32) - 1 - pad) / bits;
+        if (f_hi >= count) f_hi = count - 1;
+        const uint64_t f_al = f_lo & ~3ull;
+        uint64_t n = f_hi - f_al + 1;
+        const uint64_t n_bulk_max = (count & ~3ull) > f_al ? (count & ~3ull) - f_al : 0;   // whole 16-byte pieces inside the vector
+        const uint64_t n_bulk = ((n + 3) & ~3ull) <= n_bulk_max ? ((n + 3) & ~3ull) : n_bulk_max;
+        s_rel[buf] = (int64_t)(pad + f_al * bits) - (int64_t)bit0;
+        const uint32_t dst = st0 + (uint32_t)buf * stage_words * 4u;
+        for (uint64_t i = n_bulk; i < n; ++i) stage[(uint32_t)buf * stage_words + i] = words[f_al + i];   // <= 3 elements at the vector's end
+        if (f_hi + 1 >= count)                                                                            // last tile: slots past the last element read as zero
+            for (uint64_t i = n; i < n + 8 && i < stage_words; ++i) stage[(uint32_t)buf * stage_words + i] = 0u;
+        mbar_expect_tx(bar0 + 8u * buf, (uint32_t)(n_bulk * 4));
+        if (n_bulk) bulk_g2s(dst, words + f_al, (uint32_t)(n_bulk * 4), bar0 + 8u * buf);
+    };
+    if (threadIdx.x == 0) issue(t, 0);
+    uint32_t phase[2] = {0u, 0u};
+    for (int buf = 0; t < ntiles; t += gridDim.x, buf ^= 1) {
+        if (threadIdx.x == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x, buf ^ 1);
+        mbar_wait(bar0 + 8u * buf, phase[buf]);
+        phase[buf] ^= 1u;
+        const int32_t rel_tile = (int32_t)s_rel[buf];                  // <= 0 except for the first tile (pad), > -(4 * bits)
+        const uint32_t* el = stage + (uint32_t)buf * stage_words;
+        const uint64_t w_base = t * (uint64_t)WB_WORDS;
+        // a thread owns runs of WB_RUN = 4 consecutive stream words (one 16-byte store, consecutive lanes -> consecutive
+        // 16-byte pieces: a warp writes 512 contiguous bytes per store) and walks the elements that feed a run ONCE, left
+        // to right, through a 64-bit bit accumulator (`fill` valid bits at the top): every element costs one
+        // shared-memory load, two shifts and an OR, every finished word one shift
+#pragma unroll
+        for (uint32_t rr = 0; rr < WB_WORDS / WB_RUN / WB_THREADS; ++rr) {
+            const uint32_t w0 = (threadIdx.x + rr * WB_THREADS) * WB_RUN;
+            if (w_base + w0 >= nwords) break;
+            const int32_t x = (int32_t)(32u * w0) - rel_tile;          // bit offset of the run from staged element 0
+            uint32_t i = x > 0 ? __umulhi((uint32_t)x, magic) : 0u;     // element that holds the run's first bit (x < 2^27)
+            const int32_t rel = (int32_t)(i * bits) - x;                // its start relative to the run: in (-bits, 0], or pad > 0 for the stream's first word
+            // (hi, lo): 64 stream bits, `fill` of them valid from the top.  An element, left-aligned in 32 bits (which
+            // also drops anything above its `bits`), lands `fill` bits from the top: two shifts, two ORs.  Staged slots
+            // past the vector's end hold zeros, so no bounds test is needed here.
+            uint32_t hi = 0u, lo = 0u, fill = 0u;
+            if (rel > 0) fill = (uint32_t)rel;                          // leading zero bits (the stream's padding)
+            else if (rel < 0) {                                         // the first element starts before the run: keep its low bits
+                hi = el[i] << (la + (uint32_t)(-rel));                  // drops the bits that belong to the previous word
+                fill = bits + (uint32_t)rel; ++i;
+            }
+            uint32_t r[WB_RUN];
+#pragma unroll
+            for (int k = 0; k < WB_RUN; ++k) {
+                while (fill < 32u) {                                    // one or two elements complete a word at the shipped widths
+                    const uint32_t a = el[i] << la;
+                    hi |= a >> fill;
+                    lo |= __funnelshift_r(0u, a, fill);                 // (a:0) >> fill, low word; 0 when fill == 0
+                    fill += bits; ++i;
+                }
+                r[k] = __byte_perm(hi, 0, 0x0123);                      // first stream byte first
+                hi = lo; lo = 0u; fill -= 32u;
+            }
+            __stcs(reinterpret_cast<uint4*>(out + w_base + w0), make_uint4(r[0], r[1], r[2], r[3]));    // nwords is a multiple of 4
+        }
+        __syncthreads();                                               // the stage is free for the tile after next
+    }
+}
+
 // unpack: tile = WU_ELEMS consecutive elements, thread = 4 of them (one 16-byte store)
 #define WU_ELEMS (WP_THREADS * 4)
 #define WU_BUF (WU_ELEMS + 16)
@@ -258,6 +374,70 @@ k_wire_unpack32(const uint8_t* __restrict__ in, uint64_t count, uint32_t bits, u
                 const uint32_t wi = o >> 5;
                 const uint32_t hi = __byte_perm(w[wi], 0, 0x0123), lo = __byte_perm(w[wi + 1], 0, 0x0123);
                 // 32 stream bits from bit (o & 31) of hi:lo; a word past the staged ones only feeds bits that are shifted out
+                r[k] = (__funnelshift_l(lo, hi, o & 31u) >> (32u - bits)) & fm;
+            }
+            uint32_t* dst = words + j0 + e0;
+            if (e0 + 4u <= ne && ((uintptr_t)dst & 15u) == 0) __stcs(reinterpret_cast<uint4*>(dst), make_uint4(r[0], r[1], r[2], r[3]));
+            else for (uint32_t k = 0; k < 4u && e0 + k < ne; ++k) dst[k] = r[k];
+        }
+        __syncthreads();
+    }
+}
+
+// unpack, second form (launched when the stream is 16-byte aligned): tiles of WUB_ELEMS elements, the tile's bytes of
+// the stream fetched by ONE bulk asynchronous copy per tile (thread 0, mbarrier completion), two tiles in flight;
+// a thread converts four groups of four consecutive elements (one 16-byte store each).
+#define WUB_ELEMS 4096
+__global__ void __launch_bounds__(WB_THREADS)
+k_wire_unpack32_bulk(const uint8_t* __restrict__ in, uint64_t count, uint32_t bits, uint32_t pad, uint64_t nbytes,
+                     uint32_t stage_words, uint32_t* __restrict__ words) {
+    extern __shared__ __align__(128) uint32_t stage[];            // 2 x stage_words, stream words as stored (big-endian)
+    __shared__ __align__(8) uint64_t bars[2];
+    const uint32_t fm = bits >= 32u ? 0xffffffffu : ((1u << bits) - 1u);
+    const uint64_t ntiles = (count + WUB_ELEMS - 1) / WUB_ELEMS;
+    uint64_t t = blockIdx.x;
+    if (t >= ntiles) return;
+    const uint32_t bar0 = smem_u32(&bars[0]), st0 = smem_u32(stage);
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](uint64_t tile, int buf) {
+        const uint64_t j0 = tile * WUB_ELEMS;
+        const uint32_t ne = (uint32_t)(count - j0 < WUB_ELEMS ? count - j0 : WUB_ELEMS);
+        const uint64_t b_lo = pad + j0 * bits, b_hi = b_lo + (uint64_t)ne * bits;      // stream bits of the tile
+        const uint64_t byte_al = (b_lo >> 3) & ~15ull;
+        const uint64_t byte_end = ((b_hi + 7) >> 3) + 4;                                // one word of slack for the funnel shift
+        const uint64_t want = (byte_end - byte_al + 15) & ~15ull;
+        const uint64_t avail = (nbytes & ~15ull) > byte_al ? (nbytes & ~15ull) - byte_al : 0;
+        const uint64_t n_bulk = want <= avail ? want : avail;
+        uint8_t* sb = reinterpret_cast<uint8_t*>(stage + (uint32_t)buf * stage_words);
+        for (uint64_t i = n_bulk; i < want; ++i) sb[i] = byte_al + i < nbytes ? in[byte_al + i] : (uint8_t)0;   // the stream's last < 16 bytes
+        mbar_expect_tx(bar0 + 8u * buf, (uint32_t)n_bulk);
+        if (n_bulk) bulk_g2s(st0 + (uint32_t)buf * stage_words * 4u, in + byte_al, (uint32_t)n_bulk, bar0 + 8u * buf);
+    };
+    if (threadIdx.x == 0) issue(t, 0);
+    uint32_t phase[2] = {0u, 0u};
+    for (int buf = 0; t < ntiles; t += gridDim.x, buf ^= 1) {
+        if (threadIdx.x == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x, buf ^ 1);
+        mbar_wait(bar0 + 8u * buf, phase[buf]);
+        phase[buf] ^= 1u;
+        const uint64_t j0 = t * WUB_ELEMS;
+        const uint32_t ne = (uint32_t)(count - j0 < WUB_ELEMS ? count - j0 : WUB_ELEMS);
+        const uint64_t b_lo = pad + j0 * bits;
+        const uint32_t o_base = (uint32_t)(b_lo - (((b_lo >> 3) & ~15ull) << 3));        // bit offset of element j0 in the stage
+        const uint32_t* w = stage + (uint32_t)buf * stage_words;
+#pragma unroll
+        for (uint32_t q = 0; q < WUB_ELEMS / 4 / WB_THREADS; ++q) {
+            const uint32_t e0 = 4u * (threadIdx.x + q * WB_THREADS);
+            if (e0 >= ne) break;
+            uint32_t r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t o = o_base + (e0 + k) * bits;
+                const uint32_t wi = o >> 5;
+                const uint32_t hi = __byte_perm(w[wi], 0, 0x0123), lo = __byte_perm(w[wi + 1], 0, 0x0123);
                 r[k] = (__funnelshift_l(lo, hi, o & 31u) >> (32u - bits)) & fm;
             }
             uint32_t* dst = words + j0 + e0;
@@ -558,7 +738,19 @@ int flashe_wire_pack(flashe_ctx* ctx, const void* words, int word_bytes, uint64_
         const uint64_t nvec = nbytes >> 4;
         const uint32_t pad = (uint32_t)(8 * nbytes - count * (uint64_t)bits);
         int launches = 0;
-        if (nvec) {
+        if (nvec && ((uintptr_t)words & 15u) == 0) {
+            // bulk-staged form: stage = the elements of one tile (+ alignment slack), two stages
+            const uint32_t stage_words = (uint32_t)(((WB_WORDS * 32 + bits - 1) / bits + 2 + 8 + 31) & ~31);
+            const size_t smem = 2u * (size_t)stage_words * 4u;
+            static bool attr_done = false;
+            if (!attr_done) { FLASHE_CUDA_TRY(cudaFuncSetAttribute(k_wire_pack32_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * ((WB_WORDS * 32 / 8) + 64))); attr_done = true; }
+            const uint32_t magic = (uint32_t)((1ull << 32) / (uint64_t)bits) + 1u;      // floor(x / bits) = umulhi(x, magic) for x < 2^17
+            const uint64_t nwords = nvec * 4;
+            const int grid = grid_occ(info.num_sms, info.device, (const void*)k_wire_pack32_bulk, ceil_div_u64(nwords, WB_WORDS) * WB_THREADS, WB_THREADS, smem);
+            k_wire_pack32_bulk<<<grid, WB_THREADS, smem, cs>>>(reinterpret_cast<const uint32_t*>(words), count, (uint32_t)bits, pad, nwords, magic,
+                                                                stage_words, reinterpret_cast<uint32_t*>(out));
+            ++launches;
+        } else if (nvec) {
             const int grid = grid_cap(info.num_sms, ceil_div_u64(nvec, WP_THREADS), 8);
             k_wire_pack32<<<grid, WP_THREADS, 0, cs>>>(reinterpret_cast<const uint32_t*>(words), count, (uint32_t)bits, pad, nvec,
                                                         reinterpret_cast<uint4*>(out));
@@ -586,8 +778,17 @@ int flashe_wire_unpack(flashe_ctx* ctx, const uint8_t* in, uint64_t count, int b
     uint64_t nbytes; rc = flashe_wire_nbytes(bits, count, &nbytes); if (rc) return rc;
     if (word_bytes == 4 && ((uintptr_t)words_out & 3u) == 0 && ((uintptr_t)in & 15u) == 0) {
         const uint32_t pad = (uint32_t)(8 * nbytes - count * (uint64_t)bits);
+        if (bits >= 8) {
+            const uint32_t stage_words = (uint32_t)(((WUB_ELEMS * (uint32_t)bits / 8 + 16 + 4 + 16) / 4 + 31) & ~31);
+            const size_t smem = 2u * (size_t)stage_words * 4u;
+            static bool attr_done = false;
+            if (!attr_done) { FLASHE_CUDA_TRY(cudaFuncSetAttribute(k_wire_unpack32_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (WUB_ELEMS * 4 + 256))); attr_done = true; }
+            const int grid = grid_occ(info.num_sms, info.device, (const void*)k_wire_unpack32_bulk, ceil_div_u64(count, WUB_ELEMS) * WB_THREADS, WB_THREADS, smem);
+            k_wire_unpack32_bulk<<<grid, WB_THREADS, smem, cs>>>(in, count, (uint32_t)bits, pad, nbytes, stage_words, reinterpret_cast<uint32_t*>(words_out));
+        } else {
         const int grid = grid_cap(info.num_sms, ceil_div_u64(count, WU_ELEMS), 8);
         k_wire_unpack32<<<grid, WP_THREADS, 0, cs>>>(in, count, (uint32_t)bits, pad, nbytes, reinterpret_cast<uint32_t*>(words_out));
+        }
         flashe_count_launches(1);
         FLASHE_CUDA_TRY(cudaGetLastError());
         return FLASHE_OK;

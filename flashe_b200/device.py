@@ -94,9 +94,13 @@ class NoiseSpec:
     u: Optional[torch.Tensor] = None
     seed: int = 0
     stream: int = 0
+    resolution: int = 53      # device generator: 53 (numpy's construction, two words per element) or 32 (throughput mode)
 
     def c(self):
-        return _cabi.Noise(self.u.data_ptr() if self.u is not None else None, self.seed, self.stream)
+        if self.resolution not in (53, 32):
+            raise ValueError("noise resolution must be 53 or 32")
+        return _cabi.Noise(self.u.data_ptr() if self.u is not None else None, self.seed, self.stream,
+                           _cabi.NOISE_32 if self.resolution == 32 else _cabi.NOISE_53, 0)
 
 
 def _iter32(it):
@@ -314,6 +318,20 @@ class DeviceContext(object):
                                                          mask.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
+    def encode_add_premasked_batch(self, x, codec: CodecSpec, noise: NoiseSpec, masks, span: VectorSpan, out=None):
+        """All clients' online step in one launch: x float32 [n, count], masks / out words [n, count]."""
+        if x.dim() != 2 or x.shape[1] != span.n or x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device:
+            raise ValueError("x must be a contiguous float32 [n_clients, count] tensor on %s" % self.device)
+        n = x.shape[0]
+        self._check_words(masks, n * span.n, "masks")
+        if noise.u is not None:
+            self._check(noise.u, torch.float64, n * span.n, "noise.u")
+        out = self.empty_words(span.n, rows=n) if out is None else self._check_words(out, n * span.n, "out")
+        cc, nc = codec.c(span.total_len), noise.c()
+        _cabi.check(self.lib.flashe_encode_add_premasked_batch(self._h, C.byref(span.c()), n, x.data_ptr(), span.n, C.byref(cc), C.byref(nc),
+                                                               span.n, masks.data_ptr(), span.n, out.data_ptr(), span.n, self._stream()))
+        return out
+
     def aggregate(self, cts, mode=AGG_ELEMENTWISE, carry_in=0, out=None, carry_out=None):
         """cts: words [n, L] (+[,2]); returns words [L]."""
         n = cts.shape[0]
@@ -349,9 +367,10 @@ class DeviceContext(object):
                                                    self._stream()))
         return out
 
-    def rng_uniform(self, seed, stream, begin, count, out=None):
+    def rng_uniform(self, seed, stream, begin, count, out=None, resolution=53):
         out = torch.empty(count, dtype=torch.float64, device=self.device) if out is None else out
-        _cabi.check(self.lib.flashe_rng_uniform(self._h, seed, stream, begin, count, out.data_ptr(), self._stream()))
+        _cabi.check(self.lib.flashe_rng_uniform(self._h, seed, stream, _cabi.NOISE_32 if resolution == 32 else _cabi.NOISE_53,
+                                                begin, count, out.data_ptr(), self._stream()))
         return out
 
     def batch_pack(self, q, element_bits, factor):

@@ -79,10 +79,18 @@ typedef struct flashe_codec {
  * the device generate them with the counter-based generator (u == NULL): element j of client
  * `rng_stream` uses Philox4x32-10(key=rng_seed, counter=(j>>1, rng_stream)) and the res53
  * construction numpy uses; flashe_rng_uniform() materialises exactly those numbers. */
+enum { FLASHE_NOISE_53 = 0, FLASHE_NOISE_32 = 1 };
 typedef struct flashe_noise {
     const double* u;     /* device, [count] for this shard, or NULL */
     uint64_t rng_seed;
     uint64_t rng_stream;
+    int32_t resolution;  /* device generator only.  FLASHE_NOISE_53: numpy's 53-bit construction, two 32-bit words per
+                          * element (above).  FLASHE_NOISE_32 (throughput mode): u_j = w * 2^-32 with w = word (j & 3)
+                          * of Philox4x32-10(key = rng_seed, counter = (j >> 2, rng_stream)) — one generator call per
+                          * four elements.  Rounding a 16-bit quantisation stochastically needs far fewer than 32
+                          * random bits; ciphertexts still equal the oracle's when it is fed the same u
+                          * (flashe_rng_uniform materialises either stream). */
+    int32_t reserved;
 } flashe_noise;
 
 int flashe_abi_version(void);
@@ -174,6 +182,14 @@ int flashe_encode_add_premasked(flashe_ctx* ctx, const flashe_span* span, const 
                                 const flashe_codec* codec, const flashe_noise* noise, const void* mask,
                                 void* ct_out, void* stream);
 
+/* Same for n_clients logical clients hosted on this device in ONE launch (the online round of the mask
+ * precomputation schedule): client c reads x + c*x_stride floats and mask + c*mask_stride words, writes
+ * ct_out + c*ct_stride words, and draws its noise from noise->u + c*u_stride or stream id rng_stream + c. */
+int flashe_encode_add_premasked_batch(flashe_ctx* ctx, const flashe_span* span, int n_clients, const float* x,
+                                      uint64_t x_stride, const flashe_codec* codec, const flashe_noise* noise,
+                                      uint64_t u_stride, const void* mask, uint64_t mask_stride, void* ct_out,
+                                      uint64_t ct_stride, void* stream);
+
 /* Server sum of n ciphertext vectors (vector c at cts + c*stride words):
  *   FLASHE_AGG_ELEMENTWISE  out[j] = sum_c ct_c[j] mod 2^b           (proc/jzf_aggregator.py:421-430)
  *   FLASHE_AGG_PACKED       the (x + y) % (1 << (b*L)) sum of the packed wire integers
@@ -208,7 +224,7 @@ int flashe_decrypt_decode(flashe_ctx* ctx, uint32_t iter, const int32_t* add_idx
                           const flashe_codec* codec, double* out, void* p_out, void* stream);
 
 /* The device noise generator made visible: out[j - begin] = u_j for j in [begin, begin+count). */
-int flashe_rng_uniform(flashe_ctx* ctx, uint64_t rng_seed, uint64_t rng_stream, uint64_t begin,
+int flashe_rng_uniform(flashe_ctx* ctx, uint64_t rng_seed, uint64_t rng_stream, int resolution, uint64_t begin,
                        uint64_t count, double* out, void* stream);
 
 /* Lane batching for int_bits up to 128 (shipped: 120) — _static_batching_padding_asymmetric /

@@ -278,9 +278,18 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def noise_uniform(seed, stream, begin, count):
-    """u_j for j in [begin, begin+count): what flashe_rng_uniform / the fused encode kernels draw."""
+def noise_uniform(seed, stream, begin, count, resolution=53):
+    """u_j for j in [begin, begin+count): what flashe_rng_uniform / the fused encode kernels draw.
+    resolution=32 (throughput mode): u_j = word (j & 3) of Philox(counter = (j >> 2, stream)) * 2^-32."""
     j = np.arange(begin, begin + count, dtype=np.uint64)
+    if resolution == 32:
+        c = j >> np.uint64(2)
+        z = np.zeros_like(c)
+        o = philox4x32_10(c & np.uint64(0xFFFFFFFF), c >> np.uint64(32), z + np.uint64(int(stream) & 0xFFFFFFFF),
+                          z + np.uint64((int(stream) >> 32) & 0xFFFFFFFF), int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF)
+        k = (j & np.uint64(3)).astype(np.int64)
+        w = np.choose(k, [o[0], o[1], o[2], o[3]])
+        return w.astype(np.float64) / 4294967296.0
     c = j >> np.uint64(1)
     z = np.zeros_like(c)
     o = philox4x32_10(c & np.uint64(0xFFFFFFFF), c >> np.uint64(32), z + np.uint64(int(stream) & 0xFFFFFFFF),

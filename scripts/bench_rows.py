@@ -23,7 +23,12 @@ def hbm_peak():
         return 6650.0
 
 
+ONCE = "--once" in sys.argv          # one warm-up + one timed launch per kernel: for `ncu --set full` captures
+
+
 def timed(fn, steps=5, warmup=3):
+    if ONCE:
+        steps, warmup = 1, 1
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -115,10 +120,20 @@ def main():
     codec = fb.CodecSpec(alpha=0.5938345, element_bits=16)
     ms = timed(lambda: ctx.encode_add_premasked(x, codec, fb.NoiseSpec(seed=1, stream=0), mask, span, out=ct))
     report("encode_add_premasked (device noise)", ms, L * 12, L, "elements/s")
+    ms = timed(lambda: ctx.encode_add_premasked(x, codec, fb.NoiseSpec(seed=1, stream=0, resolution=32), mask, span, out=ct))
+    report("encode_add_premasked (device noise, 32-bit resolution)", ms, L * 12, L, "elements/s")
     ms = timed(lambda: ctx.add_premasked(ct, mask, 1, out=ct))
     report("add_premasked", ms, L * 12, L, "elements/s")
     ms = timed(lambda: ctx.masks(0, [0, 1], [1, -1], span, out=mask))
     report("masks fill (2 streams, b=32)", ms, L * 4, 2 * L // 4, "AES blocks/s")
+    # write-only and read-only streams: what this part's HBM gives a kernel whose traffic is all stores / all loads
+    # (the copy peak mixes them 1:1); decode writes 2 bytes for every byte it reads
+    big = torch.empty(L * 2, dtype=torch.float32, device=dev)
+    ms = timed(lambda: big.fill_(1.0))
+    report("torch fill_ (write-only, 800 MB)", ms, L * 8, L * 2, "elements/s")
+    ms = timed(lambda: big.sum())
+    report("torch sum (read-only, 800 MB)", ms, L * 8, L * 2, "elements/s")
+    del big
     out = torch.empty(L, dtype=torch.float64, device=dev)
     ms = timed(lambda: ctx.decode(ct, fb.CodecSpec(alpha=0.5938345, element_bits=16, n_clients=64), span, out=out))
     report("decode", ms, L * 12, L, "elements/s")

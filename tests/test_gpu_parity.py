@@ -779,6 +779,44 @@ def test_device_noise_is_the_documented_philox_stream(fb):
         got = _np(ctx.rng_uniform(seed, stream, begin, cnt))
         want = O.noise_uniform(seed, stream, begin, cnt)
         assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (seed, stream, begin)
+        got32 = _np(ctx.rng_uniform(seed, stream, begin, cnt, resolution=32))
+        want32 = O.noise_uniform(seed, stream, begin, cnt, resolution=32)
+        assert np.array_equal(got32.view(np.uint64), want32.view(np.uint64)), (seed, stream, begin)
+        assert got32.min() >= 0.0 and got32.max() < 1.0
+
+
+@pytest.mark.parametrize("bits,n_jobs,L", [(32, 16, 1_000_000), (32, 7, 7 * 50_001), (20, 8, 600_001), (24, 5, 300_000), (64, 8, 200_000), (16, 4, 100_000)])
+def test_throughput_mode_noise_32_bit_resolution(fb, bits, n_jobs, L):
+    """NoiseSpec(resolution=32): one Philox word per element.  Every fused path (aligned / shifted / slab, batch and
+    shared streams, the premasked online step) must draw exactly the documented stream: ciphertexts equal the
+    oracle's when it is fed rng_uniform(..., resolution=32)."""
+    n, it, alpha = 3, 2, 0.37
+    ctx = ctx_for(fb, bits)
+    span = fb.VectorSpan(L, n_jobs)
+    codec = fb.CodecSpec(alpha=alpha, element_bits=16, n_clients=n)
+    x = (np.random.RandomState(L % 97).standard_normal((n, L)) * 0.2).astype(np.float32)
+    noise = fb.NoiseSpec(seed=11, stream=5, resolution=32)
+    want = []
+    for c in range(n):
+        u = O.noise_uniform(11, 5 + c, 0, L, resolution=32)
+        q = O.quantize(x[c], u, alpha, 16)
+        want.append(O.encrypt(KEY, bits, n_jobs, it, c, "double", O.to_words(q, bits) if bits > 32 else q))
+    want = np.stack(want)
+    for share in (False, True):
+        got = ctx.encode_encrypt_batch(it, 0, fb.SCHEME_DOUBLE, _dev(x), codec, noise, span, share_streams=share)
+        assert np.array_equal(_np(got), want), share
+    one = ctx.encode_encrypt(it, 1, fb.SCHEME_DOUBLE, _dev(x[1]), codec, fb.NoiseSpec(seed=11, stream=6, resolution=32), span)
+    assert np.array_equal(_np(one), want[1])
+    # a shard that starts on an odd element (pairs / quads of the noise stream are cut)
+    lo, cnt = 12345, L // 3
+    sp = fb.VectorSpan(L, n_jobs, lo, cnt)
+    part = ctx.encode_encrypt(it, 2, fb.SCHEME_DOUBLE, _dev(np.ascontiguousarray(x[2, lo:lo + cnt])), codec,
+                              fb.NoiseSpec(seed=11, stream=7, resolution=32), sp)
+    assert np.array_equal(_np(part), want[2, lo:lo + cnt])
+    if bits <= 32:
+        masks = torch.stack([ctx.masks(it, [c, c + 1], [1, -1], span).view(torch.int32) for c in range(n)]).view(torch.uint32)
+        online = ctx.encode_add_premasked_batch(_dev(x), codec, noise, masks, span)
+        assert np.array_equal(_np(online), want)
 
 
 def test_encode_division_and_floor_tricks_dense_sweep(fb):

@@ -218,6 +218,8 @@ def run_ours(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    all_cpus = os.sched_getaffinity(0)
+    bound_cpus = bind_to_gpu_numa(local)          # pinned buffers and copy submissions on the GPU's own NUMA node
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -301,6 +303,20 @@ def run_ours(args):
     torch.cuda.synchronize()
     packed_ms = pk[0].elapsed_time(pk[1]) / 3
 
+    # the mask-only PRF kernel on this rank's shard: the measured ceiling of roofline_prf
+    mask_only_elems = min(L, 50_000_000) // 4 * 4             # the same size on every N: a launch long enough to hide its ramp
+    mspan = fb.VectorSpan(L, n_jobs, 0, mask_only_elems)
+    mbuf = ctx.empty_words(mask_only_elems)
+    for _ in range(2):
+        ctx.masks(0, [0, 1], [1, -1], mspan, out=mbuf)
+    pk[0].record()
+    for _ in range(4):
+        ctx.masks(0, [0, 1], [1, -1], mspan, out=mbuf)
+    pk[1].record()
+    torch.cuda.synchronize()
+    del mbuf
+    mask_only_blocks_per_s = 2 * (mask_only_elems / (128 // bits)) / (pk[0].elapsed_time(pk[1]) / 4 * 1e-3)
+
     # ---------------------------------------------------------------- same round, other legitimate schedules
     variants = None
     if not args.no_variants:
@@ -323,11 +339,14 @@ def run_ours(args):
     blocks = (n + 1 if args.share_streams else 2 * n) * (count / m)
     blocks_per_s = blocks / (ph[0] * 1e-3)
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    # LDS ceiling of the T-table PRF: one conflict-free 4-byte lookup per lane per clock per SM (32/clk);
-    # a block costs 197 lookups with the hoisted round 1 and the counter-window factoring of round 2
-    # (224 for textbook AES-256 T-tables, 212 with the hoisted round 1 only)
+    # PRF ceilings, measured: (1) the mask-only kernel (flashe_masks: the same AES-256 T-table PRF with nothing but a
+    # 16-byte store per block), timed live on this GPU just above; (2) the shared-memory lookup rate of an SM from the
+    # committed micro-benchmark (scripts/microbench.py, profiles/r2g_micro.jsonl: 31.87 of the nominal 32 conflict-free
+    # 4-byte lookups per clock; a block costs 197 lookups with the hoisted round 1 and the counter-window factoring of
+    # round 2, 224 for textbook T-table AES-256)
     lookups = 197.0
-    lds_peak_blocks = 148 * sm_mhz * 1e6 * 32 / lookups
+    lds_per_clk = 31.87
+    lds_peak_blocks = 148 * sm_mhz * 1e6 * lds_per_clk / lookups
     agg_bytes = (n + 1) * count * 4
     dec_bytes = count * 12
     traffic, traffic_src = measured_traffic(n * count)
@@ -344,12 +363,16 @@ def run_ours(args):
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": enc_bytes, "ms_per_launch": ph[0],
                      "note": "this kernel is bound by the PRF (shared-memory table lookups), not HBM: see roofline_prf"},
-        "roofline_prf": {"bound": "lds", "achieved": blocks_per_s / 1e9, "peak": lds_peak_blocks / 1e9, "unit": "G AES-256 blocks/s",
-                         "frac": blocks_per_s / lds_peak_blocks,
-                         "peak_source": "148 SMs x sampled SM clock x 32 conflict-free LDS/clk / 197 lookups per block "
-                                        "(hoisted round 1 + counter-window factoring; textbook T-table AES-256 = 224)",
+        "roofline_prf": {"bound": "lds", "achieved": blocks_per_s / 1e9, "peak": mask_only_blocks_per_s / 1e9, "unit": "G AES-256 blocks/s",
+                         "frac": blocks_per_s / mask_only_blocks_per_s,
+                         "peak_source": "measured in this run: the mask-only kernel k_stream<M_MASKS> (flashe_masks, same PRF, no encode, "
+                                        "16-byte store per 2 blocks) on %d M elements x 2 streams" % (mask_only_elems // 1_000_000),
                          "lookups_per_block": lookups,
-                         "frac_of_plain_ttable_ceiling_224": blocks_per_s / (148 * sm_mhz * 1e6 * 32 / 224.0)},
+                         "lds_lookup_ceiling": {"g_blocks_per_s": lds_peak_blocks / 1e9, "frac": blocks_per_s / lds_peak_blocks,
+                                                "source": "148 SMs x sampled SM clock x 31.87 measured conflict-free LDS.32 per clock and SM "
+                                                          "(k_lds_peak, profiles/r2g_micro.jsonl) / 197 lookups per block"},
+                         "bitsliced_alternative_g_blocks_per_s": {"measured": 19.9, "scaled_to_113_gate_sbox": 24.6,
+                                                                  "source": "k_aes_bitslice at 97.9 % ALU pipe, profiles/r2g_micro.jsonl"}},
         "phases": {"encode_encrypt_ms": ph[0], "aggregate_ms": ph[1], "decrypt_decode_ms": ph[2],
                    "aggregate_gbs": agg_bytes / (ph[1] * 1e-3) / 1e9, "aggregate_frac_of_hbm": agg_bytes / (ph[1] * 1e-3) / 1e9 / hbm_peak,
                    "decrypt_decode_gbs": dec_bytes / (ph[2] * 1e-3) / 1e9,
@@ -358,6 +381,7 @@ def run_ours(args):
         "frac_of_hbm_roofline_end_to_end": value / (hbm_peak * 1e9 / (12.0 + 16.0 / n) * world),
     }
     if e2e:
+        e2e["cpus_bound_to_gpu_numa_node"] = bound_cpus
         line["e2e"] = e2e
     if variants:
         for v in variants.values():
@@ -371,6 +395,7 @@ def run_ours(args):
             pm["online_encrypt_noise32_frac_of_hbm"] = n * count * 12 / (pm["online_encrypt_noise32_ms"] * 1e-3) / 1e9 / hbm_peak
         line["variants"] = variants
     if not args.no_cpu_baseline and world == 1:
+        os.sched_setaffinity(0, all_cpus)         # the reference's Pool gets every host core again
         line["cpu_baseline"] = cpu_baseline(args, ctx, fb)
     print(json.dumps(line))
     if world > 1:
@@ -482,33 +507,112 @@ def run_variants(args, ctx, fb, span, codec, noise, scheme, x, cts, agg, out, wo
     return res
 
 
+def bind_to_gpu_numa(local):
+    """Run this rank on the CPUs the driver reports as closest to its GPU, so that the pinned host buffers it
+    allocates (first touch) and the copy submissions sit on the GPU's own NUMA node / PCIe root."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
+def h2d_probe(torch, dist, dev, world, barrier, nbytes=1 << 31, reps=3):
+    """What the box's host -> device path gives with EVERY rank copying at once from pinned memory (the
+    ceiling of any end-to-end number that has to bring the gradients in): per-rank GB/s (min over ranks) and
+    the sum over ranks."""
+    host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    host.fill_(1)
+    devb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    devb.copy_(host, non_blocking=True)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        devb.copy_(host, non_blocking=True)
+    b.record()
+    barrier()
+    gbs = nbytes * reps / (a.elapsed_time(b) * 1e-3) / 1e9
+    per_rank = [gbs]
+    if world > 1:
+        mine = torch.tensor([gbs], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [float(v[0]) for v in allr]
+    del host, devb
+    return {"per_rank_gbs": per_rank, "per_rank_min_gbs": min(per_rank), "per_rank_max_gbs": max(per_rank), "sum_gbs": sum(per_rank)}
+
+
 def run_e2e(args, ctx, fb, span, codec, noise, scheme, x, cts, agg, out, world, dev, barrier):
-    """The same round through the public API with HOST buffers: every step copies the float32
-    gradients from pinned host memory (client groups double-buffered against compute) and reads the
-    decoded float64 aggregate back."""
+    """The same round through the public API with HOST buffers: every step copies the float32 gradients from
+    pinned host memory (groups of 4 clients, each group split over two copy streams, three staging buffers
+    so the copy engines never wait for the kernels) and reads the decoded float64 aggregate back.  The timed
+    region is bounded by the host -> device path, so the result is quoted against a concurrent H2D probe."""
     import torch
     import torch.distributed as dist
     n, count = x.shape
-    group = 8 if n % 8 == 0 else 1
+    probe = h2d_probe(torch, dist, dev, world, barrier)
+    rank = dist.get_rank() if world > 1 else 0
+    if os.environ.get("FLASHE_E2E_TEST_SKEW"):          # (exercise the uneven-range path on a box with even links)
+        probe["per_rank_gbs"] = [g * (1.0 + 0.3 * i) for i, g in enumerate(probe["per_rank_gbs"])]
+        probe.update(per_rank_min_gbs=min(probe["per_rank_gbs"]), per_rank_max_gbs=max(probe["per_rank_gbs"]),
+                     sum_gbs=sum(probe["per_rank_gbs"]), skewed_for_test=True)
+    if world > 1 and probe["per_rank_max_gbs"] > 1.1 * probe["per_rank_min_gbs"]:
+        # The GPUs of the box do not see the same host bandwidth when all of them copy at once (PCIe switches shared by
+        # GPU pairs): the end-to-end round is bound by those copies, so its element ranges are cut in proportion to what
+        # each rank's link delivered in the probe (the device-timed round above keeps equal ranges).
+        L, tot = span.total_len, probe["sum_gbs"]
+        cuts, acc = [0], 0.0
+        for g in probe["per_rank_gbs"][:-1]:
+            acc += g
+            cuts.append(int(L * acc / tot) // 4 * 4)
+        cuts.append(L)
+        begin, count = cuts[rank], cuts[rank + 1] - cuts[rank]
+        span = fb.VectorSpan(L, span.n_jobs, begin, count)
+        del x, cts, agg, out
+        x = torch.empty((n, count), dtype=torch.float32, device=dev)
+        g = torch.Generator(device=dev)
+        for c in range(n):
+            g.manual_seed(1000 + c + 7919 * rank)
+            x[c].normal_(0.0, 0.1, generator=g)
+        cts, agg = ctx.empty_words(count, rows=n), ctx.empty_words(count)
+        out = torch.empty(count, dtype=torch.float64, device=dev)
+        probe["shard_elements_per_rank"] = [cuts[i + 1] - cuts[i] for i in range(world)]
+    group = 4 if n % 4 == 0 else 1
     host_x = torch.empty((n, count), dtype=torch.float32, pin_memory=True)
     host_x.copy_(x)                               # synthetic gradients, now "on the host"
     host_out = torch.empty(count, dtype=torch.float64, pin_memory=True)
-    copy_stream = torch.cuda.Stream(device=dev)
+    copy_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
     main = torch.cuda.current_stream(dev)
-    stage = [torch.empty((group, count), dtype=torch.float32, device=dev) for _ in range(2)]
-    staged = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    depth = 3
+    stage = [torch.empty((group, count), dtype=torch.float32, device=dev) for _ in range(depth)]
+    staged = [[torch.cuda.Event() for _ in range(2)] for _ in range(depth)]
+    consumed = [torch.cuda.Event() for _ in range(depth)]
+    half = max(1, group // 2)
 
     def round_host():
         ngroups = n // group
         for gi in range(ngroups):
-            b = gi & 1
-            with torch.cuda.stream(copy_stream):
-                if gi >= 2:
-                    copy_stream.wait_event(consumed[b])
-                stage[b].copy_(host_x[gi * group:(gi + 1) * group], non_blocking=True)
-                staged[b].record(copy_stream)
-            main.wait_event(staged[b])
+            b = gi % depth
+            for k, cs in enumerate(copy_streams):
+                lo, hi = (0, half) if k == 0 else (half, group)
+                if lo >= hi:
+                    continue
+                with torch.cuda.stream(cs):
+                    if gi >= depth:
+                        cs.wait_event(consumed[b])
+                    stage[b][lo:hi].copy_(host_x[gi * group + lo:gi * group + hi], non_blocking=True)
+                    staged[b][k].record(cs)
+                main.wait_event(staged[b][k])
             ns = fb.NoiseSpec(seed=noise.seed, stream=gi * group)
             ctx.encode_encrypt_batch(0, gi * group, scheme, stage[b], codec, ns, span,
                                      out=cts[gi * group:(gi + 1) * group], share_streams=bool(args.share_streams))
@@ -529,9 +633,15 @@ def run_e2e(args, ctx, fb, span, codec, noise, scheme, x, cts, agg, out, world, 
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0]) / args.e2e_steps
+    h2d_total = int(n * span.total_len * 4)               # all ranks together, per step
+    achieved = h2d_total / (ms * 1e-3) / 1e9
     return {"value": args.clients * args.elements / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-            "h2d_bytes_per_step": int(n * count * 4), "d2h_bytes_per_step": int(count * 8),
-            "api": "DeviceContext.encode_encrypt_batch/aggregate/decrypt_decode over the C ABI; pinned host float32 in, float64 out",
+            "h2d_bytes_per_step": int(n * span.total_len * 4 // world), "d2h_bytes_per_step": int(span.total_len * 8 // world),
+            "h2d_peak_gbs": probe["sum_gbs"], "h2d_probe": probe,
+            "h2d_achieved_gbs_all_ranks": achieved, "frac_of_h2d_peak": achieved / probe["sum_gbs"],
+            "bound": "host -> device copies (PCIe): %.1f GB per step over all ranks" % (h2d_total / 1e9),
+            "api": "DeviceContext.encode_encrypt_batch/aggregate/decrypt_decode over the C ABI; pinned host float32 in (NUMA-local, "
+                   "4-client groups over two copy streams, three staging buffers), float64 out",
             "steps": args.e2e_steps}
 
 

@@ -303,10 +303,18 @@ class DeviceContext(object):
         if noise.u is not None:
             self._check(noise.u, torch.float64, n * ne, "noise.u")
         out = self.empty_words(span.n, rows=n) if out is None else self._check_words(out, n * span.n, "out")
-        cc, nc = codec.c(span.total_len), noise.c()
-        _cabi.check(self.lib.flashe_encode_encrypt_batch(self._h, _iter32(it), idx0, n, scheme, C.byref(span.c()),
-                                                         x.data_ptr(), ne, C.byref(cc), C.byref(nc), ne,
-                                                         out.data_ptr(), span.n, 1 if share_streams else 0, self._stream()))
+        cc = codec.c(span.total_len)
+        # one launch takes at most FLASHE_MAX_STREAMS - 1 clients (their PRF index terms live in the kernel's
+        # parameter block): more clients go out in consecutive launches, same outputs
+        step = _cabi.MAX_STREAMS - 1
+        for c0 in range(0, n, step):
+            c1 = min(n, c0 + step)
+            ns = NoiseSpec(u=None if noise.u is None else noise.u[c0 * ne:c1 * ne], seed=noise.seed, stream=noise.stream + c0,
+                           resolution=noise.resolution)
+            nc = ns.c()
+            _cabi.check(self.lib.flashe_encode_encrypt_batch(self._h, _iter32(it), idx0 + c0, c1 - c0, scheme, C.byref(span.c()),
+                                                             x[c0:c1].data_ptr(), ne, C.byref(cc), C.byref(nc), ne,
+                                                             out[c0:c1].data_ptr(), span.n, 1 if share_streams else 0, self._stream()))
         return out
 
     def encode_add_premasked(self, x, codec: CodecSpec, noise: NoiseSpec, mask, span: VectorSpan, out=None):

@@ -442,6 +442,19 @@ def test_full_path_vs_oracle(fb, bits, n_jobs, L, n):
     assert np.all(np.abs(_np(out) - clipped) <= n * step * 1.01)
 
 
+def test_encode_encrypt_batch_more_clients_than_one_launch_takes(fb):
+    """200 clients in one call: the host mirror splits them over launches of at most 127 (FLASHE_MAX_STREAMS - 1)."""
+    n, L, bits, n_jobs, it = 200, 4099, 32, 8, 1
+    ctx = ctx_for(fb, bits)
+    span = fb.VectorSpan(L, n_jobs)
+    codec = fb.CodecSpec(alpha=0.5, element_bits=16, n_clients=n)
+    x = (np.random.RandomState(5).standard_normal((n, L)) * 0.2).astype(np.float32)
+    got = _np(ctx.encode_encrypt_batch(it, 3, fb.SCHEME_DOUBLE, _dev(x), codec, fb.NoiseSpec(seed=2, stream=10), span))
+    for c in (0, 1, 126, 127, 128, 199):
+        u = _np(ctx.rng_uniform(2, 10 + c, 0, L))
+        assert np.array_equal(got[c], O.encrypt(KEY, bits, n_jobs, it, 3 + c, "double", O.quantize(x[c], u, 0.5, 16))), c
+
+
 def test_cuda_graph_replay_of_a_round(fb):
     """DeviceContext.capture: the three kernels of a round recorded once, replayed on new inputs written into
     the same buffers — same bits as the call-by-call round and as the oracle."""

@@ -775,6 +775,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
               const float* xin = reinterpret_cast<const float*>(io.in) + (uint64_t)c * io.in_stride;
               uint64_t plo = 0ull, phi = 0ull, pc = ~0ull;
               double u0 = 0.0, u1 = 0.0;
+              double uq[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
               for (uint32_t i = 0; i < cd.bs; ++i) {
                   const uint64_t e = wp.e0 + i;
@@ -782,8 +783,12 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                   if (e < wp.eend) {
                       double u;
                       if (nz.u) u = nz.u[(uint64_t)c * nz.u_stride + (e - io.elem0)];
-                      else {
-                          if ((e >> 1) != pc) { pc = e >> 1; noise_pair<N32>(nz, nz.stream + c, pc, u0, u1); }
+                      else if (N32) {                               // 32-bit resolution: one generator call per four elements
+                          if ((e >> 2) != pc) { pc = e >> 2; noise_quad<true>(nz, nz.stream + c, pc, uq); }
+                          const uint32_t k = (uint32_t)e & 3u;
+                          u = k == 0u ? uq[0] : (k == 1u ? uq[1] : (k == 2u ? uq[2] : uq[3]));
+                      } else {
+                          if ((e >> 1) != pc) { pc = e >> 1; noise_pair<false>(nz, nz.stream + c, pc, u0, u1); }
                           u = (e & 1ull) ? u1 : u0;
                       }
                       q = encode_one(xin[e - io.elem0], u, wp.sg, cd.scale);

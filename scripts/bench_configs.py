@@ -47,9 +47,18 @@ def dense_round(name, L, n, bits, n_jobs, dev):
     ms_calls = timed(rnd)                       # three library calls per round from Python (host-side marshalling included)
     replay = ctx.capture(rnd)                   # the same three kernels as one CUDA graph launch
     ms = timed(replay, steps=20, warmup=5)
+    noise32 = fb.NoiseSpec(seed=7, stream=0, resolution=32)
+
+    def rnd32():
+        ctx.encode_encrypt_batch(0, 0, fb.SCHEME_DOUBLE, x, codec, noise32, span, out=cts)
+        ctx.aggregate(cts, fb.AGG_ELEMENTWISE, out=agg)
+        ctx.decrypt_decode(0, [n], [0], agg, codec, span, out=out)
+
+    ms32 = timed(ctx.capture(rnd32), steps=20, warmup=5)
     m = 128 // bits
     print(json.dumps({"config": name, "elements": L, "clients": n, "int_bits": bits, "n_jobs": n_jobs, "ms_per_round": ms,
-                      "ms_per_round_separate_calls": ms_calls, "schedule": "CUDA graph of 3 kernels (encode+encrypt batch, aggregate, decrypt+decode)",
+                      "ms_per_round_separate_calls": ms_calls, "ms_per_round_noise_32bit_resolution": ms32,
+                      "g_aes_blocks_per_s_noise_32bit_resolution": (2 * n + 2) * -(-L // (128 // bits)) / (ms32 * 1e-3) / 1e9, "schedule": "CUDA graph of 3 kernels (encode+encrypt batch, aggregate, decrypt+decode)",
                       "client_elements_per_s": n * L / (ms * 1e-3), "aes_blocks_per_round": (2 * n + 2) * -(-L // m),
                       "g_aes_blocks_per_s": (2 * n + 2) * -(-L // m) / (ms * 1e-3) / 1e9}), flush=True)
 
@@ -103,10 +112,17 @@ def batched_round(dev, L=25_000_000, n=10, n_jobs=16, bits=120, element_bits=16)
     rnd(); rnd_fused()
     same = bool(torch.equal(cts.view(torch.int64), cts2.view(torch.int64)))
     fused_ms = timed(rnd_fused, steps=5, warmup=2)
+
+    def rnd_fused32():
+        ctx.encode_encrypt_batch(0, 0, fb.SCHEME_DOUBLE, x, bcodec, fb.NoiseSpec(seed=7, stream=0, resolution=32), span_w, out=cts2)
+        ctx.aggregate(cts2, fb.AGG_ELEMENTWISE, out=agg2)
+        ctx.decrypt_decode(0, [n], [0], agg2, bcodec, span_w, out=out2)
+
+    fused32_ms = timed(rnd_fused32, steps=5, warmup=2)
     fused_packed_ms = timed(rnd_fused_packed, steps=5, warmup=2)
     print(json.dumps({"config": "batched: 25M elements as 120-bit words (6 lanes), 10 clients, full round", "elements": L, "words": nw, "clients": n,
                       "int_bits": bits, "n_jobs": n_jobs, "ms_per_round": fused_ms, "client_elements_per_s": n * L / (fused_ms * 1e-3),
-                      "ms_per_round_packed_carry_sum": fused_packed_ms,
+                      "ms_per_round_packed_carry_sum": fused_packed_ms, "ms_per_round_noise_32bit_resolution": fused32_ms,
                       "ms_per_round_unfused_7_kernels": ms, "fused_ciphertexts_equal_unfused": same,
                       "g_aes_blocks_per_s": (2 * n + 2) * nw / (fused_ms * 1e-3) / 1e9,
                       "encrypt_only_ms_10_clients": enc_ms, "encrypt_g_aes_blocks_per_s": 2 * n * nw / (enc_ms * 1e-3) / 1e9}), flush=True)

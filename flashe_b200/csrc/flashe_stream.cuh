@@ -326,6 +326,9 @@ static __device__ __noinline__ void aes256_block_slow(const KeySched& ks, uint32
 // 25M x 10 clients at int_bits 20, encode 2.60 -> 2.45 ms.
 #define FLASHE_AES_UNROLL_M6 1
 #endif
+#ifndef FLASHE_AES_UNROLL_A6
+#define FLASHE_AES_UNROLL_A6 1      // the m == 6, aligned instantiation (b = 20)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // k_stream: persistent, one 512-thread CTA per SM (128 KB of tables + per-warp slabs).
@@ -432,6 +435,9 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     // m = 4, chunk starts off a 16-byte boundary: instead of 64/32-bit pieces the lanes own the memory-ALIGNED
     // quads and receive the 1-3 mask words that belong to the neighbouring block by shuffle (see fast_item)
     constexpr bool SHIFT_OK = (WORDS == 1 && MMAX == 4 && !ALIGNED && !SHARE && MODE != M_SCATTER);
+    // ALIGNED with MMAX == 6: m is exactly 6 (b = 20, 21: the reference's shipped width) and every chunk starts on a
+    // multiple of 4 elements, so an item is 96 whole 16-byte quads (three per lane) and m is a compile-time constant
+    constexpr bool A6 = (WORDS == 1 && MMAX == 6 && ALIGNED);
     // 16-byte words (the shipped 120-bit batch mode), m = 1: masks / apply always; encode / decode when the codec
     // batches lanes into the word (cd.bs != 0: encode -> pack -> mask and unmask -> unpack -> decode fused)
     constexpr bool W4_OK = (WORDS == 4 && !SHARE && MODE != M_SCATTER);
@@ -508,7 +514,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
       // through the slab, and all per-item geometry is a handful of additions.  The bounds are
       // computed once per unit.
       uint64_t wf_lo = 1, wf_hi = 0;
-      const uint32_t mm = (WORDS == 1 && MMAX == 4) ? 4u : (WORDS == 4 ? 1u : m);   // compile-time where the instantiation fixes it
+      const uint32_t mm = (WORDS == 1 && MMAX == 4) ? 4u : (A6 ? 6u : (WORDS == 4 ? 1u : m));   // compile-time where the instantiation fixes it
       const uint32_t item_elems = ITEM_BLOCKS * mm;
       // (8-byte words: only m = 2, and only chunks that start on an even element of an even shard, so that a
       //  block is one aligned 16-byte pair and one noise pair)
@@ -564,7 +570,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
 #pragma unroll
                   for (int k = 0; k < NQ; ++k) {
                       const uint32_t q = lane + 32u * k;
-                      if ((MMAX == 4 || q < nquads) && !(run_first && q == 0u)) ldg_quad(in + 4u * q, qr, r[k]);
+                      if ((MMAX == 4 || A6 || q < nquads) && !(run_first && q == 0u)) ldg_quad(in + 4u * q, qr, r[k]);
                   }
               }
               uint32_t acc[NB][MMAX];
@@ -593,7 +599,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wc.c0), "=r"(wc.c1), "=r"(wc.c2), "=r"(wc.c3) : "r"(slot) : "memory");
                   }
                   uint32_t oa[4], ob[4];
-                  aes256_x2w<(MMAX == 4 ? FLASHE_AES_UNROLL : FLASHE_AES_UNROLL_M6)>(ks, y, st.pre[sidx][0], wc, ctrA, ctrB, oa, ob);
+                  aes256_x2w<(MMAX == 4 ? FLASHE_AES_UNROLL : (A6 ? FLASHE_AES_UNROLL_A6 : FLASHE_AES_UNROLL_M6))>(ks, y, st.pre[sidx][0], wc, ctrA, ctrB, oa, ob);
                   accumulate_slots<1, MMAX>(oa, g.b, mm, sign, acc[0]);
                   accumulate_slots<1, MMAX>(ob, g.b, mm, sign, acc[1]);
               }
@@ -616,7 +622,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
 #pragma unroll
                   for (int h = 0; h < NB; ++h) {
                       const uint32_t a0 = fslab + (lane + 32u * h) * mm * 4u;
-                      if (mm == 6u) {
+                      if (A6 || mm == 6u) {
 #pragma unroll
                           for (int k = 0; k + 1 < MMAX; k += 2)
                               asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a0 + 4u * k), "r"(acc[h][k]), "r"(acc[h][k + 1]) : "memory");
@@ -662,7 +668,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
 #pragma unroll
               for (int h = 0; h < NQ; ++h) {
                   const uint32_t q = lane + 32u * h;                 // this lane's h-th quad of the item
-                  if (MMAX != 4 && q >= nquads) break;
+                  if (MMAX != 4 && !A6 && q >= nquads) break;
                   if (SHIFT_OK && run_first && q == 0u) continue;    // partial quad: handled element-wise below
                   const uint64_t o = o0q + 4u * q;
                   const uint64_t j = e0q + 4u * q;
@@ -1214,6 +1220,7 @@ static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom&
             if (b <= 32) {
                 if (ctx->m == 4 && g.aligned4 && io.quad) return launch_stream_t<1, 4, MODE, true, true, N32>(ctx, st, g, io, cd, nz, stream);
                 if (ctx->m <= 4) return launch_stream_t<1, 4, MODE, true, false, N32>(ctx, st, g, io, cd, nz, stream);
+                if (ctx->m == 6 && g.aligned4 && io.quad) return launch_stream_t<1, 6, MODE, true, true, N32>(ctx, st, g, io, cd, nz, stream);
                 if (ctx->m <= 6) return launch_stream_t<1, 6, MODE, true, false, N32>(ctx, st, g, io, cd, nz, stream);
                 return launch_stream_t<1, 16, MODE, true, false, N32>(ctx, st, g, io, cd, nz, stream);
             }
@@ -1224,6 +1231,7 @@ static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom&
     if (b <= 32) {
         if (ctx->m == 4 && g.aligned4 && io.quad && MODE != M_SCATTER) return launch_stream_t<1, 4, MODE, false, true, N32>(ctx, st, g, io, cd, nz, stream);
         if (ctx->m <= 4) return launch_stream_t<1, 4, MODE, false, false, N32>(ctx, st, g, io, cd, nz, stream);
+        if (ctx->m == 6 && g.aligned4 && io.quad && MODE != M_SCATTER) return launch_stream_t<1, 6, MODE, false, true, N32>(ctx, st, g, io, cd, nz, stream);
         if (ctx->m <= 6) return launch_stream_t<1, 6, MODE, false, false, N32>(ctx, st, g, io, cd, nz, stream);
         return launch_stream_t<1, 16, MODE, false, false, N32>(ctx, st, g, io, cd, nz, stream);
     }

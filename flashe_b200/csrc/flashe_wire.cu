@@ -519,11 +519,21 @@ k_topk_hist(const float* __restrict__ x, const TopkSeg* __restrict__ segs, int n
         const uint32_t prefix = st[s].prefix;
         const uint64_t base = (tile - sg.tile0) * TK_TILE;
         const float* xs = x + sg.begin;
-#pragma unroll 4
-        for (int r = 0; r < TK_PER; ++r) {
-            const uint64_t i = base + (uint64_t)r * TK_THREADS + threadIdx.x;
-            if (i < sg.n) {
-                const uint32_t key = key_of(xs[i]);
+        // 16-byte loads (four per thread in flight) when the layer starts on a 16-byte boundary; element order does
+        // not matter for a histogram
+        const bool vec = (((uintptr_t)xs) & 15u) == 0;
+#pragma unroll
+        for (int r = 0; r < TK_PER / 4; ++r) {
+            const uint64_t i = base + 4ull * ((uint64_t)r * TK_THREADS + threadIdx.x);
+            uint32_t keys[4]; uint32_t nk = 0;
+            if (vec && i + 4 <= sg.n) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(xs + i));
+                keys[0] = key_of(v.x); keys[1] = key_of(v.y); keys[2] = key_of(v.z); keys[3] = key_of(v.w); nk = 4;
+            } else {
+                for (uint32_t k = 0; k < 4u && i + k < sg.n; ++k) keys[nk++] = key_of(xs[i + k]);
+            }
+            for (uint32_t k = 0; k < nk; ++k) {
+                const uint32_t key = keys[k];
                 if (hi_shift >= 31u || (key >> hi_shift) == (prefix >> hi_shift)) atomicAdd(&sh[(key >> shift) & dmask], 1u);
             }
         }
@@ -580,10 +590,18 @@ k_topk_count(const float* __restrict__ x, const TopkSeg* __restrict__ segs, int 
         const uint64_t base = (tile - sg.tile0) * TK_TILE;
         const float* xs = x + sg.begin;
         uint32_t g = 0, e = 0;
-#pragma unroll 4
-        for (int r = 0; r < TK_PER; ++r) {
-            const uint64_t i = base + (uint64_t)r * TK_THREADS + threadIdx.x;   // counts do not need index order
-            if (i < sg.n) { const uint32_t key = key_of(xs[i]); g += key > T; e += key == T; }
+        const bool vec = (((uintptr_t)xs) & 15u) == 0;
+#pragma unroll
+        for (int r = 0; r < TK_PER / 4; ++r) {                              // counts do not need index order
+            const uint64_t i = base + 4ull * ((uint64_t)r * TK_THREADS + threadIdx.x);
+            if (vec && i + 4 <= sg.n) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(xs + i));
+                const uint32_t k0 = key_of(v.x), k1 = key_of(v.y), k2 = key_of(v.z), k3 = key_of(v.w);
+                g += (k0 > T) + (k1 > T) + (k2 > T) + (k3 > T);
+                e += (k0 == T) + (k1 == T) + (k2 == T) + (k3 == T);
+            } else {
+                for (uint32_t k = 0; k < 4u && i + k < sg.n; ++k) { const uint32_t key = key_of(xs[i + k]); g += key > T; e += key == T; }
+            }
         }
         for (int d = 16; d > 0; d >>= 1) { g += __shfl_down_sync(0xffffffffu, g, d); e += __shfl_down_sync(0xffffffffu, e, d); }
         if ((threadIdx.x & 31u) == 0) { sg_[threadIdx.x >> 5] = g; se_[threadIdx.x >> 5] = e; }

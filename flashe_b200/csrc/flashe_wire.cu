@@ -8,6 +8,8 @@
 // multiple of the SM count, wide accesses where the layout allows.  No tensor cores.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -463,93 +465,106 @@ k_wire_unpack32_bulk(const uint8_t* __restrict__ in, uint64_t count, uint32_t bi
 // Selection = 3-pass MSD radix select on key = bits(|x|) (monotone for non-negative floats, NaN above
 // inf as numpy sorts it): 11 + 11 + 9 bits, block-private shared-memory histograms merged with global
 // atomics, one small block picks the bucket.  Compaction keeps index order (= sorted locations): tile
-// counts, one-block scan, ordered write.  x is read 5 times (L2-resident for layers up to ~30 M).
+// counts, one-block scan, ordered write.
+//
+// Two routes to the threshold, chosen per layer ON THE DEVICE, with identical results:
+//   candidate route (sparse selections, k <= n/40): a strided sample of the layer (<= 16 K elements) gives a
+//     conservative lower bound `lo` (the lower edge of the 11-bit bucket holding the sample's r-th largest key,
+//     r ~ 1.5x the expected rank + 6 sigma); ONE pass over x appends every element with key >= lo (2-4 % of
+//     the layer) to a candidate list; the three radix passes and the tile counts then run on that list.  x is
+//     read twice in total (filter, ordered write) instead of five times and no histogram sees every element
+//     (a shared-memory atomic per element costs ~2 clk per lane, 10x the HBM time of the pass).
+//   exact route: the radix passes and the tile counts read x itself.  Taken by layers that are too small or
+//     too dense for sampling, and by any layer whose candidate list turns out to hold fewer than k elements
+//     (bound above the true threshold: skewed sample) or to overflow its region (n/8 slots: heavy ties).
+//   Both routes end in the same TopkState (threshold, ties to skip) because the bound is bucket-aligned:
+//   every bucket at or above the threshold's is complete in the candidate list.
 // =================================================================================================
 struct TopkState { uint32_t prefix; uint32_t k_rem; uint32_t c_eq; uint32_t pad; };
-// one layer: elements [begin, begin+n) of x, k to keep, first tile number, first output slot
-struct TopkSeg { uint64_t begin; uint64_t tile0; uint64_t out_off; uint32_t n; uint32_t k; };
+// one layer: elements [begin, begin+n) of x, k to keep, first tile number, first output slot; candidate route:
+// region [cbegin, cbegin+cap) of the candidate arrays (tiles from ctile0), sample lines (32 elements each)
+// numbered from samp0: line i sits at element 32 * (i * samp_stride + jitter(i)); samp_rank = r above.
+struct TopkSeg {
+    uint64_t begin, tile0, out_off;
+    uint32_t n, k;
+    uint64_t cbegin, ctile0, samp0;
+    uint32_t cap, samp_lines, samp_stride, samp_rank;
+};
 
 #define TK_THREADS 256
 #define TK_PER 16
 #define TK_TILE (TK_THREADS * TK_PER)
 #define TK_BINS 2048
+#define TK_SAMPLE_ALL 16384u         // layers up to this size are "sampled" completely
 
 __device__ __forceinline__ uint32_t key_of(float x) { return __float_as_uint(x) & 0x7fffffffu; }
+__device__ __forceinline__ uint32_t key_of_bits(uint32_t w) { return w & 0x7fffffffu; }
+// Every kernel of the chain is launched with programmatic stream serialization (topk_launch): it may start while
+// its predecessor drains, lets its own successor do the same, and waits here before touching any data.
+__device__ __forceinline__ void topk_pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 // All layers are processed by the same launches: the tiles (TK_TILE elements, never across a layer
-// boundary) of every layer are numbered consecutively and a tile finds its layer by binary search.
-__device__ __forceinline__ int topk_seg_of_tile(const TopkSeg* __restrict__ segs, int nseg, uint64_t tile) {
+// boundary) of every layer are numbered consecutively and a tile finds its layer by binary search: the LAST
+// layer whose first tile is <= the tile (layers without tiles of a kind share their successor's number).
+// WHICH: 0 = x tiles (tile0), 1 = candidate tiles (ctile0), 2 = sample lines (samp0).
+template <int WHICH>
+__device__ __forceinline__ uint64_t topk_first(const TopkSeg& s) { return WHICH == 0 ? s.tile0 : (WHICH == 1 ? s.ctile0 : s.samp0); }
+template <int WHICH>
+__device__ __forceinline__ int topk_seg_of(const TopkSeg* __restrict__ segs, int nseg, uint64_t t) {
     int lo = 0, hi = nseg - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (segs[mid].tile0 <= tile) lo = mid; else hi = mid - 1; }
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (topk_first<WHICH>(segs[mid]) <= t) lo = mid; else hi = mid - 1; }
     return lo;
+}
+// The route of a layer, decided by its candidate count once the filter pass has run.
+__device__ __forceinline__ bool topk_exact_route(const TopkSeg& s, uint32_t count) { return s.cap == 0u || count > s.cap || count < s.k; }
+// What a histogram / count pass reads for a layer: CAND = the candidate keys of a candidate-route layer,
+// !CAND = x itself for an exact-route layer; n = 0 when the layer belongs to the other route.
+struct TopkView { uint64_t begin; uint64_t tile0; uint32_t n; };
+template <bool CAND>
+__device__ __forceinline__ TopkView topk_view(const TopkSeg& s, const uint32_t* __restrict__ cand_count, int idx) {
+    const uint32_t count = cand_count ? cand_count[idx] : 0u;
+    const bool exact = topk_exact_route(s, count);
+    TopkView v;
+    if (CAND) { v.begin = s.cbegin; v.tile0 = s.ctile0; v.n = exact ? 0u : count; }
+    else { v.begin = s.begin; v.tile0 = s.tile0; v.n = exact ? s.n : 0u; }
+    return v;
 }
 
 __global__ void k_topk_init(const TopkSeg* __restrict__ segs, int nseg, TopkState* __restrict__ st) {
+    topk_pdl_enter();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < nseg) { TopkState v; v.prefix = 0u; v.k_rem = segs[s].k; v.c_eq = 0u; v.pad = 0u; st[s] = v; }
 }
 
-// pass 0: shift 20 / 11 bits; pass 1: shift 9 / 11 bits; pass 2: shift 0 / 9 bits.
-// A block owns a contiguous run of tiles; its shared histogram is merged into the layer's global one
-// whenever the run crosses into the next layer (and at the end).
-__global__ void __launch_bounds__(TK_THREADS)
-k_topk_hist(const float* __restrict__ x, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles, uint64_t tiles_per_block,
-            const TopkState* __restrict__ st, uint32_t shift, uint32_t nbits, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t sh[TK_BINS];
-    const uint64_t t_begin = (uint64_t)blockIdx.x * tiles_per_block;
-    uint64_t t_end = t_begin + tiles_per_block;
-    if (t_end > ntiles) t_end = ntiles;
-    if (t_begin >= t_end) return;
-    for (uint32_t i = threadIdx.x; i < TK_BINS; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    const uint32_t hi_shift = shift + nbits;               // bits above the digit must equal the prefix
-    const uint32_t dmask = (1u << nbits) - 1u;
-    int s = topk_seg_of_tile(segs, nseg, t_begin);
-    for (uint64_t tile = t_begin; tile < t_end; ++tile) {
-        while (s + 1 < nseg && segs[s + 1].tile0 <= tile) {           // the run enters the next (non-empty) layer
-            __syncthreads();
-            for (uint32_t i = threadIdx.x; i < TK_BINS; i += blockDim.x) {
-                const uint32_t c = sh[i];
-                if (c) { atomicAdd(&hist[(size_t)s * TK_BINS + i], c); sh[i] = 0; }
-            }
-            __syncthreads();
-            ++s;
-        }
+__device__ __forceinline__ uint32_t topk_hash(uint32_t i) { i *= 0x9E3779B1u; i ^= i >> 15; i *= 0x85EBCA77u; i ^= i >> 13; return i; }
+
+// Sample histogram: one warp per sample line (32 consecutive elements, one or two 128-byte lines), top 11 key bits.
+__global__ void __launch_bounds__(256)
+k_topk_sample(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, int nseg, uint64_t nlines, uint32_t* __restrict__ hist) {
+    topk_pdl_enter();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t line = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; line < nlines; line += nwarps) {
+        const int s = topk_seg_of<2>(segs, nseg, line);
         const TopkSeg sg = segs[s];
-        const uint32_t prefix = st[s].prefix;
-        const uint64_t base = (tile - sg.tile0) * TK_TILE;
-        const float* xs = x + sg.begin;
-        // 16-byte loads (four per thread in flight) when the layer starts on a 16-byte boundary; element order does
-        // not matter for a histogram
-        const bool vec = (((uintptr_t)xs) & 15u) == 0;
-#pragma unroll
-        for (int r = 0; r < TK_PER / 4; ++r) {
-            const uint64_t i = base + 4ull * ((uint64_t)r * TK_THREADS + threadIdx.x);
-            uint32_t keys[4]; uint32_t nk = 0;
-            if (vec && i + 4 <= sg.n) {
-                const float4 v = __ldcs(reinterpret_cast<const float4*>(xs + i));
-                keys[0] = key_of(v.x); keys[1] = key_of(v.y); keys[2] = key_of(v.z); keys[3] = key_of(v.w); nk = 4;
-            } else {
-                for (uint32_t k = 0; k < 4u && i + k < sg.n; ++k) keys[nk++] = key_of(xs[i + k]);
-            }
-            for (uint32_t k = 0; k < nk; ++k) {
-                const uint32_t key = keys[k];
-                if (hi_shift >= 31u || (key >> hi_shift) == (prefix >> hi_shift)) atomicAdd(&sh[(key >> shift) & dmask], 1u);
-            }
-        }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < TK_BINS; i += blockDim.x) {
-        const uint32_t c = sh[i];
-        if (c) atomicAdd(&hist[(size_t)s * TK_BINS + i], c);
+        const uint32_t i = (uint32_t)(line - sg.samp0);
+        const uint32_t jit = sg.samp_stride > 1u ? topk_hash(i) % sg.samp_stride : 0u;
+        const uint64_t e = ((uint64_t)i * sg.samp_stride + jit) * 32u + lane;
+        if (e < sg.n) atomicAdd(&hist[(size_t)s * TK_BINS + (key_of_bits(x[sg.begin + e]) >> 20)], 1u);
     }
 }
 
-// One block of 1024 threads per layer: suffix sums of the histogram from the top bin; the bucket holding
-// the k_rem-th largest key extends the prefix.  Clears the histogram for the next pass.
+// One block of 1024 threads per layer: suffix sums of the histogram from the top bin.  Clears the histogram.
+//   lo_out == NULL  the bucket holding the k_rem-th largest key extends the layer's prefix (radix passes);
+//   lo_out != NULL  the lower edge of the bucket holding the sample's samp_rank-th largest key -> lo_out[layer].
 __global__ void __launch_bounds__(1024)
-k_topk_pick(uint32_t* __restrict__ hist_all, TopkState* __restrict__ st_all, uint32_t shift) {
+k_topk_pick(uint32_t* __restrict__ hist_all, TopkState* __restrict__ st_all, uint32_t shift, const TopkSeg* __restrict__ segs,
+            uint32_t* __restrict__ lo_out) {
     __shared__ uint32_t warp_tot[32];
+    topk_pdl_enter();
     uint32_t* hist = hist_all + (size_t)blockIdx.x * TK_BINS;
     TopkState* st = st_all + blockIdx.x;
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
@@ -568,58 +583,291 @@ k_topk_pick(uint32_t* __restrict__ hist_all, TopkState* __restrict__ st_all, uin
     }
     __syncthreads();
     const uint32_t before = (warp ? warp_tot[warp - 1] : 0u) + incl - (c0 + c1);   // keys in higher bins
-    const uint32_t k_rem = st->k_rem;
+    const uint32_t k_rem = lo_out ? segs[blockIdx.x].samp_rank : st->k_rem;
     __syncthreads();
     // the k_rem-th largest lies in the first bin (from the top) whose inclusive count reaches k_rem
-    if (before < k_rem && k_rem <= before + c0) {
+    const bool in0 = before < k_rem && k_rem <= before + c0;
+    const bool in1 = before + c0 < k_rem && k_rem <= before + c0 + c1;
+    if (lo_out) {
+        if (in0) lo_out[blockIdx.x] = b0 << 20; else if (in1) lo_out[blockIdx.x] = b1 << 20;   // (stays 0 when the sample is shorter than the rank)
+    } else if (in0) {
         st->prefix |= b0 << shift; st->k_rem = k_rem - before; st->c_eq = c0;
-    } else if (before + c0 < k_rem && k_rem <= before + c0 + c1) {
+    } else if (in1) {
         st->prefix |= b1 << shift; st->k_rem = k_rem - before - c0; st->c_eq = c1;
     }
 }
 
-// per-tile counts of (key > T, key == T)
-__global__ void __launch_bounds__(TK_THREADS)
-k_topk_count(const float* __restrict__ x, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles,
-             const TopkState* __restrict__ st, uint2* __restrict__ tile_counts) {
-    __shared__ uint32_t sg_[TK_THREADS / 32], se_[TK_THREADS / 32];
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int s = topk_seg_of_tile(segs, nseg, tile);
-        const TopkSeg sg = segs[s];
-        const uint32_t T = st[s].prefix;
-        const uint64_t base = (tile - sg.tile0) * TK_TILE;
-        const float* xs = x + sg.begin;
-        uint32_t g = 0, e = 0;
-        const bool vec = (((uintptr_t)xs) & 15u) == 0;
+// Sixteen keys of a tile per thread, four rows of one 16-byte quad each: row r, thread t holds elements
+// 4 * (256 r + t) .. + 3 of the tile, so that a warp covers 512 contiguous bytes per access.  `valid` = bit per key.
+__device__ __forceinline__ uint32_t topk_load_tile(const uint32_t* __restrict__ xs, uint64_t base, uint32_t n, bool vec, uint32_t (&w)[TK_PER]) {
+    uint32_t valid = 0u;
 #pragma unroll
-        for (int r = 0; r < TK_PER / 4; ++r) {                              // counts do not need index order
-            const uint64_t i = base + 4ull * ((uint64_t)r * TK_THREADS + threadIdx.x);
-            if (vec && i + 4 <= sg.n) {
-                const float4 v = __ldcs(reinterpret_cast<const float4*>(xs + i));
-                const uint32_t k0 = key_of(v.x), k1 = key_of(v.y), k2 = key_of(v.z), k3 = key_of(v.w);
-                g += (k0 > T) + (k1 > T) + (k2 > T) + (k3 > T);
-                e += (k0 == T) + (k1 == T) + (k2 == T) + (k3 == T);
-            } else {
-                for (uint32_t k = 0; k < 4u && i + k < sg.n; ++k) { const uint32_t key = key_of(xs[i + k]); g += key > T; e += key == T; }
+    for (int r = 0; r < TK_PER / 4; ++r) {
+        const uint64_t i = base + 4ull * ((uint64_t)r * TK_THREADS + threadIdx.x);
+        if (vec && i + 4 <= n) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(xs + i));
+            w[4 * r] = v.x; w[4 * r + 1] = v.y; w[4 * r + 2] = v.z; w[4 * r + 3] = v.w;
+            valid |= 0xfu << (4 * r);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w[4 * r + k] = 0u;
+                if (i + k < n) { w[4 * r + k] = xs[i + k]; valid |= 1u << (4 * r + k); }
             }
+        }
+    }
+    return valid;
+}
+
+// element k (dynamic) of a thread's sixteen registers: a select tree (used on the rare hit paths only)
+template <typename T>
+__device__ __forceinline__ T topk_pick16(const T (&v)[TK_PER], uint32_t k) {
+    const bool b0 = k & 1u, b1 = k & 2u, b2 = k & 4u, b3 = k & 8u;
+    const T a0 = b0 ? v[1] : v[0], a1 = b0 ? v[3] : v[2], a2 = b0 ? v[5] : v[4], a3 = b0 ? v[7] : v[6];
+    const T a4 = b0 ? v[9] : v[8], a5 = b0 ? v[11] : v[10], a6 = b0 ? v[13] : v[12], a7 = b0 ? v[15] : v[14];
+    const T c0 = b1 ? a1 : a0, c1 = b1 ? a3 : a2, c2 = b1 ? a5 : a4, c3 = b1 ? a7 : a6;
+    const T d0 = b2 ? c1 : c0, d1 = b2 ? c3 : c2;
+    return b3 ? d1 : d0;
+}
+// index inside the tile of a thread's element k (topk_load_tile's layout)
+__device__ __forceinline__ uint32_t topk_elem_of(uint32_t k) { return 4u * ((k >> 2) * TK_THREADS + threadIdx.x) + (k & 3u); }
+
+// Candidate filter: every element with key >= lo[layer] is appended (key, index within the layer) to the layer's
+// region.  A block owns a contiguous run of tiles (the layer table is walked, not searched) and collects its
+// candidates in shared memory; the region's cursor is bumped once per flush (buffer full, layer change, end of the
+// run) instead of once per tile, so no tile waits for the round trip of an atomic, and the flush writes are
+// coalesced.  The cursor keeps counting past the region's end, which is how the later passes see an overflow.
+// The loads of the next tile are in flight while the current one is scanned; the few candidates of a thread (2-4 %
+// of the elements) are visited through the set bits of its hit mask.
+#define TK_FBUF 2048u
+__global__ void __launch_bounds__(TK_THREADS)
+k_topk_filter(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles, uint64_t tiles_per_block,
+              const uint32_t* __restrict__ lo_all, uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_key, uint32_t* __restrict__ cand_idx) {
+    __shared__ uint2 buf[TK_FBUF];
+    __shared__ uint32_t wtot[2][TK_THREADS / 32];
+    __shared__ uint32_t slot0;
+    topk_pdl_enter();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t t_begin = (uint64_t)blockIdx.x * tiles_per_block;
+    uint64_t t_end = t_begin + tiles_per_block;
+    if (t_end > ntiles) t_end = ntiles;
+    if (t_begin >= t_end) return;
+    int s = topk_seg_of<0>(segs, nseg, t_begin);
+    TopkSeg sg = segs[s];
+    uint32_t lo = lo_all[s];
+    uint32_t w[TK_PER], valid = 0u;
+    if (sg.cap) valid = topk_load_tile(x + sg.begin, (t_begin - sg.tile0) * TK_TILE, sg.n, (((uintptr_t)(x + sg.begin)) & 15u) == 0, w);
+    uint32_t fill = 0u;                                                 // (block-uniform) entries of layer s waiting in buf
+    // claims `count` slots of layer s; returns the first one, or 0xffffffff when the region cannot hold them
+    auto claim = [&](uint32_t count) -> uint32_t {
+        __syncthreads();                                                // buf complete / slot0 free
+        if (threadIdx.x == 0) slot0 = atomicAdd(&cand_count[s], count);
+        __syncthreads();
+        const uint32_t first = slot0;
+        return first + count <= sg.cap ? first : 0xffffffffu;
+    };
+    auto flush = [&]() {
+        if (fill == 0u) return;
+        const uint32_t first = claim(fill);
+        if (first != 0xffffffffu)
+            for (uint32_t j = threadIdx.x; j < fill; j += TK_THREADS) { const uint2 c = buf[j]; cand_key[sg.cbegin + first + j] = c.x; cand_idx[sg.cbegin + first + j] = c.y; }
+        __syncthreads();                                                // buf may be refilled
+        fill = 0u;
+    };
+    for (uint64_t tile = t_begin; tile < t_end; ++tile) {
+        // the next tile's layer and loads
+        int s2 = s;
+        TopkSeg sg2 = sg;
+        uint32_t lo2 = lo, w2[TK_PER], valid2 = 0u;
+        if (tile + 1 < t_end) {
+            bool moved = false;
+            while (s2 + 1 < nseg && segs[s2 + 1].tile0 <= tile + 1) { ++s2; moved = true; }
+            if (moved) { sg2 = segs[s2]; lo2 = lo_all[s2]; }
+            if (sg2.cap) valid2 = topk_load_tile(x + sg2.begin, (tile + 1 - sg2.tile0) * TK_TILE, sg2.n, (((uintptr_t)(x + sg2.begin)) & 15u) == 0, w2);
+        }
+        if (sg.cap) {                                                   // (block-uniform)
+            const uint32_t base = (uint32_t)((tile - sg.tile0) * TK_TILE);
+            const float lo_f = __uint_as_float(lo);
+            uint32_t sel = 0u;
+#pragma unroll
+            for (int k = 0; k < TK_PER; ++k) sel |= (uint32_t)(!(fabsf(__uint_as_float(w[k])) < lo_f)) << k;   // key >= lo, NaN included (its key is above inf)
+            sel &= valid;
+            const uint32_t cnt = __popc(sel);
+            uint32_t incl = cnt;
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+            const uint32_t pb = (uint32_t)tile & 1u;                    // alternating shared slots: one barrier per tile
+            if (lane == 31) wtot[pb][warp] = incl;
+            __syncthreads();
+            uint32_t before = incl - cnt, total = 0u;
+#pragma unroll
+            for (uint32_t v = 0; v < TK_THREADS / 32; ++v) { const uint32_t c = wtot[pb][v]; if (v < warp) before += c; total += c; }
+            if (fill + total > TK_FBUF) flush();
+            if (total > TK_FBUF) {                                      // a tile denser than the buffer (bound too low): straight to the region
+                const uint32_t first = claim(total);
+                if (first != 0xffffffffu) {
+                    uint32_t m = sel, j = first + before;
+                    while (m) {
+                        const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+                        m &= m - 1u;
+                        cand_key[sg.cbegin + j] = key_of_bits(topk_pick16(w, k));
+                        cand_idx[sg.cbegin + j] = base + topk_elem_of(k);
+                        ++j;
+                    }
+                }
+            } else {
+                uint32_t m = sel, j = fill + before;
+                while (m) {
+                    const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+                    m &= m - 1u;
+                    buf[j] = make_uint2(key_of_bits(topk_pick16(w, k)), base + topk_elem_of(k));
+                    ++j;
+                }
+                fill += total;
+            }
+        }
+        if (s2 != s) flush();                                           // the buffer holds one layer's candidates
+        s = s2; sg = sg2; lo = lo2; valid = valid2;
+#pragma unroll
+        for (int k = 0; k < TK_PER; ++k) w[k] = w2[k];
+    }
+    flush();
+}
+
+// pass 0: shift 20 / 11 bits; pass 1: shift 9 / 11 bits; pass 2: shift 0 / 9 bits.
+// A block owns a contiguous run of tiles; its shared histogram is merged into the layer's global one
+// whenever the run crosses into the next layer (and at the end).  CAND: the tiles are those of the candidate
+// regions and `x` is the candidate key array; otherwise the tiles of x itself (exact-route layers only).
+template <bool CAND>
+__global__ void __launch_bounds__(TK_THREADS)
+k_topk_hist(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles, uint64_t tiles_per_block,
+            const TopkState* __restrict__ st, const uint32_t* __restrict__ cand_count, uint32_t shift, uint32_t nbits, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[TK_BINS];
+    const uint64_t t_begin = (uint64_t)blockIdx.x * tiles_per_block;
+    uint64_t t_end = t_begin + tiles_per_block;
+    if (t_end > ntiles) t_end = ntiles;
+    topk_pdl_enter();
+    if (t_begin >= t_end) return;
+    for (uint32_t i = threadIdx.x; i < TK_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint32_t hi_shift = shift + nbits;               // bits above the digit must equal the prefix
+    const uint32_t dmask = (1u << nbits) - 1u;
+    int s = topk_seg_of<CAND ? 1 : 0>(segs, nseg, t_begin);
+    bool dirty = false;                                    // (block-uniform) the shared histogram holds counts of layer s
+    for (uint64_t tile = t_begin; tile < t_end; ++tile) {
+        while (s + 1 < nseg && topk_first<CAND ? 1 : 0>(segs[s + 1]) <= tile) {   // the run enters the next layer
+            if (dirty) {
+                __syncthreads();
+                for (uint32_t i = threadIdx.x; i < TK_BINS; i += blockDim.x) {
+                    const uint32_t c = sh[i];
+                    if (c) { atomicAdd(&hist[(size_t)s * TK_BINS + i], c); sh[i] = 0; }
+                }
+                __syncthreads();
+                dirty = false;
+            }
+            ++s;
+        }
+        const TopkView vw = topk_view<CAND>(segs[s], cand_count, s);
+        const uint64_t base = (tile - vw.tile0) * TK_TILE;
+        if (base >= vw.n) {                                // other route, or past the candidates that exist:
+            if (s + 1 >= nseg) break;                      // on to the next layer's first tile
+            const uint64_t nxt = topk_first<CAND ? 1 : 0>(segs[s + 1]);
+            tile = (nxt > tile ? nxt : tile + 1) - 1;
+            continue;
+        }
+        dirty = true;
+        const uint32_t prefix = st[s].prefix;
+        const uint32_t* xs = x + vw.begin;
+        uint32_t w[TK_PER];
+        const uint32_t valid = topk_load_tile(xs, base, vw.n, (((uintptr_t)xs) & 15u) == 0, w);   // element order does not matter here
+#pragma unroll
+        for (int k = 0; k < TK_PER; ++k) {
+            const uint32_t key = key_of_bits(w[k]);
+            if (((valid >> k) & 1u) && (hi_shift >= 31u || (key >> hi_shift) == (prefix >> hi_shift))) atomicAdd(&sh[(key >> shift) & dmask], 1u);
+        }
+    }
+    if (!dirty) return;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < TK_BINS; i += blockDim.x) {
+        const uint32_t c = sh[i];
+        if (c) atomicAdd(&hist[(size_t)s * TK_BINS + i], c);
+    }
+}
+
+// exact route: per-tile counts of (key > T, key == T) read from x; a block owns a contiguous run of tiles and
+// jumps over the layers of the candidate route
+__global__ void __launch_bounds__(TK_THREADS)
+k_topk_count(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles, uint64_t tiles_per_block,
+             const TopkState* __restrict__ st, const uint32_t* __restrict__ cand_count, uint2* __restrict__ tile_counts) {
+    __shared__ uint32_t sg_[TK_THREADS / 32], se_[TK_THREADS / 32];
+    topk_pdl_enter();
+    const uint64_t t_begin = (uint64_t)blockIdx.x * tiles_per_block;
+    uint64_t t_end = t_begin + tiles_per_block;
+    if (t_end > ntiles) t_end = ntiles;
+    if (t_begin >= t_end) return;
+    int s = topk_seg_of<0>(segs, nseg, t_begin);
+    for (uint64_t tile = t_begin; tile < t_end; ++tile) {
+        while (s + 1 < nseg && segs[s + 1].tile0 <= tile) ++s;
+        const TopkView vw = topk_view<false>(segs[s], cand_count, s);
+        if (vw.n == 0u) {                                   // candidate route: k_topk_cand_count fills these tiles
+            if (s + 1 >= nseg) break;
+            const uint64_t nxt = segs[s + 1].tile0;
+            tile = (nxt > tile ? nxt : tile + 1) - 1;
+            continue;
+        }
+        const uint32_t T = st[s].prefix;
+        const uint64_t base = (tile - vw.tile0) * TK_TILE;
+        const uint32_t* xs = x + vw.begin;
+        uint32_t w[TK_PER];
+        const uint32_t valid = topk_load_tile(xs, base, vw.n, (((uintptr_t)xs) & 15u) == 0, w);   // counts do not need index order
+        uint32_t g = 0, e = 0;
+#pragma unroll
+        for (int k = 0; k < TK_PER; ++k) {
+            const uint32_t key = key_of_bits(w[k]), ok = (valid >> k) & 1u;
+            g += ok & (uint32_t)(key > T); e += ok & (uint32_t)(key == T);
         }
         for (int d = 16; d > 0; d >>= 1) { g += __shfl_down_sync(0xffffffffu, g, d); e += __shfl_down_sync(0xffffffffu, e, d); }
         if ((threadIdx.x & 31u) == 0) { sg_[threadIdx.x >> 5] = g; se_[threadIdx.x >> 5] = e; }
         __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t G = 0, E = 0;
-            for (int w = 0; w < TK_THREADS / 32; ++w) { G += sg_[w]; E += se_[w]; }
+            for (int v = 0; v < TK_THREADS / 32; ++v) { G += sg_[v]; E += se_[v]; }
             tile_counts[tile] = make_uint2(G, E);
         }
         __syncthreads();
     }
 }
 
-// exclusive scan of each layer's tile counts in place (one block per layer)
+// candidate route: the same per-tile counts from the candidate list (every element at or above the threshold is
+// a candidate); tile_counts starts zeroed
+__global__ void __launch_bounds__(TK_THREADS)
+k_topk_cand_count(const uint32_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_idx, const TopkSeg* __restrict__ segs, int nseg,
+                  uint64_t nctiles, const TopkState* __restrict__ st, const uint32_t* __restrict__ cand_count, uint2* __restrict__ tile_counts) {
+    topk_pdl_enter();
+    for (uint64_t tile = blockIdx.x; tile < nctiles; tile += gridDim.x) {
+        const int s = topk_seg_of<1>(segs, nseg, tile);
+        const TopkSeg sg = segs[s];
+        const TopkView vw = topk_view<true>(sg, cand_count, s);
+        const uint64_t base = (tile - vw.tile0) * TK_TILE;
+        if (base >= vw.n) continue;
+        const uint32_t T = st[s].prefix;
+        for (uint32_t r = threadIdx.x; r < TK_TILE; r += TK_THREADS) {
+            const uint64_t i = base + r;
+            if (i >= vw.n) break;
+            const uint32_t key = cand_key[vw.begin + i];
+            if (key >= T) {
+                uint32_t* tc = reinterpret_cast<uint32_t*>(&tile_counts[sg.tile0 + cand_idx[vw.begin + i] / TK_TILE]);
+                atomicAdd(tc + (key == T ? 1 : 0), 1u);
+            }
+        }
+    }
+}
+
+// exclusive scan of each layer's tile counts in place (one block per layer, four tiles per thread and step)
 __global__ void __launch_bounds__(1024)
 k_topk_scan(uint2* __restrict__ tile_counts_all, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles_all) {
     __shared__ uint32_t wg[32], we[32];
     __shared__ uint32_t carry_g, carry_e;
+    topk_pdl_enter();
     const int s = blockIdx.x;
     const uint64_t t0 = segs[s].tile0, t1 = s + 1 < nseg ? segs[s + 1].tile0 : ntiles_all;
     uint2* tile_counts = tile_counts_all + t0;
@@ -627,10 +875,13 @@ k_topk_scan(uint2* __restrict__ tile_counts_all, const TopkSeg* __restrict__ seg
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     if (t == 0) { carry_g = 0; carry_e = 0; }
     __syncthreads();
-    for (uint64_t base = 0; base < ntiles; base += 1024) {
-        const uint64_t i = base + t;
-        const uint2 c = i < ntiles ? tile_counts[i] : make_uint2(0, 0);
-        uint32_t g = c.x, e = c.y;
+    for (uint64_t base = 0; base < ntiles; base += 4096) {
+        const uint64_t i0 = base + 4ull * t;
+        uint2 c[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = i0 + k < ntiles ? tile_counts[i0 + k] : make_uint2(0, 0);
+        const uint32_t own_g = c[0].x + c[1].x + c[2].x + c[3].x, own_e = c[0].y + c[1].y + c[2].y + c[3].y;
+        uint32_t g = own_g, e = own_e;
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t og = __shfl_up_sync(0xffffffffu, g, d), oe = __shfl_up_sync(0xffffffffu, e, d);
             if (lane >= (uint32_t)d) { g += og; e += oe; }
@@ -646,82 +897,159 @@ k_topk_scan(uint2* __restrict__ tile_counts_all, const TopkSeg* __restrict__ seg
             wg[lane] = a; we[lane] = b;
         }
         __syncthreads();
-        const uint32_t pg = carry_g + (warp ? wg[warp - 1] : 0u) + g - c.x;
-        const uint32_t pe = carry_e + (warp ? we[warp - 1] : 0u) + e - c.y;
-        if (i < ntiles) tile_counts[i] = make_uint2(pg, pe);
+        uint32_t pg = carry_g + (warp ? wg[warp - 1] : 0u) + g - own_g;
+        uint32_t pe = carry_e + (warp ? we[warp - 1] : 0u) + e - own_e;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < ntiles) tile_counts[i0 + k] = make_uint2(pg, pe);
+            pg += c[k].x; pe += c[k].y;
+        }
         __syncthreads();
-        if (t == 1023) { carry_g = pg + c.x; carry_e = pe + c.y; }
+        if (t == 1023) { carry_g = pg; carry_e = pe; }
         __syncthreads();
     }
 }
 
-// Ordered write.  Thread t of a tile owns the TK_PER consecutive elements [t*TK_PER, (t+1)*TK_PER) so
-// that positions follow the index order.  An element is selected when key > T, or key == T and at least
-// c_eq - k_rem tied elements precede it.  Output slot = (#selected before it in its layer) + out_off.
+// Ordered write.  A tile is four rows of 256 16-byte quads (topk_load_tile's layout: every access of a warp
+// covers 512 contiguous bytes of x, the residual and the new residual); the index order inside the tile is
+// row-major, so a thread's output slots follow from a block scan of its per-row counts, packed 16 bits per row
+// into one 64-bit word each for (key > T) and (key == T).  An element is selected when key > T, or key == T and
+// at least c_eq - k_rem tied elements precede it.  Output slot = (#selected before it in its layer) + out_off.
+// Every row leaves as x + residual in one 16-byte store; the ~1 % of elements at or above the threshold are then
+// visited through the set bits of the thread's hit mask (compact output, zero into the new residual: a later store
+// of the same thread to the same address).  A block owns a contiguous run of tiles; the loads of the next tile are
+// in flight while the current one is scanned and written.
+struct TopkTile { uint32_t w[TK_PER]; float rv[TK_PER]; uint32_t valid; bool vec; };
+__device__ __forceinline__ void topk_write_load(TopkTile& t, const uint32_t* __restrict__ x, const float* __restrict__ res_in, const float* res_out,
+                                                const TopkSeg& sg, uint64_t tile) {
+    const uint32_t* xs = x + sg.begin;
+    const uint64_t base = (tile - sg.tile0) * TK_TILE;
+    t.vec = ((((uintptr_t)xs) | (res_in ? (uintptr_t)(res_in + sg.begin) : 0) | (res_out ? (uintptr_t)(res_out + sg.begin) : 0)) & 15u) == 0;
+    t.valid = topk_load_tile(xs, base, sg.n, t.vec, t.w);
+    if (res_in) {
+#pragma unroll
+        for (int r = 0; r < TK_PER / 4; ++r) {
+            const uint64_t i = base + 4ull * ((uint64_t)r * TK_THREADS + threadIdx.x);
+            const float* rp = res_in + sg.begin + i;
+            if (t.vec && i + 4 <= sg.n) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(rp));
+                t.rv[4 * r] = v.x; t.rv[4 * r + 1] = v.y; t.rv[4 * r + 2] = v.z; t.rv[4 * r + 3] = v.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t.rv[4 * r + k] = i + k < sg.n ? rp[k] : 0.0f;
+            }
+        }
+    }
+}
 __global__ void __launch_bounds__(TK_THREADS)
-k_topk_write(const float* __restrict__ x, const float* __restrict__ res_in, const TopkSeg* __restrict__ segs, int nseg,
-             uint64_t ntiles, const TopkState* __restrict__ st_all, const uint2* __restrict__ tile_prefix,
-             float* __restrict__ values_all, int64_t* __restrict__ index_all, float* __restrict__ res_out) {
-    __shared__ uint32_t wg[TK_THREADS / 32], we[TK_THREADS / 32];
+k_topk_write(const uint32_t* __restrict__ x, const float* __restrict__ res_in, const TopkSeg* __restrict__ segs, int nseg,
+             uint64_t ntiles, uint64_t tiles_per_block, const TopkState* __restrict__ st_all, const uint2* __restrict__ tile_prefix,
+             float* __restrict__ values_all, int64_t* __restrict__ index_all, float* res_out) {
+    __shared__ uint64_t wg[2][TK_THREADS / 32], we[2][TK_THREADS / 32];
+    topk_pdl_enter();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int s = topk_seg_of_tile(segs, nseg, tile);
-        const TopkSeg sgm = segs[s];
+    const uint64_t t_begin = (uint64_t)blockIdx.x * tiles_per_block;
+    uint64_t t_end = t_begin + tiles_per_block;
+    if (t_end > ntiles) t_end = ntiles;
+    if (t_begin >= t_end) return;
+    int s = topk_seg_of<0>(segs, nseg, t_begin);
+    TopkSeg sgm = segs[s];
+    TopkTile cur;
+    topk_write_load(cur, x, res_in, res_out, sgm, t_begin);
+    for (uint64_t tile = t_begin; tile < t_end; ++tile) {
+        int s2 = s;
+        TopkSeg sg2 = sgm;
+        TopkTile nxt;
+        if (tile + 1 < t_end) {
+            bool moved = false;
+            while (s2 + 1 < nseg && segs[s2 + 1].tile0 <= tile + 1) { ++s2; moved = true; }
+            if (moved) sg2 = segs[s2];
+            topk_write_load(nxt, x, res_in, res_out, sg2, tile + 1);
+        }
         const TopkState st = st_all[s];
         const uint32_t T = st.prefix, skip_eq = st.c_eq - st.k_rem;   // ties with rank < skip_eq are not taken
-        const uint64_t n = sgm.n;
-        const float* xs = x + sgm.begin;
-        float* values = values_all + sgm.out_off;
-        int64_t* index = index_all + sgm.out_off;
-        const uint64_t i0 = (tile - sgm.tile0) * TK_TILE + (uint64_t)threadIdx.x * TK_PER;
-        float xv[TK_PER];
-        uint32_t g = 0, e = 0;
-        if (i0 + TK_PER <= n && ((reinterpret_cast<uintptr_t>(xs + i0) & 15u) == 0)) {
+        const uint32_t n = sgm.n;
+        const uint32_t base = (uint32_t)((tile - sgm.tile0) * TK_TILE);
+        float f[TK_PER];
+        uint32_t gm = 0u, em = 0u;                              // hit masks: key > T, key == T
 #pragma unroll
-            for (int r = 0; r < TK_PER; r += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(xs + i0 + r);
-                xv[r] = v.x; xv[r + 1] = v.y; xv[r + 2] = v.z; xv[r + 3] = v.w;
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < TK_PER; ++r) xv[r] = (i0 + r < n) ? xs[i0 + r] : 0.0f;
+        for (int k = 0; k < TK_PER; ++k) {
+            const uint32_t key = key_of_bits(cur.w[k]);
+            gm |= (uint32_t)(key > T) << k; em |= (uint32_t)(key == T) << k;
+            f[k] = res_in ? __fadd_rn(__uint_as_float(cur.w[k]), cur.rv[k]) : __uint_as_float(cur.w[k]);
         }
+        gm &= cur.valid; em &= cur.valid;
+        uint64_t G = 0ull, E = 0ull;
 #pragma unroll
-        for (int r = 0; r < TK_PER; ++r)
-            if (i0 + r < n) { const uint32_t key = key_of(xv[r]); g += key > T; e += key == T; }
-        // block-exclusive scan of (g, e) in thread order
-        uint32_t sg = g, se = e;
+        for (int r = 0; r < TK_PER / 4; ++r) {
+            G |= (uint64_t)__popc(gm & (0xfu << (4 * r))) << (16 * r);
+            E |= (uint64_t)__popc(em & (0xfu << (4 * r))) << (16 * r);
+        }
+        // block scan of the packed counts in thread order (a row holds at most 1024 elements: 16 bits suffice)
+        uint64_t sg = G, se = E;
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t og = __shfl_up_sync(0xffffffffu, sg, d), oe = __shfl_up_sync(0xffffffffu, se, d);
+            const uint64_t og = __shfl_up_sync(0xffffffffu, sg, d), oe = __shfl_up_sync(0xffffffffu, se, d);
             if (lane >= (uint32_t)d) { sg += og; se += oe; }
         }
-        if (lane == 31) { wg[warp] = sg; we[warp] = se; }
-        __syncthreads();
-        uint32_t bg = 0, be = 0;
-        for (uint32_t w = 0; w < warp; ++w) { bg += wg[w]; be += we[w]; }
-        const uint2 tp = tile_prefix[tile];
-        uint32_t gt_before = tp.x + bg + sg - g;      // key > T before this thread's first element
-        uint32_t eq_before = tp.y + be + se - e;      // key == T before it
+        const uint32_t pb = (uint32_t)tile & 1u;                // alternating slots: one barrier per tile
+        if (lane == 31) { wg[pb][warp] = sg; we[pb][warp] = se; }
+        // the rows of the new residual (selected positions are zeroed below)
+        if (res_out) {
 #pragma unroll
-        for (int r = 0; r < TK_PER; ++r) {
-            const uint64_t i = i0 + r;
-            if (i < n) {
-                const uint32_t key = key_of(xv[r]);
-                const bool is_eq = key == T;
-                const bool sel = key > T || (is_eq && eq_before >= skip_eq);
-                const float f = res_in ? __fadd_rn(xv[r], res_in[sgm.begin + i]) : xv[r];
-                if (sel) {
-                    const uint32_t taken_eq = eq_before > skip_eq ? eq_before - skip_eq : 0u;   // selected ties before i
-                    const uint64_t pos = (uint64_t)gt_before + taken_eq;
-                    values[pos] = f;
-                    index[pos] = (int64_t)(sgm.begin + i);
-                }
-                if (res_out) res_out[sgm.begin + i] = sel ? 0.0f : f;
-                gt_before += key > T; eq_before += is_eq;
+            for (int r = 0; r < TK_PER / 4; ++r) {
+                const uint32_t i0 = base + 4u * ((uint32_t)r * TK_THREADS + threadIdx.x);
+                float* op = res_out + sgm.begin + i0;
+                if (cur.vec && i0 + 4u <= n) __stcs(reinterpret_cast<float4*>(op), make_float4(f[4 * r], f[4 * r + 1], f[4 * r + 2], f[4 * r + 3]));
+                else for (int k = 0; k < 4; ++k) if (i0 + k < n) op[k] = f[4 * r + k];
             }
         }
         __syncthreads();
+        uint32_t hits = gm | em;
+        if (hits) {
+            uint64_t bg = 0ull, be = 0ull, tg = 0ull, te = 0ull;    // threads before this warp; the whole tile
+#pragma unroll
+            for (uint32_t v = 0; v < TK_THREADS / 32; ++v) { const uint64_t a = wg[pb][v], b = we[pb][v]; if (v < warp) { bg += a; be += b; } tg += a; te += b; }
+            // per row: hits before this thread's quad = rows before (totals) + threads before in the row; rows packed 16 bits each
+            const uint64_t rows_g = (tg << 16) + (tg << 32) + (tg << 48), rows_e = (te << 16) + (te << 32) + (te << 48);   // exclusive prefix over rows
+            const uint64_t xg = bg + sg - G + rows_g, xe = be + se - E + rows_e;
+            const uint2 tp = tile_prefix[tile];
+            float* values = values_all + sgm.out_off;
+            int64_t* index = index_all + sgm.out_off;
+            while (hits) {
+                const uint32_t k = (uint32_t)__ffs((int)hits) - 1u;
+                hits &= hits - 1u;
+                const uint32_t r = k >> 2, below = (1u << k) - 1u, rowm = 0xfu << (4u * r);
+                const uint32_t gt_before = tp.x + (uint32_t)((xg >> (16u * r)) & 0xffffu) + __popc(gm & rowm & below);
+                const uint32_t eq_before = tp.y + (uint32_t)((xe >> (16u * r)) & 0xffffu) + __popc(em & rowm & below);
+                const bool is_gt = (gm >> k) & 1u;
+                if (is_gt || eq_before >= skip_eq) {
+                    const uint32_t taken_eq = eq_before > skip_eq ? eq_before - skip_eq : 0u;   // selected ties before it
+                    const uint64_t pos = (uint64_t)gt_before + taken_eq;
+                    const uint64_t gi = sgm.begin + base + topk_elem_of(k);
+                    values[pos] = topk_pick16(f, k);
+                    index[pos] = (int64_t)gi;
+                    if (res_out) res_out[gi] = 0.0f;
+                }
+            }
+        }
+        s = s2; sgm = sg2;
+        cur = nxt;
     }
+}
+
+// Launch with programmatic stream serialization (the kernels call topk_pdl_enter first): the launch latency of the
+// ~20 small kernels of the chain overlaps the tail of their predecessors.  FLASHE_PDL=0 turns it off.
+template <typename... KArgs, typename... Args>
+static cudaError_t topk_launch(void (*kern)(KArgs...), int grid, int block, cudaStream_t cs, Args... args) {
+    static const bool pdl = [] { const char* e = getenv("FLASHE_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.stream = cs;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // =================================================================================================
@@ -837,7 +1165,12 @@ int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_
     }
     if (total == 0) return FLASHE_OK;
     if (!x || !values_out || !index_out) return flashe_fail(FLASHE_EINVAL, "NULL buffer");
-    // Layers are processed in groups of at most TK_GROUP by the same nine launches (the per-layer
+    // FLASHE_TOPK_ROUTE (tests): "exact" = no layer samples; "badbound" = the sample rank is forced to 1, so the bound
+    // lands above the threshold and the device has to fall back to the exact route.
+    const char* route_env = getenv("FLASHE_TOPK_ROUTE");
+    const bool force_exact = route_env && strcmp(route_env, "exact") == 0;
+    const bool bad_bound = route_env && strcmp(route_env, "badbound") == 0;
+    // Layers are processed in groups of at most TK_GROUP by the same launches (the per-layer
     // histograms of a group are 8 KB each).  Empty layers are dropped from the table.
     const int TK_GROUP = 4096;
     std::vector<TopkSeg> segs;
@@ -847,13 +1180,38 @@ int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_
     int launches = 0;
     uint64_t begin = 0, out_off = 0;
     int s = 0;
+    const uint32_t* xw = reinterpret_cast<const uint32_t*>(x);
     while (e == cudaSuccess && s < nseg) {
         segs.clear();
-        uint64_t ntiles = 0;
+        uint64_t ntiles = 0, nctiles = 0, nlines = 0;
         for (; s < nseg && (int)segs.size() < TK_GROUP; ++s) {
             const uint64_t n = seg_end[s] - begin;
             if (n) {
-                TopkSeg g; g.begin = begin; g.tile0 = ntiles; g.out_off = out_off; g.n = (uint32_t)n; g.k = (uint32_t)k[s];
+                TopkSeg g;
+                memset(&g, 0, sizeof(g));
+                g.begin = begin; g.tile0 = ntiles; g.out_off = out_off; g.n = (uint32_t)n; g.k = (uint32_t)k[s];
+                g.cbegin = nctiles * TK_TILE; g.ctile0 = nctiles; g.samp0 = nlines;
+                // candidate route: sparse selections of layers large enough to sample
+                if (!force_exact && n >= 4096 && k[s] * 40 <= n) {
+                    uint32_t lines, stride, rank;
+                    if (n <= TK_SAMPLE_ALL) { lines = (uint32_t)((n + 31) / 32); stride = 1; rank = (uint32_t)k[s]; }
+                    else {
+                        const uint64_t lines_total = n / 32;
+                        uint64_t want = lines_total / 64;
+                        want = want < 128 ? 128 : (want > 512 ? 512 : want);
+                        lines = (uint32_t)want; stride = (uint32_t)(lines_total / want);
+                        const double sp = 32.0 * (double)lines * (double)k[s] / (double)n;     // expected sample elements above the threshold
+                        rank = (uint32_t)(1.5 * sp + 6.0 * sqrt(sp) + 8.0) + 1u;
+                        if (bad_bound) rank = 1u;
+                        if (rank >= 32u * lines) lines = 0;
+                    }
+                    if (lines) {
+                        g.cap = (uint32_t)(((n / 8) + 3) & ~3ull);
+                        g.samp_lines = lines; g.samp_stride = stride; g.samp_rank = rank;
+                        nctiles += ceil_div_u64(g.cap, TK_TILE);
+                        nlines += lines;
+                    }
+                }
                 segs.push_back(g);
                 ntiles += ceil_div_u64(n, TK_TILE);
             }
@@ -862,34 +1220,54 @@ int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_
         }
         const int ng = (int)segs.size();
         if (ng == 0) continue;
-        // workspace: layer table | states | histograms | tile counts
+        // workspace: layer table | states | [histograms | candidate counts | bounds | tile counts] (zeroed) | candidate keys | candidate indices
         const size_t seg_bytes = (sizeof(TopkSeg) * (size_t)ng + 255) & ~(size_t)255;
         const size_t st_bytes = (sizeof(TopkState) * (size_t)ng + 255) & ~(size_t)255;
         const size_t hist_bytes = sizeof(uint32_t) * TK_BINS * (size_t)ng;
-        e = cudaMallocAsync((void**)&ws, seg_bytes + st_bytes + hist_bytes + sizeof(uint2) * (size_t)ntiles, cs);
+        const size_t cnt_bytes = (sizeof(uint32_t) * (size_t)ng + 255) & ~(size_t)255;
+        const size_t tile_bytes = (sizeof(uint2) * (size_t)ntiles + 255) & ~(size_t)255;
+        const size_t zero_bytes = hist_bytes + 2 * cnt_bytes + tile_bytes;
+        const size_t cand_bytes = sizeof(uint32_t) * (size_t)nctiles * TK_TILE;
+        e = cudaMallocAsync((void**)&ws, seg_bytes + st_bytes + zero_bytes + 2 * cand_bytes, cs);
         if (e != cudaSuccess) break;
         TopkSeg* dseg = reinterpret_cast<TopkSeg*>(ws);
         TopkState* st = reinterpret_cast<TopkState*>(ws + seg_bytes);
-        uint32_t* hist = reinterpret_cast<uint32_t*>(ws + seg_bytes + st_bytes);
-        uint2* tiles = reinterpret_cast<uint2*>(ws + seg_bytes + st_bytes + hist_bytes);
+        uint8_t* zero0 = ws + seg_bytes + st_bytes;
+        uint32_t* hist = reinterpret_cast<uint32_t*>(zero0);
+        uint32_t* cand_count = reinterpret_cast<uint32_t*>(zero0 + hist_bytes);
+        uint32_t* lo = reinterpret_cast<uint32_t*>(zero0 + hist_bytes + cnt_bytes);
+        uint2* tiles = reinterpret_cast<uint2*>(zero0 + hist_bytes + 2 * cnt_bytes);
+        uint32_t* cand_key = reinterpret_cast<uint32_t*>(zero0 + zero_bytes);
+        uint32_t* cand_idx = reinterpret_cast<uint32_t*>(zero0 + zero_bytes + cand_bytes);
         e = cudaMemcpyAsync(dseg, segs.data(), sizeof(TopkSeg) * (size_t)ng, cudaMemcpyHostToDevice, cs);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(cs);          // segs (pageable) is reused by the next group
-        if (e == cudaSuccess) e = cudaMemsetAsync(hist, 0, hist_bytes, cs);
-        if (e == cudaSuccess) {
-            k_topk_init<<<(ng + 255) / 256, 256, 0, cs>>>(dseg, ng, st);
-            const int gh = grid_cap(info.num_sms, ntiles, 8);
-            const uint64_t tpb = ceil_div_u64(ntiles, (uint64_t)gh);
-            const uint32_t shifts[3] = {20u, 9u, 0u}, nbits[3] = {11u, 11u, 9u};
-            for (int p = 0; p < 3; ++p) {
-                k_topk_hist<<<gh, TK_THREADS, 0, cs>>>(x, dseg, ng, ntiles, tpb, st, shifts[p], nbits[p], hist);
-                k_topk_pick<<<ng, 1024, 0, cs>>>(hist, st, shifts[p]);
-            }
-            k_topk_count<<<gh, TK_THREADS, 0, cs>>>(x, dseg, ng, ntiles, st, tiles);
-            k_topk_scan<<<ng, 1024, 0, cs>>>(tiles, dseg, ng, ntiles);
-            k_topk_write<<<gh, TK_THREADS, 0, cs>>>(x, residual_in, dseg, ng, ntiles, st, tiles, values_out, index_out, residual_out);
-            launches += 10;
-            e = cudaGetLastError();
+        // (a pageable source has been staged by the time cudaMemcpyAsync returns: `segs` may be refilled)
+        if (e == cudaSuccess) e = cudaMemsetAsync(zero0, 0, zero_bytes, cs);
+        const int gh = grid_cap(info.num_sms, ntiles, 8);
+        const uint64_t tpb = ceil_div_u64(ntiles, (uint64_t)gh);
+        const int gc = grid_cap(info.num_sms, nctiles, 8);
+        const uint64_t ctpb = nctiles ? ceil_div_u64(nctiles, (uint64_t)gc) : 0;
+        uint32_t* null_lo = nullptr;
+#define TK_GO(call) do { if (e == cudaSuccess) { e = (call); ++launches; } } while (0)
+        TK_GO(topk_launch(k_topk_init, (ng + 255) / 256, 256, cs, dseg, ng, st));
+        if (nctiles) {
+            TK_GO(topk_launch(k_topk_sample, grid_cap(info.num_sms, ceil_div_u64(nlines, 8), 8), 256, cs, xw, dseg, ng, nlines, hist));
+            TK_GO(topk_launch(k_topk_pick, ng, 1024, cs, hist, st, 0u, dseg, lo));
+            const int gf = grid_occ(info.num_sms, info.device, (const void*)k_topk_filter, ntiles * TK_THREADS, TK_THREADS);   // exactly the resident CTAs: equal runs, one wave
+            TK_GO(topk_launch(k_topk_filter, gf, TK_THREADS, cs, xw, dseg, ng, ntiles, ceil_div_u64(ntiles, (uint64_t)gf), lo, cand_count, cand_key, cand_idx));
         }
+        const uint32_t shifts[3] = {20u, 9u, 0u}, nbits[3] = {11u, 11u, 9u};
+        for (int p = 0; p < 3; ++p) {
+            if (nctiles) TK_GO(topk_launch(k_topk_hist<true>, gc, TK_THREADS, cs, cand_key, dseg, ng, nctiles, ctpb, st, cand_count, shifts[p], nbits[p], hist));
+            TK_GO(topk_launch(k_topk_hist<false>, gh, TK_THREADS, cs, xw, dseg, ng, ntiles, tpb, st, cand_count, shifts[p], nbits[p], hist));
+            TK_GO(topk_launch(k_topk_pick, ng, 1024, cs, hist, st, shifts[p], dseg, null_lo));
+        }
+        TK_GO(topk_launch(k_topk_count, gh, TK_THREADS, cs, xw, dseg, ng, ntiles, tpb, st, cand_count, tiles));
+        if (nctiles) TK_GO(topk_launch(k_topk_cand_count, gc, TK_THREADS, cs, cand_key, cand_idx, dseg, ng, nctiles, st, cand_count, tiles));
+        TK_GO(topk_launch(k_topk_scan, ng, 1024, cs, tiles, dseg, ng, ntiles));
+        const int gw = grid_occ(info.num_sms, info.device, (const void*)k_topk_write, ntiles * TK_THREADS, TK_THREADS);
+        TK_GO(topk_launch(k_topk_write, gw, TK_THREADS, cs, xw, residual_in, dseg, ng, ntiles, ceil_div_u64(ntiles, (uint64_t)gw), st, tiles, values_out, index_out, residual_out));
+#undef TK_GO
+        if (e == cudaSuccess) e = cudaGetLastError();
         cudaFreeAsync(ws, cs);
         ws = nullptr;
     }

@@ -164,6 +164,34 @@ def test_sparsify_ties_zeros_and_specials(fb):
         assert np.array_equal(_np(rem).view(np.uint32), want_r[0].view(np.uint32)), k
 
 
+@pytest.mark.parametrize("route", ["exact", "badbound"])
+def test_sparsify_routes_agree(fb, route, monkeypatch):
+    # The threshold is found either from a sampled candidate list (default for sparse selections) or from x itself.
+    # FLASHE_TOPK_ROUTE=exact disables sampling on the host; =badbound forces a sample bound ABOVE the threshold, so
+    # the device must notice the short candidate list and take the exact route by itself.  All three must agree bit
+    # for bit with each other and with the reference's argsort order.
+    rs = np.random.RandomState(21)
+    ctx = fb.DeviceContext(KEY, 32)
+    sizes = [3_000_001, 20_000, 4096, 250_000, 7, 1_000_000]
+    ends = np.cumsum(sizes)
+    layers = [(rs.standard_normal(s) * rs.uniform(0.01, 3.0)).astype(np.float32) for s in sizes]
+    layers[3] = (layers[3] * 1e-3).astype(np.float32)
+    layers[3][::5] = 0.125                                 # a fifth of one layer tied at its maximum: the candidate list overflows
+    layers[5][:500_000] *= 40.0                            # structure a strided sample has to cope with
+    x = _dev(np.concatenate(layers))
+    res = _dev((rs.standard_normal(int(ends[-1])) * 0.01).astype(np.float32))
+    ks = [O.sparsify_k(0.01, s) for s in sizes]
+    want_v, want_r, want_loc, _ = O.sparsify(layers, list(np.split(_np(res), ends[:-1])), 0.01)
+    monkeypatch.delenv("FLASHE_TOPK_ROUTE", raising=False)
+    v0, i0, r0 = ctx.topk_sparsify(x, ends, ks, residual=res)
+    assert np.array_equal(_np(i0), want_loc)
+    assert np.array_equal(_np(v0).view(np.uint32), np.concatenate(want_v).view(np.uint32))
+    assert np.array_equal(_np(r0).view(np.uint32), np.concatenate(want_r).view(np.uint32))
+    monkeypatch.setenv("FLASHE_TOPK_ROUTE", route)
+    v1, i1, r1 = ctx.topk_sparsify(x, ends, ks, residual=res)
+    assert torch.equal(i0, i1) and torch.equal(v0.view(torch.int32), v1.view(torch.int32)) and torch.equal(r0.view(torch.int32), r1.view(torch.int32))
+
+
 def test_sparse_round_c4_shape_end_to_end(fb):
     # sparsify -> encode compact -> single-mask encrypt -> expand + zero fill -> sum -> sparse decrypt == sum of q
     total, n, b, n_jobs = 200000, 4, 32, 8

@@ -81,6 +81,10 @@ SIGNATURES = {
     "flashe_wire_unpack": (_int, [_vp, _vp, _u64, _int, _int, _vp, _vp]),
     "flashe_topk_sparsify": (_int, [_vp, _vp, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64), _int, _vp, _vp, _vp, _vp]),
     "flashe_segment_stats": (_int, [_vp, _vp, _vp, _u64, C.POINTER(_u64), C.POINTER(C.c_double), _int, _int, _vp, _vp]),
+    "flashe_peer_alloc": (_int, [_vp, _u64, C.POINTER(_vp), _u8p]),
+    "flashe_peer_open": (_int, [_vp, _u8p, C.POINTER(_vp)]),
+    "flashe_peer_close": (_int, [_vp, _vp]),
+    "flashe_peer_free": (_int, [_vp, _vp]),
     "flashe_launch_count": (_u64, []),
 }
 

@@ -251,6 +251,11 @@ __device__ __forceinline__ void ldg_v4(const void* p, uint32_t& a, uint32_t& b, 
 __device__ __forceinline__ void stg_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// four float64 as ONE 32-byte store (sm_100: STG.256).  A warp then writes 1 KB of whole sectors per instruction — what a
+// peer GPU's memory behind NVLink wants (two 16-byte stores per lane arrive there as half-filled sectors).
+__device__ __forceinline__ void stg_d4(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 __device__ __forceinline__ void stg_d2(double* p, double a, double b) {
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }

@@ -114,6 +114,7 @@ __global__ void k_decode(const typename Word<WORDS>::T* __restrict__ v, uint64_t
 __global__ void __launch_bounds__(256)
 k_decode_v4(const uint4* __restrict__ v, uint64_t begin, uint64_t nvec, const __grid_constant__ CodecDev cd, double* __restrict__ out) {
     const bool one_seg = cd.nseg == 1;
+    const bool out32 = (reinterpret_cast<uintptr_t>(out) & 31u) == 0u;     // 32-byte stores (one per four elements)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     // two independent 16-byte loads in flight per thread (the kernel is pure streaming: 4 B in, 8 B out per element)
     for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += 2 * stride) {
@@ -136,8 +137,8 @@ k_decode_v4(const uint4* __restrict__ v, uint64_t begin, uint64_t nvec, const __
                 if (k && !one_seg && j + k >= sg.end) sg = find_seg(cd, j + k);
                 d[k] = decode_one((double)p[k], sg.two_an, cd.den, cd.den_rcp, sg.an);
             }
-            stg_d2(out + 4ull * i, d[0], d[1]);
-            stg_d2(out + 4ull * i + 2, d[2], d[3]);
+            if (out32) stg_d4(out + 4ull * i, d[0], d[1], d[2], d[3]);
+            else { stg_d2(out + 4ull * i, d[0], d[1]); stg_d2(out + 4ull * i + 2, d[2], d[3]); }
         }
     }
 }

@@ -264,6 +264,55 @@ int flashe_ctx_destroy(flashe_ctx* ctx) {
     delete ctx;
     return FLASHE_OK;
 }
+// ---- peer buffers (cudaIpc): see the header ----------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == FLASHE_PEER_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+int flashe_peer_alloc(flashe_ctx* ctx, uint64_t bytes, void** ptr_out, uint8_t* handle_out) {
+    if (!ctx) return fail(FLASHE_EINVAL, "ctx is NULL");
+    if (!ptr_out || !handle_out || bytes == 0) return fail(FLASHE_EINVAL, "need bytes > 0, ptr_out and handle_out");
+    *ptr_out = nullptr;
+    FlasheDeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(FLASHE_ECUDA, "cudaSetDevice failed");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? FLASHE_ENOMEM : FLASHE_ECUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); cudaGetLastError(); return fail(FLASHE_ECUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    memcpy(handle_out, &h, sizeof(h));
+    *ptr_out = p;
+    return FLASHE_OK;
+}
+int flashe_peer_open(flashe_ctx* ctx, const uint8_t* handle, void** ptr_out) {
+    if (!ctx) return fail(FLASHE_EINVAL, "ctx is NULL");
+    if (!handle || !ptr_out) return fail(FLASHE_EINVAL, "need handle and ptr_out");
+    *ptr_out = nullptr;
+    FlasheDeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(FLASHE_ECUDA, "cudaSetDevice failed");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(FLASHE_ECUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+    *ptr_out = p;
+    return FLASHE_OK;
+}
+int flashe_peer_close(flashe_ctx* ctx, void* ptr) {
+    if (!ctx) return fail(FLASHE_EINVAL, "ctx is NULL");
+    if (!ptr) return FLASHE_OK;
+    FlasheDeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(FLASHE_ECUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+    return FLASHE_OK;
+}
+int flashe_peer_free(flashe_ctx* ctx, void* ptr) {
+    if (!ctx) return fail(FLASHE_EINVAL, "ctx is NULL");
+    if (!ptr) return FLASHE_OK;
+    FlasheDeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(FLASHE_ECUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaFree(ptr));
+    return FLASHE_OK;
+}
+
 int flashe_ctx_int_bits(const flashe_ctx* ctx) { return ctx ? ctx->int_bits : fail(FLASHE_EINVAL, "ctx is NULL"); }
 int flashe_ctx_device(const flashe_ctx* ctx) { return ctx ? ctx->device : fail(FLASHE_EINVAL, "ctx is NULL"); }
 

@@ -292,7 +292,9 @@ __device__ __forceinline__ void stg_quad(void* p, uint32_t r, uint32_t a, uint32
 }
 // four consecutive float64 outputs, first one `r` elements past a 32-byte boundary of the element grid
 __device__ __forceinline__ void stg_quad_f64(double* p, uint32_t r, const double (&v)[4]) {
-    if ((r & 1u) == 0u) {
+    if ((reinterpret_cast<uintptr_t>(p) & 31u) == 0u) {        // (warp-uniform) whole 32-byte sectors in one store
+        stg_d4(p, v[0], v[1], v[2], v[3]);
+    } else if ((r & 1u) == 0u) {
         stg_d2(p, v[0], v[1]);
         stg_d2(p + 2, v[2], v[3]);
     } else {

@@ -116,6 +116,18 @@ def _i32(xs):
     return (C.c_int32 * max(1, len(xs)))(*[int(x) for x in xs])
 
 
+class PeerSlice(object):
+    """A range of a peer buffer (memory of ANOTHER process's GPU, mapped by flashe_peer_open): accepted wherever an
+    `out=` float64 / word tensor is, so that a kernel stores its result straight into the owner's vector over
+    NVLink.  Only the address and the size are known here — torch never sees the memory."""
+
+    def __init__(self, address, nbytes):
+        self.address, self.nbytes = int(address), int(nbytes)
+
+    def data_ptr(self):
+        return self.address
+
+
 class DeviceContext(object):
     """One (key, int_bits, device) context = flashe_ctx."""
 
@@ -218,6 +230,10 @@ class DeviceContext(object):
         return t
 
     def _check(self, t, dtype, n, what):
+        if isinstance(t, PeerSlice):
+            if t.nbytes != n * torch.empty(0, dtype=dtype).element_size() or t.address % 16:
+                raise ValueError("%s: peer slice must hold %d elements of %s and be 16-byte aligned" % (what, n, dtype))
+            return t
         if t.device != self.device or t.dtype != dtype or not t.is_contiguous() or t.numel() != n:
             raise ValueError("%s must be a contiguous %s tensor of %d elements on %s" % (what, dtype, n, self.device))
         return t
@@ -374,6 +390,25 @@ class DeviceContext(object):
                                                    out.data_ptr(), p_out.data_ptr() if p_out is not None else None,
                                                    self._stream()))
         return out
+
+    # ------------------------------------------------------------------ peer buffers (multi-GPU gather, sharding.PeerGather)
+    def peer_alloc(self, nbytes):
+        """-> (address, 64-byte handle): device memory of this GPU that other processes can map (flashe_peer_alloc)."""
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        _cabi.check(self.lib.flashe_peer_alloc(self._h, int(nbytes), C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def peer_open(self, handle: bytes):
+        ptr = C.c_void_p()
+        _cabi.check(self.lib.flashe_peer_open(self._h, (C.c_uint8 * 64).from_buffer_copy(handle), C.byref(ptr)))
+        return ptr.value
+
+    def peer_close(self, address):
+        _cabi.check(self.lib.flashe_peer_close(self._h, C.c_void_p(address)))
+
+    def peer_free(self, address):
+        _cabi.check(self.lib.flashe_peer_free(self._h, C.c_void_p(address)))
 
     def rng_uniform(self, seed, stream, begin, count, out=None, resolution=53):
         out = torch.empty(count, dtype=torch.float64, device=self.device) if out is None else out

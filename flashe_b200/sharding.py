@@ -9,8 +9,10 @@ works on elements [begin_g, begin_g + count_g) of the whole vector and passes th
     each rank aggregates its shard with carry_in = 0 and emits a 4-word carry descriptor; one
     all-gather of those descriptors (16 bytes per rank) tells every rank its true carry-in, which a
     fix-up kernel ripples into the shard (in practice it touches one element);
-  * gathering the shards into one tensor (when a caller wants the whole aggregate on one GPU) is an
-    NCCL all-gather over NVLink, outside the per-element math.
+  * gathering the shards into one tensor (when a caller wants the whole result on one GPU): either an
+    NCCL all-gather afterwards (gather_shards), or no collective at all — PeerGather maps the owner's
+    vector into every rank (flashe_peer_open) and the decode kernel of each rank stores its shard
+    straight into it over NVLink, element by element as the PRF work proceeds.
 """
 from typing import List, Sequence, Tuple
 
@@ -86,3 +88,59 @@ def gather_shards(shard: torch.Tensor, counts: Sequence[int], group=None) -> tor
     dist.all_gather(parts, buf, group=group)
     whole = torch.cat([p[:c] for p, c in zip(parts, counts)])
     return whole.view(shard.dtype)
+
+
+class PeerGather(object):
+    """The whole decoded vector on ONE GPU without a gather step: rank `root` owns `total_len` float64 (device memory
+    exported with flashe_peer_alloc), every other rank maps it (flashe_peer_open) and hands `slice_of(begin, count)`
+    as the `out=` of DeviceContext.decrypt_decode / decode — the kernel's stores then land in the owner's memory
+    over NVLink while it is still computing the rest of its shard.  `finish()` synchronises the writers and the
+    owner; `tensor()` (root only) views the owner's memory as a torch tensor.
+
+    The reference has no counterpart: its arbiter is a single CPU process (proc/jzf_aggregator.py:404-430)."""
+
+    def __init__(self, ctx, total_len, root=0, group=None, itemsize=8):
+        self.ctx, self.total_len, self.root, self.group, self.itemsize = ctx, int(total_len), root, group, itemsize
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._owned = self._mapped = None
+        handle = [None]
+        if self.rank == root:
+            self._owned, handle[0] = ctx.peer_alloc(self.total_len * itemsize)
+        if self.world > 1:
+            dist.broadcast_object_list(handle, src=root, group=group)
+            if self.rank != root:
+                self._mapped = ctx.peer_open(handle[0])
+        self.base = self._owned if self.rank == root else self._mapped
+
+    def slice_of(self, begin, count):
+        from .device import PeerSlice
+        if begin < 0 or begin + count > self.total_len:
+            raise ValueError("slice outside the gathered vector")
+        return PeerSlice(self.base + begin * self.itemsize, count * self.itemsize)
+
+    def finish(self):
+        """Every writer's stream has completed and the owner may read."""
+        torch.cuda.synchronize(self.ctx.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def tensor(self, dtype=torch.float64):
+        """Root only: a copy-free torch view of the owner's memory (valid until close())."""
+        if self.rank != self.root:
+            raise RuntimeError("only the owning rank can view the gathered vector")
+        import ctypes
+        n = self.total_len * self.itemsize
+        iface = {"shape": (n,), "typestr": "|u1", "data": (self._owned, False), "version": 3, "strides": None}
+        holder = type("PeerMemory", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=self.ctx.device).view(dtype)
+
+    def close(self):
+        if self._mapped is not None:
+            self.ctx.peer_close(self._mapped)
+            self._mapped = None
+        if self.world > 1:
+            dist.barrier(group=self.group)            # nobody maps the buffer any more
+        if self._owned is not None:
+            self.ctx.peer_free(self._owned)
+            self._owned = None

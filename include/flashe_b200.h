@@ -330,6 +330,23 @@ int flashe_segment_stats(flashe_ctx* ctx, const double* w, double* w_out, uint64
                          const uint64_t* seg_end, const double* shift, int nseg, int order, double* stats_out,
                          void* stream);
 
+/* ---- peer buffers: the gather of a sharded result without a collective (SURVEY §8 e) --------------
+ * One process per GPU.  The reference has no counterpart (its arbiter is one CPU process holding the whole
+ * vector, proc/jzf_aggregator.py:404-430); here the decoded shards of G GPUs have to meet on the GPU that owns
+ * the model.  flashe_peer_alloc allocates `bytes` of device memory with cudaMalloc (outside any caching
+ * allocator, so that it can be exported) and fills a 64-byte handle (cudaIpcMemHandle_t) that other processes of
+ * the same node pass to flashe_peer_open; the pointer that comes back addresses the OWNER's memory over NVLink
+ * and can be given to any entry of this library as an output buffer — e.g. flashe_decrypt_decode(..., out =
+ * peer + 8 * shard_begin) makes the decode kernel store its shard straight into the gathering GPU's vector: the
+ * transfer overlaps the PRF work element by element, there is no staging copy and no all-gather afterwards.
+ * The owner must not read the buffer before the writers' streams have completed (a barrier after their
+ * synchronisation is enough); flashe_peer_close unmaps, flashe_peer_free releases the owner's allocation. */
+#define FLASHE_PEER_HANDLE_BYTES 64
+int flashe_peer_alloc(flashe_ctx* ctx, uint64_t bytes, void** ptr_out, uint8_t handle_out[FLASHE_PEER_HANDLE_BYTES]);
+int flashe_peer_open(flashe_ctx* ctx, const uint8_t handle[FLASHE_PEER_HANDLE_BYTES], void** ptr_out);
+int flashe_peer_close(flashe_ctx* ctx, void* ptr);
+int flashe_peer_free(flashe_ctx* ctx, void* ptr);
+
 /* Number of kernels this library has launched on the calling process since load (bench bookkeeping). */
 uint64_t flashe_launch_count(void);
 

@@ -23,7 +23,7 @@ if ROOT not in sys.path:
 
 from flashe_b200.device import (AGG_ELEMENTWISE, AGG_PACKED, SCHEME_DOUBLE, CodecSpec, DeviceContext, NoiseSpec,  # noqa: E402
                                 VectorSpan)
-from flashe_b200.sharding import aggregate_packed_sharded, gather_shards, shard_bounds  # noqa: E402
+from flashe_b200.sharding import PeerGather, aggregate_packed_sharded, gather_shards, shard_bounds  # noqa: E402
 
 KEY = bytes(range(32))
 
@@ -81,7 +81,31 @@ def main():
             out_g = gather_shards(out_s, counts)
         else:
             agg_g, aggp_g, out_g = agg_s, aggp_s, out_s
+        # the same decode with every rank's kernel storing its shard straight into rank 0's vector (peer memory over
+        # NVLink, sharding.PeerGather): no gather step at all
+        pg = PeerGather(ctx, L, root=0)
+        ctx.decrypt_decode(it, [n], [0], agg_s, codec, span, out=pg.slice_of(begin, count))
+        pg.finish()
+        peer_ok = bool(torch.equal(pg.tensor().view(torch.int64), out_w.view(torch.int64))) if rank == 0 else True
+        if world > 1 and L >= 4_000_000:                                # device-timed, max over ranks
+            def timed(fn, steps=10):
+                fn(); torch.cuda.synchronize(); dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    fn()
+                e1.record(); torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t.item())
+            peer_slice = pg.slice_of(begin, count)
+            results["gather_ms_b%d_L%d" % (bits, L)] = {
+                "decode_then_nccl_all_gather": timed(lambda: gather_shards(ctx.decrypt_decode(it, [n], [0], agg_s, codec, span), counts)),
+                "decode_into_peer_memory": timed(lambda: ctx.decrypt_decode(it, [n], [0], agg_s, codec, span, out=peer_slice)),
+                "decode_local_only": timed(lambda: ctx.decrypt_decode(it, [n], [0], agg_s, codec, span))}
+        pg.close()
         checks = {
+            "decoded_gathered_through_peer_memory": peer_ok,
             "ciphertext_shard": bool(torch.equal(cts_s.view(torch.int32), cts_w[:, begin:begin + count].contiguous().view(torch.int32))),
             "aggregate_elementwise": bool(torch.equal(agg_g.view(torch.int32), agg_w.view(torch.int32))),
             "aggregate_packed_carry": bool(torch.equal(aggp_g.view(torch.int32), aggp_w.view(torch.int32))),
@@ -90,6 +114,40 @@ def main():
         }
         results["b%d_L%d_n%d" % (bits, L, n)] = checks
         ok = ok and all(checks.values())
+        ctx.close()
+    if world > 1:
+        # the gather at BASELINE config 5's size (100 M elements, float64 result = 800 MB on the owner), timed alone
+        L, n, bits = 100_000_000, 64, 32
+        ctx = DeviceContext(KEY, bits, dev)
+        begin, count = shard_bounds(L, world, rank)
+        counts = [shard_bounds(L, world, r)[1] for r in range(world)]
+        span = VectorSpan(total_len=L, n_jobs=16, begin=begin, count=count)
+        codec = CodecSpec(alpha=5.938345 * 0.1, element_bits=16, n_clients=n)
+        agg_s = torch.randint(-2 ** 31, 2 ** 31 - 1, (count,), device=dev, dtype=torch.int32).view(torch.uint32)
+        pg = PeerGather(ctx, L, root=0)
+        peer_slice = pg.slice_of(begin, count)
+
+        def timed(fn, steps=5):
+            fn(); torch.cuda.synchronize(); dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        local = ctx.decrypt_decode(0, [n], [0], agg_s, codec, span)
+        ctx.decrypt_decode(0, [n], [0], agg_s, codec, span, out=peer_slice)
+        pg.finish()
+        same = bool(torch.equal(pg.tensor()[begin:begin + count].view(torch.int64), local.view(torch.int64))) if rank == 0 else True
+        ok = ok and same
+        results["gather_ms_100M"] = {
+            "decode_then_nccl_all_gather": timed(lambda: gather_shards(ctx.decrypt_decode(0, [n], [0], agg_s, codec, span), counts)),
+            "decode_into_peer_memory": timed(lambda: ctx.decrypt_decode(0, [n], [0], agg_s, codec, span, out=peer_slice)),
+            "decode_local_only": timed(lambda: ctx.decrypt_decode(0, [n], [0], agg_s, codec, span)),
+            "bytes_to_owner_per_writer": count * 8, "root_shard_equal": same}
+        pg.close()
         ctx.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     if world > 1:

@@ -488,6 +488,28 @@ def test_cuda_graph_replay_of_a_round(fb):
     assert np.array_equal(got_out.view(np.uint64), O.unquantize(p_want, 0.4, 16, n).view(np.uint64))
 
 
+def test_decode_into_an_exported_peer_buffer(fb):
+    """sharding.PeerGather on one rank: the decode kernel writes into memory allocated by flashe_peer_alloc (the
+    buffer other GPUs would map and write into over NVLink; scripts/multi_gpu_check.py does that under torchrun)
+    through a PeerSlice `out=`, shard by shard, and the owner's view equals the plain call bit for bit."""
+    from flashe_b200.sharding import PeerGather, shard_bounds
+    L, n, bits, n_jobs, it = 300_007, 4, 32, 8, 2
+    ctx = ctx_for(fb, bits)
+    codec = fb.CodecSpec(alpha=0.7, element_bits=16, n_clients=n)
+    agg = _dev(np.random.RandomState(4).randint(0, 2 ** 32, L, dtype=np.uint64).astype(np.uint32))
+    want = ctx.decrypt_decode(it, [n], [0], agg, codec, fb.VectorSpan(L, n_jobs))
+    pg = PeerGather(ctx, L)
+    for r in range(3):
+        begin, count = shard_bounds(L, 3, r)
+        span = fb.VectorSpan(L, n_jobs, begin=begin, count=count)
+        ctx.decrypt_decode(it, [n], [0], agg[begin:begin + count].contiguous(), codec, span, out=pg.slice_of(begin, count))
+    pg.finish()
+    assert torch.equal(pg.tensor().view(torch.int64), want.view(torch.int64))
+    with pytest.raises(ValueError):
+        pg.slice_of(L - 3, 8)
+    pg.close()
+
+
 def test_single_scheme_many_streams(fb):
     """single masking decrypt subtracts one stream per survivor; > FLASHE_MAX_STREAMS needs chaining."""
     bits, n_jobs, L, n = 32, 8, 20000, 150

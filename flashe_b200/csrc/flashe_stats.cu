@@ -30,6 +30,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -239,28 +241,48 @@ static void plan_node(uint64_t begin, uint64_t n, uint32_t seg, bool in_mid, std
     plan_node(begin + n2, n - n2, seg, in_mid, groups, mids);
 }
 
-extern "C" int flashe_segment_stats(flashe_ctx* ctx, const double* w, double* w_out, uint64_t total, const uint64_t* seg_end,
-                                    const double* shift, int nseg, int order, double* stats_out, void* stream) {
-    flashe_ctx_info info;
-    { int rc = flashe_ctx_get_info(ctx, &info); if (rc) return rc; }
-    FlasheDeviceGuard guard(info.device);
-    if (!guard.ok) return flashe_fail(FLASHE_ECUDA, "cudaSetDevice failed");
-    cudaStream_t cs = (cudaStream_t)stream;
-    if (nseg < 1 || !seg_end) return flashe_fail(FLASHE_EINVAL, "need nseg >= 1 and seg_end");
-    if (seg_end[nseg - 1] != total) return flashe_fail(FLASHE_EINVAL, "seg_end[nseg-1] must equal total");
-    if (!stats_out) return flashe_fail(FLASHE_EINVAL, "stats_out is NULL");
-    if (total && !w) return flashe_fail(FLASHE_EINVAL, "w is NULL");
-    if (order != FLASHE_SUM_PAIRWISE && order != FLASHE_SUM_SEQUENTIAL) return flashe_fail(FLASHE_EINVAL, "unknown summation order");
-    std::vector<StatSegD> segs((size_t)nseg);
+// A layout's plan, resident on its device.  Up to STAT_PLANS layouts are kept (least recently used goes first);
+// a plan in use by a call stays alive through the shared_ptr even if it is evicted meanwhile, and its device
+// tables are only read by kernels that were enqueued before the free (cudaFree synchronises the device).
+struct StatPlan {
+    int device = 0, order = 0;
+    std::vector<uint64_t> seg_end;
+    std::vector<StatSegD> segs;            // shift = 0: filled per call
+    uint32_t n_groups = 0, n_mids = 0;
+    StatGroup* d_groups = nullptr; StatMid* d_mids = nullptr; uint32_t* d_shapes = nullptr;
+    uint64_t stamp = 0;
+    ~StatPlan() {
+        int prev = -1;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) cudaSetDevice(device);
+        if (d_groups) cudaFree(d_groups);
+        if (d_mids) cudaFree(d_mids);
+        if (d_shapes) cudaFree(d_shapes);
+        if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    }
+};
+#define STAT_PLANS 8
+static std::mutex g_plan_mu;
+static std::vector<std::shared_ptr<StatPlan>> g_plans;
+static uint64_t g_plan_clock = 0;
+
+static int stats_plan(int device, const uint64_t* seg_end, int nseg, int order, std::shared_ptr<StatPlan>* out) {
+    std::lock_guard<std::mutex> lock(g_plan_mu);
+    for (auto& p : g_plans)
+        if (p->device == device && p->order == order && p->seg_end.size() == (size_t)nseg && memcmp(p->seg_end.data(), seg_end, 8 * (size_t)nseg) == 0) {
+            p->stamp = ++g_plan_clock; *out = p; return FLASHE_OK;
+        }
+    auto p = std::make_shared<StatPlan>();
+    p->device = device; p->order = order; p->seg_end.assign(seg_end, seg_end + nseg);
+    p->segs.resize((size_t)nseg);
     std::vector<StatGroup> groups;
     std::vector<StatMid> mids;
     uint64_t prev = 0;
     for (int s = 0; s < nseg; ++s) {
-        if (seg_end[s] < prev) return flashe_fail(FLASHE_EINVAL, "seg_end must be ascending");
-        segs[s].begin = prev; segs[s].n = seg_end[s] - prev; segs[s].shift = shift ? shift[s] : 0.0;
-        segs[s].first_mid = (uint32_t)mids.size();
-        if (order == FLASHE_SUM_PAIRWISE && segs[s].n) plan_node(prev, segs[s].n, (uint32_t)s, false, groups, mids);
-        segs[s].n_mid = (uint32_t)mids.size() - segs[s].first_mid;
+        StatSegD& sg = p->segs[(size_t)s];
+        sg.begin = prev; sg.n = seg_end[s] - prev; sg.shift = 0.0;
+        sg.first_mid = (uint32_t)mids.size();
+        if (order == FLASHE_SUM_PAIRWISE && sg.n) plan_node(prev, sg.n, (uint32_t)s, false, groups, mids);
+        sg.n_mid = (uint32_t)mids.size() - sg.first_mid;
         prev = seg_end[s];
     }
     if (groups.size() > 0xfffffff0ull) return flashe_fail(FLASHE_EUNSUPPORTED, "vector too long for one statistics call");
@@ -278,30 +300,66 @@ extern "C" int flashe_segment_stats(flashe_ctx* ctx, const double* w, double* w_
             g.shape = it->second.first; g.nleaf = it->second.second;
         }
     }
+    p->n_groups = (uint32_t)groups.size(); p->n_mids = (uint32_t)mids.size();
+    cudaError_t e = cudaSuccess;
+    if (!groups.empty()) { e = cudaMalloc((void**)&p->d_groups, sizeof(StatGroup) * groups.size()); if (e == cudaSuccess) e = cudaMemcpy(p->d_groups, groups.data(), sizeof(StatGroup) * groups.size(), cudaMemcpyHostToDevice); }
+    if (e == cudaSuccess && !mids.empty()) { e = cudaMalloc((void**)&p->d_mids, sizeof(StatMid) * mids.size()); if (e == cudaSuccess) e = cudaMemcpy(p->d_mids, mids.data(), sizeof(StatMid) * mids.size(), cudaMemcpyHostToDevice); }
+    if (e == cudaSuccess && !shapes.empty()) { e = cudaMalloc((void**)&p->d_shapes, 4 * shapes.size()); if (e == cudaSuccess) e = cudaMemcpy(p->d_shapes, shapes.data(), 4 * shapes.size(), cudaMemcpyHostToDevice); }
+    if (e != cudaSuccess) { cudaGetLastError(); return flashe_fail(FLASHE_ECUDA, std::string("flashe_segment_stats (plan): ") + cudaGetErrorString(e)); }
+    p->stamp = ++g_plan_clock;
+    if (g_plans.size() >= STAT_PLANS) {
+        size_t victim = 0;
+        for (size_t i = 1; i < g_plans.size(); ++i) if (g_plans[i]->stamp < g_plans[victim]->stamp) victim = i;
+        g_plans.erase(g_plans.begin() + (long)victim);
+    }
+    g_plans.push_back(p);
+    *out = p;
+    return FLASHE_OK;
+}
+
+extern "C" int flashe_segment_stats(flashe_ctx* ctx, const double* w, double* w_out, uint64_t total, const uint64_t* seg_end,
+                                    const double* shift, int nseg, int order, double* stats_out, void* stream) {
+    flashe_ctx_info info;
+    { int rc = flashe_ctx_get_info(ctx, &info); if (rc) return rc; }
+    FlasheDeviceGuard guard(info.device);
+    if (!guard.ok) return flashe_fail(FLASHE_ECUDA, "cudaSetDevice failed");
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (nseg < 1 || !seg_end) return flashe_fail(FLASHE_EINVAL, "need nseg >= 1 and seg_end");
+    if (seg_end[nseg - 1] != total) return flashe_fail(FLASHE_EINVAL, "seg_end[nseg-1] must equal total");
+    if (!stats_out) return flashe_fail(FLASHE_EINVAL, "stats_out is NULL");
+    if (total && !w) return flashe_fail(FLASHE_EINVAL, "w is NULL");
+    if (order != FLASHE_SUM_PAIRWISE && order != FLASHE_SUM_SEQUENTIAL) return flashe_fail(FLASHE_EINVAL, "unknown summation order");
+    // The plan (groups, mid nodes, leaf shapes) depends only on the layer sizes: it is built once per layout and kept
+    // on the device (a model's layout is the same every round); only the per-layer shifts travel with each call.
+    std::vector<StatSegD> segs((size_t)nseg);
+    uint64_t prev = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (seg_end[s] < prev) return flashe_fail(FLASHE_EINVAL, "seg_end must be ascending");
+        prev = seg_end[s];
+    }
+    std::shared_ptr<StatPlan> plan;
+    { int rc = stats_plan(info.device, seg_end, nseg, order, &plan); if (rc) return rc; }
+    for (int s = 0; s < nseg; ++s) { segs[s] = plan->segs[(size_t)s]; segs[s].shift = shift ? shift[s] : 0.0; }
+    const uint32_t n_groups = plan->n_groups, n_mids = plan->n_mids;
     auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t b_seg = pad(sizeof(StatSegD) * segs.size()), b_grp = pad(sizeof(StatGroup) * groups.size()),
-                 b_mid = pad(sizeof(StatMid) * mids.size()), b_gs = pad(8 * groups.size()), b_ms = pad(8 * mids.size()),
-                 b_sh = pad(4 * shapes.size());
+    const size_t b_seg = pad(sizeof(StatSegD) * segs.size()), b_gs = pad(8 * (size_t)n_groups), b_ms = pad(8 * (size_t)n_mids);
     uint8_t* ws = nullptr;
-    FLASHE_CUDA_TRY(cudaMallocAsync((void**)&ws, b_seg + b_grp + b_mid + b_gs + b_ms + b_sh + 256, cs));
+    FLASHE_CUDA_TRY(cudaMallocAsync((void**)&ws, b_seg + b_gs + b_ms + 256, cs));
     StatSegD* dseg = reinterpret_cast<StatSegD*>(ws);
-    StatGroup* dgrp = reinterpret_cast<StatGroup*>(ws + b_seg);
-    StatMid* dmid = reinterpret_cast<StatMid*>(ws + b_seg + b_grp);
-    double* gsum = reinterpret_cast<double*>(ws + b_seg + b_grp + b_mid);
-    double* msum = reinterpret_cast<double*>(ws + b_seg + b_grp + b_mid + b_gs);
-    uint32_t* dshape = reinterpret_cast<uint32_t*>(ws + b_seg + b_grp + b_mid + b_gs + b_ms);
+    double* gsum = reinterpret_cast<double*>(ws + b_seg);
+    double* msum = reinterpret_cast<double*>(ws + b_seg + b_gs);
+    const StatGroup* dgrp = plan->d_groups;
+    const StatMid* dmid = plan->d_mids;
+    const uint32_t* dshape = plan->d_shapes;
+    // (a pageable source has been staged by the time cudaMemcpyAsync returns: `segs` may go out of scope)
     cudaError_t e = cudaMemcpyAsync(dseg, segs.data(), sizeof(StatSegD) * segs.size(), cudaMemcpyHostToDevice, cs);
-    if (e == cudaSuccess && !groups.empty()) e = cudaMemcpyAsync(dgrp, groups.data(), sizeof(StatGroup) * groups.size(), cudaMemcpyHostToDevice, cs);
-    if (e == cudaSuccess && !mids.empty()) e = cudaMemcpyAsync(dmid, mids.data(), sizeof(StatMid) * mids.size(), cudaMemcpyHostToDevice, cs);
-    if (e == cudaSuccess && !shapes.empty()) e = cudaMemcpyAsync(dshape, shapes.data(), 4 * shapes.size(), cudaMemcpyHostToDevice, cs);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);   // the host vectors (pageable memory) go out of scope
     int launches = 0;
     if (e == cudaSuccess && order == FLASHE_SUM_SEQUENTIAL) {
         k_stats_sequential<<<nseg, 32, 0, cs>>>(w, w_out, dseg, nseg, stats_out);
         launches = 1;
         e = cudaGetLastError();
     } else if (e == cudaSuccess) {
-        const uint32_t ng = (uint32_t)groups.size(), nm = (uint32_t)mids.size();
+        const uint32_t ng = n_groups, nm = n_mids;
         const uint64_t cap = (uint64_t)info.num_sms * 8;
         const uint64_t want = (ng + SG_WARPS - 1) / SG_WARPS;
         const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));

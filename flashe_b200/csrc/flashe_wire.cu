@@ -640,9 +640,12 @@ __device__ __forceinline__ uint32_t topk_elem_of(uint32_t k) { return 4u * ((k >
 // The loads of the next tile are in flight while the current one is scanned; the few candidates of a thread (2-4 %
 // of the elements) are visited through the set bits of its hit mask.
 #define TK_FBUF 2048u
+#define TKF_STAGES 3
 __global__ void __launch_bounds__(TK_THREADS)
 k_topk_filter(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles, uint64_t tiles_per_block,
               const uint32_t* __restrict__ lo_all, uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_key, uint32_t* __restrict__ cand_idx) {
+    extern __shared__ __align__(128) uint32_t tkf_ring[];             // TKF_STAGES tiles of x (whole tiles of aligned layers, bulk copy engine)
+    __shared__ __align__(8) uint64_t full[TKF_STAGES];
     __shared__ uint2 buf[TK_FBUF];
     __shared__ uint32_t wtot[2][TK_THREADS / 32];
     __shared__ uint32_t slot0;
@@ -652,11 +655,43 @@ k_topk_filter(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, 
     uint64_t t_end = t_begin + tiles_per_block;
     if (t_end > ntiles) t_end = ntiles;
     if (t_begin >= t_end) return;
+    const uint32_t bar0 = smem_u32(&full[0]), ring0 = smem_u32(tkf_ring);
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < TKF_STAGES; ++q) mbar_init(bar0 + 8u * q, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     int s = topk_seg_of<0>(segs, nseg, t_begin);
     TopkSeg sg = segs[s];
     uint32_t lo = lo_all[s];
-    uint32_t w[TK_PER], valid = 0u;
-    if (sg.cap) valid = topk_load_tile(x + sg.begin, (t_begin - sg.tile0) * TK_TILE, sg.n, (((uintptr_t)(x + sg.begin)) & 15u) == 0, w);
+    // Per-layer state in 32 bits: tile index inside the layer, its tile count, how many of them are whole, whether the
+    // layer's tiles can come through the ring.  Tiles are consecutive and every layer has at least one, so the layer
+    // of the next tile is s or s + 1: the table is walked without a search and without 64-bit arithmetic per tile.
+    auto layer_bulk = [&](const TopkSeg& g) { return g.cap != 0u && (((uintptr_t)(x + g.begin)) & 15u) == 0; };
+    uint32_t lt = (uint32_t)(t_begin - sg.tile0), ntl = (sg.n + TK_TILE - 1u) / TK_TILE, nfull = sg.n / TK_TILE;
+    bool lbulk = layer_bulk(sg);
+    const uint32_t nrun = (uint32_t)(t_end - t_begin);
+    // thread 0: the same cursor for the tile being issued, TKF_STAGES - 1 tiles ahead
+    int s_is = s;
+    uint32_t lt_is = lt, ntl_is = ntl, nfull_is = nfull, q_is = 0u;
+    bool lbulk_is = lbulk;
+    uint64_t e_is = sg.begin + (uint64_t)lt * TK_TILE;                  // first element of the tile being issued
+    auto issue_next = [&]() {                                           // issues the cursor's tile and advances the cursor
+        if (lbulk_is && lt_is < nfull_is) {
+            mbar_expect_tx(bar0 + 8u * q_is, TK_TILE * 4u);
+            bulk_g2s(ring0 + q_is * (TK_TILE * 4u), x + e_is, TK_TILE * 4u, bar0 + 8u * q_is);
+        }
+        q_is = q_is + 1u == TKF_STAGES ? 0u : q_is + 1u;
+        if (++lt_is == ntl_is) {
+            if (++s_is < nseg) {
+                const TopkSeg g = segs[s_is];
+                lt_is = 0u; ntl_is = (g.n + TK_TILE - 1u) / TK_TILE; nfull_is = g.n / TK_TILE; lbulk_is = layer_bulk(g); e_is = g.begin;
+            }
+        } else e_is += TK_TILE;
+    };
+    __syncthreads();                                                    // barriers initialised
+    if (threadIdx.x == 0)
+        for (uint32_t j = 0; j < nrun && j < TKF_STAGES - 1u; ++j) issue_next();
+    uint32_t phase = 0u;                                                // one parity bit per stage
     uint32_t fill = 0u;                                                 // (block-uniform) entries of layer s waiting in buf
     // claims `count` slots of layer s; returns the first one, or 0xffffffff when the region cannot hold them
     auto claim = [&](uint32_t count) -> uint32_t {
@@ -674,19 +709,27 @@ k_topk_filter(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, 
         __syncthreads();                                                // buf may be refilled
         fill = 0u;
     };
-    for (uint64_t tile = t_begin; tile < t_end; ++tile) {
-        // the next tile's layer and loads
-        int s2 = s;
-        TopkSeg sg2 = sg;
-        uint32_t lo2 = lo, w2[TK_PER], valid2 = 0u;
-        if (tile + 1 < t_end) {
-            bool moved = false;
-            while (s2 + 1 < nseg && segs[s2 + 1].tile0 <= tile + 1) { ++s2; moved = true; }
-            if (moved) { sg2 = segs[s2]; lo2 = lo_all[s2]; }
-            if (sg2.cap) valid2 = topk_load_tile(x + sg2.begin, (tile + 1 - sg2.tile0) * TK_TILE, sg2.n, (((uintptr_t)(x + sg2.begin)) & 15u) == 0, w2);
-        }
+    uint32_t q = 0u;                                                    // ring stage of the current tile
+    for (uint32_t j = 0; j < nrun; ++j) {
+        const bool more = j + (TKF_STAGES - 1u) < nrun;                 // a tile to issue: into the stage of tile j - 1
         if (sg.cap) {                                                   // (block-uniform)
-            const uint32_t base = (uint32_t)((tile - sg.tile0) * TK_TILE);
+            const bool bulk = lbulk && lt < nfull;
+            const uint32_t* ring = tkf_ring + q * TK_TILE;
+            uint32_t w[TK_PER], valid;
+            if (bulk) {
+                mbar_wait(bar0 + 8u * q, (phase >> q) & 1u);
+                phase ^= 1u << q;
+                const uint4* xs4 = reinterpret_cast<const uint4*>(ring);
+#pragma unroll
+                for (int r = 0; r < TK_PER / 4; ++r) {
+                    const uint4 v = xs4[r * TK_THREADS + threadIdx.x];
+                    w[4 * r] = v.x; w[4 * r + 1] = v.y; w[4 * r + 2] = v.z; w[4 * r + 3] = v.w;
+                }
+                valid = 0xffffu;
+            } else {
+                valid = topk_load_tile(x + sg.begin, (uint64_t)lt * TK_TILE, sg.n, (((uintptr_t)(x + sg.begin)) & 15u) == 0, w);
+            }
+            const uint32_t base = lt * TK_TILE;
             const float lo_f = __uint_as_float(lo);
             uint32_t sel = 0u;
 #pragma unroll
@@ -695,40 +738,49 @@ k_topk_filter(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, 
             const uint32_t cnt = __popc(sel);
             uint32_t incl = cnt;
             for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
-            const uint32_t pb = (uint32_t)tile & 1u;                    // alternating shared slots: one barrier per tile
+            const uint32_t pb = j & 1u;                                 // alternating shared slots: one barrier per tile
             if (lane == 31) wtot[pb][warp] = incl;
-            __syncthreads();
+            __syncthreads();                                            // ... which also ends every read of tile j - 1's stage
+            if (threadIdx.x == 0 && more) issue_next();
             uint32_t before = incl - cnt, total = 0u;
 #pragma unroll
             for (uint32_t v = 0; v < TK_THREADS / 32; ++v) { const uint32_t c = wtot[pb][v]; if (v < warp) before += c; total += c; }
+            // a candidate's key: still in the ring stage for a bulk tile (one shared load), else picked from the registers
+            auto key_at = [&](uint32_t k) { return key_of_bits(bulk ? ring[topk_elem_of(k)] : topk_pick16(w, k)); };
             if (fill + total > TK_FBUF) flush();
             if (total > TK_FBUF) {                                      // a tile denser than the buffer (bound too low): straight to the region
                 const uint32_t first = claim(total);
                 if (first != 0xffffffffu) {
-                    uint32_t m = sel, j = first + before;
+                    uint32_t m = sel, jj = first + before;
                     while (m) {
                         const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
                         m &= m - 1u;
-                        cand_key[sg.cbegin + j] = key_of_bits(topk_pick16(w, k));
-                        cand_idx[sg.cbegin + j] = base + topk_elem_of(k);
-                        ++j;
+                        cand_key[sg.cbegin + jj] = key_at(k);
+                        cand_idx[sg.cbegin + jj] = base + topk_elem_of(k);
+                        ++jj;
                     }
                 }
             } else {
-                uint32_t m = sel, j = fill + before;
+                uint32_t m = sel, jj = fill + before;
                 while (m) {
                     const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
                     m &= m - 1u;
-                    buf[j] = make_uint2(key_of_bits(topk_pick16(w, k)), base + topk_elem_of(k));
-                    ++j;
+                    buf[jj] = make_uint2(key_at(k), base + topk_elem_of(k));
+                    ++jj;
                 }
                 fill += total;
             }
+        } else {
+            __syncthreads();                                            // every read of tile j - 1's stage has ended
+            if (threadIdx.x == 0 && more) issue_next();
         }
-        if (s2 != s) flush();                                           // the buffer holds one layer's candidates
-        s = s2; sg = sg2; lo = lo2; valid = valid2;
-#pragma unroll
-        for (int k = 0; k < TK_PER; ++k) w[k] = w2[k];
+        q = q + 1u == TKF_STAGES ? 0u : q + 1u;
+        if (++lt == ntl && j + 1u < nrun) {                             // the run enters the next layer
+            flush();                                                    // the buffer holds one layer's candidates
+            ++s;
+            sg = segs[s]; lo = lo_all[s];
+            lt = 0u; ntl = (sg.n + TK_TILE - 1u) / TK_TILE; nfull = sg.n / TK_TILE; lbulk = layer_bulk(sg);
+        }
     }
     flush();
 }
@@ -738,14 +790,12 @@ k_topk_filter(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, 
 // whenever the run crosses into the next layer (and at the end).  CAND: the tiles are those of the candidate
 // regions and `x` is the candidate key array; otherwise the tiles of x itself (exact-route layers only).
 template <bool CAND>
-__global__ void __launch_bounds__(TK_THREADS)
-k_topk_hist(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles, uint64_t tiles_per_block,
-            const TopkState* __restrict__ st, const uint32_t* __restrict__ cand_count, uint32_t shift, uint32_t nbits, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t sh[TK_BINS];
-    const uint64_t t_begin = (uint64_t)blockIdx.x * tiles_per_block;
+__device__ __forceinline__ void topk_hist_run(uint32_t* sh, uint32_t bid, const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, int nseg,
+                                              uint64_t ntiles, uint64_t tiles_per_block, const TopkState* __restrict__ st,
+                                              const uint32_t* __restrict__ cand_count, uint32_t shift, uint32_t nbits, uint32_t* __restrict__ hist) {
+    const uint64_t t_begin = (uint64_t)bid * tiles_per_block;
     uint64_t t_end = t_begin + tiles_per_block;
     if (t_end > ntiles) t_end = ntiles;
-    topk_pdl_enter();
     if (t_begin >= t_end) return;
     for (uint32_t i = threadIdx.x; i < TK_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -792,15 +842,26 @@ k_topk_hist(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, in
         if (c) atomicAdd(&hist[(size_t)s * TK_BINS + i], c);
     }
 }
-
-// exact route: per-tile counts of (key > T, key == T) read from x; a block owns a contiguous run of tiles and
-// jumps over the layers of the candidate route
+// ONE launch per radix pass for both routes: the first `gc` blocks walk the candidate tiles, the others the tiles of x
+// (where they find nothing to do unless a layer takes the exact route).
 __global__ void __launch_bounds__(TK_THREADS)
-k_topk_count(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles, uint64_t tiles_per_block,
-             const TopkState* __restrict__ st, const uint32_t* __restrict__ cand_count, uint2* __restrict__ tile_counts) {
-    __shared__ uint32_t sg_[TK_THREADS / 32], se_[TK_THREADS / 32];
+k_topk_hist(const uint32_t* __restrict__ x, const uint32_t* __restrict__ cand_key, const TopkSeg* __restrict__ segs, int nseg,
+            uint32_t gc, uint64_t nctiles, uint64_t ctpb, uint64_t ntiles, uint64_t tpb,
+            const TopkState* __restrict__ st, const uint32_t* __restrict__ cand_count, uint32_t shift, uint32_t nbits, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[TK_BINS];
     topk_pdl_enter();
-    const uint64_t t_begin = (uint64_t)blockIdx.x * tiles_per_block;
+    if (blockIdx.x < gc) topk_hist_run<true>(sh, blockIdx.x, cand_key, segs, nseg, nctiles, ctpb, st, cand_count, shift, nbits, hist);
+    else topk_hist_run<false>(sh, blockIdx.x - gc, x, segs, nseg, ntiles, tpb, st, cand_count, shift, nbits, hist);
+}
+
+// Per-tile counts of (key > T, key == T), both routes in one launch.  Exact route (blocks >= gc): read from x; a block
+// owns a contiguous run of tiles and jumps over the layers of the candidate route.  Candidate route (blocks < gc): see
+// topk_cand_count_run.
+__device__ __forceinline__ void topk_count_run(uint32_t bid, const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles,
+                                               uint64_t tiles_per_block, const TopkState* __restrict__ st, const uint32_t* __restrict__ cand_count,
+                                               uint2* __restrict__ tile_counts) {
+    __shared__ uint32_t sg_[TK_THREADS / 32], se_[TK_THREADS / 32];
+    const uint64_t t_begin = (uint64_t)bid * tiles_per_block;
     uint64_t t_end = t_begin + tiles_per_block;
     if (t_end > ntiles) t_end = ntiles;
     if (t_begin >= t_end) return;
@@ -838,21 +899,21 @@ k_topk_count(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, i
 }
 
 // candidate route: the same per-tile counts from the candidate list (every element at or above the threshold is
-// a candidate); tile_counts starts zeroed
-__global__ void __launch_bounds__(TK_THREADS)
-k_topk_cand_count(const uint32_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_idx, const TopkSeg* __restrict__ segs, int nseg,
-                  uint64_t nctiles, const TopkState* __restrict__ st, const uint32_t* __restrict__ cand_count, uint2* __restrict__ tile_counts) {
-    topk_pdl_enter();
-    for (uint64_t tile = blockIdx.x; tile < nctiles; tile += gridDim.x) {
-        const int s = topk_seg_of<1>(segs, nseg, tile);
+// a candidate); tile_counts starts zeroed.  The blocks are dealt to the layers directly (P blocks per layer, layers
+// round-robin over the nblk / P slots): the list lengths are only known on the device, and a search per work unit
+// through a table of mostly empty regions cost more than the counting.
+__device__ __forceinline__ void topk_cand_count_run(uint32_t bid, uint32_t nblk, const uint32_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_idx,
+                                                    const TopkSeg* __restrict__ segs, int nseg, const TopkState* __restrict__ st,
+                                                    const uint32_t* __restrict__ cand_count, uint2* __restrict__ tile_counts) {
+    const uint32_t P = nblk / (uint32_t)nseg > 0u ? nblk / (uint32_t)nseg : 1u, slots = nblk / P;
+    const uint32_t slot = bid / P, j = bid % P;
+    if (slot >= slots) return;
+    for (uint32_t s = slot; s < (uint32_t)nseg; s += slots) {
         const TopkSeg sg = segs[s];
-        const TopkView vw = topk_view<true>(sg, cand_count, s);
-        const uint64_t base = (tile - vw.tile0) * TK_TILE;
-        if (base >= vw.n) continue;
+        const TopkView vw = topk_view<true>(sg, cand_count, (int)s);
+        if (vw.n == 0u) continue;
         const uint32_t T = st[s].prefix;
-        for (uint32_t r = threadIdx.x; r < TK_TILE; r += TK_THREADS) {
-            const uint64_t i = base + r;
-            if (i >= vw.n) break;
+        for (uint32_t i = j * TK_THREADS + threadIdx.x; i < vw.n; i += P * TK_THREADS) {
             const uint32_t key = cand_key[vw.begin + i];
             if (key >= T) {
                 uint32_t* tc = reinterpret_cast<uint32_t*>(&tile_counts[sg.tile0 + cand_idx[vw.begin + i] / TK_TILE]);
@@ -861,53 +922,13 @@ k_topk_cand_count(const uint32_t* __restrict__ cand_key, const uint32_t* __restr
         }
     }
 }
-
-// exclusive scan of each layer's tile counts in place (one block per layer, four tiles per thread and step)
-__global__ void __launch_bounds__(1024)
-k_topk_scan(uint2* __restrict__ tile_counts_all, const TopkSeg* __restrict__ segs, int nseg, uint64_t ntiles_all) {
-    __shared__ uint32_t wg[32], we[32];
-    __shared__ uint32_t carry_g, carry_e;
+__global__ void __launch_bounds__(TK_THREADS)
+k_topk_count(const uint32_t* __restrict__ x, const uint32_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_idx, const TopkSeg* __restrict__ segs, int nseg,
+             uint32_t gc, uint64_t nctiles, uint64_t ntiles, uint64_t tpb, const TopkState* __restrict__ st, const uint32_t* __restrict__ cand_count,
+             uint2* __restrict__ tile_counts) {
     topk_pdl_enter();
-    const int s = blockIdx.x;
-    const uint64_t t0 = segs[s].tile0, t1 = s + 1 < nseg ? segs[s + 1].tile0 : ntiles_all;
-    uint2* tile_counts = tile_counts_all + t0;
-    const uint64_t ntiles = t1 - t0;
-    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
-    if (t == 0) { carry_g = 0; carry_e = 0; }
-    __syncthreads();
-    for (uint64_t base = 0; base < ntiles; base += 4096) {
-        const uint64_t i0 = base + 4ull * t;
-        uint2 c[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) c[k] = i0 + k < ntiles ? tile_counts[i0 + k] : make_uint2(0, 0);
-        const uint32_t own_g = c[0].x + c[1].x + c[2].x + c[3].x, own_e = c[0].y + c[1].y + c[2].y + c[3].y;
-        uint32_t g = own_g, e = own_e;
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t og = __shfl_up_sync(0xffffffffu, g, d), oe = __shfl_up_sync(0xffffffffu, e, d);
-            if (lane >= (uint32_t)d) { g += og; e += oe; }
-        }
-        if (lane == 31) { wg[warp] = g; we[warp] = e; }
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t a = wg[lane], b = we[lane];
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t oa = __shfl_up_sync(0xffffffffu, a, d), ob = __shfl_up_sync(0xffffffffu, b, d);
-                if (lane >= (uint32_t)d) { a += oa; b += ob; }
-            }
-            wg[lane] = a; we[lane] = b;
-        }
-        __syncthreads();
-        uint32_t pg = carry_g + (warp ? wg[warp - 1] : 0u) + g - own_g;
-        uint32_t pe = carry_e + (warp ? we[warp - 1] : 0u) + e - own_e;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k < ntiles) tile_counts[i0 + k] = make_uint2(pg, pe);
-            pg += c[k].x; pe += c[k].y;
-        }
-        __syncthreads();
-        if (t == 1023) { carry_g = pg; carry_e = pe; }
-        __syncthreads();
-    }
+    if (blockIdx.x < gc) topk_cand_count_run(blockIdx.x, gc, cand_key, cand_idx, segs, nseg, st, cand_count, tile_counts);
+    else topk_count_run(blockIdx.x - gc, x, segs, nseg, ntiles, tpb, st, cand_count, tile_counts);
 }
 
 // Ordered write.  A tile is four rows of 256 16-byte quads (topk_load_tile's layout: every access of a warp
@@ -941,10 +962,17 @@ __device__ __forceinline__ void topk_write_load(TopkTile& t, const uint32_t* __r
         }
     }
 }
+// Whole tiles of 16-byte aligned layers reach the block through a ring of TKW_STAGES shared-memory stages filled by
+// the bulk copy engine (cp.async.bulk + mbarrier, issued TKW_STAGES - 1 tiles ahead by thread 0): the prefetch holds
+// no registers, so two CTAs per SM keep six tiles (192 KB) in flight.  Partial tiles and unaligned layers are read
+// straight from global memory.
+#define TKW_STAGES 3
 __global__ void __launch_bounds__(TK_THREADS)
 k_topk_write(const uint32_t* __restrict__ x, const float* __restrict__ res_in, const TopkSeg* __restrict__ segs, int nseg,
-             uint64_t ntiles, uint64_t tiles_per_block, const TopkState* __restrict__ st_all, const uint2* __restrict__ tile_prefix,
+             uint64_t ntiles, uint64_t tiles_per_block, const TopkState* __restrict__ st_all, const uint2* __restrict__ tile_counts,
              float* __restrict__ values_all, int64_t* __restrict__ index_all, float* res_out) {
+    extern __shared__ __align__(128) uint32_t tkw_ring[];          // TKW_STAGES x (x tile | residual tile)
+    __shared__ __align__(8) uint64_t full[TKW_STAGES];
     __shared__ uint64_t wg[2][TK_THREADS / 32], we[2][TK_THREADS / 32];
     topk_pdl_enter();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -952,24 +980,83 @@ k_topk_write(const uint32_t* __restrict__ x, const float* __restrict__ res_in, c
     uint64_t t_end = t_begin + tiles_per_block;
     if (t_end > ntiles) t_end = ntiles;
     if (t_begin >= t_end) return;
+    const uint32_t bar0 = smem_u32(&full[0]), ring0 = smem_u32(tkw_ring);
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < TKW_STAGES; ++q) mbar_init(bar0 + 8u * q, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     int s = topk_seg_of<0>(segs, nseg, t_begin);
     TopkSeg sgm = segs[s];
-    TopkTile cur;
-    topk_write_load(cur, x, res_in, res_out, sgm, t_begin);
-    for (uint64_t tile = t_begin; tile < t_end; ++tile) {
-        int s2 = s;
-        TopkSeg sg2 = sgm;
-        TopkTile nxt;
-        if (tile + 1 < t_end) {
-            bool moved = false;
-            while (s2 + 1 < nseg && segs[s2 + 1].tile0 <= tile + 1) { ++s2; moved = true; }
-            if (moved) sg2 = segs[s2];
-            topk_write_load(nxt, x, res_in, res_out, sg2, tile + 1);
+    // 32-bit per-layer cursor (see k_topk_filter): tile inside the layer, tiles of the layer, whole tiles, ring-eligible
+    auto layer_bulk = [&](const TopkSeg& g) {
+        return ((((uintptr_t)(x + g.begin)) | (res_in ? (uintptr_t)(res_in + g.begin) : 0) | (res_out ? (uintptr_t)(res_out + g.begin) : 0)) & 15u) == 0;
+    };
+    uint32_t lt = (uint32_t)(t_begin - sgm.tile0), ntl = (sgm.n + TK_TILE - 1u) / TK_TILE, nfull = sgm.n / TK_TILE;
+    bool lbulk = layer_bulk(sgm);
+    const uint32_t nrun = (uint32_t)(t_end - t_begin);
+    int s_is = s;                                                   // thread 0: cursor of the tile being issued
+    uint32_t lt_is = lt, ntl_is = ntl, nfull_is = nfull, q_is = 0u;
+    bool lbulk_is = lbulk;
+    uint64_t e_is = sgm.begin + (uint64_t)lt * TK_TILE;
+    const uint32_t stage_bytes = 2u * TK_TILE * 4u;
+    auto issue_next = [&]() {
+        if (lbulk_is && lt_is < nfull_is) {
+            mbar_expect_tx(bar0 + 8u * q_is, (res_in ? 2u : 1u) * TK_TILE * 4u);
+            bulk_g2s(ring0 + q_is * stage_bytes, x + e_is, TK_TILE * 4u, bar0 + 8u * q_is);
+            if (res_in) bulk_g2s(ring0 + q_is * stage_bytes + TK_TILE * 4u, res_in + e_is, TK_TILE * 4u, bar0 + 8u * q_is);
         }
-        const TopkState st = st_all[s];
+        q_is = q_is + 1u == TKW_STAGES ? 0u : q_is + 1u;
+        if (++lt_is == ntl_is) {
+            if (++s_is < nseg) {
+                const TopkSeg g = segs[s_is];
+                lt_is = 0u; ntl_is = (g.n + TK_TILE - 1u) / TK_TILE; nfull_is = g.n / TK_TILE; lbulk_is = layer_bulk(g); e_is = g.begin;
+            }
+        } else e_is += TK_TILE;
+    };
+    __syncthreads();                                               // barriers initialised
+    if (threadIdx.x == 0)
+        for (uint32_t j = 0; j < nrun && j < TKW_STAGES - 1u; ++j) issue_next();
+    uint32_t phase = 0u;                                           // one parity bit per stage
+    // (key > T, key == T) elements of the layer before the current tile: the per-tile counts of the tiles between the
+    // layer's first one and the run's first one, summed once per run by the whole block (no scan pass over the table);
+    // from there the block keeps the count itself, and a run enters every further layer at its first tile (0, 0)
+    uint32_t run_g = 0u, run_e = 0u;
+    {
+        uint32_t g = 0u, e = 0u;
+        for (uint64_t t = sgm.tile0 + threadIdx.x; t < t_begin; t += TK_THREADS) { const uint2 c = tile_counts[t]; g += c.x; e += c.y; }
+        for (int d = 16; d > 0; d >>= 1) { g += __shfl_down_sync(0xffffffffu, g, d); e += __shfl_down_sync(0xffffffffu, e, d); }
+        if (lane == 0) { wg[0][warp] = g; we[0][warp] = e; }
+        __syncthreads();
+#pragma unroll
+        for (uint32_t v = 0; v < TK_THREADS / 32; ++v) { run_g += (uint32_t)wg[0][v]; run_e += (uint32_t)we[0][v]; }
+        __syncthreads();
+    }
+    TopkState st = st_all[s];
+    uint32_t q = 0u;
+    for (uint32_t j = 0; j < nrun; ++j) {
+        const bool more = j + (TKW_STAGES - 1u) < nrun;
+        const bool bulk = lbulk && lt < nfull;
+        const uint32_t* ring_x = tkw_ring + q * (2u * TK_TILE);
+        const float* ring_r = reinterpret_cast<const float*>(ring_x + TK_TILE);
+        TopkTile cur;
+        if (bulk) {
+            mbar_wait(bar0 + 8u * q, (phase >> q) & 1u);
+            phase ^= 1u << q;
+            const uint4* xs4 = reinterpret_cast<const uint4*>(ring_x);
+            const float4* rs4 = reinterpret_cast<const float4*>(ring_r);
+#pragma unroll
+            for (int r = 0; r < TK_PER / 4; ++r) {
+                const uint4 v = xs4[r * TK_THREADS + threadIdx.x];
+                cur.w[4 * r] = v.x; cur.w[4 * r + 1] = v.y; cur.w[4 * r + 2] = v.z; cur.w[4 * r + 3] = v.w;
+                if (res_in) { const float4 u = rs4[r * TK_THREADS + threadIdx.x]; cur.rv[4 * r] = u.x; cur.rv[4 * r + 1] = u.y; cur.rv[4 * r + 2] = u.z; cur.rv[4 * r + 3] = u.w; }
+            }
+            cur.valid = 0xffffu; cur.vec = true;
+        } else {
+            topk_write_load(cur, x, res_in, res_out, sgm, sgm.tile0 + lt);
+        }
         const uint32_t T = st.prefix, skip_eq = st.c_eq - st.k_rem;   // ties with rank < skip_eq are not taken
         const uint32_t n = sgm.n;
-        const uint32_t base = (uint32_t)((tile - sgm.tile0) * TK_TILE);
+        const uint32_t base = lt * TK_TILE;
         float f[TK_PER];
         uint32_t gm = 0u, em = 0u;                              // hit masks: key > T, key == T
 #pragma unroll
@@ -991,7 +1078,7 @@ k_topk_write(const uint32_t* __restrict__ x, const float* __restrict__ res_in, c
             const uint64_t og = __shfl_up_sync(0xffffffffu, sg, d), oe = __shfl_up_sync(0xffffffffu, se, d);
             if (lane >= (uint32_t)d) { sg += og; se += oe; }
         }
-        const uint32_t pb = (uint32_t)tile & 1u;                // alternating slots: one barrier per tile
+        const uint32_t pb = j & 1u;                             // alternating slots: one barrier per tile
         if (lane == 31) { wg[pb][warp] = sg; we[pb][warp] = se; }
         // the rows of the new residual (selected positions are zeroed below)
         if (res_out) {
@@ -1003,53 +1090,67 @@ k_topk_write(const uint32_t* __restrict__ x, const float* __restrict__ res_in, c
                 else for (int k = 0; k < 4; ++k) if (i0 + k < n) op[k] = f[4 * r + k];
             }
         }
-        __syncthreads();
+        __syncthreads();                                        // ... which also ends every read of tile j - 1's stage
+        if (threadIdx.x == 0 && more) issue_next();
         uint32_t hits = gm | em;
-        if (hits) {
-            uint64_t bg = 0ull, be = 0ull, tg = 0ull, te = 0ull;    // threads before this warp; the whole tile
+        uint64_t bg = 0ull, be = 0ull, tg = 0ull, te = 0ull;    // threads before this warp; the whole tile
 #pragma unroll
-            for (uint32_t v = 0; v < TK_THREADS / 32; ++v) { const uint64_t a = wg[pb][v], b = we[pb][v]; if (v < warp) { bg += a; be += b; } tg += a; te += b; }
+        for (uint32_t v = 0; v < TK_THREADS / 32; ++v) { const uint64_t a = wg[pb][v], b = we[pb][v]; if (v < warp) { bg += a; be += b; } tg += a; te += b; }
+        if (hits) {
             // per row: hits before this thread's quad = rows before (totals) + threads before in the row; rows packed 16 bits each
             const uint64_t rows_g = (tg << 16) + (tg << 32) + (tg << 48), rows_e = (te << 16) + (te << 32) + (te << 48);   // exclusive prefix over rows
             const uint64_t xg = bg + sg - G + rows_g, xe = be + se - E + rows_e;
-            const uint2 tp = tile_prefix[tile];
             float* values = values_all + sgm.out_off;
             int64_t* index = index_all + sgm.out_off;
             while (hits) {
                 const uint32_t k = (uint32_t)__ffs((int)hits) - 1u;
                 hits &= hits - 1u;
                 const uint32_t r = k >> 2, below = (1u << k) - 1u, rowm = 0xfu << (4u * r);
-                const uint32_t gt_before = tp.x + (uint32_t)((xg >> (16u * r)) & 0xffffu) + __popc(gm & rowm & below);
-                const uint32_t eq_before = tp.y + (uint32_t)((xe >> (16u * r)) & 0xffffu) + __popc(em & rowm & below);
+                const uint32_t gt_before = run_g + (uint32_t)((xg >> (16u * r)) & 0xffffu) + __popc(gm & rowm & below);
+                const uint32_t eq_before = run_e + (uint32_t)((xe >> (16u * r)) & 0xffffu) + __popc(em & rowm & below);
                 const bool is_gt = (gm >> k) & 1u;
                 if (is_gt || eq_before >= skip_eq) {
                     const uint32_t taken_eq = eq_before > skip_eq ? eq_before - skip_eq : 0u;   // selected ties before it
                     const uint64_t pos = (uint64_t)gt_before + taken_eq;
-                    const uint64_t gi = sgm.begin + base + topk_elem_of(k);
-                    values[pos] = topk_pick16(f, k);
+                    const uint32_t el = topk_elem_of(k);
+                    const uint64_t gi = sgm.begin + base + el;
+                    // the value: still in the ring stage for a bulk tile (same operands, same rounding), else picked from the registers
+                    values[pos] = bulk ? (res_in ? __fadd_rn(__uint_as_float(ring_x[el]), ring_r[el]) : __uint_as_float(ring_x[el])) : topk_pick16(f, k);
                     index[pos] = (int64_t)gi;
                     if (res_out) res_out[gi] = 0.0f;
                 }
             }
         }
-        s = s2; sgm = sg2;
-        cur = nxt;
+        q = q + 1u == TKW_STAGES ? 0u : q + 1u;
+        if (++lt == ntl && j + 1u < nrun) {                     // the run enters the next layer, at its first tile
+            ++s;
+            sgm = segs[s]; st = st_all[s];
+            lt = 0u; ntl = (sgm.n + TK_TILE - 1u) / TK_TILE; nfull = sgm.n / TK_TILE; lbulk = layer_bulk(sgm);
+            run_g = 0u; run_e = 0u;
+        } else {
+            run_g += (uint32_t)((tg & 0xffffu) + ((tg >> 16) & 0xffffu) + ((tg >> 32) & 0xffffu) + (tg >> 48));
+            run_e += (uint32_t)((te & 0xffffu) + ((te >> 16) & 0xffffu) + ((te >> 32) & 0xffffu) + (te >> 48));
+        }
     }
 }
 
 // Launch with programmatic stream serialization (the kernels call topk_pdl_enter first): the launch latency of the
 // ~20 small kernels of the chain overlaps the tail of their predecessors.  FLASHE_PDL=0 turns it off.
 template <typename... KArgs, typename... Args>
-static cudaError_t topk_launch(void (*kern)(KArgs...), int grid, int block, cudaStream_t cs, Args... args) {
+static cudaError_t topk_launch_s(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t cs, Args... args) {
     static const bool pdl = [] { const char* e = getenv("FLASHE_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.stream = cs;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = cs;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1u : 0u;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t topk_launch(void (*kern)(KArgs...), int grid, int block, cudaStream_t cs, Args... args) {
+    return topk_launch_s(kern, grid, block, 0, cs, args...);
 }
 
 // =================================================================================================
@@ -1252,20 +1353,23 @@ int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_
         if (nctiles) {
             TK_GO(topk_launch(k_topk_sample, grid_cap(info.num_sms, ceil_div_u64(nlines, 8), 8), 256, cs, xw, dseg, ng, nlines, hist));
             TK_GO(topk_launch(k_topk_pick, ng, 1024, cs, hist, st, 0u, dseg, lo));
-            const int gf = grid_occ(info.num_sms, info.device, (const void*)k_topk_filter, ntiles * TK_THREADS, TK_THREADS);   // exactly the resident CTAs: equal runs, one wave
-            TK_GO(topk_launch(k_topk_filter, gf, TK_THREADS, cs, xw, dseg, ng, ntiles, ceil_div_u64(ntiles, (uint64_t)gf), lo, cand_count, cand_key, cand_idx));
+            const size_t f_smem = (size_t)TKF_STAGES * TK_TILE * 4u;
+            { static bool attr_done = false; if (!attr_done && e == cudaSuccess) { e = cudaFuncSetAttribute(k_topk_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem); attr_done = true; } }
+            const int gf = grid_occ(info.num_sms, info.device, (const void*)k_topk_filter, ntiles * TK_THREADS, TK_THREADS, f_smem);   // exactly the resident CTAs: equal runs, one wave
+            TK_GO(topk_launch_s(k_topk_filter, gf, TK_THREADS, f_smem, cs, xw, dseg, ng, ntiles, ceil_div_u64(ntiles, (uint64_t)gf), lo, cand_count, cand_key, cand_idx));
         }
         const uint32_t shifts[3] = {20u, 9u, 0u}, nbits[3] = {11u, 11u, 9u};
+        const uint32_t gcu = nctiles ? (uint32_t)gc : 0u;
         for (int p = 0; p < 3; ++p) {
-            if (nctiles) TK_GO(topk_launch(k_topk_hist<true>, gc, TK_THREADS, cs, cand_key, dseg, ng, nctiles, ctpb, st, cand_count, shifts[p], nbits[p], hist));
-            TK_GO(topk_launch(k_topk_hist<false>, gh, TK_THREADS, cs, xw, dseg, ng, ntiles, tpb, st, cand_count, shifts[p], nbits[p], hist));
+            TK_GO(topk_launch(k_topk_hist, (int)gcu + gh, TK_THREADS, cs, xw, cand_key, dseg, ng, gcu, nctiles, ctpb, ntiles, tpb, st, cand_count, shifts[p], nbits[p], hist));
             TK_GO(topk_launch(k_topk_pick, ng, 1024, cs, hist, st, shifts[p], dseg, null_lo));
         }
-        TK_GO(topk_launch(k_topk_count, gh, TK_THREADS, cs, xw, dseg, ng, ntiles, tpb, st, cand_count, tiles));
-        if (nctiles) TK_GO(topk_launch(k_topk_cand_count, gc, TK_THREADS, cs, cand_key, cand_idx, dseg, ng, nctiles, st, cand_count, tiles));
-        TK_GO(topk_launch(k_topk_scan, ng, 1024, cs, tiles, dseg, ng, ntiles));
-        const int gw = grid_occ(info.num_sms, info.device, (const void*)k_topk_write, ntiles * TK_THREADS, TK_THREADS);
-        TK_GO(topk_launch(k_topk_write, gw, TK_THREADS, cs, xw, residual_in, dseg, ng, ntiles, ceil_div_u64(ntiles, (uint64_t)gw), st, tiles, values_out, index_out, residual_out));
+        const uint32_t gcc = nctiles ? (uint32_t)grid_cap(info.num_sms, 4 * nctiles, 8) : 0u;
+        TK_GO(topk_launch(k_topk_count, (int)gcc + gh, TK_THREADS, cs, xw, cand_key, cand_idx, dseg, ng, gcc, nctiles, ntiles, tpb, st, cand_count, tiles));
+        const size_t w_smem = (size_t)TKW_STAGES * 2u * TK_TILE * 4u;
+        { static bool attr_done = false; if (!attr_done && e == cudaSuccess) { e = cudaFuncSetAttribute(k_topk_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w_smem); attr_done = true; } }
+        const int gw = grid_occ(info.num_sms, info.device, (const void*)k_topk_write, ntiles * TK_THREADS, TK_THREADS, w_smem);
+        TK_GO(topk_launch_s(k_topk_write, gw, TK_THREADS, w_smem, cs, xw, residual_in, dseg, ng, ntiles, ceil_div_u64(ntiles, (uint64_t)gw), st, tiles, values_out, index_out, residual_out));
 #undef TK_GO
         if (e == cudaSuccess) e = cudaGetLastError();
         cudaFreeAsync(ws, cs);

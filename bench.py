@@ -393,6 +393,11 @@ def run_ours(args):
             pm["online_encrypt_gbs"] = n * count * 12 / (pm["online_encrypt_ms"] * 1e-3) / 1e9
             pm["online_encrypt_frac_of_hbm"] = pm["online_encrypt_gbs"] / hbm_peak
             pm["online_encrypt_noise32_frac_of_hbm"] = n * count * 12 / (pm["online_encrypt_noise32_ms"] * 1e-3) / 1e9 / hbm_peak
+            # the same schedule with the 32-bit-resolution generator in the online step (aggregate and decrypt+decode unchanged)
+            ms32 = pm["ms_per_step"] - pm["online_encrypt_ms"] + pm["online_encrypt_noise32_ms"]
+            pm["noise32_ms_per_step"] = ms32
+            pm["noise32_value"] = n * L / (ms32 * 1e-3)
+            pm["noise32_frac_of_hbm_roofline_end_to_end"] = pm["noise32_value"] / (hbm_peak * 1e9 / pm["hbm_bytes_per_client_element"] * world)
         line["variants"] = variants
     if not args.no_cpu_baseline and world == 1:
         os.sched_setaffinity(0, all_cpus)         # the reference's Pool gets every host core again

@@ -251,6 +251,15 @@ __device__ __forceinline__ void ldg_v4(const void* p, uint32_t& a, uint32_t& b, 
 __device__ __forceinline__ void stg_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// 32-byte global accesses (sm_100: LDG.256 / STG.256), streaming (no L1 allocation); the address must be 32-byte aligned
+__device__ __forceinline__ void ldg_v8(const void* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(void* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 // four float64 as ONE 32-byte store (sm_100: STG.256).  A warp then writes 1 KB of whole sectors per instruction — what a
 // peer GPU's memory behind NVLink wants (two 16-byte stores per lane arrive there as half-filled sectors).
 __device__ __forceinline__ void stg_d4(double* p, double a, double b, double c, double d) {

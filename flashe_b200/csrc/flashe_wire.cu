@@ -242,6 +242,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// FB: the element width as a compile-time constant (0 = any width, taken from `bits`): the elements that feed a run of
+// four stream words then land through constant shifts (see the run loop).
+template <int FB>
 __global__ void __launch_bounds__(WB_THREADS)
 k_wire_pack32_bulk(const uint32_t* __restrict__ words, uint64_t count, uint32_t bits, uint32_t pad, uint64_t nwords,
                    uint32_t magic, uint32_t stage_words, uint32_t* __restrict__ out) {
@@ -299,6 +302,30 @@ k_wire_pack32_bulk(const uint32_t* __restrict__ words, uint64_t count, uint32_t 
             // (hi, lo): 64 stream bits, `fill` of them valid from the top.  An element, left-aligned in 32 bits (which
             // also drops anything above its `bits`), lands `fill` bits from the top: two shifts, two ORs.  Staged slots
             // past the vector's end hold zeros, so no bounds test is needed here.
+            if (FB > 0 && rel <= 0) {
+                // Fixed width: the NE elements i .. i+NE-1 cover the run's 128 bits from any start inside element i.  They
+                // are laid end to end in S (constant shifts, resolved at compile time); the run is S shifted left by the
+                // start's offset inside element i: four funnel shifts.  (Bits of S past the run may come from a slot the
+                // tile does not own: they are never selected.)
+                constexpr int NE = (128 + 2 * FB - 2) / (FB > 0 ? FB : 1);
+                constexpr int NW = (NE * FB + 31) / 32;
+                uint32_t S[NW + 1];
+#pragma unroll
+                for (int k = 0; k <= NW; ++k) S[k] = 0u;
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const uint32_t v = FB == 32 ? el[i + e] : (el[i + e] & ((1u << (FB & 31)) - 1u));
+                    const int p = e * FB, w = p >> 5, off = p & 31;
+                    if (off + FB <= 32) S[w] |= v << ((32 - FB - off) & 31);
+                    else { S[w] |= v >> ((off + FB - 32) & 31); S[w + 1] |= v << ((64 - FB - off) & 31); }
+                }
+                const uint32_t sh = (uint32_t)(-rel);                   // 0 <= sh < FB
+                uint32_t r[WB_RUN];
+#pragma unroll
+                for (int k = 0; k < WB_RUN; ++k) r[k] = __byte_perm(__funnelshift_l(S[k + 1], S[k], sh), 0, 0x0123);
+                __stcs(reinterpret_cast<uint4*>(out + w_base + w0), make_uint4(r[0], r[1], r[2], r[3]));
+                continue;
+            }
             uint32_t hi = 0u, lo = 0u, fill = 0u;
             if (rel > 0) fill = (uint32_t)rel;                          // leading zero bits (the stream's padding)
             else if (rel < 0) {                                         // the first element starts before the run: keep its low bits
@@ -1189,13 +1216,14 @@ int flashe_wire_pack(flashe_ctx* ctx, const void* words, int word_bytes, uint64_
             // bulk-staged form: stage = the elements of one tile (+ alignment slack), two stages
             const uint32_t stage_words = (uint32_t)(((WB_WORDS * 32 + bits - 1) / bits + 2 + 8 + 31) & ~31);
             const size_t smem = 2u * (size_t)stage_words * 4u;
-            static bool attr_done = false;
-            if (!attr_done) { FLASHE_CUDA_TRY(cudaFuncSetAttribute(k_wire_pack32_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * ((WB_WORDS * 32 / 8) + 64))); attr_done = true; }
             const uint32_t magic = (uint32_t)((1ull << 32) / (uint64_t)bits) + 1u;      // floor(x / bits) = umulhi(x, magic) for x < 2^17
             const uint64_t nwords = nvec * 4;
-            const int grid = grid_occ(info.num_sms, info.device, (const void*)k_wire_pack32_bulk, ceil_div_u64(nwords, WB_WORDS) * WB_THREADS, WB_THREADS, smem);
-            k_wire_pack32_bulk<<<grid, WB_THREADS, smem, cs>>>(reinterpret_cast<const uint32_t*>(words), count, (uint32_t)bits, pad, nwords, magic,
-                                                                stage_words, reinterpret_cast<uint32_t*>(out));
+            // the shipped widths (20: un-batched ciphertexts, 32: the wide configs, 24) have their own instantiation
+            auto kern = bits == 20 ? k_wire_pack32_bulk<20> : (bits == 32 ? k_wire_pack32_bulk<32> : (bits == 24 ? k_wire_pack32_bulk<24> : k_wire_pack32_bulk<0>));
+            FLASHE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * ((WB_WORDS * 32 / 8) + 64)));
+            const int grid = grid_occ(info.num_sms, info.device, (const void*)kern, ceil_div_u64(nwords, WB_WORDS) * WB_THREADS, WB_THREADS, smem);
+            kern<<<grid, WB_THREADS, smem, cs>>>(reinterpret_cast<const uint32_t*>(words), count, (uint32_t)bits, pad, nwords, magic,
+                                                 stage_words, reinterpret_cast<uint32_t*>(out));
             ++launches;
         } else if (nvec) {
             const int grid = grid_cap(info.num_sms, ceil_div_u64(nvec, WP_THREADS), 8);

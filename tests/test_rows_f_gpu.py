@@ -147,6 +147,27 @@ def test_sparsify_vs_oracle_with_residual_rounds(fb, sizes, sparsity):
         assert np.array_equal(_np(rem_d).view(np.uint32), np.concatenate(rem_o).view(np.uint32))
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_sparsify_many_random_layers(fb, seed):
+    # runs of tiles that cross layer boundaries, partial tiles, aligned and unaligned layer starts, layers on both routes
+    rs = np.random.RandomState(100 + seed)
+    ctx = fb.DeviceContext(KEY, 32)
+    sizes = [int(v) for v in rs.choice([1, 3, 17, 4095, 4096, 4097, 8192, 16384, 16385, 20000, 50001, 131072, 262147], size=24)]
+    if seed == 2:
+        sizes = [s - s % 4 + 4 for s in sizes]              # every layer 16-byte aligned: the ring path everywhere
+    ends = np.cumsum(sizes)
+    sparsity = [0.01, 0.003, 0.02][seed]
+    ks = [O.sparsify_k(sparsity, s) for s in sizes]
+    rem_d, rem_o = None, None
+    for rnd in range(2):
+        layers = [(rs.standard_normal(s) * rs.uniform(1e-3, 10.0)).astype(np.float32) for s in sizes]
+        want_v, rem_o, want_loc, _ = O.sparsify(layers, rem_o, sparsity)
+        vals, idx, rem_d = ctx.topk_sparsify(_dev(np.concatenate(layers)), ends, ks, residual=rem_d)
+        assert np.array_equal(_np(idx), want_loc)
+        assert np.array_equal(_np(vals).view(np.uint32), np.concatenate(want_v).view(np.uint32))
+        assert np.array_equal(_np(rem_d).view(np.uint32), np.concatenate(rem_o).view(np.uint32))
+
+
 def test_sparsify_ties_zeros_and_specials(fb):
     # heavy ties (quantised magnitudes, signed zeros) and inf / nan: stable-argsort order, highest index first
     rs = np.random.RandomState(11)

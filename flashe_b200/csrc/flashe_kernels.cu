@@ -174,12 +174,16 @@ static void make_geom(const flashe_ctx* ctx, const flashe_span* s, uint32_t sup,
     g->S_cnt = unit_of(g->end - 1) - g->S_lo + 1;
 }
 
-// Items per work unit: as large as possible (amortises the per-unit chunk decode) while every warp of
-// the persistent grid still gets at least ~32 units.
+// Items per work unit: as large as possible (amortises the per-unit chunk decode: two 64-bit divisions) while every
+// warp of the persistent grid still gets at least FLASHE_UNITS_PER_WARP units (the last wave is dealt in pieces of
+// sup / 8 items, so the tail does not grow with the unit size).
+#ifndef FLASHE_UNITS_PER_WARP
+#define FLASHE_UNITS_PER_WARP 8       // measured (profiles/r3n_ab_units_per_warp.txt): 32 -> 8 is 4-9 % on the 2.5M-element configs, 4 loses to its tail
+#endif
 static uint32_t pick_sup(const flashe_ctx* ctx, const flashe_span* s, uint64_t rows) {
     const uint64_t items = ceil_div(ceil_div(s->count ? s->count : 1, ctx->m), ITEM_BLOCKS) * (rows ? rows : 1);
     const uint64_t warps = (uint64_t)ctx->num_sms * (STREAM_THREADS / 32);
-    uint64_t sup = items / (warps * 32);
+    uint64_t sup = items / (warps * FLASHE_UNITS_PER_WARP);
     return (uint32_t)(sup < 1 ? 1 : (sup > 32 ? 32 : sup));
 }
 

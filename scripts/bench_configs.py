@@ -215,6 +215,8 @@ def main():
     dense_round("25M elements, 10 clients, int_bits 20 (C3-sized dense round)", 25_000_000, 10, 20, n_jobs, dev)
     dense_round("25M elements, 10 clients, int_bits 24", 25_000_000, 10, 24, n_jobs, dev)
     dense_round("25M elements, 10 clients, int_bits 64", 25_000_000, 10, 64, n_jobs, dev)
+    if "--dense-only" in sys.argv:
+        return
     batched_round(dev, n_jobs=n_jobs)
     precompute_c3(dev, n_jobs=n_jobs)
     sparse_c4(dev, n_jobs=n_jobs)

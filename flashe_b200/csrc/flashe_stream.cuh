@@ -422,7 +422,9 @@ template <int WORDS> struct InType<M_ENCODE, WORDS> { typedef float T; };
 
 // ALIGNED (4-byte words, m = 4 only): the host has checked that every chunk of the span starts on a
 // multiple of 4 elements, so the lane-local path is 128-bit accesses without an alignment switch.
-template <int WORDS, int MMAX, int MODE, bool SHARE, bool ALIGNED, bool N32 = false>
+// M6S (4-byte words, MMAX = 6): m is exactly 6 like in the ALIGNED instantiation, but the chunks may start anywhere
+// (SHIFT6 in the kernel); the purely aligned layout keeps its own instantiation, which is 3 % faster without that code.
+template <int WORDS, int MMAX, int MODE, bool SHARE, bool ALIGNED, bool N32 = false, bool M6S = false>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
 k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab st, const __grid_constant__ Geom g,
          const __grid_constant__ IoDev io, const __grid_constant__ CodecDev cd, const __grid_constant__ NoiseDev nz) {
@@ -437,9 +439,15 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     // m = 4, chunk starts off a 16-byte boundary: instead of 64/32-bit pieces the lanes own the memory-ALIGNED
     // quads and receive the 1-3 mask words that belong to the neighbouring block by shuffle (see fast_item)
     constexpr bool SHIFT_OK = (WORDS == 1 && MMAX == 4 && !ALIGNED && !SHARE && MODE != M_SCATTER);
-    // ALIGNED with MMAX == 6: m is exactly 6 (b = 20, 21: the reference's shipped width) and every chunk starts on a
-    // multiple of 4 elements, so an item is 96 whole 16-byte quads (three per lane) and m is a compile-time constant
-    constexpr bool A6 = (WORDS == 1 && MMAX == 6 && ALIGNED);
+    // ALIGNED or M6S with MMAX == 6: m is exactly 6 (b = 19..21: the reference's shipped width is 20), a compile-time
+    // constant: an item is 96 whole 16-byte quads (three per lane).  ALIGNED: every chunk starts on a multiple of 4
+    // elements; M6S: chunks that start off a 16-byte boundary are handled by SHIFT6 below
+    constexpr bool A6 = (WORDS == 1 && MMAX == 6 && (ALIGNED || M6S));
+    // m = 6, chunk starts off a 16-byte boundary of the buffers (what an arbitrary model length gives: L / n_jobs is
+    // rarely a multiple of 4): the masks already pass through the warp's slab, so they are written there SHIFTED by the
+    // misalignment and read back as the MEMORY-aligned quads; the quad that straddles two items is completed by the
+    // previous item's last words, which stay in the slab (see fast_item).  Same idea as SHIFT_OK, through the slab.
+    constexpr bool SHIFT6 = (WORDS == 1 && MMAX == 6 && M6S && !ALIGNED && !SHARE && MODE != M_SCATTER);
     // 16-byte words (the shipped 120-bit batch mode), m = 1: masks / apply always; encode / decode when the codec
     // batches lanes into the word (cd.bs != 0: encode -> pack -> mask and unmask -> unpack -> decode fused)
     constexpr bool W4_OK = (WORDS == 4 && !SHARE && MODE != M_SCATTER);
@@ -522,7 +530,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
       //  block is one aligned 16-byte pair and one noise pair)
       const bool w2_here = W2_OK && m == 2u && ((it.cb | g.begin) & 1ull) == 0ull;
       const bool w4_here = W4_OK && (!W4_CODEC || w4_batched);
-      if ((QUAD_OK || w4_here || w2_here) && io.quad && !(SHIFT_OK && (g.begin & 1ull))) {
+      if ((QUAD_OK || w4_here || w2_here) && io.quad && !((SHIFT_OK || SHIFT6) && (g.begin & 1ull))) {
           const uint64_t shift = (uint64_t)mm * it.off;             // e0(w) = cb - shift + 64 m w
           const uint64_t full_end = it.cb + (MMAX == 4 ? (it.clen & ~3ull) : (it.clen / mm) * mm);   // end of the chunk's last whole block
           const uint64_t hi_e = (full_end < g.end ? full_end : g.end) + shift;
@@ -548,11 +556,12 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
           // Shifted mode: quads start qr0 elements BEFORE the item (aligned in memory, aligned noise pairs); quad
           // q's first qr0 mask words come from the block before it.  Quad 0 of the run's first item is partial
           // (lane 0 handles its own elements one by one), and so are the qr0 elements after the run's last quad.
-          const bool shifted = SHIFT_OK && qr0 != 0u;
+          const bool shifted6 = SHIFT6 && qr0 != 0u;
+          const bool shifted = (SHIFT_OK && qr0 != 0u) || shifted6;
           const bool run_first = shifted && w == wA, run_last = shifted && w + 1 == wBx;
           // alignment switch of the 16-byte accesses: with SHIFT_OK every quad is aligned (qr0 != 0 => shifted),
           // which removes the 64/32-bit piece code from this instantiation's hot loop
-          const uint32_t qr = SHIFT_OK ? 0u : qr0;
+          const uint32_t qr = (SHIFT_OK || SHIFT6) ? 0u : qr0;
           const uint64_t o0q = shifted ? o0 - qr0 : o0, e0q = shifted ? e0 - qr0 : e0;
           const uint32_t nquads = item_elems >> 2;                  // 16 m; lane owns quads lane + 32 k
           const uint32_t ctrA = ctr0 + lane, ctrB = ctrA + 32u;
@@ -621,10 +630,20 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                   // words (m = 5: odd; m = 6: written as 64-bit pairs, 16 lanes x 24 bytes hit 32 distinct banks):
                   // conflict-free.  Read back as 16-byte quads.
                   __syncwarp();                                      // the previous round's quads have been read
+                  // shifted: word i of the item goes to slab word i + qr0, so that memory-aligned quad q sits at 16 q; the
+                  // first qr0 slab words (the head of quad 0) are the previous item's last qr0 mask words, which lie at
+                  // slab words 384 .. 384 + qr0 - 1 until this item overwrites them
+                  uint32_t carry_w = 0u;
+                  if (SHIFT6 && shifted6 && !run_first && lane < qr0) carry_w = lds32(fslab + 4u * (384u + lane));
+                  if (SHIFT6 && shifted6) __syncwarp();
+                  if (SHIFT6 && shifted6 && !run_first && lane < qr0) sts32(fslab + 4u * lane, carry_w);
 #pragma unroll
                   for (int h = 0; h < NB; ++h) {
-                      const uint32_t a0 = fslab + (lane + 32u * h) * mm * 4u;
-                      if (A6 || mm == 6u) {
+                      const uint32_t a0 = fslab + (lane + 32u * h) * mm * 4u + (SHIFT6 && shifted6 ? 4u * qr0 : 0u);
+                      if (SHIFT6 && shifted6 && (qr0 & 1u)) {        // odd shift: the pairs are not 8-byte aligned
+#pragma unroll
+                          for (int k = 0; k < MMAX; ++k) sts32(a0 + 4u * k, acc[h][k]);
+                      } else if (A6 || mm == 6u) {
 #pragma unroll
                           for (int k = 0; k + 1 < MMAX; k += 2)
                               asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a0 + 4u * k), "r"(acc[h][k]), "r"(acc[h][k + 1]) : "memory");
@@ -671,7 +690,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
               for (int h = 0; h < NQ; ++h) {
                   const uint32_t q = lane + 32u * h;                 // this lane's h-th quad of the item
                   if (MMAX != 4 && !A6 && q >= nquads) break;
-                  if (SHIFT_OK && run_first && q == 0u) continue;    // partial quad: handled element-wise below
+                  if ((SHIFT_OK || SHIFT6) && run_first && q == 0u) continue;    // partial quad: handled element-wise below
                   const uint64_t o = o0q + 4u * q;
                   const uint64_t j = e0q + 4u * q;
                   uint32_t mw[4];
@@ -695,7 +714,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                           for (int k = 0; k < 4; ++k) u[k] = up[k];
                       } else if (N32 && (j & 3ull) == 0ull) {                // 32-bit resolution: the quad is one generator call
                           noise_quad<true>(nz, nz.stream + c, j >> 2, u);
-                      } else if (ALIGNED || SHIFT_OK || (j & 1ull) == 0ull) {   // (SHIFT_OK: quads start at begin + 4k, begin even)
+                      } else if (ALIGNED || SHIFT_OK || SHIFT6 || (j & 1ull) == 0ull) {   // (SHIFT_OK / SHIFT6: quads start at begin + 4k, begin even)
                           noise_pair<N32>(nz, nz.stream + c, j >> 1, u[0], u[1]);
                           noise_pair<N32>(nz, nz.stream + c, (j >> 1) + 1, u[2], u[3]);
                       } else {                      // odd chunk start: the four elements touch three pairs
@@ -731,6 +750,38 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                       }
                       if (io.aux) stg_quad(reinterpret_cast<uint32_t*>(io.aux) + o, qr, pw[0], pw[1], pw[2], pw[3]);
                       stg_quad_f64(io.outf + o, qr, dv);
+                  }
+              }
+              if constexpr (SHIFT6) {
+                  // edges of a shifted m = 6 run, one element at a time: the 4 - qr0 elements before the first item's first
+                  // aligned quad (lane 0) and the last qr0 elements of the last item (lane 31); their masks are in the slab
+                  const bool head = shifted6 && run_first && lane == 0u, tail = shifted6 && run_last && lane == 31u;
+                  if (head || tail) {
+                      const uint32_t i_lo = head ? 0u : 384u - qr0, i_hi = head ? 4u - qr0 : 384u;
+#pragma unroll 1
+                      for (uint32_t i = i_lo; i < i_hi; ++i) {
+                          const uint32_t mword = lds32(fslab + 4u * (i + qr0));
+                          const uint64_t o = o0 + i, j = e0 + i;
+                          if (MODE == M_MASKS) {
+                              reinterpret_cast<uint32_t*>(io.out)[o] = mword & mk32;
+                          } else if (MODE == M_APPLY) {
+                              const uint64_t oc = (uint64_t)c * io.out_stride + o;
+                              reinterpret_cast<uint32_t*>(io.out)[oc] = (reinterpret_cast<const uint32_t*>(io.in)[(uint64_t)c * io.in_stride + o] + mword) & mk32;
+                          } else if (MODE == M_ENCODE) {
+                              const float x = reinterpret_cast<const float*>(io.in)[(uint64_t)c * io.in_stride + o];
+                              const double u = nz.u ? nz.u[(uint64_t)c * nz.u_stride + o] : noise_one<N32>(nz, nz.stream + c, j);
+                              const Seg sg = find_seg(cd, j);
+                              const uint32_t qv = encode_one(x, u, sg, cd.scale);
+                              const uint64_t oc = (uint64_t)c * io.out_stride + o;
+                              if (io.aux) reinterpret_cast<uint32_t*>(io.aux)[oc] = qv;
+                              reinterpret_cast<uint32_t*>(io.out)[oc] = (qv + mword) & mk32;
+                          } else if (MODE == M_DECODE) {
+                              const uint32_t pw = (reinterpret_cast<const uint32_t*>(io.in)[o] + mword) & mk32;
+                              if (io.aux) reinterpret_cast<uint32_t*>(io.aux)[o] = pw;
+                              const Seg sg = find_seg(cd, j);
+                              io.outf[o] = decode_one((double)pw, sg.two_an, cd.den, cd.den_rcp, sg.an);
+                          }
+                      }
                   }
               }
               if constexpr (SHIFT_OK) {
@@ -1215,10 +1266,10 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
 #undef PRE_OF
 }
 
-template <int WORDS, int MMAX, int MODE, bool SHARE, bool ALIGNED = false, bool N32 = false>
+template <int WORDS, int MMAX, int MODE, bool SHARE, bool ALIGNED = false, bool N32 = false, bool M6S = false>
 static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,
                            const NoiseDev& nz, cudaStream_t stream) {
-    auto kern = k_stream<WORDS, MMAX, MODE, SHARE, ALIGNED, N32>;
+    auto kern = k_stream<WORDS, MMAX, MODE, SHARE, ALIGNED, N32, M6S>;
     // the opt-in shared-memory size is a per-device property of the function: set it once per device
     static std::atomic<uint64_t> attr_set{0};
     const uint64_t dev_bit = 1ull << (ctx->device & 63);
@@ -1283,6 +1334,7 @@ static int launch_stream(const flashe_ctx* ctx, const StreamTab& st, const Geom&
         if (ctx->m == 4 && g.aligned4 && io.quad && MODE != M_SCATTER) return launch_stream_t<1, 4, MODE, false, true, N32>(ctx, st, g, io, cd, nz, stream);
         if (ctx->m <= 4) return launch_stream_t<1, 4, MODE, false, false, N32>(ctx, st, g, io, cd, nz, stream);
         if (ctx->m == 6 && g.aligned4 && io.quad && MODE != M_SCATTER) return launch_stream_t<1, 6, MODE, false, true, N32>(ctx, st, g, io, cd, nz, stream);
+        if (ctx->m == 6 && io.quad && MODE != M_SCATTER) return launch_stream_t<1, 6, MODE, false, false, N32, true>(ctx, st, g, io, cd, nz, stream);   // any chunk alignment
         if (ctx->m <= 6) return launch_stream_t<1, 6, MODE, false, false, N32>(ctx, st, g, io, cd, nz, stream);
         return launch_stream_t<1, 16, MODE, false, false, N32>(ctx, st, g, io, cd, nz, stream);
     }

@@ -29,7 +29,15 @@ struct flashe_ctx {
     uint8_t key[32];
     KeySched ks;
     uint32_t* d_te0;   // device copy of the Te0 table (256 words): source of the kernels' shared-memory tables
+    uint32_t* d_tickets;              // (ticket, done) counter pairs of k_stream's dynamic deal, all zero between launches
+    struct flashe_ticket_state* tickets;   // host bookkeeping of the slots (flashe_kernels.cu)
 };
+
+// Counter pair for one k_stream launch on `stream`, or NULL (static deal: FLASHE_DYNAMIC=0, slots exhausted, per-thread
+// default stream).  Launches that may run concurrently never share a slot: eager launches get the slot of their stream
+// (one stream serialises its launches; a dependent launch only draws tickets after griddepcontrol.wait), every launch
+// recorded during stream capture gets a slot of its own for the life of the context.
+uint32_t* flashe_ticket_slot(const flashe_ctx* ctx, cudaStream_t stream);
 
 
 int flashe_check_span(const flashe_span* s);

@@ -187,6 +187,32 @@ static uint32_t pick_sup(const flashe_ctx* ctx, const flashe_span* s, uint64_t r
     return (uint32_t)(sup < 1 ? 1 : (sup > 32 ? 32 : sup));
 }
 
+// ---- ticket slots of the dynamic deal (flashe_internal.h) ---------------------------------------------------------
+#define TICKET_STREAM_SLOTS 64
+#define TICKET_CAPTURE_SLOTS 4032
+struct flashe_ticket_state {
+    std::mutex mu;
+    cudaStream_t streams[TICKET_STREAM_SLOTS];
+    int n_streams = 0, next_capture = 0;
+};
+uint32_t* flashe_ticket_slot(const flashe_ctx* ctx, cudaStream_t stream) {
+    static const bool on = [] { const char* e = getenv("FLASHE_DYNAMIC"); return !(e && e[0] == '0'); }();
+    if (!on || !ctx->d_tickets || !ctx->tickets || stream == cudaStreamPerThread) return nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    flashe_ticket_state* ts = ctx->tickets;
+    std::lock_guard<std::mutex> lk(ts->mu);
+    if (cap != cudaStreamCaptureStatusNone) {
+        if (ts->next_capture >= TICKET_CAPTURE_SLOTS) return nullptr;
+        return ctx->d_tickets + 2 * (TICKET_STREAM_SLOTS + ts->next_capture++);
+    }
+    for (int i = 0; i < ts->n_streams; ++i)
+        if (ts->streams[i] == stream) return ctx->d_tickets + 2 * i;
+    if (ts->n_streams >= TICKET_STREAM_SLOTS) return nullptr;
+    ts->streams[ts->n_streams] = stream;
+    return ctx->d_tickets + 2 * ts->n_streams++;
+}
+
 static int make_streams(const flashe_ctx* ctx, uint32_t iter, const int32_t* prf, const int32_t* sign, int n, StreamTab* st) {
     if (n < 1 || n > MAXS) return fail(FLASHE_EINVAL, "nstreams must be in [1, FLASHE_MAX_STREAMS]");
     if (!prf) return fail(FLASHE_EINVAL, "prf_idx is NULL");
@@ -253,6 +279,15 @@ int flashe_ctx_create(const uint8_t* seed, size_t seed_len, int int_bits, int de
     cudaError_t e = cudaMalloc((void**)&ctx->d_te0, sizeof(haes::te0));
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_te0, haes::te0, sizeof(haes::te0), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(ctx->d_te0); delete ctx; return fail(FLASHE_ECUDA, std::string("Te0 table upload: ") + cudaGetErrorString(e)); }
+    const size_t ticket_bytes = 2 * sizeof(uint32_t) * (TICKET_STREAM_SLOTS + TICKET_CAPTURE_SLOTS);
+    e = cudaMalloc((void**)&ctx->d_tickets, ticket_bytes);
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_tickets, 0, ticket_bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    ctx->tickets = new (std::nothrow) flashe_ticket_state();
+    if (e != cudaSuccess || !ctx->tickets) {
+        cudaFree(ctx->d_tickets); cudaFree(ctx->d_te0); delete ctx->tickets; delete ctx;
+        return fail(FLASHE_ECUDA, std::string("ticket counters: ") + cudaGetErrorString(e));
+    }
     *out = ctx;
     return FLASHE_OK;
 }
@@ -264,7 +299,9 @@ int flashe_ctx_destroy(flashe_ctx* ctx) {
     {
         FlasheDeviceGuard guard(ctx->device);
         if (ctx->d_te0) cudaFree(ctx->d_te0);
+        if (ctx->d_tickets) cudaFree(ctx->d_tickets);
     }
+    delete ctx->tickets;
     delete ctx;
     return FLASHE_OK;
 }

@@ -469,10 +469,17 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     // Programmatic dependent launch: this grid may have been started while the previous kernel of the stream was
     // still draining (launch_stream_t sets the attribute).  Let OUR successor start as early as it can, build the
     // tables (they depend on nothing a predecessor writes), and only then wait for the predecessor's memory.
+#ifdef FLASHE_TRACE
+    unsigned long long tr_begin, tr_wait, tr_edge = 0ull, tr_items = 0ull, tr_nedge = 0ull;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_begin));
+#endif
     asm volatile("griddepcontrol.launch_dependents;");
     fill_tables(io.te0);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
+#ifdef FLASHE_TRACE
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_wait));
+#endif
 
     // slab word index -> byte offset; 4-byte words are skewed by one word per 32 so that the
     // lane-major stores (stride m) and the element-major loads never pile onto one bank
@@ -495,7 +502,33 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
     const uint32_t fine = g.sup < 8u ? g.sup : 8u;
     const uint32_t piece_items = (g.sup + fine - 1u) / fine;
     const uint64_t n_virtual = n_main + (n_units - n_main) * fine;
-    for (uint64_t v = gw; v < n_virtual; v += gstride) {
+    // Dealing.  Static (io.tickets == NULL): warp gw takes v = gw, gw + gstride, ...  Dynamic: the warps claim v from a
+    // ticket counter in global memory, so a warp that drew slow units (edge items of a chunk run 1.6x a whole item; SMs
+    // and warps of one SM do not progress at exactly the same rate) simply claims fewer: measured on the per-warp
+    // timeline, the static deal left 8 % (2.5 M elements x 10 clients) to 20 % (1 M x 3) between the median and the last
+    // warp.  The fine pieces are claimed in REVERSE order: the very last piece of the list is the last chunk's trailing
+    // edge item, which would otherwise be the tail of every launch.  Every warp draws exactly one ticket past the end;
+    // it then bumps the `done` counter, and the last warp to do so zeroes both for the next launch on this slot
+    // (flashe_ticket_slot: one slot per stream, or per captured launch).
+    uint32_t* const tk = io.tickets;
+    uint64_t v_static = gw;
+    bool first_draw = true;
+    const uint64_t rev_lo = n_main > gstride ? n_main : gstride;      // (the first wave is dealt statically, see below)
+    auto next_v = [&]() -> uint64_t {
+        if (tk && !first_draw) {
+            uint32_t k32 = 0u;
+            if (lane == 0u) k32 = atomicAdd(tk, 1u);
+            const uint64_t k = (uint64_t)__shfl_sync(0xffffffffu, k32, 0) + gstride;
+            return k < rev_lo || k >= n_virtual ? k : rev_lo + (n_virtual - 1u - k);
+        }
+        // static deal, and the first unit of every warp under the dynamic deal (2368 warps drawing from one address at
+        // the same instant is 2 us of serialised atomics before any work starts)
+        first_draw = false;
+        const uint64_t v = v_static;
+        v_static += gstride;
+        return v;
+    };
+    for (uint64_t v = next_v(); v < n_virtual; v = next_v()) {
         const bool whole = v < n_main;
         const uint64_t t = whole ? v : n_main + (v - n_main) / fine;
         const uint32_t piece = whole ? 0u : (uint32_t)((v - n_main) % fine);
@@ -1090,10 +1123,25 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
           cached_win = win;
         }
       };
+#ifdef FLASHE_TRACE
+      unsigned long long tr_e0 = 0ull;
+      bool tr_in_edge = false;
+#define TR_EDGE_CLOSE() do { if (tr_in_edge) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); tr_edge += t__ - tr_e0; tr_in_edge = false; } } while (0)
+#else
+#define TR_EDGE_CLOSE() do { } while (0)
+#endif
       for (uint32_t sub = 0; sub < nsub; ++sub, ++it.w) {
+        TR_EDGE_CLOSE();
+#ifdef FLASHE_TRACE
+        ++tr_items;
+#endif
         if (QUAD_OK && it.w >= wf_lo && it.w < wf_hi) { fast_item(it.w); continue; }
         if (W2_OK && it.w >= wf_lo && it.w < wf_hi) { fast_item_w2(it.w); continue; }
         if (w4_here && it.w >= wf_lo && it.w < wf_hi) { fast_item_w4(it.w); continue; }
+#ifdef FLASHE_TRACE
+        ++tr_nedge; tr_in_edge = true;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_e0));
+#endif
         const uint64_t blk0 = it.w ? it.w * ITEM_BLOCKS - it.off : 0;  // first block of the item
         const uint32_t nblk = it.w ? ITEM_BLOCKS : ITEM_BLOCKS - it.off;
         if (blk0 * m >= it.clen) break;                                // past the chunk's last item
@@ -1117,13 +1165,16 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
         // (edge items and layouts without a lane-local path: the window terms are recomputed per call)
         auto stream_into = [&](uint32_t sidx, int sign, word_t (&acc)[NB][MMAX]) {
             uint32_t oa[4], ob[4];
-            WinC wc = {0u, 0u, 0u, 0u};
-            if (fast) wc = window_consts(ks, y, PRE_OF(sidx), (uint32_t)ctr0);
-            if (!onA) return;
-            if (onB && fast) {
-                aes256_x2w(ks, y, st.pre[sidx][0], wc, (uint32_t)ctrA, (uint32_t)ctrB, oa, ob);
-                accumulate_slots<WORDS, MMAX>(oa, g.b, m, sign, acc[0]);
-                accumulate_slots<WORDS, MMAX>(ob, g.b, m, sign, acc[1]);
+            if (fast) {
+                // (warp-uniform) EVERY lane runs both of its blocks, whether the chunk holds them or not - a lane without
+                // block B would otherwise send the warp through the one-block routine as well (both sides of a divergent
+                // branch: twice the lookups) - and, where this path only serves the edge items of a lane-local layout, the
+                // ROLLED form of the rounds: edge items are rare, what they cost is instruction fetch (ncu on a launch of
+                // edge items only: 67 % of the stall samples were no_inst)
+                const WinC wc = window_consts(ks, y, PRE_OF(sidx), (uint32_t)ctr0);
+                aes256_x2w<(QUAD_OK || W2_OK || W4_OK) ? 1 : FLASHE_AES_UNROLL>(ks, y, st.pre[sidx][0], wc, (uint32_t)ctrA, (uint32_t)ctrB, oa, ob);
+                if (onA) accumulate_slots<WORDS, MMAX>(oa, g.b, m, sign, acc[0]);
+                if (onB) accumulate_slots<WORDS, MMAX>(ob, g.b, m, sign, acc[1]);
             } else {
                 const uint32_t prf = st.prf[sidx];
                 if (onA) {
@@ -1262,12 +1313,55 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
             }
         }
       }
+      TR_EDGE_CLOSE();
     }
+    if (tk && lane == 0u) {
+        // this warp has drawn its one ticket past the end; when every warp of the grid has, nobody touches the slot again
+        if (atomicAdd(tk + 1, 1u) == gridDim.x * nwarps - 1u) { tk[0] = 0u; tk[1] = 0u; }
+    }
+#ifdef FLASHE_TRACE
+    if (io.trace && lane == 0u) {
+        unsigned long long tr_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_end));
+        unsigned long long* rec = io.trace + 6ull * ((unsigned long long)blockIdx.x * nwarps + warp);
+        rec[0] = tr_begin; rec[1] = tr_wait; rec[2] = tr_end; rec[3] = tr_edge; rec[4] = tr_items; rec[5] = tr_nedge;
+    }
+#endif
+#undef TR_EDGE_CLOSE
 #undef PRE_OF
 }
 
+#ifdef FLASHE_TRACE
+#include <stdio.h>
+#include <algorithm>
+#include <vector>
+static void flashe_trace_report(const unsigned long long* r, size_t n, int mode, int mmax, int aligned, int m6s, unsigned sup, unsigned long long units) {
+    unsigned long long t0 = ~0ull, tw0 = ~0ull, tend = 0;
+    std::vector<long long> ends, pro;
+    for (size_t i = 0; i < n; ++i) { const unsigned long long* q = r + 6 * i; if (!q[0]) continue; t0 = std::min(t0, q[0]); tw0 = std::min(tw0, q[1]); tend = std::max(tend, q[2]); }
+    unsigned long long items = 0, edges = 0, max_items = 0, max_edge = 0, max_edge_ns = 0, sum_edge_ns = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const unsigned long long* q = r + 6 * i; if (!q[0]) continue;
+        ends.push_back((long long)(q[2] - t0)); pro.push_back((long long)(q[1] - q[0]));
+        items += q[4]; edges += q[5]; max_items = std::max(max_items, q[4]); max_edge = std::max(max_edge, q[5]); max_edge_ns = std::max(max_edge_ns, q[3]); sum_edge_ns += q[3];
+    }
+    std::sort(ends.begin(), ends.end()); std::sort(pro.begin(), pro.end());
+    const size_t k = ends.size();
+    if (!k) return;
+    fprintf(stderr, "[trace] mode %d mmax %d aligned %d m6s %d sup %u units %llu | warps %zu items %llu (max/warp %llu) edge items %llu (max/warp %llu) | span %.1f us, prologue p50 %.1f max %.1f us, first wait-done at %.1f | warp end p0 %.1f p10 %.1f p50 %.1f p90 %.1f p99 %.1f max %.1f us | edge time: mean per edge item %.2f us, max per warp %.1f us\n",
+            mode, mmax, aligned, m6s, sup, units, k, items, max_items, edges, max_edge, (tend - t0) * 1e-3, pro[k / 2] * 1e-3, pro[k - 1] * 1e-3, (tw0 - t0) * 1e-3,
+            ends[0] * 1e-3, ends[k / 10] * 1e-3, ends[k / 2] * 1e-3, ends[k * 9 / 10] * 1e-3, ends[k * 99 / 100] * 1e-3, ends[k - 1] * 1e-3,
+            edges ? sum_edge_ns * 1e-3 / edges : 0.0, max_edge_ns * 1e-3);
+    // the five last warps: items, edge items, edge time
+    std::vector<size_t> idx; for (size_t i = 0; i < n; ++i) if (r[6 * i]) idx.push_back(i);
+    std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return r[6 * a + 2] > r[6 * b + 2]; });
+    for (size_t j = 0; j < 5 && j < idx.size(); ++j) { const unsigned long long* q = r + 6 * idx[j];
+        fprintf(stderr, "[trace]   late warp cta %zu w %zu: end %.1f us items %llu edge %llu edge time %.1f us\n", idx[j] / 16, idx[j] % 16, (q[2] - t0) * 1e-3, q[4], q[5], q[3] * 1e-3); }
+}
+#endif
+
 template <int WORDS, int MMAX, int MODE, bool SHARE, bool ALIGNED = false, bool N32 = false, bool M6S = false>
-static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io, const CodecDev& cd,
+static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geom& g, const IoDev& io_in, const CodecDev& cd,
                            const NoiseDev& nz, cudaStream_t stream) {
     auto kern = k_stream<WORDS, MMAX, MODE, SHARE, ALIGNED, N32, M6S>;
     // the opt-in shared-memory size is a per-device property of the function: set it once per device
@@ -1277,7 +1371,7 @@ static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geo
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_set.fetch_or(dev_bit, std::memory_order_release);
     }
-    const uint64_t items = (st.batch && !io.share) ? g.S_cnt * io.n_clients : g.S_cnt;
+    const uint64_t items = (st.batch && !io_in.share) ? g.S_cnt * io_in.n_clients : g.S_cnt;
     if (items == 0) return FLASHE_OK;
     const int slab_bytes = (2 * 32 * MMAX + 2 + (WORDS == 1 ? 2 * MMAX + 1 : 0)) * WORDS * 4;
     int threads = STREAM_THREADS;
@@ -1295,6 +1389,34 @@ static int launch_stream_t(const flashe_ctx* ctx, const StreamTab& st, const Geo
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1u : 0u;
+    IoDev io_t = io_in;
+    // Dynamic dealing: the ticket (units x <= 8 pieces + one per warp) must fit 32 bits, and the launch must be long
+    // enough for the re-balancing to pay for the draws (FLASHE_DYNAMIC_MIN_ITEMS warp items per warp; below that the
+    // static deal is as good: with a handful of items per warp the tail is one item either way)
+    static const uint64_t dyn_min_items = [] { const char* e = getenv("FLASHE_DYNAMIC_MIN_ITEMS"); return (uint64_t)(e ? atoi(e) : 6); }();
+    const bool dyn_ok = items * 8u + blocks * (uint64_t)wpb < 0xfffffff0ull && items * g.sup >= dyn_min_items * blocks * (uint64_t)wpb;
+    io_t.tickets = dyn_ok ? flashe_ticket_slot(ctx, stream) : nullptr;
+    const IoDev& io = io_t;
+#ifdef FLASHE_TRACE
+    // tuning builds only: per-warp timeline of this launch, summarised on stderr (FLASHE_TRACE_PRINT=1)
+    static const bool tr_print = [] { const char* e = getenv("FLASHE_TRACE_PRINT"); return e && e[0] == '1'; }();
+    cudaStreamCaptureStatus tr_cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &tr_cap);
+    if (tr_print && tr_cap == cudaStreamCaptureStatusNone) {
+        static unsigned long long* tr_host = nullptr;
+        const size_t n_rec = (size_t)blocks * wpb;
+        if (!tr_host) CUDA_TRY(cudaHostAlloc((void**)&tr_host, 6 * sizeof(unsigned long long) * 148 * 16 * 2, cudaHostAllocMapped));
+        memset(tr_host, 0, 6 * sizeof(unsigned long long) * n_rec);
+        IoDev io2 = io;
+        CUDA_TRY(cudaHostGetDevicePointer((void**)&io2.trace, tr_host, 0));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ctx->ks, st, g, io2, cd, nz));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        flashe_trace_report(tr_host, n_rec, MODE, MMAX, (int)ALIGNED, (int)M6S, (unsigned)g.sup, (unsigned long long)items);
+        flashe_count_launches(1);
+        return FLASHE_OK;
+    }
+#endif
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ctx->ks, st, g, io, cd, nz));
     flashe_count_launches(1);
     CUDA_TRY(cudaGetLastError());

@@ -52,6 +52,10 @@ struct IoDev {
     uint64_t dense_len;                     // scatter: words in the dense target (indices outside are skipped)
     uint64_t elem0;                         // lane batching: first element of the shard's first word (x / u / q / outf offsets)
     const uint32_t* te0;                    // Te0 table in global memory (flashe_ctx::d_te0), source of the shared-memory tables
+    uint32_t* tickets;                      // (ticket, done) counters of the dynamic deal (flashe_ticket_slot), NULL: static deal
+#ifdef FLASHE_TRACE
+    unsigned long long* trace;              // tuning builds only (scripts/build_variant.sh trace -DFLASHE_TRACE=1): per-warp timeline
+#endif
 };
 
 enum { M_MASKS = 0, M_APPLY = 1, M_ENCODE = 2, M_DECODE = 3, M_SCATTER = 4 };

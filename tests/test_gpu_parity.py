@@ -488,6 +488,58 @@ def test_cuda_graph_replay_of_a_round(fb):
     assert np.array_equal(got_out.view(np.uint64), O.unquantize(p_want, 0.4, 16, n).view(np.uint64))
 
 
+def test_dynamic_deal_concurrent_streams_and_graphs(fb):
+    """The stream kernel's warps draw their work units from a ticket counter (one slot per stream, one per captured
+    launch, reset by the launch's last warp).  Launches that overlap in time - two streams, two graphs replayed on two
+    streams, the same context - must not disturb each other, and a slot must come back clean launch after launch:
+    every result equals the one a lone launch on the default stream gave."""
+    L, n, bits, n_jobs, it = 400_003, 4, 20, 16, 5
+    ctx = ctx_for(fb, bits)
+    span = fb.VectorSpan(L, n_jobs)
+    codec = fb.CodecSpec(alpha=0.4, element_bits=16, n_clients=n)
+    noise = fb.NoiseSpec(seed=3, stream=0)
+    x = _dev((np.random.RandomState(8).standard_normal((n, L)) * 0.2).astype(np.float32))
+    want_ct = ctx.encode_encrypt_batch(it, 0, fb.SCHEME_DOUBLE, x, codec, noise, span)
+    want_agg = ctx.aggregate(want_ct, fb.AGG_ELEMENTWISE)
+    want_out = ctx.decrypt_decode(it, [n], [0], want_agg, codec, span)
+    q = O.quantize(_np(x[1]), _np(ctx.rng_uniform(3, 1, 0, L)), 0.4, 16)
+    assert np.array_equal(_np(want_ct[1]), O.encrypt(KEY, bits, n_jobs, it, 1, "double", q))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    bufs = [(ctx.empty_words(L, rows=n), ctx.empty_words(L), torch.empty(L, dtype=torch.float64, device="cuda")) for _ in streams]
+
+    def rnd(k):
+        cts, agg, out = bufs[k]
+        ctx.encode_encrypt_batch(it, 0, fb.SCHEME_DOUBLE, x, codec, noise, span, out=cts)
+        ctx.aggregate(cts, fb.AGG_ELEMENTWISE, out=agg)
+        ctx.decrypt_decode(it, [n], [0], agg, codec, span, out=out)
+
+    def check():
+        torch.cuda.synchronize()
+        for cts, agg, out in bufs:
+            assert torch.equal(cts.view(torch.int32), want_ct.view(torch.int32))
+            assert torch.equal(out.view(torch.int64), want_out.view(torch.int64))
+            cts.zero_(); out.zero_()
+        torch.cuda.synchronize()
+
+    for _ in range(6):                                   # eager launches interleaved over three streams
+        for k, s in enumerate(streams):
+            with torch.cuda.stream(s):
+                rnd(k)
+    check()
+    replays = []
+    for k, s in enumerate(streams):                      # one graph per stream, replayed concurrently
+        with torch.cuda.stream(s):
+            replays.append(ctx.capture(lambda k=k: rnd(k)))
+    check()
+    for _ in range(6):
+        for k, s in enumerate(streams):
+            with torch.cuda.stream(s):
+                replays[k]()
+        rnd(0)                                           # ... with eager launches on the default stream in between
+    check()
+
+
 def test_decode_into_an_exported_peer_buffer(fb):
     """sharding.PeerGather on one rank: the decode kernel writes into memory allocated by flashe_peer_alloc (the
     buffer other GPUs would map and write into over NVLink; scripts/multi_gpu_check.py does that under torchrun)

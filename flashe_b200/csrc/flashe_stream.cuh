@@ -51,12 +51,25 @@ __device__ __forceinline__ uint32_t smem_window_base() {
 }
 
 __device__ __forceinline__ void fill_tables(const uint32_t* __restrict__ g_te0) {   // g_te0: Te0, 256 words (flashe_ctx::d_te0)
-    // word w of the 128 KB region: region = w>>14, entry = (w>>6)&255, table-in-region = (w>>5)&1
-    for (uint32_t w = threadIdx.x; w < 32768u; w += blockDim.x) {
-        uint32_t t = ((w >> 14) << 1) | ((w >> 5) & 1u);
-        uint32_t v = __ldg(g_te0 + ((w >> 6) & 255u));
-        v = __funnelshift_r(v, v, 8 * t);  // Te_t = ror(Te0, 8t)
-        sts32(TAB_BASE + 4u * w, v);
+    // One warp store writes the 32 replicas (128 bytes) of one (entry, table) pair.  A warp owns 256 / nwarps consecutive
+    // entries: ONE coalesced load brings them in (lane i holds entry e0 + i), each is broadcast by shuffle and stored
+    // four times, rotated (Te_t = ror(Te0, 8 t)).  The per-word loop this replaces paid one dependent global load per
+    // store: 3.3 us per launch on the per-warp timeline, never hidden - a k_stream CTA owns its SM's whole register
+    // file, so a dependent launch cannot become resident next to its predecessor.
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t per = (256u + nwarps - 1u) / nwarps;          // entries per warp: 16 with 16 warps (<= 32 for >= 8 warps)
+    for (uint32_t base = warp * per; base < 256u && base < (warp + 1u) * per; base += 32u) {
+        const uint32_t n_here = min(min(32u, 256u - base), (warp + 1u) * per - base);
+        const uint32_t mine = lane < n_here ? __ldg(g_te0 + base + lane) : 0u;
+#pragma unroll 4
+        for (uint32_t i = 0; i < n_here; ++i) {
+            const uint32_t v = __shfl_sync(0xffffffffu, mine, i);
+            const uint32_t a = TAB_BASE + (base + i) * 256u + lane * 4u;
+            sts32(a, v);                                              // T0: region 0, first half of the entry's row
+            sts32(a + 128u, __funnelshift_r(v, v, 8));                // T1
+            sts32(a + 0x10000u, __funnelshift_r(v, v, 16));           // T2: region 1
+            sts32(a + 0x10080u, __funnelshift_r(v, v, 24));           // T3
+        }
     }
 }
 
@@ -786,13 +799,16 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                   }
               }
               if constexpr (SHIFT6) {
-                  // edges of a shifted m = 6 run, one element at a time: the 4 - qr0 elements before the first item's first
-                  // aligned quad (lane 0) and the last qr0 elements of the last item (lane 31); their masks are in the slab
-                  const bool head = shifted6 && run_first && lane == 0u, tail = shifted6 && run_last && lane == 31u;
-                  if (head || tail) {
-                      const uint32_t i_lo = head ? 0u : 384u - qr0, i_hi = head ? 4u - qr0 : 384u;
-#pragma unroll 1
-                      for (uint32_t i = i_lo; i < i_hi; ++i) {
+                  // edges of a shifted m = 6 run, one element per LANE: the 4 - qr0 elements before the first item's first
+                  // aligned quad (lanes 0 ..) and the last qr0 elements of the last item (lanes .. 31); their masks are in the
+                  // slab, so any lane can take one (a single lane looping over them was 2 x 3 dependent passes of noise +
+                  // encode per run: 7 % of a launch whose runs are three items long)
+                  uint32_t i_edge = 0xffffffffu;
+                  if (shifted6 && run_first && lane < 4u - qr0) i_edge = lane;
+                  else if (shifted6 && run_last && lane >= 32u - qr0) i_edge = 352u + lane;      // 384 - qr0 + (lane - (32 - qr0))
+                  if (i_edge != 0xffffffffu) {
+                      {
+                          const uint32_t i = i_edge;
                           const uint32_t mword = lds32(fslab + 4u * (i + qr0));
                           const uint64_t o = o0 + i, j = e0 + i;
                           if (MODE == M_MASKS) {

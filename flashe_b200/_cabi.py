@@ -75,6 +75,7 @@ SIGNATURES = {
     "flashe_sparse_expand": (_int, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "flashe_sparse_sum": (_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_u64), _vp, _int, _u64, _vp, _vp]),
     "flashe_sparse_apply_masks": (_int, [_vp, _u32, _i32p, _i32p, _int, _spanp, _vp, _vp, _u64, _vp]),
+    "flashe_sparse_apply_masks_batch": (_int, [_vp, _u32, _i32p, _int, _int, C.POINTER(_u64), _u32, C.POINTER(_vp), _vp, _u64, _vp]),
     "flashe_sparse_overlap": (_int, [_vp, C.POINTER(_vp), C.POINTER(_u64), _int, _u64, C.POINTER(_u64), _vp]),
     "flashe_wire_nbytes": (_int, [_int, _u64, C.POINTER(_u64)]),
     "flashe_wire_pack": (_int, [_vp, _vp, _int, _u64, _int, _vp, _vp]),

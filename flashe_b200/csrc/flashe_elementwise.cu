@@ -657,11 +657,210 @@ __global__ void k_scatter_add(const typename Word<WORDS>::T* __restrict__ compac
     }
 }
 
+// ---- the arbiter's sparse sum and the overlap counts by TILES of the dense vector ----------------------------------
+// The index lists are sorted, so the entries of one client that fall into a tile of the dense vector are one
+// contiguous run of its list.  k_sparse_splits finds the runs (one binary search per client and tile boundary);
+// k_sparse_sum_tiled then builds every tile of the output in shared memory - start from the sum of the zero words, add
+// (compact - zero) for the entries of all clients with shared-memory atomics - and writes it ONCE, coalesced: total
+// words out + sum k_c (index + word) in, instead of one read-modify-write of a 32-byte sector per entry and one launch
+// per client (32 clients x 1 % of 50 M: 0.62 ms -> see profiles/).  The overlap counts of dynamic_masking use the same
+// runs: an entry of client i searches only client i+1's run of the same tile.
+struct SparseClient { const void* compact; const int64_t* index; uint64_t k; uint64_t zero_lo, zero_hi; };
+#define SPARSE_TILE_BYTES 32768u
+
+__global__ void k_sparse_splits(const SparseClient* __restrict__ cl, int n, uint64_t total, uint32_t tile_log2, uint64_t n_tiles,
+                                uint32_t* __restrict__ splits) {
+    const uint64_t per = n_tiles + 1, all = per * (uint64_t)n;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < all; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t c = g / per, t = g - c * per;
+        const int64_t bound = t == n_tiles ? (int64_t)total : (int64_t)(t << tile_log2);    // first index of tile t
+        const int64_t* __restrict__ idx = cl[c].index;
+        uint64_t lo = 0, hi = cl[c].k;
+        while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (__ldg(idx + mid) < bound) lo = mid + 1; else hi = mid; }
+        splits[g] = (uint32_t)lo;
+    }
+}
+
+template <int WORDS> __device__ __forceinline__ void smem_add(typename Word<WORDS>::T* p, typename Word<WORDS>::T v);
+template <> __device__ __forceinline__ void smem_add<1>(uint32_t* p, uint32_t v) { atomicAdd(p, v); }
+template <> __device__ __forceinline__ void smem_add<2>(uint64_t* p, uint64_t v) { atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+template <> __device__ __forceinline__ void smem_add<4>(u128* p, u128 v) { *p = Word<4>::add(*p, v); }   // (one client at a time, see below)
+
+template <int WORDS>
+__global__ void __launch_bounds__(256)
+k_sparse_sum_tiled(const SparseClient* __restrict__ cl, int n, const uint32_t* __restrict__ splits, uint64_t total, uint64_t n_tiles,
+                   typename Word<WORDS>::T zsum, uint32_t b, typename Word<WORDS>::T* dense, int inplace, int subtract) {
+    // inplace: the tile starts from what `dense` holds (flashe_sparse_apply_masks_batch) instead of the sum of the zero
+    // words; subtract: the entries are taken away (compact = masks, zero words unused)
+    typedef Word<WORDS> WT;
+    typedef typename WT::T word_t;
+    constexpr uint32_t TILE = SPARSE_TILE_BYTES / (4u * WORDS);
+    __shared__ __align__(16) word_t acc[TILE];
+    const word_t mk = WT::mask(b);
+    const uint64_t per = n_tiles + 1;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint64_t a = t * TILE;
+        const uint32_t cnt = (uint32_t)(total - a < TILE ? total - a : TILE);
+        if (inplace) { for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) acc[i] = dense[a + i]; }
+        else { for (uint32_t i = threadIdx.x; i < TILE; i += blockDim.x) acc[i] = zsum; }
+        __syncthreads();
+        if (WORDS <= 2) {
+            // one warp per client, all clients at once: entries of different clients may meet in a word (atomics)
+            for (int c = (int)warp; c < n; c += (int)nwarps) {
+                const uint32_t p0 = __ldg(splits + (uint64_t)c * per + t), p1 = __ldg(splits + (uint64_t)c * per + t + 1);
+                if (p0 >= p1) continue;
+                const word_t* __restrict__ cp = reinterpret_cast<const word_t*>(cl[c].compact);
+                const int64_t* __restrict__ ix = cl[c].index;
+                word_t z; if constexpr (WORDS == 1) z = (uint32_t)cl[c].zero_lo & mk; else if constexpr (WORDS == 2) z = cl[c].zero_lo & mk;
+                for (uint32_t p = p0 + lane; p < p1; p += 32u)
+                    smem_add<WORDS>(&acc[(uint32_t)((uint64_t)__ldg(ix + p) - a)], subtract ? WT::sub(WT::zero(), cp[p]) : WT::sub(cp[p], z));
+            }
+        } else {
+            // 16-byte words have no atomic: the clients take turns (a client's indices are unique)
+            for (int c = 0; c < n; ++c) {
+                const uint32_t p0 = __ldg(splits + (uint64_t)c * per + t), p1 = __ldg(splits + (uint64_t)c * per + t + 1);
+                if (p0 < p1) {
+                    const word_t* __restrict__ cp = reinterpret_cast<const word_t*>(cl[c].compact);
+                    const int64_t* __restrict__ ix = cl[c].index;
+                    word_t z;
+                    if constexpr (WORDS == 4) { z.lo = cl[c].zero_lo; z.hi = cl[c].zero_hi; z = WT::band(z, mk); }
+                    for (uint32_t p = p0 + threadIdx.x; p < p1; p += blockDim.x)
+                        smem_add<WORDS>(&acc[(uint32_t)((uint64_t)__ldg(ix + p) - a)], subtract ? WT::sub(WT::zero(), cp[p]) : WT::sub(cp[p], z));
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+        word_t* out = dense + a;
+        if ((reinterpret_cast<uintptr_t>(out) & 15u) == 0u) {             // (block-uniform) whole 16-byte stores
+            constexpr uint32_t PER16 = 4u / WORDS;                        // words per 16 bytes
+            const uint32_t nvec = cnt / PER16;
+            const uint4* av = reinterpret_cast<const uint4*>(acc);
+            for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+                uint4 v = av[i];
+                if constexpr (WORDS == 1) { const uint32_t m = mk; v.x &= m; v.y &= m; v.z &= m; v.w &= m; }
+                else if constexpr (WORDS == 2) { const uint64_t m = mk; v.x &= (uint32_t)m; v.y &= (uint32_t)(m >> 32); v.z &= (uint32_t)m; v.w &= (uint32_t)(m >> 32); }
+                else { v.x &= (uint32_t)mk.lo; v.y &= (uint32_t)(mk.lo >> 32); v.z &= (uint32_t)mk.hi; v.w &= (uint32_t)(mk.hi >> 32); }
+                reinterpret_cast<uint4*>(out)[i] = v;
+            }
+            for (uint32_t i = nvec * PER16 + threadIdx.x; i < cnt; i += blockDim.x) out[i] = WT::band(acc[i], mk);
+        } else {
+            for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) out[i] = WT::band(acc[i], mk);
+        }
+        __syncthreads();
+    }
+}
+
+// overlap[i] += number of entries of client i found in client i+1's run of the same tile (blockIdx.y = i)
+__global__ void __launch_bounds__(256)
+k_sparse_overlap_tiled(const SparseClient* __restrict__ cl, const uint32_t* __restrict__ splits, uint64_t total, uint32_t tile_log2,
+                       uint64_t n_tiles, unsigned long long* __restrict__ out) {
+    const int i = (int)blockIdx.y;
+    const int64_t* __restrict__ a = cl[i].index;
+    const int64_t* __restrict__ bq = cl[i + 1].index;
+    const uint64_t ka = cl[i].k, kb = cl[i + 1].k;
+    const uint32_t* __restrict__ sp = splits + (uint64_t)(i + 1) * (n_tiles + 1);
+    unsigned long long local = 0;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < ka; p += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t v = a[p];
+        uint64_t lo = 0, hi = kb;                                          // (values outside [0, total): the whole list, as before)
+        if (v >= 0 && (uint64_t)v < total) { const uint64_t t = (uint64_t)v >> tile_log2; lo = __ldg(sp + t); hi = __ldg(sp + t + 1); }
+        const uint64_t end = hi;
+        while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (__ldg(bq + mid) < v) lo = mid + 1; else hi = mid; }
+        local += (lo < end && __ldg(bq + lo) == v) ? 1ull : 0ull;
+    }
+    for (int dlt = 16; dlt > 0; dlt >>= 1) local += __shfl_down_sync(0xffffffffu, local, dlt);
+    if ((threadIdx.x & 31u) == 0 && local) atomicAdd(out + i, local);
+}
+
+// Uploads the client table and computes the runs; *ws_out (one stream-ordered allocation) holds both.
+static int sparse_prepare(flashe_ctx* ctx, const void* const* compacts, const int64_t* const* indexes, const uint64_t* ks, const void* zero_words,
+                          int word_bytes, int n, uint64_t total, uint32_t tile_log2, cudaStream_t cs, uint8_t** ws_out, SparseClient** cl_out,
+                          uint32_t** splits_out, uint64_t* n_tiles_out) {
+    const uint64_t n_tiles = (total + (1ull << tile_log2) - 1) >> tile_log2;
+    std::vector<SparseClient> h((size_t)n);
+    for (int c = 0; c < n; ++c) {
+        memset(&h[c], 0, sizeof(SparseClient));
+        h[c].compact = compacts ? compacts[c] : nullptr; h[c].index = indexes[c]; h[c].k = ks[c];
+        if (zero_words) memcpy(&h[c].zero_lo, (const uint8_t*)zero_words + (size_t)c * word_bytes, (size_t)word_bytes);
+    }
+    const size_t cl_bytes = (sizeof(SparseClient) * (size_t)n + 255) & ~(size_t)255;
+    const size_t sp_bytes = sizeof(uint32_t) * (size_t)n * (size_t)(n_tiles + 1);
+    uint8_t* ws = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&ws, cl_bytes + sp_bytes, cs));
+    cudaError_t e = cudaMemcpyAsync(ws, h.data(), sizeof(SparseClient) * (size_t)n, cudaMemcpyHostToDevice, cs);   // (pageable source: staged before the call returns)
+    if (e != cudaSuccess) { cudaFreeAsync(ws, cs); return fail(FLASHE_ECUDA, std::string("sparse client table: ") + cudaGetErrorString(e)); }
+    SparseClient* cl = reinterpret_cast<SparseClient*>(ws);
+    uint32_t* splits = reinterpret_cast<uint32_t*>(ws + cl_bytes);
+    k_sparse_splits<<<GRID_OCC(ctx, k_sparse_splits, (uint64_t)n * (n_tiles + 1), 256), 256, 0, cs>>>(cl, n, total, tile_log2, n_tiles, splits);
+    count_launch();
+    *ws_out = ws; *cl_out = cl; *splits_out = splits; *n_tiles_out = n_tiles;
+    return FLASHE_OK;
+}
+
+template <int WORDS>
+static int sparse_sum_tiled_t(flashe_ctx* ctx, const void* const* compacts, const int64_t* const* indexes, const uint64_t* ks,
+                              const void* zero_words, int n, uint64_t total, void* dense_out, cudaStream_t cs) {
+    typedef Word<WORDS> WT;
+    typedef typename WT::T word_t;
+    constexpr uint32_t TILE = SPARSE_TILE_BYTES / (4u * WORDS);
+    uint32_t tile_log2 = 0; while ((1u << tile_log2) < TILE) ++tile_log2;
+    std::vector<word_t> zeros((size_t)n);
+    memcpy(zeros.data(), zero_words, sizeof(word_t) * (size_t)n);
+    const word_t mk = WT::mask((uint32_t)ctx->int_bits);
+    word_t zsum = WT::zero();
+    for (int c = 0; c < n; ++c) zsum = WT::band(WT::add(zsum, WT::band(zeros[c], mk)), mk);
+    uint8_t* ws; SparseClient* cl; uint32_t* splits; uint64_t n_tiles;
+    int rc = sparse_prepare(ctx, compacts, indexes, ks, zero_words, 4 * WORDS, n, total, tile_log2, cs, &ws, &cl, &splits, &n_tiles);
+    if (rc) return rc;
+    const int grid = (int)(n_tiles < (uint64_t)ctx->num_sms * 32 ? n_tiles : (uint64_t)ctx->num_sms * 32);
+    k_sparse_sum_tiled<WORDS><<<grid, 256, 0, cs>>>(cl, n, splits, total, n_tiles, zsum, (uint32_t)ctx->int_bits, (word_t*)dense_out, 0, 0);
+    count_launch();
+    cudaFreeAsync(ws, cs);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+
+// dense[index_c[p]] += / -= compact_c[p] (mod 2^b) for every client, in place, by tiles (flashe_internal.h)
+template <int WORDS>
+static int sparse_accumulate_t(flashe_ctx* ctx, const void* const* compacts, const int64_t* const* indexes, const uint64_t* ks, int n,
+                               int subtract, uint64_t total, void* dense, cudaStream_t cs) {
+    typedef typename Word<WORDS>::T word_t;
+    constexpr uint32_t TILE = SPARSE_TILE_BYTES / (4u * WORDS);
+    uint32_t tile_log2 = 0; while ((1u << tile_log2) < TILE) ++tile_log2;
+    uint8_t* ws; SparseClient* cl; uint32_t* splits; uint64_t n_tiles;
+    int rc = sparse_prepare(ctx, compacts, indexes, ks, nullptr, 4 * WORDS, n, total, tile_log2, cs, &ws, &cl, &splits, &n_tiles);
+    if (rc) return rc;
+    const int grid = (int)(n_tiles < (uint64_t)ctx->num_sms * 32 ? n_tiles : (uint64_t)ctx->num_sms * 32);
+    k_sparse_sum_tiled<WORDS><<<grid, 256, 0, cs>>>(cl, n, splits, total, n_tiles, Word<WORDS>::zero(), (uint32_t)ctx->int_bits, (word_t*)dense, 1, subtract);
+    count_launch();
+    cudaFreeAsync(ws, cs);
+    CUDA_TRY(cudaGetLastError());
+    return FLASHE_OK;
+}
+int flashe_sparse_accumulate_tiled(flashe_ctx* ctx, const void* const* compacts, const int64_t* const* indexes, const uint64_t* ks, int n,
+                                   int subtract, uint64_t total, void* dense, cudaStream_t cs) {
+    if (ctx->words == 1) return sparse_accumulate_t<1>(ctx, compacts, indexes, ks, n, subtract, total, dense, cs);
+    if (ctx->words == 2) return sparse_accumulate_t<2>(ctx, compacts, indexes, ks, n, subtract, total, dense, cs);
+    return sparse_accumulate_t<4>(ctx, compacts, indexes, ks, n, subtract, total, dense, cs);
+}
+
 template <int WORDS>
 static int sparse_sum_t(flashe_ctx* ctx, const void* const* compacts, const int64_t* const* indexes, const uint64_t* ks,
                         const void* zero_words, int n, uint64_t total, void* dense_out, cudaStream_t cs) {
     typedef Word<WORDS> WT;
     typedef typename WT::T word_t;
+    // the tiled form needs 32-bit list positions and cannot be recorded into a CUDA graph (it uploads a table);
+    // FLASHE_SPARSE_TILED=0 keeps the per-client scatter-adds (A/B measurements)
+    {
+        static const bool tiled = [] { const char* e = getenv("FLASHE_SPARSE_TILED"); return !(e && e[0] == '0'); }();
+        bool ok = tiled;
+        for (int c = 0; c < n; ++c) ok = ok && ks[c] < (1ull << 32);
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(cs, &cap) != cudaSuccess) { cudaGetLastError(); ok = false; }
+        if (ok && cap == cudaStreamCaptureStatusNone) return sparse_sum_tiled_t<WORDS>(ctx, compacts, indexes, ks, zero_words, n, total, dense_out, cs);
+    }
     std::vector<word_t> zeros((size_t)n);                              // the caller's buffer need not be aligned
     memcpy(zeros.data(), zero_words, sizeof(word_t) * (size_t)n);
     const word_t mk = WT::mask((uint32_t)ctx->int_bits);
@@ -1103,6 +1302,23 @@ int flashe_sparse_overlap(flashe_ctx* ctx, const int64_t* const* index, const ui
     unsigned long long* d = nullptr;
     CUDA_TRY(cudaMallocAsync((void**)&d, sizeof(unsigned long long) * (size_t)(n - 1), cs));
     cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long) * (size_t)(n - 1), cs);
+    // one launch for all pairs, every search confined to the neighbour's run of the entry's tile (k_sparse_overlap_tiled)
+    static const bool tiled = [] { const char* ev = getenv("FLASHE_SPARSE_TILED"); return !(ev && ev[0] == '0'); }();
+    bool tiled_ok = tiled && total > 0 && e == cudaSuccess;
+    uint64_t kmax = 0;
+    for (int i = 0; i < n; ++i) { tiled_ok = tiled_ok && k[i] < (1ull << 32) && (k[i] == 0 || index[i]); if (k[i] > kmax) kmax = k[i]; }
+    if (tiled_ok && kmax) {
+        const uint32_t tile_log2 = 13;
+        uint8_t* ws; SparseClient* cl; uint32_t* splits; uint64_t n_tiles;
+        int rc = sparse_prepare(ctx, nullptr, index, k, nullptr, 0, n, total, tile_log2, cs, &ws, &cl, &splits, &n_tiles);
+        if (rc) { cudaFreeAsync(d, cs); return rc; }
+        const int gx = GRID_OCC(ctx, k_sparse_overlap_tiled, kmax, 256);
+        const int per_pair = gx / (n - 1) > 0 ? gx / (n - 1) : 1;            // the pairs share the resident CTAs
+        k_sparse_overlap_tiled<<<dim3((unsigned)per_pair, (unsigned)(n - 1)), 256, 0, cs>>>(cl, splits, total, tile_log2, n_tiles, d);
+        count_launch();
+        e = cudaGetLastError();
+        cudaFreeAsync(ws, cs);
+    } else
     for (int i = 0; e == cudaSuccess && i + 1 < n; ++i) {
         if (k[i] == 0 || k[i + 1] == 0) continue;
         k_overlap<<<GRID_OCC(ctx, k_overlap, k[i], 256), 256, 0, cs>>>(index[i], k[i], index[i + 1], k[i + 1], d + i);

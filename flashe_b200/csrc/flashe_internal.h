@@ -41,6 +41,10 @@ uint32_t* flashe_ticket_slot(const flashe_ctx* ctx, cudaStream_t stream);
 
 
 int flashe_check_span(const flashe_span* s);
+// flashe_elementwise.cu: dense[index_c[p]] += (subtract: -=) compact_c[p] mod 2^int_bits for every client c, in place, built
+// tile by tile in shared memory (index lists sorted unique, ks[c] < 2^32; not capturable: uploads a table)
+int flashe_sparse_accumulate_tiled(flashe_ctx* ctx, const void* const* compacts, const int64_t* const* indexes, const uint64_t* ks, int n,
+                                   int subtract, uint64_t total, void* dense, cudaStream_t cs);
 static inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 static inline int grid_1d(const flashe_ctx* ctx, uint64_t work_items, int threads, int per_sm) {

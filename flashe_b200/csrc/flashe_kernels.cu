@@ -530,5 +530,54 @@ int flashe_sparse_apply_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf
     return flashe_launch_stream_scatter(ctx, st, g, io, cd, nz, cs);
 }
 
+int flashe_sparse_apply_masks_batch(flashe_ctx* ctx, uint32_t iter, const int32_t* prf_idx, int sign, int n_clients, const uint64_t* ks,
+                                    uint32_t n_jobs, const int64_t* const* indexes, void* dense, uint64_t dense_len, void* stream) {
+    ENTER(ctx);
+    if (n_clients < 1 || !prf_idx || !ks || !indexes) return fail(FLASHE_EINVAL, "need n_clients >= 1, prf_idx, ks and indexes");
+    if (n_jobs == 0) return fail(FLASHE_EINVAL, "n_jobs must be >= 1");
+    if (!dense) return fail(FLASHE_EINVAL, "dense is NULL");
+    uint64_t words_total = 0;
+    std::vector<uint64_t> off((size_t)n_clients);
+    for (int c = 0; c < n_clients; ++c) {
+        if (ks[c] > dense_len) return fail(FLASHE_EINVAL, "more compact positions than dense words");
+        if (ks[c] >= (1ull << 32)) return fail(FLASHE_EUNSUPPORTED, "index lists of 2^32 or more entries");
+        if (ks[c] && !indexes[c]) return fail(FLASHE_EINVAL, "NULL index list");
+        off[c] = words_total;
+        words_total += (ks[c] + 3) & ~3ull;                              // rows stay 16-byte aligned
+    }
+    if (words_total == 0) return FLASHE_OK;
+    const size_t wb = 4u * (size_t)ctx->words;
+    uint8_t* masks = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&masks, words_total * wb, cs));
+    // 1. F(iter, prf_c) over the compact positions of every client: one launch per run of clients whose lists have the
+    //    same length (the reference's sparsity is per layer of a common model: every client's list has the same length)
+    int rc = FLASHE_OK;
+    for (int c0 = 0; rc == FLASHE_OK && c0 < n_clients;) {
+        int c1 = c0 + 1;
+        while (c1 < n_clients && ks[c1] == ks[c0] && c1 - c0 < MAXS) ++c1;
+        if (ks[c0]) {
+            flashe_span span; memset(&span, 0, sizeof(span));
+            span.total_len = ks[c0]; span.begin = 0; span.count = ks[c0]; span.n_jobs = n_jobs;
+            StreamTab st; rc = make_streams(ctx, iter, prf_idx + c0, nullptr, c1 - c0, &st);
+            if (rc == FLASHE_OK) {
+                st.batch = 1; st.dbl = 0;
+                Geom g; make_geom(ctx, &span, pick_sup(ctx, &span, (uint64_t)(c1 - c0)), &g);
+                IoDev io; memset(&io, 0, sizeof(io));
+                io.out = masks + off[c0] * wb; io.out_stride = (ks[c0] + 3) & ~3ull; io.n_clients = (uint32_t)(c1 - c0);
+                CodecDev cd; memset(&cd, 0, sizeof(cd)); NoiseDev nz; memset(&nz, 0, sizeof(nz));
+                rc = flashe_launch_stream_masks(ctx, st, g, io, cd, nz, cs);
+            }
+        }
+        c0 = c1;
+    }
+    // 2. dense[index_c[p]] += sign * mask_c[p], every client at once, tile by tile
+    if (rc == FLASHE_OK) {
+        std::vector<const void*> rows((size_t)n_clients);
+        for (int c = 0; c < n_clients; ++c) rows[c] = masks + off[c] * wb;
+        rc = flashe_sparse_accumulate_tiled(ctx, rows.data(), indexes, ks, n_clients, sign < 0 ? 1 : 0, dense_len, dense, cs);
+    }
+    cudaFreeAsync(masks, cs);
+    return rc;
+}
 
 }  // extern "C"

@@ -747,8 +747,8 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(mw[0]), "=r"(mw[1]), "=r"(mw[2]), "=r"(mw[3]) : "r"(fslab + 16u * q) : "memory");
                   }
                   // (mw is reduced mod 2^b together with the sum below; only the mask output needs it by itself)
-                  if (MODE == M_MASKS) {
-                      stg_quad(reinterpret_cast<uint32_t*>(io.out) + o, qr, mw[0] & mk32, mw[1] & mk32, mw[2] & mk32, mw[3] & mk32);
+                  if (MODE == M_MASKS) {                       // (batch: one row per stream entry; otherwise c = 0)
+                      stg_quad(reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o, qr, mw[0] & mk32, mw[1] & mk32, mw[2] & mk32, mw[3] & mk32);
                   } else if (MODE == M_APPLY) {
                       uint32_t* out = reinterpret_cast<uint32_t*>(io.out) + (uint64_t)c * io.out_stride + o;
                       stg_quad(out, qr, (r[h][0] + mw[0]) & mk32, (r[h][1] + mw[1]) & mk32, (r[h][2] + mw[2]) & mk32, (r[h][3] + mw[3]) & mk32);
@@ -812,7 +812,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                           const uint32_t mword = lds32(fslab + 4u * (i + qr0));
                           const uint64_t o = o0 + i, j = e0 + i;
                           if (MODE == M_MASKS) {
-                              reinterpret_cast<uint32_t*>(io.out)[o] = mword & mk32;
+                              reinterpret_cast<uint32_t*>(io.out)[(uint64_t)c * io.out_stride + o] = mword & mk32;
                           } else if (MODE == M_APPLY) {
                               const uint64_t oc = (uint64_t)c * io.out_stride + o;
                               reinterpret_cast<uint32_t*>(io.out)[oc] = (reinterpret_cast<const uint32_t*>(io.in)[(uint64_t)c * io.in_stride + o] + mword) & mk32;
@@ -845,7 +845,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                           const uint32_t mword = i == 0u ? e4[0] : (i == 1u ? e4[1] : (i == 2u ? e4[2] : e4[3]));
                           const uint64_t o = ob + i, j = jb + i;
                           if (MODE == M_MASKS) {
-                              reinterpret_cast<uint32_t*>(io.out)[o] = mword & mk32;
+                              reinterpret_cast<uint32_t*>(io.out)[(uint64_t)c * io.out_stride + o] = mword & mk32;
                           } else if (MODE == M_APPLY) {
                               const uint64_t oc = (uint64_t)c * io.out_stride + o;
                               reinterpret_cast<uint32_t*>(io.out)[oc] = (reinterpret_cast<const uint32_t*>(io.in)[(uint64_t)c * io.in_stride + o] + mword) & mk32;
@@ -1025,7 +1025,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                   v = Word<4>::add(x, v);
               }
               v = Word<4>::band(v, mk128);
-              u128* out = reinterpret_cast<u128*>(io.out) + (MODE == M_APPLY ? (uint64_t)c * io.out_stride : 0ull) + o0 + lane + 32u * h;
+              u128* out = reinterpret_cast<u128*>(io.out) + (uint64_t)c * io.out_stride + o0 + lane + 32u * h;
               stg_v4(out, (uint32_t)v.lo, (uint32_t)(v.lo >> 32), (uint32_t)v.hi, (uint32_t)(v.hi >> 32));
           }
           cached_win = win;
@@ -1131,7 +1131,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                       if (io.aux) stg_v4(reinterpret_cast<uint64_t*>(io.aux) + o, (uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
                       stg_d2(io.outf + o, d0, d1);
                   } else {
-                      uint64_t* out = reinterpret_cast<uint64_t*>(io.out) + (MODE == M_MASKS ? 0ull : (uint64_t)c * io.out_stride) + o;
+                      uint64_t* out = reinterpret_cast<uint64_t*>(io.out) + (uint64_t)c * io.out_stride + o;
                       stg_v4(out, (uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
                   }
               }
@@ -1278,7 +1278,7 @@ k_stream(const __grid_constant__ KeySched ks, const __grid_constant__ StreamTab 
                     }
                 }
                 if (MODE == M_MASKS) {
-                    word_t* out = reinterpret_cast<word_t*>(io.out);
+                    word_t* out = reinterpret_cast<word_t*>(io.out) + (uint64_t)c * io.out_stride;
                     if (v0) out[o0] = mw0;
                     if (v1) out[o0 + 1] = mw1;
                 } else if (MODE == M_APPLY) {

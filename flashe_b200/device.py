@@ -504,6 +504,28 @@ class DeviceContext(object):
                                                        C.byref(span.c()), index.data_ptr(), dense.data_ptr(), total, self._stream()))
         return dense
 
+    def sparse_apply_masks_batch(self, it, prf_idx, sign, n_jobs, index_lists, dense, validate=True):
+        """dense[index_c[i]] += sign * F(it, prf_idx[c])[i] for every client c in ONE call (jzf_flashe.py:315-343): the
+        masks of all clients are generated over their compact positions (chunk rule on each list's own length) and
+        added tile by tile of `dense`.  Same result as one sparse_apply_masks per client."""
+        n = len(index_lists)
+        if n != len(prf_idx) or n < 1:
+            raise ValueError("one prf index per index list")
+        total = dense.numel() * dense.element_size() // self.word_bytes
+        if dense.device != self.device or not dense.is_contiguous():
+            raise ValueError("dense must be contiguous on %s" % self.device)
+        for ix in index_lists:
+            self._check(ix, torch.int64, ix.numel(), "index")
+            if validate and ix.numel():
+                bad = bool((ix[0] < 0) | (ix[-1] >= total)) or (ix.numel() > 1 and not bool((ix[1:] > ix[:-1]).all()))
+                if bad:
+                    raise IndexError("sparse index list must be sorted, unique and inside [0, %d)" % total)
+        ptrs = (C.c_void_p * n)(*[ix.data_ptr() for ix in index_lists])
+        ks = (C.c_uint64 * n)(*[ix.numel() for ix in index_lists])
+        _cabi.check(self.lib.flashe_sparse_apply_masks_batch(self._h, _iter32(it), _i32(prf_idx), int(sign), n, ks, int(n_jobs), ptrs,
+                                                             dense.data_ptr(), total, self._stream()))
+        return dense
+
     def sparse_overlap(self, index_lists, total):
         n = len(index_lists)
         if n < 2:

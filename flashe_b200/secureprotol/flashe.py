@@ -180,10 +180,12 @@ class FlasheCipher(Encrypt):
             # to dense and summed mod 2^b.
             ctx = self._ctx
             dense = ctx.zeros_words(int(self.total))
-            for client_idx, mask in enumerate(self.masks):
+            lists = []
+            for mask in self.masks:
                 index = mask if isinstance(mask, torch.Tensor) else torch.as_tensor(np.asarray(mask, dtype=np.int64))
-                index = index.to(ctx.device)
-                ctx.sparse_apply_masks(self.iter_index, [client_idx], [1], self._span(index.numel()), index, dense)
+                lists.append(index.to(ctx.device).contiguous())
+            # every client's term in one device call (masks of all clients, then one tiled accumulate into `dense`)
+            ctx.sparse_apply_masks_batch(self.iter_index, list(range(len(lists))), 1, self.n_jobs, lists, dense)
             self.next_iter_decrypt_prepared["minus"] = dense
 
     def set_idx_list(self, raw_idx_list=None, mode="encrypt"):

@@ -260,8 +260,8 @@ int flashe_sparse_expand(flashe_ctx* ctx, const void* compact, const int64_t* in
 /* The arbiter's sum of the expanded uploads (expand_to_dense for every client, then the element-wise
  * reduce of proc/jzf_aggregator.py:421-430) without materialising the n dense vectors:
  *   dense_out[j] = sum_c (j in index_c ? compact_c[.] : zero_c)   mod 2^int_bits
- * computed as fill(sum_c zero_c) followed by one scatter-add of (compact_c - zero_c) per client: O(total +
- * sum k_c) instead of O(n * total) bytes.  compacts / indexes: HOST arrays of n device pointers (words
+ * built tile by tile of the dense vector in shared memory (start from sum_c zero_c, add compact_c - zero_c for the
+ * entries of all clients, one coalesced write): O(total + sum k_c) instead of O(n * total) bytes.  compacts / indexes: HOST arrays of n device pointers (words
  * and int64_t, index sorted unique); ks: HOST uint64_t[n]; zero_words: HOST array of n words. */
 int flashe_sparse_sum(flashe_ctx* ctx, const void* const* compacts, const int64_t* const* indexes,
                       const uint64_t* ks, const void* zero_words, int n_clients, uint64_t total,
@@ -275,6 +275,18 @@ int flashe_sparse_sum(flashe_ctx* ctx, const void* const* compacts, const int64_
 int flashe_sparse_apply_masks(flashe_ctx* ctx, uint32_t iter, const int32_t* prf_idx, const int32_t* sign,
                               int nstreams, const flashe_span* span, const int64_t* index, void* dense,
                               uint64_t dense_len, void* stream);
+
+/* The same term for EVERY client in one call — what a client's decrypt of the sparse aggregate needs
+ * (sp/jzf_flashe.py:315-343: "for every client c regenerate F(t,c) over len(mask_c) compact positions, scatter to
+ * dense, sum"): dense[index_c[i]] += sign * F(iter, prf_idx[c])[i] for c < n_clients, i < ks[c], the chunk rule
+ * applied to each list's own length ks[c] with n_jobs chunks.  The masks of all clients are generated into a
+ * workspace (one launch per run of equal list lengths) and added tile by tile of the dense vector in shared
+ * memory: two passes over `dense` instead of one read-modify-write of a sector per entry and one launch per client.
+ * prf_idx, ks, indexes: HOST arrays of n_clients entries (indexes: device int64_t lists, sorted unique, entries
+ * outside [0, dense_len) are skipped); sign: +1 or -1.  Uploads a small table: not capturable into a CUDA graph. */
+int flashe_sparse_apply_masks_batch(flashe_ctx* ctx, uint32_t iter, const int32_t* prf_idx, int sign, int n_clients,
+                                    const uint64_t* ks, uint32_t n_jobs, const int64_t* const* indexes, void* dense,
+                                    uint64_t dense_len, void* stream);
 
 /* dynamic_masking cost model (proc/jzf_flashe_block.py:89-117): overlap[i] = |mask_i ∩ mask_{i+1}| for
  * the n-1 adjacent pairs; index lists are device int64_t arrays (sorted unique); `index` and `k` are

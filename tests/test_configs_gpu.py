@@ -262,6 +262,12 @@ def test_c4_sparse_top1pct_of_50m_32_clients(fb):
     for c in range(n):
         ctx.sparse_apply_masks(it, [c], [-1], span, index_d[c], p)
     assert torch.equal(_i64(p), dense_sum & 0xFFFFFFFF)
+    # the same through the one-call forms: tiled sparse sum on the server, every client's masks in one call on the client
+    cts = [ctx.encrypt(it, c, fb.SCHEME_SINGLE, _dev(qs[c]), span) for c in range(n)]
+    fused = ctx.sparse_sum(cts, index_d, total, zeros)
+    assert torch.equal(fused.view(torch.int32), acc.view(torch.int32))
+    ctx.sparse_apply_masks_batch(it, list(range(n)), -1, n_jobs, index_d, fused)
+    assert torch.equal(_i64(fused), dense_sum & 0xFFFFFFFF)
     # cost model inputs
     ov = ctx.sparse_overlap(index_d, total)
     want = [int(np.intersect1d(index[i], index[i + 1], assume_unique=True).size) for i in range(n - 1)]

@@ -488,6 +488,36 @@ def test_cuda_graph_replay_of_a_round(fb):
     assert np.array_equal(got_out.view(np.uint64), O.unquantize(p_want, 0.4, 16, n).view(np.uint64))
 
 
+@pytest.mark.parametrize("bits", [32, 20, 64, 120])
+def test_sparse_apply_masks_batch_equals_per_client_calls(fb, bits):
+    """flashe_sparse_apply_masks_batch (masks of every client into a workspace - one launch per run of equal list lengths -
+    then one tiled accumulate) against one flashe_sparse_apply_masks per client and against the oracle's masks."""
+    ctx = ctx_for(fb, bits)
+    rs = np.random.RandomState(100 + bits)
+    total, n_jobs, it = 150_001, 5, 3
+    ks = [4000, 4000, 4000, 0, 777, 4000, 1]                               # runs of equal lengths, an empty list, odd lengths
+    prf = [2, 3, 4, 5, 9, 10, 11]
+    lists = [_dev(np.sort(rs.choice(total, size=k, replace=False)).astype(np.int64)) for k in ks]
+    base = ctx.words_from_ints(np.array([int.from_bytes(rs.bytes(16), "little") & ((1 << bits) - 1) for _ in range(total)], dtype=object))
+    for sign in (1, -1):
+        want = base.clone()
+        for c, ix in enumerate(lists):
+            if ix.numel():
+                ctx.sparse_apply_masks(it, [prf[c]], [sign], fb.VectorSpan(ix.numel(), n_jobs), ix, want)
+        got = ctx.sparse_apply_masks_batch(it, prf, sign, n_jobs, lists, base.clone())
+        torch.cuda.synchronize()
+        assert torch.equal(got.view(torch.int32), want.view(torch.int32)), sign
+    # oracle: the term of client 4 (777 positions) by itself
+    z = ctx.sparse_apply_masks_batch(it, [prf[4]], 1, n_jobs, [lists[4]], ctx.zeros_words(total))
+    m = O.from_words(O.masks(KEY, bits, n_jobs, it, [prf[4]], [1], ks[4]), bits)
+    zi = ctx.ints_from_words(z)
+    idx = _np(lists[4])
+    assert [int(zi[j]) for j in idx] == [int(v) for v in m]
+    assert sum(int(v) for v in zi) == sum(int(v) for v in m)
+    with pytest.raises(IndexError):
+        ctx.sparse_apply_masks_batch(it, [1], 1, n_jobs, [_dev(np.array([5, 4], dtype=np.int64))], ctx.zeros_words(total))
+
+
 def test_dynamic_deal_concurrent_streams_and_graphs(fb):
     """The stream kernel's warps draw their work units from a ticket counter (one slot per stream, one per captured
     launch, reset by the launch's last warp).  Launches that overlap in time - two streams, two graphs replayed on two

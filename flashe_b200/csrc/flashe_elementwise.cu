@@ -666,10 +666,18 @@ __global__ void k_scatter_add(const typename Word<WORDS>::T* __restrict__ compac
 // per client (32 clients x 1 % of 50 M: 0.62 ms -> see profiles/).  The overlap counts of dynamic_masking use the same
 // runs: an entry of client i searches only client i+1's run of the same tile.
 struct SparseClient { const void* compact; const int64_t* index; uint64_t k; uint64_t zero_lo, zero_hi; };
+// Up to SPARSE_PARAM_CLIENTS clients travel in the kernel parameters (no table upload: a cudaMemcpyAsync from pageable
+// memory would hold the host until the stream reaches it); more clients go through a table in global memory.
+#define SPARSE_PARAM_CLIENTS 64
+struct SparseClientsParam { SparseClient c[SPARSE_PARAM_CLIENTS]; };
 #define SPARSE_TILE_BYTES 32768u
+#ifndef SP_DEPTH
+#define SP_DEPTH 6u        // measured with SP_MINB (profiles/r4m_ab_sparse_variants.txt): 6 loads in flight x 4 CTAs per SM
+#endif
 
-__global__ void k_sparse_splits(const SparseClient* __restrict__ cl, int n, uint64_t total, uint32_t tile_log2, uint64_t n_tiles,
-                                uint32_t* __restrict__ splits) {
+__global__ void k_sparse_splits(const SparseClient* __restrict__ cl_g, const __grid_constant__ SparseClientsParam P, int n, uint64_t total,
+                                uint32_t tile_log2, uint64_t n_tiles, uint32_t* __restrict__ splits) {
+    const SparseClient* __restrict__ cl = cl_g ? cl_g : P.c;
     const uint64_t per = n_tiles + 1, all = per * (uint64_t)n;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < all; g += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t c = g / per, t = g - c * per;
@@ -686,10 +694,15 @@ template <> __device__ __forceinline__ void smem_add<1>(uint32_t* p, uint32_t v)
 template <> __device__ __forceinline__ void smem_add<2>(uint64_t* p, uint64_t v) { atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
 template <> __device__ __forceinline__ void smem_add<4>(u128* p, u128 v) { *p = Word<4>::add(*p, v); }   // (one client at a time, see below)
 
-template <int WORDS>
-__global__ void __launch_bounds__(256)
-k_sparse_sum_tiled(const SparseClient* __restrict__ cl, int n, const uint32_t* __restrict__ splits, uint64_t total, uint64_t n_tiles,
-                   typename Word<WORDS>::T zsum, uint32_t b, typename Word<WORDS>::T* dense, int inplace, int subtract) {
+#ifndef SP_MINB
+#define SP_MINB 4
+#endif
+template <int WORDS, bool ONE_GROUP>
+__global__ void __launch_bounds__(256, SP_MINB)
+k_sparse_sum_tiled(const SparseClient* __restrict__ cl_g, const __grid_constant__ SparseClientsParam P, int n, const uint32_t* __restrict__ splits,
+                   uint64_t total, uint64_t n_tiles, typename Word<WORDS>::T zsum, uint32_t b, typename Word<WORDS>::T* dense, int inplace,
+                   int subtract) {
+    const SparseClient* __restrict__ cl = cl_g ? cl_g : P.c;
     // inplace: the tile starts from what `dense` holds (flashe_sparse_apply_masks_batch) instead of the sum of the zero
     // words; subtract: the entries are taken away (compact = masks, zero words unused)
     typedef Word<WORDS> WT;
@@ -699,6 +712,22 @@ k_sparse_sum_tiled(const SparseClient* __restrict__ cl, int n, const uint32_t* _
     __shared__ __align__(16) word_t acc[TILE];
     const word_t mk = WT::mask(b);
     const uint64_t per = n_tiles + 1;
+    // n <= blockDim.x (the usual case): a thread keeps ONE client for the whole launch - tpc threads per client - so the
+    // client's pointers are fetched once and the run bounds of the NEXT tile are fetched while this tile's run is walked
+    constexpr bool one_group = ONE_GROUP && WORDS <= 2;                // (the host launches it when 1 <= n <= blockDim.x)
+    uint32_t g_tpc = 1u, g_r = 0u, g_p0 = 0u, g_p1 = 0u;
+    const word_t* g_cp = nullptr; const int64_t* g_ix = nullptr; const uint32_t* g_sp = nullptr;
+    word_t g_z = WT::zero();
+    if (one_group) {
+        g_tpc = blockDim.x / (uint32_t)n;
+        const uint32_t cg = threadIdx.x / g_tpc;
+        g_r = threadIdx.x - cg * g_tpc;
+        if (cg < (uint32_t)n) {
+            g_cp = reinterpret_cast<const word_t*>(cl[cg].compact); g_ix = cl[cg].index; g_sp = splits + (uint64_t)cg * per;
+            if constexpr (WORDS <= 2) g_z = (word_t)cl[cg].zero_lo & mk;
+            if (blockIdx.x < n_tiles) { g_p0 = __ldg(g_sp + blockIdx.x); g_p1 = __ldg(g_sp + blockIdx.x + 1); }
+        }
+    }
     for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const uint64_t a = t * TILE;
         const uint32_t cnt = (uint32_t)(total - a < TILE ? total - a : TILE);
@@ -718,7 +747,28 @@ k_sparse_sum_tiled(const SparseClient* __restrict__ cl, int n, const uint32_t* _
         } else {
             for (uint32_t i = threadIdx.x; i < TILE; i += blockDim.x) acc[i] = zsum;
         }
-        if constexpr (WORDS <= 2) {
+        if constexpr (one_group) {
+            {
+                __syncthreads();                                           // the tile is initialised
+                uint32_t np0 = 0u, np1 = 0u;
+                const uint64_t tn = t + gridDim.x;
+                if (g_sp && tn < n_tiles) { np0 = __ldg(g_sp + tn); np1 = __ldg(g_sp + tn + 1); }   // used after this tile
+                const uint32_t a32 = (uint32_t)a;                          // offsets in the tile: low words suffice (TILE <= 2^32)
+                for (uint32_t p = g_p0 + g_r; p < g_p1; p += SP_DEPTH * g_tpc) {   // SP_DEPTH entries' loads in flight, then their adds
+                    uint32_t off[SP_DEPTH]; word_t v[SP_DEPTH];
+#pragma unroll
+                    for (uint32_t q = 0; q < SP_DEPTH; ++q) {
+                        const uint32_t pq = p + q * g_tpc;
+                        if (pq < g_p1) { off[q] = (uint32_t)__ldg(reinterpret_cast<const uint2*>(g_ix + pq)).x - a32; v[q] = __ldg(g_cp + pq); }
+                    }
+#pragma unroll
+                    for (uint32_t q = 0; q < SP_DEPTH; ++q)
+                        if (p + q * g_tpc < g_p1) smem_add<WORDS>(&acc[off[q]], subtract ? WT::sub(WT::zero(), v[q]) : WT::sub(v[q], g_z));
+                }
+                g_p0 = np0; g_p1 = np1;
+                __syncthreads();
+            }
+        } else if constexpr (WORDS <= 2 && !ONE_GROUP) {
             // tpc threads per client walk the client's run of this tile, every client at once and no barrier between
             // fetching the run bounds and walking the run (a warp per client, run after run, or a block-wide scan of the
             // run lengths first, both left the loads of a tile in dependent phases: 84 - 92 us for 32 clients x 1 % of
@@ -790,8 +840,9 @@ k_sparse_sum_tiled(const SparseClient* __restrict__ cl, int n, const uint32_t* _
 // took 0.57 ms for 32 clients x 1 % of 50 M; confined to the neighbour's run of the tile but still in global memory: 0.16.)
 #define OV_CAP 6144u
 __global__ void __launch_bounds__(256)
-k_sparse_overlap_tiled(const SparseClient* __restrict__ cl, int n, const uint32_t* __restrict__ splits, uint32_t tile_log2,
-                       uint64_t n_tiles, unsigned long long* __restrict__ out) {
+k_sparse_overlap_tiled(const SparseClient* __restrict__ cl_g, const __grid_constant__ SparseClientsParam P, int n,
+                       const uint32_t* __restrict__ splits, uint32_t tile_log2, uint64_t n_tiles, unsigned long long* __restrict__ out) {
+    const SparseClient* __restrict__ cl = cl_g ? cl_g : P.c;
     __shared__ uint32_t s_off[OV_CAP];
     __shared__ uint32_t s_pre[257], s_warp[8];
     const uint64_t per = n_tiles + 1;
@@ -858,23 +909,29 @@ k_sparse_overlap_tiled(const SparseClient* __restrict__ cl, int n, const uint32_
 // Uploads the client table and computes the runs; *ws_out (one stream-ordered allocation) holds both.
 static int sparse_prepare(flashe_ctx* ctx, const void* const* compacts, const int64_t* const* indexes, const uint64_t* ks, const void* zero_words,
                           int word_bytes, int n, uint64_t total, uint32_t tile_log2, cudaStream_t cs, uint8_t** ws_out, SparseClient** cl_out,
-                          uint32_t** splits_out, uint64_t* n_tiles_out) {
+                          SparseClientsParam* P, uint32_t** splits_out, uint64_t* n_tiles_out) {
     const uint64_t n_tiles = (total + (1ull << tile_log2) - 1) >> tile_log2;
-    std::vector<SparseClient> h((size_t)n);
+    const bool in_params = n <= SPARSE_PARAM_CLIENTS;
+    std::vector<SparseClient> h((size_t)(in_params ? 0 : n));
+    memset(P, 0, sizeof(*P));
     for (int c = 0; c < n; ++c) {
-        memset(&h[c], 0, sizeof(SparseClient));
-        h[c].compact = compacts ? compacts[c] : nullptr; h[c].index = indexes[c]; h[c].k = ks[c];
-        if (zero_words) memcpy(&h[c].zero_lo, (const uint8_t*)zero_words + (size_t)c * word_bytes, (size_t)word_bytes);
+        SparseClient e; memset(&e, 0, sizeof(e));
+        e.compact = compacts ? compacts[c] : nullptr; e.index = indexes[c]; e.k = ks[c];
+        if (zero_words) memcpy(&e.zero_lo, (const uint8_t*)zero_words + (size_t)c * word_bytes, (size_t)word_bytes);
+        if (in_params) P->c[c] = e; else h[c] = e;
     }
-    const size_t cl_bytes = (sizeof(SparseClient) * (size_t)n + 255) & ~(size_t)255;
+    const size_t cl_bytes = in_params ? 0 : ((sizeof(SparseClient) * (size_t)n + 255) & ~(size_t)255);
     const size_t sp_bytes = sizeof(uint32_t) * (size_t)n * (size_t)(n_tiles + 1);
     uint8_t* ws = nullptr;
     CUDA_TRY(cudaMallocAsync((void**)&ws, cl_bytes + sp_bytes, cs));
-    cudaError_t e = cudaMemcpyAsync(ws, h.data(), sizeof(SparseClient) * (size_t)n, cudaMemcpyHostToDevice, cs);   // (pageable source: staged before the call returns)
-    if (e != cudaSuccess) { cudaFreeAsync(ws, cs); return fail(FLASHE_ECUDA, std::string("sparse client table: ") + cudaGetErrorString(e)); }
-    SparseClient* cl = reinterpret_cast<SparseClient*>(ws);
+    SparseClient* cl = nullptr;
+    if (!in_params) {
+        cudaError_t e = cudaMemcpyAsync(ws, h.data(), sizeof(SparseClient) * (size_t)n, cudaMemcpyHostToDevice, cs);   // (pageable source: staged before the call returns)
+        if (e != cudaSuccess) { cudaFreeAsync(ws, cs); return fail(FLASHE_ECUDA, std::string("sparse client table: ") + cudaGetErrorString(e)); }
+        cl = reinterpret_cast<SparseClient*>(ws);
+    }
     uint32_t* splits = reinterpret_cast<uint32_t*>(ws + cl_bytes);
-    k_sparse_splits<<<GRID_OCC(ctx, k_sparse_splits, (uint64_t)n * (n_tiles + 1), 256), 256, 0, cs>>>(cl, n, total, tile_log2, n_tiles, splits);
+    k_sparse_splits<<<GRID_OCC(ctx, k_sparse_splits, (uint64_t)n * (n_tiles + 1), 256), 256, 0, cs>>>(cl, *P, n, total, tile_log2, n_tiles, splits);
     count_launch();
     *ws_out = ws; *cl_out = cl; *splits_out = splits; *n_tiles_out = n_tiles;
     return FLASHE_OK;
@@ -892,11 +949,12 @@ static int sparse_sum_tiled_t(flashe_ctx* ctx, const void* const* compacts, cons
     const word_t mk = WT::mask((uint32_t)ctx->int_bits);
     word_t zsum = WT::zero();
     for (int c = 0; c < n; ++c) zsum = WT::band(WT::add(zsum, WT::band(zeros[c], mk)), mk);
-    uint8_t* ws; SparseClient* cl; uint32_t* splits; uint64_t n_tiles;
-    int rc = sparse_prepare(ctx, compacts, indexes, ks, zero_words, 4 * WORDS, n, total, tile_log2, cs, &ws, &cl, &splits, &n_tiles);
+    uint8_t* ws; SparseClient* cl; uint32_t* splits; uint64_t n_tiles; SparseClientsParam P;
+    int rc = sparse_prepare(ctx, compacts, indexes, ks, zero_words, 4 * WORDS, n, total, tile_log2, cs, &ws, &cl, &P, &splits, &n_tiles);
     if (rc) return rc;
     const int grid = (int)(n_tiles < (uint64_t)ctx->num_sms * 32 ? n_tiles : (uint64_t)ctx->num_sms * 32);
-    k_sparse_sum_tiled<WORDS><<<grid, 256, 0, cs>>>(cl, n, splits, total, n_tiles, zsum, (uint32_t)ctx->int_bits, (word_t*)dense_out, 0, 0);
+    if (WORDS <= 2 && n <= 256) k_sparse_sum_tiled<WORDS, (WORDS <= 2)><<<grid, 256, 0, cs>>>(cl, P, n, splits, total, n_tiles, zsum, (uint32_t)ctx->int_bits, (word_t*)dense_out, 0, 0);
+    else k_sparse_sum_tiled<WORDS, false><<<grid, 256, 0, cs>>>(cl, P, n, splits, total, n_tiles, zsum, (uint32_t)ctx->int_bits, (word_t*)dense_out, 0, 0);
     count_launch();
     cudaFreeAsync(ws, cs);
     CUDA_TRY(cudaGetLastError());
@@ -910,11 +968,12 @@ static int sparse_accumulate_t(flashe_ctx* ctx, const void* const* compacts, con
     typedef typename Word<WORDS>::T word_t;
     constexpr uint32_t TILE = SPARSE_TILE_BYTES / (4u * WORDS);
     uint32_t tile_log2 = 0; while ((1u << tile_log2) < TILE) ++tile_log2;
-    uint8_t* ws; SparseClient* cl; uint32_t* splits; uint64_t n_tiles;
-    int rc = sparse_prepare(ctx, compacts, indexes, ks, nullptr, 4 * WORDS, n, total, tile_log2, cs, &ws, &cl, &splits, &n_tiles);
+    uint8_t* ws; SparseClient* cl; uint32_t* splits; uint64_t n_tiles; SparseClientsParam P;
+    int rc = sparse_prepare(ctx, compacts, indexes, ks, nullptr, 4 * WORDS, n, total, tile_log2, cs, &ws, &cl, &P, &splits, &n_tiles);
     if (rc) return rc;
     const int grid = (int)(n_tiles < (uint64_t)ctx->num_sms * 32 ? n_tiles : (uint64_t)ctx->num_sms * 32);
-    k_sparse_sum_tiled<WORDS><<<grid, 256, 0, cs>>>(cl, n, splits, total, n_tiles, Word<WORDS>::zero(), (uint32_t)ctx->int_bits, (word_t*)dense, 1, subtract);
+    if (WORDS <= 2 && n <= 256) k_sparse_sum_tiled<WORDS, (WORDS <= 2)><<<grid, 256, 0, cs>>>(cl, P, n, splits, total, n_tiles, Word<WORDS>::zero(), (uint32_t)ctx->int_bits, (word_t*)dense, 1, subtract);
+    else k_sparse_sum_tiled<WORDS, false><<<grid, 256, 0, cs>>>(cl, P, n, splits, total, n_tiles, Word<WORDS>::zero(), (uint32_t)ctx->int_bits, (word_t*)dense, 1, subtract);
     count_launch();
     cudaFreeAsync(ws, cs);
     CUDA_TRY(cudaGetLastError());
@@ -1394,11 +1453,11 @@ int flashe_sparse_overlap(flashe_ctx* ctx, const int64_t* const* index, const ui
         for (int i = 0; i < n; ++i) ksum += k[i];
         uint32_t tile_log2 = 8;
         while (tile_log2 < 20 && ((ksum << (tile_log2 + 1)) / total) * 2 <= OV_CAP) ++tile_log2;
-        uint8_t* ws; SparseClient* cl; uint32_t* splits; uint64_t n_tiles;
-        int rc = sparse_prepare(ctx, nullptr, index, k, nullptr, 0, n, total, tile_log2, cs, &ws, &cl, &splits, &n_tiles);
+        uint8_t* ws; SparseClient* cl; uint32_t* splits; uint64_t n_tiles; SparseClientsParam P;
+        int rc = sparse_prepare(ctx, nullptr, index, k, nullptr, 0, n, total, tile_log2, cs, &ws, &cl, &P, &splits, &n_tiles);
         if (rc) { cudaFreeAsync(d, cs); return rc; }
         const int grid = GRID_OCC(ctx, k_sparse_overlap_tiled, n_tiles * 256, 256);
-        k_sparse_overlap_tiled<<<grid, 256, 0, cs>>>(cl, n, splits, tile_log2, n_tiles, d);
+        k_sparse_overlap_tiled<<<grid, 256, 0, cs>>>(cl, P, n, splits, tile_log2, n_tiles, d);
         count_launch();
         e = cudaGetLastError();
         cudaFreeAsync(ws, cs);

@@ -518,6 +518,42 @@ def test_sparse_apply_masks_batch_equals_per_client_calls(fb, bits):
         ctx.sparse_apply_masks_batch(it, [1], 1, n_jobs, [_dev(np.array([5, 4], dtype=np.int64))], ctx.zeros_words(total))
 
 
+@pytest.mark.parametrize("n,total,kmax", [(70, 40_001, 900), (300, 20_003, 120), (32, 5_000, 5_000), (3, 100_000, 60_000)])
+def test_sparse_tiled_paths_many_clients_dense_lists_unaligned(fb, n, total, kmax):
+    """The tiled sparse kernels outside the shipped shape: more clients than travel in the kernel parameters (70: table in
+    global memory), more than a block has threads (300: grouped walk, per-pair overlap kernels), index lists that cover
+    the whole vector (32 x 5000: a tile's runs exceed the overlap kernel's shared-memory buffer; adjacent lists are equal),
+    long runs per tile (3 x 60 %), and a dense vector that starts 4 bytes off a 16-byte boundary."""
+    bits = 32
+    ctx = ctx_for(fb, bits)
+    rs = np.random.RandomState(n)
+    ks = [kmax if kmax == total else int(rs.randint(1, kmax + 1)) for _ in range(n)]
+    lists_np = [np.sort(rs.choice(total, size=k, replace=False)).astype(np.int64) for k in ks]
+    lists = [_dev(a) for a in lists_np]
+    vals_np = [rs.randint(0, 2 ** 32, size=k, dtype=np.uint64).astype(np.uint32) for k in ks]
+    vals = [_dev(v) for v in vals_np]
+    zeros = [int(z) for z in rs.randint(0, 2 ** 32, size=n, dtype=np.uint64)]
+    want = np.full(total, sum(zeros) % 2 ** 32, dtype=np.uint64)
+    for c in range(n):
+        want[lists_np[c]] += vals_np[c].astype(np.uint64) + (2 ** 32 - zeros[c])
+    want = (want % 2 ** 32).astype(np.uint32)
+    buf = torch.zeros(total + 4, dtype=torch.int32, device="cuda").view(torch.uint32)
+    for off in (0, 1):                                                     # 16-byte aligned / 4 bytes off
+        out = buf[off:off + total]
+        got = ctx.sparse_sum(vals, lists, total, zeros, out=out)
+        assert np.array_equal(_np(got), want), off
+    # every client's masks in one call == client by client
+    base = _dev(rs.randint(0, 2 ** 32, size=total, dtype=np.uint64).astype(np.uint32))
+    per_client = base.clone()
+    prf = list(range(5, 5 + n))
+    for c in range(n):
+        ctx.sparse_apply_masks(7, [prf[c]], [-1], fb.VectorSpan(ks[c], 3), lists[c], per_client)
+    one_call = ctx.sparse_apply_masks_batch(7, prf, -1, 3, lists, base.clone())
+    assert torch.equal(one_call.view(torch.int32), per_client.view(torch.int32))
+    ov = ctx.sparse_overlap(lists, total)
+    assert ov == [int(np.intersect1d(lists_np[i], lists_np[i + 1], assume_unique=True).size) for i in range(n - 1)]
+
+
 def test_dynamic_deal_concurrent_streams_and_graphs(fb):
     """The stream kernel's warps draw their work units from a ticket counter (one slot per stream, one per captured
     launch, reset by the launch's last warp).  Launches that overlap in time - two streams, two graphs replayed on two

@@ -844,56 +844,55 @@ k_sparse_overlap_tiled(const SparseClient* __restrict__ cl_g, const __grid_const
                        const uint32_t* __restrict__ splits, uint32_t tile_log2, uint64_t n_tiles, unsigned long long* __restrict__ out) {
     const SparseClient* __restrict__ cl = cl_g ? cl_g : P.c;
     __shared__ uint32_t s_off[OV_CAP];
-    __shared__ uint32_t s_pre[257], s_warp[8];
     const uint64_t per = n_tiles + 1;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    // tpc threads share a client for the whole launch: thread (cg, r) brings in and looks up entries r, r + tpc, .. of
-    // client cg's run; its hits stay in a register until the end
+    // tpc threads share a client for the whole launch: thread (cg, r) brings entries r, r + tpc, .. of client cg's run
+    // into the client's SLOT of s_off (OV_CAP / n offsets: no scan of the run lengths, no layout to agree on) and looks
+    // them up in the next client's slot; its hits stay in a register until the end.  The run bounds of the next tile are
+    // fetched while this tile is worked on.  A tile in which some run exceeds its slot searches in global memory.
     const uint32_t tpc = blockDim.x / (uint32_t)n, cg = threadIdx.x / tpc, r = threadIdx.x - cg * tpc;
-    const bool mine = cg < (uint32_t)n;
+    const uint32_t slot = OV_CAP / (uint32_t)n;
+    const bool mine = cg < (uint32_t)n, has_next = mine && cg + 1u < (uint32_t)n;
     const int64_t* __restrict__ ix = mine ? cl[cg].index : nullptr;
-    const int64_t* __restrict__ ix_next = (mine && cg + 1u < (uint32_t)n) ? cl[cg + 1u].index : nullptr;
+    const int64_t* __restrict__ ix_next = has_next ? cl[cg + 1u].index : nullptr;
+    const uint32_t* __restrict__ sp = splits + (uint64_t)(mine ? cg : 0u) * per;
     unsigned long long hits = 0ull;
+    uint32_t p0 = 0u, p1 = 0u, q1 = 0u;                                    // own run [p0, p1), next client's run [p1', q1): list positions
+    uint32_t q0 = 0u;
+    if (mine && blockIdx.x < n_tiles) {
+        p0 = __ldg(sp + blockIdx.x); p1 = __ldg(sp + blockIdx.x + 1);
+        if (has_next) { q0 = __ldg(sp + per + blockIdx.x); q1 = __ldg(sp + per + blockIdx.x + 1); }
+    }
     for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const uint64_t a = t << tile_log2;
-        // run lengths of clients 0 .. n-1 (thread c), inclusive scan over the block -> where each run sits in s_off
-        uint32_t len = 0u;
-        if ((int)threadIdx.x < n) len = __ldg(splits + (uint64_t)threadIdx.x * per + t + 1) - __ldg(splits + (uint64_t)threadIdx.x * per + t);
-        uint32_t p0 = 0u, p1 = 0u, q0 = 0u, q1 = 0u;                      // own run, next client's run (list positions)
-        if (mine) { p0 = __ldg(splits + (uint64_t)cg * per + t); p1 = __ldg(splits + (uint64_t)cg * per + t + 1); }
-        if (ix_next) { q0 = __ldg(splits + (uint64_t)(cg + 1u) * per + t); q1 = __ldg(splits + (uint64_t)(cg + 1u) * per + t + 1); }
-        uint32_t incl = len;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
-        if (lane == 31u) s_warp[warp] = incl;
-        __syncthreads();
-        uint32_t before = 0u;
-        for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
-        s_pre[threadIdx.x + 1] = before + incl;
-        if (threadIdx.x == 0u) s_pre[0] = 0u;
-        __syncthreads();
-        if (s_pre[n] <= OV_CAP) {
+        const uint32_t a32 = (uint32_t)(t << tile_log2);                   // offsets inside the tile: low words suffice
+        const uint64_t tn = t + gridDim.x;
+        uint32_t np0 = 0u, np1 = 0u, nq0 = 0u, nq1 = 0u;
+        if (mine && tn < n_tiles) {
+            np0 = __ldg(sp + tn); np1 = __ldg(sp + tn + 1);
+            if (has_next) { nq0 = __ldg(sp + per + tn); nq1 = __ldg(sp + per + tn + 1); }
+        }
+        const uint32_t len = p1 - p0, len_next = q1 - q0;
+        if (!__syncthreads_or(len > slot)) {                               // (also: the previous tile's lookups are done)
             if (mine) {
-                const uint32_t base = s_pre[cg];
-                for (uint32_t p = p0 + r; p < p1; p += 4u * tpc) {         // four loads in flight
-                    uint32_t o[4];
+                const uint32_t base = cg * slot;
+                for (uint32_t k = r; k < len; k += 6u * tpc) {             // six loads in flight
+                    uint32_t o[6];
 #pragma unroll
-                    for (uint32_t q = 0; q < 4u; ++q) if (p + q * tpc < p1) o[q] = (uint32_t)((uint64_t)__ldg(ix + p + q * tpc) - a);
+                    for (uint32_t q = 0; q < 6u; ++q) if (k + q * tpc < len) o[q] = (uint32_t)__ldg(reinterpret_cast<const uint2*>(ix + p0 + k + q * tpc)).x - a32;
 #pragma unroll
-                    for (uint32_t q = 0; q < 4u; ++q) if (p + q * tpc < p1) s_off[base + (p + q * tpc - p0)] = o[q];
+                    for (uint32_t q = 0; q < 6u; ++q) if (k + q * tpc < len) s_off[base + k + q * tpc] = o[q];
                 }
             }
             __syncthreads();
-            if (ix_next) {
-                const uint32_t base = s_pre[cg], nb = s_pre[cg + 1u], ne = s_pre[cg + 2u];
-                for (uint32_t k = r; k < p1 - p0; k += tpc) {
+            if (has_next) {
+                const uint32_t base = cg * slot, nb = base + slot;
+                for (uint32_t k = r; k < len; k += tpc) {
                     const uint32_t v = s_off[base + k];
-                    uint32_t lo = nb, hi = ne;
-                    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] < v) lo = mid + 1; else hi = mid; }
-                    hits += (lo < ne && s_off[lo] == v) ? 1ull : 0ull;
+                    uint32_t lo = 0u, hi = len_next;
+                    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (s_off[nb + mid] < v) lo = mid + 1; else hi = mid; }
+                    hits += (lo < len_next && s_off[nb + lo] == v) ? 1ull : 0ull;
                 }
             }
-        } else if (ix_next) {                                              // the tile's runs do not fit: search in global memory
+        } else if (has_next) {                                             // some run does not fit its slot: search in global memory
             for (uint32_t p = p0 + r; p < p1; p += tpc) {
                 const int64_t v = __ldg(ix + p);
                 uint32_t lo = q0, hi = q1;
@@ -901,9 +900,69 @@ k_sparse_overlap_tiled(const SparseClient* __restrict__ cl_g, const __grid_const
                 hits += (lo < q1 && __ldg(ix_next + lo) == v) ? 1ull : 0ull;
             }
         }
-        __syncthreads();
+        p0 = np0; p1 = np1; q0 = nq0; q1 = nq1;
     }
-    if (ix_next && hits) atomicAdd(out + cg, hits);
+    if (has_next && hits) atomicAdd(out + cg, hits);
+}
+
+// The same counts through per-client BITMAPS of the tile (n <= 64 clients: n x tile / 8 <= 32 KB of shared memory): the
+// entries of every client set their bits, then every entry of client i tests its bit in client i+1's bitmap - a dozen
+// instructions per entry where the binary search in shared memory spent ~90 (ncu: that kernel was issue-bound, 66 M warp
+// instructions, 98 us for 32 clients x 1 % of 50 M).  The entries are read a second time for the test (L1 / L2 hits), and
+// a third pass clears exactly the words that were set.
+#define OVB_BYTES 32768u
+__global__ void __launch_bounds__(256)
+k_sparse_overlap_bitmap(const SparseClient* __restrict__ cl_g, const __grid_constant__ SparseClientsParam P, int n,
+                        const uint32_t* __restrict__ splits, uint32_t tile_log2, uint64_t n_tiles, unsigned long long* __restrict__ out) {
+    const SparseClient* __restrict__ cl = cl_g ? cl_g : P.c;
+    __shared__ uint32_t bm[OVB_BYTES / 4u];
+    const uint64_t per = n_tiles + 1;
+    const uint32_t wpc = 1u << (tile_log2 - 5u);                           // bitmap words per client
+    const uint32_t tpc = blockDim.x / (uint32_t)n, cg = threadIdx.x / tpc, r = threadIdx.x - cg * tpc;
+    const bool mine = cg < (uint32_t)n, has_next = mine && cg + 1u < (uint32_t)n;
+    const int64_t* __restrict__ ix = mine ? cl[cg].index : nullptr;
+    const uint32_t* __restrict__ sp = splits + (uint64_t)(mine ? cg : 0u) * per;
+    uint32_t* own = bm + cg * wpc;
+    const uint32_t* nxt = own + wpc;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)n * wpc; i += blockDim.x) bm[i] = 0u;
+    unsigned long long hits = 0ull;
+    uint32_t p0 = 0u, p1 = 0u;
+    if (mine && blockIdx.x < n_tiles) { p0 = __ldg(sp + blockIdx.x); p1 = __ldg(sp + blockIdx.x + 1); }
+    __syncthreads();
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint32_t a32 = (uint32_t)(t << tile_log2);
+        const uint64_t tn = t + gridDim.x;
+        uint32_t np0 = 0u, np1 = 0u;
+        if (mine && tn < n_tiles) { np0 = __ldg(sp + tn); np1 = __ldg(sp + tn + 1); }
+        for (uint32_t p = p0 + r; p < p1; p += 6u * tpc) {                 // set: six loads in flight
+            uint32_t o[6];
+#pragma unroll
+            for (uint32_t q = 0; q < 6u; ++q) if (p + q * tpc < p1) o[q] = (uint32_t)__ldg(reinterpret_cast<const uint2*>(ix + p + q * tpc)).x - a32;
+#pragma unroll
+            for (uint32_t q = 0; q < 6u; ++q) if (p + q * tpc < p1) atomicOr(own + (o[q] >> 5), 1u << (o[q] & 31u));
+        }
+        __syncthreads();
+        if (has_next) {
+            for (uint32_t p = p0 + r; p < p1; p += 6u * tpc) {             // test in the next client's bitmap
+                uint32_t o[6];
+#pragma unroll
+                for (uint32_t q = 0; q < 6u; ++q) if (p + q * tpc < p1) o[q] = (uint32_t)__ldg(reinterpret_cast<const uint2*>(ix + p + q * tpc)).x - a32;
+#pragma unroll
+                for (uint32_t q = 0; q < 6u; ++q) if (p + q * tpc < p1) hits += (nxt[o[q] >> 5] >> (o[q] & 31u)) & 1u;
+            }
+        }
+        __syncthreads();
+        for (uint32_t p = p0 + r; p < p1; p += 6u * tpc) {                 // clear the words this thread set
+            uint32_t o[6];
+#pragma unroll
+            for (uint32_t q = 0; q < 6u; ++q) if (p + q * tpc < p1) o[q] = (uint32_t)__ldg(reinterpret_cast<const uint2*>(ix + p + q * tpc)).x - a32;
+#pragma unroll
+            for (uint32_t q = 0; q < 6u; ++q) if (p + q * tpc < p1) own[o[q] >> 5] = 0u;
+        }
+        __syncthreads();
+        p0 = np0; p1 = np1;
+    }
+    if (has_next && hits) atomicAdd(out + cg, hits);
 }
 
 // Uploads the client table and computes the runs; *ws_out (one stream-ordered allocation) holds both.
@@ -1447,7 +1506,19 @@ int flashe_sparse_overlap(flashe_ctx* ctx, const int64_t* const* index, const ui
     bool tiled_ok = tiled && total > 0 && e == cudaSuccess;
     uint64_t kmax = 0;
     for (int i = 0; i < n; ++i) { tiled_ok = tiled_ok && k[i] < (1ull << 32) && (k[i] == 0 || index[i]); if (k[i] > kmax) kmax = k[i]; }
-    if (tiled_ok && kmax && n <= 256) {
+    if (tiled_ok && kmax && n <= 64) {
+        // per-client bitmaps of the tile: the largest power-of-two tile with n bitmaps in OVB_BYTES of shared memory
+        uint32_t tile_log2 = 5;
+        while (tile_log2 < 16 && ((uint64_t)n << (tile_log2 + 1 - 3)) <= OVB_BYTES) ++tile_log2;
+        uint8_t* ws; SparseClient* cl; uint32_t* splits; uint64_t n_tiles; SparseClientsParam P;
+        int rc = sparse_prepare(ctx, nullptr, index, k, nullptr, 0, n, total, tile_log2, cs, &ws, &cl, &P, &splits, &n_tiles);
+        if (rc) { cudaFreeAsync(d, cs); return rc; }
+        const int grid = GRID_OCC(ctx, k_sparse_overlap_bitmap, n_tiles * 256, 256);
+        k_sparse_overlap_bitmap<<<grid, 256, 0, cs>>>(cl, P, n, splits, tile_log2, n_tiles, d);
+        count_launch();
+        e = cudaGetLastError();
+        cudaFreeAsync(ws, cs);
+    } else if (tiled_ok && kmax && n <= 256) {
         // tile size: the runs of all clients in a tile should fit the kernel's shared-memory buffer twice over on average
         uint64_t ksum = 0;
         for (int i = 0; i < n; ++i) ksum += k[i];

@@ -516,6 +516,7 @@ struct TopkSeg {
     uint32_t n, k;
     uint64_t cbegin, ctile0, samp0;
     uint32_t cap, samp_lines, samp_stride, samp_rank;
+    uint32_t small, pad;               // small: the three radix passes of this layer run inside ONE block (k_topk_select_small)
 };
 
 #define TK_THREADS 256
@@ -523,6 +524,8 @@ struct TopkSeg {
 #define TK_TILE (TK_THREADS * TK_PER)
 #define TK_BINS 2048
 #define TK_SAMPLE_ALL 16384u         // layers up to this size are "sampled" completely
+#define TK_SMALL_N (1u << 22)         // candidate-route layers up to this size (<= 2^19 candidates) and ...
+#define TK_SMALL_EXACT 65536u        // ... exact-route layers up to this size select inside one block
 
 __device__ __forceinline__ uint32_t key_of(float x) { return __float_as_uint(x) & 0x7fffffffu; }
 __device__ __forceinline__ uint32_t key_of_bits(uint32_t w) { return w & 0x7fffffffu; }
@@ -550,13 +553,15 @@ __device__ __forceinline__ bool topk_exact_route(const TopkSeg& s, uint32_t coun
 // What a histogram / count pass reads for a layer: CAND = the candidate keys of a candidate-route layer,
 // !CAND = x itself for an exact-route layer; n = 0 when the layer belongs to the other route.
 struct TopkView { uint64_t begin; uint64_t tile0; uint32_t n; };
-template <bool CAND>
+// RADIX: the view of the multi-block histogram passes, which leave the small layers to k_topk_select_small.
+template <bool CAND, bool RADIX = false>
 __device__ __forceinline__ TopkView topk_view(const TopkSeg& s, const uint32_t* __restrict__ cand_count, int idx) {
     const uint32_t count = cand_count ? cand_count[idx] : 0u;
     const bool exact = topk_exact_route(s, count);
     TopkView v;
     if (CAND) { v.begin = s.cbegin; v.tile0 = s.ctile0; v.n = exact ? 0u : count; }
     else { v.begin = s.begin; v.tile0 = s.tile0; v.n = exact ? s.n : 0u; }
+    if (RADIX && s.small) v.n = 0u;
     return v;
 }
 
@@ -622,6 +627,109 @@ k_topk_pick(uint32_t* __restrict__ hist_all, TopkState* __restrict__ st_all, uin
     } else if (in1) {
         st->prefix |= b1 << shift; st->k_rem = k_rem - before - c0; st->c_eq = c1;
     }
+}
+
+// The sample bound of a layer in ONE block: k_topk_sample's histogram of the top 11 key bits over the layer's sample
+// lines (at most 512 lines = 16 K elements whatever the layer's size) in shared memory, then k_topk_pick's suffix scan
+// for the bucket of the samp_rank-th largest sample -> lo_out[layer] (stays 0 when the sample is shorter than the rank
+// or the layer is not sampled).  One launch instead of two, no global histogram traffic.
+__global__ void __launch_bounds__(1024)
+k_topk_bound(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, uint32_t* __restrict__ lo_out) {
+    __shared__ uint32_t sh[TK_BINS];
+    __shared__ uint32_t warp_tot[32];
+    topk_pdl_enter();
+    const TopkSeg sg = segs[blockIdx.x];
+    if (sg.samp_lines == 0u) return;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    sh[t] = 0u; sh[t + 1024u] = 0u;
+    __syncthreads();
+    // at most 512 lines (host: TK_SAMPLE_ALL / 32 and the cap on `want`): 16 per warp, all loads in flight before the counts
+    for (uint32_t i0 = warp; i0 < sg.samp_lines; i0 += 32u * 16u) {
+        uint32_t v[16]; uint32_t ok = 0u;
+#pragma unroll
+        for (uint32_t q = 0; q < 16u; ++q) {
+            const uint32_t i = i0 + 32u * q;
+            if (i < sg.samp_lines) {
+                const uint32_t jit = sg.samp_stride > 1u ? topk_hash(i) % sg.samp_stride : 0u;
+                const uint64_t e = ((uint64_t)i * sg.samp_stride + jit) * 32u + lane;
+                if (e < sg.n) { v[q] = x[sg.begin + e]; ok |= 1u << q; }
+            }
+        }
+#pragma unroll
+        for (uint32_t q = 0; q < 16u; ++q) if ((ok >> q) & 1u) atomicAdd(&sh[key_of_bits(v[q]) >> 20], 1u);
+    }
+    __syncthreads();
+    const uint32_t b0 = TK_BINS - 1 - 2 * t, b1 = b0 - 1;
+    const uint32_t c0 = sh[b0], c1 = sh[b1];
+    uint32_t incl = c0 + c1;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_tot[lane];
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, w, d); if (lane >= (uint32_t)d) w += o; }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t before = (warp ? warp_tot[warp - 1] : 0u) + incl - (c0 + c1);
+    const uint32_t k_rem = sg.samp_rank;
+    if (before < k_rem && k_rem <= before + c0) lo_out[blockIdx.x] = b0 << 20;
+    else if (before + c0 < k_rem && k_rem <= before + c0 + c1) lo_out[blockIdx.x] = b1 << 20;
+}
+
+// Small layers: all three radix passes and their picks inside ONE block of 1024 threads per layer - the keys of the
+// layer's view (its candidate list, or x itself on the exact route) are read three times by the same block, the
+// histogram lives in shared memory, nothing is exchanged between blocks.  A model of many layers spent six launches
+// (~80 us for 200 layers of 250 k, most of it launch and pick latency) on a few thousand candidates per layer.
+// Leaves the same TopkState as k_topk_hist + k_topk_pick x 3.
+__global__ void __launch_bounds__(1024)
+k_topk_select_small(const uint32_t* __restrict__ x, const uint32_t* __restrict__ cand_key, const TopkSeg* __restrict__ segs,
+                    const uint32_t* __restrict__ cand_count, TopkState* __restrict__ st_all) {
+    __shared__ uint32_t sh[TK_BINS];
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t s_prefix, s_krem, s_ceq;
+    topk_pdl_enter();
+    const TopkSeg sg = segs[blockIdx.x];
+    if (!sg.small) return;
+    const uint32_t count = cand_count ? cand_count[blockIdx.x] : 0u;
+    const bool exact = topk_exact_route(sg, count);
+    const uint32_t* __restrict__ keys = exact ? x + sg.begin : cand_key + sg.cbegin;
+    const uint32_t n = exact ? sg.n : count;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    if (t == 0) { s_prefix = 0u; s_krem = sg.k; s_ceq = 0u; }
+    const uint32_t shifts[3] = {20u, 9u, 0u}, nbits[3] = {11u, 11u, 9u};
+#pragma unroll 1
+    for (int p = 0; p < 3; ++p) {
+        sh[t] = 0u; sh[t + 1024u] = 0u;
+        __syncthreads();
+        const uint32_t prefix = s_prefix, k_rem = s_krem;
+        const uint32_t shift = shifts[p], hi_shift = shift + nbits[p], dmask = (1u << nbits[p]) - 1u;
+        for (uint32_t i = t; i < n; i += 1024u) {
+            const uint32_t key = key_of_bits(keys[i]);
+            if (hi_shift >= 31u || (key >> hi_shift) == (prefix >> hi_shift)) atomicAdd(&sh[(key >> shift) & dmask], 1u);
+        }
+        __syncthreads();
+        // the pick of k_topk_pick: thread t owns bins TK_BINS-1-2t and the one below, suffix sums from the top bin
+        const uint32_t b0 = TK_BINS - 1 - 2 * t, b1 = b0 - 1;
+        const uint32_t c0 = sh[b0], c1 = sh[b1];
+        uint32_t incl = c0 + c1;
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_tot[lane];
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, w, d); if (lane >= (uint32_t)d) w += o; }
+            warp_tot[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t before = (warp ? warp_tot[warp - 1] : 0u) + incl - (c0 + c1);
+        const bool in0 = before < k_rem && k_rem <= before + c0;
+        const bool in1 = before + c0 < k_rem && k_rem <= before + c0 + c1;
+        if (in0) { s_prefix = prefix | (b0 << shift); s_krem = k_rem - before; s_ceq = c0; }
+        else if (in1) { s_prefix = prefix | (b1 << shift); s_krem = k_rem - before - c0; s_ceq = c1; }
+        __syncthreads();
+    }
+    if (t == 0) { TopkState v; v.prefix = s_prefix; v.k_rem = s_krem; v.c_eq = s_ceq; v.pad = 0u; st_all[blockIdx.x] = v; }
 }
 
 // Sixteen keys of a tile per thread, four rows of one 16-byte quad each: row r, thread t holds elements
@@ -843,9 +951,9 @@ __device__ __forceinline__ void topk_hist_run(uint32_t* sh, uint32_t bid, const 
             }
             ++s;
         }
-        const TopkView vw = topk_view<CAND>(segs[s], cand_count, s);
+        const TopkView vw = topk_view<CAND, true>(segs[s], cand_count, s);
         const uint64_t base = (tile - vw.tile0) * TK_TILE;
-        if (base >= vw.n) {                                // other route, or past the candidates that exist:
+        if (base >= vw.n) {                                // other route (or a small layer), or past the candidates that exist:
             if (s + 1 >= nseg) break;                      // on to the next layer's first tile
             const uint64_t nxt = topk_first<CAND ? 1 : 0>(segs[s + 1]);
             tile = (nxt > tile ? nxt : tile + 1) - 1;
@@ -1302,6 +1410,7 @@ int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_
     // Layers are processed in groups of at most TK_GROUP by the same launches (the per-layer
     // histograms of a group are 8 KB each).  Empty layers are dropped from the table.
     const int TK_GROUP = 4096;
+    static const bool small_on = [] { const char* ev = getenv("FLASHE_TOPK_SMALL"); return !(ev && ev[0] == '0'); }();   // (A/B switch)
     std::vector<TopkSeg> segs;
     segs.reserve((size_t)(nseg < TK_GROUP ? nseg : TK_GROUP));
     uint8_t* ws = nullptr;
@@ -1313,6 +1422,7 @@ int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_
     while (e == cudaSuccess && s < nseg) {
         segs.clear();
         uint64_t ntiles = 0, nctiles = 0, nlines = 0;
+        int n_small = 0;
         for (; s < nseg && (int)segs.size() < TK_GROUP; ++s) {
             const uint64_t n = seg_end[s] - begin;
             if (n) {
@@ -1341,6 +1451,9 @@ int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_
                         nlines += lines;
                     }
                 }
+                // small: the radix passes of the layer fit one block (candidate lists of up to TK_SMALL_N / 8 keys, or a short x)
+                g.small = (small_on && ((g.cap != 0u && n <= TK_SMALL_N) || n <= TK_SMALL_EXACT)) ? 1u : 0u;
+                if (g.small) ++n_small;
                 segs.push_back(g);
                 ntiles += ceil_div_u64(n, TK_TILE);
             }
@@ -1377,10 +1490,13 @@ int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_
         const uint64_t ctpb = nctiles ? ceil_div_u64(nctiles, (uint64_t)gc) : 0;
         uint32_t* null_lo = nullptr;
 #define TK_GO(call) do { if (e == cudaSuccess) { e = (call); ++launches; } } while (0)
-        TK_GO(topk_launch(k_topk_init, (ng + 255) / 256, 256, cs, dseg, ng, st));
+        if (n_small != ng) TK_GO(topk_launch(k_topk_init, (ng + 255) / 256, 256, cs, dseg, ng, st));   // (k_topk_select_small writes the whole state of a small layer)
         if (nctiles) {
-            TK_GO(topk_launch(k_topk_sample, grid_cap(info.num_sms, ceil_div_u64(nlines, 8), 8), 256, cs, xw, dseg, ng, nlines, hist));
-            TK_GO(topk_launch(k_topk_pick, ng, 1024, cs, hist, st, 0u, dseg, lo));
+            if (small_on && ng >= 8) TK_GO(topk_launch(k_topk_bound, ng, 1024, cs, xw, dseg, lo));   // (a lone block is slower than 64 sampling blocks + the pick: 50 M single layer 0.197 -> 0.202 ms)
+            else {
+                TK_GO(topk_launch(k_topk_sample, grid_cap(info.num_sms, ceil_div_u64(nlines, 8), 8), 256, cs, xw, dseg, ng, nlines, hist));
+                TK_GO(topk_launch(k_topk_pick, ng, 1024, cs, hist, st, 0u, dseg, lo));
+            }
             const size_t f_smem = (size_t)TKF_STAGES * TK_TILE * 4u;
             { static bool attr_done = false; if (!attr_done && e == cudaSuccess) { e = cudaFuncSetAttribute(k_topk_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f_smem); attr_done = true; } }
             const int gf = grid_occ(info.num_sms, info.device, (const void*)k_topk_filter, ntiles * TK_THREADS, TK_THREADS, f_smem);   // exactly the resident CTAs: equal runs, one wave
@@ -1388,7 +1504,8 @@ int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_
         }
         const uint32_t shifts[3] = {20u, 9u, 0u}, nbits[3] = {11u, 11u, 9u};
         const uint32_t gcu = nctiles ? (uint32_t)gc : 0u;
-        for (int p = 0; p < 3; ++p) {
+        if (n_small > 0) TK_GO(topk_launch(k_topk_select_small, ng, 1024, cs, xw, cand_key, dseg, cand_count, st));
+        for (int p = 0; p < 3 && n_small != ng; ++p) {         // the multi-block passes serve the layers that are not small
             TK_GO(topk_launch(k_topk_hist, (int)gcu + gh, TK_THREADS, cs, xw, cand_key, dseg, ng, gcu, nctiles, ctpb, ntiles, tpb, st, cand_count, shifts[p], nbits[p], hist));
             TK_GO(topk_launch(k_topk_pick, ng, 1024, cs, hist, st, shifts[p], dseg, null_lo));
         }

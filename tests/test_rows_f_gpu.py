@@ -185,6 +185,31 @@ def test_sparsify_ties_zeros_and_specials(fb):
         assert np.array_equal(_np(rem).view(np.uint32), want_r[0].view(np.uint32)), k
 
 
+def test_sparsify_small_and_large_layers_in_one_call(fb):
+    # Layers whose radix passes run inside one block (k_topk_select_small: up to 4 M elements on the candidate route, 64 K on
+    # the exact route) next to layers that take the multi-block passes (6 M and 5 M elements; 100 k at sparsity 0.5 = exact
+    # route above the one-block limit): both kinds in the same launches, more than 8 layers (the one-block sample bound).
+    rs = np.random.RandomState(31)
+    ctx = fb.DeviceContext(KEY, 32)
+    sizes = [6_000_000, 100_000, 3000, 5_000_001, 70_000, 9, 262_144, 40_000, 1_000_000]
+    sparsity = [0.01, 0.5, 0.01, 0.002, 0.3, 0.5, 0.01, 0.02, 0.004]
+    ends = np.cumsum(sizes)
+    layers = [(rs.standard_normal(s) * rs.uniform(0.01, 3.0)).astype(np.float32) for s in sizes]
+    ks = [O.sparsify_k(p, s) for p, s in zip(sparsity, sizes)]
+    vals, idx, rem = ctx.topk_sparsify(_dev(np.concatenate(layers)), ends, ks)
+    got_i, got_v, got_r = _np(idx), _np(vals), _np(rem)
+    o = 0
+    for li, (x, k) in enumerate(zip(layers, ks)):
+        order = np.argsort(np.abs(x), kind="stable")[-k:]                 # jzf_aggregator.py:600-606: stable argsort, last k
+        loc = np.sort(order)
+        base = int(ends[li] - sizes[li])
+        assert np.array_equal(got_i[o:o + k], loc + base), li
+        assert np.array_equal(got_v[o:o + k].view(np.uint32), x[loc].view(np.uint32)), li
+        r = x.copy(); r[loc] = 0.0
+        assert np.array_equal(got_r[base:base + sizes[li]].view(np.uint32), r.view(np.uint32)), li
+        o += k
+
+
 @pytest.mark.parametrize("route", ["exact", "badbound"])
 def test_sparsify_routes_agree(fb, route, monkeypatch):
     # The threshold is found either from a sampled candidate list (default for sparse selections) or from x itself.

@@ -683,8 +683,9 @@ k_topk_bound(const uint32_t* __restrict__ x, const TopkSeg* __restrict__ segs, u
 // (~80 us for 200 layers of 250 k, most of it launch and pick latency) on a few thousand candidates per layer.
 // Leaves the same TopkState as k_topk_hist + k_topk_pick x 3.
 __global__ void __launch_bounds__(1024)
-k_topk_select_small(const uint32_t* __restrict__ x, const uint32_t* __restrict__ cand_key, const TopkSeg* __restrict__ segs,
-                    const uint32_t* __restrict__ cand_count, TopkState* __restrict__ st_all) {
+k_topk_select_small(const uint32_t* __restrict__ x, const uint32_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_idx,
+                    const TopkSeg* __restrict__ segs, const uint32_t* __restrict__ cand_count, TopkState* __restrict__ st_all,
+                    uint2* __restrict__ tile_counts) {
     __shared__ uint32_t sh[TK_BINS];
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t s_prefix, s_krem, s_ceq;
@@ -730,6 +731,15 @@ k_topk_select_small(const uint32_t* __restrict__ x, const uint32_t* __restrict__
         __syncthreads();
     }
     if (t == 0) { TopkState v; v.prefix = s_prefix; v.k_rem = s_krem; v.c_eq = s_ceq; v.pad = 0u; st_all[blockIdx.x] = v; }
+    // ... and the per-tile counts of (key > T, key == T) that k_topk_count would make for this layer (tile_counts starts zeroed)
+    const uint32_t T = s_prefix;
+    for (uint32_t i = t; i < n; i += 1024u) {
+        const uint32_t key = key_of_bits(keys[i]);
+        if (key >= T) {
+            const uint32_t e = exact ? i : cand_idx[sg.cbegin + i];       // element index inside the layer
+            atomicAdd(reinterpret_cast<uint32_t*>(&tile_counts[sg.tile0 + e / TK_TILE]) + (key == T ? 1 : 0), 1u);
+        }
+    }
 }
 
 // Sixteen keys of a tile per thread, four rows of one 16-byte quad each: row r, thread t holds elements
@@ -1003,8 +1013,8 @@ __device__ __forceinline__ void topk_count_run(uint32_t bid, const uint32_t* __r
     int s = topk_seg_of<0>(segs, nseg, t_begin);
     for (uint64_t tile = t_begin; tile < t_end; ++tile) {
         while (s + 1 < nseg && segs[s + 1].tile0 <= tile) ++s;
-        const TopkView vw = topk_view<false>(segs[s], cand_count, s);
-        if (vw.n == 0u) {                                   // candidate route: k_topk_cand_count fills these tiles
+        const TopkView vw = topk_view<false, true>(segs[s], cand_count, s);
+        if (vw.n == 0u) {                                   // candidate route (k_topk_cand_count fills these tiles) or a small layer
             if (s + 1 >= nseg) break;
             const uint64_t nxt = segs[s + 1].tile0;
             tile = (nxt > tile ? nxt : tile + 1) - 1;
@@ -1045,7 +1055,7 @@ __device__ __forceinline__ void topk_cand_count_run(uint32_t bid, uint32_t nblk,
     if (slot >= slots) return;
     for (uint32_t s = slot; s < (uint32_t)nseg; s += slots) {
         const TopkSeg sg = segs[s];
-        const TopkView vw = topk_view<true>(sg, cand_count, (int)s);
+        const TopkView vw = topk_view<true, true>(sg, cand_count, (int)s);   // (small layers: counted by k_topk_select_small)
         if (vw.n == 0u) continue;
         const uint32_t T = st[s].prefix;
         for (uint32_t i = j * TK_THREADS + threadIdx.x; i < vw.n; i += P * TK_THREADS) {
@@ -1504,13 +1514,13 @@ int flashe_topk_sparsify(flashe_ctx* ctx, const float* x, const float* residual_
         }
         const uint32_t shifts[3] = {20u, 9u, 0u}, nbits[3] = {11u, 11u, 9u};
         const uint32_t gcu = nctiles ? (uint32_t)gc : 0u;
-        if (n_small > 0) TK_GO(topk_launch(k_topk_select_small, ng, 1024, cs, xw, cand_key, dseg, cand_count, st));
+        if (n_small > 0) TK_GO(topk_launch(k_topk_select_small, ng, 1024, cs, xw, cand_key, cand_idx, dseg, cand_count, st, tiles));
         for (int p = 0; p < 3 && n_small != ng; ++p) {         // the multi-block passes serve the layers that are not small
             TK_GO(topk_launch(k_topk_hist, (int)gcu + gh, TK_THREADS, cs, xw, cand_key, dseg, ng, gcu, nctiles, ctpb, ntiles, tpb, st, cand_count, shifts[p], nbits[p], hist));
             TK_GO(topk_launch(k_topk_pick, ng, 1024, cs, hist, st, shifts[p], dseg, null_lo));
         }
         const uint32_t gcc = nctiles ? (uint32_t)grid_cap(info.num_sms, 4 * nctiles, 8) : 0u;
-        TK_GO(topk_launch(k_topk_count, (int)gcc + gh, TK_THREADS, cs, xw, cand_key, cand_idx, dseg, ng, gcc, nctiles, ntiles, tpb, st, cand_count, tiles));
+        if (n_small != ng) TK_GO(topk_launch(k_topk_count, (int)gcc + gh, TK_THREADS, cs, xw, cand_key, cand_idx, dseg, ng, gcc, nctiles, ntiles, tpb, st, cand_count, tiles));
         const size_t w_smem = (size_t)TKW_STAGES * 2u * TK_TILE * 4u;
         { static bool attr_done = false; if (!attr_done && e == cudaSuccess) { e = cudaFuncSetAttribute(k_topk_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w_smem); attr_done = true; } }
         const int gw = grid_occ(info.num_sms, info.device, (const void*)k_topk_write, ntiles * TK_THREADS, TK_THREADS, w_smem);

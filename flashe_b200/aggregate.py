@@ -68,7 +68,7 @@ def aggregate_sparse(models, masks, total, int_bits, device=None):
         zeros.append(int(a[-1]))
         compacts.append(ctx.words_from_ints(a[:-1]))
         indexes.append(torch.as_tensor(np.asarray(ma, dtype=np.int64)).to(ctx.device))
-    return ctx.ints_from_words(ctx.sparse_sum(compacts, indexes, int(total), zeros))
+    return ctx.ints_from_words(ctx.sparse_sum(compacts, indexes, int(total), zeros, validate=True))   # (the masks come from the clients)
 
 
 def dynamic_masking(masks, total, device=None):

@@ -469,15 +469,26 @@ class DeviceContext(object):
         _cabi.check(self.lib.flashe_sparse_expand(self._h, compact.data_ptr(), index.data_ptr(), k, total, zb, out.data_ptr(), self._stream()))
         return out
 
-    def sparse_sum(self, compacts, indexes, total, zeros, out=None):
+    def _check_index_list(self, ix, total):
+        """The tiled sparse kernels rely on sorted unique index lists inside [0, total) (the reference sends
+        `sorted(locations)`, jzf_aggregator.py:605-618; its fancy indexing raises IndexError outside the range)."""
+        if ix.numel():
+            bad = bool((ix[0] < 0) | (ix[-1] >= total)) or (ix.numel() > 1 and not bool((ix[1:] > ix[:-1]).all()))
+            if bad:
+                raise IndexError("sparse index list must be sorted, unique and inside [0, %d)" % total)
+
+    def sparse_sum(self, compacts, indexes, total, zeros, out=None, validate=False):
         """Sum over clients of expand_to_dense(compact_c, index_c, zero_c) mod 2^b without the n dense
-        vectors (fill with the sum of the zero words, one scatter-add per client)."""
+        vectors: every tile of the result is built in shared memory from the clients' runs of sorted indices
+        (flashe_sparse_sum).  validate=True checks the lists on the device first (lists from other parties)."""
         n = len(compacts)
         if n < 1 or len(indexes) != n or len(zeros) != n:
             raise ValueError("compacts, indexes and zeros must have the same non-zero length")
         for a, ix in zip(compacts, indexes):
             self._check(ix, torch.int64, ix.numel(), "index")
             self._check_words(a, ix.numel(), "compact")
+            if validate:
+                self._check_index_list(ix, total)
         out = self.empty_words(total) if out is None else self._check_words(out, total, "out")
         cp = (C.c_void_p * n)(*[t.data_ptr() for t in compacts])
         ip = (C.c_void_p * n)(*[t.data_ptr() for t in indexes])

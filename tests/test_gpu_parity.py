@@ -516,6 +516,10 @@ def test_sparse_apply_masks_batch_equals_per_client_calls(fb, bits):
     assert sum(int(v) for v in zi) == sum(int(v) for v in m)
     with pytest.raises(IndexError):
         ctx.sparse_apply_masks_batch(it, [1], 1, n_jobs, [_dev(np.array([5, 4], dtype=np.int64))], ctx.zeros_words(total))
+    with pytest.raises(IndexError):                                        # unsorted list from a client: refused before the tiled sum
+        ctx.sparse_sum([ctx.zeros_words(2)], [_dev(np.array([5, 4], dtype=np.int64))], total, [0], validate=True)
+    with pytest.raises(IndexError):
+        ctx.sparse_sum([ctx.zeros_words(1)], [_dev(np.array([total], dtype=np.int64))], total, [0], validate=True)
 
 
 @pytest.mark.parametrize("n,total,kmax", [(70, 40_001, 900), (300, 20_003, 120), (32, 5_000, 5_000), (3, 100_000, 60_000)])

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FLASHE_ABI_VERSION 2
+#define FLASHE_ABI_VERSION 2   /* (entry points added since 2 without changing an existing one: flashe_sparse_apply_masks_batch) */
 
 enum {
     FLASHE_OK = 0,
